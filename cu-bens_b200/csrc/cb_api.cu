@@ -1,0 +1,942 @@
+// cb_api.cu - the C-ABI of include/cubens_b200.h: handle, uploads, the sorted
+// element-to-nonzero maps, generation bookkeeping and host<->device transfers.
+//
+// Maps built once per model (host side, then resident in HBM):
+//   node -> corner CSR    every (element, local node) touching a joint, sorted by
+//                         (element type, element) = the order the reference adds contributions
+//   node-pair blocks      for every joint B and every joint A sharing an element with it: the
+//                         list of (element, a, b) sub-blocks that sum into the block (rows of A,
+//                         columns of B) of the global matrix, again in reference order
+//   CSC pattern           columns of joint B are contiguous and all of the same height
+//                         colh[B] = sum of free DOFs of its neighbour joints, so
+//                         Ap[eq] = base[B] + cc*colh[B]; row indices are the neighbours' equation
+//                         ranges in ascending order (codes() numbers equations joint by joint,
+//                         model.c:944-960, which is what makes the block pattern valid)
+#include "../../include/cubens_b200.h"
+#include "cb_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(CB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count)
+    {
+        n = count;
+        if (count == 0) { p = nullptr; return 0; }
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            fail(CB_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T),
+                 cudaGetErrorString(e));
+            p = nullptr;
+            return 1;
+        }
+        return 0;
+    }
+    int upload(const std::vector<T> &v)
+    {
+        if (alloc(v.size())) return 1;
+        if (v.empty()) return 0;
+        return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct Plan {
+    DevBuf<CbPair> pairs;
+    long npairs = 0;
+};
+
+struct cb_handle {
+    cb_sizes sz{};
+    cb_flags fl{};
+    long NE_BR = 0;
+    int layout = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    long launches = 0;
+    double last_stiff_ms = 0, last_forces_ms = 0;
+    long j0 = 0, j1 = 0;          // owned joints
+    bool plan_ready = false;
+    bool keb_dirty = true;
+
+    // host copies needed after create
+    std::vector<int32_t> h_jc;    // [NJ][8]
+    std::vector<long> h_maxa;
+    std::vector<int32_t> h_nodes[4];
+    std::vector<int32_t> h_first; // first equation (1-based) of each joint, 0 if none
+    std::vector<uint8_t> h_mask;
+    std::vector<int32_t> h_nfree;
+    // CSC pattern pieces (host)
+    std::vector<int32_t> adj_start, adj;      // joint adjacency CSR (sorted, incl. self)
+    std::vector<int64_t> base;                // first Ax index of joint B's columns
+    std::vector<int32_t> colh;
+    long nnz = 0, lss = 0;
+
+    // device: nodes and vectors
+    DevBuf<int32_t> jc;
+    DevBuf<double> x, x_temp, x_ip;
+    DevBuf<double> dd, f_temp, f, d, d_temp, sm;
+    // shells
+    DevBuf<int32_t> sh_nodes;
+    DevBuf<double> sh_const, sh_keb, sh_Nm, sh_fg, sh_dens;
+    DevBuf<double> sh_frame[3], sh_dsl[3], sh_ef[3];   // 0 = committed, 1/2 = iterate ping-pong
+    // trusses
+    DevBuf<int32_t> tr_nodes;
+    DevBuf<double> tr_const, tr_fg, tr_dens;
+    DevBuf<double> tr_frame[3], tr_ef[3];
+    // frames
+    DevBuf<int32_t> fr_nodes, fr_osflag, fr_mendrel;
+    DevBuf<double> fr_const, fr_offset, fr_efFE_ref, fr_fg, fr_dens;
+    DevBuf<double> fr_frame[3], fr_xfr[3], fr_efFE[3], fr_ef[3];
+    // bricks
+    DevBuf<int32_t> br_nodes;
+    DevBuf<double> br_const;
+    // generation roles: index into the [3] arrays
+    int gP = 1, gN = 2;          // frame-like state: _ip buffer, _i buffer
+    bool i_is_ip = true;         // *_i currently aliases *_ip (after begin_increment/end_iteration)
+    int eP = 1, eN = 2;          // element end forces: newest, scratch
+    // maps
+    DevBuf<int32_t> node_cstart;
+    DevBuf<CbCorner> corners;
+    DevBuf<CbContrib> contribs;
+    Plan plan_csc, plan_sky;
+    DevBuf<int> Ap, Ai;
+    DevBuf<long> maxa;
+    DevBuf<double> Ax, ss;
+    long map_bytes = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+extern "C" int cb_abi_version(void) { return CB_ABI_VERSION; }
+extern "C" const char *cb_last_error(void) { return g_err; }
+extern "C" int cb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static CbDev make_dev(cb_handle *h)
+{
+    CbDev d{};
+    d.NJ = h->sz.NJ; d.NEQ = h->sz.NEQ;
+    d.NE_TR = h->sz.NE_TR; d.NE_FR = h->sz.NE_FR; d.NE_SH = h->sz.NE_SH; d.NE_BR = h->NE_BR;
+    d.ANAFLAG = h->fl.ANAFLAG;
+    d.jc = h->jc.p;
+    d.sh_nodes = h->sh_nodes.p; d.sh_const = h->sh_const.p; d.sh_keb = h->sh_keb.p;
+    d.sh_Nm = h->sh_Nm.p; d.sh_fg = h->sh_fg.p;
+    d.fr_nodes = h->fr_nodes.p; d.fr_const = h->fr_const.p; d.fr_offset = h->fr_offset.p;
+    d.fr_osflag = h->fr_osflag.p; d.fr_mendrel = h->fr_mendrel.p;
+    d.fr_efFE_ref = h->fr_efFE_ref.p; d.fr_fg = h->fr_fg.p;
+    d.tr_nodes = h->tr_nodes.p; d.tr_const = h->tr_const.p; d.tr_fg = h->tr_fg.p;
+    d.br_nodes = h->br_nodes.p; d.br_const = h->br_const.p;
+    return d;
+}
+
+static int d2d(double *dst, const double *src, size_t n, cudaStream_t s)
+{
+    if (n == 0) return 0;
+    return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, s) != cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------------
+// cb_create
+// ------------------------------------------------------------------------------------------
+extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model *m,
+                         cb_handle **out)
+{
+    if (!sz || !fl || !m || !out) return fail(CB_ERR_ARG, "cb_create: null argument");
+    *out = nullptr;
+    if (fl->ANAFLAG != 1 && fl->ANAFLAG != 2)
+        return fail(CB_ERR_UNSUPPORTED, "ANAFLAG=%d: only 1 (elastic) and 2 (geometric "
+                    "nonlinear) are built; 3 (plasticity) / 4 (FSI) are listed in DESIGN.md",
+                    fl->ANAFLAG);
+    if (sz->NE_FBR != 0) return fail(CB_ERR_UNSUPPORTED, "fluid bricks (FSI) are out of scope");
+    if (sz->NJ <= 0 || sz->NEQ <= 0) return fail(CB_ERR_ARG, "NJ and NEQ must be positive");
+    if (sz->NJ > 0x7fffffffL / 8 || sz->NEQ > 0x7ffffff0L)
+        return fail(CB_ERR_OVERFLOW, "NJ / NEQ exceed 32-bit device indices");
+    int ndev = cb_device_count();
+    if (ndev <= 0) return fail(CB_ERR_CUDA, "no CUDA device available (no CPU fallback exists)");
+    if (fl->device < 0 || fl->device >= ndev) return fail(CB_ERR_ARG, "bad device ordinal");
+    CUDA_TRY(cudaSetDevice(fl->device));
+
+    cb_handle *h = new cb_handle();
+    h->sz = *sz; h->fl = *fl;
+    h->NE_BR = sz->NE_SBR + sz->NE_FBR;
+    h->layout = fl->matrix_layout ? fl->matrix_layout
+                                  : (fl->SLVFLAG == 0 ? CB_MAT_SKYLINE : CB_MAT_CSC);
+    h->j0 = 0; h->j1 = sz->NJ;
+    const long NJ = sz->NJ, TR = sz->NE_TR, FR = sz->NE_FR, SH = sz->NE_SH, BR = h->NE_BR;
+    if ((h->layout & CB_MAT_SKYLINE) && !m->maxa) {
+        delete h; return fail(CB_ERR_ARG, "skyline layout needs maxa");
+    }
+    if (BR && (h->layout & CB_MAT_SKYLINE)) {
+        delete h;
+        return fail(CB_ERR_UNSUPPORTED, "bricks scatter to the dense layout only in the "
+                    "reference (brick.c:383-395, skylin ignores them): use CB_MAT_CSC");
+    }
+    if (FR) { delete h; return fail(CB_ERR_UNSUPPORTED, "frame elements: not built yet"); }
+    if (BR) { delete h; return fail(CB_ERR_UNSUPPORTED, "brick elements: not built yet"); }
+
+#define BAIL(code) do { int c_ = (code); cb_destroy(h); return c_; } while (0)
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)
+        BAIL(fail(CB_ERR_CUDA, "stream/event creation failed"));
+
+    // ---- joints ---------------------------------------------------------------------------
+    h->h_jc.assign((size_t)NJ * 8, 0);
+    h->h_first.assign(NJ, 0); h->h_mask.assign(NJ, 0); h->h_nfree.assign(NJ, 0);
+    for (long j = 0; j < NJ; ++j) {
+        long prev = 0; int nf = 0; unsigned mask = 0;
+        for (int r = 0; r < 7; ++r) {
+            long q = m->jcode[j * 7 + r];
+            if (q < 0 || q > sz->NEQ) BAIL(fail(CB_ERR_ARG, "jcode[%ld][%d]=%ld out of range", j, r, q));
+            h->h_jc[j * 8 + r] = (int32_t)q;
+            if (q) {
+                if (nf == 0) h->h_first[j] = (int32_t)q;
+                else if (q != prev + 1)
+                    BAIL(fail(CB_ERR_UNSUPPORTED, "joint %ld: equations are not numbered joint by "
+                              "joint (FSI pressure DOFs / released warping joints)", j + 1));
+                prev = q; ++nf; mask |= 1u << r;
+            }
+        }
+        h->h_mask[j] = (uint8_t)mask; h->h_nfree[j] = nf;
+    }
+    std::vector<double> hx(m->x, m->x + (size_t)NJ * 3);
+    if (h->jc.upload(h->h_jc) || h->x.upload(hx) || h->x_temp.upload(hx) || h->x_ip.upload(hx))
+        BAIL(CB_ERR_CUDA);
+    for (DevBuf<double> *b : {&h->dd, &h->f_temp, &h->f, &h->d, &h->d_temp, &h->sm}) {
+        if (b->alloc(sz->NEQ)) BAIL(CB_ERR_CUDA);
+        cudaMemset(b->p, 0, sz->NEQ * sizeof(double));
+    }
+    if (h->layout & CB_MAT_SKYLINE) {
+        h->h_maxa.assign(m->maxa, m->maxa + sz->NEQ + 1);
+        h->lss = h->h_maxa[sz->NEQ] - 1;
+        if (h->maxa.upload(h->h_maxa)) BAIL(CB_ERR_CUDA);
+    }
+
+    // ---- element incidences (0-based int32) + consistency of mcode with jcode --------------
+    const long *minc = m->minc;
+    auto take_nodes = [&](int type, long ne, int nn, int pad, long moff) -> int {
+        std::vector<int32_t> &v = h->h_nodes[type];
+        v.assign((size_t)ne * pad, 0);
+        for (long e = 0; e < ne; ++e)
+            for (int a = 0; a < nn; ++a) {
+                long j = minc[moff + e * nn + a];
+                if (j < 1 || j > NJ) return fail(CB_ERR_ARG, "minc joint %ld out of range", j);
+                v[e * pad + a] = (int32_t)(j - 1);
+            }
+        return 0;
+    };
+    if (take_nodes(CB_T_TRUSS, TR, 2, 2, 0)) BAIL(CB_ERR_ARG);
+    if (take_nodes(CB_T_FRAME, FR, 2, 2, 2 * TR)) BAIL(CB_ERR_ARG);
+    if (take_nodes(CB_T_SHELL, SH, 3, 4, 2 * TR + 2 * FR)) BAIL(CB_ERR_ARG);
+    if (take_nodes(CB_T_BRICK, BR, 8, 8, 2 * TR + 2 * FR + 3 * SH)) BAIL(CB_ERR_ARG);
+    if (m->mcode) {
+        const long *mc = m->mcode;
+        for (long e = 0; e < TR; ++e)
+            for (int a = 0; a < 2; ++a)
+                for (int r = 0; r < 3; ++r)
+                    if (mc[e * 6 + a * 3 + r] != m->jcode[(long)h->h_nodes[0][e * 2 + a] * 7 + r])
+                        BAIL(fail(CB_ERR_ARG, "mcode of truss %ld disagrees with jcode", e + 1));
+        const long o = 6 * TR + 14 * FR;
+        for (long e = 0; e < SH; ++e)
+            for (int a = 0; a < 3; ++a)
+                for (int r = 0; r < 6; ++r)
+                    if (mc[o + e * 18 + a * 6 + r] != m->jcode[(long)h->h_nodes[2][e * 4 + a] * 7 + r])
+                        BAIL(fail(CB_ERR_ARG, "mcode of shell %ld disagrees with jcode", e + 1));
+    }
+    if (h->tr_nodes.upload(h->h_nodes[0]) || h->fr_nodes.upload(h->h_nodes[1]) ||
+        h->sh_nodes.upload(h->h_nodes[2]) || h->br_nodes.upload(h->h_nodes[3]))
+        BAIL(CB_ERR_CUDA);
+
+    // ---- trusses ---------------------------------------------------------------------------
+    if (TR) {
+        std::vector<double> c((size_t)TR * CB_TR_CONST), fr((size_t)TR * CB_TR_FRAME),
+            dn(m->dens ? m->dens : m->emod, (m->dens ? m->dens : m->emod) + TR);
+        for (long e = 0; e < TR; ++e) {
+            c[e * 4 + 0] = m->emod[e]; c[e * 4 + 1] = m->carea[e]; c[e * 4 + 2] = m->llength[e];
+            c[e * 4 + 3] = pow(m->llength[e], 3);       // libm, as truss.c:109 evaluates it
+            fr[e * 4 + 0] = m->c1[e]; fr[e * 4 + 1] = m->c2[e]; fr[e * 4 + 2] = m->c3[e];
+            fr[e * 4 + 3] = m->llength[e];              // defllen = llength (main.c:1672-1676)
+        }
+        if (h->tr_const.upload(c) || h->tr_dens.upload(dn) || h->tr_fg.alloc((size_t)TR * 6))
+            BAIL(CB_ERR_CUDA);
+        for (int g = 0; g < 3; ++g) {
+            if (h->tr_frame[g].upload(fr) || h->tr_ef[g].alloc((size_t)TR * 2)) BAIL(CB_ERR_CUDA);
+            cudaMemset(h->tr_ef[g].p, 0, (size_t)TR * 2 * sizeof(double));
+        }
+    }
+    // ---- shells ----------------------------------------------------------------------------
+    if (SH) {
+        const long pe = TR + FR, pc = TR + 3 * FR;
+        std::vector<double> c((size_t)SH * CB_SH_CONST, 0.0), fr((size_t)SH * CB_SH_FRAME),
+            dsl(m->slength, m->slength + (size_t)SH * 3), dn((size_t)SH, 0.0);
+        for (long e = 0; e < SH; ++e) {
+            double *q = &c[e * CB_SH_CONST];
+            q[0] = m->emod[pe + e]; q[1] = m->nu[e]; q[2] = m->thick[e];
+            q[3] = pow(m->thick[e], 3);                 // libm, as shell.c:545 evaluates it
+            q[4] = m->farea[e];
+            q[5] = m->xlocal[e * 3]; q[6] = m->xlocal[e * 3 + 1]; q[7] = m->xlocal[e * 3 + 2];
+            q[8] = m->slength[e * 3]; q[9] = m->slength[e * 3 + 1]; q[10] = m->slength[e * 3 + 2];
+            double *f = &fr[e * CB_SH_FRAME];
+            for (int k = 0; k < 3; ++k) {
+                f[k] = m->c1[pc + e * 3 + k]; f[3 + k] = m->c2[pc + e * 3 + k];
+                f[6 + k] = m->c3[pc + e * 3 + k];
+            }
+            f[9] = m->farea[e];                          // deffarea = farea (main.c:1700)
+            if (m->dens) dn[e] = m->dens[e];             // pdens+i, shell.c:61 / 1551
+        }
+        if (h->sh_const.upload(c) || h->sh_dens.upload(dn) || h->sh_keb.alloc((size_t)SH * 81) ||
+            h->sh_Nm.alloc((size_t)SH * 4) || h->sh_fg.alloc((size_t)SH * 18))
+            BAIL(CB_ERR_CUDA);
+        for (int g = 0; g < 3; ++g) {
+            if (h->sh_frame[g].upload(fr) || h->sh_dsl[g].upload(dsl) ||
+                h->sh_ef[g].alloc((size_t)SH * 18))
+                BAIL(CB_ERR_CUDA);
+            cudaMemset(h->sh_ef[g].p, 0, (size_t)SH * 18 * sizeof(double));
+        }
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    *out = h;
+    return CB_OK;
+#undef BAIL
+}
+
+extern "C" void cb_destroy(cb_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->fl.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (DevBuf<double> *b : {&h->x, &h->x_temp, &h->x_ip, &h->dd, &h->f_temp, &h->f, &h->d,
+                              &h->d_temp, &h->sm, &h->sh_const, &h->sh_keb, &h->sh_Nm, &h->sh_fg,
+                              &h->sh_dens, &h->tr_const, &h->tr_fg, &h->tr_dens, &h->fr_const,
+                              &h->fr_offset, &h->fr_efFE_ref, &h->fr_fg, &h->fr_dens, &h->br_const,
+                              &h->Ax, &h->ss})
+        b->release();
+    for (int g = 0; g < 3; ++g) {
+        h->sh_frame[g].release(); h->sh_dsl[g].release(); h->sh_ef[g].release();
+        h->tr_frame[g].release(); h->tr_ef[g].release();
+        h->fr_frame[g].release(); h->fr_xfr[g].release(); h->fr_efFE[g].release();
+        h->fr_ef[g].release();
+    }
+    for (DevBuf<int32_t> *b : {&h->jc, &h->sh_nodes, &h->tr_nodes, &h->fr_nodes, &h->fr_osflag,
+                               &h->fr_mendrel, &h->br_nodes, &h->node_cstart})
+        b->release();
+    h->corners.release(); h->contribs.release(); h->plan_csc.pairs.release();
+    h->plan_sky.pairs.release(); h->Ap.release(); h->Ai.release(); h->maxa.release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int cb_set_owned_joints(cb_handle *h, long j0, long j1)
+{
+    if (!h) return fail(CB_ERR_ARG, "null handle");
+    if (h->plan_ready) return fail(CB_ERR_ARG, "cb_set_owned_joints must precede the first assembly");
+    if (j0 < 0 || j1 > h->sz.NJ || j0 > j1) return fail(CB_ERR_ARG, "bad joint range");
+    h->j0 = j0; h->j1 = j1;
+    return CB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the sorted element-to-nonzero maps
+// ------------------------------------------------------------------------------------------
+static int build_plan(cb_handle *h)
+{
+    if (h->plan_ready) return CB_OK;
+    const long NJ = h->sz.NJ;
+    const long ne[4] = {h->sz.NE_TR, h->sz.NE_FR, h->sz.NE_SH, h->NE_BR};
+    const int nn[4] = {2, 2, 3, 8}, pad[4] = {2, 2, 4, 8};
+    // node -> corner CSR, filled in (type, element, local node) order
+    std::vector<int32_t> cstart(NJ + 1, 0);
+    long ncorner = 0;
+    for (int t = 0; t < 4; ++t)
+        for (long e = 0; e < ne[t]; ++e)
+            for (int a = 0; a < nn[t]; ++a) { ++cstart[h->h_nodes[t][e * pad[t] + a] + 1]; ++ncorner; }
+    if (ncorner > 0x7fffffffL) return fail(CB_ERR_OVERFLOW, "too many element corners");
+    for (long j = 0; j < NJ; ++j) cstart[j + 1] += cstart[j];
+    std::vector<CbCorner> corners(ncorner);
+    {
+        std::vector<int32_t> fill(cstart.begin(), cstart.end() - 1);
+        for (int t = 0; t < 4; ++t)
+            for (long e = 0; e < ne[t]; ++e)
+                for (int a = 0; a < nn[t]; ++a) {
+                    int32_t j = h->h_nodes[t][e * pad[t] + a];
+                    CbCorner c{}; c.e = (int32_t)e; c.type = (uint8_t)t; c.b = (uint8_t)a;
+                    corners[fill[j]++] = c;
+                }
+    }
+    // joint adjacency (sorted unique, includes the joint itself when it has elements)
+    h->adj_start.assign(NJ + 1, 0);
+    h->adj.clear();
+    h->adj.reserve((size_t)ncorner * 3);
+    std::vector<int32_t> tmp;
+    for (long j = 0; j < NJ; ++j) {
+        tmp.clear();
+        for (int c = cstart[j]; c < cstart[j + 1]; ++c) {
+            const CbCorner &cr = corners[c];
+            const int32_t *nd = &h->h_nodes[cr.type][(long)cr.e * pad[cr.type]];
+            for (int a = 0; a < nn[cr.type]; ++a) tmp.push_back(nd[a]);
+        }
+        std::sort(tmp.begin(), tmp.end());
+        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        h->adj.insert(h->adj.end(), tmp.begin(), tmp.end());
+        h->adj_start[j + 1] = (int32_t)h->adj.size();
+    }
+    // CSC geometry
+    h->base.assign(NJ + 1, 0); h->colh.assign(NJ, 0);
+    std::vector<int32_t> rowoff(h->adj.size(), 0);
+    long nnz = 0;
+    for (long j = 0; j < NJ; ++j) {
+        int hgt = 0;
+        for (int k = h->adj_start[j]; k < h->adj_start[j + 1]; ++k) {
+            rowoff[k] = hgt; hgt += h->h_nfree[h->adj[k]];
+        }
+        if (h->h_nfree[j] && hgt == 0) hgt = 0;
+        h->colh[j] = hgt; h->base[j] = nnz;
+        nnz += (long)h->h_nfree[j] * hgt;
+    }
+    h->base[NJ] = nnz;
+    if ((h->layout & CB_MAT_CSC) && nnz > 0x7fffffffL)
+        return fail(CB_ERR_OVERFLOW, "nnz=%ld exceeds the 32-bit CSC indices umfpack_di_* takes", nnz);
+    h->nnz = nnz;
+
+    // node-pair blocks and their contribution lists
+    std::vector<CbPair> pairs_csc, pairs_sky;
+    std::vector<CbContrib> contribs;
+    contribs.reserve((size_t)ncorner * 3);
+    for (long B = h->j0; B < h->j1; ++B) {
+        if (!h->h_nfree[B]) continue;
+        for (int k = h->adj_start[B]; k < h->adj_start[B + 1]; ++k) {
+            const int32_t A = h->adj[k];
+            if (!h->h_nfree[A]) continue;
+            CbPair p{};
+            p.cstart = (int32_t)contribs.size();
+            for (int c = cstart[B]; c < cstart[B + 1]; ++c) {
+                const CbCorner &cr = corners[c];
+                const int32_t *nd = &h->h_nodes[cr.type][(long)cr.e * pad[cr.type]];
+                for (int a = 0; a < nn[cr.type]; ++a)
+                    if (nd[a] == A) {
+                        CbContrib ct{}; ct.e = cr.e; ct.type = cr.type; ct.a = (uint8_t)a; ct.b = cr.b;
+                        contribs.push_back(ct);
+                    }
+            }
+            long cnt = (long)contribs.size() - p.cstart;
+            if (cnt > 65535) return fail(CB_ERR_OVERFLOW, "joint valence too large");
+            p.ccount = (uint16_t)cnt;
+            p.colh = h->colh[B];
+            p.off = (int32_t)(h->base[B] + rowoff[k]);
+            p.eqA0 = h->h_first[A]; p.eqB0 = h->h_first[B];
+            p.maskA = h->h_mask[A]; p.maskB = h->h_mask[B];
+            if (h->layout & CB_MAT_CSC) pairs_csc.push_back(p);
+            if ((h->layout & CB_MAT_SKYLINE) && A <= B) pairs_sky.push_back(p);
+        }
+    }
+    if (contribs.size() > 0x7fffffffUL) return fail(CB_ERR_OVERFLOW, "too many contributions");
+    // bucket the blocks by contribution count (descending, stable) so a warp's threads loop alike
+    auto bucket = [](std::vector<CbPair> &v) {
+        std::stable_sort(v.begin(), v.end(),
+                         [](const CbPair &a, const CbPair &b) { return a.ccount > b.ccount; });
+    };
+    bucket(pairs_csc); bucket(pairs_sky);
+
+    if (h->node_cstart.upload(cstart) || h->corners.upload(corners) || h->contribs.upload(contribs))
+        return CB_ERR_CUDA;
+    if (h->layout & CB_MAT_CSC) {
+        if (h->plan_csc.pairs.upload(pairs_csc)) return CB_ERR_CUDA;
+        h->plan_csc.npairs = (long)pairs_csc.size();
+        if (h->Ax.alloc((size_t)nnz)) return CB_ERR_CUDA;
+        cudaMemset(h->Ax.p, 0, (size_t)nnz * sizeof(double));
+        std::vector<int> Ap(h->sz.NEQ + 1, 0);
+        for (long j = 0; j < NJ; ++j)
+            for (int cc = 0; cc < h->h_nfree[j]; ++cc)
+                Ap[h->h_first[j] - 1 + cc] = (int)(h->base[j] + (long)cc * h->colh[j]);
+        Ap[h->sz.NEQ] = (int)nnz;
+        if (h->Ap.upload(Ap)) return CB_ERR_CUDA;
+    }
+    if (h->layout & CB_MAT_SKYLINE) {
+        if (h->plan_sky.pairs.upload(pairs_sky)) return CB_ERR_CUDA;
+        h->plan_sky.npairs = (long)pairs_sky.size();
+        if (h->ss.alloc((size_t)h->lss)) return CB_ERR_CUDA;
+        cudaMemset(h->ss.p, 0, (size_t)h->lss * sizeof(double));
+    }
+    h->map_bytes = (long)((pairs_csc.size() + pairs_sky.size()) * sizeof(CbPair) +
+                          contribs.size() * sizeof(CbContrib));
+    h->plan_ready = true;
+    return CB_OK;
+}
+
+static int ensure_keb(cb_handle *h)
+{
+    if (!h->keb_dirty) return CB_OK;
+    CbDev d = make_dev(h);
+    if (cbk_shell_init_keb(d, h->sh_keb.p, h->stream)) return fail(CB_ERR_CUDA, "keb init launch");
+    if (h->sz.NE_SH) ++h->launches;
+    h->keb_dirty = false;
+    return CB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// generation bookkeeping
+// ------------------------------------------------------------------------------------------
+extern "C" int cb_begin_increment(cb_handle *h)
+{
+    if (!h) return fail(CB_ERR_ARG, "null handle");
+    cudaSetDevice(h->fl.device);
+    cudaStream_t s = h->stream;
+    const long TR = h->sz.NE_TR, SH = h->sz.NE_SH;
+    int bad = 0;
+    bad |= d2d(h->d_temp.p, h->d.p, h->sz.NEQ, s);
+    bad |= d2d(h->f_temp.p, h->f.p, h->sz.NEQ, s);
+    bad |= d2d(h->x_temp.p, h->x.p, (size_t)h->sz.NJ * 3, s);
+    for (int g = 1; g <= 2; ++g) {
+        bad |= d2d(h->sh_frame[g].p, h->sh_frame[0].p, (size_t)SH * CB_SH_FRAME, s);
+        bad |= d2d(h->sh_dsl[g].p, h->sh_dsl[0].p, (size_t)SH * 3, s);
+        bad |= d2d(h->tr_frame[g].p, h->tr_frame[0].p, (size_t)TR * CB_TR_FRAME, s);
+    }
+    bad |= d2d(h->sh_ef[h->eP].p, h->sh_ef[0].p, (size_t)SH * 18, s);
+    bad |= d2d(h->tr_ef[h->eP].p, h->tr_ef[0].p, (size_t)TR * 2, s);
+    h->i_is_ip = true;
+    if (bad) return fail(CB_ERR_CUDA, "cb_begin_increment: device copy failed");
+    return CB_OK;
+}
+
+extern "C" int cb_end_iteration(cb_handle *h)
+{
+    if (!h) return fail(CB_ERR_ARG, "null handle");
+    if (!h->i_is_ip) { std::swap(h->gP, h->gN); h->i_is_ip = true; }   // _ip <- _i by renaming
+    return CB_OK;
+}
+
+extern "C" int cb_commit(cb_handle *h)
+{
+    if (!h) return fail(CB_ERR_ARG, "null handle");
+    cudaSetDevice(h->fl.device);
+    cudaStream_t s = h->stream;
+    const long TR = h->sz.NE_TR, SH = h->sz.NE_SH;
+    const int gi = h->i_is_ip ? h->gP : h->gN;       // buffer holding the *_i generation
+    int bad = 0;
+    bad |= d2d(h->d.p, h->d_temp.p, h->sz.NEQ, s);
+    bad |= d2d(h->f.p, h->f_temp.p, h->sz.NEQ, s);
+    bad |= d2d(h->x.p, h->x_temp.p, (size_t)h->sz.NJ * 3, s);
+    bad |= d2d(h->sh_frame[0].p, h->sh_frame[gi].p, (size_t)SH * CB_SH_FRAME, s);
+    bad |= d2d(h->sh_dsl[0].p, h->sh_dsl[gi].p, (size_t)SH * 3, s);
+    bad |= d2d(h->tr_frame[0].p, h->tr_frame[gi].p, (size_t)TR * CB_TR_FRAME, s);
+    bad |= d2d(h->sh_ef[0].p, h->sh_ef[h->eP].p, (size_t)SH * 18, s);
+    bad |= d2d(h->tr_ef[0].p, h->tr_ef[h->eP].p, (size_t)TR * 2, s);
+    if (bad) return fail(CB_ERR_CUDA, "cb_commit: device copy failed");
+    return CB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// hot path
+// ------------------------------------------------------------------------------------------
+extern "C" int cb_stiff(cb_handle *h, int gen)
+{
+    if (!h) return fail(CB_ERR_ARG, "null handle");
+    cudaSetDevice(h->fl.device);
+    int rc = build_plan(h); if (rc) return rc;
+    rc = ensure_keb(h); if (rc) return rc;
+    CbStiffArgs a{};
+    a.d = make_dev(h);
+    const int g = (gen == CB_GEN_COMMITTED) ? 0 : h->gP;
+    const int ge = (gen == CB_GEN_COMMITTED) ? 0 : h->eP;
+    a.x = (gen == CB_GEN_COMMITTED) ? h->x.p : h->x_temp.p;
+    a.sh_frame = h->sh_frame[g].p; a.sh_ef = h->sh_ef[ge].p;
+    a.tr_frame = h->tr_frame[g].p; a.tr_ef = h->tr_ef[ge].p;
+    a.contribs = h->contribs.p;
+    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    if (h->fl.ANAFLAG == 2 && h->sz.NE_SH) {
+        if (cbk_shell_prep(a.d, a.x, a.sh_frame, h->stream)) return fail(CB_ERR_CUDA, "prep launch");
+        ++h->launches;
+    }
+    if (h->layout & CB_MAT_CSC) {
+        a.pairs = h->plan_csc.pairs.p; a.npairs = h->plan_csc.npairs;
+        a.out = h->Ax.p; a.skyline = 0; a.maxa = nullptr;
+        if (cbk_stiff(a, h->stream, &h->launches)) return fail(CB_ERR_CUDA, "assembly launch");
+    }
+    if (h->layout & CB_MAT_SKYLINE) {
+        a.pairs = h->plan_sky.pairs.p; a.npairs = h->plan_sky.npairs;
+        a.out = h->ss.p; a.skyline = 1; a.maxa = h->maxa.p;
+        if (cbk_stiff(a, h->stream, &h->launches)) return fail(CB_ERR_CUDA, "assembly launch");
+    }
+    CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->last_stiff_ms = ms;
+    return CB_OK;
+}
+
+__global__ void k_axpy1(long n, const double *__restrict__ x, double *__restrict__ y)
+{
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) y[i] += x[i];
+}
+
+static CbForceArgs force_args(cb_handle *h)
+{
+    CbForceArgs a{};
+    a.d = make_dev(h);
+    a.x_temp = h->x_temp.p; a.x_ip = h->x_ip.p; a.dd = h->dd.p;
+    a.sh_frame_ip = h->sh_frame[h->gP].p; a.sh_frame_i = h->sh_frame[h->gN].p;
+    a.sh_dsl_i = h->sh_dsl[h->gN].p;
+    a.sh_ef_ip = h->sh_ef[h->eP].p; a.sh_ef_i = h->sh_ef[h->eN].p;
+    a.tr_frame_i = h->tr_frame[h->gN].p; a.tr_ef_i = h->tr_ef[h->eN].p;
+    a.node_cstart = h->node_cstart.p; a.corners = h->corners.p; a.f_temp = h->f_temp.p;
+    return a;
+}
+
+extern "C" int cb_update_forces_dev(cb_handle *h, const double *dd_dev, double *dlpf_inout,
+                                    int itecnt, int *frcchk_fr, int *frcchk_sh)
+{
+    if (!h) return fail(CB_ERR_ARG, "null handle");
+    cudaSetDevice(h->fl.device);
+    int rc = build_plan(h); if (rc) return rc;
+    rc = ensure_keb(h); if (rc) return rc;
+    if (frcchk_fr) *frcchk_fr = 0;
+    if (frcchk_sh) *frcchk_sh = 0;
+    if (h->fl.ANAFLAG == 1)
+        return fail(CB_ERR_ARG, "ANAFLAG 1 recovers forces with cb_forces_linear (main.c:1774-1793)");
+    cudaStream_t s = h->stream;
+    // after end_iteration/begin_increment *_i aliases *_ip: the next iterate goes to the other buffer
+    if (h->i_is_ip) h->i_is_ip = false;
+    CbForceArgs a = force_args(h);
+    if (dd_dev && dd_dev != h->dd.p) { if (d2d(h->dd.p, dd_dev, h->sz.NEQ, s)) return fail(CB_ERR_CUDA, "dd copy"); }
+    a.dlpf = dlpf_inout ? *dlpf_inout : 0.0; a.itecnt = itecnt;
+    CUDA_TRY(cudaEventRecord(h->ev0, s));
+    {   // d_temp += dd (main.c:1949)
+        unsigned g = (unsigned)((h->sz.NEQ + 255) / 256);
+        k_axpy1<<<g, 256, 0, s>>>(h->sz.NEQ, h->dd.p, h->d_temp.p); ++h->launches;
+    }
+    if (cbk_node_update(a, s)) return fail(CB_ERR_CUDA, "node update launch");
+    ++h->launches;
+    if (cbk_forces(a, s, &h->launches)) return fail(CB_ERR_CUDA, "forces launch");
+    if (cbk_gather_f(a, s)) return fail(CB_ERR_CUDA, "gather launch");
+    ++h->launches;
+    CUDA_TRY(cudaEventRecord(h->ev1, s));
+    std::swap(h->eP, h->eN);                      // ef_ip <- ef_i (main.c:1982-1984) by renaming
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->last_forces_ms = ms;
+    return CB_OK;
+}
+
+extern "C" int cb_update_forces(cb_handle *h, const double *dd, double *dlpf_inout, int itecnt,
+                                double *f_temp_out, int *frcchk_fr, int *frcchk_sh)
+{
+    if (!h || !dd) return fail(CB_ERR_ARG, "null argument");
+    cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaMemcpyAsync(h->dd.p, dd, h->sz.NEQ * sizeof(double), cudaMemcpyHostToDevice,
+                             h->stream));
+    int rc = cb_update_forces_dev(h, h->dd.p, dlpf_inout, itecnt, frcchk_fr, frcchk_sh);
+    if (rc) return rc;
+    if (f_temp_out)
+        CUDA_TRY(cudaMemcpy(f_temp_out, h->f_temp.p, h->sz.NEQ * sizeof(double),
+                            cudaMemcpyDeviceToHost));
+    return CB_OK;
+}
+
+extern "C" int cb_forces_linear(cb_handle *h, const double *d, double *f_out)
+{
+    if (!h || !d) return fail(CB_ERR_ARG, "null argument");
+    cudaSetDevice(h->fl.device);
+    int rc = build_plan(h); if (rc) return rc;
+    rc = ensure_keb(h); if (rc) return rc;
+    cudaStream_t s = h->stream;
+    CUDA_TRY(cudaMemcpyAsync(h->d.p, d, h->sz.NEQ * sizeof(double), cudaMemcpyHostToDevice, s));
+    CbForceArgs a = force_args(h);
+    // main.c:1776-1792 passes the committed arrays for both generations: ef <- forces(d)
+    a.sh_frame_i = h->sh_frame[0].p; a.sh_ef_i = h->sh_ef[0].p;
+    a.tr_frame_i = h->tr_frame[0].p; a.tr_ef_i = h->tr_ef[0].p;
+    a.f_temp = h->f.p;
+    if (cbk_forces_linear(a, h->d.p, s, &h->launches)) return fail(CB_ERR_CUDA, "forces launch");
+    if (cbk_gather_f(a, s)) return fail(CB_ERR_CUDA, "gather launch");
+    ++h->launches;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (f_out)
+        CUDA_TRY(cudaMemcpy(f_out, h->f.p, h->sz.NEQ * sizeof(double), cudaMemcpyDeviceToHost));
+    return CB_OK;
+}
+
+extern "C" int cb_mass(cb_handle *h)
+{
+    if (!h) return fail(CB_ERR_ARG, "null handle");
+    cudaSetDevice(h->fl.device);
+    int rc = build_plan(h); if (rc) return rc;
+    CbDev d = make_dev(h);
+    CUDA_TRY(cudaMemsetAsync(h->sm.p, 0, h->sz.NEQ * sizeof(double), h->stream));
+    if (cbk_mass(d, h->x.p, h->sh_const.p, h->tr_const.p, h->fr_const.p, nullptr, h->tr_dens.p,
+                 h->fr_dens.p, h->sh_dens.p, h->node_cstart.p, h->corners.p, h->sm.p, h->stream,
+                 &h->launches))
+        return fail(CB_ERR_CUDA, "mass launch");
+    h->keb_dirty = true;      // farea / slength were refreshed from x (App. B.5)
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return CB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------
+extern "C" int cb_get_skyline(cb_handle *h, double *ss, long n)
+{
+    if (!h || !ss) return fail(CB_ERR_ARG, "null argument");
+    if (!(h->layout & CB_MAT_SKYLINE) || !h->ss.p) return fail(CB_ERR_ARG, "no skyline matrix assembled");
+    if (n != h->lss) return fail(CB_ERR_ARG, "skyline length %ld != lss %ld", n, h->lss);
+    cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaMemcpy(ss, h->ss.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    return CB_OK;
+}
+
+extern "C" long cb_csc_nnz(cb_handle *h)
+{
+    if (!h) return -1;
+    cudaSetDevice(h->fl.device);
+    if (build_plan(h)) return -1;
+    return (h->layout & CB_MAT_CSC) ? h->nnz : -1;
+}
+
+static void host_pattern(cb_handle *h, int *Ap, int *Ai)
+{
+    const long NJ = h->sz.NJ;
+    for (long j = 0; j < NJ; ++j)
+        for (int cc = 0; cc < h->h_nfree[j]; ++cc) {
+            long p = h->base[j] + (long)cc * h->colh[j];
+            Ap[h->h_first[j] - 1 + cc] = (int)p;
+            if (!Ai) continue;
+            for (int k = h->adj_start[j]; k < h->adj_start[j + 1]; ++k) {
+                const int32_t A = h->adj[k];
+                for (int rr = 0; rr < h->h_nfree[A]; ++rr) Ai[p++] = h->h_first[A] - 1 + rr;
+            }
+        }
+    Ap[h->sz.NEQ] = (int)h->nnz;
+}
+
+extern "C" int cb_csc_pattern(cb_handle *h, int *Ap, int *Ai)
+{
+    if (!h || !Ap) return fail(CB_ERR_ARG, "null argument");
+    cudaSetDevice(h->fl.device);
+    int rc = build_plan(h); if (rc) return rc;
+    if (!(h->layout & CB_MAT_CSC)) return fail(CB_ERR_ARG, "handle has no CSC layout");
+    host_pattern(h, Ap, Ai);
+    return CB_OK;
+}
+
+extern "C" int cb_get_csc_values(cb_handle *h, double *Ax)
+{
+    if (!h || !Ax) return fail(CB_ERR_ARG, "null argument");
+    if (!(h->layout & CB_MAT_CSC) || !h->Ax.p) return fail(CB_ERR_ARG, "no CSC matrix assembled");
+    cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaMemcpy(Ax, h->Ax.p, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToHost));
+    return CB_OK;
+}
+
+extern "C" long cb_csc_compact(cb_handle *h, double drop_tol, int *Ap, int *Ai, double *Ax)
+{
+    if (!h || !Ap || !Ai || !Ax) { fail(CB_ERR_ARG, "null argument"); return -1; }
+    if (!(h->layout & CB_MAT_CSC) || !h->Ax.p) { fail(CB_ERR_ARG, "no CSC matrix assembled"); return -1; }
+    cudaSetDevice(h->fl.device);
+    std::vector<int> fAp(h->sz.NEQ + 1), fAi((size_t)h->nnz);
+    std::vector<double> fAx((size_t)h->nnz);
+    host_pattern(h, fAp.data(), fAi.data());
+    if (cudaMemcpy(fAx.data(), h->Ax.p, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToHost) !=
+        cudaSuccess) { fail(CB_ERR_CUDA, "Ax download failed"); return -1; }
+    long nz = 0;
+    Ap[0] = 0;
+    for (long c = 0; c < h->sz.NEQ; ++c) {
+        for (int p = fAp[c]; p < fAp[c + 1]; ++p)
+            if (fabs(fAx[p]) > drop_tol) { Ai[nz] = fAi[p]; Ax[nz] = fAx[p]; ++nz; }   // solve.c:112
+        Ap[c + 1] = (int)nz;
+    }
+    return nz;
+}
+
+extern "C" int cb_get_mass(cb_handle *h, double *sm)
+{
+    if (!h || !sm) return fail(CB_ERR_ARG, "null argument");
+    cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaMemcpy(sm, h->sm.p, h->sz.NEQ * sizeof(double), cudaMemcpyDeviceToHost));
+    return CB_OK;
+}
+
+extern "C" int cb_get_f(cb_handle *h, double *f)
+{
+    if (!h || !f) return fail(CB_ERR_ARG, "null argument");
+    cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaMemcpy(f, h->f_temp.p, h->sz.NEQ * sizeof(double), cudaMemcpyDeviceToHost));
+    return CB_OK;
+}
+
+extern "C" double *cb_dev_Ax(cb_handle *h) { return h ? h->Ax.p : nullptr; }
+extern "C" double *cb_dev_skyline(cb_handle *h) { return h ? h->ss.p : nullptr; }
+extern "C" double *cb_dev_f(cb_handle *h) { return h ? h->f_temp.p : nullptr; }
+extern "C" double *cb_dev_dd(cb_handle *h) { return h ? h->dd.p : nullptr; }
+extern "C" const int *cb_dev_Ap(cb_handle *h) { return h ? h->Ap.p : nullptr; }
+extern "C" const int *cb_dev_Ai(cb_handle *h)
+{
+    if (!h || !(h->layout & CB_MAT_CSC)) return nullptr;
+    cudaSetDevice(h->fl.device);
+    if (build_plan(h)) return nullptr;
+    if (!h->Ai.p) {
+        std::vector<int> Ap(h->sz.NEQ + 1), Ai((size_t)h->nnz);
+        host_pattern(h, Ap.data(), Ai.data());
+        if (h->Ai.upload(Ai)) return nullptr;
+    }
+    return h->Ai.p;
+}
+
+// ------------------------------------------------------------------------------------------
+// state transfer in the reference's host layout
+// ------------------------------------------------------------------------------------------
+struct View {          // where a reference array lives on the device
+    long n = 0;        // reference length
+    // per element type: device buffer, record stride, offset inside the record, items per element
+    struct Part { double *p; long ne; int stride, off, cnt; } part[3];
+    int nparts = 0;
+    double *flat = nullptr;   // plain vector (nodes / NEQ)
+};
+
+static int make_view(cb_handle *h, int which, View &v)
+{
+    const long TR = h->sz.NE_TR, FR = h->sz.NE_FR, SH = h->sz.NE_SH, NJ = h->sz.NJ, NEQ = h->sz.NEQ;
+    const int gi = h->i_is_ip ? h->gP : h->gN, gp = h->gP;
+    auto cosines = [&](int g, int row) {
+        v.n = TR + 3 * FR + 3 * SH;
+        v.part[0] = {h->tr_frame[g].p, TR, CB_TR_FRAME, row, 1};
+        v.part[1] = {h->fr_frame[g].p, FR, CB_FR_FRAME, 3 * row, 3};
+        v.part[2] = {h->sh_frame[g].p, SH, CB_SH_FRAME, 3 * row, 3};
+        v.nparts = 3;
+    };
+    auto efv = [&](int g) {
+        v.n = 2 * TR + 14 * FR + 18 * SH;
+        v.part[0] = {h->tr_ef[g].p, TR, 2, 0, 2};
+        v.part[1] = {h->fr_ef[g].p, FR, 14, 0, 14};
+        v.part[2] = {h->sh_ef[g].p, SH, 18, 0, 18};
+        v.nparts = 3;
+    };
+    auto dll = [&](int g) {
+        v.n = TR + FR;
+        v.part[0] = {h->tr_frame[g].p, TR, CB_TR_FRAME, 3, 1};
+        v.part[1] = {h->fr_frame[g].p, FR, CB_FR_FRAME, 9, 1};
+        v.nparts = 2;
+    };
+    auto dfa = [&](int g) { v.n = SH; v.part[0] = {h->sh_frame[g].p, SH, CB_SH_FRAME, 9, 1}; v.nparts = 1; };
+    auto dslv = [&](int g) { v.n = 3 * SH; v.part[0] = {h->sh_dsl[g].p, SH, 3, 0, 3}; v.nparts = 1; };
+    switch (which) {
+    case CB_ARR_X: v.n = NJ * 3; v.flat = h->x.p; break;
+    case CB_ARR_X_TEMP: v.n = NJ * 3; v.flat = h->x_temp.p; break;
+    case CB_ARR_X_IP: v.n = NJ * 3; v.flat = h->x_ip.p; break;
+    case CB_ARR_D: v.n = NEQ; v.flat = h->d.p; break;
+    case CB_ARR_D_TEMP: v.n = NEQ; v.flat = h->d_temp.p; break;
+    case CB_ARR_F: v.n = NEQ; v.flat = h->f.p; break;
+    case CB_ARR_F_TEMP: v.n = NEQ; v.flat = h->f_temp.p; break;
+    case CB_ARR_C1: cosines(0, 0); break;
+    case CB_ARR_C2: cosines(0, 1); break;
+    case CB_ARR_C3: cosines(0, 2); break;
+    case CB_ARR_C1_I: cosines(gi, 0); break;
+    case CB_ARR_C2_I: cosines(gi, 1); break;
+    case CB_ARR_C3_I: cosines(gi, 2); break;
+    case CB_ARR_C1_IP: cosines(gp, 0); break;
+    case CB_ARR_C2_IP: cosines(gp, 1); break;
+    case CB_ARR_C3_IP: cosines(gp, 2); break;
+    case CB_ARR_EF: efv(0); break;
+    case CB_ARR_EF_I: case CB_ARR_EF_IP: efv(h->eP); break;
+    case CB_ARR_DEFLLEN: dll(0); break;
+    case CB_ARR_DEFLLEN_I: dll(gi); break;
+    case CB_ARR_DEFLLEN_IP: dll(gp); break;
+    case CB_ARR_DEFFAREA: dfa(0); break;
+    case CB_ARR_DEFFAREA_I: dfa(gi); break;
+    case CB_ARR_DEFFAREA_IP: dfa(gp); break;
+    case CB_ARR_DEFSLEN: dslv(0); break;
+    case CB_ARR_DEFSLEN_I: dslv(gi); break;
+    case CB_ARR_DEFSLEN_IP: dslv(gp); break;
+    case CB_ARR_FAREA: v.n = SH; v.part[0] = {h->sh_const.p, SH, CB_SH_CONST, 4, 1}; v.nparts = 1; break;
+    case CB_ARR_SLENGTH: v.n = 3 * SH; v.part[0] = {h->sh_const.p, SH, CB_SH_CONST, 8, 3}; v.nparts = 1; break;
+    case CB_ARR_LLENGTH:
+        v.n = TR + FR;
+        v.part[0] = {h->tr_const.p, TR, CB_TR_CONST, 2, 1};
+        v.part[1] = {h->fr_const.p, FR, CB_FR_CONST, 3, 1};
+        v.nparts = 2; break;
+    default: return fail(CB_ERR_UNSUPPORTED, "array id %d is not transferable in this build", which);
+    }
+    return CB_OK;
+}
+
+static int transfer(cb_handle *h, int which, double *host, long n, bool down)
+{
+    if (!h || (!host && n != 0)) return fail(CB_ERR_ARG, "null argument");
+    cudaSetDevice(h->fl.device);
+    cudaStreamSynchronize(h->stream);
+    View v; int rc = make_view(h, which, v); if (rc) return rc;
+    if (n != v.n) return fail(CB_ERR_ARG, "array %d: length %ld, expected %ld", which, n, v.n);
+    if (v.flat) {
+        if (n == 0) return CB_OK;
+        CUDA_TRY(cudaMemcpy(down ? (void *)host : (void *)v.flat, down ? (void *)v.flat : (void *)host,
+                            (size_t)n * sizeof(double),
+                            down ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice));
+        return CB_OK;
+    }
+    long pos = 0;
+    for (int k = 0; k < v.nparts; ++k) {
+        const View::Part &pt = v.part[k];
+        if (pt.ne == 0) continue;
+        std::vector<double> tmp((size_t)pt.ne * pt.stride);
+        CUDA_TRY(cudaMemcpy(tmp.data(), pt.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (long e = 0; e < pt.ne; ++e)
+            for (int c = 0; c < pt.cnt; ++c) {
+                double &dv = tmp[(size_t)e * pt.stride + pt.off + c];
+                if (down) host[pos] = dv; else dv = host[pos];
+                ++pos;
+            }
+        if (!down)
+            CUDA_TRY(cudaMemcpy(pt.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return CB_OK;
+}
+
+extern "C" int cb_download(cb_handle *h, int which, double *dst, long n)
+{
+    return transfer(h, which, dst, n, true);
+}
+extern "C" int cb_upload(cb_handle *h, int which, const double *src, long n)
+{
+    return transfer(h, which, const_cast<double *>(src), n, false);
+}
+
+extern "C" long cb_launch_count(cb_handle *h) { return h ? h->launches : 0; }
+extern "C" double cb_last_stiff_ms(cb_handle *h) { return h ? h->last_stiff_ms : 0; }
+extern "C" double cb_last_forces_ms(cb_handle *h) { return h ? h->last_forces_ms : 0; }
+extern "C" long cb_map_bytes(cb_handle *h) { return h ? h->map_bytes : 0; }
+extern "C" int cb_sync(cb_handle *h)
+{
+    if (!h) return fail(CB_ERR_ARG, "null handle");
+    cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return CB_OK;
+}
+extern "C" void *cb_stream(cb_handle *h) { return h ? (void *)h->stream : nullptr; }

@@ -1,0 +1,710 @@
+// cb_forces.cu - co-rotational kinematics update + internal-force recovery + f_int / mass gather.
+//
+// THIS TRANSLATION UNIT IS COMPILED WITH -fmad=false.  The internal-force path is a chain of
+// differences of nearly equal numbers (current minus reference local coordinates, rigid-body
+// parts of the displacement increment cancelling inside ke_b * ddb), so agreement with the
+// reference to 1e-12 needs the reference's own rounding sequence, not just its formulas.  Every
+// routine here therefore keeps the reference's operation ORDER (left-to-right sums, divide not
+// reciprocal-multiply) with separate IEEE multiplies and adds - which is what gcc emits for the
+// reference on baseline x86-64 (no FMA unit in the target).  Structure is still exploited: the
+// 18x18 transformation matrices are block-diagonal copies of one 3x3 triad, so products with
+// their structural zeros (which add +-0 and change nothing) are skipped.
+//
+// Replaces (per Newton iteration):  updatc misc.c:71-185, forces_tr truss.c:231-378,
+// forces_fr frame.c:902-1312, forces_sh shell.c:1593-2400 (ANAFLAG 1, 2), the f_temp scatter
+// inlined in each of them, mass_tr/fr/sh truss.c:381, frame.c:1314, shell.c:1505; once per model:
+// stiffe_b_sh shell.c:533-658 (DKT bending matrix, geometry-constant).
+#include "cb_internal.h"
+
+#define CB_TPB 128
+
+__device__ __forceinline__ double dot3(const double *a, const double *b)
+{   // misc.c:252-262: dp = 0; dp += a[i]*b[i]
+    double dp = 0.0;
+    dp += a[0] * b[0];
+    dp += a[1] * b[1];
+    dp += a[2] * b[2];
+    return dp;
+}
+
+__device__ __forceinline__ void cross3(const double *a, const double *b, double *c, bool unit)
+{   // misc.c:264-282
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+    if (unit) {
+        double len = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+        c[0] /= len; c[1] /= len; c[2] /= len;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// DKT plate-bending stiffness, Batoz explicit form (shell.c:533-658).  ke_b[9][9] row-major.
+// ------------------------------------------------------------------------------------------
+__device__ void dkt_alpha_T(const double *sc, double aT[9][9])
+{
+    const double X2 = sc[5], X3 = sc[6], Y3 = sc[7];
+    const double x23 = X2 - X3;
+    const double l12 = sc[8] * sc[8], l23 = sc[9] * sc[9], l31 = sc[10] * sc[10];
+    const double p4 = -6 * x23 / l23;
+    const double p5 = -6 * X3 / l31;
+    const double p6 = 6 * X2 / l12;
+    const double t4 = 6 * Y3 / l23;
+    const double t5 = -6 * Y3 / l31;
+    const double q4 = -3 * x23 * Y3 / l23;
+    const double q5 = 3 * X3 * Y3 / l31;
+    const double r4 = 3 * (Y3 * Y3) / l23;
+    const double r5 = 3 * (Y3 * Y3) / l31;
+    // transpose of Batoz' alpha (rows = w, theta_x, theta_y of vertices 1, 2, 3)
+    aT[0][0] = Y3 * p6;        aT[0][1] = -(Y3 * p6);      aT[0][2] = Y3 * p5;
+    aT[0][3] = -(X2 * t5);     aT[0][4] = 0;               aT[0][5] = x23 * t5;
+    aT[0][6] = -(X3 * p6) - X2 * p5;  aT[0][7] = -x23 * p6;  aT[0][8] = x23 * p5 + Y3 * t5;
+
+    aT[1][0] = 0;              aT[1][1] = 0;               aT[1][2] = -(Y3 * q5);
+    aT[1][3] = x23 + X2 * r5;  aT[1][4] = x23;             aT[1][5] = x23 * (1 - r5);
+    aT[1][6] = X2 * q5 + Y3;   aT[1][7] = Y3;              aT[1][8] = -x23 * q5 + Y3 * (1 - r5);
+
+    aT[2][0] = -4 * Y3;        aT[2][1] = 2 * Y3;          aT[2][2] = Y3 * (2 - r5);
+    aT[2][3] = -(X2 * q5);     aT[2][4] = 0;               aT[2][5] = x23 * q5;
+    aT[2][6] = -4 * x23 + X2 * r5;  aT[2][7] = 2 * x23;    aT[2][8] = x23 * (2 - r5) + Y3 * q5;
+
+    aT[3][0] = -(Y3 * p6);     aT[3][1] = Y3 * p6;         aT[3][2] = Y3 * p4;
+    aT[3][3] = 0;              aT[3][4] = X2 * t4;         aT[3][5] = -(X3 * t4);
+    aT[3][6] = X3 * p6;        aT[3][7] = x23 * p6 + X2 * p4;  aT[3][8] = -(X3 * p4) + Y3 * t4;
+
+    aT[4][0] = 0;              aT[4][1] = 0;               aT[4][2] = Y3 * q4;
+    aT[4][3] = X3;             aT[4][4] = X3 + X2 * r4;    aT[4][5] = X3 * (1 - r4);
+    aT[4][6] = -Y3;            aT[4][7] = -Y3 + X2 * q4;   aT[4][8] = Y3 * (r4 - 1) - X3 * q4;
+
+    aT[5][0] = -2 * Y3;        aT[5][1] = 4 * Y3;          aT[5][2] = Y3 * (r4 - 2);
+    aT[5][3] = 0;              aT[5][4] = -(X2 * q4);      aT[5][5] = X3 * q4;
+    aT[5][6] = 2 * X3;         aT[5][7] = -4 * X3 + X2 * r4;  aT[5][8] = X3 * (2 - r4) - Y3 * q4;
+
+    aT[6][0] = 0;              aT[6][1] = 0;               aT[6][2] = -(Y3 * (p4 + p5));
+    aT[6][3] = X2 * t5;        aT[6][4] = -(X2 * t4);      aT[6][5] = -x23 * t5 + X3 * t4;
+    aT[6][6] = X2 * p5;        aT[6][7] = -(X2 * p4);
+    aT[6][8] = -x23 * p5 + X3 * p4 - Y3 * (t4 + t5);
+
+    aT[7][0] = 0;              aT[7][1] = 0;               aT[7][2] = Y3 * (q4 - q5);
+    aT[7][3] = X2 * (r5 - 1);  aT[7][4] = X2 * (r4 - 1);   aT[7][5] = -x23 * r5 - X3 * r4 - X2;
+    aT[7][6] = X2 * q5;        aT[7][7] = X2 * q4;
+    aT[7][8] = -x23 * q5 - X3 * q4 + Y3 * (r4 - r5);
+
+    aT[8][0] = 0;              aT[8][1] = 0;               aT[8][2] = Y3 * (r4 - r5);
+    aT[8][3] = -(X2 * q5);     aT[8][4] = -(X2 * q4);      aT[8][5] = X3 * q4 + x23 * q5;
+    aT[8][6] = X2 * (r5 - 2);  aT[8][7] = X2 * (r4 - 2);
+    aT[8][8] = -x23 * r5 - X3 * r4 + 4 * X2 + Y3 * (q5 - q4);
+}
+
+__global__ void __launch_bounds__(CB_TPB)
+k_shell_init_keb(CbDev d, double *__restrict__ keb)
+{
+    long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (e >= d.NE_SH) return;
+    double sc[CB_SH_CONST];
+#pragma unroll
+    for (int i = 0; i < CB_SH_CONST; ++i) sc[i] = d.sh_const[e * CB_SH_CONST + i];
+    const double E = sc[0], nu = sc[1], t3 = sc[3], A0 = sc[4];
+    const double E1 = E * t3 / (12 * (1 - nu * nu));
+    const double E3 = E1;
+    const double E2 = E * t3 / (12 * (1 - nu * nu)) * nu;
+    const double E4 = E * t3 / (12 * (1 - nu * nu)) * (1 - nu) / 2;
+    double aT[9][9], Q[9][9];
+    dkt_alpha_T(sc, aT);
+    for (int i = 0; i < 9; ++i) {           // shell.c:610-648, the three row blocks are alike
+        double b1 = 0, b2 = 0, b3 = 0;
+        for (int j = 0; j < 3; ++j) {
+            b1 += E1 * aT[i][j] + E2 * aT[i][j + 3];
+            b2 += E2 * aT[i][j] + E3 * aT[i][j + 3];
+            b3 += E4 * aT[i][j + 6];
+        }
+        for (int j = 0; j < 3; ++j) {
+            Q[i][j] = (E1 * aT[i][j] + E2 * aT[i][j + 3] + b1) / 24;
+            Q[i][j + 3] = (E2 * aT[i][j] + E3 * aT[i][j + 3] + b2) / 24;
+            Q[i][j + 6] = (E4 * aT[i][j + 6] + b3) / 24;
+        }
+    }
+    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j < 9; ++j) {
+            double sum = 0;
+            for (int k = 0; k < 9; ++k) sum += Q[i][k] * aT[j][k];
+            keb[e * 81 + i * 9 + j] = sum / (2 * A0);
+        }
+}
+
+int cbk_shell_init_keb(const CbDev &d, double *keb_out, cudaStream_t s)
+{
+    if (d.NE_SH == 0) return 0;
+    unsigned g = (unsigned)((d.NE_SH + CB_TPB - 1) / CB_TPB);
+    k_shell_init_keb<<<g, CB_TPB, 0, s>>>(d, keb_out);
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// plane-stress constitutive coefficients (shell.c:497-501 / 672-676)
+__device__ __forceinline__ void plane_stress(double E, double nu, double &C00, double &C01,
+                                             double &C22)
+{
+    C00 = E / (1 - nu * nu);
+    C01 = E / (1 - nu * nu) * nu;
+    C22 = E / (1 - nu * nu) * (1 - nu) / 2;
+}
+
+// membrane strain-displacement matrix with area `A` (shell.c:503-510 / 678-686)
+__device__ __forceinline__ void membrane_B(const double *sc, double A, double Bm[3][6])
+{
+    const double X2 = sc[5], X3 = sc[6], Y3 = sc[7];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) Bm[i][j] = 0;
+    Bm[0][0] = Bm[2][1] = -(Y3 / (2 * A));
+    Bm[0][2] = Bm[2][3] = Y3 / (2 * A);
+    Bm[1][1] = Bm[2][0] = (X3 - X2) / (2 * A);
+    Bm[1][3] = Bm[2][2] = -(X3 / (2 * A));
+    Bm[1][5] = Bm[2][4] = X2 / (2 * A);
+}
+
+// current local membrane coordinates (mem_coord, shell.c:2402-2446) minus the reference ones
+// (shell.c:164-167): returns dm[2], dm[4], dm[5]
+__device__ __forceinline__ void membrane_dm(const double *xj, const double *xk, const double *xl,
+                                            const double *R, const double *sc, double &dm2,
+                                            double &dm4, double &dm5)
+{
+    double Xk[3], Xl[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { Xk[m] = xk[m] - xj[m]; Xl[m] = xl[m] - xj[m]; }
+    const double x01 = dot3(R, Xk);        // T[0][:] . X[:,1]
+    const double x02 = dot3(R, Xl);        // T[0][:] . X[:,2]
+    const double x12 = dot3(R + 3, Xl);    // T[1][:] . X[:,2]
+    dm5 = x12 - sc[7];
+    dm4 = x02 - sc[6];
+    dm2 = x01 - sc[5];
+}
+
+// ------------------------------------------------------------------------------------------
+// prep for the geometric stiffness: membrane force resultants Nm (shell.c:688-704) from the
+// coordinates and triad the stiffness pass is evaluated at.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CB_TPB)
+k_shell_prep(CbDev d, const double *__restrict__ x, const double *__restrict__ frame)
+{
+    long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (e >= d.NE_SH) return;
+    double sc[CB_SH_CONST], R[CB_SH_FRAME];
+#pragma unroll
+    for (int i = 0; i < CB_SH_CONST; ++i) sc[i] = d.sh_const[e * CB_SH_CONST + i];
+#pragma unroll
+    for (int i = 0; i < CB_SH_FRAME; ++i) R[i] = frame[e * CB_SH_FRAME + i];
+    const int4 nd = reinterpret_cast<const int4 *>(d.sh_nodes)[e];
+    double xj[3], xk[3], xl[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        xj[m] = x[(long)nd.x * 3 + m]; xk[m] = x[(long)nd.y * 3 + m]; xl[m] = x[(long)nd.z * 3 + m];
+    }
+    double dm[6] = {0, 0, 0, 0, 0, 0};
+    membrane_dm(xj, xk, xl, R, sc, dm[2], dm[4], dm[5]);
+    double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    plane_stress(sc[0], sc[1], C[0][0], C[0][1], C[2][2]);
+    C[1][1] = C[0][0]; C[1][0] = C[0][1];
+    double Bm[3][6];
+    membrane_B(sc, R[9], Bm);
+    double Nm[3];
+    for (int i = 0; i < 3; ++i) {
+        double sum = 0;
+        for (int j = 0; j < 6; ++j) {
+            double cb = 0;                      // C_Bm[i][j] (shell.c:689-697)
+            for (int k = 0; k < 3; ++k) cb += C[i][k] * Bm[k][j];
+            sum += cb * dm[j];
+        }
+        Nm[i] = sc[2] * sum;
+    }
+    d.sh_Nm[e * 4 + 0] = Nm[0]; d.sh_Nm[e * 4 + 1] = Nm[1]; d.sh_Nm[e * 4 + 2] = Nm[2];
+    d.sh_Nm[e * 4 + 3] = 0;
+}
+
+int cbk_shell_prep(const CbDev &d, const double *x, const double *sh_frame, cudaStream_t s)
+{
+    if (d.NE_SH == 0) return 0;
+    unsigned g = (unsigned)((d.NE_SH + CB_TPB - 1) / CB_TPB);
+    k_shell_prep<<<g, CB_TPB, 0, s>>>(d, x, sh_frame);
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------------
+// updatc, nodal part (misc.c:83-93): x_ip <- x_temp ; x_temp += dd[jcode-1] on free DOFs 1-3
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_node_update(long NJ, const int32_t *__restrict__ jc, const double *__restrict__ dd,
+              double *__restrict__ x_temp, double *__restrict__ x_ip)
+{
+    long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (t >= NJ * 3) return;
+    long i = t / 3; int j = (int)(t - i * 3);
+    int k = jc[i * 8 + j];
+    double xv = x_temp[t];
+    x_ip[t] = xv;
+    if (k != 0) x_temp[t] = xv + dd[k - 1];
+}
+
+int cbk_node_update(const CbForceArgs &a, cudaStream_t s)
+{
+    long n = a.d.NJ * 3;
+    unsigned g = (unsigned)((n + 255) / 256);
+    k_node_update<<<g, 256, 0, s>>>(a.d.NJ, a.d.jc, a.dd, a.x_temp, a.x_ip);
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// gather the 6 incremental (or total) displacements of one node; fixed DOFs read as 0
+__device__ __forceinline__ void gather_node6(const int32_t *jc, const double *v, int node,
+                                             double *D)
+{
+    const int4 a = reinterpret_cast<const int4 *>(jc)[(long)node * 2];
+    const int4 b = reinterpret_cast<const int4 *>(jc)[(long)node * 2 + 1];
+    D[0] = a.x ? v[a.x - 1] : 0.0; D[1] = a.y ? v[a.y - 1] : 0.0; D[2] = a.z ? v[a.z - 1] : 0.0;
+    D[3] = a.w ? v[a.w - 1] : 0.0; D[4] = b.x ? v[b.x - 1] : 0.0; D[5] = b.y ? v[b.y - 1] : 0.0;
+}
+
+// updatc, shell part (misc.c:153-184): side lengths, area, triad from the current coordinates
+__device__ __forceinline__ void shell_triad(const double *xj, const double *xk, const double *xl,
+                                            double *R /*[10]*/, double *dsl /*[3]*/)
+{
+    double el12[3], el23[3], el31[3], normal[3], lx[3], ly[3], lz[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        el23[m] = xl[m] - xk[m];
+        el31[m] = xl[m] - xj[m];
+        el12[m] = xk[m] - xj[m];
+    }
+    dsl[1] = sqrt(dot3(el23, el23));
+    dsl[2] = sqrt(dot3(el31, el31));
+    dsl[0] = sqrt(dot3(el12, el12));
+    cross3(el12, el31, normal, false);
+    const double A = 0.5 * sqrt(dot3(normal, normal));
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { lx[m] = el12[m] / dsl[0]; lz[m] = normal[m] / (2 * A); }
+    cross3(lz, lx, ly, true);
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { R[m] = lx[m]; R[3 + m] = ly[m]; R[6 + m] = lz[m]; }
+    R[9] = A;
+}
+
+// ------------------------------------------------------------------------------------------
+// forces_sh, ANAFLAG 2 (shell.c:1728-1785, 2305-2347, 2386-2397) fused with the shell block of
+// updatc.  One thread per element.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CB_TPB)
+k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restrict__ dd,
+               const double *__restrict__ frame_ip, double *__restrict__ frame_i,
+               double *__restrict__ dsl_i, const double *__restrict__ ef_ip,
+               double *__restrict__ ef_i)
+{
+    long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (e >= d.NE_SH) return;
+    double sc[CB_SH_CONST], Rp[CB_SH_FRAME], Ri[CB_SH_FRAME], dsl[3];
+#pragma unroll
+    for (int i = 0; i < CB_SH_CONST; ++i) sc[i] = d.sh_const[e * CB_SH_CONST + i];
+#pragma unroll
+    for (int i = 0; i < CB_SH_FRAME; ++i) Rp[i] = frame_ip[e * CB_SH_FRAME + i];
+    const int4 nd = reinterpret_cast<const int4 *>(d.sh_nodes)[e];
+    const int nn[3] = {nd.x, nd.y, nd.z};
+    double X[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int m = 0; m < 3; ++m) X[a][m] = x_temp[(long)nn[a] * 3 + m];
+
+    shell_triad(X[0], X[1], X[2], Ri, dsl);
+#pragma unroll
+    for (int i = 0; i < CB_SH_FRAME; ++i) frame_i[e * CB_SH_FRAME + i] = Ri[i];
+    dsl_i[e * 3 + 0] = dsl[0]; dsl_i[e * 3 + 1] = dsl[1]; dsl_i[e * 3 + 2] = dsl[2];
+
+    // membrane: total force from the current local coordinates (shell.c:1729-1744, 1767-1775)
+    double dm2, dm4, dm5;
+    membrane_dm(X[0], X[1], X[2], Ri, sc, dm2, dm4, dm5);
+    double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    plane_stress(sc[0], sc[1], C[0][0], C[0][1], C[2][2]);
+    C[1][1] = C[0][0]; C[1][0] = C[0][1];
+    double Bm[3][6];
+    membrane_B(sc, sc[4], Bm);
+    double ef_temp[6];
+    {
+        const double dmv[6] = {0, 0, dm2, 0, dm4, dm5};
+        for (int i = 0; i < 6; ++i) {
+            double BC[3];
+            for (int j = 0; j < 3; ++j) {       // Bm_C[i][j] (shell.c:513-521)
+                double sum = 0;
+                for (int k = 0; k < 3; ++k) sum += Bm[k][i] * C[k][j];
+                BC[j] = sum;
+            }
+            double acc = 0;
+            for (int j = 0; j < 6; ++j) {
+                double sum = 0;                  // ke_m[i][j] (shell.c:522-530)
+                for (int k = 0; k < 3; ++k) sum += BC[k] * Bm[k][j];
+                acc += (sc[2] * sc[4] * sum) * dmv[j];
+            }
+            ef_temp[i] = acc;
+        }
+    }
+
+    // bending: incremental force ke_b * ddb, ddb = T_ip * DD on the bending DOFs (1746-1785)
+    double DD[3][6];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) gather_node6(d.jc, dd, nn[a], DD[a]);
+    double ddb[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        ddb[3 * a + 0] = dot3(Rp + 6, DD[a]);        // w       : c3_ip . translations
+        ddb[3 * a + 1] = dot3(Rp + 0, DD[a] + 3);    // theta_x : c1_ip . rotations
+        ddb[3 * a + 2] = dot3(Rp + 3, DD[a] + 3);    // theta_y : c2_ip . rotations
+    }
+    double defb[9];
+    const double *kb = d.sh_keb + e * 81;
+    for (int i = 0; i < 9; ++i) {
+        double sum = 0;
+        for (int j = 0; j < 9; ++j) sum += kb[i * 9 + j] * ddb[j];
+        defb[i] = sum;
+    }
+
+    // T_i * T_ip^T is block diagonal with M = R_i R_ip^T (shell.c:2326-2338)
+    double M[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2) M[r][s2] = dot3(Ri + 3 * r, Rp + 3 * s2);
+
+    // ef_i = ef_temp + Ti_Tip (def + ef_ip) with the membrane slots of ef_ip zeroed (1773, 2342-2348)
+    double efi[18], fg[18];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double vt[3], vr[3];
+        vt[0] = 0.0; vt[1] = 0.0;
+        vt[2] = defb[3 * a] + ef_ip[e * 18 + 6 * a + 2];
+        vr[0] = defb[3 * a + 1] + ef_ip[e * 18 + 6 * a + 3];
+        vr[1] = defb[3 * a + 2] + ef_ip[e * 18 + 6 * a + 4];
+        vr[2] = 0.0 + ef_ip[e * 18 + 6 * a + 5];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const double et = (r < 2) ? ef_temp[2 * a + r] : 0.0;
+            efi[6 * a + r] = et + dot3(M[r], vt);
+            efi[6 * a + 3 + r] = 0.0 + dot3(M[r], vr);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) ef_i[e * 18 + i] = efi[i];
+    // element force in global axes, T_i^T ef_i (shell.c:2388-2392)
+#pragma unroll
+    for (int g = 0; g < 6; ++g)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double sum = 0;
+            sum += Ri[c] * efi[3 * g];
+            sum += Ri[3 + c] * efi[3 * g + 1];
+            sum += Ri[6 + c] * efi[3 * g + 2];
+            fg[3 * g + c] = sum;
+        }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) d.sh_fg[e * 18 + i] = fg[i];
+}
+
+// forces_sh, ANAFLAG 1 (shell.c:1695-1727, 2386-2397): ef = k_sh (T D), total displacements
+__global__ void __launch_bounds__(CB_TPB)
+k_shell_forces_linear(CbDev d, const double *__restrict__ dtot, const double *__restrict__ frame,
+                      double *__restrict__ ef_out)
+{
+    long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (e >= d.NE_SH) return;
+    double sc[CB_SH_CONST], R[CB_SH_FRAME];
+#pragma unroll
+    for (int i = 0; i < CB_SH_CONST; ++i) sc[i] = d.sh_const[e * CB_SH_CONST + i];
+#pragma unroll
+    for (int i = 0; i < CB_SH_FRAME; ++i) R[i] = frame[e * CB_SH_FRAME + i];
+    const int4 nd = reinterpret_cast<const int4 *>(d.sh_nodes)[e];
+    const int nn[3] = {nd.x, nd.y, nd.z};
+    double D[3][6], dl[18];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        gather_node6(d.jc, dtot, nn[a], D[a]);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            dl[6 * a + r] = dot3(R + 3 * r, D[a]);
+            dl[6 * a + 3 + r] = dot3(R + 3 * r, D[a] + 3);
+        }
+    }
+    double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    plane_stress(sc[0], sc[1], C[0][0], C[0][1], C[2][2]);
+    C[1][1] = C[0][0]; C[1][0] = C[0][1];
+    double Bm[3][6];
+    membrane_B(sc, sc[4], Bm);
+    const int fm[6] = {0, 1, 6, 7, 12, 13};
+    const int fb[9] = {2, 3, 4, 8, 9, 10, 14, 15, 16};
+    double ef[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) ef[i] = 0;
+    for (int i = 0; i < 6; ++i) {
+        double BC[3];
+        for (int j = 0; j < 3; ++j) {
+            double sum = 0;
+            for (int k = 0; k < 3; ++k) sum += Bm[k][i] * C[k][j];
+            BC[j] = sum;
+        }
+        double acc = 0;
+        for (int j = 0; j < 6; ++j) {
+            double sum = 0;
+            for (int k = 0; k < 3; ++k) sum += BC[k] * Bm[k][j];
+            acc += (sc[2] * sc[4] * sum) * dl[fm[j]];
+        }
+        ef[fm[i]] = acc;
+    }
+    const double *kb = d.sh_keb + e * 81;
+    for (int i = 0; i < 9; ++i) {
+        double sum = 0;
+        for (int j = 0; j < 9; ++j) sum += kb[i * 9 + j] * dl[fb[j]];
+        ef[fb[i]] = sum;
+    }
+    // drilling stiffness ke_b[1][1]/1e4 etc. (shell.c:482-484)
+    ef[5] = (kb[1 * 9 + 1] / 10000) * dl[5];
+    ef[11] = (kb[4 * 9 + 4] / 10000) * dl[11];
+    ef[17] = (kb[7 * 9 + 7] / 10000) * dl[17];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) ef_out[e * 18 + i] = ef[i];
+#pragma unroll
+    for (int g = 0; g < 6; ++g)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double sum = 0;
+            sum += R[c] * ef[3 * g];
+            sum += R[3 + c] * ef[3 * g + 1];
+            sum += R[6 + c] * ef[3 * g + 2];
+            d.sh_fg[e * 18 + 3 * g + c] = sum;
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// truss: updatc (misc.c:97-108) + forces_tr (truss.c:326-376 nonlinear, 243-325 linear)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CB_TPB)
+k_truss_forces(CbDev d, const double *__restrict__ x_temp, double *__restrict__ frame_i,
+               double *__restrict__ ef_i)
+{
+    long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (e >= d.NE_TR) return;
+    const int j = d.tr_nodes[e * 2], k = d.tr_nodes[e * 2 + 1];
+    double el[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) el[m] = x_temp[(long)k * 3 + m] - x_temp[(long)j * 3 + m];
+    const double dl = sqrt(dot3(el, el));
+    const double c[3] = {el[0] / dl, el[1] / dl, el[2] / dl};
+    frame_i[e * 4 + 0] = c[0]; frame_i[e * 4 + 1] = c[1]; frame_i[e * 4 + 2] = c[2];
+    frame_i[e * 4 + 3] = dl;
+    const double E = d.tr_const[e * 4 + 0], A = d.tr_const[e * 4 + 1], L0 = d.tr_const[e * 4 + 2];
+    const double strain = (dl - L0) / L0;
+    const double ef0 = E * A * (strain + 0.5 * (strain * strain)) * dl / L0;
+    const double ef1 = -ef0;
+    ef_i[e * 2] = ef0; ef_i[e * 2 + 1] = ef1;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {           // f_temp -= ef * c  (truss.c:351-375)
+        d.tr_fg[e * 6 + m] = -(ef0 * c[m]);
+        d.tr_fg[e * 6 + 3 + m] = -(ef1 * c[m]);
+    }
+}
+
+__global__ void __launch_bounds__(CB_TPB)
+k_truss_forces_linear(CbDev d, const double *__restrict__ dtot, const double *__restrict__ frame,
+                      double *__restrict__ ef_out)
+{
+    long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (e >= d.NE_TR) return;
+    const int nj = d.tr_nodes[e * 2], nk = d.tr_nodes[e * 2 + 1];
+    double D[6];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        int q = d.jc[(long)nj * 8 + m]; D[m] = q ? dtot[q - 1] : 0.0;
+        q = d.jc[(long)nk * 8 + m];     D[3 + m] = q ? dtot[q - 1] : 0.0;
+    }
+    const double c[3] = {frame[e * 4], frame[e * 4 + 1], frame[e * 4 + 2]};
+    const double d0 = dot3(c, D), d1 = dot3(c, D + 3);
+    const double E = d.tr_const[e * 4 + 0], A = d.tr_const[e * 4 + 1], L0 = d.tr_const[e * 4 + 2];
+    const double kk = A * E / L0, kn = -(A * E / L0);
+    double s0 = 0; s0 += kk * d0; s0 += kn * d1;
+    double s1 = 0; s1 += kn * d0; s1 += kk * d1;
+    ef_out[e * 2] = s0; ef_out[e * 2 + 1] = s1;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        d.tr_fg[e * 6 + m] = -(s0 * c[m]);
+        d.tr_fg[e * 6 + 3 + m] = -(s1 * c[m]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// f_temp: segmented reduction over the node -> corner map (sorted by element type, element), one
+// thread per node; reproduces the reference's summation order (all trusses, frames, shells)
+// without atomics (replaces the `f_temp[mcode-1] += ...` scatters).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_gather_f(CbDev d, const int32_t *__restrict__ cstart, const CbCorner *__restrict__ corners,
+           double *__restrict__ f)
+{
+    long n = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (n >= d.NJ) return;
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    const int c0 = cstart[n], c1 = cstart[n + 1];
+    for (int c = c0; c < c1; ++c) {
+        const CbCorner cr = corners[c];
+        if (cr.type == CB_T_SHELL) {
+            const double *p = d.sh_fg + (long)cr.e * 18 + cr.b * 6;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) acc[r] += p[r];
+        } else if (cr.type == CB_T_FRAME) {
+            const double *p = d.fr_fg + (long)cr.e * 14 + cr.b * 7;
+#pragma unroll
+            for (int r = 0; r < 7; ++r) acc[r] += p[r];
+        } else if (cr.type == CB_T_TRUSS) {
+            const double *p = d.tr_fg + (long)cr.e * 6 + cr.b * 3;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) acc[r] += p[r];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        const int q = d.jc[n * 8 + r];
+        if (q != 0) f[q - 1] = acc[r];
+    }
+}
+
+int cbk_gather_f(const CbForceArgs &a, cudaStream_t s)
+{
+    unsigned g = (unsigned)((a.d.NJ + 255) / 256);
+    k_gather_f<<<g, 256, 0, s>>>(a.d, a.node_cstart, a.corners, a.f_temp);
+    return cudaGetLastError() != cudaSuccess;
+}
+
+int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
+{
+    const CbDev &d = a.d;
+    if (d.NE_TR) {
+        unsigned g = (unsigned)((d.NE_TR + CB_TPB - 1) / CB_TPB);
+        k_truss_forces<<<g, CB_TPB, 0, s>>>(d, a.x_temp, a.tr_frame_i, a.tr_ef_i);
+        ++*launches;
+    }
+    if (d.NE_SH) {
+        unsigned g = (unsigned)((d.NE_SH + CB_TPB - 1) / CB_TPB);
+        k_shell_forces<<<g, CB_TPB, 0, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
+                                            a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i);
+        ++*launches;
+    }
+    return cudaGetLastError() != cudaSuccess;
+}
+
+int cbk_forces_linear(const CbForceArgs &a, const double *d_total, cudaStream_t s, long *launches)
+{
+    const CbDev &d = a.d;
+    if (d.NE_TR) {
+        unsigned g = (unsigned)((d.NE_TR + CB_TPB - 1) / CB_TPB);
+        k_truss_forces_linear<<<g, CB_TPB, 0, s>>>(d, d_total, a.tr_frame_i, a.tr_ef_i);
+        ++*launches;
+    }
+    if (d.NE_SH) {
+        unsigned g = (unsigned)((d.NE_SH + CB_TPB - 1) / CB_TPB);
+        k_shell_forces_linear<<<g, CB_TPB, 0, s>>>(d, d_total, a.sh_frame_i, a.sh_ef_i);
+        ++*launches;
+    }
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------------
+// lumped / row-summed diagonal mass (SLVFLAG==0 layout): mass_tr truss.c:381-441, mass_sh
+// shell.c:1505-1591.  The reference routines first overwrite llength / slength / farea with
+// values recomputed from the committed coordinates; k_mass_refresh does the
+// same to the device constants, then one thread per node sums its corners.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CB_TPB)
+k_mass_refresh_shell(CbDev d, const double *__restrict__ x, double *__restrict__ sh_const)
+{
+    long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (e >= d.NE_SH) return;
+    const int4 nd = reinterpret_cast<const int4 *>(d.sh_nodes)[e];
+    double xj[3], xk[3], xl[3], el12[3], el23[3], el31[3], normal[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        xj[m] = x[(long)nd.x * 3 + m]; xk[m] = x[(long)nd.y * 3 + m]; xl[m] = x[(long)nd.z * 3 + m];
+        el23[m] = xl[m] - xk[m]; el31[m] = xl[m] - xj[m]; el12[m] = xk[m] - xj[m];
+    }
+    sh_const[e * CB_SH_CONST + 9] = sqrt(dot3(el23, el23));
+    sh_const[e * CB_SH_CONST + 10] = sqrt(dot3(el31, el31));
+    sh_const[e * CB_SH_CONST + 8] = sqrt(dot3(el12, el12));
+    cross3(el12, el31, normal, false);
+    sh_const[e * CB_SH_CONST + 4] = 0.5 * sqrt(dot3(normal, normal));
+}
+
+__global__ void __launch_bounds__(CB_TPB)
+k_mass_refresh_truss(CbDev d, const double *__restrict__ x, double *__restrict__ tr_const)
+{
+    long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (e >= d.NE_TR) return;
+    const int j = d.tr_nodes[e * 2], k = d.tr_nodes[e * 2 + 1];
+    double el[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) el[m] = x[(long)k * 3 + m] - x[(long)j * 3 + m];
+    tr_const[e * CB_TR_CONST + 2] = sqrt(dot3(el, el));
+}
+
+__global__ void __launch_bounds__(256)
+k_mass_gather(CbDev d, const int32_t *__restrict__ cstart, const CbCorner *__restrict__ corners,
+              const double *__restrict__ dens_tr, const double *__restrict__ dens_sh,
+              double *__restrict__ sm)
+{
+    long n = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (n >= d.NJ) return;
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    const int c0 = cstart[n], c1 = cstart[n + 1];
+    for (int c = c0; c < c1; ++c) {
+        const CbCorner cr = corners[c];
+        if (cr.type == CB_T_SHELL) {
+            const double *sc = d.sh_const + (long)cr.e * CB_SH_CONST;
+            const double Mtot = dens_sh[cr.e] * sc[4] * sc[2];
+            const double mt = Mtot / 3;
+            const double mr = Mtot / 3 * (sc[2] * sc[2]) / 12;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { acc[r] += mt; acc[3 + r] += mr; }
+        } else if (cr.type == CB_T_TRUSS) {
+            // consistent mass row-summed onto the diagonal, only over free partner DOFs
+            // (truss.c:416-425): row ie gets m[ie][ie] + m[ie][ie+-3] if that DOF is free
+            const double *tc = d.tr_const + (long)cr.e * CB_TR_CONST;
+            const double m3 = (dens_tr[cr.e] * tc[1] * tc[2]) / 3;
+            const double m6 = (dens_tr[cr.e] * tc[1] * tc[2]) / 6;
+            const int other = d.tr_nodes[(long)cr.e * 2 + (1 - cr.b)];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int qo = d.jc[(long)other * 8 + r];
+                // the reference loops je ascending: end 0 adds diag then partner, end 1 partner
+                // then diag
+                if (cr.b == 0) { acc[r] += m3; if (qo) acc[r] += m6; }
+                else { if (qo) acc[r] += m6; acc[r] += m3; }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        const int q = d.jc[n * 8 + r];
+        if (q != 0) sm[q - 1] = acc[r];
+    }
+}
+
+int cbk_mass(const CbDev &d, const double *x, double *sh_const_mut, double *tr_const_mut,
+             double *fr_const_mut, double *fr_xfr, const double *dens_tr, const double *dens_fr,
+             const double *dens_sh, const int32_t *node_cstart, const CbCorner *corners,
+             double *sm, cudaStream_t s, long *launches)
+{
+    (void)fr_const_mut; (void)fr_xfr; (void)dens_fr;
+    if (d.NE_TR) {
+        unsigned g = (unsigned)((d.NE_TR + CB_TPB - 1) / CB_TPB);
+        k_mass_refresh_truss<<<g, CB_TPB, 0, s>>>(d, x, tr_const_mut); ++*launches;
+    }
+    if (d.NE_SH) {
+        unsigned g = (unsigned)((d.NE_SH + CB_TPB - 1) / CB_TPB);
+        k_mass_refresh_shell<<<g, CB_TPB, 0, s>>>(d, x, sh_const_mut); ++*launches;
+    }
+    unsigned g = (unsigned)((d.NJ + 255) / 256);
+    k_mass_gather<<<g, 256, 0, s>>>(d, node_cstart, corners, dens_tr, dens_sh, sm); ++*launches;
+    return cudaGetLastError() != cudaSuccess;
+}

@@ -1,0 +1,156 @@
+// cb_internal.h - device-side data layout shared by the translation units of libcubens_b200.
+//
+// Layout in HBM:
+//   nodal arrays  AoS xyz  [NJ][3] doubles, three generations (committed / temp / ip)
+//   jcode         [NJ][8] int32 (7 used) so one node's equation numbers are two 16-byte loads
+//   per-element records are AoS and 16-byte aligned so a thread fetches its element with
+//   128-bit loads: shell constants [NE][12], shell frame state [NE][10] per generation,
+//   element end forces [NE][18|14|2] per generation, DKT bending matrix [NE][81].
+//   NEQ vectors   dd, f_temp, d_temp, d, f, sm.
+//   tangent matrix: CSC values Ax[nnz] (node-block structural pattern) and/or the reference's
+//   skyline vector ss[lss].
+#ifndef CB_INTERNAL_H
+#define CB_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CB_T_TRUSS 0
+#define CB_T_FRAME 1
+#define CB_T_SHELL 2
+#define CB_T_BRICK 3
+
+#define CB_SH_CONST 12   // E, nu, t, t^3 (libm pow on the host), A0, x2, x3, y3, l12, l23, l31, pad
+#define CB_SH_FRAME 10   // c1xyz c2xyz c3xyz, deformed area
+#define CB_FR_CONST 16   // E, G, A, L0, L0^2(libm), L0^3(libm), Iz, Iy, J, Cw, aux xyz, pad
+#define CB_FR_FRAME 10   // c1xyz c2xyz c3xyz, deformed length
+#define CB_TR_CONST 4    // E, A, L0, L0^3(libm)
+#define CB_TR_FRAME 4    // c1 c2 c3 deformed length
+
+// one contribution of an element block to a node-pair block of the global matrix
+struct CbContrib {
+    int32_t e;       // type-local element index
+    uint8_t type;    // CB_T_*
+    uint8_t a;       // local node of the row block
+    uint8_t b;       // local node of the column block
+    uint8_t pad;
+};
+
+// one node-pair block (row node A, column node B) = one thread of the assembly kernel
+struct CbPair {
+    int32_t off;      // CSC: index of (first free row of A, first free column of B) in Ax
+    int32_t colh;     // CSC: column height of node B's columns
+    int32_t cstart;   // first contribution
+    int32_t eqA0;     // first equation (1-based) of node A, 0 if none
+    int32_t eqB0;     // first equation (1-based) of node B
+    uint16_t ccount;  // number of contributions
+    uint8_t maskA;    // free-DOF mask of node A (bit r = DOF r free), 7 bits
+    uint8_t maskB;
+};
+
+// one element corner touching a node (node -> corner CSR), used by the f_int / mass gathers
+struct CbCorner {
+    int32_t e;
+    uint8_t type;
+    uint8_t b;       // local node index inside the element
+    uint8_t pad[2];
+};
+
+struct CbGenShell {      // one generation of shell state
+    double *frame;       // [NE][CB_SH_FRAME]
+    double *dsl;         // [NE][3] deformed side lengths
+};
+struct CbGenFrame {
+    double *frame;       // [NE][CB_FR_FRAME]
+    double *xfr;         // [NE][6]
+    double *efFE;        // [NE][14]
+};
+struct CbGenTruss {
+    double *frame;       // [NE][CB_TR_FRAME]
+};
+
+// everything a kernel needs, passed by value
+struct CbDev {
+    long NJ, NEQ;
+    long NE_TR, NE_FR, NE_SH, NE_BR;
+    int ANAFLAG;
+    // nodes
+    const int32_t *jc;       // [NJ][8]
+    // shells
+    const int32_t *sh_nodes; // [NE][4] 0-based
+    const double *sh_const;  // [NE][CB_SH_CONST]
+    const double *sh_keb;    // [NE][81]
+    double *sh_Nm;           // [NE][4] membrane force resultants for the geometric stiffness
+    double *sh_fg;           // [NE][18] element force in global axes (staging for the gather)
+    // frames
+    const int32_t *fr_nodes; // [NE][2]
+    const double *fr_const;  // [NE][CB_FR_CONST]
+    const double *fr_offset; // [NE][6]
+    const int32_t *fr_osflag;
+    const int32_t *fr_mendrel; // [NE][5]
+    const double *fr_efFE_ref; // [NE][14]
+    double *fr_fg;           // [NE][14]
+    // trusses
+    const int32_t *tr_nodes; // [NE][2]
+    const double *tr_const;  // [NE][CB_TR_CONST]
+    double *tr_fg;           // [NE][6]
+    // bricks
+    const int32_t *br_nodes; // [NE][8]
+    const double *br_const;  // [NE][4]  E, nu, rho, pad
+};
+
+// ---- host launch wrappers implemented in the .cu files ------------------------------------
+struct CbStiffArgs {
+    CbDev d;
+    const double *x;         // coordinates the stiffness is evaluated at (x_temp or x)
+    const double *sh_frame;  // [NE][CB_SH_FRAME] generation read
+    const double *sh_ef;     // unused for ANAFLAG<=2 shells
+    const double *fr_frame, *fr_ef, *fr_efFE;
+    const double *tr_frame, *tr_ef;
+    const CbPair *pairs; long npairs;
+    const CbContrib *contribs;
+    double *out;             // Ax or ss
+    const long *maxa;        // device copy (skyline mode) or nullptr
+    int skyline;
+};
+
+struct CbForceArgs {
+    CbDev d;
+    double *x_temp, *x_ip;
+    const double *dd;        // [NEQ] device
+    // shells
+    const double *sh_frame_ip; double *sh_frame_i; double *sh_dsl_i;
+    const double *sh_ef_ip; double *sh_ef_i;
+    // frames
+    const double *fr_frame_ip; double *fr_frame_i; double *fr_xfr_i;
+    const double *fr_ef_ip; double *fr_ef_i;
+    const double *fr_efFE_ip; double *fr_efFE_i;
+    // trusses
+    double *tr_frame_i; double *tr_ef_i;
+    double dlpf; int itecnt;
+    // gather
+    const int32_t *node_cstart; const CbCorner *corners;
+    double *f_temp;
+};
+
+#ifdef __cplusplus
+extern "C++" {
+#endif
+// cb_forces.cu  (compiled with -fmad=false: reference operation order, IEEE mul/add)
+int cbk_shell_init_keb(const CbDev &d, double *keb_out, cudaStream_t s);
+int cbk_shell_prep(const CbDev &d, const double *x, const double *sh_frame, cudaStream_t s);
+int cbk_node_update(const CbForceArgs &a, cudaStream_t s);
+int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches);
+int cbk_forces_linear(const CbForceArgs &a, const double *d_total, cudaStream_t s, long *launches);
+int cbk_gather_f(const CbForceArgs &a, cudaStream_t s);
+int cbk_mass(const CbDev &d, const double *x, double *sh_const_mut, double *tr_const_mut,
+             double *fr_const_mut, double *fr_xfr, const double *dens_tr, const double *dens_fr,
+             const double *dens_sh, const int32_t *node_cstart, const CbCorner *corners,
+             double *sm, cudaStream_t s, long *launches);
+// cb_stiff.cu  (FMA contraction allowed)
+int cbk_stiff(const CbStiffArgs &a, cudaStream_t s, long *launches);
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,244 @@
+"""cubens_b200 - Python face of the C-ABI in include/cubens_b200.h (ctypes, no torch types).
+
+The reference is C and so is the real host (cu-bens_b200/host/); this module is
+what bench.py and the tests drive: it loads the in-tree ``libcubens_b200.so`` (hand-written
+sm_100a kernels), mirrors the reference's call sequence with the reference's names, and FAILS
+LOUDLY if the library or a CUDA device is missing - there is no CPU path behind it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+from .model import Model  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "libcubens_b200.so"))
+
+CB_GEN_IP, CB_GEN_COMMITTED = 0, 1
+CB_MAT_CSC, CB_MAT_SKYLINE, CB_MAT_BOTH = 1, 2, 3
+
+ARR = dict(X=1, X_TEMP=2, X_IP=3, C1=4, C2=5, C3=6, C1_I=7, C2_I=8, C3_I=9, C1_IP=10, C2_IP=11,
+           C3_IP=12, EF=13, EF_I=14, EF_IP=15, DEFLLEN=16, DEFLLEN_I=17, DEFLLEN_IP=18,
+           DEFFAREA=19, DEFFAREA_I=20, DEFFAREA_IP=21, DEFSLEN=22, DEFSLEN_I=23, DEFSLEN_IP=24,
+           XFR=25, XFR_TEMP=26, EFFE=27, EFFE_I=28, EFFE_IP=29, D=30, D_TEMP=31, F=32, F_TEMP=33,
+           LLENGTH=34, FAREA=35, SLENGTH=36)
+
+EXPORTS = [
+    "cb_abi_version", "cb_last_error", "cb_device_count", "cb_create", "cb_destroy",
+    "cb_set_owned_joints", "cb_begin_increment", "cb_stiff", "cb_mass", "cb_update_forces",
+    "cb_update_forces_dev", "cb_forces_linear", "cb_end_iteration", "cb_commit",
+    "cb_get_skyline", "cb_csc_nnz", "cb_csc_pattern", "cb_get_csc_values", "cb_csc_compact",
+    "cb_get_mass", "cb_get_f", "cb_dev_Ax", "cb_dev_skyline", "cb_dev_f", "cb_dev_dd",
+    "cb_dev_Ap", "cb_dev_Ai", "cb_download", "cb_upload", "cb_launch_count",
+    "cb_last_stiff_ms", "cb_last_forces_ms", "cb_map_bytes", "cb_sync", "cb_stream",
+]
+
+
+class cb_sizes(C.Structure):
+    _fields_ = [(n, C.c_long) for n in ("NJ", "NE_TR", "NE_FR", "NE_SH", "NE_SBR", "NE_FBR", "NEQ")]
+
+
+class cb_flags(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("ANAFLAG", "ALGFLAG", "SLVFLAG", "matrix_layout", "device")]
+
+
+_MODEL_FIELDS = ["x", "minc", "jcode", "mcode", "maxa", "emod", "dens", "carea", "llength", "c1",
+                 "c2", "c3", "nu", "thick", "farea", "slength", "xlocal", "gmod", "istrong",
+                 "iweak", "ipolar", "iwarp", "auxpt", "offset", "osflag", "mendrel", "efFE_ref"]
+
+
+class cb_model(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _MODEL_FIELDS]
+
+
+class CubensError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the CUDA library.  Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise CubensError(f"{path} not found - build it with `make -C cu-bens_b200` "
+                          "(or __graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(path)
+    lib.cb_last_error.restype = C.c_char_p
+    lib.cb_csc_nnz.restype = C.c_long
+    lib.cb_csc_compact.restype = C.c_long
+    lib.cb_launch_count.restype = C.c_long
+    lib.cb_map_bytes.restype = C.c_long
+    lib.cb_last_stiff_ms.restype = C.c_double
+    lib.cb_last_forces_ms.restype = C.c_double
+    for n in ("cb_dev_Ax", "cb_dev_skyline", "cb_dev_f", "cb_dev_dd", "cb_dev_Ap", "cb_dev_Ai",
+              "cb_stream"):
+        getattr(lib, n).restype = C.c_void_p
+    lib.cb_destroy.restype = None
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data) if a is not None and a.size else C.c_void_p(0)
+
+
+class Assembler:
+    """One model resident on one B200.  Method names follow the reference call sites they
+    replace (see include/cubens_b200.h for the file:line table)."""
+
+    def __init__(self, m, layout=0, device=0):
+        self.lib = load_library()
+        self.m = m
+        if self.lib.cb_device_count() <= 0:
+            raise CubensError("no CUDA device visible - the element/assembly path has no CPU fallback")
+        sz = cb_sizes(m.NJ, m.NE_TR, m.NE_FR, m.NE_SH, m.NE_SBR, m.NE_FBR, m.NEQ)
+        fl = cb_flags(m.ANAFLAG, m.ALGFLAG, m.SLVFLAG, layout, device)
+        keep = {}
+        cm = cb_model()
+        for n in _MODEL_FIELDS:
+            a = getattr(m, n, None)
+            if a is not None:
+                dt = np.int32 if n in ("osflag", "mendrel") else (np.int64 if n in ("minc", "jcode", "mcode", "maxa") else np.float64)
+                a = np.ascontiguousarray(a, dtype=dt)
+                keep[n] = a
+            setattr(cm, n, _p(a) if a is not None else C.c_void_p(0))
+        h = C.c_void_p(0)
+        rc = self.lib.cb_create(C.byref(sz), C.byref(fl), C.byref(cm), C.byref(h))
+        self._check(rc)
+        self.h = h
+        self.layout = layout if layout else (CB_MAT_SKYLINE if m.SLVFLAG == 0 else CB_MAT_CSC)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CubensError(f"cubens_b200 error {rc}: {self.lib.cb_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- main.c loop mirror ---------------------------------------------------------------
+    def set_owned_joints(self, j0, j1):
+        self._check(self.lib.cb_set_owned_joints(self.h, C.c_long(j0), C.c_long(j1)))
+
+    def begin_increment(self):
+        self._check(self.lib.cb_begin_increment(self.h))
+
+    def stiff(self, gen=CB_GEN_IP):
+        self._check(self.lib.cb_stiff(self.h, C.c_int(gen)))
+
+    def mass(self):
+        self._check(self.lib.cb_mass(self.h))
+        sm = np.zeros(self.m.NEQ)
+        self._check(self.lib.cb_get_mass(self.h, _p(sm)))
+        return sm
+
+    def update_forces(self, dd, dlpf=1.0, itecnt=0, want_f=True):
+        dd = np.ascontiguousarray(dd, dtype=np.float64)
+        f = np.zeros(self.m.NEQ) if want_f else None
+        cdl = C.c_double(dlpf); fr = C.c_int(0); sh = C.c_int(0)
+        self._check(self.lib.cb_update_forces(self.h, _p(dd), C.byref(cdl), C.c_int(itecnt),
+                                              _p(f) if want_f else C.c_void_p(0), C.byref(fr),
+                                              C.byref(sh)))
+        return f, fr.value, sh.value, cdl.value
+
+    def update_forces_dev(self, dlpf=1.0, itecnt=0):
+        """dd already resident in the device buffer cb_dev_dd(); f_temp stays on the device."""
+        cdl = C.c_double(dlpf); fr = C.c_int(0); sh = C.c_int(0)
+        self._check(self.lib.cb_update_forces_dev(self.h, C.c_void_p(self.lib.cb_dev_dd(self.h)),
+                                                  C.byref(cdl), C.c_int(itecnt), C.byref(fr),
+                                                  C.byref(sh)))
+        return fr.value, sh.value
+
+    def forces_linear(self, d):
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        f = np.zeros(self.m.NEQ)
+        self._check(self.lib.cb_forces_linear(self.h, _p(d), _p(f)))
+        return f
+
+    def end_iteration(self):
+        self._check(self.lib.cb_end_iteration(self.h))
+
+    def commit(self):
+        self._check(self.lib.cb_commit(self.h))
+
+    # ---- results --------------------------------------------------------------------------
+    def skyline(self):
+        ss = np.zeros(self.m.lss)
+        self._check(self.lib.cb_get_skyline(self.h, _p(ss), C.c_long(ss.size)))
+        return ss
+
+    def csc(self):
+        nnz = self.lib.cb_csc_nnz(self.h)
+        if nnz < 0:
+            raise CubensError(self.lib.cb_last_error().decode())
+        Ap = np.zeros(self.m.NEQ + 1, dtype=np.int32); Ai = np.zeros(nnz, dtype=np.int32)
+        Ax = np.zeros(nnz)
+        self._check(self.lib.cb_csc_pattern(self.h, _p(Ap), _p(Ai)))
+        self._check(self.lib.cb_get_csc_values(self.h, _p(Ax)))
+        return Ap, Ai, Ax
+
+    def csc_compact(self, drop_tol=1e-10):
+        nnz = self.lib.cb_csc_nnz(self.h)
+        Ap = np.zeros(self.m.NEQ + 1, dtype=np.int32); Ai = np.zeros(nnz, dtype=np.int32)
+        Ax = np.zeros(nnz)
+        nz = self.lib.cb_csc_compact(self.h, C.c_double(drop_tol), _p(Ap), _p(Ai), _p(Ax))
+        if nz < 0:
+            raise CubensError(self.lib.cb_last_error().decode())
+        return Ap, Ai[:nz].copy(), Ax[:nz].copy()
+
+    def download(self, name):
+        m = self.m
+        n = {"X": m.NJ * 3, "X_TEMP": m.NJ * 3, "X_IP": m.NJ * 3, "D": m.NEQ, "D_TEMP": m.NEQ,
+             "F": m.NEQ, "F_TEMP": m.NEQ, "LLENGTH": m.NE_TR + m.NE_FR, "FAREA": m.NE_SH,
+             "SLENGTH": 3 * m.NE_SH, "XFR": 6 * m.NE_FR, "XFR_TEMP": 6 * m.NE_FR}.get(name)
+        if n is None:
+            if name.startswith("C"):
+                n = m.n_c
+            elif name.startswith("EFFE"):
+                n = 14 * m.NE_FR
+            elif name.startswith("EF"):
+                n = m.n_ef
+            elif name.startswith("DEFLLEN"):
+                n = m.NE_TR + m.NE_FR
+            elif name.startswith("DEFFAREA"):
+                n = m.NE_SH
+            elif name.startswith("DEFSLEN"):
+                n = 3 * m.NE_SH
+        out = np.zeros(n)
+        self._check(self.lib.cb_download(self.h, C.c_int(ARR[name]), _p(out), C.c_long(n)))
+        return out
+
+    def upload(self, name, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        self._check(self.lib.cb_upload(self.h, C.c_int(ARR[name]), _p(a), C.c_long(a.size)))
+
+    # ---- instrumentation -------------------------------------------------------------------
+    @property
+    def launches(self):
+        return self.lib.cb_launch_count(self.h)
+
+    @property
+    def last_stiff_ms(self):
+        return self.lib.cb_last_stiff_ms(self.h)
+
+    @property
+    def last_forces_ms(self):
+        return self.lib.cb_last_forces_ms(self.h)
+
+    @property
+    def map_bytes(self):
+        return self.lib.cb_map_bytes(self.h)

@@ -1,0 +1,128 @@
+"""Synthetic meshes of the BASELINE.json shapes.
+
+plate_model    unit-square DKT plate, nx*ny cells, 2 triangles per cell (a,b,c),(a,c,d),
+               joints numbered ``nid(i,j) = i*(ny+1)+j+1`` (row-major along the short side),
+               all four edges pinned (DOF 1-3), centre point load -1000 in z; material of
+               Sample_Input_Files/model_def_5c_shell.txt:33 unless overridden.
+lattice_model  cubic n*n*n frame lattice, members along x, y, z, base plane clamped;
+               properties of Sample_Input_Files/model_def_5b_frame.txt:36.
+truss_model    the same lattice topology with 2-node trusses (pinned base).
+brick_model    nx*ny*nz 8-node bricks, base clamped (linear: stiff_br only).
+perturbation   the seeded dd ~ U(-1e-4,1e-4) of section 8(d), rng 20261017.
+"""
+from __future__ import annotations
+
+import numpy as np
+from .model import build_model, I64, F64
+
+SHELL_5C = (2.1e11, 0.3, 0.01, 8050.0, 3.45e8)      # E, nu, t, rho, fy
+# model_def_5b_frame.txt:36  E,G,rho,A,Iz,Iy,J,Cw ; :57 fy,Zz,Zy
+FRAME_5B = (29000.0, 11200.0, 7.34e-7, 9.13, 110.0, 37.1, 0.536, 0.0, 36.0, 24.7, 11.3)
+TRUSS_5A = (29000.0, 1.0, 7.34e-7, 36.0)            # E, A, rho, fy
+BRICK_DEF = (2.1e11, 0.3, 8050.0, 3.45e8)           # E, nu, rho, fy
+
+
+def plate_model(nx, ny, lx=1.0, ly=1.0, props=SHELL_5C, load=-1000.0, ANAFLAG=2, ALGFLAG=1,
+                SLVFLAG=0, pinned=True, z_bump=0.0):
+    i, j = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="ij")
+    xs = (i * (lx / nx)).astype(F64)
+    ys = (j * (ly / ny)).astype(F64)
+    zs = np.zeros_like(xs)
+    if z_bump:
+        zs = z_bump * np.sin(np.pi * xs / lx) * np.sin(np.pi * ys / ly)
+    x = np.stack([xs, ys, zs], axis=-1).reshape(-1)
+    nid = (i * (ny + 1) + j + 1).astype(I64)
+    a = nid[:-1, :-1]; b = nid[1:, :-1]; c = nid[1:, 1:]; d = nid[:-1, 1:]
+    t1 = np.stack([a, b, c], axis=-1)
+    t2 = np.stack([a, c, d], axis=-1)
+    shells = np.stack([t1, t2], axis=2).reshape(-1, 3)
+    fixed = []
+    if pinned:
+        edge = (i == 0) | (i == nx) | (j == 0) | (j == ny)
+        ej = nid[edge]
+        fixed = np.stack([np.repeat(ej, 3), np.tile(np.array([1, 2, 3], dtype=I64), ej.size)],
+                         axis=1)
+    centre = int(nid[nx // 2, ny // 2])
+    return build_model(x, shells=shells, fixed=fixed, shell_props=props,
+                       loads=[(centre, 3, load)], ANAFLAG=ANAFLAG, ALGFLAG=ALGFLAG,
+                       SLVFLAG=SLVFLAG, meta=dict(kind="plate", nx=nx, ny=ny, centre=centre))
+
+
+def _lattice(n, h=1.0):
+    g = np.arange(n)
+    i, j, k = np.meshgrid(g, g, g, indexing="ij")
+    nid = (i * n * n + j * n + k + 1).astype(I64)
+    x = np.stack([i * h, j * h, k * h], axis=-1).astype(F64).reshape(-1)
+    mx = np.stack([nid[:-1], nid[1:]], axis=-1).reshape(-1, 2)          # along x
+    my = np.stack([nid[:, :-1], nid[:, 1:]], axis=-1).reshape(-1, 2)    # along y
+    mz = np.stack([nid[:, :, :-1], nid[:, :, 1:]], axis=-1).reshape(-1, 2)  # along z
+    return x, nid, mx, my, mz
+
+
+def lattice_model(n, h=100.0, props=FRAME_5B, ANAFLAG=2, ALGFLAG=1, SLVFLAG=0, load=1.0):
+    x, nid, mx, my, mz = _lattice(n, h)
+    frames = np.concatenate([mx, my, mz])
+    X = x.reshape(-1, 3)
+    aux = X[frames[:, 0] - 1].copy()
+    aux[:len(mx)] += np.array([0.0, 1.0, 0.0]) * h
+    aux[len(mx):len(mx) + len(my)] += np.array([1.0, 0.0, 0.0]) * h
+    aux[len(mx) + len(my):] += np.array([0.0, 1.0, 0.0]) * h
+    base = nid[:, :, 0].reshape(-1)
+    fixed = np.stack([np.repeat(base, 7), np.tile(np.arange(1, 8, dtype=I64), base.size)], axis=1)
+    top = int(nid[n // 2, n // 2, n - 1])
+    return build_model(x, frames=frames, fixed=fixed, frame_props=props, frame_aux=aux,
+                       loads=[(top, 1, load)], ANAFLAG=ANAFLAG, ALGFLAG=ALGFLAG, SLVFLAG=SLVFLAG,
+                       meta=dict(kind="lattice", n=n, top=top))
+
+
+def truss_model(n, h=100.0, props=TRUSS_5A, ANAFLAG=2, ALGFLAG=1, SLVFLAG=0, load=1.0):
+    x, nid, mx, my, mz = _lattice(n, h)
+    # face diagonals in the xz and yz planes make the pin-jointed lattice stable
+    dxz = np.stack([nid[:-1, :, :-1], nid[1:, :, 1:]], axis=-1).reshape(-1, 2)
+    dyz = np.stack([nid[:, :-1, :-1], nid[:, 1:, 1:]], axis=-1).reshape(-1, 2)
+    dxy = np.stack([nid[:-1, :-1, :], nid[1:, 1:, :]], axis=-1).reshape(-1, 2)
+    trusses = np.concatenate([mx, my, mz, dxz, dyz, dxy])
+    base = nid[:, :, 0].reshape(-1)
+    fixed = np.stack([np.repeat(base, 3), np.tile(np.arange(1, 4, dtype=I64), base.size)], axis=1)
+    top = int(nid[n // 2, n // 2, n - 1])
+    return build_model(x, trusses=trusses, fixed=fixed, truss_props=props,
+                       loads=[(top, 1, load)], ANAFLAG=ANAFLAG, ALGFLAG=ALGFLAG, SLVFLAG=SLVFLAG,
+                       meta=dict(kind="truss", n=n, top=top))
+
+
+def brick_model(nx, ny, nz, h=1.0, props=BRICK_DEF, skin=False, shell_props=SHELL_5C,
+                SLVFLAG=2, distort=0.0, seed=7):
+    """nx*ny*nz hexahedra; node order per brick.c:199-315: local node n has natural
+    coordinates (r,s,t) signs (+,+,+),(-,+,+),(-,-,+),(+,-,+),(+,+,-),(-,+,-),(-,-,-),(+,-,-).
+    ``skin`` adds DKT shells on the top face sharing the brick joints (config 5 shape)."""
+    i, j, k = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    nid = (i * (ny + 1) * (nz + 1) + j * (nz + 1) + k + 1).astype(I64)
+    x = np.stack([i * h, j * h, k * h], axis=-1).astype(F64)
+    if distort:
+        rng = np.random.default_rng(seed)
+        x = x + distort * h * rng.uniform(-1, 1, size=x.shape)
+    x = x.reshape(-1)
+    lo, hi = slice(0, -1), slice(1, None)
+    sel = {(+1): hi, (-1): lo}
+    signs = [(1, 1, 1), (-1, 1, 1), (-1, -1, 1), (1, -1, 1), (1, 1, -1), (-1, 1, -1),
+             (-1, -1, -1), (1, -1, -1)]
+    bricks = np.stack([nid[sel[a], sel[b], sel[c]] for (a, b, c) in signs], axis=-1).reshape(-1, 8)
+    base = nid[:, :, 0].reshape(-1)
+    fixed = np.stack([np.repeat(base, 3), np.tile(np.arange(1, 4, dtype=I64), base.size)], axis=1)
+    shells = None
+    if skin:
+        top = nid[:, :, nz]
+        a = top[:-1, :-1]; b = top[1:, :-1]; c = top[1:, 1:]; d = top[:-1, 1:]
+        shells = np.stack([np.stack([a, b, c], -1), np.stack([a, c, d], -1)], axis=2).reshape(-1, 3)
+    corner = int(nid[nx, ny, nz])
+    return build_model(x, shells=shells, bricks=bricks, fixed=fixed, brick_props=props,
+                       shell_props=shell_props, loads=[(corner, 3, -1000.0)], ANAFLAG=1,
+                       ALGFLAG=1, SLVFLAG=SLVFLAG,
+                       meta=dict(kind="brick", nx=nx, ny=ny, nz=nz))
+
+
+def perturbation(model, scale=1e-4, seed=20261017):
+    """Seeded incremental displacement of SURVEY.md section 8(d): dd ~ U(-scale, scale) per
+    free DOF, numpy default_rng(20261017)."""
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-scale, scale, size=model.NEQ).astype(F64)

@@ -1,0 +1,194 @@
+/*
+ * cubens_b200.h - C-ABI of the B200-native element / assembly hot path of CU-BENs.
+ *
+ * The reference has no plugin or FFI layer: its boundary is the set of plain C routines of
+ * prototypes.h that main.c calls once per Newton iteration with 12-32 raw pointers each, all
+ * sizes and flags living in file-scope globals (main.c:323-328).  This header is the drop-in
+ * for exactly those call sites.  Every entry point is `extern "C"`, takes plain pointers and
+ * sizes in the reference's own host layout (1-based `long` joint/equation
+ * numbers, AoS xyz, per-type offsets inside the shared emod/c1/ef/mcode/minc arrays) and
+ * returns an int status; the caller keeps ownership of every host pointer.  INTEGRATION.md
+ * shows the edits to main.c / solve.c.
+ *
+ *   reference call (file:line)                         replacement
+ *   -------------------------------------------------  ---------------------------------------
+ *   main.c:491-1437 allocation + prop_* results         cb_create (uploads, builds the maps)
+ *   main.c:1833-1882 generation copies at increment     cb_begin_increment
+ *   main.c:1899-1921 ss=0; stiff_tr; stiff_fr; stiff_sh cb_stiff            (+ stiff_br, brick.c:79)
+ *       truss.c:82  frame.c:226  shell.c:110  misc.c:41
+ *   main.c:3590-3619 sm=0; mass_tr; mass_fr; mass_sh    cb_mass
+ *   main.c:1948-1984 d_temp+=dd; f_temp=0; updatc;      cb_update_forces
+ *       forces_tr; forces_fr; forces_sh; ef_ip=ef_i
+ *       misc.c:71  truss.c:231  frame.c:902  shell.c:1593
+ *   main.c:1774-1793 linear force recovery              cb_forces_linear
+ *   main.c:2006-2028 _ip <- _i                          cb_end_iteration
+ *   main.c:2074-2134 commit converged increment         cb_commit
+ *   solve.c:110-119  dense -> Ap/Ai/Ax scan             cb_csc_pattern / cb_get_csc_values /
+ *                                                       cb_csc_compact (device-assembled CSC)
+ *   ss[] skyline layout (model.c:1269-1278)             cb_get_skyline
+ *   output()/checkPoint() reads (misc.c:345,494)        cb_download / cb_upload
+ *
+ * There is NO CPU fallback: every compute entry point needs a CUDA device and returns
+ * CB_ERR_CUDA if none is usable.
+ */
+#ifndef CUBENS_B200_H
+#define CUBENS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_ABI_VERSION 1
+
+/* status codes (the reference uses 0 = ok / 1 = error, solve.c:558-562, frame.c:1201) */
+enum {
+    CB_OK = 0,
+    CB_ERR_ARG = 1,          /* bad argument / inconsistent sizes                         */
+    CB_ERR_CUDA = 2,         /* no device, allocation or launch failure                   */
+    CB_ERR_UNSUPPORTED = 3,  /* feature of the reference outside this build (see DESIGN)  */
+    CB_ERR_OVERFLOW = 4      /* a count does not fit the device's 32-bit indices          */
+};
+
+/* which generation of the updated-Lagrangian state a call reads */
+enum { CB_GEN_IP = 0, CB_GEN_COMMITTED = 1 };
+
+/* layout of the assembled tangent matrix */
+enum {
+    CB_MAT_CSC = 1,      /* full (unsymmetric-storage) CSC, structural node-block pattern  */
+    CB_MAT_SKYLINE = 2,  /* the reference's skyline vector ss[lss] addressed through maxa  */
+    CB_MAT_BOTH = 3
+};
+
+/* the sizes main.c reads from the deck (main.c:384-427) + NEQ from codes() (model.c:943) */
+typedef struct cb_sizes {
+    long NJ, NE_TR, NE_FR, NE_SH, NE_SBR, NE_FBR, NEQ;
+} cb_sizes;
+
+/* ANAFLAG 1 = first-order elastic, 2 = geometric nonlinear (main.c:63-90).  ANAFLAG 3
+ * (material nonlinear) and 4 (FSI) return CB_ERR_UNSUPPORTED from cb_create.            */
+typedef struct cb_flags {
+    int ANAFLAG, ALGFLAG, SLVFLAG;
+    int matrix_layout;      /* CB_MAT_*; 0 picks SKYLINE when SLVFLAG==0 else CSC          */
+    int device;             /* CUDA device ordinal                                         */
+} cb_flags;
+
+/* Host arrays exactly as main.c holds them after struc/codes/skylin/prop_* (App. A).
+ * Pointers for absent element types may be NULL.  All are read during cb_create only.    */
+typedef struct cb_model {
+    const double *x;         /* [NJ*3]                                main.c:491            */
+    const long   *minc;      /* [2TR+2FR+3SH+8BR] 1-based joints      model.c:95-137        */
+    const long   *jcode;     /* [NJ*7] 0 = fixed, else equation no.   model.c:941-987       */
+    const long   *mcode;     /* [6TR+14FR+18SH+24BR]                  model.c:992-1142      */
+    const long   *maxa;      /* [NEQ+1] (skyline layouts only)        model.c:1269-1278     */
+    const double *emod;      /* [TR+FR+SH+BR]                                               */
+    const double *dens;      /* [TR+FR+SH+BR], indexed [n] per type like the reference      */
+    const double *carea;     /* [TR+FR]                                                     */
+    const double *llength;   /* [TR+FR]   initial lengths from prop_tr / prop_fr            */
+    const double *c1, *c2, *c3;   /* [TR+3FR+3SH] initial direction cosines                 */
+    /* shells (prop_sh, shell.c:43-108) */
+    const double *nu;        /* [SH+BR]                                                     */
+    const double *thick;     /* [SH]                                                        */
+    const double *farea;     /* [SH]                                                        */
+    const double *slength;   /* [SH*3]                                                      */
+    const double *xlocal;    /* [SH*3]                                                      */
+    /* frames (prop_fr, frame.c:43-224) */
+    const double *gmod, *istrong, *iweak, *ipolar, *iwarp;   /* [FR]                        */
+    const double *auxpt;     /* [FR*3]                                                      */
+    const double *offset;    /* [FR*6]                                                      */
+    const int    *osflag;    /* [FR]                                                        */
+    const int    *mendrel;   /* [FR*5]                                                      */
+    const double *efFE_ref;  /* [FR*14] reference fixed-end forces from load()              */
+} cb_model;
+
+typedef struct cb_handle cb_handle;
+
+/* ---- life cycle ---------------------------------------------------------------------- */
+int  cb_abi_version(void);
+const char *cb_last_error(void);                 /* text of the last failure on this thread */
+int  cb_device_count(void);                      /* 0 when no CUDA device is usable         */
+
+int  cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model *m, cb_handle **out);
+void cb_destroy(cb_handle *h);
+
+/* Multi-GPU: each rank creates its handle from a sub-model that keeps the GLOBAL
+ * joint / equation numbering (NJ, NEQ, jcode, x) but only the elements of its partition plus
+ * the halo elements that touch its owned joints.  cb_set_owned_joints then restricts the
+ * assembled matrix columns, the mass and the f_int gather to joints [j0, j1) (0-based), so the
+ * owned column slice is complete without any exchange of matrix entries.  Must be called
+ * before the first cb_stiff / cb_update_forces.  Default: all joints.                       */
+int  cb_set_owned_joints(cb_handle *h, long j0, long j1);
+
+/* ---- the Newton-iteration hot path ---------------------------------------------------- */
+int  cb_begin_increment(cb_handle *h);                                /* main.c:1833-1882  */
+int  cb_stiff(cb_handle *h, int gen);                                 /* main.c:1899-1921  */
+int  cb_mass(cb_handle *h);                                           /* main.c:3590-3619  */
+/* dd: host [NEQ] incremental displacements from solve().  f_temp_out (may be NULL): host
+ * [NEQ] internal force vector.  dlpf_inout / itecnt as forces_fr takes them (frame.c:908);
+ * frcchk_fr / frcchk_sh receive the routines' return codes (0 for ANAFLAG 1, 2).          */
+int  cb_update_forces(cb_handle *h, const double *dd, double *dlpf_inout, int itecnt,
+                      double *f_temp_out, int *frcchk_fr, int *frcchk_sh);
+/* same with dd / f_temp already resident on the device (no PCIe traffic)                  */
+int  cb_update_forces_dev(cb_handle *h, const double *dd_dev, double *dlpf_inout, int itecnt,
+                          int *frcchk_fr, int *frcchk_sh);
+int  cb_forces_linear(cb_handle *h, const double *d, double *f_out);  /* main.c:1774-1793  */
+int  cb_end_iteration(cb_handle *h);                                  /* main.c:2006-2028  */
+int  cb_commit(cb_handle *h);                                         /* main.c:2074-2134  */
+
+/* ---- results -------------------------------------------------------------------------- */
+/* skyline vector in the reference's layout; n must equal lss = maxa[NEQ]-1                */
+int  cb_get_skyline(cb_handle *h, double *ss, long n);
+/* structural CSC: nnz, then pattern (int Ap[NEQ+1], Ai[nnz], 0-based as umfpack_di_*      */
+/* expects) and values Ax[nnz]                                                             */
+long cb_csc_nnz(cb_handle *h);
+int  cb_csc_pattern(cb_handle *h, int *Ap, int *Ai);
+int  cb_get_csc_values(cb_handle *h, double *Ax);
+/* value-thresholded copy with the reference's rule fabs(a) > drop_tol (solve.c:112);      */
+/* returns the compacted nnz (Ap/Ai/Ax sized for cb_csc_nnz), or -1                        */
+long cb_csc_compact(cb_handle *h, double drop_tol, int *Ap, int *Ai, double *Ax);
+int  cb_get_mass(cb_handle *h, double *sm_diag);       /* diagonal [NEQ], SLVFLAG 0 layout */
+int  cb_get_f(cb_handle *h, double *f_temp);           /* [NEQ]                            */
+
+/* device-resident views for consumers that stay on the GPU (no copies): */
+double *cb_dev_Ax(cb_handle *h);
+double *cb_dev_skyline(cb_handle *h);
+double *cb_dev_f(cb_handle *h);
+double *cb_dev_dd(cb_handle *h);
+const int *cb_dev_Ap(cb_handle *h);
+const int *cb_dev_Ai(cb_handle *h);       /* built lazily on first use                     */
+
+/* ---- state transfer for output()/checkPoint()/restartStep() (misc.c:345,494,605) ------ */
+enum {
+    CB_ARR_X = 1, CB_ARR_X_TEMP, CB_ARR_X_IP,
+    CB_ARR_C1, CB_ARR_C2, CB_ARR_C3,                 /* committed                            */
+    CB_ARR_C1_I, CB_ARR_C2_I, CB_ARR_C3_I,
+    CB_ARR_C1_IP, CB_ARR_C2_IP, CB_ARR_C3_IP,
+    CB_ARR_EF, CB_ARR_EF_I, CB_ARR_EF_IP,
+    CB_ARR_DEFLLEN, CB_ARR_DEFLLEN_I, CB_ARR_DEFLLEN_IP,
+    CB_ARR_DEFFAREA, CB_ARR_DEFFAREA_I, CB_ARR_DEFFAREA_IP,
+    CB_ARR_DEFSLEN, CB_ARR_DEFSLEN_I, CB_ARR_DEFSLEN_IP,
+    CB_ARR_XFR, CB_ARR_XFR_TEMP,
+    CB_ARR_EFFE, CB_ARR_EFFE_I, CB_ARR_EFFE_IP,
+    CB_ARR_D, CB_ARR_D_TEMP, CB_ARR_F, CB_ARR_F_TEMP,
+    CB_ARR_LLENGTH, CB_ARR_FAREA, CB_ARR_SLENGTH     /* mass_* overwrite these (App. B.5)    */
+};
+/* n = number of doubles of the reference array (checked) */
+int  cb_download(cb_handle *h, int which, double *dst, long n);
+int  cb_upload(cb_handle *h, int which, const double *src, long n);
+
+/* ---- instrumentation ------------------------------------------------------------------- */
+/* kernels launched by this handle since creation (bench.py's gpu_launches)                 */
+long cb_launch_count(cb_handle *h);
+/* CUDA-event time in ms of the most recent cb_stiff / cb_update_forces* device work        */
+double cb_last_stiff_ms(cb_handle *h);
+double cb_last_forces_ms(cb_handle *h);
+/* bytes of implementation-only maps read per cb_stiff (reported next to the roofline)      */
+long cb_map_bytes(cb_handle *h);
+/* block the host until all work queued on this handle's stream has finished                */
+int  cb_sync(cb_handle *h);
+/* the CUDA stream (cudaStream_t cast to void*) all of this handle's kernels run on         */
+void *cb_stream(cb_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUBENS_B200_H */

@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py - BASELINE.json's metric on BASELINE.json's config.
+
+metric   elements assembled / s (K_t + f_int); ms_per_step = per-Newton-iteration assembly ms
+workload configs[2]: synthetic 1000x1000 DKT shell plate, 2 000 000 triangles, NEQ 6 000 006,
+         geometric nonlinear (ANAFLAG 2), state perturbed by the seeded dd of SURVEY.md 8(d)
+step     one Newton-iteration assembly = `ss=0; stiff_sh` + `updatc; f_temp=0; forces_sh;
+         ef_ip=ef_i; _ip=_i`  (main.c:1897-2028 minus solve() and test())
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 1000]
+
+One JSON line on stdout (rank 0).  `value` is device-resident (dd / f_temp / CSC stay in HBM),
+`e2e` goes through the C-ABI with host buffers: dd host->device, f_temp and the CSC values
+device->host every step (what the reference's host-side solve() consumes).  The CPU baseline and
+`--impl reference` time the UNMODIFIED reference routines (oracle/_ref, compiled from
+/root/reference by oracle/Makefile) on all host cores over a bounded sample of the same mesh.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "cu-bens_b200", "python"))
+
+ALG_BYTES_KT = 1192.0     # algorithmic HBM bytes per DKT element, K_t pass
+ALG_BYTES_FINT = 654.0    # f_int pass
+METRIC = "elements assembled/sec (K_t+f_int)"
+UNIT = "elements/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the unmodified reference on a bounded sample (strips of the same plate)
+# ------------------------------------------------------------------------------------------
+SAMPLE_NX, SAMPLE_NY = 1000, 2           # one strip: 1000 x 2 cells = 4000 triangles
+
+
+def _cpu_worker(args):
+    """time `reps` Newton-iteration assemblies of one strip with the reference routines"""
+    wid, reps, warm, cell = args
+    from oracle import refbind as R
+    from cubens_b200 import meshgen
+    m = meshgen.plate_model(SAMPLE_NX, SAMPLE_NY, lx=SAMPLE_NX * cell, ly=SAMPLE_NY * cell)
+    s = R.RefState(m)
+    s.begin_increment()
+    dd = meshgen.perturbation(m, seed=20261017 + wid)
+    R.update_forces(m, s, dd); s.end_iteration()
+    small = dd * 1e-3
+    ts = []
+    for it in range(warm + reps):
+        t0 = time.perf_counter()
+        R.stiff(m, s, SLVFLAG=0)                 # ss=0 ; stiff_sh (skyline scatter)
+        R.update_forces(m, s, small)             # updatc ; forces_sh ; ef_ip=ef_i
+        s.end_iteration()                        # _ip <- _i
+        ts.append(time.perf_counter() - t0)
+    return m.NE_SH, ts[warm:]
+
+
+def cpu_sample(steps, warmup, cell, cores=None):
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(w, steps, warmup, cell) for w in range(cores)])
+        wall = time.perf_counter() - t0
+    ne = res[0][0]
+    per_step = np.max(np.array([r[1] for r in res]), axis=0)      # slowest core per step
+    total = float(per_step.sum())
+    value = cores * ne * steps / total
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{cores} independent {SAMPLE_NX}x{SAMPLE_NY}-cell strips of the same plate "
+                      f"({ne} DKT shells each, chunk-local skyline), {steps} Newton-iteration "
+                      f"assemblies per core, unmodified stiff_sh+updatc+forces_sh at gcc -O2",
+            "ms_per_step": 1e3 * total / steps, "wall_s": wall,
+            "per_core_elements_per_s": ne * steps / total}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import refbind as R
+    if not R.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libcubens_ref.so not built"}))
+        return
+    cell = 1.0 / a.n
+    r = cpu_sample(a.steps, a.warmup, cell)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"synthetic {a.n}x{a.n} DKT shell plate ({2 * a.n * a.n} elements) "
+                                   "geometric-nonlinear Newton: bounded sample, see cpu_baseline.sample"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def partition_rows(n, world, rank):
+    """contiguous strips of cell rows (along i); returns (i0, i1)"""
+    per = n // world
+    i0 = rank * per
+    i1 = n if rank == world - 1 else i0 + per
+    return i0, i1
+
+
+def run_gpu(a):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+
+    # CPU baseline first (rank 0, N=1 only): fork before any CUDA context exists in this process
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        from oracle import refbind as R
+        if R.available():
+            cpu = cpu_sample(a.cpu_steps, 1, 1.0 / a.n)
+
+    import cubens_b200 as cb
+    from cubens_b200 import meshgen
+    from cubens_b200.partition import plate_partition
+
+    n = a.n
+    if world == 1:
+        m = meshgen.plate_model(n, n, SLVFLAG=2)
+        owned = None
+        n_local = m.NE_SH
+    else:
+        m, owned, n_local = plate_partition(n, n, world, rank, weak=not a.strong)
+    asm = cb.Assembler(m, layout=cb.CB_MAT_CSC, device=local)
+    if owned is not None:
+        asm.set_owned_joints(*owned)
+    # seeded perturbation so the plate is no longer flat and every local entry is non-zero
+    full_dd = meshgen.perturbation(m)
+    asm.begin_increment()
+    asm.update_forces(full_dd, want_f=False)
+    asm.end_iteration()
+    step_dd = full_dd * 1e-3
+    asm.set_dd(step_dd)
+    nnz = asm.lib.cb_csc_nnz(asm.h)
+
+    exchange = None
+    if world > 1:
+        from cubens_b200.partition import InterfaceExchange
+        exchange = InterfaceExchange(asm, m, world, rank, dist, owned)
+
+    def step():
+        asm.stiff()                      # K_t  -> device CSC
+        asm.update_forces_dev()          # updatc + f_int -> device f_temp
+        if exchange is not None:
+            exchange.reduce()            # interface residual sums over NVLink (NCCL)
+        asm.end_iteration()
+
+    def barrier():
+        asm.sync()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    barrier()
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    l0 = asm.launches
+    asm_ms, st_ms, fo_ms = [], [], []
+    barrier()
+    asm.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+        if a.detail:
+            asm_ms.append(asm.last_assemble_ms); st_ms.append(asm.last_stiff_ms)
+            fo_ms.append(asm.last_forces_ms)
+    dev_ms = asm.timer_stop_ms()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    launches = asm.launches - l0
+    clk = clocks.stop() if rank == 0 else None
+
+    # per-kernel split (separate short loop so the event reads do not stall the timed region)
+    for _ in range(5):
+        asm.stiff(); asm_ms.append(asm.last_assemble_ms); st_ms.append(asm.last_stiff_ms)
+        asm.update_forces_dev(); fo_ms.append(asm.last_forces_ms)
+        asm.end_iteration()
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_ms, wall_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms = float(t[0]), float(t[1])
+        cnt = torch.tensor([float(n_local), float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        total_el, launches = int(cnt[0]), int(cnt[1])
+    else:
+        total_el = n_local
+    ms_step = dev_ms / a.steps
+    value = total_el / (ms_step * 1e-3)
+
+    # ---- e2e through the C-ABI with host buffers (N=1: dd H2D, f_temp + CSC values D2H) -------
+    e2e = None
+    if world == 1:
+        hdd = asm.pinned(m.NEQ); hdd[:] = step_dd
+        hf = asm.pinned(m.NEQ)
+        hAx = asm.pinned(nnz)
+        import ctypes as C
+        lib = asm.lib
+
+        def e2e_step():
+            asm.stiff()
+            rc = lib.cb_get_csc_values(asm.h, C.c_void_p(hAx.ctypes.data)); assert rc == 0
+            cdl = C.c_double(1.0); fr = C.c_int(0); sh = C.c_int(0)
+            rc = lib.cb_update_forces(asm.h, C.c_void_p(hdd.ctypes.data), C.byref(cdl), C.c_int(0),
+                                      C.c_void_p(hf.ctypes.data), C.byref(fr), C.byref(sh))
+            assert rc == 0
+            asm.end_iteration()
+
+        e2e_step()
+        asm.sync()
+        ke = max(3, min(a.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            e2e_step()
+        asm.sync()
+        e_ms = 1e3 * (time.perf_counter() - t0) / ke
+        e2e = {"value": total_el / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
+               "h2d_bytes_per_step": int(m.NEQ * 8), "d2h_bytes_per_step": int(m.NEQ * 8 + nnz * 8),
+               "note": "dd pinned host->device; f_temp and all CSC values device->pinned host each "
+                       "step (what the host-side solve() consumes); steps=%d" % ke}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peak()
+    k_ms = float(np.median(asm_ms))
+    ach = ALG_BYTES_KT * n_local / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("k_assemble_blocks_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong" if (world > 1 and a.strong) else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic {n}x{n}-cell DKT shell plate per GPU ({total_el} elements "
+                               f"in total, NEQ {m.NEQ}) geometric-nonlinear Newton-iteration "
+                               "assembly (BASELINE.json configs[2])",
+                   "matrix": f"device CSC, nnz {nnz} per rank", "parallelism": f"element-partition x{world}",
+                   "l2": "inputs and outputs (2 GB CSC + 1.7 GB element state per GPU) exceed the 126 MB L2",
+                   "seed": 20261017},
+        "clocks": clk, "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / a.steps,
+        "split_ms": {"stiff_total": float(np.median(st_ms)), "assemble_kernel": k_ms,
+                     "update_forces": float(np.median(fo_ms))},
+        "roofline": {"kernel": "k_assemble_blocks", "bound": "hbm", "achieved": ach, "peak": peak,
+                     "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                     "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": ALG_BYTES_KT * n_local,
+                     "whole_step_frac": (ALG_BYTES_KT + ALG_BYTES_FINT) * n_local / (ms_step * 1e-3) / 1e9 / peak,
+                     "map_bytes_per_launch": asm.map_bytes},
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if cpu is not None:
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native")
+    ap.add_argument("--n", type=int, default=1000, help="plate cells per side (1000 = BASELINE)")
+    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--detail", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="N>1: split ONE n x n plate across the ranks (default: weak scaling, every "
+                         "rank owns an n x n-cell strip of an (n*N) x n plate)")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_gpu(a)
+
+
+if __name__ == "__main__":
+    main()

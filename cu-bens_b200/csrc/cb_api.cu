@@ -78,9 +78,11 @@ struct cb_handle {
     long NE_BR = 0;
     int layout = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
+    cudaEvent_t evA = nullptr, evB = nullptr;     // user timer (cb_timer_start/stop)
+    bool stiff_timed = false, forces_timed = false;
     long launches = 0;
-    double last_stiff_ms = 0, last_forces_ms = 0;
+    double last_stiff_ms = 0, last_forces_ms = 0, last_assemble_ms = 0;
     long j0 = 0, j1 = 0;          // owned joints
     bool plan_ready = false;
     bool keb_dirty = true;
@@ -206,7 +208,10 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
 
 #define BAIL(code) do { int c_ = (code); cb_destroy(h); return c_; } while (0)
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+        cudaEventCreate(&h->ev2) != cudaSuccess || cudaEventCreate(&h->ev3) != cudaSuccess ||
+        cudaEventCreate(&h->ev4) != cudaSuccess || cudaEventCreate(&h->ev5) != cudaSuccess ||
+        cudaEventCreate(&h->evA) != cudaSuccess || cudaEventCreate(&h->evB) != cudaSuccess)
         BAIL(fail(CB_ERR_CUDA, "stream/event creation failed"));
 
     // ---- joints ---------------------------------------------------------------------------
@@ -353,6 +358,12 @@ extern "C" void cb_destroy(cb_handle *h)
     h->plan_sky.pairs.release(); h->Ap.release(); h->Ai.release(); h->maxa.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
+    if (h->ev3) cudaEventDestroy(h->ev3);
+    if (h->ev4) cudaEventDestroy(h->ev4);
+    if (h->ev5) cudaEventDestroy(h->ev5);
+    if (h->evA) cudaEventDestroy(h->evA);
+    if (h->evB) cudaEventDestroy(h->evB);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -490,6 +501,8 @@ static int build_plan(cb_handle *h)
     }
     h->map_bytes = (long)((pairs_csc.size() + pairs_sky.size()) * sizeof(CbPair) +
                           contribs.size() * sizeof(CbContrib));
+    // uploads above went through the legacy default stream; the handle's stream is non-blocking
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(CB_ERR_CUDA, "sync after map upload");
     h->plan_ready = true;
     return CB_OK;
 }
@@ -578,19 +591,20 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
         if (cbk_shell_prep(a.d, a.x, a.sh_frame, h->stream)) return fail(CB_ERR_CUDA, "prep launch");
         ++h->launches;
     }
+    CUDA_TRY(cudaEventRecord(h->ev2, h->stream));
     if (h->layout & CB_MAT_CSC) {
         a.pairs = h->plan_csc.pairs.p; a.npairs = h->plan_csc.npairs;
         a.out = h->Ax.p; a.skyline = 0; a.maxa = nullptr;
         if (cbk_stiff(a, h->stream, &h->launches)) return fail(CB_ERR_CUDA, "assembly launch");
     }
+    CUDA_TRY(cudaEventRecord(h->ev3, h->stream));
     if (h->layout & CB_MAT_SKYLINE) {
         a.pairs = h->plan_sky.pairs.p; a.npairs = h->plan_sky.npairs;
         a.out = h->ss.p; a.skyline = 1; a.maxa = h->maxa.p;
         if (cbk_stiff(a, h->stream, &h->launches)) return fail(CB_ERR_CUDA, "assembly launch");
     }
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->last_stiff_ms = ms;
+    h->stiff_timed = true;
     return CB_OK;
 }
 
@@ -630,7 +644,7 @@ extern "C" int cb_update_forces_dev(cb_handle *h, const double *dd_dev, double *
     CbForceArgs a = force_args(h);
     if (dd_dev && dd_dev != h->dd.p) { if (d2d(h->dd.p, dd_dev, h->sz.NEQ, s)) return fail(CB_ERR_CUDA, "dd copy"); }
     a.dlpf = dlpf_inout ? *dlpf_inout : 0.0; a.itecnt = itecnt;
-    CUDA_TRY(cudaEventRecord(h->ev0, s));
+    CUDA_TRY(cudaEventRecord(h->ev4, s));
     {   // d_temp += dd (main.c:1949)
         unsigned g = (unsigned)((h->sz.NEQ + 255) / 256);
         k_axpy1<<<g, 256, 0, s>>>(h->sz.NEQ, h->dd.p, h->d_temp.p); ++h->launches;
@@ -640,10 +654,9 @@ extern "C" int cb_update_forces_dev(cb_handle *h, const double *dd_dev, double *
     if (cbk_forces(a, s, &h->launches)) return fail(CB_ERR_CUDA, "forces launch");
     if (cbk_gather_f(a, s)) return fail(CB_ERR_CUDA, "gather launch");
     ++h->launches;
-    CUDA_TRY(cudaEventRecord(h->ev1, s));
+    CUDA_TRY(cudaEventRecord(h->ev5, s));
     std::swap(h->eP, h->eN);                      // ef_ip <- ef_i (main.c:1982-1984) by renaming
-    CUDA_TRY(cudaStreamSynchronize(s));
-    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->last_forces_ms = ms;
+    h->forces_timed = true;
     return CB_OK;
 }
 
@@ -657,8 +670,9 @@ extern "C" int cb_update_forces(cb_handle *h, const double *dd, double *dlpf_ino
     int rc = cb_update_forces_dev(h, h->dd.p, dlpf_inout, itecnt, frcchk_fr, frcchk_sh);
     if (rc) return rc;
     if (f_temp_out)
-        CUDA_TRY(cudaMemcpy(f_temp_out, h->f_temp.p, h->sz.NEQ * sizeof(double),
-                            cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpyAsync(f_temp_out, h->f_temp.p, h->sz.NEQ * sizeof(double),
+                                 cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     return CB_OK;
 }
 
@@ -709,6 +723,7 @@ extern "C" int cb_get_skyline(cb_handle *h, double *ss, long n)
     if (!(h->layout & CB_MAT_SKYLINE) || !h->ss.p) return fail(CB_ERR_ARG, "no skyline matrix assembled");
     if (n != h->lss) return fail(CB_ERR_ARG, "skyline length %ld != lss %ld", n, h->lss);
     cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaMemcpy(ss, h->ss.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
     return CB_OK;
 }
@@ -752,6 +767,7 @@ extern "C" int cb_get_csc_values(cb_handle *h, double *Ax)
     if (!h || !Ax) return fail(CB_ERR_ARG, "null argument");
     if (!(h->layout & CB_MAT_CSC) || !h->Ax.p) return fail(CB_ERR_ARG, "no CSC matrix assembled");
     cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaMemcpy(Ax, h->Ax.p, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToHost));
     return CB_OK;
 }
@@ -764,6 +780,7 @@ extern "C" long cb_csc_compact(cb_handle *h, double drop_tol, int *Ap, int *Ai, 
     std::vector<int> fAp(h->sz.NEQ + 1), fAi((size_t)h->nnz);
     std::vector<double> fAx((size_t)h->nnz);
     host_pattern(h, fAp.data(), fAi.data());
+    cudaStreamSynchronize(h->stream);
     if (cudaMemcpy(fAx.data(), h->Ax.p, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToHost) !=
         cudaSuccess) { fail(CB_ERR_CUDA, "Ax download failed"); return -1; }
     long nz = 0;
@@ -780,6 +797,7 @@ extern "C" int cb_get_mass(cb_handle *h, double *sm)
 {
     if (!h || !sm) return fail(CB_ERR_ARG, "null argument");
     cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaMemcpy(sm, h->sm.p, h->sz.NEQ * sizeof(double), cudaMemcpyDeviceToHost));
     return CB_OK;
 }
@@ -788,6 +806,7 @@ extern "C" int cb_get_f(cb_handle *h, double *f)
 {
     if (!h || !f) return fail(CB_ERR_ARG, "null argument");
     cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaMemcpy(f, h->f_temp.p, h->sz.NEQ * sizeof(double), cudaMemcpyDeviceToHost));
     return CB_OK;
 }
@@ -899,6 +918,7 @@ static int transfer(cb_handle *h, int which, double *host, long n, bool down)
         CUDA_TRY(cudaMemcpy(down ? (void *)host : (void *)v.flat, down ? (void *)v.flat : (void *)host,
                             (size_t)n * sizeof(double),
                             down ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice));
+        if (!down) CUDA_TRY(cudaDeviceSynchronize());
         return CB_OK;
     }
     long pos = 0;
@@ -916,6 +936,7 @@ static int transfer(cb_handle *h, int which, double *host, long n, bool down)
         if (!down)
             CUDA_TRY(cudaMemcpy(pt.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
+    if (!down) CUDA_TRY(cudaDeviceSynchronize());
     return CB_OK;
 }
 
@@ -929,8 +950,47 @@ extern "C" int cb_upload(cb_handle *h, int which, const double *src, long n)
 }
 
 extern "C" long cb_launch_count(cb_handle *h) { return h ? h->launches : 0; }
-extern "C" double cb_last_stiff_ms(cb_handle *h) { return h ? h->last_stiff_ms : 0; }
-extern "C" double cb_last_forces_ms(cb_handle *h) { return h ? h->last_forces_ms : 0; }
+static double elapsed(cb_handle *h, cudaEvent_t a, cudaEvent_t b)
+{
+    cudaSetDevice(h->fl.device);
+    if (cudaEventSynchronize(b) != cudaSuccess) return -1.0;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) return -1.0;
+    return ms;
+}
+extern "C" double cb_last_stiff_ms(cb_handle *h) { return (h && h->stiff_timed) ? elapsed(h, h->ev0, h->ev1) : 0; }
+extern "C" double cb_last_forces_ms(cb_handle *h) { return (h && h->forces_timed) ? elapsed(h, h->ev4, h->ev5) : 0; }
+extern "C" int cb_timer_start(cb_handle *h)
+{
+    if (!h) return fail(CB_ERR_ARG, "null handle");
+    cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaEventRecord(h->evA, h->stream));
+    return CB_OK;
+}
+extern "C" double cb_timer_stop_ms(cb_handle *h)
+{
+    if (!h) return -1.0;
+    cudaSetDevice(h->fl.device);
+    if (cudaEventRecord(h->evB, h->stream) != cudaSuccess) return -1.0;
+    return elapsed(h, h->evA, h->evB);
+}
+extern "C" double cb_last_assemble_ms(cb_handle *h) { return (h && h->stiff_timed) ? elapsed(h, h->ev2, h->ev3) : 0; }
+extern "C" int cb_set_dd(cb_handle *h, const double *dd)
+{
+    if (!h || !dd) return fail(CB_ERR_ARG, "null argument");
+    cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(h->dd.p, dd, h->sz.NEQ * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return CB_OK;
+}
+extern "C" void *cb_host_alloc(unsigned long bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void cb_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" long cb_map_bytes(cb_handle *h) { return h ? h->map_bytes : 0; }
 extern "C" int cb_sync(cb_handle *h)
 {

@@ -32,7 +32,8 @@ EXPORTS = [
     "cb_get_skyline", "cb_csc_nnz", "cb_csc_pattern", "cb_get_csc_values", "cb_csc_compact",
     "cb_get_mass", "cb_get_f", "cb_dev_Ax", "cb_dev_skyline", "cb_dev_f", "cb_dev_dd",
     "cb_dev_Ap", "cb_dev_Ai", "cb_download", "cb_upload", "cb_launch_count",
-    "cb_last_stiff_ms", "cb_last_forces_ms", "cb_map_bytes", "cb_sync", "cb_stream",
+    "cb_last_stiff_ms", "cb_last_forces_ms", "cb_last_assemble_ms", "cb_timer_start", "cb_timer_stop_ms", "cb_set_dd", "cb_host_alloc",
+    "cb_host_free", "cb_map_bytes", "cb_sync", "cb_stream",
 ]
 
 
@@ -77,6 +78,12 @@ def load_library(path=None):
     lib.cb_map_bytes.restype = C.c_long
     lib.cb_last_stiff_ms.restype = C.c_double
     lib.cb_last_forces_ms.restype = C.c_double
+    lib.cb_last_assemble_ms.restype = C.c_double
+    lib.cb_timer_stop_ms.restype = C.c_double
+    lib.cb_host_alloc.restype = C.c_void_p
+    lib.cb_host_alloc.argtypes = [C.c_ulong]
+    lib.cb_host_free.restype = None
+    lib.cb_host_free.argtypes = [C.c_void_p]
     for n in ("cb_dev_Ax", "cb_dev_skyline", "cb_dev_f", "cb_dev_dd", "cb_dev_Ap", "cb_dev_Ai",
               "cb_stream"):
         getattr(lib, n).restype = C.c_void_p
@@ -121,6 +128,9 @@ class Assembler:
 
     def close(self):
         if getattr(self, "h", None):
+            for ptr in getattr(self, "_pinned", []):
+                self.lib.cb_host_free(C.c_void_p(ptr))
+            self._pinned = []
             self.lib.cb_destroy(self.h)
             self.h = None
 
@@ -238,6 +248,33 @@ class Assembler:
     @property
     def last_forces_ms(self):
         return self.lib.cb_last_forces_ms(self.h)
+
+    @property
+    def last_assemble_ms(self):
+        return self.lib.cb_last_assemble_ms(self.h)
+
+    def timer_start(self):
+        self._check(self.lib.cb_timer_start(self.h))
+
+    def timer_stop_ms(self):
+        return self.lib.cb_timer_stop_ms(self.h)
+
+    def sync(self):
+        self._check(self.lib.cb_sync(self.h))
+
+    def set_dd(self, dd):
+        dd = np.ascontiguousarray(dd, dtype=np.float64)
+        self._check(self.lib.cb_set_dd(self.h, _p(dd)))
+
+    def pinned(self, n, dtype=np.float64):
+        """numpy view of a page-locked host buffer (freed with the Assembler)"""
+        nbytes = int(n) * np.dtype(dtype).itemsize
+        ptr = self.lib.cb_host_alloc(C.c_ulong(max(nbytes, 8)))
+        if not ptr:
+            raise CubensError("cudaHostAlloc failed")
+        self._pinned = getattr(self, "_pinned", []) + [ptr]
+        buf = (C.c_char * max(nbytes, 8)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=int(n))
 
     @property
     def map_bytes(self):

@@ -256,7 +256,8 @@ def truss_geometry(x, ends):
 # ------------------------------------------------------------------------------------------
 def build_model(x, trusses=None, frames=None, shells=None, bricks=None, fixed=(),
                 truss_props=None, frame_props=None, shell_props=None, brick_props=None,
-                frame_aux=None, loads=(), ANAFLAG=2, ALGFLAG=1, SLVFLAG=0, meta=None):
+                frame_aux=None, loads=(), ANAFLAG=2, ALGFLAG=1, SLVFLAG=0, meta=None,
+                jflags=None, want_skyline=None):
     """Assemble a ``Model`` the way main.c:330-1437 does for a deck with these elements.
 
     trusses/frames [n,2], shells [n,3], bricks [n,8]: 1-based joint numbers.
@@ -278,9 +279,17 @@ def build_model(x, trusses=None, frames=None, shells=None, bricks=None, fixed=()
     tr, fr, sh, br = arr(trusses, 2), arr(frames, 2), arr(shells, 3), arr(bricks, 8)
     NE_TR, NE_FR, NE_SH, NE_SBR = len(tr), len(fr), len(sh), len(br)
     minc = np.concatenate([tr.reshape(-1), fr.reshape(-1), sh.reshape(-1), br.reshape(-1)])
-    jflags = initial_jcode(NJ, NE_TR, NE_FR, NE_SH, NE_SBR, minc, fixed)
+    # jflags: the -1/0 jcode of the GLOBAL model when this is an element-partition sub-model
+    # (joints without local elements must keep their global equation numbers)
+    if jflags is None:
+        jflags = initial_jcode(NJ, NE_TR, NE_FR, NE_SH, NE_SBR, minc, fixed)
     jcode, mcode, NEQ = codes(jflags, minc, NE_TR, NE_FR, NE_SH, NE_SBR)
-    kht, maxa, lss = skylin(mcode, NEQ, NE_TR, NE_FR, NE_SH)
+    if want_skyline is None:
+        want_skyline = (SLVFLAG == 0)
+    if want_skyline:
+        kht, maxa, lss = skylin(mcode, NEQ, NE_TR, NE_FR, NE_SH)
+    else:
+        kht, maxa, lss = None, None, 0
 
     def props(p, n, k):
         if n == 0:

@@ -178,11 +178,23 @@ int  cb_upload(cb_handle *h, int which, const double *src, long n);
 /* ---- instrumentation ------------------------------------------------------------------- */
 /* kernels launched by this handle since creation (bench.py's gpu_launches)                 */
 long cb_launch_count(cb_handle *h);
-/* CUDA-event time in ms of the most recent cb_stiff / cb_update_forces* device work        */
+/* CUDA-event time in ms of the most recent cb_stiff / cb_update_forces* device work.  The hot   */
+/* calls only enqueue work on the handle's stream; these getters, cb_sync and every cb_get_* / */
+/* cb_download wait for it.                                                                    */
 double cb_last_stiff_ms(cb_handle *h);
 double cb_last_forces_ms(cb_handle *h);
 /* bytes of implementation-only maps read per cb_stiff (reported next to the roofline)      */
 long cb_map_bytes(cb_handle *h);
+/* CUDA-event time in ms of the block-assembly kernel alone (the dominant kernel; roofline)  */
+double cb_last_assemble_ms(cb_handle *h);
+/* CUDA events on this handle's stream bracketing any sequence of calls (device timeline)     */
+int    cb_timer_start(cb_handle *h);
+double cb_timer_stop_ms(cb_handle *h);
+/* stage dd in the device buffer cb_dev_dd() for cb_update_forces_dev (host -> device copy)  */
+int  cb_set_dd(cb_handle *h, const double *dd);
+/* page-locked host buffers so the Ap/Ai/Ax and f_temp transfers run at full PCIe rate        */
+void *cb_host_alloc(unsigned long bytes);
+void  cb_host_free(void *p);
 /* block the host until all work queued on this handle's stream has finished                */
 int  cb_sync(cb_handle *h);
 /* the CUDA stream (cudaStream_t cast to void*) all of this handle's kernels run on         */

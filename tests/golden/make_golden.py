@@ -1,0 +1,102 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref, compiled from
+/root/reference by oracle/Makefile).  The reference ships no tests and no expected outputs
+(SURVEY.md section 4), so these vectors - arrays read back in memory from its own routines at
+full double precision - are the golden fixtures for this path.  Run from the repo root:
+
+    python tests/golden/make_golden.py
+
+Each file holds, for a model rebuilt through cubens_b200.meshgen with the arguments in
+``cases()`` and a fixed seeded sequence of Newton-like iterations, the reference's skyline K_t,
+dense K_t (small cases), f_temp, ef_i, triads and the lumped mass."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "cu-bens_b200", "python"))
+
+from cubens_b200 import meshgen, model as M  # noqa: E402
+from oracle import refbind as R              # noqa: E402
+
+
+def cases():
+    """name -> (factory name, kwargs, post-processing id)"""
+    return {
+        "plate_3x2": ("plate_model", dict(nx=3, ny=2, z_bump=0.02), None),
+        "plate_5x4_flat": ("plate_model", dict(nx=5, ny=4), None),
+        "plate_lin_3x3": ("plate_model", dict(nx=3, ny=3, ANAFLAG=1), None),
+        "truss_3": ("truss_model", dict(n=3), None),
+        "truss_lin_3": ("truss_model", dict(n=3, ANAFLAG=1), None),
+        "lattice_3": ("lattice_model", dict(n=3), "fe"),
+        "lattice_3_offsets_releases": ("lattice_model", dict(n=3), "offrel"),
+        "lattice_lin_3": ("lattice_model", dict(n=3, ANAFLAG=1), None),
+        "brick_2x2x2": ("brick_model", dict(nx=2, ny=2, nz=2, distort=0.1), None),
+        "brick_skin_2x2x1": ("brick_model", dict(nx=2, ny=2, nz=1, distort=0.05, skin=True), None),
+    }
+
+
+def build(name):
+    fac, kw, post = cases()[name]
+    m = getattr(meshgen, fac)(**kw)
+    if post in ("fe", "offrel"):
+        rng = np.random.default_rng(11)
+        m.efFE_ref[:] = rng.uniform(-1, 1, m.efFE_ref.size)
+    if post == "offrel":
+        rng = np.random.default_rng(12)
+        m.osflag[::3] = 1
+        m.offset[:] = rng.uniform(-5, 5, m.offset.size) * np.repeat(m.osflag, 6)
+        rel = m.mendrel.reshape(-1, 5)
+        rel[1::4] = [1, 1, 0, 0, 0]; rel[2::4] = [1, 0, 1, 1, 0]
+        rel[3::7] = [1, 1, 1, 1, 0]; rel[5::11] = [1, 1, 1, 1, 1]
+        xfr, ll, lx, ly, lz = M.frame_geometry(m.x, m.minc.reshape(-1, 2) - 1, m.auxpt, m.offset,
+                                               m.osflag)
+        m.xfr[:] = xfr.reshape(-1); m.llength[:] = ll
+        m.c1[:] = lx.reshape(-1); m.c2[:] = ly.reshape(-1); m.c3[:] = lz.reshape(-1)
+    return m
+
+
+def record(name, B=R, n_iter=3):
+    """replay the fixed sequence through backend B (refbind or oraclebind)"""
+    m = build(name)
+    out = {"NEQ": m.NEQ, "lss": m.lss, "jcode": m.jcode, "mcode": m.mcode}
+    if m.maxa is not None:
+        out["maxa"] = m.maxa
+    s = R.RefState(m)
+    rng = np.random.default_rng(2026)
+    if m.NE_BR:
+        out["K_dense"] = B.stiff(m, s, SLVFLAG=2, gen="c")
+        return m, out
+    if m.ANAFLAG == 1:
+        out["K_sky"] = B.stiff(m, s, SLVFLAG=0, gen="c")
+        d = rng.uniform(-1e-3, 1e-3, m.NEQ)
+        out["d"] = d
+        out["f_lin"] = B.forces_linear(m, s, d)
+        out["ef_lin"] = s.ef.copy()
+        return m, out
+    s.begin_increment()
+    for it in range(n_iter):
+        out[f"K_sky_{it}"] = B.stiff(m, s, SLVFLAG=0)
+        if m.NEQ <= 200:
+            out[f"K_dense_{it}"] = B.stiff(m, s, SLVFLAG=2)
+        dd = rng.uniform(-1e-4, 1e-4, m.NEQ) * (100.0 if m.NE_FR or m.NE_TR else 1.0)
+        out[f"dd_{it}"] = dd
+        B.update_forces(m, s, dd, dlpf=0.25, itecnt=it)
+        out[f"f_{it}"] = s.f_temp.copy(); out[f"ef_{it}"] = s.ef_i.copy()
+        out[f"c1_{it}"] = s.c1_i.copy(); out[f"c2_{it}"] = s.c2_i.copy(); out[f"c3_{it}"] = s.c3_i.copy()
+        if m.NE_FR:
+            out[f"efFE_{it}"] = s.efFE_i.copy()
+        s.end_iteration()
+    s.commit()
+    out["mass"] = B.mass(m, s, SLVFLAG=0) if B is R else B.mass(m, s)
+    return m, out
+
+
+if __name__ == "__main__":
+    assert R.available(), "build oracle/_ref first (make -C oracle ref)"
+    for name in cases():
+        m, out = record(name)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "NEQ", m.NEQ, "arrays", len(out))

@@ -1,0 +1,104 @@
+"""CPU suite: the C-ABI library loads and exports every symbol of include/cubens_b200.h, fails
+loudly without a GPU, and the host-side partition logic is consistent (gloo, world_size 2)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    import cubens_b200 as cb
+    lib = cb.load_library()
+    hdr = open(os.path.join(ROOT, "include", "cubens_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(cb_[a-z_A-Z0-9]+)\s*\(", hdr)))
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert set(cb.EXPORTS) <= set(declared)
+    assert lib.cb_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """without a CUDA device creation must fail loudly (never silently compute on the CPU)"""
+    import cubens_b200 as cb
+    from cubens_b200 import meshgen
+    lib = cb.load_library()
+    if lib.cb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(cb.CubensError):
+        cb.Assembler(meshgen.plate_model(2, 2))
+
+
+def test_product_does_not_touch_oracle():
+    """nothing under cu-bens_b200/ or include/ may reference oracle/"""
+    bad = []
+    for base in ("cu-bens_b200", "include"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, base)):
+            if "build" in dp or "__pycache__" in dp:
+                continue
+            for f in fs:
+                if f.endswith((".so", ".o", ".log")):
+                    continue
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                if re.search(r"\boracle[/.]", txt) and "never touches" not in txt:
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+def test_partition_numbering_consistent():
+    from cubens_b200 import meshgen
+    from cubens_b200.partition import plate_partition
+    world, nx, ny = 3, 4, 5
+    full = meshgen.plate_model(nx * world, ny, lx=nx * world / ny, ly=1.0, SLVFLAG=2)
+    owned_total, el_total = 0, 0
+    cover = np.zeros(full.NJ, dtype=int)
+    for r in range(world):
+        m, (j0, j1), ne = plate_partition(nx, ny, world, r)
+        assert m.NEQ == full.NEQ and np.array_equal(m.jcode, full.jcode)
+        assert np.abs(m.x - full.x).max() < 1e-15
+        cover[j0:j1] += 1; el_total += ne
+        # every element touching an owned joint is present locally (halo complete)
+        tri_full = full.minc.reshape(-1, 3) - 1
+        need = np.any((tri_full >= j0) & (tri_full < j1), axis=1)
+        have = {tuple(t) for t in (m.minc.reshape(-1, 3) - 1).tolist()}
+        assert all(tuple(t) in have for t in tri_full[need].tolist())
+    assert np.all(cover == 1) and el_total == full.NE_SH
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, os.path.join(%(root)r, "cu-bens_b200", "python"))
+import numpy as np, torch, torch.distributed as dist
+from cubens_b200.partition import plate_partition
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+m, (j0, j1), ne = plate_partition(4, 5, world, rank)
+jc = m.jcode.reshape(-1, 7)
+eq = jc[j0:j1].reshape(-1); eq = eq[eq > 0]
+own = np.zeros(m.NEQ); own[eq - 1] = 1.0
+t = torch.from_numpy(own); dist.all_reduce(t)
+assert torch.all(t == 1.0), "every equation must be owned by exactly one rank"
+n = torch.tensor([float(ne)]); dist.all_reduce(n)
+assert int(n) == 2 * 4 * world * 5
+# residual-sum exchange: partial dot products over owned equations add up to the global one
+rng = np.random.default_rng(0); r = rng.normal(size=m.NEQ)
+part = torch.tensor([float(np.dot(r[eq - 1], r[eq - 1]))], dtype=torch.float64); dist.all_reduce(part)
+assert abs(float(part) - float(np.dot(r, r))) < 1e-9 * float(np.dot(r, r))
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_partition_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(WORKER % {"root": ROOT})
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+                          "29731", str(script)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2

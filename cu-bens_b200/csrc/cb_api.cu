@@ -70,6 +70,10 @@ template <typename T> struct DevBuf {
 struct Plan {
     DevBuf<CbPair> pairs;
     long npairs = 0;
+    DevBuf<CbTile> tiles;
+    DevBuf<CbTPair> tpairs;
+    long ntiles = 0;
+    int tile_smem_out = 0;
 };
 
 struct cb_handle {
@@ -99,6 +103,7 @@ struct cb_handle {
     std::vector<int64_t> base;                // first Ax index of joint B's columns
     std::vector<int32_t> colh;
     long nnz = 0, lss = 0;
+    int64_t ax_base = 0;                      // Ax holds the columns of the owned joints only
 
     // device: nodes and vectors
     DevBuf<int32_t> jc;
@@ -106,7 +111,8 @@ struct cb_handle {
     DevBuf<double> dd, f_temp, f, d, d_temp, sm;
     // shells
     DevBuf<int32_t> sh_nodes;
-    DevBuf<double> sh_const, sh_keb, sh_Nm, sh_fg, sh_dens;
+    DevBuf<double> sh_const, sh_keb, sh_kebc, sh_Nm, sh_fg, sh_dens;
+    long ncontrib = 0;
     DevBuf<double> sh_frame[3], sh_dsl[3], sh_ef[3];   // 0 = committed, 1/2 = iterate ping-pong
     // trusses
     DevBuf<int32_t> tr_nodes;
@@ -127,6 +133,7 @@ struct cb_handle {
     DevBuf<int32_t> node_cstart;
     DevBuf<CbCorner> corners;
     DevBuf<CbContrib> contribs;
+    int max_dof = 3, mixed = 0;
     Plan plan_csc, plan_sky;
     DevBuf<int> Ap, Ai;
     DevBuf<long> maxa;
@@ -319,7 +326,7 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
             if (m->dens) dn[e] = m->dens[e];             // pdens+i, shell.c:61 / 1551
         }
         if (h->sh_const.upload(c) || h->sh_dens.upload(dn) || h->sh_keb.alloc((size_t)SH * 81) ||
-            h->sh_Nm.alloc((size_t)SH * 4) || h->sh_fg.alloc((size_t)SH * 18))
+            h->sh_Nm.alloc((size_t)SH * CB_SH_KREC) || h->sh_fg.alloc((size_t)SH * 18))
             BAIL(CB_ERR_CUDA);
         for (int g = 0; g < 3; ++g) {
             if (h->sh_frame[g].upload(fr) || h->sh_dsl[g].upload(dsl) ||
@@ -340,7 +347,7 @@ extern "C" void cb_destroy(cb_handle *h)
     cudaSetDevice(h->fl.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf<double> *b : {&h->x, &h->x_temp, &h->x_ip, &h->dd, &h->f_temp, &h->f, &h->d,
-                              &h->d_temp, &h->sm, &h->sh_const, &h->sh_keb, &h->sh_Nm, &h->sh_fg,
+                              &h->d_temp, &h->sm, &h->sh_const, &h->sh_keb, &h->sh_kebc, &h->sh_Nm, &h->sh_fg,
                               &h->sh_dens, &h->tr_const, &h->tr_fg, &h->tr_dens, &h->fr_const,
                               &h->fr_offset, &h->fr_efFE_ref, &h->fr_fg, &h->fr_dens, &h->br_const,
                               &h->Ax, &h->ss})
@@ -355,6 +362,7 @@ extern "C" void cb_destroy(cb_handle *h)
                                &h->fr_mendrel, &h->br_nodes, &h->node_cstart})
         b->release();
     h->corners.release(); h->contribs.release(); h->plan_csc.pairs.release();
+    h->plan_csc.tiles.release(); h->plan_csc.tpairs.release();
     h->plan_sky.pairs.release(); h->Ap.release(); h->Ai.release(); h->maxa.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -380,6 +388,8 @@ extern "C" int cb_set_owned_joints(cb_handle *h, long j0, long j1)
 // ------------------------------------------------------------------------------------------
 // the sorted element-to-nonzero maps
 // ------------------------------------------------------------------------------------------
+static void host_pattern(cb_handle *h, int *Ap, int *Ai);
+
 static int build_plan(cb_handle *h)
 {
     if (h->plan_ready) return CB_OK;
@@ -436,16 +446,26 @@ static int build_plan(cb_handle *h)
         nnz += (long)h->h_nfree[j] * hgt;
     }
     h->base[NJ] = nnz;
+    h->ax_base = h->base[h->j0];
+    nnz = h->base[h->j1] - h->base[h->j0];        // owned column slice
     if ((h->layout & CB_MAT_CSC) && nnz > 0x7fffffffL)
         return fail(CB_ERR_OVERFLOW, "nnz=%ld exceeds the 32-bit CSC indices umfpack_di_* takes", nnz);
     h->nnz = nnz;
 
     // node-pair blocks and their contribution lists
     std::vector<CbPair> pairs_csc, pairs_sky;
+    std::vector<CbTPair> tpairs;
+    std::vector<CbTile> tiles;
     std::vector<CbContrib> contribs;
     contribs.reserve((size_t)ncorner * 3);
+    const int OUTMAX = 2046;                 // doubles of tile output staged in shared memory (+2 pad)
+    bool tiles_ok = (h->layout & CB_MAT_CSC) != 0;
+    CbTile cur{}; cur.nc = cur.np = cur.nout = 0; bool open = false;
+    int max_tile_out = 0;
     for (long B = h->j0; B < h->j1; ++B) {
         if (!h->h_nfree[B]) continue;
+        const long c_before = (long)contribs.size();
+        const size_t tp_before = tpairs.size();
         for (int k = h->adj_start[B]; k < h->adj_start[B + 1]; ++k) {
             const int32_t A = h->adj[k];
             if (!h->h_nfree[A]) continue;
@@ -464,33 +484,77 @@ static int build_plan(cb_handle *h)
             if (cnt > 65535) return fail(CB_ERR_OVERFLOW, "joint valence too large");
             p.ccount = (uint16_t)cnt;
             p.colh = h->colh[B];
-            p.off = (int32_t)(h->base[B] + rowoff[k]);
+            p.off = (int32_t)(h->base[B] - h->ax_base + rowoff[k]);
             p.eqA0 = h->h_first[A]; p.eqB0 = h->h_first[B];
             p.maskA = h->h_mask[A]; p.maskB = h->h_mask[B];
             if (h->layout & CB_MAT_CSC) pairs_csc.push_back(p);
             if ((h->layout & CB_MAT_SKYLINE) && A <= B) pairs_sky.push_back(p);
+            if (tiles_ok) {
+                CbTPair tp{};
+                tp.rel = (int32_t)rowoff[k];          // fixed up below: + (base[B] - tile.out0)
+                tp.colh = h->colh[B];
+                tp.cs = 0; tp.cnt = (uint16_t)cnt; tp.maskA = p.maskA; tp.maskB = p.maskB;
+                tp.pad = 0;
+                tpairs.push_back(tp);
+            }
         }
+        if (!tiles_ok) continue;
+        // pack joint B into the current tile (or start a new one)
+        const int node_nc = (int)((long)contribs.size() - c_before);
+        const int node_np = (int)(tpairs.size() - tp_before);
+        const long node_out = (long)h->h_nfree[B] * h->colh[B];
+        if (node_nc > CB_TILE_T || node_out > OUTMAX) { tiles_ok = false; continue; }
+        if (open && (cur.nc + node_nc > CB_TILE_T || cur.nout + node_out > OUTMAX ||
+                     h->base[B] - h->ax_base != cur.out0 + cur.nout)) {
+            tiles.push_back(cur); open = false;
+        }
+        if (!open) {
+            cur = CbTile{}; cur.out0 = h->base[B] - h->ax_base; cur.nout = 0; cur.c0 = (int32_t)c_before;
+            cur.nc = 0; cur.p0 = (int32_t)tp_before; cur.np = 0; open = true;
+        }
+        // fix up this joint's pairs: offsets relative to the tile
+        int cs = cur.nc;
+        for (size_t q = tp_before; q < tpairs.size(); ++q) {
+            tpairs[q].rel += (int32_t)(h->base[B] - h->ax_base - cur.out0);
+            tpairs[q].cs = (uint16_t)cs; cs += tpairs[q].cnt;
+        }
+        cur.nc += node_nc; cur.np += node_np; cur.nout += (int32_t)node_out;
+        if (cur.nout > max_tile_out) max_tile_out = cur.nout;
     }
+    if (open) tiles.push_back(cur);
+    // inside a tile, order the pair records by contribution count so that the threads of a warp
+    // loop alike in the reduction phase (the contribution list itself keeps reference order)
+    for (CbTile &tl : tiles)
+        std::stable_sort(tpairs.begin() + tl.p0, tpairs.begin() + tl.p0 + tl.np,
+                         [](const CbTPair &x, const CbTPair &y) { return x.cnt > y.cnt; });
     if (contribs.size() > 0x7fffffffUL) return fail(CB_ERR_OVERFLOW, "too many contributions");
-    // bucket the blocks by contribution count (descending, stable) so a warp's threads loop alike
+    h->ncontrib = (long)contribs.size();
+    {
+        const bool has3 = h->sz.NE_TR || h->NE_BR, has6 = h->sz.NE_SH != 0, has7 = h->sz.NE_FR != 0;
+        h->max_dof = has7 ? 7 : (has6 ? 6 : 3);
+        h->mixed = ((int)has3 + (int)has6 + (int)has7) > 1;
+    }
+    // block-owner kernel (skyline, or CSC fallback for joints too large for a tile): bucket the
+    // blocks by contribution count (descending, stable) so a warp's threads loop alike
     auto bucket = [](std::vector<CbPair> &v) {
         std::stable_sort(v.begin(), v.end(),
                          [](const CbPair &a, const CbPair &b) { return a.ccount > b.ccount; });
     };
-    bucket(pairs_csc); bucket(pairs_sky);
+    bucket(pairs_sky);
+    if (tiles_ok) pairs_csc.clear(); else { bucket(pairs_csc); tiles.clear(); tpairs.clear(); }
 
     if (h->node_cstart.upload(cstart) || h->corners.upload(corners) || h->contribs.upload(contribs))
         return CB_ERR_CUDA;
     if (h->layout & CB_MAT_CSC) {
         if (h->plan_csc.pairs.upload(pairs_csc)) return CB_ERR_CUDA;
         h->plan_csc.npairs = (long)pairs_csc.size();
+        if (h->plan_csc.tiles.upload(tiles) || h->plan_csc.tpairs.upload(tpairs)) return CB_ERR_CUDA;
+        h->plan_csc.ntiles = (long)tiles.size();
+        h->plan_csc.tile_smem_out = (max_tile_out + 3) & ~1;   // room for the parity shift, kept even
         if (h->Ax.alloc((size_t)nnz)) return CB_ERR_CUDA;
         cudaMemset(h->Ax.p, 0, (size_t)nnz * sizeof(double));
         std::vector<int> Ap(h->sz.NEQ + 1, 0);
-        for (long j = 0; j < NJ; ++j)
-            for (int cc = 0; cc < h->h_nfree[j]; ++cc)
-                Ap[h->h_first[j] - 1 + cc] = (int)(h->base[j] + (long)cc * h->colh[j]);
-        Ap[h->sz.NEQ] = (int)nnz;
+        host_pattern(h, Ap.data(), nullptr);
         if (h->Ap.upload(Ap)) return CB_ERR_CUDA;
     }
     if (h->layout & CB_MAT_SKYLINE) {
@@ -500,6 +564,7 @@ static int build_plan(cb_handle *h)
         cudaMemset(h->ss.p, 0, (size_t)h->lss * sizeof(double));
     }
     h->map_bytes = (long)((pairs_csc.size() + pairs_sky.size()) * sizeof(CbPair) +
+                          tiles.size() * sizeof(CbTile) + tpairs.size() * sizeof(CbTPair) +
                           contribs.size() * sizeof(CbContrib));
     // uploads above went through the legacy default stream; the handle's stream is non-blocking
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(CB_ERR_CUDA, "sync after map upload");
@@ -513,6 +578,12 @@ static int ensure_keb(cb_handle *h)
     CbDev d = make_dev(h);
     if (cbk_shell_init_keb(d, h->sh_keb.p, h->stream)) return fail(CB_ERR_CUDA, "keb init launch");
     if (h->sz.NE_SH) ++h->launches;
+    if (h->sz.NE_SH && h->plan_ready && h->plan_csc.ntiles) {
+        if (!h->sh_kebc.p && h->sh_kebc.alloc((size_t)h->ncontrib * 10)) return CB_ERR_CUDA;
+        if (cbk_shell_init_kebc(d, h->contribs.p, h->ncontrib, h->sh_kebc.p, h->stream))
+            return fail(CB_ERR_CUDA, "kebc init launch");
+        ++h->launches;
+    }
     h->keb_dirty = false;
     return CB_OK;
 }
@@ -587,19 +658,23 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
     a.tr_frame = h->tr_frame[g].p; a.tr_ef = h->tr_ef[ge].p;
     a.contribs = h->contribs.p;
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    if (h->fl.ANAFLAG == 2 && h->sz.NE_SH) {
+    if (h->sz.NE_SH) {
         if (cbk_shell_prep(a.d, a.x, a.sh_frame, h->stream)) return fail(CB_ERR_CUDA, "prep launch");
         ++h->launches;
     }
+    a.max_dof = h->max_dof; a.mixed = h->mixed;
     CUDA_TRY(cudaEventRecord(h->ev2, h->stream));
     if (h->layout & CB_MAT_CSC) {
         a.pairs = h->plan_csc.pairs.p; a.npairs = h->plan_csc.npairs;
+        a.tiles = h->plan_csc.ntiles ? h->plan_csc.tiles.p : nullptr; a.ntiles = h->plan_csc.ntiles;
+        a.tpairs = h->plan_csc.tpairs.p; a.kebc = h->sh_kebc.p;
+        a.tile_smem_out = h->plan_csc.tile_smem_out;
         a.out = h->Ax.p; a.skyline = 0; a.maxa = nullptr;
         if (cbk_stiff(a, h->stream, &h->launches)) return fail(CB_ERR_CUDA, "assembly launch");
     }
     CUDA_TRY(cudaEventRecord(h->ev3, h->stream));
     if (h->layout & CB_MAT_SKYLINE) {
-        a.pairs = h->plan_sky.pairs.p; a.npairs = h->plan_sky.npairs;
+        a.pairs = h->plan_sky.pairs.p; a.npairs = h->plan_sky.npairs; a.tiles = nullptr;
         a.out = h->ss.p; a.skyline = 1; a.maxa = h->maxa.p;
         if (cbk_stiff(a, h->stream, &h->launches)) return fail(CB_ERR_CUDA, "assembly launch");
     }
@@ -738,17 +813,21 @@ extern "C" long cb_csc_nnz(cb_handle *h)
 
 static void host_pattern(cb_handle *h, int *Ap, int *Ai)
 {
+    // columns of joints outside the owned range are empty (element-partition slices)
     const long NJ = h->sz.NJ;
-    for (long j = 0; j < NJ; ++j)
+    for (long j = 0; j < NJ; ++j) {
+        const bool own = j >= h->j0 && j < h->j1;
         for (int cc = 0; cc < h->h_nfree[j]; ++cc) {
-            long p = h->base[j] + (long)cc * h->colh[j];
+            long p = own ? h->base[j] - h->ax_base + (long)cc * h->colh[j]
+                         : (j < h->j0 ? 0 : h->nnz);
             Ap[h->h_first[j] - 1 + cc] = (int)p;
-            if (!Ai) continue;
+            if (!Ai || !own) continue;
             for (int k = h->adj_start[j]; k < h->adj_start[j + 1]; ++k) {
                 const int32_t A = h->adj[k];
                 for (int rr = 0; rr < h->h_nfree[A]; ++rr) Ai[p++] = h->h_first[A] - 1 + rr;
             }
         }
+    }
     Ap[h->sz.NEQ] = (int)h->nnz;
 }
 

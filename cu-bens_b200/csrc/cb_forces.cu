@@ -128,7 +128,7 @@ k_shell_init_keb(CbDev d, double *__restrict__ keb)
         for (int j = 0; j < 9; ++j) {
             double sum = 0;
             for (int k = 0; k < 9; ++k) sum += Q[i][k] * aT[j][k];
-            keb[e * 81 + i * 9 + j] = sum / (2 * A0);
+            keb[e * 81 + CB_KEB(i, j)] = sum / (2 * A0);
         }
 }
 
@@ -137,6 +137,36 @@ int cbk_shell_init_keb(const CbDev &d, double *keb_out, cudaStream_t s)
     if (d.NE_SH == 0) return 0;
     unsigned g = (unsigned)((d.NE_SH + CB_TPB - 1) / CB_TPB);
     k_shell_init_keb<<<g, CB_TPB, 0, s>>>(d, keb_out);
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// contribution-ordered copy of the 3x3 DKT sub-blocks: the assembly kernel reads it with fully
+// coalesced loads and without waiting for the contribution record (static across iterations)
+__global__ void __launch_bounds__(256)
+k_shell_init_kebc(CbDev d, const CbContrib *__restrict__ contribs, long ncontrib,
+                  double *__restrict__ kebc)
+{
+    long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (c >= ncontrib) return;
+    const CbContrib ct = contribs[c];
+    double *o = kebc + c * 10;
+    if (ct.type != CB_T_SHELL) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) o[i] = 0.0;
+        return;
+    }
+    const double *kb = d.sh_keb + (long)ct.e * 81 + (3 * ct.a + ct.b) * 9;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o[i] = kb[i];
+    o[9] = 0.0;
+}
+
+int cbk_shell_init_kebc(const CbDev &d, const CbContrib *contribs, long ncontrib, double *kebc,
+                        cudaStream_t s)
+{
+    if (ncontrib == 0 || d.NE_SH == 0) return 0;
+    unsigned g = (unsigned)((ncontrib + 255) / 256);
+    k_shell_init_kebc<<<g, 256, 0, s>>>(d, contribs, ncontrib, kebc);
     return cudaGetLastError() != cudaSuccess;
 }
 
@@ -182,8 +212,9 @@ __device__ __forceinline__ void membrane_dm(const double *xj, const double *xk, 
 }
 
 // ------------------------------------------------------------------------------------------
-// prep for the geometric stiffness: membrane force resultants Nm (shell.c:688-704) from the
-// coordinates and triad the stiffness pass is evaluated at.
+// prep for the stiffness pass: membrane force resultants Nm (shell.c:688-704) from the
+// coordinates and triad the stiffness is evaluated at, packed with the triad and the
+// element's membrane coefficients into one 144-byte record per shell.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CB_TPB)
 k_shell_prep(CbDev d, const double *__restrict__ x, const double *__restrict__ frame)
@@ -218,8 +249,16 @@ k_shell_prep(CbDev d, const double *__restrict__ x, const double *__restrict__ f
         }
         Nm[i] = sc[2] * sum;
     }
-    d.sh_Nm[e * 4 + 0] = Nm[0]; d.sh_Nm[e * 4 + 1] = Nm[1]; d.sh_Nm[e * 4 + 2] = Nm[2];
-    d.sh_Nm[e * 4 + 3] = 0;
+    // record for the assembly kernel: triad, reference local coordinates, membrane coefficients
+    // t*A0*C/(2A0)^2 and geometric coefficients A_def*Nm/(2A_def)^2 (zero for ANAFLAG 1)
+    double *kr = d.sh_Nm + e * CB_SH_KREC;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) kr[i] = R[i];
+    kr[9] = sc[5]; kr[10] = sc[6]; kr[11] = sc[7];
+    const double smc = sc[2] / (4 * sc[4]);
+    kr[12] = smc * C[0][0]; kr[13] = smc * C[0][1]; kr[14] = smc * C[2][2];
+    const double gs = (d.ANAFLAG == 2) ? 1.0 / (4 * R[9]) : 0.0;
+    kr[15] = gs * Nm[0]; kr[16] = gs * Nm[1]; kr[17] = gs * Nm[2];
 }
 
 int cbk_shell_prep(const CbDev &d, const double *x, const double *sh_frame, cudaStream_t s)
@@ -359,9 +398,11 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
     }
     double defb[9];
     const double *kb = d.sh_keb + e * 81;
+#pragma unroll
     for (int i = 0; i < 9; ++i) {
         double sum = 0;
-        for (int j = 0; j < 9; ++j) sum += kb[i * 9 + j] * ddb[j];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) sum += kb[CB_KEB(i, j)] * ddb[j];
         defb[i] = sum;
     }
 
@@ -456,15 +497,17 @@ k_shell_forces_linear(CbDev d, const double *__restrict__ dtot, const double *__
         ef[fm[i]] = acc;
     }
     const double *kb = d.sh_keb + e * 81;
+#pragma unroll
     for (int i = 0; i < 9; ++i) {
         double sum = 0;
-        for (int j = 0; j < 9; ++j) sum += kb[i * 9 + j] * dl[fb[j]];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) sum += kb[CB_KEB(i, j)] * dl[fb[j]];
         ef[fb[i]] = sum;
     }
     // drilling stiffness ke_b[1][1]/1e4 etc. (shell.c:482-484)
-    ef[5] = (kb[1 * 9 + 1] / 10000) * dl[5];
-    ef[11] = (kb[4 * 9 + 4] / 10000) * dl[11];
-    ef[17] = (kb[7 * 9 + 7] / 10000) * dl[17];
+    ef[5] = (kb[CB_KEB(1, 1)] / 10000) * dl[5];
+    ef[11] = (kb[CB_KEB(4, 4)] / 10000) * dl[11];
+    ef[17] = (kb[CB_KEB(7, 7)] / 10000) * dl[17];
 #pragma unroll
     for (int i = 0; i < 18; ++i) ef_out[e * 18 + i] = ef[i];
 #pragma unroll

@@ -48,6 +48,30 @@ struct CbPair {
     uint8_t maskB;
 };
 
+// ---- tile assembly (CSC): one CTA owns a run of consecutive joints ------------------------
+#define CB_TILE_T 128            // threads per CTA = max contributions per tile
+struct CbTile {
+    int64_t out0;     // first Ax index of the tile's (contiguous) output range
+    int32_t nout;     // number of Ax entries
+    int32_t c0;       // first contribution
+    int32_t nc;       // contributions (<= CB_TILE_T)
+    int32_t p0;       // first pair
+    int32_t np;       // pairs
+    int32_t pad;
+};
+struct CbTPair {
+    int32_t rel;      // offset of (first free row of A, first free column of B) in the tile output
+    int32_t colh;     // column height of joint B
+    uint16_t cs;      // first contribution, relative to the tile
+    uint16_t cnt;     // contributions
+    uint8_t maskA, maskB;
+    uint16_t pad;
+};
+
+// DKT bending matrix ke_b[9][9] is stored as nine contiguous 3x3 joint-pair blocks
+#define CB_KEB(i, j) ((((i) / 3) * 3 + ((j) / 3)) * 9 + ((i) % 3) * 3 + ((j) % 3))
+#define CB_SH_KREC 18   // per-shell record for the stiffness pass: R[9], X2,X3,Y3, cm00,cm01,cm22, n0,n1,n2
+
 // one element corner touching a node (node -> corner CSR), used by the f_int / mass gathers
 struct CbCorner {
     int32_t e;
@@ -80,7 +104,7 @@ struct CbDev {
     const int32_t *sh_nodes; // [NE][4] 0-based
     const double *sh_const;  // [NE][CB_SH_CONST]
     const double *sh_keb;    // [NE][81]
-    double *sh_Nm;           // [NE][4] membrane force resultants for the geometric stiffness
+    double *sh_Nm;           // [NE][CB_SH_KREC] stiffness-pass record written by k_shell_prep
     double *sh_fg;           // [NE][18] element force in global axes (staging for the gather)
     // frames
     const int32_t *fr_nodes; // [NE][2]
@@ -109,6 +133,11 @@ struct CbStiffArgs {
     const double *tr_frame, *tr_ef;
     const CbPair *pairs; long npairs;
     const CbContrib *contribs;
+    const CbTile *tiles; long ntiles; const CbTPair *tpairs;
+    const double *kebc;      // [ncontrib][10] DKT 3x3 sub-block of each shell contribution (static)
+    int tile_smem_out;       // doubles of output staging per tile
+    int max_dof;             // 3, 6 or 7: largest DOF count per joint among the model's elements
+    int mixed;               // element types with different DOF counts per joint are present
     double *out;             // Ax or ss
     const long *maxa;        // device copy (skyline mode) or nullptr
     int skyline;
@@ -138,6 +167,8 @@ extern "C++" {
 #endif
 // cb_forces.cu  (compiled with -fmad=false: reference operation order, IEEE mul/add)
 int cbk_shell_init_keb(const CbDev &d, double *keb_out, cudaStream_t s);
+int cbk_shell_init_kebc(const CbDev &d, const CbContrib *contribs, long ncontrib, double *kebc,
+                        cudaStream_t s);
 int cbk_shell_prep(const CbDev &d, const double *x, const double *sh_frame, cudaStream_t s);
 int cbk_node_update(const CbForceArgs &a, cudaStream_t s);
 int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches);

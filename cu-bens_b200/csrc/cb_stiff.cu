@@ -4,34 +4,70 @@
 // frame.c:226-362, shell.c:110-344, brick.c:79-397) together with the generic dense
 // transform() (misc.c:41-69) and the skyline / dense scatter inlined in each of them.
 //
-// One thread owns one node-pair block of the global matrix (row node A, column node B) and walks
-// the block's sorted contribution list (element type, element, local row node a, local column
-// node b - the order the reference adds them in).  For each contribution it evaluates only the
-// 6x6 (7x7 frame, 3x3 truss/brick) sub-block K_ab = T_a^T k_ab T_b of that element - the
-// transformation is block diagonal, so the reference's 2*18^3 dense products collapse to four
-// 3x3 triple products - accumulates in registers and finally writes the block once.  No atomics,
-// no colouring, no staging of element matrices in HBM: the only HBM write is the matrix itself.
-// Threads are bucketed by contribution count on the host so warps do uniform work.
+// The global matrix is tiled by joint pairs (row joint A, column joint B).  A block receives the
+// sub-blocks K_ab = T_a^T k_ab T_b of the elements containing both joints; the contribution list
+// is sorted by (block, element type, element) - the order the reference adds them in.  The
+// transformation is block diagonal, so a sub-block costs four sparse 3x3 triple products instead
+// of a share of the reference's 2*18^3 dense MACs.
+//
+//   k_assemble_tiles   (CSC)      one CTA owns a run of consecutive joints, i.e. one contiguous
+//                                 range of Ax.  Phase 1: one thread per contribution evaluates its
+//                                 sub-block into shared memory (uniform work per thread).
+//                                 Phase 2: segmented reduction over the sorted contribution list,
+//                                 one thread per (block, column), into an output image of the
+//                                 tile in shared memory.  Phase 3: the image is streamed to HBM with
+//                                 fully coalesced stores.  No atomics, no colouring, no element
+//                                 matrices staged in HBM, bit-reproducible.
+//   k_assemble_blocks  (skyline)  one thread owns one block and loops its contributions; used for
+//                                 the reference's skyline layout (small / medium models that keep
+//                                 the SLVFLAG=0 host solver), where the output is not contiguous.
 #include "cb_internal.h"
 
 #define CB_TPB_K 128
 
-// ---- R^T S R for the four 3x3 sub-blocks of a shell node-pair block -----------------------
-// R rows are the local axes e1,e2,e3 (R[3*r+c]); S is given in local axes.
-__device__ __forceinline__ void rtsr_add(const double *R, const double S[3][3], double *acc,
-                                         int r0, int c0, int ld)
+// ---- sparse R^T S R pieces ------------------------------------------------------------------
+// R rows are the local axes e1,e2,e3 (R[3*r+c]).  out is row-major with leading dimension ld.
+
+// S = [[s00,s01,0],[s10,s11,0],[0,0,s22]]
+__device__ __forceinline__ void rtsr_diag(const double *R, double s00, double s01, double s10,
+                                          double s11, double s22, double *out, int ld)
 {
-    double W[3][3];                      // W = S R
+    double W0[3], W1[3], W2[3];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-            W[r][q] = S[r][0] * R[q] + S[r][1] * R[3 + q] + S[r][2] * R[6 + q];
+    for (int q = 0; q < 3; ++q) {
+        W0[q] = s00 * R[q] + s01 * R[3 + q];
+        W1[q] = s10 * R[q] + s11 * R[3 + q];
+        W2[q] = s22 * R[6 + q];
+    }
 #pragma unroll
     for (int p = 0; p < 3; ++p)
 #pragma unroll
         for (int q = 0; q < 3; ++q)
-            acc[(r0 + p) * ld + c0 + q] += R[p] * W[0][q] + R[3 + p] * W[1][q] + R[6 + p] * W[2][q];
+            out[p * ld + q] = R[p] * W0[q] + R[3 + p] * W1[q] + R[6 + p] * W2[q];
+}
+
+// S = [[0,0,0],[0,0,0],[a,b,0]]  (row w couples to theta_x, theta_y):  out = e3^T (a e1 + b e2)
+__device__ __forceinline__ void rtsr_row(const double *R, double a, double b, double *out, int ld)
+{
+    double w[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) w[q] = a * R[q] + b * R[3 + q];
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) out[p * ld + q] = R[6 + p] * w[q];
+}
+
+// S = [[0,0,a],[0,0,b],[0,0,0]]:  out = (a e1 + b e2)^T e3
+__device__ __forceinline__ void rtsr_col(const double *R, double a, double b, double *out, int ld)
+{
+    double v[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) v[p] = a * R[p] + b * R[3 + p];
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) out[p * ld + q] = v[p] * R[6 + q];
 }
 
 // shape-function gradients of the CST in the reference local axes: node 0,1,2 -> (bx, by)*2A
@@ -42,60 +78,38 @@ __device__ __forceinline__ void cst_grad(int n, double X2, double X3, double Y3,
     by = (n == 0) ? (X3 - X2) : (n == 1 ? -X3 : X2);
 }
 
-// K_ab (6x6, global axes) of shell e, added into acc[6][6] (row-major, ld = 7 for frame mixing)
-__device__ __forceinline__ void shell_block(const CbStiffArgs &A, int e, int a, int b, double *acc,
-                                            int ld)
+// K_ab (6x6, global axes) of shell e -> blk (row-major, leading dimension ld)
+// membrane  shell.c:487-531, DKT bending (precomputed) shell.c:533-658, drilling shell.c:482-484,
+// geometric shell.c:660-840, rotation shell.c:285-305 + misc.c:41-69
+__device__ __forceinline__ void shell_block(const CbDev &d, int e, int a, int b, double *blk, int ld)
 {
-    const double *sc = A.d.sh_const + (long)e * CB_SH_CONST;
-    const double *fr = A.sh_frame + (long)e * CB_SH_FRAME;
-    double R[9];
+    const double2 *kr2 = reinterpret_cast<const double2 *>(d.sh_Nm + (long)e * CB_SH_KREC);
+    double kr[CB_SH_KREC];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = fr[i];
-    const double E = sc[0], nu = sc[1], t = sc[2], A0 = sc[4], X2 = sc[5], X3 = sc[6], Y3 = sc[7];
-    const double C00 = E / (1 - nu * nu), C01 = C00 * nu, C22 = C00 * (1 - nu) / 2;
+    for (int i = 0; i < CB_SH_KREC / 2; ++i) { double2 v = kr2[i]; kr[2 * i] = v.x; kr[2 * i + 1] = v.y; }
+    const double *R = kr;
     double bxa, bya, bxb, byb;
-    cst_grad(a, X2, X3, Y3, bxa, bya);
-    cst_grad(b, X2, X3, Y3, bxb, byb);
-    // membrane (shell.c:487-531): t*A0 * Bm_a^T C Bm_b with Bm = grad/(2 A0)
-    const double sm = t * A0 / (4 * A0 * A0);
-    double m00 = sm * (C00 * bxa * bxb + C22 * bya * byb);
-    double m01 = sm * (C01 * bxa * byb + C22 * bya * bxb);
-    double m10 = sm * (C01 * bya * bxb + C22 * bxa * byb);
-    double m11 = sm * (C00 * bya * byb + C22 * bxa * bxb);
-    double g = 0.0;
-    if (A.d.ANAFLAG == 2) {
-        // geometric (shell.c:660-840): A_def * Bnl^T N Bnl, Bnl = grad/(2 A_def)
-        const double Ad = fr[9];
-        const double *Nm = A.d.sh_Nm + (long)e * 4;
-        g = (bxa * (Nm[0] * bxb + Nm[2] * byb) + bya * (Nm[2] * bxb + Nm[1] * byb)) / (4 * Ad);
-    }
-    // bending 3x3 sub-block of the precomputed DKT matrix (rows w,tx,ty of a; cols of b)
-    const double *kb = A.d.sh_keb + (long)e * 81 + (3 * a) * 9 + 3 * b;
+    cst_grad(a, kr[9], kr[10], kr[11], bxa, bya);
+    cst_grad(b, kr[9], kr[10], kr[11], bxb, byb);
+    const double m00 = kr[12] * bxa * bxb + kr[14] * bya * byb;
+    const double m01 = kr[13] * bxa * byb + kr[14] * bya * bxb;
+    const double m10 = kr[13] * bya * bxb + kr[14] * bxa * byb;
+    const double m11 = kr[12] * bya * byb + kr[14] * bxa * bxb;
+    const double g = bxa * (kr[15] * bxb + kr[17] * byb) + bya * (kr[17] * bxb + kr[16] * byb);
+    // bending 3x3 sub-block (rows w,tx,ty of a; cols of b), stored block-contiguous
+    const double *kb = d.sh_keb + (long)e * 81 + (3 * a + b) * 9;
     const double k00 = kb[0], k01 = kb[1], k02 = kb[2];
-    const double k10 = kb[9], k11 = kb[10], k12 = kb[11];
-    const double k20 = kb[18], k21 = kb[19], k22 = kb[20];
-    double drill = 0.0;
-    if (a == b) drill = A.d.sh_keb[(long)e * 81 + (3 * a + 1) * 10] / 10000;   // shell.c:482-484
-    {   // translation-translation
-        const double S[3][3] = {{m00 + g, m01, 0}, {m10, m11 + g, 0}, {0, 0, k00 + g}};
-        rtsr_add(R, S, acc, 0, 0, ld);
-    }
-    {   // translation(row) - rotation(col): w row couples to theta_x, theta_y
-        const double S[3][3] = {{0, 0, 0}, {0, 0, 0}, {k01, k02, 0}};
-        rtsr_add(R, S, acc, 0, 3, ld);
-    }
-    {   // rotation(row) - translation(col)
-        const double S[3][3] = {{0, 0, k10}, {0, 0, k20}, {0, 0, 0}};
-        rtsr_add(R, S, acc, 3, 0, ld);
-    }
-    {   // rotation - rotation, drilling stiffness on theta_z
-        const double S[3][3] = {{k11, k12, 0}, {k21, k22, 0}, {0, 0, drill}};
-        rtsr_add(R, S, acc, 3, 3, ld);
-    }
+    const double k10 = kb[3], k11 = kb[4], k12 = kb[5];
+    const double k20 = kb[6], k21 = kb[7], k22 = kb[8];
+    const double drill = (a == b) ? k11 / 10000 : 0.0;
+    rtsr_diag(R, m00 + g, m01, m10, m11 + g, k00 + g, blk, ld);             // translation-translation
+    rtsr_row(R, k01, k02, blk + 3, ld);                                     // translation-rotation
+    rtsr_col(R, k10, k20, blk + 3 * ld, ld);                                // rotation-translation
+    rtsr_diag(R, k11, k12, k21, k22, drill, blk + 3 * ld + 3, ld);          // rotation-rotation
 }
 
 // K_ab (3x3) of truss e (truss.c:102-166)
-__device__ __forceinline__ void truss_block(const CbStiffArgs &A, int e, int a, int b, double *acc,
+__device__ __forceinline__ void truss_block(const CbStiffArgs &A, int e, int a, int b, double *blk,
                                             int ld)
 {
     const double *tc = A.d.tr_const + (long)e * CB_TR_CONST;
@@ -114,11 +128,194 @@ __device__ __forceinline__ void truss_block(const CbStiffArgs &A, int e, int a, 
     for (int p = 0; p < 3; ++p)
 #pragma unroll
         for (int q = 0; q < 3; ++q)
-            acc[p * ld + q] += s * (k * c[p] * c[q] + ((p == q) ? gN : 0.0));
+            blk[p * ld + q] = s * (k * c[p] * c[q] + ((p == q) ? gN : 0.0));
 }
 
 // ------------------------------------------------------------------------------------------
-// the assembly kernel: one thread per node-pair block
+// CSC: tile kernel.  ND = largest DOF count per joint among the model's element types.
+// Persistent CTAs (grid = resident CTAs), software-pipelined over tiles: the header, the
+// contribution record and the element inputs of the NEXT tile are requested while the current
+// tile is being reduced and written out, so no HBM round trip sits on the critical path.
+// shared memory: stage[ND*ND][CB_TILE_T+1] doubles | obuf[tile_smem_out] doubles |
+//                spair[CB_TILE_T] pair records | ndof[CB_TILE_T]
+// ------------------------------------------------------------------------------------------
+struct ShellIn {               // inputs of one shell contribution
+    double kr[CB_SH_KREC];     // stiffness-pass record of the element
+    double kb[10];             // its 3x3 DKT sub-block for (a,b), contribution-ordered copy
+};
+
+__device__ __forceinline__ void shell_load(const CbStiffArgs &A, const CbContrib &ct, long cidx,
+                                           ShellIn &in)
+{
+    const double2 *kr2 = reinterpret_cast<const double2 *>(A.d.sh_Nm + (long)ct.e * CB_SH_KREC);
+#pragma unroll
+    for (int i = 0; i < CB_SH_KREC / 2; ++i) { double2 v = __ldg(kr2 + i); in.kr[2 * i] = v.x; in.kr[2 * i + 1] = v.y; }
+    const double2 *kb2 = reinterpret_cast<const double2 *>(A.kebc + cidx * 10);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { double2 v = __ldg(kb2 + i); in.kb[2 * i] = v.x; in.kb[2 * i + 1] = v.y; }
+}
+
+// K_ab (6x6, global axes) from preloaded inputs, written straight to the stage column of thread t
+template <int ND>
+__device__ __forceinline__ void shell_block_stage(const ShellIn &in, int a, int b, double *stg)
+{
+    constexpr int STR = CB_TILE_T + 1;
+    const double *R = in.kr;
+    double bxa, bya, bxb, byb;
+    cst_grad(a, in.kr[9], in.kr[10], in.kr[11], bxa, bya);
+    cst_grad(b, in.kr[9], in.kr[10], in.kr[11], bxb, byb);
+    const double m00 = in.kr[12] * bxa * bxb + in.kr[14] * bya * byb;
+    const double m01 = in.kr[13] * bxa * byb + in.kr[14] * bya * bxb;
+    const double m10 = in.kr[13] * bya * bxb + in.kr[14] * bxa * byb;
+    const double m11 = in.kr[12] * bya * byb + in.kr[14] * bxa * bxb;
+    const double g = bxa * (in.kr[15] * bxb + in.kr[17] * byb) + bya * (in.kr[17] * bxb + in.kr[16] * byb);
+    const double *kb = in.kb;
+    const double drill = (a == b) ? kb[4] / 10000 : 0.0;
+    double s[9];
+    rtsr_diag(R, m00 + g, m01, m10, m11 + g, kb[0] + g, s, 3);
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) stg[(p * ND + q) * STR] = s[p * 3 + q];
+    rtsr_row(R, kb[1], kb[2], s, 3);
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) stg[(p * ND + 3 + q) * STR] = s[p * 3 + q];
+    rtsr_col(R, kb[3], kb[6], s, 3);
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) stg[((3 + p) * ND + q) * STR] = s[p * 3 + q];
+    rtsr_diag(R, kb[4], kb[5], kb[7], kb[8], drill, s, 3);
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) stg[((3 + p) * ND + 3 + q) * STR] = s[p * 3 + q];
+}
+
+template <int ND>
+__global__ void __launch_bounds__(CB_TILE_T, (ND <= 6) ? 4 : 3)
+k_assemble_tiles(CbStiffArgs A)
+{
+    extern __shared__ double smem[];
+    constexpr int STR = CB_TILE_T + 1;
+    constexpr int NN = ND * ND;
+    double *stage = smem;
+    double *obuf = smem + ((NN * STR + 1) & ~1);           // 16-byte aligned
+    CbTPair *spair = reinterpret_cast<CbTPair *>(obuf + A.tile_smem_out);       // [CB_TILE_T]
+    unsigned char *ndof = reinterpret_cast<unsigned char *>(spair + CB_TILE_T);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+    long tile = blockIdx.x;
+    if (tile >= A.ntiles) return;
+    CbTile tl = A.tiles[tile];
+    CbContrib ct{};
+    if (t < tl.nc) ct = A.contribs[tl.c0 + t];
+    ShellIn in;
+    if (ND >= 6 && t < tl.nc && ct.type == CB_T_SHELL) shell_load(A, ct, (long)tl.c0 + t, in);
+
+    for (;;) {
+        const long next = tile + gridDim.x;
+        const bool has_next = next < A.ntiles;
+        CbTile tln = tl;
+        if (has_next) tln = A.tiles[next];                 // requested now, needed after phase 1
+        if (t < tl.np) spair[t] = A.tpairs[tl.p0 + t];
+
+        // ---- phase 1: one contribution per thread -> its column of `stage` ---------------------
+        if (t < tl.nc) {
+            double *stg = stage + t;
+            if (ct.type == CB_T_SHELL) {
+                if constexpr (ND >= 6) {
+                    if (ND > 6) {
+#pragma unroll
+                        for (int i = 0; i < NN; ++i) stg[i * STR] = 0.0;
+                    }
+                    shell_block_stage<ND>(in, ct.a, ct.b, stg);
+                }
+                ndof[t] = 6;
+            } else {
+                double blk[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) blk[i] = 0.0;
+                if (ct.type == CB_T_TRUSS) truss_block(A, ct.e, ct.a, ct.b, blk, 3);
+#pragma unroll
+                for (int i = 0; i < NN; ++i) stg[i * STR] = 0.0;
+#pragma unroll
+                for (int p = 0; p < 3; ++p)
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) stg[(p * ND + q) * STR] = blk[p * 3 + q];
+                ndof[t] = 3;
+            }
+        }
+        // request the next tile's contribution record, then its element inputs; they land while
+        // this tile is reduced and written out
+        CbContrib ctn{};
+        if (has_next && t < tln.nc) ctn = A.contribs[tln.c0 + t];
+        __syncthreads();
+        if (ND >= 6 && has_next && t < tln.nc && ctn.type == CB_T_SHELL)
+            shell_load(A, ctn, (long)tln.c0 + t, in);
+
+        // ---- phase 2: segmented reduction over the sorted contribution list, one thread per
+        // (joint-pair block, column): ND rows of `stage` summed over the block's contributions in
+        // reference order, written as one contiguous column run of the tile's output image.  The
+        // image is shifted by the parity of out0 so phase 3 can use aligned 16-byte accesses.
+        const int shift = (int)(tl.out0 & 1);
+        const int nitems = tl.np * ND;
+        for (int it = t; it < nitems; it += CB_TILE_T) {
+            const int p = it / ND, c = it - p * ND;
+            const CbTPair pr = spair[p];
+            constexpr unsigned FULL = (1u << ND) - 1u;
+            if (pr.maskA == FULL && pr.maskB == FULL && !A.mixed) {
+                const double *src = stage + c * STR + pr.cs;
+                double acc[ND];
+#pragma unroll
+                for (int r = 0; r < ND; ++r) acc[r] = src[r * ND * STR];
+                for (int q = 1; q < pr.cnt; ++q) {
+#pragma unroll
+                    for (int r = 0; r < ND; ++r) acc[r] += src[r * ND * STR + q];
+                }
+                double *dst = obuf + shift + pr.rel + c * pr.colh;
+#pragma unroll
+                for (int r = 0; r < ND; ++r) dst[r] = acc[r];
+            } else {
+                if (!((pr.maskB >> c) & 1)) continue;
+                const int cc = __popc(pr.maskB & ((1u << c) - 1));
+                double *dst = obuf + shift + pr.rel + cc * pr.colh;
+                int rr = 0;
+                for (int r = 0; r < ND; ++r) {
+                    if (!((pr.maskA >> r) & 1)) continue;
+                    const double *src = stage + (r * ND + c) * STR + pr.cs;
+                    double sum = 0.0;
+                    for (int q = 0; q < pr.cnt; ++q)
+                        if (!A.mixed || (r < ndof[pr.cs + q] && c < ndof[pr.cs + q])) sum += src[q];
+                    dst[rr++] = sum;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 3: stream the tile's output image to HBM (coalesced, 16-byte vectors) --------
+        {
+            double *dst = A.out + tl.out0;
+            const double *img = obuf + shift;
+            if (shift && t == 0) dst[0] = img[0];
+            const int nv = (tl.nout - shift) >> 1;                   // aligned pairs
+            const double2 *img2 = reinterpret_cast<const double2 *>(img + shift);
+            double2 *dst2 = reinterpret_cast<double2 *>(dst + shift);
+            for (int i = t; i < nv; i += CB_TILE_T) dst2[i] = img2[i];
+            const int tail = shift + 2 * nv;
+            if (tail < tl.nout && t == CB_TILE_T - 1) dst[tail] = img[tail];
+        }
+
+        if (!has_next) break;
+        tile = next; tl = tln; ct = ctn;
+        __syncthreads();          // obuf / spair are rewritten by the next iteration
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// skyline: one thread per node-pair block
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CB_TPB_K)
 k_assemble_blocks(CbStiffArgs A)
@@ -131,11 +328,23 @@ k_assemble_blocks(CbStiffArgs A)
     for (int i = 0; i < 49; ++i) acc[i] = 0.0;
     for (int c = 0; c < pr.ccount; ++c) {
         const CbContrib ct = A.contribs[pr.cstart + c];
-        if (ct.type == CB_T_SHELL) shell_block(A, ct.e, ct.a, ct.b, acc, 7);
-        else if (ct.type == CB_T_TRUSS) truss_block(A, ct.e, ct.a, ct.b, acc, 7);
+        if (ct.type == CB_T_SHELL) {
+            double blk[36];
+            shell_block(A.d, ct.e, ct.a, ct.b, blk, 6);
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int q = 0; q < 6; ++q) acc[r * 7 + q] += blk[r * 6 + q];
+        } else if (ct.type == CB_T_TRUSS) {
+            double blk[9];
+            truss_block(A, ct.e, ct.a, ct.b, blk, 3);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) acc[r * 7 + q] += blk[r * 3 + q];
+        }
     }
     if (!A.skyline) {
-        // CSC: column cc of node B is contiguous; rows of node A start at pr.off inside it
         int cc = 0;
 #pragma unroll
         for (int c = 0; c < 7; ++c) {
@@ -171,11 +380,43 @@ k_assemble_blocks(CbStiffArgs A)
     }
 }
 
+template <int ND>
+static int launch_tiles(const CbStiffArgs &a, cudaStream_t s)
+{
+    const size_t smem = (size_t)(((ND * ND * (CB_TILE_T + 1) + 1) & ~1) + a.tile_smem_out) * sizeof(double) +
+                        CB_TILE_T * sizeof(CbTPair) + CB_TILE_T;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_assemble_tiles<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024) != cudaSuccess)
+            return 1;
+        configured = true;
+    }
+    if (smem > 200 * 1024) return 1;
+    int per_sm = 0, dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_tiles<ND>, CB_TILE_T, smem) !=
+            cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    long grid = (long)per_sm * nsm;                    // persistent: one wave of resident CTAs
+    if (grid > a.ntiles) grid = a.ntiles;
+    k_assemble_tiles<ND><<<(unsigned)grid, CB_TILE_T, smem, s>>>(a);
+    return cudaGetLastError() != cudaSuccess;
+}
+
 int cbk_stiff(const CbStiffArgs &a, cudaStream_t s, long *launches)
 {
-    if (a.npairs == 0) return 0;
-    unsigned g = (unsigned)((a.npairs + CB_TPB_K - 1) / CB_TPB_K);
-    k_assemble_blocks<<<g, CB_TPB_K, 0, s>>>(a);
+    if (a.skyline || a.tiles == nullptr) {
+        if (a.npairs == 0) return 0;
+        unsigned g = (unsigned)((a.npairs + CB_TPB_K - 1) / CB_TPB_K);
+        k_assemble_blocks<<<g, CB_TPB_K, 0, s>>>(a);
+        ++*launches;
+        return cudaGetLastError() != cudaSuccess;
+    }
+    if (a.ntiles == 0) return 0;
     ++*launches;
-    return cudaGetLastError() != cudaSuccess;
+    if (a.max_dof <= 3) return launch_tiles<3>(a, s);
+    if (a.max_dof <= 6) return launch_tiles<6>(a, s);
+    return launch_tiles<7>(a, s);
 }

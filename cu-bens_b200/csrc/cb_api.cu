@@ -90,6 +90,7 @@ struct cb_handle {
     long j0 = 0, j1 = 0;          // owned joints
     bool plan_ready = false;
     bool keb_dirty = true;
+    bool krec_fresh = false;      // krec written by the last force pass describes the *_i state
 
     // host copies needed after create
     std::vector<int32_t> h_jc;    // [NJ][8]
@@ -308,21 +309,22 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
     // ---- shells ----------------------------------------------------------------------------
     if (SH) {
         const long pe = TR + FR, pc = TR + 3 * FR;
+        // component-major (SoA) host images, see cb_internal.h
         std::vector<double> c((size_t)SH * CB_SH_CONST, 0.0), fr((size_t)SH * CB_SH_FRAME),
-            dsl(m->slength, m->slength + (size_t)SH * 3), dn((size_t)SH, 0.0);
+            dsl((size_t)SH * 3), dn((size_t)SH, 0.0);
+        auto C = [&](int comp, long e) -> double & { return c[(size_t)comp * SH + e]; };
+        auto F = [&](int comp, long e) -> double & { return fr[(size_t)comp * SH + e]; };
         for (long e = 0; e < SH; ++e) {
-            double *q = &c[e * CB_SH_CONST];
-            q[0] = m->emod[pe + e]; q[1] = m->nu[e]; q[2] = m->thick[e];
-            q[3] = pow(m->thick[e], 3);                 // libm, as shell.c:545 evaluates it
-            q[4] = m->farea[e];
-            q[5] = m->xlocal[e * 3]; q[6] = m->xlocal[e * 3 + 1]; q[7] = m->xlocal[e * 3 + 2];
-            q[8] = m->slength[e * 3]; q[9] = m->slength[e * 3 + 1]; q[10] = m->slength[e * 3 + 2];
-            double *f = &fr[e * CB_SH_FRAME];
+            C(0, e) = m->emod[pe + e]; C(1, e) = m->nu[e]; C(2, e) = m->thick[e];
+            C(3, e) = pow(m->thick[e], 3);              // libm, as shell.c:545 evaluates it
+            C(4, e) = m->farea[e];
             for (int k = 0; k < 3; ++k) {
-                f[k] = m->c1[pc + e * 3 + k]; f[3 + k] = m->c2[pc + e * 3 + k];
-                f[6 + k] = m->c3[pc + e * 3 + k];
+                C(5 + k, e) = m->xlocal[e * 3 + k]; C(8 + k, e) = m->slength[e * 3 + k];
+                dsl[(size_t)k * SH + e] = m->slength[e * 3 + k];
+                F(k, e) = m->c1[pc + e * 3 + k]; F(3 + k, e) = m->c2[pc + e * 3 + k];
+                F(6 + k, e) = m->c3[pc + e * 3 + k];
             }
-            f[9] = m->farea[e];                          // deffarea = farea (main.c:1700)
+            F(9, e) = m->farea[e];                       // deffarea = farea (main.c:1700)
             if (m->dens) dn[e] = m->dens[e];             // pdens+i, shell.c:61 / 1551
         }
         if (h->sh_const.upload(c) || h->sh_dens.upload(dn) || h->sh_keb.alloc((size_t)SH * 81) ||
@@ -608,7 +610,7 @@ extern "C" int cb_begin_increment(cb_handle *h)
     }
     bad |= d2d(h->sh_ef[h->eP].p, h->sh_ef[0].p, (size_t)SH * 18, s);
     bad |= d2d(h->tr_ef[h->eP].p, h->tr_ef[0].p, (size_t)TR * 2, s);
-    h->i_is_ip = true;
+    h->i_is_ip = true; h->krec_fresh = false;
     if (bad) return fail(CB_ERR_CUDA, "cb_begin_increment: device copy failed");
     return CB_OK;
 }
@@ -658,9 +660,10 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
     a.tr_frame = h->tr_frame[g].p; a.tr_ef = h->tr_ef[ge].p;
     a.contribs = h->contribs.p;
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    if (h->sz.NE_SH) {
+    if (h->sz.NE_SH && !(gen != CB_GEN_COMMITTED && h->krec_fresh && h->i_is_ip)) {
         if (cbk_shell_prep(a.d, a.x, a.sh_frame, h->stream)) return fail(CB_ERR_CUDA, "prep launch");
         ++h->launches;
+        h->krec_fresh = (gen != CB_GEN_COMMITTED) && h->i_is_ip;
     }
     a.max_dof = h->max_dof; a.mixed = h->mixed;
     CUDA_TRY(cudaEventRecord(h->ev2, h->stream));
@@ -731,7 +734,7 @@ extern "C" int cb_update_forces_dev(cb_handle *h, const double *dd_dev, double *
     ++h->launches;
     CUDA_TRY(cudaEventRecord(h->ev5, s));
     std::swap(h->eP, h->eN);                      // ef_ip <- ef_i (main.c:1982-1984) by renaming
-    h->forces_timed = true;
+    h->forces_timed = true; h->krec_fresh = true;
     return CB_OK;
 }
 
@@ -785,6 +788,7 @@ extern "C" int cb_mass(cb_handle *h)
                  &h->launches))
         return fail(CB_ERR_CUDA, "mass launch");
     h->keb_dirty = true;      // farea / slength were refreshed from x (App. B.5)
+    h->krec_fresh = false;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return CB_OK;
 }
@@ -914,7 +918,8 @@ extern "C" const int *cb_dev_Ai(cb_handle *h)
 struct View {          // where a reference array lives on the device
     long n = 0;        // reference length
     // per element type: device buffer, record stride, offset inside the record, items per element
-    struct Part { double *p; long ne; int stride, off, cnt; } part[3];
+    // soa: component c of element e at p[(off+c)*ne + e]; else p[e*stride + off + c]
+    struct Part { double *p; long ne; int stride, off, cnt; bool soa; } part[3];
     int nparts = 0;
     double *flat = nullptr;   // plain vector (nodes / NEQ)
 };
@@ -925,26 +930,26 @@ static int make_view(cb_handle *h, int which, View &v)
     const int gi = h->i_is_ip ? h->gP : h->gN, gp = h->gP;
     auto cosines = [&](int g, int row) {
         v.n = TR + 3 * FR + 3 * SH;
-        v.part[0] = {h->tr_frame[g].p, TR, CB_TR_FRAME, row, 1};
-        v.part[1] = {h->fr_frame[g].p, FR, CB_FR_FRAME, 3 * row, 3};
-        v.part[2] = {h->sh_frame[g].p, SH, CB_SH_FRAME, 3 * row, 3};
+        v.part[0] = {h->tr_frame[g].p, TR, CB_TR_FRAME, row, 1, false};
+        v.part[1] = {h->fr_frame[g].p, FR, CB_FR_FRAME, 3 * row, 3, false};
+        v.part[2] = {h->sh_frame[g].p, SH, CB_SH_FRAME, 3 * row, 3, true};
         v.nparts = 3;
     };
     auto efv = [&](int g) {
         v.n = 2 * TR + 14 * FR + 18 * SH;
-        v.part[0] = {h->tr_ef[g].p, TR, 2, 0, 2};
-        v.part[1] = {h->fr_ef[g].p, FR, 14, 0, 14};
-        v.part[2] = {h->sh_ef[g].p, SH, 18, 0, 18};
+        v.part[0] = {h->tr_ef[g].p, TR, 2, 0, 2, false};
+        v.part[1] = {h->fr_ef[g].p, FR, 14, 0, 14, false};
+        v.part[2] = {h->sh_ef[g].p, SH, 18, 0, 18, true};
         v.nparts = 3;
     };
     auto dll = [&](int g) {
         v.n = TR + FR;
-        v.part[0] = {h->tr_frame[g].p, TR, CB_TR_FRAME, 3, 1};
-        v.part[1] = {h->fr_frame[g].p, FR, CB_FR_FRAME, 9, 1};
+        v.part[0] = {h->tr_frame[g].p, TR, CB_TR_FRAME, 3, 1, false};
+        v.part[1] = {h->fr_frame[g].p, FR, CB_FR_FRAME, 9, 1, false};
         v.nparts = 2;
     };
-    auto dfa = [&](int g) { v.n = SH; v.part[0] = {h->sh_frame[g].p, SH, CB_SH_FRAME, 9, 1}; v.nparts = 1; };
-    auto dslv = [&](int g) { v.n = 3 * SH; v.part[0] = {h->sh_dsl[g].p, SH, 3, 0, 3}; v.nparts = 1; };
+    auto dfa = [&](int g) { v.n = SH; v.part[0] = {h->sh_frame[g].p, SH, CB_SH_FRAME, 9, 1, true}; v.nparts = 1; };
+    auto dslv = [&](int g) { v.n = 3 * SH; v.part[0] = {h->sh_dsl[g].p, SH, 3, 0, 3, true}; v.nparts = 1; };
     switch (which) {
     case CB_ARR_X: v.n = NJ * 3; v.flat = h->x.p; break;
     case CB_ARR_X_TEMP: v.n = NJ * 3; v.flat = h->x_temp.p; break;
@@ -973,12 +978,12 @@ static int make_view(cb_handle *h, int which, View &v)
     case CB_ARR_DEFSLEN: dslv(0); break;
     case CB_ARR_DEFSLEN_I: dslv(gi); break;
     case CB_ARR_DEFSLEN_IP: dslv(gp); break;
-    case CB_ARR_FAREA: v.n = SH; v.part[0] = {h->sh_const.p, SH, CB_SH_CONST, 4, 1}; v.nparts = 1; break;
-    case CB_ARR_SLENGTH: v.n = 3 * SH; v.part[0] = {h->sh_const.p, SH, CB_SH_CONST, 8, 3}; v.nparts = 1; break;
+    case CB_ARR_FAREA: v.n = SH; v.part[0] = {h->sh_const.p, SH, CB_SH_CONST, 4, 1, true}; v.nparts = 1; break;
+    case CB_ARR_SLENGTH: v.n = 3 * SH; v.part[0] = {h->sh_const.p, SH, CB_SH_CONST, 8, 3, true}; v.nparts = 1; break;
     case CB_ARR_LLENGTH:
         v.n = TR + FR;
-        v.part[0] = {h->tr_const.p, TR, CB_TR_CONST, 2, 1};
-        v.part[1] = {h->fr_const.p, FR, CB_FR_CONST, 3, 1};
+        v.part[0] = {h->tr_const.p, TR, CB_TR_CONST, 2, 1, false};
+        v.part[1] = {h->fr_const.p, FR, CB_FR_CONST, 3, 1, false};
         v.nparts = 2; break;
     default: return fail(CB_ERR_UNSUPPORTED, "array id %d is not transferable in this build", which);
     }
@@ -997,7 +1002,7 @@ static int transfer(cb_handle *h, int which, double *host, long n, bool down)
         CUDA_TRY(cudaMemcpy(down ? (void *)host : (void *)v.flat, down ? (void *)v.flat : (void *)host,
                             (size_t)n * sizeof(double),
                             down ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice));
-        if (!down) CUDA_TRY(cudaDeviceSynchronize());
+        if (!down) { CUDA_TRY(cudaDeviceSynchronize()); h->krec_fresh = false; }
         return CB_OK;
     }
     long pos = 0;
@@ -1008,14 +1013,15 @@ static int transfer(cb_handle *h, int which, double *host, long n, bool down)
         CUDA_TRY(cudaMemcpy(tmp.data(), pt.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
         for (long e = 0; e < pt.ne; ++e)
             for (int c = 0; c < pt.cnt; ++c) {
-                double &dv = tmp[(size_t)e * pt.stride + pt.off + c];
+                double &dv = pt.soa ? tmp[(size_t)(pt.off + c) * pt.ne + e]
+                                    : tmp[(size_t)e * pt.stride + pt.off + c];
                 if (down) host[pos] = dv; else dv = host[pos];
                 ++pos;
             }
         if (!down)
             CUDA_TRY(cudaMemcpy(pt.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
-    if (!down) CUDA_TRY(cudaDeviceSynchronize());
+    if (!down) { CUDA_TRY(cudaDeviceSynchronize()); h->krec_fresh = false; }
     return CB_OK;
 }
 

@@ -17,6 +17,9 @@
 #include "cb_internal.h"
 
 #define CB_TPB 128
+#ifndef CB_FORCES_MINB
+#define CB_FORCES_MINB 4
+#endif
 
 __device__ __forceinline__ double dot3(const double *a, const double *b)
 {   // misc.c:252-262: dp = 0; dp += a[i]*b[i]
@@ -103,7 +106,7 @@ k_shell_init_keb(CbDev d, double *__restrict__ keb)
     if (e >= d.NE_SH) return;
     double sc[CB_SH_CONST];
 #pragma unroll
-    for (int i = 0; i < CB_SH_CONST; ++i) sc[i] = d.sh_const[e * CB_SH_CONST + i];
+    for (int i = 0; i < CB_SH_CONST; ++i) sc[i] = SOA(d.sh_const, i, e, d.NE_SH);
     const double E = sc[0], nu = sc[1], t3 = sc[3], A0 = sc[4];
     const double E1 = E * t3 / (12 * (1 - nu * nu));
     const double E3 = E1;
@@ -128,7 +131,7 @@ k_shell_init_keb(CbDev d, double *__restrict__ keb)
         for (int j = 0; j < 9; ++j) {
             double sum = 0;
             for (int k = 0; k < 9; ++k) sum += Q[i][k] * aT[j][k];
-            keb[e * 81 + CB_KEB(i, j)] = sum / (2 * A0);
+            SOA(keb, CB_KEB(i, j), e, d.NE_SH) = sum / (2 * A0);
         }
 }
 
@@ -155,9 +158,8 @@ k_shell_init_kebc(CbDev d, const CbContrib *__restrict__ contribs, long ncontrib
         for (int i = 0; i < 10; ++i) o[i] = 0.0;
         return;
     }
-    const double *kb = d.sh_keb + (long)ct.e * 81 + (3 * ct.a + ct.b) * 9;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) o[i] = kb[i];
+    for (int i = 0; i < 9; ++i) o[i] = SOA(d.sh_keb, (3 * ct.a + ct.b) * 9 + i, ct.e, d.NE_SH);
     o[9] = 0.0;
 }
 
@@ -212,33 +214,21 @@ __device__ __forceinline__ void membrane_dm(const double *xj, const double *xk, 
 }
 
 // ------------------------------------------------------------------------------------------
-// prep for the stiffness pass: membrane force resultants Nm (shell.c:688-704) from the
-// coordinates and triad the stiffness is evaluated at, packed with the triad and the
-// element's membrane coefficients into one 144-byte record per shell.
+// stiffness-pass record (krec) of one shell: triad, reference local coordinates, membrane
+// coefficients t*A0*C/(2A0)^2 and geometric coefficients A_def*Nm/(2A_def)^2, with the membrane
+// force resultants Nm evaluated exactly as stiffg_sh does (shell.c:688-704).  The record is
+// gathered per contribution by the assembly kernel, so it is stored AoS [NE][18]; the 32
+// records of a warp are transposed through shared memory and written as one contiguous run.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CB_TPB)
-k_shell_prep(CbDev d, const double *__restrict__ x, const double *__restrict__ frame)
+__device__ __forceinline__ void shell_krec(const double *sc, const double *R /*[10]*/, double dm2,
+                                           double dm4, double dm5, int anaflag, double *kr)
 {
-    long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (e >= d.NE_SH) return;
-    double sc[CB_SH_CONST], R[CB_SH_FRAME];
-#pragma unroll
-    for (int i = 0; i < CB_SH_CONST; ++i) sc[i] = d.sh_const[e * CB_SH_CONST + i];
-#pragma unroll
-    for (int i = 0; i < CB_SH_FRAME; ++i) R[i] = frame[e * CB_SH_FRAME + i];
-    const int4 nd = reinterpret_cast<const int4 *>(d.sh_nodes)[e];
-    double xj[3], xk[3], xl[3];
-#pragma unroll
-    for (int m = 0; m < 3; ++m) {
-        xj[m] = x[(long)nd.x * 3 + m]; xk[m] = x[(long)nd.y * 3 + m]; xl[m] = x[(long)nd.z * 3 + m];
-    }
-    double dm[6] = {0, 0, 0, 0, 0, 0};
-    membrane_dm(xj, xk, xl, R, sc, dm[2], dm[4], dm[5]);
     double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     plane_stress(sc[0], sc[1], C[0][0], C[0][1], C[2][2]);
     C[1][1] = C[0][0]; C[1][0] = C[0][1];
     double Bm[3][6];
     membrane_B(sc, R[9], Bm);
+    const double dm[6] = {0, 0, dm2, 0, dm4, dm5};
     double Nm[3];
     for (int i = 0; i < 3; ++i) {
         double sum = 0;
@@ -249,16 +239,58 @@ k_shell_prep(CbDev d, const double *__restrict__ x, const double *__restrict__ f
         }
         Nm[i] = sc[2] * sum;
     }
-    // record for the assembly kernel: triad, reference local coordinates, membrane coefficients
-    // t*A0*C/(2A0)^2 and geometric coefficients A_def*Nm/(2A_def)^2 (zero for ANAFLAG 1)
-    double *kr = d.sh_Nm + e * CB_SH_KREC;
 #pragma unroll
     for (int i = 0; i < 9; ++i) kr[i] = R[i];
     kr[9] = sc[5]; kr[10] = sc[6]; kr[11] = sc[7];
     const double smc = sc[2] / (4 * sc[4]);
     kr[12] = smc * C[0][0]; kr[13] = smc * C[0][1]; kr[14] = smc * C[2][2];
-    const double gs = (d.ANAFLAG == 2) ? 1.0 / (4 * R[9]) : 0.0;
+    const double gs = (anaflag == 2) ? 1.0 / (4 * R[9]) : 0.0;
     kr[15] = gs * Nm[0]; kr[16] = gs * Nm[1]; kr[17] = gs * Nm[2];
+}
+
+// all 32 lanes of the warp must call this (kr may be garbage for lanes past the last element)
+__device__ __forceinline__ void warp_store_krec(double *krec_base, long e_warp0, long ne,
+                                                const double *kr, double (*tile)[CB_SH_KREC + 1])
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < CB_SH_KREC; ++i) tile[lane][i] = kr[i];
+    __syncwarp();
+    const long nval = ((ne - e_warp0) < 32 ? (ne - e_warp0) : 32) * CB_SH_KREC;
+    double *dst = krec_base + e_warp0 * CB_SH_KREC;
+    for (int i = lane; i < nval; i += 32) dst[i] = tile[i / CB_SH_KREC][i % CB_SH_KREC];
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone prep for the stiffness pass (used when the record left by the last force pass does
+// not describe the state the stiffness is evaluated at: first iteration of an increment,
+// committed-state stiffness of the arc-length driver, linear analysis)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CB_TPB)
+k_shell_prep(CbDev d, const double *__restrict__ x, const double *__restrict__ frame)
+{
+    __shared__ double tile[CB_TPB / 32][32][CB_SH_KREC + 1];
+    const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const bool live = e < d.NE_SH;
+    double kr[CB_SH_KREC];
+    if (live) {
+        double sc[CB_SH_CONST], R[CB_SH_FRAME];
+#pragma unroll
+        for (int i = 0; i < CB_SH_CONST; ++i) sc[i] = SOA(d.sh_const, i, e, d.NE_SH);
+#pragma unroll
+        for (int i = 0; i < CB_SH_FRAME; ++i) R[i] = SOA(frame, i, e, d.NE_SH);
+        const int4 nd = reinterpret_cast<const int4 *>(d.sh_nodes)[e];
+        double xj[3], xk[3], xl[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            xj[m] = x[(long)nd.x * 3 + m]; xk[m] = x[(long)nd.y * 3 + m]; xl[m] = x[(long)nd.z * 3 + m];
+        }
+        double dm2, dm4, dm5;
+        membrane_dm(xj, xk, xl, R, sc, dm2, dm4, dm5);
+        shell_krec(sc, R, dm2, dm4, dm5, d.ANAFLAG, kr);
+    }
+    warp_store_krec(d.sh_Nm, e - (threadIdx.x & 31), d.NE_SH, kr, tile[threadIdx.x >> 5]);
 }
 
 int cbk_shell_prep(const CbDev &d, const double *x, const double *sh_frame, cudaStream_t s)
@@ -331,35 +363,55 @@ __device__ __forceinline__ void shell_triad(const double *xj, const double *xk, 
 // forces_sh, ANAFLAG 2 (shell.c:1728-1785, 2305-2347, 2386-2397) fused with the shell block of
 // updatc.  One thread per element.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CB_TPB)
+__global__ void __launch_bounds__(CB_TPB, 2)
 k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restrict__ dd,
                const double *__restrict__ frame_ip, double *__restrict__ frame_i,
                double *__restrict__ dsl_i, const double *__restrict__ ef_ip,
                double *__restrict__ ef_i)
 {
-    long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (e >= d.NE_SH) return;
+    // [99][CB_TPB]: the element's DKT matrix (81) and previous end forces (18), copied straight
+    // from HBM by cp.async at kernel entry so their latency overlaps the geometry update; the
+    // region is reused for the krec transposition at the end.
+    extern __shared__ double sbuf[];
+    double (*tile)[32][CB_SH_KREC + 1] = reinterpret_cast<double (*)[32][CB_SH_KREC + 1]>(sbuf);
+    const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const bool live = e < d.NE_SH;
+    double kr[CB_SH_KREC];
+    double *mycol = sbuf + threadIdx.x;
+    if (live) {
+        const unsigned sdst = (unsigned)__cvta_generic_to_shared(mycol);
+#pragma unroll
+        for (int c = 0; c < 81; ++c)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + c * CB_TPB * 8),
+                         "l"(d.sh_keb + (long)c * d.NE_SH + e));
+#pragma unroll
+        for (int c = 0; c < 18; ++c)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + (81 + c) * CB_TPB * 8),
+                         "l"(ef_ip + (long)c * d.NE_SH + e));
+        asm volatile("cp.async.commit_group;");
+    }
+    if (live) {
     double sc[CB_SH_CONST], Rp[CB_SH_FRAME], Ri[CB_SH_FRAME], dsl[3];
 #pragma unroll
-    for (int i = 0; i < CB_SH_CONST; ++i) sc[i] = d.sh_const[e * CB_SH_CONST + i];
+    for (int i = 0; i < CB_SH_CONST; ++i) sc[i] = __ldg(&SOA(d.sh_const, i, e, d.NE_SH));
 #pragma unroll
-    for (int i = 0; i < CB_SH_FRAME; ++i) Rp[i] = frame_ip[e * CB_SH_FRAME + i];
+    for (int i = 0; i < CB_SH_FRAME; ++i) Rp[i] = __ldg(&SOA(frame_ip, i, e, d.NE_SH));
     const int4 nd = reinterpret_cast<const int4 *>(d.sh_nodes)[e];
     const int nn[3] = {nd.x, nd.y, nd.z};
     double X[3][3];
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
-        for (int m = 0; m < 3; ++m) X[a][m] = x_temp[(long)nn[a] * 3 + m];
+        for (int m = 0; m < 3; ++m) X[a][m] = __ldg(&x_temp[(long)nn[a] * 3 + m]);
 
     shell_triad(X[0], X[1], X[2], Ri, dsl);
-#pragma unroll
-    for (int i = 0; i < CB_SH_FRAME; ++i) frame_i[e * CB_SH_FRAME + i] = Ri[i];
-    dsl_i[e * 3 + 0] = dsl[0]; dsl_i[e * 3 + 1] = dsl[1]; dsl_i[e * 3 + 2] = dsl[2];
 
     // membrane: total force from the current local coordinates (shell.c:1729-1744, 1767-1775)
     double dm2, dm4, dm5;
     membrane_dm(X[0], X[1], X[2], Ri, sc, dm2, dm4, dm5);
+    // record for the next stiffness pass: after `_ip <- _i` this triad / area / dm are exactly
+    // what stiff_sh evaluates (shell.c:159-171)
+    shell_krec(sc, Ri, dm2, dm4, dm5, d.ANAFLAG, kr);
     double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     plane_stress(sc[0], sc[1], C[0][0], C[0][1], C[2][2]);
     C[1][1] = C[0][0]; C[1][0] = C[0][1];
@@ -397,14 +449,17 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
         ddb[3 * a + 2] = dot3(Rp + 3, DD[a] + 3);    // theta_y : c2_ip . rotations
     }
     double defb[9];
-    const double *kb = d.sh_keb + e * 81;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");      // own copies only: no barrier needed
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
         double sum = 0;
 #pragma unroll
-        for (int j = 0; j < 9; ++j) sum += kb[CB_KEB(i, j)] * ddb[j];
+        for (int j = 0; j < 9; ++j) sum += mycol[CB_KEB(i, j) * CB_TPB] * ddb[j];
         defb[i] = sum;
     }
+    double efp[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) efp[i] = (i % 6 >= 2) ? mycol[(81 + i) * CB_TPB] : 0.0;
 
     // T_i * T_ip^T is block diagonal with M = R_i R_ip^T (shell.c:2326-2338)
     double M[3][3];
@@ -419,10 +474,10 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
     for (int a = 0; a < 3; ++a) {
         double vt[3], vr[3];
         vt[0] = 0.0; vt[1] = 0.0;
-        vt[2] = defb[3 * a] + ef_ip[e * 18 + 6 * a + 2];
-        vr[0] = defb[3 * a + 1] + ef_ip[e * 18 + 6 * a + 3];
-        vr[1] = defb[3 * a + 2] + ef_ip[e * 18 + 6 * a + 4];
-        vr[2] = 0.0 + ef_ip[e * 18 + 6 * a + 5];
+        vt[2] = defb[3 * a] + efp[6 * a + 2];
+        vr[0] = defb[3 * a + 1] + efp[6 * a + 3];
+        vr[1] = defb[3 * a + 2] + efp[6 * a + 4];
+        vr[2] = 0.0 + efp[6 * a + 5];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             const double et = (r < 2) ? ef_temp[2 * a + r] : 0.0;
@@ -431,7 +486,7 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
         }
     }
 #pragma unroll
-    for (int i = 0; i < 18; ++i) ef_i[e * 18 + i] = efi[i];
+    for (int i = 0; i < 18; ++i) SOA(ef_i, i, e, d.NE_SH) = efi[i];
     // element force in global axes, T_i^T ef_i (shell.c:2388-2392)
 #pragma unroll
     for (int g = 0; g < 6; ++g)
@@ -444,7 +499,18 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
             fg[3 * g + c] = sum;
         }
 #pragma unroll
-    for (int i = 0; i < 18; ++i) d.sh_fg[e * 18 + i] = fg[i];
+    for (int b = 0; b < 3; ++b) {
+        double2 *o = reinterpret_cast<double2 *>(CB_FG(d.sh_fg, b, e, d.NE_SH));
+#pragma unroll
+        for (int i = 0; i < 3; ++i) o[i] = make_double2(fg[6 * b + 2 * i], fg[6 * b + 2 * i + 1]);
+    }
+#pragma unroll
+    for (int i = 0; i < CB_SH_FRAME; ++i) SOA(frame_i, i, e, d.NE_SH) = Ri[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) SOA(dsl_i, i, e, d.NE_SH) = dsl[i];
+    }
+    __syncthreads();          // everyone is done with sbuf before it becomes the krec tile
+    warp_store_krec(d.sh_Nm, e - (threadIdx.x & 31), d.NE_SH, kr, tile[threadIdx.x >> 5]);
 }
 
 // forces_sh, ANAFLAG 1 (shell.c:1695-1727, 2386-2397): ef = k_sh (T D), total displacements
@@ -456,9 +522,9 @@ k_shell_forces_linear(CbDev d, const double *__restrict__ dtot, const double *__
     if (e >= d.NE_SH) return;
     double sc[CB_SH_CONST], R[CB_SH_FRAME];
 #pragma unroll
-    for (int i = 0; i < CB_SH_CONST; ++i) sc[i] = d.sh_const[e * CB_SH_CONST + i];
+    for (int i = 0; i < CB_SH_CONST; ++i) sc[i] = SOA(d.sh_const, i, e, d.NE_SH);
 #pragma unroll
-    for (int i = 0; i < CB_SH_FRAME; ++i) R[i] = frame[e * CB_SH_FRAME + i];
+    for (int i = 0; i < CB_SH_FRAME; ++i) R[i] = SOA(frame, i, e, d.NE_SH);
     const int4 nd = reinterpret_cast<const int4 *>(d.sh_nodes)[e];
     const int nn[3] = {nd.x, nd.y, nd.z};
     double D[3][6], dl[18];
@@ -496,20 +562,19 @@ k_shell_forces_linear(CbDev d, const double *__restrict__ dtot, const double *__
         }
         ef[fm[i]] = acc;
     }
-    const double *kb = d.sh_keb + e * 81;
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
         double sum = 0;
 #pragma unroll
-        for (int j = 0; j < 9; ++j) sum += kb[CB_KEB(i, j)] * dl[fb[j]];
+        for (int j = 0; j < 9; ++j) sum += SOA(d.sh_keb, CB_KEB(i, j), e, d.NE_SH) * dl[fb[j]];
         ef[fb[i]] = sum;
     }
     // drilling stiffness ke_b[1][1]/1e4 etc. (shell.c:482-484)
-    ef[5] = (kb[CB_KEB(1, 1)] / 10000) * dl[5];
-    ef[11] = (kb[CB_KEB(4, 4)] / 10000) * dl[11];
-    ef[17] = (kb[CB_KEB(7, 7)] / 10000) * dl[17];
+    ef[5] = (SOA(d.sh_keb, CB_KEB(1, 1), e, d.NE_SH) / 10000) * dl[5];
+    ef[11] = (SOA(d.sh_keb, CB_KEB(4, 4), e, d.NE_SH) / 10000) * dl[11];
+    ef[17] = (SOA(d.sh_keb, CB_KEB(7, 7), e, d.NE_SH) / 10000) * dl[17];
 #pragma unroll
-    for (int i = 0; i < 18; ++i) ef_out[e * 18 + i] = ef[i];
+    for (int i = 0; i < 18; ++i) SOA(ef_out, i, e, d.NE_SH) = ef[i];
 #pragma unroll
     for (int g = 0; g < 6; ++g)
 #pragma unroll
@@ -518,7 +583,7 @@ k_shell_forces_linear(CbDev d, const double *__restrict__ dtot, const double *__
             sum += R[c] * ef[3 * g];
             sum += R[3 + c] * ef[3 * g + 1];
             sum += R[6 + c] * ef[3 * g + 2];
-            d.sh_fg[e * 18 + 3 * g + c] = sum;
+            CB_FG(d.sh_fg, g / 2, e, d.NE_SH)[(g % 2) * 3 + c] = sum;
         }
 }
 
@@ -594,7 +659,7 @@ k_gather_f(CbDev d, const int32_t *__restrict__ cstart, const CbCorner *__restri
     for (int c = c0; c < c1; ++c) {
         const CbCorner cr = corners[c];
         if (cr.type == CB_T_SHELL) {
-            const double *p = d.sh_fg + (long)cr.e * 18 + cr.b * 6;
+            const double *p = CB_FG(d.sh_fg, cr.b, cr.e, d.NE_SH);
 #pragma unroll
             for (int r = 0; r < 6; ++r) acc[r] += p[r];
         } else if (cr.type == CB_T_FRAME) {
@@ -631,8 +696,16 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
     }
     if (d.NE_SH) {
         unsigned g = (unsigned)((d.NE_SH + CB_TPB - 1) / CB_TPB);
-        k_shell_forces<<<g, CB_TPB, 0, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
-                                            a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i);
+        const size_t smem = (size_t)99 * CB_TPB * sizeof(double);
+        static bool configured = false;
+        if (!configured) {
+            if (cudaFuncSetAttribute(k_shell_forces, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem) != cudaSuccess)
+                return 1;
+            configured = true;
+        }
+        k_shell_forces<<<g, CB_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
+                                               a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i);
         ++*launches;
     }
     return cudaGetLastError() != cudaSuccess;
@@ -672,11 +745,11 @@ k_mass_refresh_shell(CbDev d, const double *__restrict__ x, double *__restrict__
         xj[m] = x[(long)nd.x * 3 + m]; xk[m] = x[(long)nd.y * 3 + m]; xl[m] = x[(long)nd.z * 3 + m];
         el23[m] = xl[m] - xk[m]; el31[m] = xl[m] - xj[m]; el12[m] = xk[m] - xj[m];
     }
-    sh_const[e * CB_SH_CONST + 9] = sqrt(dot3(el23, el23));
-    sh_const[e * CB_SH_CONST + 10] = sqrt(dot3(el31, el31));
-    sh_const[e * CB_SH_CONST + 8] = sqrt(dot3(el12, el12));
+    SOA(sh_const, 9, e, d.NE_SH) = sqrt(dot3(el23, el23));
+    SOA(sh_const, 10, e, d.NE_SH) = sqrt(dot3(el31, el31));
+    SOA(sh_const, 8, e, d.NE_SH) = sqrt(dot3(el12, el12));
     cross3(el12, el31, normal, false);
-    sh_const[e * CB_SH_CONST + 4] = 0.5 * sqrt(dot3(normal, normal));
+    SOA(sh_const, 4, e, d.NE_SH) = 0.5 * sqrt(dot3(normal, normal));
 }
 
 __global__ void __launch_bounds__(CB_TPB)
@@ -703,10 +776,10 @@ k_mass_gather(CbDev d, const int32_t *__restrict__ cstart, const CbCorner *__res
     for (int c = c0; c < c1; ++c) {
         const CbCorner cr = corners[c];
         if (cr.type == CB_T_SHELL) {
-            const double *sc = d.sh_const + (long)cr.e * CB_SH_CONST;
-            const double Mtot = dens_sh[cr.e] * sc[4] * sc[2];
+            const double A0 = SOA(d.sh_const, 4, cr.e, d.NE_SH), th = SOA(d.sh_const, 2, cr.e, d.NE_SH);
+            const double Mtot = dens_sh[cr.e] * A0 * th;
             const double mt = Mtot / 3;
-            const double mr = Mtot / 3 * (sc[2] * sc[2]) / 12;
+            const double mr = Mtot / 3 * (th * th) / 12;
 #pragma unroll
             for (int r = 0; r < 3; ++r) { acc[r] += mt; acc[3 + r] += mr; }
         } else if (cr.type == CB_T_TRUSS) {

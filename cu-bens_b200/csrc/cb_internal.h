@@ -3,9 +3,10 @@
 // Layout in HBM:
 //   nodal arrays  AoS xyz  [NJ][3] doubles, three generations (committed / temp / ip)
 //   jcode         [NJ][8] int32 (7 used) so one node's equation numbers are two 16-byte loads
-//   per-element records are AoS and 16-byte aligned so a thread fetches its element with
-//   128-bit loads: shell constants [NE][12], shell frame state [NE][10] per generation,
-//   element end forces [NE][18|14|2] per generation, DKT bending matrix [NE][81].
+//   per-element shell arrays touched by one thread per element are component-major (SoA):
+//   constants [12][NE], frame state [10][NE] and end forces [18][NE] per generation, deformed side
+//   lengths [3][NE], DKT bending matrix [81][NE]; the stiffness-pass record krec [NE][18] and the
+//   contribution-ordered DKT blocks kebc [ncontrib][10] are gathered per contribution and stay AoS.
 //   NEQ vectors   dd, f_temp, d_temp, d, f, sm.
 //   tangent matrix: CSC values Ax[nnz] (node-block structural pattern) and/or the reference's
 //   skyline vector ss[lss].
@@ -68,7 +69,12 @@ struct CbTPair {
     uint16_t pad;
 };
 
-// DKT bending matrix ke_b[9][9] is stored as nine contiguous 3x3 joint-pair blocks
+// Per-element shell arrays read or written by one thread per element are stored component-major
+// ("SoA": component c of element e at [c*NE + e]) so that a warp's accesses are fully coalesced.
+#define SOA(p, comp, e, ne) (p)[(long)(comp) * (ne) + (e)]
+// staging of element forces in global axes for the joint gather: [local joint][element][6]
+#define CB_FG(p, b, e, ne) ((p) + ((long)(b) * (ne) + (e)) * 6)
+// DKT bending matrix ke_b[9][9]: component index = nine 3x3 joint-pair blocks, block-major
 #define CB_KEB(i, j) ((((i) / 3) * 3 + ((j) / 3)) * 9 + ((i) % 3) * 3 + ((j) % 3))
 #define CB_SH_KREC 18   // per-shell record for the stiffness pass: R[9], X2,X3,Y3, cm00,cm01,cm22, n0,n1,n2
 
@@ -102,10 +108,10 @@ struct CbDev {
     const int32_t *jc;       // [NJ][8]
     // shells
     const int32_t *sh_nodes; // [NE][4] 0-based
-    const double *sh_const;  // [NE][CB_SH_CONST]
-    const double *sh_keb;    // [NE][81]
+    const double *sh_const;  // [CB_SH_CONST][NE]
+    const double *sh_keb;    // [81][NE], component = CB_KEB(i,j)
     double *sh_Nm;           // [NE][CB_SH_KREC] stiffness-pass record written by k_shell_prep
-    double *sh_fg;           // [NE][18] element force in global axes (staging for the gather)
+    double *sh_fg;           // [3][NE][6] element force in global axes (staging for the gather)
     // frames
     const int32_t *fr_nodes; // [NE][2]
     const double *fr_const;  // [NE][CB_FR_CONST]
@@ -127,7 +133,7 @@ struct CbDev {
 struct CbStiffArgs {
     CbDev d;
     const double *x;         // coordinates the stiffness is evaluated at (x_temp or x)
-    const double *sh_frame;  // [NE][CB_SH_FRAME] generation read
+    const double *sh_frame;  // [CB_SH_FRAME][NE] generation read
     const double *sh_ef;     // unused for ANAFLAG<=2 shells
     const double *fr_frame, *fr_ef, *fr_efFE;
     const double *tr_frame, *tr_ef;

@@ -97,10 +97,12 @@ __device__ __forceinline__ void shell_block(const CbDev &d, int e, int a, int b,
     const double m11 = kr[12] * bya * byb + kr[14] * bxa * bxb;
     const double g = bxa * (kr[15] * bxb + kr[17] * byb) + bya * (kr[17] * bxb + kr[16] * byb);
     // bending 3x3 sub-block (rows w,tx,ty of a; cols of b), stored block-contiguous
-    const double *kb = d.sh_keb + (long)e * 81 + (3 * a + b) * 9;
-    const double k00 = kb[0], k01 = kb[1], k02 = kb[2];
-    const double k10 = kb[3], k11 = kb[4], k12 = kb[5];
-    const double k20 = kb[6], k21 = kb[7], k22 = kb[8];
+    double kbv[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) kbv[i] = SOA(d.sh_keb, (3 * a + b) * 9 + i, e, d.NE_SH);
+    const double k00 = kbv[0], k01 = kbv[1], k02 = kbv[2];
+    const double k10 = kbv[3], k11 = kbv[4], k12 = kbv[5];
+    const double k20 = kbv[6], k21 = kbv[7], k22 = kbv[8];
     const double drill = (a == b) ? k11 / 10000 : 0.0;
     rtsr_diag(R, m00 + g, m01, m10, m11 + g, k00 + g, blk, ld);             // translation-translation
     rtsr_row(R, k01, k02, blk + 3, ld);                                     // translation-rotation

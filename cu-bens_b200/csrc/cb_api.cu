@@ -211,7 +211,6 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
         return fail(CB_ERR_UNSUPPORTED, "bricks scatter to the dense layout only in the "
                     "reference (brick.c:383-395, skylin ignores them): use CB_MAT_CSC");
     }
-    if (FR) { delete h; return fail(CB_ERR_UNSUPPORTED, "frame elements: not built yet"); }
     if (BR) { delete h; return fail(CB_ERR_UNSUPPORTED, "brick elements: not built yet"); }
 
 #define BAIL(code) do { int c_ = (code); cb_destroy(h); return c_; } while (0)
@@ -278,6 +277,12 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
                 for (int r = 0; r < 3; ++r)
                     if (mc[e * 6 + a * 3 + r] != m->jcode[(long)h->h_nodes[0][e * 2 + a] * 7 + r])
                         BAIL(fail(CB_ERR_ARG, "mcode of truss %ld disagrees with jcode", e + 1));
+        for (long e = 0; e < FR; ++e)
+            for (int a2 = 0; a2 < 2; ++a2)
+                for (int r = 0; r < 7; ++r)
+                    if (mc[6 * TR + e * 14 + a2 * 7 + r] != m->jcode[(long)h->h_nodes[1][e * 2 + a2] * 7 + r])
+                        BAIL(fail(CB_ERR_UNSUPPORTED, "mcode of frame %ld disagrees with jcode "
+                                  "(released-warping joints are not supported)", e + 1));
         const long o = 6 * TR + 14 * FR;
         for (long e = 0; e < SH; ++e)
             for (int a = 0; a < 3; ++a)
@@ -304,6 +309,46 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
         for (int g = 0; g < 3; ++g) {
             if (h->tr_frame[g].upload(fr) || h->tr_ef[g].alloc((size_t)TR * 2)) BAIL(CB_ERR_CUDA);
             cudaMemset(h->tr_ef[g].p, 0, (size_t)TR * 2 * sizeof(double));
+        }
+    }
+    // ---- frames ----------------------------------------------------------------------------
+    if (FR) {
+        std::vector<double> c((size_t)FR * CB_FR_CONST, 0.0), fr((size_t)FR * CB_FR_FRAME),
+            xfr((size_t)FR * 6), off((size_t)FR * 6, 0.0), fe((size_t)FR * 14, 0.0), dn((size_t)FR, 0.0);
+        std::vector<int32_t> osf(FR, 0), rel((size_t)FR * 5, 0);
+        for (long e = 0; e < FR; ++e) {
+            double *q = &c[e * CB_FR_CONST];
+            const double L = m->llength[TR + e];
+            q[0] = m->emod[TR + e]; q[1] = m->gmod[e]; q[2] = m->carea[TR + e]; q[3] = L;
+            q[4] = L * L; q[5] = pow(L, 3);             // libm, as frame.c:372 evaluates it
+            q[6] = m->istrong[e]; q[7] = m->iweak[e]; q[8] = m->ipolar[e]; q[9] = m->iwarp[e];
+            for (int k = 0; k < 3; ++k) {
+                q[10 + k] = m->auxpt[e * 3 + k];
+                fr[e * CB_FR_FRAME + k] = m->c1[TR + e * 3 + k];
+                fr[e * CB_FR_FRAME + 3 + k] = m->c2[TR + e * 3 + k];
+                fr[e * CB_FR_FRAME + 6 + k] = m->c3[TR + e * 3 + k];
+            }
+            fr[e * CB_FR_FRAME + 9] = L;                 // defllen = llength (main.c:1680)
+            if (m->osflag) osf[e] = m->osflag[e];
+            if (m->mendrel) for (int k = 0; k < 5; ++k) rel[e * 5 + k] = m->mendrel[e * 5 + k];
+            for (int k = 0; k < 6; ++k) {
+                if (m->offset) off[e * 6 + k] = m->offset[e * 6 + k];
+                const long jn = h->h_nodes[1][e * 2 + k / 3];
+                xfr[e * 6 + k] = m->x[jn * 3 + k % 3] + (osf[e] ? off[e * 6 + k] : 0.0);
+            }
+            if (m->efFE_ref) for (int k = 0; k < 14; ++k) fe[e * 14 + k] = m->efFE_ref[e * 14 + k];
+            if (m->dens) dn[e] = m->dens[e];             // prop_fr: pdens+i (frame.c:62)
+        }
+        if (h->fr_const.upload(c) || h->fr_offset.upload(off) || h->fr_osflag.upload(osf) ||
+            h->fr_mendrel.upload(rel) || h->fr_efFE_ref.upload(fe) || h->fr_dens.upload(dn) ||
+            h->fr_fg.alloc((size_t)FR * 14))
+            BAIL(CB_ERR_CUDA);
+        for (int g = 0; g < 3; ++g) {
+            if (h->fr_frame[g].upload(fr) || h->fr_xfr[g].upload(xfr) ||
+                h->fr_efFE[g].alloc((size_t)FR * 14) || h->fr_ef[g].alloc((size_t)FR * 14))
+                BAIL(CB_ERR_CUDA);
+            cudaMemset(h->fr_efFE[g].p, 0, (size_t)FR * 14 * sizeof(double));
+            cudaMemset(h->fr_ef[g].p, 0, (size_t)FR * 14 * sizeof(double));
         }
     }
     // ---- shells ----------------------------------------------------------------------------
@@ -598,7 +643,7 @@ extern "C" int cb_begin_increment(cb_handle *h)
     if (!h) return fail(CB_ERR_ARG, "null handle");
     cudaSetDevice(h->fl.device);
     cudaStream_t s = h->stream;
-    const long TR = h->sz.NE_TR, SH = h->sz.NE_SH;
+    const long TR = h->sz.NE_TR, SH = h->sz.NE_SH, FR = h->sz.NE_FR;
     int bad = 0;
     bad |= d2d(h->d_temp.p, h->d.p, h->sz.NEQ, s);
     bad |= d2d(h->f_temp.p, h->f.p, h->sz.NEQ, s);
@@ -607,7 +652,11 @@ extern "C" int cb_begin_increment(cb_handle *h)
         bad |= d2d(h->sh_frame[g].p, h->sh_frame[0].p, (size_t)SH * CB_SH_FRAME, s);
         bad |= d2d(h->sh_dsl[g].p, h->sh_dsl[0].p, (size_t)SH * 3, s);
         bad |= d2d(h->tr_frame[g].p, h->tr_frame[0].p, (size_t)TR * CB_TR_FRAME, s);
+        bad |= d2d(h->fr_frame[g].p, h->fr_frame[0].p, (size_t)FR * CB_FR_FRAME, s);
+        bad |= d2d(h->fr_efFE[g].p, h->fr_efFE[0].p, (size_t)FR * 14, s);
     }
+    bad |= d2d(h->fr_xfr[1].p, h->fr_xfr[0].p, (size_t)FR * 6, s);
+    bad |= d2d(h->fr_ef[h->eP].p, h->fr_ef[0].p, (size_t)FR * 14, s);
     bad |= d2d(h->sh_ef[h->eP].p, h->sh_ef[0].p, (size_t)SH * 18, s);
     bad |= d2d(h->tr_ef[h->eP].p, h->tr_ef[0].p, (size_t)TR * 2, s);
     h->i_is_ip = true; h->krec_fresh = false;
@@ -627,7 +676,7 @@ extern "C" int cb_commit(cb_handle *h)
     if (!h) return fail(CB_ERR_ARG, "null handle");
     cudaSetDevice(h->fl.device);
     cudaStream_t s = h->stream;
-    const long TR = h->sz.NE_TR, SH = h->sz.NE_SH;
+    const long TR = h->sz.NE_TR, SH = h->sz.NE_SH, FR = h->sz.NE_FR;
     const int gi = h->i_is_ip ? h->gP : h->gN;       // buffer holding the *_i generation
     int bad = 0;
     bad |= d2d(h->d.p, h->d_temp.p, h->sz.NEQ, s);
@@ -638,6 +687,10 @@ extern "C" int cb_commit(cb_handle *h)
     bad |= d2d(h->tr_frame[0].p, h->tr_frame[gi].p, (size_t)TR * CB_TR_FRAME, s);
     bad |= d2d(h->sh_ef[0].p, h->sh_ef[h->eP].p, (size_t)SH * 18, s);
     bad |= d2d(h->tr_ef[0].p, h->tr_ef[h->eP].p, (size_t)TR * 2, s);
+    bad |= d2d(h->fr_frame[0].p, h->fr_frame[gi].p, (size_t)FR * CB_FR_FRAME, s);
+    bad |= d2d(h->fr_efFE[0].p, h->fr_efFE[gi].p, (size_t)FR * 14, s);
+    bad |= d2d(h->fr_xfr[0].p, h->fr_xfr[1].p, (size_t)FR * 6, s);
+    bad |= d2d(h->fr_ef[0].p, h->fr_ef[h->eP].p, (size_t)FR * 14, s);
     if (bad) return fail(CB_ERR_CUDA, "cb_commit: device copy failed");
     return CB_OK;
 }
@@ -658,6 +711,7 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
     a.x = (gen == CB_GEN_COMMITTED) ? h->x.p : h->x_temp.p;
     a.sh_frame = h->sh_frame[g].p; a.sh_ef = h->sh_ef[ge].p;
     a.tr_frame = h->tr_frame[g].p; a.tr_ef = h->tr_ef[ge].p;
+    a.fr_frame = h->fr_frame[g].p; a.fr_ef = h->fr_ef[ge].p; a.fr_efFE = h->fr_efFE[g].p;
     a.contribs = h->contribs.p;
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     if (h->sz.NE_SH && !(gen != CB_GEN_COMMITTED && h->krec_fresh && h->i_is_ip)) {
@@ -701,6 +755,10 @@ static CbForceArgs force_args(cb_handle *h)
     a.sh_dsl_i = h->sh_dsl[h->gN].p;
     a.sh_ef_ip = h->sh_ef[h->eP].p; a.sh_ef_i = h->sh_ef[h->eN].p;
     a.tr_frame_i = h->tr_frame[h->gN].p; a.tr_ef_i = h->tr_ef[h->eN].p;
+    a.fr_frame_ip = h->fr_frame[h->gP].p; a.fr_frame_i = h->fr_frame[h->gN].p;
+    a.fr_xfr_i = h->fr_xfr[1].p;
+    a.fr_ef_ip = h->fr_ef[h->eP].p; a.fr_ef_i = h->fr_ef[h->eN].p;
+    a.fr_efFE_ip = h->fr_efFE[h->gP].p; a.fr_efFE_i = h->fr_efFE[h->gN].p;
     a.node_cstart = h->node_cstart.p; a.corners = h->corners.p; a.f_temp = h->f_temp.p;
     return a;
 }
@@ -766,6 +824,8 @@ extern "C" int cb_forces_linear(cb_handle *h, const double *d, double *f_out)
     // main.c:1776-1792 passes the committed arrays for both generations: ef <- forces(d)
     a.sh_frame_i = h->sh_frame[0].p; a.sh_ef_i = h->sh_ef[0].p;
     a.tr_frame_i = h->tr_frame[0].p; a.tr_ef_i = h->tr_ef[0].p;
+    a.fr_frame_i = h->fr_frame[0].p; a.fr_ef_i = h->fr_ef[0].p; a.fr_efFE_i = h->fr_efFE[0].p;
+    a.fr_xfr_i = h->fr_xfr[0].p;
     a.f_temp = h->f.p;
     if (cbk_forces_linear(a, h->d.p, s, &h->launches)) return fail(CB_ERR_CUDA, "forces launch");
     if (cbk_gather_f(a, s)) return fail(CB_ERR_CUDA, "gather launch");
@@ -783,7 +843,7 @@ extern "C" int cb_mass(cb_handle *h)
     int rc = build_plan(h); if (rc) return rc;
     CbDev d = make_dev(h);
     CUDA_TRY(cudaMemsetAsync(h->sm.p, 0, h->sz.NEQ * sizeof(double), h->stream));
-    if (cbk_mass(d, h->x.p, h->sh_const.p, h->tr_const.p, h->fr_const.p, nullptr, h->tr_dens.p,
+    if (cbk_mass(d, h->x.p, h->sh_const.p, h->tr_const.p, h->fr_const.p, h->fr_xfr[0].p, h->tr_dens.p,
                  h->fr_dens.p, h->sh_dens.p, h->node_cstart.p, h->corners.p, h->sm.p, h->stream,
                  &h->launches))
         return fail(CB_ERR_CUDA, "mass launch");
@@ -978,6 +1038,11 @@ static int make_view(cb_handle *h, int which, View &v)
     case CB_ARR_DEFSLEN: dslv(0); break;
     case CB_ARR_DEFSLEN_I: dslv(gi); break;
     case CB_ARR_DEFSLEN_IP: dslv(gp); break;
+    case CB_ARR_XFR: v.n = 6 * FR; v.flat = h->fr_xfr[0].p; break;
+    case CB_ARR_XFR_TEMP: v.n = 6 * FR; v.flat = h->fr_xfr[1].p; break;
+    case CB_ARR_EFFE: v.n = 14 * FR; v.flat = h->fr_efFE[0].p; break;
+    case CB_ARR_EFFE_I: v.n = 14 * FR; v.flat = h->fr_efFE[gi].p; break;
+    case CB_ARR_EFFE_IP: v.n = 14 * FR; v.flat = h->fr_efFE[gp].p; break;
     case CB_ARR_FAREA: v.n = SH; v.part[0] = {h->sh_const.p, SH, CB_SH_CONST, 4, 1, true}; v.nparts = 1; break;
     case CB_ARR_SLENGTH: v.n = 3 * SH; v.part[0] = {h->sh_const.p, SH, CB_SH_CONST, 8, 3, true}; v.nparts = 1; break;
     case CB_ARR_LLENGTH:

@@ -15,6 +15,7 @@
 // inlined in each of them, mass_tr/fr/sh truss.c:381, frame.c:1314, shell.c:1505; once per model:
 // stiffe_b_sh shell.c:533-658 (DKT bending matrix, geometry-constant).
 #include "cb_internal.h"
+#include "cb_frame_math.cuh"
 
 #define CB_TPB 128
 #ifndef CB_FORCES_MINB
@@ -39,6 +40,15 @@ __device__ __forceinline__ void cross3(const double *a, const double *b, double 
         double len = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
         c[0] /= len; c[1] /= len; c[2] /= len;
     }
+}
+
+// x^3 rounded once (double-double product), standing in for libm pow(x,3) when a length has
+// to be re-cubed on the device (mass_* overwrite llength)
+__device__ __forceinline__ double cube_rn(double x)
+{
+    const double p = x * x, pe = __fma_rn(x, x, -p);
+    const double q = p * x, qe = __fma_rn(p, x, -q);
+    return q + (qe + pe * x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -644,6 +654,178 @@ k_truss_forces_linear(CbDev d, const double *__restrict__ dtot, const double *__
 }
 
 // ------------------------------------------------------------------------------------------
+// frames: updatc (misc.c:112-147) + forces_fr (frame.c:902-1312, ANAFLAG 1 / 2, yldflag == 0).
+// INPLACE = the linear call of main.c:1782 where ef_ip/ef_i and efFE_ip/efFE_i are the same
+// arrays: rows are then updated in place, exactly as the reference does.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void frame_triad(const double *xa, const double *xb, const double *aux,
+                                            double *F /*[10]*/)
+{
+    double el[3], lx[3], ly[3], lz[3], tmp[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) el[m] = xb[m] - xa[m];
+    const double L = sqrt(dot3(el, el));
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { lx[m] = el[m] / L; tmp[m] = aux[m] - xa[m]; }
+    cross3(lx, tmp, lz, true);
+    cross3(lz, lx, ly, true);
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { F[m] = lx[m]; F[3 + m] = ly[m]; F[6 + m] = lz[m]; }
+    F[9] = L;
+}
+
+// y = T x for T = blockdiag(R, R, 1, R, R, 1)  (frame.c:286-295); zeros of T are skipped
+__device__ __forceinline__ void frame_T_apply(const double *R, const double *x, double *y)
+{
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int o = (g < 2) ? 3 * g : 7 + 3 * (g - 2);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) y[o + r] = dot3(R + 3 * r, x + o);
+    }
+    y[6] = 0.0 + 1.0 * x[6]; y[13] = 0.0 + 1.0 * x[13];
+}
+
+__device__ __forceinline__ void frame_Tt_apply(const double *R, const double *x, double *y)
+{
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int o = (g < 2) ? 3 * g : 7 + 3 * (g - 2);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double s = 0;
+            s += R[c] * x[o]; s += R[3 + c] * x[o + 1]; s += R[6 + c] * x[o + 2];
+            y[o + c] = s;
+        }
+    }
+    y[6] = 0.0 + 1.0 * x[6]; y[13] = 0.0 + 1.0 * x[13];
+}
+
+// rigid-link matrix as forces_fr builds it (frame.c:1018-1032)
+__device__ __forceinline__ void frame_rigid_link(const double *off, double (*Tr)[14])
+{
+    for (int i = 0; i < 14; ++i)
+        for (int j = 0; j < 14; ++j) Tr[i][j] = (i == j) ? 1.0 : 0.0;
+    Tr[3][1] = -off[2]; Tr[3][2] = off[1]; Tr[4][0] = off[2]; Tr[4][2] = -off[0];
+    Tr[5][0] = -off[1]; Tr[5][1] = off[0];
+    Tr[10][8] = -off[5]; Tr[10][9] = off[4]; Tr[11][7] = off[5]; Tr[11][9] = -off[3];
+    Tr[12][7] = -off[4]; Tr[12][8] = off[3];
+}
+
+template <bool INPLACE>
+__global__ void __launch_bounds__(64)
+k_frame_forces(CbDev d, const double *__restrict__ x_new, const double *__restrict__ dd,
+               const double *frame_ip, double *frame_i, double *xfr_i, const double *ef_ip,
+               double *ef_i, const double *efFE_ip, double *efFE_i, double dlpf, int itecnt)
+{
+    const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (e >= d.NE_FR) return;
+    const double *fc = d.fr_const + e * CB_FR_CONST;
+    const int nj = d.fr_nodes[e * 2], nk = d.fr_nodes[e * 2 + 1];
+    const int os = d.fr_osflag[e];
+    double Rp[CB_FR_FRAME], Ri[CB_FR_FRAME];
+#pragma unroll
+    for (int i = 0; i < CB_FR_FRAME; ++i) Rp[i] = frame_ip[e * CB_FR_FRAME + i];
+    if (!INPLACE) {
+        // updatc, frame block
+        double xa[3], xb[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            xa[m] = x_new[(long)nj * 3 + m]; xb[m] = x_new[(long)nk * 3 + m];
+            if (os != 0) { xa[m] = xa[m] + d.fr_offset[e * 6 + m]; xb[m] = xb[m] + d.fr_offset[e * 6 + 3 + m]; }
+            xfr_i[e * 6 + m] = xa[m]; xfr_i[e * 6 + 3 + m] = xb[m];
+        }
+        frame_triad(xa, xb, fc + 10, Ri);
+#pragma unroll
+        for (int i = 0; i < CB_FR_FRAME; ++i) frame_i[e * CB_FR_FRAME + i] = Ri[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < CB_FR_FRAME; ++i) Ri[i] = Rp[i];
+    }
+    double k[14][14], eft[14];
+    frame_local_k(d, e, ef_ip, efFE_ip, Rp[9], k, eft);
+    double DD12[14], dl[14], def[14];
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        int q = d.jc[(long)nj * 8 + r]; DD12[r] = q ? dd[q - 1] : 0.0;
+        q = d.jc[(long)nk * 8 + r];     DD12[7 + r] = q ? dd[q - 1] : 0.0;
+    }
+    double Tr[14][14];
+    if (os == 0) {
+        frame_T_apply(Rp, DD12, dl);
+    } else {
+        double DDij[14];
+        frame_rigid_link(d.fr_offset + e * 6, Tr);
+        for (int i = 0; i < 14; ++i) {
+            double s = 0;
+            for (int j = 0; j < 14; ++j) s += Tr[j][i] * DD12[j];
+            DDij[i] = s;
+        }
+        frame_T_apply(Rp, DDij, dl);
+    }
+    for (int i = 0; i < 14; ++i) {
+        double s = 0;
+        for (int j = 0; j < 14; ++j) s += k[i][j] * dl[j];
+        def[i] = s;
+    }
+    // M = T_i T_ip^T: four copies of R_i R_ip^T and 1 on the warping DOFs (frame.c:1078-1086)
+    double M[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2) M[r][s2] = dot3(Ri + 3 * r, Rp + 3 * s2);
+    double efl[14], fel[14], efn[14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) { efl[i] = ef_ip[e * 14 + i]; fel[i] = efFE_ip[e * 14 + i]; }
+    const bool addref = (itecnt == 0);
+    // frame.c:1090-1096 then 1100-1155; with INPLACE later rows see the rows already rewritten
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        double *cur = pass == 0 ? efl : fel;
+        double out[14];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int o = (g < 2) ? 3 * g : 7 + 3 * (g - 2);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                double v[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    v[c] = pass == 0 ? (cur[o + c] + def[o + c])
+                                     : (addref ? (cur[o + c] + dlpf * d.fr_efFE_ref[e * 14 + o + c]) : cur[o + c]);
+                out[o + r] = dot3(M[r], v);
+                if (INPLACE) cur[o + r] = out[o + r];
+            }
+        }
+#pragma unroll
+        for (int w = 6; w < 14; w += 7) {
+            const double v = pass == 0 ? (cur[w] + def[w])
+                                       : (addref ? (cur[w] + dlpf * d.fr_efFE_ref[e * 14 + w]) : cur[w]);
+            out[w] = 0.0 + 1.0 * v;
+            if (INPLACE) cur[w] = out[w];
+        }
+#pragma unroll
+        for (int i = 0; i < 14; ++i) {
+            if (pass == 0) { ef_i[e * 14 + i] = out[i]; efn[i] = out[i]; }
+            else efFE_i[e * 14 + i] = out[i];
+        }
+    }
+    double EF[14];
+    frame_Tt_apply(Ri, efn, EF);
+    if (os != 0) {
+        double G2[14];
+        for (int i = 0; i < 14; ++i) {
+            double s = 0;
+            for (int j = 0; j < 14; ++j) s += Tr[i][j] * EF[j];
+            G2[i] = s;
+        }
+        for (int i = 0; i < 14; ++i) EF[i] = G2[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 14; ++i) d.fr_fg[e * 14 + i] = EF[i];
+}
+
+// ------------------------------------------------------------------------------------------
 // f_temp: segmented reduction over the node -> corner map (sorted by element type, element), one
 // thread per node; reproduces the reference's summation order (all trusses, frames, shells)
 // without atomics (replaces the `f_temp[mcode-1] += ...` scatters).
@@ -694,6 +876,13 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
         k_truss_forces<<<g, CB_TPB, 0, s>>>(d, a.x_temp, a.tr_frame_i, a.tr_ef_i);
         ++*launches;
     }
+    if (d.NE_FR) {
+        unsigned g = (unsigned)((d.NE_FR + 63) / 64);
+        k_frame_forces<false><<<g, 64, 0, s>>>(d, a.x_temp, a.dd, a.fr_frame_ip, a.fr_frame_i,
+                                               a.fr_xfr_i, a.fr_ef_ip, a.fr_ef_i, a.fr_efFE_ip,
+                                               a.fr_efFE_i, a.dlpf, a.itecnt);
+        ++*launches;
+    }
     if (d.NE_SH) {
         unsigned g = (unsigned)((d.NE_SH + CB_TPB - 1) / CB_TPB);
         const size_t smem = (size_t)99 * CB_TPB * sizeof(double);
@@ -717,6 +906,13 @@ int cbk_forces_linear(const CbForceArgs &a, const double *d_total, cudaStream_t 
     if (d.NE_TR) {
         unsigned g = (unsigned)((d.NE_TR + CB_TPB - 1) / CB_TPB);
         k_truss_forces_linear<<<g, CB_TPB, 0, s>>>(d, d_total, a.tr_frame_i, a.tr_ef_i);
+        ++*launches;
+    }
+    if (d.NE_FR) {
+        unsigned g = (unsigned)((d.NE_FR + 63) / 64);
+        k_frame_forces<true><<<g, 64, 0, s>>>(d, a.x_temp, d_total, a.fr_frame_i, a.fr_frame_i,
+                                              a.fr_xfr_i, a.fr_ef_i, a.fr_ef_i, a.fr_efFE_i,
+                                              a.fr_efFE_i, 0.0, 0);
         ++*launches;
     }
     if (d.NE_SH) {
@@ -761,13 +957,37 @@ k_mass_refresh_truss(CbDev d, const double *__restrict__ x, double *__restrict__
     double el[3];
 #pragma unroll
     for (int m = 0; m < 3; ++m) el[m] = x[(long)k * 3 + m] - x[(long)j * 3 + m];
-    tr_const[e * CB_TR_CONST + 2] = sqrt(dot3(el, el));
+    const double L = sqrt(dot3(el, el));
+    tr_const[e * CB_TR_CONST + 2] = L;
+    tr_const[e * CB_TR_CONST + 3] = cube_rn(L);
+}
+
+// mass_fr part 1 (frame.c:1326-1343): end coordinates and length from the committed x
+__global__ void __launch_bounds__(CB_TPB)
+k_mass_refresh_frame(CbDev d, const double *__restrict__ x, double *__restrict__ fr_const,
+                     double *__restrict__ xfr)
+{
+    long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (e >= d.NE_FR) return;
+    const int j = d.fr_nodes[e * 2], k = d.fr_nodes[e * 2 + 1];
+    double el[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        double xa = x[(long)j * 3 + m], xb = x[(long)k * 3 + m];
+        if (d.fr_osflag[e] != 0) { xa = xa + d.fr_offset[e * 6 + m]; xb = xb + d.fr_offset[e * 6 + 3 + m]; }
+        xfr[e * 6 + m] = xa; xfr[e * 6 + 3 + m] = xb;
+        el[m] = xb - xa;
+    }
+    const double L = sqrt(dot3(el, el));
+    fr_const[e * CB_FR_CONST + 3] = L;
+    fr_const[e * CB_FR_CONST + 4] = L * L;
+    fr_const[e * CB_FR_CONST + 5] = cube_rn(L);
 }
 
 __global__ void __launch_bounds__(256)
 k_mass_gather(CbDev d, const int32_t *__restrict__ cstart, const CbCorner *__restrict__ corners,
-              const double *__restrict__ dens_tr, const double *__restrict__ dens_sh,
-              double *__restrict__ sm)
+              const double *__restrict__ dens_tr, const double *__restrict__ dens_fr,
+              const double *__restrict__ dens_sh, double *__restrict__ sm)
 {
     long n = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (n >= d.NJ) return;
@@ -780,6 +1000,13 @@ k_mass_gather(CbDev d, const int32_t *__restrict__ cstart, const CbCorner *__res
             const double Mtot = dens_sh[cr.e] * A0 * th;
             const double mt = Mtot / 3;
             const double mr = Mtot / 3 * (th * th) / 12;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { acc[r] += mt; acc[3 + r] += mr; }
+        } else if (cr.type == CB_T_FRAME) {
+            // lumped (frame.c:1355-1360): rho A L / 2 on translations, rho A L^3 / 24 on rotations
+            const double *fc = d.fr_const + (long)cr.e * CB_FR_CONST;
+            const double mt = (dens_fr[cr.e] * fc[2] * fc[3]) / 24 * 12;
+            const double mr = (dens_fr[cr.e] * fc[2] * fc[3]) / 24 * (fc[3] * fc[3]);
 #pragma unroll
             for (int r = 0; r < 3; ++r) { acc[r] += mt; acc[3 + r] += mr; }
         } else if (cr.type == CB_T_TRUSS) {
@@ -811,7 +1038,10 @@ int cbk_mass(const CbDev &d, const double *x, double *sh_const_mut, double *tr_c
              const double *dens_sh, const int32_t *node_cstart, const CbCorner *corners,
              double *sm, cudaStream_t s, long *launches)
 {
-    (void)fr_const_mut; (void)fr_xfr; (void)dens_fr;
+    if (d.NE_FR) {
+        unsigned g = (unsigned)((d.NE_FR + CB_TPB - 1) / CB_TPB);
+        k_mass_refresh_frame<<<g, CB_TPB, 0, s>>>(d, x, fr_const_mut, fr_xfr); ++*launches;
+    }
     if (d.NE_TR) {
         unsigned g = (unsigned)((d.NE_TR + CB_TPB - 1) / CB_TPB);
         k_mass_refresh_truss<<<g, CB_TPB, 0, s>>>(d, x, tr_const_mut); ++*launches;
@@ -821,6 +1051,6 @@ int cbk_mass(const CbDev &d, const double *x, double *sh_const_mut, double *tr_c
         k_mass_refresh_shell<<<g, CB_TPB, 0, s>>>(d, x, sh_const_mut); ++*launches;
     }
     unsigned g = (unsigned)((d.NJ + 255) / 256);
-    k_mass_gather<<<g, 256, 0, s>>>(d, node_cstart, corners, dens_tr, dens_sh, sm); ++*launches;
+    k_mass_gather<<<g, 256, 0, s>>>(d, node_cstart, corners, dens_tr, dens_fr, dens_sh, sm); ++*launches;
     return cudaGetLastError() != cudaSuccess;
 }

@@ -1,0 +1,148 @@
+// cb_frame_math.cuh - local (element-axes) tangent stiffness of the 14-DOF space frame, shared
+// by the force path (compiled with -fmad=false: reference rounding) and the stiffness path.
+//
+// DOF order per end: u, v, w, theta_x (torsion), theta_y, theta_z, warping; end 2 at +7.
+// stiffe_fr frame.c:364-408 (elastic, warping torsion included), stiffg_fr frame.c:410-579
+// (geometric, closed form in the total end forces of the previous configuration), release
+// frame.c:798-900 (member-end bending releases by static condensation).
+#ifndef CB_FRAME_MATH_CUH
+#define CB_FRAME_MATH_CUH
+
+#include "cb_internal.h"
+
+// fc = fr_const record: E, G, A, L0, L0^2, L0^3 (host libm), Iz, Iy, J, Cw, aux xyz
+__device__ __forceinline__ void frame_elastic(double (*k)[14], const double *fc)
+{
+    const double E = fc[0], G = fc[1], A = fc[2], L = fc[3], L3 = fc[5];
+    const double Iz = fc[6], Iy = fc[7], J = fc[8], Cw = fc[9];
+#define CB_SYM(i, j, v) k[i][j] = k[j][i] = (v)
+    k[0][0] = k[7][7] = E * A / L;                 CB_SYM(7, 0, -k[0][0]);
+    k[1][1] = k[8][8] = 12 * E * Iz / L3;          CB_SYM(8, 1, -k[1][1]);
+    k[2][2] = k[9][9] = 12 * E * Iy / L3;          CB_SYM(9, 2, -k[2][2]);
+    k[3][3] = k[10][10] = 6 * G * J / (5 * L) + 12 * E * Cw / L3;   CB_SYM(10, 3, -k[3][3]);
+    k[5][5] = k[12][12] = 4 * E * Iz / L;
+    k[4][4] = k[11][11] = 4 * E * Iy / L;
+    k[6][6] = k[13][13] = 2 * G * J * L / 15 + 4 * E * Cw / L;
+    CB_SYM(5, 1, 6 * E * Iz / (L * L)); CB_SYM(12, 1, k[5][1]);
+    CB_SYM(8, 5, -k[5][1]);             CB_SYM(12, 8, -k[5][1]);
+    CB_SYM(9, 4, 6 * E * Iy / (L * L)); CB_SYM(11, 9, k[9][4]);
+    CB_SYM(4, 2, -k[9][4]);             CB_SYM(11, 2, -k[9][4]);
+    CB_SYM(6, 3, G * J / 10 + 6 * E * Cw / (L * L)); CB_SYM(13, 3, k[6][3]);
+    CB_SYM(10, 6, -k[6][3]);            CB_SYM(13, 10, -k[6][3]);
+    CB_SYM(12, 5, 2 * E * Iz / L);
+    CB_SYM(11, 4, 2 * E * Iy / L);
+    CB_SYM(13, 6, -(G * J * L / 30 - 2 * E * Cw / L));
+#undef CB_SYM
+}
+
+// ef = total end forces (ef_ip + efFE_ip) in the previous local frame, L = deformed length
+__device__ __forceinline__ void frame_geometric(double (*k)[14], const double *ef, double L,
+                                                double A, double J)
+{
+    const double P = ef[7], M4 = ef[4], M5 = ef[5], M10 = ef[10], M11 = ef[11], M12 = ef[12];
+#define CB_ADD(i, j, v) do { k[i][j] += (v); k[j][i] += (v); } while (0)
+#define CB_SUB(i, j, v) do { k[i][j] -= (v); k[j][i] -= (v); } while (0)
+    k[0][0] += P / L; k[7][7] += P / L; CB_SUB(7, 0, P / L);
+    k[1][1] += 6 * P / (5 * L); k[8][8] += 6 * P / (5 * L);
+    k[2][2] += 6 * P / (5 * L); k[9][9] += 6 * P / (5 * L);
+    CB_SUB(8, 1, 6 * P / (5 * L)); CB_SUB(9, 2, 6 * P / (5 * L));
+    k[3][3] += 6 * P * J / (5 * A * L); k[10][10] += 6 * P * J / (5 * A * L);
+    CB_SUB(10, 3, 6 * P * J / (5 * A * L));
+    k[4][4] += 2 * P * L / 15; k[11][11] += 2 * P * L / 15;
+    k[5][5] += 2 * P * L / 15; k[12][12] += 2 * P * L / 15;
+    k[6][6] += 2 * P * J / (15 * A); k[13][13] += 2 * P * J / (15 * A);
+    CB_ADD(3, 1, (11 * M4 - M11) / (10 * L)); CB_SUB(8, 3, (11 * M4 - M11) / (10 * L));
+    CB_ADD(4, 1, M10 / L); CB_ADD(5, 2, M10 / L); CB_ADD(11, 8, M10 / L); CB_ADD(12, 9, M10 / L);
+    CB_SUB(11, 1, M10 / L); CB_SUB(12, 2, M10 / L); CB_SUB(8, 4, M10 / L); CB_SUB(9, 5, M10 / L);
+    CB_ADD(5, 1, P / 10); CB_ADD(12, 1, P / 10); CB_ADD(9, 4, P / 10); CB_ADD(11, 9, P / 10);
+    CB_SUB(4, 2, P / 10); CB_SUB(11, 2, P / 10); CB_SUB(8, 5, P / 10); CB_SUB(12, 8, P / 10);
+    CB_ADD(6, 1, M4 / 10); CB_SUB(8, 6, M4 / 10);
+    CB_ADD(10, 8, (M4 - 11 * M11) / (10 * L)); CB_SUB(10, 1, (M4 - 11 * M11) / (10 * L));
+    CB_ADD(13, 8, M11 / 10); CB_SUB(13, 1, M11 / 10);
+    CB_ADD(3, 2, (11 * M5 - M12) / (10 * L)); CB_SUB(9, 3, (11 * M5 - M12) / (10 * L));
+    CB_ADD(6, 2, M5 / 10); CB_SUB(9, 6, M5 / 10);
+    CB_ADD(10, 9, (M5 - 11 * M12) / (10 * L)); CB_SUB(10, 2, (M5 - 11 * M12) / (10 * L));
+    CB_ADD(13, 9, M12 / 10); CB_SUB(13, 2, M12 / 10);
+    CB_SUB(4, 3, (2 * M5 - M12) / 5); CB_ADD(5, 3, (2 * M4 - M11) / 5);
+    CB_ADD(6, 3, P * J / (10 * A)); CB_ADD(13, 3, P * J / (10 * A));
+    CB_SUB(10, 6, P * J / (10 * A)); CB_SUB(13, 10, P * J / (10 * A));
+    CB_SUB(11, 3, (2 * M5 + M12) / 10); CB_ADD(12, 3, (2 * M4 + M11) / 10);
+    CB_SUB(6, 4, (3 * M5 - M12) * L / 30); CB_SUB(10, 4, (M5 + 2 * M12) / 10);
+    CB_SUB(11, 4, P * L / 30); CB_SUB(12, 5, P * L / 30);
+    CB_ADD(12, 4, M10 / 2); CB_SUB(11, 5, M10 / 2);
+    CB_ADD(13, 4, M5 * L / 30);
+    CB_ADD(6, 5, (3 * M4 - M11) * L / 30); CB_ADD(10, 5, (M4 + 2 * M11) / 10);
+    CB_SUB(13, 5, M4 * L / 30);
+    CB_SUB(11, 6, M12 * L / 30); CB_ADD(12, 6, M11 * L / 30);
+    CB_SUB(13, 6, P * J / (30 * A));
+    CB_ADD(11, 10, (M5 - 2 * M12) / 5); CB_SUB(12, 10, (M4 - 2 * M11) / 5);
+    CB_SUB(13, 11, (M5 - 3 * M12) * L / 30); CB_ADD(13, 12, (M4 - 3 * M11) * L / 30);
+#undef CB_ADD
+#undef CB_SUB
+}
+
+// Gauss-Jordan inverse without pivoting, as misc.c:284-343 behaves for SPD input (n <= 4)
+__device__ __forceinline__ void gj_inverse4(double *A, int n)
+{
+    double aug[4][8];
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < 2 * n; ++j)
+            aug[i][j] = (j < n) ? A[n * i + j] : ((j - n == i) ? 1.0 : 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+            if (j != i) {
+                const double m = aug[j][i] / aug[i][i];
+                for (int q = 0; q < 2 * n; ++q) aug[j][q] -= m * aug[i][q];
+            }
+    for (int i = 0; i < n; ++i)
+        for (int j = n; j < 2 * n; ++j) A[n * i + j - n] = aug[i][j] / aug[i][i];
+}
+
+// rel4 = mendrel[1..4]: strong/weak axis releases at end 1, end 2 -> DOFs 5, 4, 12, 11
+__device__ __forceinline__ void frame_release(double (*k)[14], const int *rel4)
+{
+    const int dof[4] = {5, 4, 12, 11};
+    int idx[4], r = 0;
+    for (int i = 0; i < 4; ++i)
+        if (rel4[i] == 1) idx[r++] = dof[i];
+    if (r == 0) return;
+    double kG[14][4], GkG[16], W[14][4];
+    for (int i = 0; i < 14; ++i)
+        for (int j = 0; j < r; ++j) kG[i][j] = 0 + k[i][idx[j]];
+    for (int i = 0; i < r; ++i)
+        for (int j = 0; j < r; ++j) GkG[i * r + j] = kG[idx[j]][i];
+    if (r == 1) GkG[0] = 1 / GkG[0];
+    else if (r == 2) {
+        const double det = GkG[0] * GkG[3] - GkG[1] * GkG[2], t0 = GkG[0];
+        GkG[0] = GkG[3] / det; GkG[3] = t0 / det; GkG[1] *= -1 / det; GkG[2] *= -1 / det;
+    } else gj_inverse4(GkG, r);
+    for (int i = 0; i < 14; ++i)
+        for (int j = 0; j < r; ++j) {
+            double s = 0;
+            for (int q = 0; q < r; ++q) s += kG[i][q] * GkG[q * r + j];
+            W[i][j] = s;
+        }
+    for (int i = 0; i < 14; ++i)
+        for (int j = 0; j < 14; ++j) {
+            double s = 0;
+            for (int q = 0; q < r; ++q) s += W[i][q] * kG[j][q];
+            k[i][j] -= s;
+        }
+}
+
+// full local tangent of frame e for ANAFLAG 1 / 2; eftot receives ef_ip + efFE_ip
+__device__ __forceinline__ void frame_local_k(const CbDev &d, long e, const double *ef_ip,
+                                              const double *efFE_ip, double defllen_ip,
+                                              double (*k)[14], double *eftot)
+{
+    const double *fc = d.fr_const + e * CB_FR_CONST;
+    for (int i = 0; i < 14; ++i) {
+        for (int j = 0; j < 14; ++j) k[i][j] = 0;
+        eftot[i] = ef_ip[e * 14 + i] + efFE_ip[e * 14 + i];
+    }
+    frame_elastic(k, fc);
+    if (d.ANAFLAG == 2) frame_geometric(k, eftot, defllen_ip, fc[2], fc[8]);
+    if (d.fr_mendrel[e * 5] == 1) frame_release(k, d.fr_mendrel + e * 5 + 1);
+}
+
+#endif

@@ -22,6 +22,7 @@
 //                                 the reference's skyline layout (small / medium models that keep
 //                                 the SLVFLAG=0 host solver), where the output is not contiguous.
 #include "cb_internal.h"
+#include "cb_frame_math.cuh"
 
 #define CB_TPB_K 128
 
@@ -108,6 +109,51 @@ __device__ __forceinline__ void shell_block(const CbDev &d, int e, int a, int b,
     rtsr_row(R, k01, k02, blk + 3, ld);                                     // translation-rotation
     rtsr_col(R, k10, k20, blk + 3 * ld, ld);                                // rotation-translation
     rtsr_diag(R, k11, k12, k21, k22, drill, blk + 3 * ld + 3, ld);          // rotation-rotation
+}
+
+// K_ab (7x7, global axes w.r.t. the joints) of frame e: local tangent (frame.c:364-579, releases
+// 798-900), rotation by blockdiag(R,R,1) (frame.c:286-299) and, with member-end offsets, the
+// rigid-link transformation (frame.c:304-323)
+__device__ void frame_block(const CbStiffArgs &A, int e, int a, int b, double *blk, int ld)
+{
+    double k[14][14], eft[14];
+    const double *fr = A.fr_frame + (long)e * CB_FR_FRAME;
+    frame_local_k(A.d, e, A.fr_ef, A.fr_efFE, fr[9], k, eft);
+    double R[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = fr[i];
+    double W[7][7], K[7][7];
+    for (int i = 0; i < 7; ++i) {                     // W = k_ab T_b
+        const double *kr = &k[7 * a + i][7 * b];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                W[i][3 * q + j] = kr[3 * q] * R[j] + kr[3 * q + 1] * R[3 + j] + kr[3 * q + 2] * R[6 + j];
+        W[i][6] = kr[6];
+    }
+    for (int j = 0; j < 7; ++j) {                     // K = T_a^T W
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                K[3 * p + i][j] = R[i] * W[3 * p][j] + R[3 + i] * W[3 * p + 1][j] + R[6 + i] * W[3 * p + 2][j];
+        K[6][j] = W[6][j];
+    }
+    if (A.d.fr_osflag[e] != 0) {
+        // L = [[I, S],[0, I]] (+1 on warping), S from the end offsets; K <- L_a^T K L_b
+        const double *oa = A.d.fr_offset + (long)e * 6 + 3 * a, *ob = A.d.fr_offset + (long)e * 6 + 3 * b;
+        const double Sa[3][3] = {{0, oa[2], -oa[1]}, {-oa[2], 0, oa[0]}, {oa[1], -oa[0], 0}};
+        const double Sb[3][3] = {{0, ob[2], -ob[1]}, {-ob[2], 0, ob[0]}, {ob[1], -ob[0], 0}};
+        for (int i = 0; i < 7; ++i)
+            for (int j = 0; j < 3; ++j)
+                K[i][3 + j] += K[i][0] * Sb[0][j] + K[i][1] * Sb[1][j] + K[i][2] * Sb[2][j];
+        for (int j = 0; j < 7; ++j)
+            for (int i = 0; i < 3; ++i)
+                K[3 + i][j] += Sa[0][i] * K[0][j] + Sa[1][i] * K[1][j] + Sa[2][i] * K[2][j];
+    }
+    for (int i = 0; i < 7; ++i)
+        for (int j = 0; j < 7; ++j) blk[i * ld + j] = K[i][j];
 }
 
 // K_ab (3x3) of truss e (truss.c:102-166)
@@ -236,6 +282,14 @@ k_assemble_tiles(CbStiffArgs A)
                     shell_block_stage<ND>(in, ct.a, ct.b, stg);
                 }
                 ndof[t] = 6;
+            } else if (ct.type == CB_T_FRAME) {
+                if constexpr (ND >= 7) {
+                    double blk[49];
+                    frame_block(A, ct.e, ct.a, ct.b, blk, 7);
+#pragma unroll
+                    for (int i = 0; i < 49; ++i) stg[i * STR] = blk[i];
+                }
+                ndof[t] = 7;
             } else {
                 double blk[9];
 #pragma unroll
@@ -337,6 +391,10 @@ k_assemble_blocks(CbStiffArgs A)
             for (int r = 0; r < 6; ++r)
 #pragma unroll
                 for (int q = 0; q < 6; ++q) acc[r * 7 + q] += blk[r * 6 + q];
+        } else if (ct.type == CB_T_FRAME) {
+            double blk[49];
+            frame_block(A, ct.e, ct.a, ct.b, blk, 7);
+            for (int i = 0; i < 49; ++i) acc[i] += blk[i];
         } else if (ct.type == CB_T_TRUSS) {
             double blk[9];
             truss_block(A, ct.e, ct.a, ct.b, blk, 3);
@@ -368,13 +426,15 @@ k_assemble_blocks(CbStiffArgs A)
         for (int c = 0; c < 7; ++c) {
             if (!((pr.maskB >> c) & 1)) continue;
             const long j = pr.eqB0 + cc;
-            const long dj = A.maxa[j - 1] - 1;
+            const long dj = A.maxa[j - 1] - 1, dend = A.maxa[j] - 1;   // column j occupies [dj, dend)
             int rr = 0;
 #pragma unroll
             for (int r = 0; r < 7; ++r) {
                 if (!((pr.maskA >> r) & 1)) continue;
                 const long i = pr.eqA0 + rr;
-                if (i <= j) A.out[dj + (j - i)] = acc[r * 7 + c];
+                // a joint-pair block may hold DOF pairs no element couples (e.g. rotations of two
+                // joints linked only by a truss): they are zero and can lie outside the profile
+                if (i <= j && dj + (j - i) < dend) A.out[dj + (j - i)] = acc[r * 7 + c];
                 ++rr;
             }
             ++cc;

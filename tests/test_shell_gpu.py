@@ -14,37 +14,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 
-def _walk(m, ref, asm, n_iter=3, scale=1e-4, seed=1):
-    """drive reference and device through the same sequence of calls, compare everything"""
-    s = ref.RefState(m)
-    s.begin_increment(); asm.begin_increment()
-    rng = np.random.default_rng(seed)
-    for it in range(n_iter):
-        ss_ref = ref.stiff(m, s, SLVFLAG=0)
-        asm.stiff()
-        assert relerr(asm.skyline(), ss_ref) < TOL, f"skyline K_t iter {it}"
-        dd = rng.uniform(-scale, scale, size=m.NEQ)
-        fr, sh, _ = ref.update_forces(m, s, dd)
-        f, gfr, gsh, _ = asm.update_forces(dd)
-        assert (fr, sh) == (gfr, gsh)
-        assert relerr(f, s.f_temp) < TOL, f"f_temp iter {it}"
-        assert relerr(asm.download("EF_I"), s.ef_i) < TOL
-        assert relerr(asm.download("X_TEMP"), s.x_temp) == 0.0
-        assert relerr(asm.download("X_IP"), s.x_ip) == 0.0
-        assert relerr(asm.download("D_TEMP"), s.d_temp) == 0.0
-        for nm in ("C1", "C2", "C3"):
-            assert relerr(asm.download(nm + "_I"), getattr(s, nm.lower() + "_i")) < 1e-15
-            assert relerr(asm.download(nm + "_IP"), getattr(s, nm.lower() + "_ip")) < 1e-15
-        assert relerr(asm.download("DEFFAREA_I"), s.deffarea_i) < 1e-15
-        assert relerr(asm.download("DEFSLEN_I"), s.defslen_i) < 1e-15
-        s.end_iteration(); asm.end_iteration()
-        assert relerr(asm.download("C1_IP"), s.c1_ip) < 1e-15
-    s.commit(); asm.commit()
-    assert relerr(asm.download("EF"), s.ef) < TOL
-    assert relerr(asm.download("X"), s.x) == 0.0
-    assert relerr(asm.download("D"), s.d) == 0.0
-    assert relerr(asm.download("F"), s.f) < TOL
-    return s
+from util import walk as _walk
 
 
 @pytest.mark.parametrize("nx,ny,bump", [(1, 1, 0.0), (2, 2, 0.0), (6, 4, 0.02), (9, 7, 0.05)])

@@ -28,3 +28,46 @@ def skyline_to_dense(n, maxa, ss):
             i = j - k
             K[i - 1, j - 1] = ss[maxa[j - 1] - 1 + k]
     return K
+
+
+TOL = 1e-12
+
+
+def walk(m, ref, asm, n_iter=3, scale=1e-4, seed=1, dlpf=0.25):
+    """drive reference and device through the same sequence of calls of the Newton loop
+    (main.c:1833-2134) and compare everything after every call"""
+    s = ref.RefState(m)
+    s.begin_increment(); asm.begin_increment()
+    rng = np.random.default_rng(seed)
+    for it in range(n_iter):
+        ss_ref = ref.stiff(m, s, SLVFLAG=0)
+        asm.stiff()
+        assert relerr(asm.skyline(), ss_ref) < TOL, f"skyline K_t iter {it}"
+        dd = rng.uniform(-scale, scale, size=m.NEQ)
+        fr, sh, _ = ref.update_forces(m, s, dd, dlpf=dlpf, itecnt=it)
+        f, gfr, gsh, _ = asm.update_forces(dd, dlpf=dlpf, itecnt=it)
+        assert (fr, sh) == (gfr, gsh)
+        assert relerr(f, s.f_temp) < TOL, f"f_temp iter {it}"
+        assert relerr(asm.download("EF_I"), s.ef_i) < TOL
+        assert relerr(asm.download("X_TEMP"), s.x_temp) == 0.0
+        assert relerr(asm.download("X_IP"), s.x_ip) == 0.0
+        assert relerr(asm.download("D_TEMP"), s.d_temp) == 0.0
+        for nm in ("C1", "C2", "C3"):
+            assert relerr(asm.download(nm + "_I"), getattr(s, nm.lower() + "_i")) < 1e-15
+            assert relerr(asm.download(nm + "_IP"), getattr(s, nm.lower() + "_ip")) < 1e-15
+        assert relerr(asm.download("DEFFAREA_I"), s.deffarea_i) < 1e-15
+        assert relerr(asm.download("DEFSLEN_I"), s.defslen_i) < 1e-15
+        assert relerr(asm.download("DEFLLEN_I"), s.defllen_i) < 1e-15
+        assert relerr(asm.download("EFFE_I"), s.efFE_i) < TOL
+        assert relerr(asm.download("XFR_TEMP"), s.xfr_temp) < 1e-15
+        s.end_iteration(); asm.end_iteration()
+        assert relerr(asm.download("C1_IP"), s.c1_ip) < 1e-15
+        assert relerr(asm.download("EFFE_IP"), s.efFE_ip) < TOL
+    s.commit(); asm.commit()
+    assert relerr(asm.download("EF"), s.ef) < TOL
+    assert relerr(asm.download("EFFE"), s.efFE) < TOL
+    assert relerr(asm.download("X"), s.x) == 0.0
+    assert relerr(asm.download("D"), s.d) == 0.0
+    assert relerr(asm.download("F"), s.f) < TOL
+    assert relerr(asm.download("XFR"), s.xfr) < 1e-15
+    return s

@@ -211,7 +211,11 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
         return fail(CB_ERR_UNSUPPORTED, "bricks scatter to the dense layout only in the "
                     "reference (brick.c:383-395, skylin ignores them): use CB_MAT_CSC");
     }
-    if (BR) { delete h; return fail(CB_ERR_UNSUPPORTED, "brick elements: not built yet"); }
+    if (BR && (TR || FR)) {
+        delete h;
+        return fail(CB_ERR_UNSUPPORTED, "bricks with trusses/frames: the reference overruns nu[] "
+                    "(main.c:594 vs brick.c:127), no defined behaviour to reproduce");
+    }
 
 #define BAIL(code) do { int c_ = (code); cb_destroy(h); return c_; } while (0)
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -283,6 +287,12 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
                     if (mc[6 * TR + e * 14 + a2 * 7 + r] != m->jcode[(long)h->h_nodes[1][e * 2 + a2] * 7 + r])
                         BAIL(fail(CB_ERR_UNSUPPORTED, "mcode of frame %ld disagrees with jcode "
                                   "(released-warping joints are not supported)", e + 1));
+        const long ob = 6 * TR + 14 * FR + 18 * SH;
+        for (long e = 0; e < BR; ++e)
+            for (int a2 = 0; a2 < 8; ++a2)
+                for (int r = 0; r < 3; ++r)
+                    if (mc[ob + e * 24 + a2 * 3 + r] != m->jcode[(long)h->h_nodes[3][e * 8 + a2] * 7 + r])
+                        BAIL(fail(CB_ERR_ARG, "mcode of brick %ld disagrees with jcode", e + 1));
         const long o = 6 * TR + 14 * FR;
         for (long e = 0; e < SH; ++e)
             for (int a = 0; a < 3; ++a)
@@ -310,6 +320,12 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
             if (h->tr_frame[g].upload(fr) || h->tr_ef[g].alloc((size_t)TR * 2)) BAIL(CB_ERR_CUDA);
             cudaMemset(h->tr_ef[g].p, 0, (size_t)TR * 2 * sizeof(double));
         }
+    }
+    // ---- bricks (linear, stiffness only; brick.c:127-129 reads emod/nu at TR+FR+SH+i) -------
+    if (BR) {
+        std::vector<double> c((size_t)BR * 4, 0.0);
+        for (long e = 0; e < BR; ++e) { c[e * 4] = m->emod[TR + FR + SH + e]; c[e * 4 + 1] = m->nu[SH + e]; }
+        if (h->br_const.upload(c)) BAIL(CB_ERR_CUDA);
     }
     // ---- frames ----------------------------------------------------------------------------
     if (FR) {
@@ -577,9 +593,16 @@ static int build_plan(cb_handle *h)
     if (contribs.size() > 0x7fffffffUL) return fail(CB_ERR_OVERFLOW, "too many contributions");
     h->ncontrib = (long)contribs.size();
     {
+        // ND must cover the highest free DOF of any joint (a brick-only joint still carries the
+        // three rotational equations struc() leaves free), `mixed` = some element type brings
+        // fewer DOFs per joint than ND
         const bool has3 = h->sz.NE_TR || h->NE_BR, has6 = h->sz.NE_SH != 0, has7 = h->sz.NE_FR != 0;
-        h->max_dof = has7 ? 7 : (has6 ? 6 : 3);
-        h->mixed = ((int)has3 + (int)has6 + (int)has7) > 1;
+        int top = has7 ? 7 : (has6 ? 6 : 3);
+        for (long j = 0; j < NJ; ++j)
+            for (int r = top; r < 7; ++r)
+                if ((h->h_mask[j] >> r) & 1) top = r + 1;
+        h->max_dof = top <= 3 ? 3 : (top <= 6 ? 6 : 7);
+        h->mixed = (has3 && h->max_dof != 3) || (has6 && h->max_dof != 6) || (has7 && h->max_dof != 7);
     }
     // block-owner kernel (skyline, or CSC fallback for joints too large for a tile): bucket the
     // blocks by contribution count (descending, stable) so a warp's threads loop alike

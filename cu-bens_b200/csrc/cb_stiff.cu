@@ -156,6 +156,59 @@ __device__ void frame_block(const CbStiffArgs &A, int e, int a, int b, double *b
         for (int j = 0; j < 7; ++j) blk[i * ld + j] = K[i][j];
 }
 
+// K_ab (3x3) of 8-node brick e: 2x2x2 Gauss, B_a^T C B_b detJ (brick.c:79-397, jacob 541-699).
+// For the isotropic C of brick.c:127-141 (lambda = e1, mu = e2, lambda + 2 mu = e3) the 6x24
+// strain-displacement product collapses to
+//   K_ab[i][j] = detJ * (lambda g_a[i] g_b[j] + mu g_a[j] g_b[i] + mu delta_ij g_a.g_b),
+// g_n = J^-1 dN_n/d(r,s,t).  Bricks are linear and assembled once.
+__device__ void brick_block(const CbStiffArgs &A, int e, int a, int b, double *blk, int ld)
+{
+    const int sg[8] = {+1, -1, +1, -1, -1, +1, -1, +1};
+    const int sr[8] = {+1, -1, -1, +1, +1, -1, -1, +1};
+    const int ss[8] = {+1, +1, -1, -1, +1, +1, -1, -1};
+    const int st[8] = {+1, +1, +1, +1, -1, -1, -1, -1};
+    const double E = A.d.br_const[(long)e * 4], v = A.d.br_const[(long)e * 4 + 1];
+    const double lam = E * v / ((1 + v) * (1 - 2 * v)), mu = .5 * (E / (1 + v));
+    double X[8][3];
+    for (int n = 0; n < 8; ++n) {
+        const long jt = A.d.br_nodes[(long)e * 8 + n];
+        for (int m = 0; m < 3; ++m) X[n][m] = A.x[jt * 3 + m];
+    }
+    double K[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    const double gp = 0.57735026918962576451;      // 1/sqrt(3)
+    for (int q = 0; q < 8; ++q) {
+        const double R = (q & 4) ? -gp : gp, S = (q & 2) ? -gp : gp, T = (q & 1) ? -gp : gp;
+        double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, da[3] = {0, 0, 0}, db[3] = {0, 0, 0};
+        for (int n = 0; n < 8; ++n) {
+            const double dr = sg[n] * (S + ss[n]) * (T + st[n]) / 8.0;
+            const double ds = sg[n] * (R + sr[n]) * (T + st[n]) / 8.0;
+            const double dt = sg[n] * (R + sr[n]) * (S + ss[n]) / 8.0;
+            for (int m = 0; m < 3; ++m) { J[0][m] += dr * X[n][m]; J[1][m] += ds * X[n][m]; J[2][m] += dt * X[n][m]; }
+            if (n == a) { da[0] = dr; da[1] = ds; da[2] = dt; }
+            if (n == b) { db[0] = dr; db[1] = ds; db[2] = dt; }
+        }
+        const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
+                     c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+        const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+        // inverse = adj / det ; g = J^-1 d
+        const double Ji[3][3] = {
+            {c00 / det, (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det, (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det},
+            {c01 / det, (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det, (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det},
+            {c02 / det, (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det, (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det}};
+        double ga[3], gb[3];
+        for (int i = 0; i < 3; ++i) {
+            ga[i] = Ji[i][0] * da[0] + Ji[i][1] * da[1] + Ji[i][2] * da[2];
+            gb[i] = Ji[i][0] * db[0] + Ji[i][1] * db[1] + Ji[i][2] * db[2];
+        }
+        const double gg = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                K[i][j] += det * (lam * ga[i] * gb[j] + mu * ga[j] * gb[i] + ((i == j) ? mu * gg : 0.0));
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) blk[i * ld + j] = K[i][j];
+}
+
 // K_ab (3x3) of truss e (truss.c:102-166)
 __device__ __forceinline__ void truss_block(const CbStiffArgs &A, int e, int a, int b, double *blk,
                                             int ld)
@@ -295,6 +348,7 @@ k_assemble_tiles(CbStiffArgs A)
 #pragma unroll
                 for (int i = 0; i < 9; ++i) blk[i] = 0.0;
                 if (ct.type == CB_T_TRUSS) truss_block(A, ct.e, ct.a, ct.b, blk, 3);
+                else if (ct.type == CB_T_BRICK) brick_block(A, ct.e, ct.a, ct.b, blk, 3);
 #pragma unroll
                 for (int i = 0; i < NN; ++i) stg[i * STR] = 0.0;
 #pragma unroll
@@ -395,9 +449,10 @@ k_assemble_blocks(CbStiffArgs A)
             double blk[49];
             frame_block(A, ct.e, ct.a, ct.b, blk, 7);
             for (int i = 0; i < 49; ++i) acc[i] += blk[i];
-        } else if (ct.type == CB_T_TRUSS) {
+        } else if (ct.type == CB_T_TRUSS || ct.type == CB_T_BRICK) {
             double blk[9];
-            truss_block(A, ct.e, ct.a, ct.b, blk, 3);
+            if (ct.type == CB_T_TRUSS) truss_block(A, ct.e, ct.a, ct.b, blk, 3);
+            else brick_block(A, ct.e, ct.a, ct.b, blk, 3);
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll

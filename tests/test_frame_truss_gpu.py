@@ -74,3 +74,18 @@ def test_mixed_shell_frame_truss(gpu, ref):
     dense = ref.stiff(m, s, SLVFLAG=2).reshape(m.NEQ, m.NEQ)
     assert relerr(csc_to_dense(m.NEQ, *asm.csc()), dense.T) < TOL
     asm.close()
+
+
+@pytest.mark.parametrize("name", ["brick_2x2x2", "brick_skin_2x2x1"])
+def test_brick_stiffness(gpu, ref, name):
+    """stiff_br (+ stiff_sh on the skinned face) into the CSC vs the reference's dense scatter"""
+    m = G.build(name)
+    asm = cb.Assembler(m, layout=cb.CB_MAT_CSC)
+    s = ref.RefState(m)
+    dense = ref.stiff(m, s, SLVFLAG=2, gen="c").reshape(m.NEQ, m.NEQ)
+    asm.stiff(cb.CB_GEN_COMMITTED)
+    K = csc_to_dense(m.NEQ, *asm.csc())
+    assert relerr(K, dense.T) < TOL
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    assert relerr(K, gold["K_dense"].reshape(m.NEQ, m.NEQ).T) < TOL
+    asm.close()

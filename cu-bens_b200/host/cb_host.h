@@ -1,0 +1,47 @@
+/* cb_host.h - C host drivers that sit where main.c's loops sit and drive the device path
+ * through the C-ABI of include/cubens_b200.h.  The reference's host stays C (north_star); this
+ * is the static Newton-Raphson / modified Newton-Raphson load-increment loop of
+ * main.c:1824-2152 written against cb_*, with the skyline LDL^T solve that solve.c:78-80 does
+ * (skyfact/skysolve, solve.c:539-698 - Bathe's COLSOL) and the convergence test of
+ * misc.c:187-250.  "Next" rows 1-2 of SURVEY.md section 8(f): host-side consumers of the path. */
+#ifndef CB_HOST_H
+#define CB_HOST_H
+#include "../../include/cubens_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* active-column (skyline) LDL^T, layout of model.c:1269-1278: maxa 1-based diagonal addresses.
+ * allow_indefinite != 0 reproduces the ALGFLAG==3 branch (pivots returned in ssd, *det_neg set
+ * when a pivot is negative) instead of failing on a non-positive pivot.  Returns 0 / 1.       */
+int  cb_sky_factor(long neq, const long *maxa, double *ss, double *ssd, int *det_neg,
+                   int allow_indefinite);
+void cb_sky_solve(long neq, const long *maxa, const double *ss, double *rhs);
+
+/* the solver controls main.c reads after the loads (main.c:1809-1812) */
+typedef struct cb_nr_params {
+    double lpfmax, lpf, dlpf, dlpfmax, dlpfmin;
+    int itemax, submax, solmin;
+    double toldisp, tolforc, tolener;
+    int algflag;                 /* 1 = Newton-Raphson, 2 = modified Newton-Raphson */
+} cb_nr_params;
+
+typedef struct cb_nr_result {
+    int status;                  /* 0 = "Solution successful", else the reference's error exit   */
+    int increments;              /* converged load increments                                    */
+    int iterations;              /* total equilibrium iterations                                 */
+    int stiff_calls, force_calls;
+    double lpf;                  /* load proportionality factor of the last converged increment  */
+} cb_nr_result;
+
+/* q [NEQ] reference load vector; d_out [NEQ] displacements of the last converged increment;
+ * hist (may be NULL) receives up to max_hist rows (lpf, iterations, d[hist_dof]) like
+ * results2.txt.  maxa / lss as skylin() produced them.                                       */
+int cb_newton_static(cb_handle *h, long neq, const long *maxa, long lss, const double *q,
+                     const cb_nr_params *p, double *d_out, cb_nr_result *res, double *hist,
+                     int max_hist, long hist_dof);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

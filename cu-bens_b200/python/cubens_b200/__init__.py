@@ -279,3 +279,62 @@ class Assembler:
     @property
     def map_bytes(self):
         return self.lib.cb_map_bytes(self.h)
+
+
+# ---- C host drivers (cu-bens_b200/host) ------------------------------------------------------
+HOST_LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "libcubens_host.so"))
+_hostlib = None
+
+
+class cb_nr_params(C.Structure):
+    _fields_ = [("lpfmax", C.c_double), ("lpf", C.c_double), ("dlpf", C.c_double),
+                ("dlpfmax", C.c_double), ("dlpfmin", C.c_double), ("itemax", C.c_int),
+                ("submax", C.c_int), ("solmin", C.c_int), ("toldisp", C.c_double),
+                ("tolforc", C.c_double), ("tolener", C.c_double), ("algflag", C.c_int)]
+
+
+class cb_nr_result(C.Structure):
+    _fields_ = [("status", C.c_int), ("increments", C.c_int), ("iterations", C.c_int),
+                ("stiff_calls", C.c_int), ("force_calls", C.c_int), ("lpf", C.c_double)]
+
+
+def load_host_library():
+    global _hostlib
+    if _hostlib is None:
+        load_library()
+        if not os.path.exists(HOST_LIB_PATH):
+            raise CubensError(f"{HOST_LIB_PATH} not found - run make -C cu-bens_b200")
+        _hostlib = C.CDLL(HOST_LIB_PATH)
+    return _hostlib
+
+
+def newton_static(asm, q, lpfmax=1.0, lpf=0.1, dlpf=0.1, dlpfmax=0.5, dlpfmin=1e-4, itemax=20,
+                  submax=5, solmin=10, toldisp=1e-8, tolforc=1e-8, tolener=1e-8, algflag=1,
+                  hist_dof=-1):
+    """the C host driver cb_newton_static (main.c:1824-2152 on the device path)"""
+    hl = load_host_library()
+    m = asm.m
+    p = cb_nr_params(lpfmax, lpf, dlpf, dlpfmax, dlpfmin, itemax, submax, solmin, toldisp, tolforc,
+                     tolener, algflag)
+    res = cb_nr_result()
+    d = np.zeros(m.NEQ)
+    hist = np.zeros(3 * 4096)
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    maxa = np.ascontiguousarray(m.maxa, dtype=np.int64)
+    hl.cb_newton_static(asm.h, C.c_long(m.NEQ), _p(maxa), C.c_long(m.lss), _p(q), C.byref(p), _p(d),
+                        C.byref(res), _p(hist), C.c_int(4096), C.c_long(hist_dof))
+    n = res.increments
+    return d, res, hist[:3 * n].reshape(-1, 3).copy()
+
+
+def sky_factor_solve(maxa, ss, rhs):
+    """host skyline LDL^T (cb_sky_factor + cb_sky_solve); ss is factorised in place"""
+    hl = load_host_library()
+    neq = len(rhs)
+    v = np.ascontiguousarray(rhs, dtype=np.float64).copy()
+    maxa = np.ascontiguousarray(maxa, dtype=np.int64)
+    rc = hl.cb_sky_factor(C.c_long(neq), _p(maxa), _p(ss), C.c_void_p(0), C.c_void_p(0), C.c_int(0))
+    if rc:
+        raise CubensError("non-positive definite stiffness matrix")
+    hl.cb_sky_solve(C.c_long(neq), _p(maxa), _p(ss), _p(v))
+    return v

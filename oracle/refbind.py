@@ -281,8 +281,9 @@ def skyline_solve(m, ss, rhs, fact=0):
     r = np.ascontiguousarray(rhs, dtype=np.float64).copy(); dd = np.zeros(n)
     ssd = np.zeros(n); det = C.c_int(0)
     z = C.c_void_p(0)
+    Ap = np.zeros(2, dtype=np.int32)          # solve() writes *pAp = 0 unconditionally (solve.c:65)
     err = l.solve(P(m.jcode), P(ss), z, z, z, z, P(r), P(dd), P(m.maxa), P(ssd),
-                  C.byref(det), z, z, z, z, z, z, z, z, z, z, z, z, z, z,
+                  C.byref(det), z, z, z, z, z, z, z, z, z, z, z, P(Ap), z, z,
                   C.c_double(0), C.c_double(0), z, C.c_int(fact), C.c_double(1), z, P(m.kht),
                   z, z, z, C.c_int(0))
     if err:

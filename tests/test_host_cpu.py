@@ -102,3 +102,17 @@ def test_partition_gloo_world2(tmp_path):
                           "29731", str(script)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_host_skyline_solver_matches_reference(ref):
+    """cb_sky_factor / cb_sky_solve (C host, COLSOL) == the reference's skyfact / skysolve, bit for
+    bit, on a real stiffness matrix"""
+    import cubens_b200 as cb
+    from cubens_b200 import meshgen
+    for m in (meshgen.plate_model(7, 5, z_bump=0.05), meshgen.lattice_model(3), meshgen.truss_model(3)):
+        s = ref.RefState(m)
+        ss = ref.stiff(m, s, SLVFLAG=0, gen="c")
+        rhs = np.random.default_rng(0).normal(size=m.NEQ)
+        x_ref, _, _ = ref.skyline_solve(m, ss.copy(), rhs)
+        x = cb.sky_factor_solve(m.maxa, ss.copy(), rhs)
+        assert np.array_equal(x, x_ref)

@@ -71,3 +71,72 @@ def walk(m, ref, asm, n_iter=3, scale=1e-4, seed=1, dlpf=0.25):
     assert relerr(asm.download("F"), s.f) < TOL
     assert relerr(asm.download("XFR"), s.xfr) < 1e-15
     return s
+
+
+def ref_newton(m, ref, q, lpfmax=1.0, lpf=0.1, dlpf=0.1, dlpfmax=0.5, dlpfmin=1e-4, itemax=20,
+               submax=5, solmin=10, toldisp=1e-8, tolforc=1e-8, tolener=1e-8, algflag=1, hist_dof=-1):
+    """The reference's NR / MNR loop (main.c:1824-2152) around the reference's OWN routines
+    (stiff_*, solve() -> skyfact/skysolve, updatc, forces_*, test) - the converged-solution oracle."""
+    import ctypes as C
+    l = ref.set_model(m)
+    s = ref.RefState(m)
+    n = m.NEQ
+    qtot = np.zeros(n); fp = np.zeros(n); f_ip = np.zeros(n); r = np.zeros(n)
+    hist = []
+    solcnt = subcnt = 0
+    stat = dict(increments=0, iterations=0, status=0, lpf=0.0)
+    ss = None
+    while True:
+        if lpf > lpfmax:
+            lpf = lpfmax
+        qtot[:] = q * lpf; fp[:] = s.f
+        dlpfp = dlpf
+        s.begin_increment()
+        itecnt = 0; frfr = frsh = 0
+        while True:
+            r[:] = qtot - s.f_temp
+            refactor = algflag == 1 or (algflag == 2 and itecnt == 0)
+            if refactor:
+                ss = ref.stiff(m, s, SLVFLAG=0)
+            dd, _, _ = ref.skyline_solve(m, ss, r, fact=0 if refactor else 1)
+            f_ip[:] = s.f_temp
+            frfr, frsh, dlpf = ref.update_forces(m, s, dd, dlpf=dlpf, itecnt=itecnt)
+            stat["iterations"] += 1
+            if itecnt == 0:
+                intener1 = C.c_double(float(ref.lib().dot(ref.P(dd), ref.P(qtot - fp), C.c_int(n))))
+            conv = C.c_int(0)
+            ref.set_model(m)
+            err = l.test(ref.P(s.d_temp), ref.P(dd), ref.P(s.f_temp), ref.P(fp), ref.P(qtot),
+                         ref.P(f_ip), C.byref(intener1), C.byref(conv), C.byref(C.c_double(toldisp)),
+                         C.byref(C.c_double(tolforc)), C.byref(C.c_double(tolener)))
+            assert err == 0
+            s.end_iteration()
+            itecnt += 1
+            if not (conv.value != 0 and frfr == 0 and frsh == 0 and itecnt <= itemax):
+                break
+        if frfr == 2:
+            dlpf = dlpfp
+        elif (conv.value != 0 or frfr or frsh) and subcnt <= submax:
+            if lpf == lpfmax:
+                stat["status"] = 4; break
+            if dlpfp == dlpfmin:
+                stat["status"] = 5; break
+            if frfr != 1:
+                dlpf = dlpfp / 2
+            dlpf = max(dlpf, dlpfmin)
+            lpf = lpf - dlpfp + dlpf
+            subcnt += 1; solcnt = 0
+        elif subcnt > submax:
+            stat["status"] = 6; break
+        else:
+            stat["increments"] += 1
+            s.commit()
+            stat["lpf"] = lpf
+            hist.append((lpf, itecnt, s.d[hist_dof] if hist_dof >= 0 else 0.0))
+            solcnt += 1; subcnt = 0
+            if solcnt >= solmin:
+                dlpf = min(dlpf * 2, dlpfmax); solcnt = 0
+            lpf += dlpf
+        if not lpf <= lpfmax:
+            break
+    return s.d.copy(), stat, np.array(hist)

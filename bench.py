@@ -243,12 +243,18 @@ def run_gpu(a):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(a.warmup, 3)):
-        step()
-    barrier()
+    # nvidia-smi samples every 100 ms: start it before the warm-up and keep the GPU under the same
+    # load for >= 0.5 s so that clocks / throttle reasons are observed under load, then go straight
+    # into the timed region
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
+    for _ in range(max(a.warmup, 3)):
+        step()
+    barrier()
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < 0.6:
+        step()
     l0 = asm.launches
     asm_ms, st_ms, fo_ms = [], [], []
     barrier()
@@ -362,7 +368,7 @@ def run_gpu(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native")
     ap.add_argument("--n", type=int, default=1000, help="plate cells per side (1000 = BASELINE)")

@@ -114,7 +114,7 @@ __device__ __forceinline__ void shell_block(const CbDev &d, int e, int a, int b,
 // K_ab (7x7, global axes w.r.t. the joints) of frame e: local tangent (frame.c:364-579, releases
 // 798-900), rotation by blockdiag(R,R,1) (frame.c:286-299) and, with member-end offsets, the
 // rigid-link transformation (frame.c:304-323)
-__device__ void frame_block(const CbStiffArgs &A, int e, int a, int b, double *blk, int ld)
+__device__ __noinline__ void frame_block(const CbStiffArgs &A, int e, int a, int b, double *blk, int ld)
 {
     double k[14][14], eft[14];
     const double *fr = A.fr_frame + (long)e * CB_FR_FRAME;
@@ -161,7 +161,7 @@ __device__ void frame_block(const CbStiffArgs &A, int e, int a, int b, double *b
 // strain-displacement product collapses to
 //   K_ab[i][j] = detJ * (lambda g_a[i] g_b[j] + mu g_a[j] g_b[i] + mu delta_ij g_a.g_b),
 // g_n = J^-1 dN_n/d(r,s,t).  Bricks are linear and assembled once.
-__device__ void brick_block(const CbStiffArgs &A, int e, int a, int b, double *blk, int ld)
+__device__ __noinline__ void brick_block(const CbStiffArgs &A, int e, int a, int b, double *blk, int ld)
 {
     const int sg[8] = {+1, -1, +1, -1, -1, +1, -1, +1};
     const int sr[8] = {+1, -1, -1, +1, +1, -1, -1, +1};
@@ -210,7 +210,7 @@ __device__ void brick_block(const CbStiffArgs &A, int e, int a, int b, double *b
 }
 
 // K_ab (3x3) of truss e (truss.c:102-166)
-__device__ __forceinline__ void truss_block(const CbStiffArgs &A, int e, int a, int b, double *blk,
+__device__ __noinline__ void truss_block(const CbStiffArgs &A, int e, int a, int b, double *blk,
                                             int ld)
 {
     const double *tc = A.d.tr_const + (long)e * CB_TR_CONST;
@@ -295,7 +295,9 @@ __device__ __forceinline__ void shell_block_stage(const ShellIn &in, int a, int 
         for (int q = 0; q < 3; ++q) stg[((3 + p) * ND + 3 + q) * STR] = s[p * 3 + q];
 }
 
-template <int ND>
+// SHELL_ONLY: the model holds nothing but DKT shells - the other element branches are compiled
+// out so that they cannot cost the hot configuration registers
+template <int ND, bool SHELL_ONLY>
 __global__ void __launch_bounds__(CB_TILE_T, (ND <= 6) ? 4 : 3)
 k_assemble_tiles(CbStiffArgs A)
 {
@@ -314,7 +316,7 @@ k_assemble_tiles(CbStiffArgs A)
     CbContrib ct{};
     if (t < tl.nc) ct = A.contribs[tl.c0 + t];
     ShellIn in;
-    if (ND >= 6 && t < tl.nc && ct.type == CB_T_SHELL) shell_load(A, ct, (long)tl.c0 + t, in);
+    if (ND >= 6 && t < tl.nc && (SHELL_ONLY || ct.type == CB_T_SHELL)) shell_load(A, ct, (long)tl.c0 + t, in);
 
     for (;;) {
         const long next = tile + gridDim.x;
@@ -326,7 +328,7 @@ k_assemble_tiles(CbStiffArgs A)
         // ---- phase 1: one contribution per thread -> its column of `stage` ---------------------
         if (t < tl.nc) {
             double *stg = stage + t;
-            if (ct.type == CB_T_SHELL) {
+            if (SHELL_ONLY || ct.type == CB_T_SHELL) {
                 if constexpr (ND >= 6) {
                     if (ND > 6) {
 #pragma unroll
@@ -335,6 +337,7 @@ k_assemble_tiles(CbStiffArgs A)
                     shell_block_stage<ND>(in, ct.a, ct.b, stg);
                 }
                 ndof[t] = 6;
+            } else if (SHELL_ONLY) {
             } else if (ct.type == CB_T_FRAME) {
                 if constexpr (ND >= 7) {
                     double blk[49];
@@ -363,7 +366,7 @@ k_assemble_tiles(CbStiffArgs A)
         CbContrib ctn{};
         if (has_next && t < tln.nc) ctn = A.contribs[tln.c0 + t];
         __syncthreads();
-        if (ND >= 6 && has_next && t < tln.nc && ctn.type == CB_T_SHELL)
+        if (ND >= 6 && has_next && t < tln.nc && (SHELL_ONLY || ctn.type == CB_T_SHELL))
             shell_load(A, ctn, (long)tln.c0 + t, in);
 
         // ---- phase 2: segmented reduction over the sorted contribution list, one thread per
@@ -497,14 +500,14 @@ k_assemble_blocks(CbStiffArgs A)
     }
 }
 
-template <int ND>
+template <int ND, bool SHELL_ONLY>
 static int launch_tiles(const CbStiffArgs &a, cudaStream_t s)
 {
     const size_t smem = (size_t)(((ND * ND * (CB_TILE_T + 1) + 1) & ~1) + a.tile_smem_out) * sizeof(double) +
                         CB_TILE_T * sizeof(CbTPair) + CB_TILE_T;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_assemble_tiles<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(k_assemble_tiles<ND, SHELL_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  200 * 1024) != cudaSuccess)
             return 1;
         configured = true;
@@ -513,12 +516,12 @@ static int launch_tiles(const CbStiffArgs &a, cudaStream_t s)
     int per_sm = 0, dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_tiles<ND>, CB_TILE_T, smem) !=
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_tiles<ND, SHELL_ONLY>, CB_TILE_T, smem) !=
             cudaSuccess || per_sm < 1)
         per_sm = 1;
     long grid = (long)per_sm * nsm;                    // persistent: one wave of resident CTAs
     if (grid > a.ntiles) grid = a.ntiles;
-    k_assemble_tiles<ND><<<(unsigned)grid, CB_TILE_T, smem, s>>>(a);
+    k_assemble_tiles<ND, SHELL_ONLY><<<(unsigned)grid, CB_TILE_T, smem, s>>>(a);
     return cudaGetLastError() != cudaSuccess;
 }
 
@@ -533,7 +536,8 @@ int cbk_stiff(const CbStiffArgs &a, cudaStream_t s, long *launches)
     }
     if (a.ntiles == 0) return 0;
     ++*launches;
-    if (a.max_dof <= 3) return launch_tiles<3>(a, s);
-    if (a.max_dof <= 6) return launch_tiles<6>(a, s);
-    return launch_tiles<7>(a, s);
+    const bool shell_only = a.d.NE_SH && !a.d.NE_TR && !a.d.NE_FR && !a.d.NE_BR && !a.mixed;
+    if (a.max_dof <= 3) return launch_tiles<3, false>(a, s);
+    if (a.max_dof <= 6) return shell_only ? launch_tiles<6, true>(a, s) : launch_tiles<6, false>(a, s);
+    return launch_tiles<7, false>(a, s);
 }

@@ -1,0 +1,101 @@
+"""Reader for the reference's positional `model_def.txt` deck (schema: the comment block of
+main.c:63-320, read order main.c:340-427, model.c:95-264, main.c:1394-1396, prop_* in
+truss.c:66 / frame.c:62-217 / shell.c:61, load() model.c:1313-1335, main.c:1809-1812).
+
+In a real integration the reference's own C parser stays in place; this
+reader exists so the tests and bench can push the SHIPPED sample decks through the device path.
+Covers truss / frame / shell decks; the static tail (joint loads + NR/MNR controls) is parsed,
+the dynamic tail (time histories) is returned unparsed in ``tail``."""
+from __future__ import annotations
+
+import numpy as np
+
+from .model import build_model, frame_geometry
+
+
+def _rows(text):
+    for line in text.replace("\r", "").split("\n"):
+        line = line.strip()
+        if line:
+            yield [t.strip() for t in line.split(",")]
+
+
+def read_deck(text):
+    it = _rows(text)
+    nxt = lambda: next(it)
+    ANAFLAG = int(nxt()[0]); ALGFLAG = int(nxt()[0])
+    if ALGFLAG >= 4:
+        nxt()                                   # CHKPT,RFLAG   (main.c:352-356)
+    SLVFLAG = int(nxt()[0]); OPTFLAG = int(nxt()[0])
+    NJ = int(nxt()[0])
+    ne = [int(v) for v in nxt()]
+    NE_TR, NE_FR, NE_SH = ne[0], ne[1], ne[2]
+    NE_BR = sum(ne[3:])
+    trusses = [[int(v) for v in nxt()] for _ in range(NE_TR)]
+    frames = [[int(v) for v in nxt()] for _ in range(NE_FR)]
+    shells = [[int(v) for v in nxt()] for _ in range(NE_SH)]
+    bricks = [[int(v) for v in nxt()] for _ in range(NE_BR)]
+    fixed = []
+    while True:                                 # joint constraints until 0,0 (model.c:222-262)
+        r = nxt()
+        if int(r[0]) == 0:
+            break
+        fixed.append((int(r[0]), int(r[1])))
+    if ANAFLAG != 4 and ALGFLAG > 3:            # prescribed-displacement DOFs (model.c:1156-1201)
+        while True:
+            r = nxt()
+            if int(r[0]) == 0:
+                break
+    x = np.array([[float(v) for v in nxt()] for _ in range(NJ)])
+    tp = [[float(v) for v in nxt()] for _ in range(NE_TR)]
+    fp = None; aux = None; offsets = {}; releases = {}
+    if NE_FR:
+        a = [[float(v) for v in nxt()] for _ in range(NE_FR)]       # E,G,rho,A,Iz,Iy,J,Cw
+        while True:                                                   # member end offsets
+            r = nxt()
+            if int(float(r[0])) == 0:
+                break
+            offsets[int(r[0])] = [float(v) for v in r[1:7]]
+        aux = [[float(v) for v in nxt()] for _ in range(NE_FR)]
+        y = [[float(v) for v in nxt()] for _ in range(NE_FR)]        # fy,Zz,Zy
+        while True:                                                   # member end releases
+            r = nxt()
+            if int(r[0]) == 0:
+                break
+            releases[int(r[0])] = [int(v) for v in r[1:5]]
+        fp = [ai + yi for ai, yi in zip(a, y)]
+    sp = [[float(v) for v in nxt()] for _ in range(NE_SH)]
+    loads = []; params = None; tail = None
+    if ALGFLAG < 4:
+        while True:                             # joint loads until 0,0,0 (model.c:1313-1335)
+            r = nxt()
+            if int(r[0]) == 0:
+                break
+            loads.append((int(r[0]), int(r[1]), float(r[2])))
+        if ANAFLAG == 1:
+            params = dict(lpfmax=float(nxt()[0]))
+        elif ALGFLAG in (1, 2):
+            a = [float(v) for v in nxt()]; b = [int(v) for v in nxt()]; c = [float(v) for v in nxt()]
+            params = dict(lpfmax=a[0], lpf=a[1], dlpf=a[2], dlpfmax=a[3], dlpfmin=a[4], itemax=b[0],
+                          submax=b[1], solmin=b[2], toldisp=c[0], tolforc=c[1], tolener=c[2],
+                          algflag=ALGFLAG)
+    else:
+        tail = [r for r in it]
+    m = build_model(x, trusses=trusses or None, frames=frames or None, shells=shells or None,
+                    bricks=bricks or None, fixed=fixed, truss_props=np.array(tp) if tp else None,
+                    frame_props=np.array(fp) if fp else None, shell_props=np.array(sp) if sp else None,
+                    frame_aux=np.array(aux) if aux else None, loads=loads, ANAFLAG=ANAFLAG,
+                    ALGFLAG=ALGFLAG, SLVFLAG=SLVFLAG, want_skyline=True,
+                    meta=dict(kind="deck", OPTFLAG=OPTFLAG))
+    if offsets or releases:
+        for k, v in offsets.items():
+            m.osflag[k - 1] = 1; m.offset[(k - 1) * 6:(k - 1) * 6 + 6] = v
+        for k, v in releases.items():
+            m.mendrel[(k - 1) * 5] = 1; m.mendrel[(k - 1) * 5 + 1:(k - 1) * 5 + 5] = v
+        if offsets:
+            fr = np.asarray(frames) - 1
+            xfr, ll, lx, ly, lz = frame_geometry(m.x, fr, m.auxpt, m.offset, m.osflag)
+            s = slice(m.NE_TR, m.NE_TR + m.NE_FR); cs = slice(m.NE_TR, m.NE_TR + 3 * m.NE_FR)
+            m.xfr[:] = xfr.reshape(-1); m.llength[s] = ll
+            m.c1[cs], m.c2[cs], m.c3[cs] = lx.reshape(-1), ly.reshape(-1), lz.reshape(-1)
+    return m, params, tail

@@ -368,3 +368,31 @@ def build_model(x, trusses=None, frames=None, shells=None, bricks=None, fixed=()
         if k != 0:
             m.q[k - 1] = val          # load(): *(pq+k-1) = mag (model.c:1328)
     return m
+
+
+_ARRAY_FIELDS = ["x", "minc", "jcode", "mcode", "maxa", "kht", "emod", "yld", "dens", "carea",
+                 "llength", "c1", "c2", "c3", "nu", "thick", "farea", "slength", "xlocal", "gmod",
+                 "istrong", "iweak", "ipolar", "iwarp", "zstrong", "zweak", "auxpt", "offset",
+                 "osflag", "mendrel", "xfr", "efFE_ref", "q"]
+_SCALAR_FIELDS = ["NJ", "NE_TR", "NE_FR", "NE_SH", "NE_SBR", "NE_FBR", "NEQ", "ANAFLAG", "ALGFLAG",
+                  "SLVFLAG", "lss"]
+
+
+def model_to_dict(m, prefix="model_"):
+    """flatten a Model into arrays for np.savez (fixtures)"""
+    out = {prefix + k: np.asarray(getattr(m, k)) for k in _SCALAR_FIELDS}
+    for k in _ARRAY_FIELDS:
+        a = getattr(m, k)
+        if a is not None:
+            out[prefix + k] = a
+    return out
+
+
+def model_from_dict(d, prefix="model_"):
+    m = Model()
+    for k in _SCALAR_FIELDS:
+        setattr(m, k, int(d[prefix + k]))
+    for k in _ARRAY_FIELDS:
+        if prefix + k in d:
+            setattr(m, k, np.ascontiguousarray(d[prefix + k]))
+    return m

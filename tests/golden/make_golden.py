@@ -94,8 +94,66 @@ def record(name, B=R, n_iter=3):
     return m, out
 
 
+DECKS = "/root/reference/Sample_Input_Files/"
+
+
+def deck_cases():
+    """the reference's shipped sample decks (its only fixtures)"""
+    return {"deck_5a_truss": "model_def_5a_truss.txt", "deck_5b_frame": "model_def_5b_frame.txt",
+            "deck_5c_shell": "model_def_5c_shell.txt", "deck_5d_shell": "model_def_5d_shell.txt"}
+
+
+def record_deck(name, B=R):
+    """parse the shipped deck (cubens_b200.deck), keep the parsed model in the fixture (the GPU box
+    has no /root/reference) and record what the reference computes on it:
+      5a  static MNR: the whole run (reference NR loop around its own routines + ben.exe's print)
+      5b/5c/5d  dynamic decks: K_t + lumped mass on the deck's mesh, and for the geometric-nonlinear
+          ones a seeded two-iteration walk (5b is ANAFLAG 3 in the deck; recorded as ANAFLAG 2)."""
+    import subprocess, tempfile
+    from cubens_b200 import deck
+    from cubens_b200.model import model_to_dict
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import ref_newton
+    text = open(DECKS + deck_cases()[name]).read()
+    m, params, _ = deck.read_deck(text)
+    if m.ANAFLAG == 3:
+        m.ANAFLAG = 2
+    out = model_to_dict(m)
+    s = R.RefState(m)
+    if params is not None and m.ANAFLAG == 2:
+        d, stat, hist = ref_newton(m, B, m.q, hist_dof=0, **params)
+        out["params"] = np.array([params[k] for k in ("lpfmax", "lpf", "dlpf", "dlpfmax", "dlpfmin",
+                                  "itemax", "submax", "solmin", "toldisp", "tolforc", "tolener",
+                                  "algflag")], dtype=np.float64)
+        out["d_ref"] = d; out["hist_ref"] = hist
+        out["stat_ref"] = np.array([stat["increments"], stat["iterations"], stat["status"]])
+        exe = os.path.join(ROOT, "oracle", "_ref", "ben.exe")
+        with tempfile.TemporaryDirectory() as td:
+            open(os.path.join(td, "model_def.txt"), "w").write(text.replace("\r", ""))
+            subprocess.check_call([exe], cwd=td, stdout=subprocess.DEVNULL)
+            last = open(os.path.join(td, "results2.txt")).read().strip().splitlines()[-1].split()
+        out["ben_exe_last"] = np.array([float(v) for v in last])
+        return m, out
+    out["K_sky"] = B.stiff(m, s, SLVFLAG=0, gen="c")
+    out["mass"] = B.mass(m, s, SLVFLAG=0) if B is R else B.mass(m, s)
+    if m.ANAFLAG == 2:
+        s = R.RefState(m); s.begin_increment()
+        rng = np.random.default_rng(77)
+        for it in range(2):
+            dd = rng.uniform(-1e-4, 1e-4, m.NEQ); out[f"dd_{it}"] = dd
+            B.update_forces(m, s, dd, dlpf=0.25, itecnt=it)
+            out[f"f_{it}"] = s.f_temp.copy(); out[f"ef_{it}"] = s.ef_i.copy()
+            s.end_iteration()
+            out[f"K_sky_{it}"] = B.stiff(m, s, SLVFLAG=0)
+    return m, out
+
+
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first (make -C oracle ref)"
+    for name in deck_cases():
+        m, out = record_deck(name)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "NEQ", m.NEQ, "arrays", len(out))
     for name in cases():
         m, out = record(name)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)

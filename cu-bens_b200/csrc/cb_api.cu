@@ -73,6 +73,8 @@ struct Plan {
     DevBuf<CbTile> tiles;
     DevBuf<CbTPair> tpairs;
     long ntiles = 0;
+    DevBuf<CbTile2> tiles2; DevBuf<CbWork> works; DevBuf<CbTPair> tpairs2; DevBuf<int32_t> telems;
+    long ntiles2 = 0;
     int tile_smem_out = 0;
 };
 
@@ -426,6 +428,8 @@ extern "C" void cb_destroy(cb_handle *h)
         b->release();
     h->corners.release(); h->contribs.release(); h->plan_csc.pairs.release();
     h->plan_csc.tiles.release(); h->plan_csc.tpairs.release();
+    h->plan_csc.tiles2.release(); h->plan_csc.works.release(); h->plan_csc.tpairs2.release();
+    h->plan_csc.telems.release();
     h->plan_sky.pairs.release(); h->Ap.release(); h->Ai.release(); h->maxa.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -517,6 +521,7 @@ static int build_plan(cb_handle *h)
 
     // node-pair blocks and their contribution lists
     std::vector<CbPair> pairs_csc, pairs_sky;
+    std::vector<int32_t> pair_B;              // column joint of pairs_csc[i] (natural order)
     std::vector<CbTPair> tpairs;
     std::vector<CbTile> tiles;
     std::vector<CbContrib> contribs;
@@ -550,7 +555,7 @@ static int build_plan(cb_handle *h)
             p.off = (int32_t)(h->base[B] - h->ax_base + rowoff[k]);
             p.eqA0 = h->h_first[A]; p.eqB0 = h->h_first[B];
             p.maskA = h->h_mask[A]; p.maskB = h->h_mask[B];
-            if (h->layout & CB_MAT_CSC) pairs_csc.push_back(p);
+            if (h->layout & CB_MAT_CSC) { pairs_csc.push_back(p); pair_B.push_back((int32_t)B); }
             if ((h->layout & CB_MAT_SKYLINE) && A <= B) pairs_sky.push_back(p);
             if (tiles_ok) {
                 CbTPair tp{};
@@ -604,6 +609,103 @@ static int build_plan(cb_handle *h)
         h->max_dof = top <= 3 ? 3 : (top <= 6 ? 6 : 7);
         h->mixed = (has3 && h->max_dof != 3) || (has6 && h->max_dof != 6) || (has7 && h->max_dof != 7);
     }
+    // ---- shell-only models: the "duo" tile plan of k_assemble_shell_tiles -------------------
+    std::vector<CbTile2> tiles2; std::vector<CbWork> works; std::vector<CbTPair> tp2;
+    std::vector<int32_t> telems;
+    bool plan2_ok = tiles_ok && h->sz.NE_SH && !h->sz.NE_TR && !h->sz.NE_FR && !h->NE_BR &&
+                    h->max_dof == 6 && !h->mixed;
+    if (plan2_ok) {
+        CbTile2 cur{}; bool open2 = false;
+        std::vector<int32_t> curel;               // distinct shells of the open tile
+        int cur_slots = 0;
+        auto close_tile = [&]() {
+            // pair records that need the partial-sum reduction first; remap the direct items
+            std::vector<int> perm(cur.np), inv(cur.np);
+            int k = 0;
+            for (int i = 0; i < cur.np; ++i) if (tp2[cur.p0 + i].cnt > 0) perm[k++] = i;
+            cur.nm = k;
+            for (int i = 0; i < cur.np; ++i) if (tp2[cur.p0 + i].cnt == 0) perm[k++] = i;
+            std::vector<CbTPair> tmp(cur.np);
+            for (int i = 0; i < cur.np; ++i) { tmp[i] = tp2[cur.p0 + perm[i]]; inv[perm[i]] = i; }
+            for (int i = 0; i < cur.np; ++i) tp2[cur.p0 + i] = tmp[i];
+            for (int i = 0; i < cur.nw; ++i) {
+                CbWork &w = works[cur.w0 + i];
+                if (w.kind == 0) w.dst = (uint16_t)inv[w.dst];
+            }
+            cur.ne = (int32_t)curel.size();
+            telems.insert(telems.end(), curel.begin(), curel.end());
+            tiles2.push_back(cur);
+            open2 = false;
+        };
+        size_t i = 0;
+        while (i < pairs_csc.size() && plan2_ok) {
+            size_t g1 = i;
+            const int32_t B = pair_B[i];
+            while (g1 < pairs_csc.size() && pair_B[g1] == B) ++g1;
+            int items_n = 0, slots_n = 0;
+            std::vector<int32_t> newel;
+            for (size_t q = i; q < g1; ++q) {
+                const CbPair &p = pairs_csc[q];
+                const int parts = (p.ccount + 1) / 2;
+                items_n += parts; if (p.ccount > 2) slots_n += parts;
+                for (int c = 0; c < p.ccount; ++c) {
+                    const int32_t e = contribs[p.cstart + c].e;
+                    if (std::find(curel.begin(), curel.end(), e) == curel.end() &&
+                        std::find(newel.begin(), newel.end(), e) == newel.end())
+                        newel.push_back(e);
+                }
+            }
+            const long out_n = (long)h->h_nfree[B] * h->colh[B];
+            const int pairs_n = (int)(g1 - i);
+            auto fits = [&](int nw, long nout, int slots, int np, size_t ne) {
+                return nw <= CB_TILE_T && nout <= CB_T2_OUT && slots <= CB_T2_SLOTS && np <= CB_TILE_T &&
+                       ne <= (size_t)CB_T2_ELEMS;
+            };
+            if (open2 && (!fits(cur.nw + items_n, cur.nout + out_n, cur_slots + slots_n, cur.np + pairs_n,
+                                curel.size() + newel.size()) ||
+                          h->base[B] - h->ax_base != cur.out0 + cur.nout)) {
+                close_tile();
+                newel.clear();
+                for (size_t q = i; q < g1; ++q)
+                    for (int c = 0; c < pairs_csc[q].ccount; ++c) {
+                        const int32_t e = contribs[pairs_csc[q].cstart + c].e;
+                        if (std::find(newel.begin(), newel.end(), e) == newel.end()) newel.push_back(e);
+                    }
+            }
+            if (!open2) {
+                curel.clear(); cur_slots = 0;
+                if (!fits(items_n, out_n, slots_n, pairs_n, newel.size())) { plan2_ok = false; break; }
+                cur = CbTile2{}; cur.out0 = h->base[B] - h->ax_base; cur.nout = 0;
+                cur.w0 = (int32_t)works.size(); cur.nw = 0; cur.p0 = (int32_t)tp2.size(); cur.np = 0;
+                cur.e0 = (int32_t)telems.size(); open2 = true;
+            }
+            curel.insert(curel.end(), newel.begin(), newel.end());
+            for (size_t q = i; q < g1; ++q) {
+                const CbPair &p = pairs_csc[q];
+                CbTPair tp{};
+                tp.rel = (int32_t)(p.off - cur.out0); tp.colh = p.colh; tp.maskA = p.maskA; tp.maskB = p.maskB;
+                const int parts = (p.ccount + 1) / 2;
+                tp.cs = 0; tp.cnt = 0;
+                if (p.ccount > 2) { tp.cs = (uint16_t)cur_slots; tp.cnt = (uint16_t)parts; }
+                for (int k = 0; k < parts; ++k) {
+                    CbWork w{}; w.c0 = p.cstart + 2 * k; w.n = (uint8_t)((2 * k + 1 < p.ccount) ? 2 : 1);
+                    if (p.ccount > 2) { w.kind = 1; w.dst = (uint16_t)(cur_slots + k); }
+                    else { w.kind = 0; w.dst = (uint16_t)cur.np; }
+                    works.push_back(w);
+                }
+                if (p.ccount > 2) cur_slots += parts;
+                for (int c = 0; c < p.ccount; ++c) {
+                    CbContrib &ct = contribs[p.cstart + c];
+                    ct.pad = (uint8_t)(std::find(curel.begin(), curel.end(), ct.e) - curel.begin());
+                }
+                tp2.push_back(tp); ++cur.np;
+            }
+            cur.nw += items_n; cur.nout += (int32_t)out_n;
+            i = g1;
+        }
+        if (plan2_ok && open2) close_tile();
+        if (!plan2_ok) { tiles2.clear(); works.clear(); tp2.clear(); telems.clear(); }
+    }
     // block-owner kernel (skyline, or CSC fallback for joints too large for a tile): bucket the
     // blocks by contribution count (descending, stable) so a warp's threads loop alike
     auto bucket = [](std::vector<CbPair> &v) {
@@ -612,6 +714,7 @@ static int build_plan(cb_handle *h)
     };
     bucket(pairs_sky);
     if (tiles_ok) pairs_csc.clear(); else { bucket(pairs_csc); tiles.clear(); tpairs.clear(); }
+    if (plan2_ok) { tiles.clear(); tpairs.clear(); }
 
     if (h->node_cstart.upload(cstart) || h->corners.upload(corners) || h->contribs.upload(contribs))
         return CB_ERR_CUDA;
@@ -620,6 +723,10 @@ static int build_plan(cb_handle *h)
         h->plan_csc.npairs = (long)pairs_csc.size();
         if (h->plan_csc.tiles.upload(tiles) || h->plan_csc.tpairs.upload(tpairs)) return CB_ERR_CUDA;
         h->plan_csc.ntiles = (long)tiles.size();
+        if (h->plan_csc.tiles2.upload(tiles2) || h->plan_csc.works.upload(works) ||
+            h->plan_csc.tpairs2.upload(tp2) || h->plan_csc.telems.upload(telems))
+            return CB_ERR_CUDA;
+        h->plan_csc.ntiles2 = (long)tiles2.size();
         h->plan_csc.tile_smem_out = (max_tile_out + 3) & ~1;   // room for the parity shift, kept even
         if (h->Ax.alloc((size_t)nnz)) return CB_ERR_CUDA;
         cudaMemset(h->Ax.p, 0, (size_t)nnz * sizeof(double));
@@ -635,6 +742,8 @@ static int build_plan(cb_handle *h)
     }
     h->map_bytes = (long)((pairs_csc.size() + pairs_sky.size()) * sizeof(CbPair) +
                           tiles.size() * sizeof(CbTile) + tpairs.size() * sizeof(CbTPair) +
+                          tiles2.size() * sizeof(CbTile2) + works.size() * sizeof(CbWork) +
+                          tp2.size() * sizeof(CbTPair) + telems.size() * sizeof(int32_t) +
                           contribs.size() * sizeof(CbContrib));
     // uploads above went through the legacy default stream; the handle's stream is non-blocking
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(CB_ERR_CUDA, "sync after map upload");
@@ -648,7 +757,7 @@ static int ensure_keb(cb_handle *h)
     CbDev d = make_dev(h);
     if (cbk_shell_init_keb(d, h->sh_keb.p, h->stream)) return fail(CB_ERR_CUDA, "keb init launch");
     if (h->sz.NE_SH) ++h->launches;
-    if (h->sz.NE_SH && h->plan_ready && h->plan_csc.ntiles) {
+    if (h->sz.NE_SH && h->plan_ready && (h->plan_csc.ntiles || h->plan_csc.ntiles2)) {
         if (!h->sh_kebc.p && h->sh_kebc.alloc((size_t)h->ncontrib * 10)) return CB_ERR_CUDA;
         if (cbk_shell_init_kebc(d, h->contribs.p, h->ncontrib, h->sh_kebc.p, h->stream))
             return fail(CB_ERR_CUDA, "kebc init launch");
@@ -748,6 +857,8 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
         a.pairs = h->plan_csc.pairs.p; a.npairs = h->plan_csc.npairs;
         a.tiles = h->plan_csc.ntiles ? h->plan_csc.tiles.p : nullptr; a.ntiles = h->plan_csc.ntiles;
         a.tpairs = h->plan_csc.tpairs.p; a.kebc = h->sh_kebc.p;
+        a.tiles2 = h->plan_csc.ntiles2 ? h->plan_csc.tiles2.p : nullptr; a.ntiles2 = h->plan_csc.ntiles2;
+        a.works = h->plan_csc.works.p; a.tpairs2 = h->plan_csc.tpairs2.p; a.tile_elems = h->plan_csc.telems.p;
         a.tile_smem_out = h->plan_csc.tile_smem_out;
         a.out = h->Ax.p; a.skyline = 0; a.maxa = nullptr;
         if (cbk_stiff(a, h->stream, &h->launches)) return fail(CB_ERR_CUDA, "assembly launch");
@@ -755,6 +866,7 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
     CUDA_TRY(cudaEventRecord(h->ev3, h->stream));
     if (h->layout & CB_MAT_SKYLINE) {
         a.pairs = h->plan_sky.pairs.p; a.npairs = h->plan_sky.npairs; a.tiles = nullptr;
+        a.tiles2 = nullptr; a.ntiles2 = 0;
         a.out = h->ss.p; a.skyline = 1; a.maxa = h->maxa.p;
         if (cbk_stiff(a, h->stream, &h->launches)) return fail(CB_ERR_CUDA, "assembly launch");
     }

@@ -76,6 +76,27 @@ struct CbTPair {
 #define CB_FG(p, b, e, ne) ((p) + ((long)(b) * (ne) + (e)) * 6)
 // DKT bending matrix ke_b[9][9]: component index = nine 3x3 joint-pair blocks, block-major
 #define CB_KEB(i, j) ((((i) / 3) * 3 + ((j) / 3)) * 9 + ((i) % 3) * 3 + ((j) % 3))
+// ---- shell-only tile assembly ("duo" plan): a thread evaluates up to two consecutive
+// contributions of one joint-pair block and sums them in registers; blocks with more than two
+// contributions are split into partial sums that are combined through shared memory
+#define CB_T2_OUT 3072           // max doubles of Ax per tile staged in shared memory
+#define CB_T2_SLOTS 40           // max partial sums per tile
+#define CB_T2_ELEMS 56           // max distinct shells per tile (their krec records are staged)
+struct CbTile2 {
+    int64_t out0;     // first Ax index of the tile's contiguous output range
+    int32_t nout;
+    int32_t w0, nw;   // work items (<= CB_TILE_T)
+    int32_t p0, np;   // pair records; the first nm need the partial-sum reduction
+    int32_t nm;
+    int32_t e0, ne;   // distinct shells of the tile
+};
+struct CbWork {
+    int32_t c0;       // first contribution (the second, if any, is c0 + 1)
+    uint8_t n;        // 1 or 2 contributions
+    uint8_t kind;     // 0: complete block -> written straight into the output image; 1: partial sum
+    uint16_t dst;     // kind 0: pair record index inside the tile; kind 1: partial-sum slot
+};
+
 #define CB_SH_KREC 18   // per-shell record for the stiffness pass: R[9], X2,X3,Y3, cm00,cm01,cm22, n0,n1,n2
 
 // one element corner touching a node (node -> corner CSR), used by the f_int / mass gathers
@@ -141,6 +162,8 @@ struct CbStiffArgs {
     const CbContrib *contribs;
     const CbTile *tiles; long ntiles; const CbTPair *tpairs;
     const double *kebc;      // [ncontrib][10] DKT 3x3 sub-block of each shell contribution (static)
+    const CbTile2 *tiles2; long ntiles2; const CbWork *works; const CbTPair *tpairs2;
+    const int32_t *tile_elems;
     int tile_smem_out;       // doubles of output staging per tile
     int max_dof;             // 3, 6 or 7: largest DOF count per joint among the model's elements
     int mixed;               // element types with different DOF counts per joint are present

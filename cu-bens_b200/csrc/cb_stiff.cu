@@ -428,6 +428,215 @@ k_assemble_tiles(CbStiffArgs A)
 }
 
 // ------------------------------------------------------------------------------------------
+// CSC, shell-only models: "duo" tile kernel.  One persistent CTA per run of consecutive joints.
+//   * the krec records of the tile's distinct shells are brought into shared memory once, by
+//     cp.async, double-buffered: the next tile's records land while this tile is processed;
+//   * phase 1: a thread evaluates up to two consecutive contributions of one joint-pair block and
+//     adds them in registers; a complete block goes straight into the tile's output image, a
+//     partial sum of a larger block (diagonal blocks: one contribution per adjacent shell) into
+//     the small partial-sum stage;
+//   * phase 2: the partial sums of those blocks are added in list order;
+//   * phase 3: the image is streamed to HBM with aligned 16-byte stores.
+// shared memory: obuf[CB_T2_OUT+2] | stage[36][CB_T2_SLOTS+1] | skrec[2][CB_T2_ELEMS][18] |
+//                spair[CB_TILE_T]
+// ------------------------------------------------------------------------------------------
+#define CB_T2_SSTR (CB_T2_SLOTS + 1)
+
+// K_ab (6x6) of one shell contribution, accumulated into blk[36] (row-major)
+__device__ __forceinline__ void shell_block_acc(const double *kr, const double *kb, int a, int b,
+                                                double *blk, bool first)
+{
+    const double *R = kr;
+    double bxa, bya, bxb, byb;
+    cst_grad(a, kr[9], kr[10], kr[11], bxa, bya);
+    cst_grad(b, kr[9], kr[10], kr[11], bxb, byb);
+    const double m00 = kr[12] * bxa * bxb + kr[14] * bya * byb;
+    const double m01 = kr[13] * bxa * byb + kr[14] * bya * bxb;
+    const double m10 = kr[13] * bya * bxb + kr[14] * bxa * byb;
+    const double m11 = kr[12] * bya * byb + kr[14] * bxa * bxb;
+    const double g = bxa * (kr[15] * bxb + kr[17] * byb) + bya * (kr[17] * bxb + kr[16] * byb);
+    const double drill = (a == b) ? kb[4] / 10000 : 0.0;
+    double s[9];
+#define CB_PUT(r0, c0)                                                                            \
+    _Pragma("unroll") for (int p = 0; p < 3; ++p) _Pragma("unroll") for (int q = 0; q < 3; ++q) {  \
+        if (first) blk[((r0) + p) * 6 + (c0) + q] = s[p * 3 + q];                                   \
+        else blk[((r0) + p) * 6 + (c0) + q] += s[p * 3 + q];                                        \
+    }
+    rtsr_diag(R, m00 + g, m01, m10, m11 + g, kb[0] + g, s, 3);
+    CB_PUT(0, 0)
+    rtsr_row(R, kb[1], kb[2], s, 3);
+    CB_PUT(0, 3)
+    rtsr_col(R, kb[3], kb[6], s, 3);
+    CB_PUT(3, 0)
+    rtsr_diag(R, kb[4], kb[5], kb[7], kb[8], drill, s, 3);
+    CB_PUT(3, 3)
+#undef CB_PUT
+}
+
+__device__ __forceinline__ void t2_issue_krec(const CbStiffArgs &A, const CbTile2 &tl, double *dstbuf)
+{
+    // 9 chunks of 16 bytes per shell record
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(dstbuf);
+    for (int i = threadIdx.x; i < tl.ne * 9; i += CB_TILE_T) {
+        const int es = i / 9, ch = i - es * 9;
+        const long e = A.tile_elems[tl.e0 + es];
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (es * CB_SH_KREC * 8 + ch * 16)),
+                     "l"(A.d.sh_Nm + e * CB_SH_KREC + ch * 2));
+    }
+    asm volatile("cp.async.commit_group;");
+}
+
+__global__ void __launch_bounds__(CB_TILE_T, 4)
+k_assemble_shell_tiles(CbStiffArgs A)
+{
+    extern __shared__ double smem[];
+    double *obuf = smem;                                              // [CB_T2_OUT + 2]
+    double *stage = obuf + CB_T2_OUT + 2;                             // [36][CB_T2_SSTR]
+    double *skrec = stage + 36 * CB_T2_SSTR + (36 * CB_T2_SSTR & 1);   // [2][CB_T2_ELEMS*18], 16 B aligned
+    CbTPair *spair = reinterpret_cast<CbTPair *>(skrec + 2 * CB_T2_ELEMS * CB_SH_KREC);
+    const int t = threadIdx.x;
+    long tile = blockIdx.x;
+    if (tile >= A.ntiles2) return;
+    CbTile2 tl = A.tiles2[tile];
+    int buf = 0;
+    t2_issue_krec(A, tl, skrec);
+    CbWork w{};
+    if (t < tl.nw) w = A.works[tl.w0 + t];
+
+    for (;;) {
+        const long next = tile + gridDim.x;
+        const bool has_next = next < A.ntiles2;
+        CbTile2 tln = tl;
+        if (has_next) tln = A.tiles2[next];
+        if (t < tl.np) spair[t] = A.tpairs2[tl.p0 + t];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                   // krec of this tile + spair visible
+        if (has_next) t2_issue_krec(A, tln, skrec + (buf ^ 1) * CB_T2_ELEMS * CB_SH_KREC);
+        const int shift = (int)(tl.out0 & 1);
+
+        // ---- phase 1 ---------------------------------------------------------------------------
+        if (t < tl.nw) {
+            const double *kr0 = skrec + buf * CB_T2_ELEMS * CB_SH_KREC;
+            double blk[36];
+            {
+                const CbContrib ct = A.contribs[w.c0];
+                double kb[10];
+                const double2 *kb2 = reinterpret_cast<const double2 *>(A.kebc + (long)w.c0 * 10);
+#pragma unroll
+                for (int i = 0; i < 5; ++i) { double2 v = __ldg(kb2 + i); kb[2 * i] = v.x; kb[2 * i + 1] = v.y; }
+                shell_block_acc(kr0 + ct.pad * CB_SH_KREC, kb, ct.a, ct.b, blk, true);
+            }
+            if (w.n == 2) {
+                const CbContrib ct = A.contribs[w.c0 + 1];
+                double kb[10];
+                const double2 *kb2 = reinterpret_cast<const double2 *>(A.kebc + (long)(w.c0 + 1) * 10);
+#pragma unroll
+                for (int i = 0; i < 5; ++i) { double2 v = __ldg(kb2 + i); kb[2 * i] = v.x; kb[2 * i + 1] = v.y; }
+                shell_block_acc(kr0 + ct.pad * CB_SH_KREC, kb, ct.a, ct.b, blk, false);
+            }
+            if (w.kind == 0) {
+                const CbTPair pr = spair[w.dst];
+                double *img = obuf + shift + pr.rel;
+                if (pr.maskA == 0x3f && pr.maskB == 0x3f) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        double *col = img + c * pr.colh;
+#pragma unroll
+                        for (int r = 0; r < 6; ++r) col[r] = blk[r * 6 + c];
+                    }
+                } else {
+                    int cc = 0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        if (!((pr.maskB >> c) & 1)) continue;
+                        double *col = img + cc * pr.colh;
+                        int rr = 0;
+#pragma unroll
+                        for (int r = 0; r < 6; ++r)
+                            if ((pr.maskA >> r) & 1) col[rr++] = blk[r * 6 + c];
+                        ++cc;
+                    }
+                }
+            } else {
+                double *stg = stage + w.dst;
+#pragma unroll
+                for (int i = 0; i < 36; ++i) stg[i * CB_T2_SSTR] = blk[i];
+            }
+        }
+        // next tile's work item: requested now, used after the barriers below
+        CbWork wn{};
+        if (has_next && t < tln.nw) wn = A.works[tln.w0 + t];
+        __syncthreads();
+
+        // ---- phase 2: blocks with more than two contributions: add their partial sums ----------
+        for (int it = t; it < tl.nm * 6; it += CB_TILE_T) {
+            const int p = it / 6, c = it - p * 6;
+            const CbTPair pr = spair[p];
+            if (!((pr.maskB >> c) & 1)) continue;
+            const int cc = __popc(pr.maskB & ((1u << c) - 1));
+            double *dst = obuf + shift + pr.rel + cc * pr.colh;
+            const double *src = stage + c * CB_T2_SSTR + pr.cs;
+            double acc[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) acc[r] = src[r * 6 * CB_T2_SSTR];
+            for (int q = 1; q < pr.cnt; ++q) {
+#pragma unroll
+                for (int r = 0; r < 6; ++r) acc[r] += src[r * 6 * CB_T2_SSTR + q];
+            }
+            if (pr.maskA == 0x3f) {
+#pragma unroll
+                for (int r = 0; r < 6; ++r) dst[r] = acc[r];
+            } else {
+                int rr = 0;
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+                    if ((pr.maskA >> r) & 1) dst[rr++] = acc[r];
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 3: stream the tile's output image to HBM -------------------------------------
+        {
+            double *dst = A.out + tl.out0;
+            const double *img = obuf + shift;
+            if (shift && t == 0) dst[0] = img[0];
+            const int nv = (tl.nout - shift) >> 1;
+            const double2 *img2 = reinterpret_cast<const double2 *>(img + shift);
+            double2 *dst2 = reinterpret_cast<double2 *>(dst + shift);
+            for (int i = t; i < nv; i += CB_TILE_T) dst2[i] = img2[i];
+            const int tail = shift + 2 * nv;
+            if (tail < tl.nout && t == CB_TILE_T - 1) dst[tail] = img[tail];
+        }
+        if (!has_next) break;
+        tile = next; tl = tln; w = wn; buf ^= 1;
+        __syncthreads();
+    }
+}
+
+static int launch_shell_tiles(const CbStiffArgs &a, cudaStream_t s)
+{
+    const size_t smem = (size_t)(CB_T2_OUT + 2 + 36 * CB_T2_SSTR + 1 + 2 * CB_T2_ELEMS * CB_SH_KREC) * sizeof(double) +
+                        CB_TILE_T * sizeof(CbTPair);
+    static int grid_cache = 0;
+    if (!grid_cache) {
+        if (cudaFuncSetAttribute(k_assemble_shell_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess)
+            return 1;
+        int per_sm = 0, dev = 0, nsm = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_shell_tiles, CB_TILE_T, smem) !=
+                cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        grid_cache = per_sm * nsm;
+    }
+    long grid = grid_cache;
+    if (grid > a.ntiles2) grid = a.ntiles2;
+    k_assemble_shell_tiles<<<(unsigned)grid, CB_TILE_T, smem, s>>>(a);
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------------
 // skyline: one thread per node-pair block
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CB_TPB_K)
@@ -527,6 +736,7 @@ static int launch_tiles(const CbStiffArgs &a, cudaStream_t s)
 
 int cbk_stiff(const CbStiffArgs &a, cudaStream_t s, long *launches)
 {
+    if (!a.skyline && a.ntiles2 > 0 && a.tiles2) { ++*launches; return launch_shell_tiles(a, s); }
     if (a.skyline || a.tiles == nullptr) {
         if (a.npairs == 0) return 0;
         unsigned g = (unsigned)((a.npairs + CB_TPB_K - 1) / CB_TPB_K);

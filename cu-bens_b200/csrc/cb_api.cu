@@ -689,6 +689,12 @@ static int build_plan(cb_handle *h)
                 if (p.ccount > 2) { tp.cs = (uint16_t)cur_slots; tp.cnt = (uint16_t)parts; }
                 for (int k = 0; k < parts; ++k) {
                     CbWork w{}; w.c0 = p.cstart + 2 * k; w.n = (uint8_t)((2 * k + 1 < p.ccount) ? 2 : 1);
+                    for (int u = 0; u < w.n; ++u) {
+                        const CbContrib &cu = contribs[w.c0 + u];
+                        const uint8_t slot = (uint8_t)(std::find(curel.begin(), curel.end(), cu.e) - curel.begin());
+                        if (u == 0) { w.a0 = cu.a; w.b0 = cu.b; w.s0 = slot; }
+                        else { w.a1 = cu.a; w.b1 = cu.b; w.s1 = slot; }
+                    }
                     if (p.ccount > 2) { w.kind = 1; w.dst = (uint16_t)(cur_slots + k); }
                     else { w.kind = 0; w.dst = (uint16_t)cur.np; }
                     works.push_back(w);

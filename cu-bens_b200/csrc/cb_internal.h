@@ -90,11 +90,13 @@ struct CbTile2 {
     int32_t nm;
     int32_t e0, ne;   // distinct shells of the tile
 };
-struct CbWork {
-    int32_t c0;       // first contribution (the second, if any, is c0 + 1)
+struct CbWork {       // 16 bytes, self-contained: no dependent load of the contribution records
+    int32_t c0;       // first contribution (the second, if any, is c0 + 1): index into kebc
     uint8_t n;        // 1 or 2 contributions
     uint8_t kind;     // 0: complete block -> written straight into the output image; 1: partial sum
     uint16_t dst;     // kind 0: pair record index inside the tile; kind 1: partial-sum slot
+    uint8_t a0, b0, s0, pad0;   // local row / column joint and tile-local shell slot, contribution 0
+    uint8_t a1, b1, s1, pad1;   // ... contribution 1
 };
 
 #define CB_SH_KREC 18   // per-shell record for the stiffness pass: R[9], X2,X3,Y3, cm00,cm01,cm22, n0,n1,n2

@@ -486,6 +486,13 @@ __device__ __forceinline__ void t2_issue_krec(const CbStiffArgs &A, const CbTile
     asm volatile("cp.async.commit_group;");
 }
 
+__device__ __forceinline__ void t2_load_kb(const CbStiffArgs &A, long c, double *kb)
+{
+    const double2 *kb2 = reinterpret_cast<const double2 *>(A.kebc + c * 10);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { double2 v = __ldg(kb2 + i); kb[2 * i] = v.x; kb[2 * i + 1] = v.y; }
+}
+
 __global__ void __launch_bounds__(CB_TILE_T, 4)
 k_assemble_shell_tiles(CbStiffArgs A)
 {
@@ -519,20 +526,14 @@ k_assemble_shell_tiles(CbStiffArgs A)
             const double *kr0 = skrec + buf * CB_T2_ELEMS * CB_SH_KREC;
             double blk[36];
             {
-                const CbContrib ct = A.contribs[w.c0];
                 double kb[10];
-                const double2 *kb2 = reinterpret_cast<const double2 *>(A.kebc + (long)w.c0 * 10);
-#pragma unroll
-                for (int i = 0; i < 5; ++i) { double2 v = __ldg(kb2 + i); kb[2 * i] = v.x; kb[2 * i + 1] = v.y; }
-                shell_block_acc(kr0 + ct.pad * CB_SH_KREC, kb, ct.a, ct.b, blk, true);
+                t2_load_kb(A, w.c0, kb);
+                shell_block_acc(kr0 + w.s0 * CB_SH_KREC, kb, w.a0, w.b0, blk, true);
             }
             if (w.n == 2) {
-                const CbContrib ct = A.contribs[w.c0 + 1];
                 double kb[10];
-                const double2 *kb2 = reinterpret_cast<const double2 *>(A.kebc + (long)(w.c0 + 1) * 10);
-#pragma unroll
-                for (int i = 0; i < 5; ++i) { double2 v = __ldg(kb2 + i); kb[2 * i] = v.x; kb[2 * i + 1] = v.y; }
-                shell_block_acc(kr0 + ct.pad * CB_SH_KREC, kb, ct.a, ct.b, blk, false);
+                t2_load_kb(A, w.c0 + 1, kb);
+                shell_block_acc(kr0 + w.s1 * CB_SH_KREC, kb, w.a1, w.b1, blk, false);
             }
             if (w.kind == 0) {
                 const CbTPair pr = spair[w.dst];
@@ -563,7 +564,7 @@ k_assemble_shell_tiles(CbStiffArgs A)
                 for (int i = 0; i < 36; ++i) stg[i * CB_T2_SSTR] = blk[i];
             }
         }
-        // next tile's work item: requested now, used after the barriers below
+        // next tile's work item: requested now, used after the reduction below
         CbWork wn{};
         if (has_next && t < tln.nw) wn = A.works[tln.w0 + t];
         __syncthreads();
@@ -594,6 +595,13 @@ k_assemble_shell_tiles(CbStiffArgs A)
             }
         }
         __syncthreads();
+
+        // the next tile's DKT blocks: pulled into L2 now so the loads of the next phase 1 are short
+        if (has_next && t < tln.nw) {
+            const double *pk = A.kebc + (long)wn.c0 * 10;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pk));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pk + 16));
+        }
 
         // ---- phase 3: stream the tile's output image to HBM -------------------------------------
         {

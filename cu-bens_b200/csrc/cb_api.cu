@@ -114,7 +114,7 @@ struct cb_handle {
     DevBuf<double> dd, f_temp, f, d, d_temp, sm;
     // shells
     DevBuf<int32_t> sh_nodes;
-    DevBuf<double> sh_const, sh_keb, sh_kebc, sh_Nm, sh_fg, sh_dens;
+    DevBuf<double> sh_const, sh_keb, sh_kebc, sh_der, sh_Nm, sh_fg, sh_dens;
     long ncontrib = 0;
     DevBuf<double> sh_frame[3], sh_dsl[3], sh_ef[3];   // 0 = committed, 1/2 = iterate ping-pong
     // trusses
@@ -162,7 +162,7 @@ static CbDev make_dev(cb_handle *h)
     d.ANAFLAG = h->fl.ANAFLAG;
     d.jc = h->jc.p;
     d.sh_nodes = h->sh_nodes.p; d.sh_const = h->sh_const.p; d.sh_keb = h->sh_keb.p;
-    d.sh_Nm = h->sh_Nm.p; d.sh_fg = h->sh_fg.p;
+    d.sh_Nm = h->sh_Nm.p; d.sh_fg = h->sh_fg.p; d.sh_der = h->sh_der.p;
     d.fr_nodes = h->fr_nodes.p; d.fr_const = h->fr_const.p; d.fr_offset = h->fr_offset.p;
     d.fr_osflag = h->fr_osflag.p; d.fr_mendrel = h->fr_mendrel.p;
     d.fr_efFE_ref = h->fr_efFE_ref.p; d.fr_fg = h->fr_fg.p;
@@ -390,7 +390,7 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
             F(9, e) = m->farea[e];                       // deffarea = farea (main.c:1700)
             if (m->dens) dn[e] = m->dens[e];             // pdens+i, shell.c:61 / 1551
         }
-        if (h->sh_const.upload(c) || h->sh_dens.upload(dn) || h->sh_keb.alloc((size_t)SH * 81) ||
+        if (h->sh_const.upload(c) || h->sh_dens.upload(dn) || h->sh_keb.alloc((size_t)SH * 81) || h->sh_der.alloc((size_t)SH * CB_SH_DER) ||
             h->sh_Nm.alloc((size_t)SH * CB_SH_KREC) || h->sh_fg.alloc((size_t)SH * 18))
             BAIL(CB_ERR_CUDA);
         for (int g = 0; g < 3; ++g) {
@@ -412,7 +412,7 @@ extern "C" void cb_destroy(cb_handle *h)
     cudaSetDevice(h->fl.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf<double> *b : {&h->x, &h->x_temp, &h->x_ip, &h->dd, &h->f_temp, &h->f, &h->d,
-                              &h->d_temp, &h->sm, &h->sh_const, &h->sh_keb, &h->sh_kebc, &h->sh_Nm, &h->sh_fg,
+                              &h->d_temp, &h->sm, &h->sh_const, &h->sh_keb, &h->sh_kebc, &h->sh_der, &h->sh_Nm, &h->sh_fg,
                               &h->sh_dens, &h->tr_const, &h->tr_fg, &h->tr_dens, &h->fr_const,
                               &h->fr_offset, &h->fr_efFE_ref, &h->fr_fg, &h->fr_dens, &h->br_const,
                               &h->Ax, &h->ss})

@@ -109,6 +109,9 @@ __device__ void dkt_alpha_T(const double *sc, double aT[9][9])
     aT[8][8] = -x23 * r5 - X3 * r4 + 4 * X2 + Y3 * (q5 - q4);
 }
 
+__device__ __forceinline__ void plane_stress(double E, double nu, double &C00, double &C01, double &C22);
+__device__ __forceinline__ void membrane_B(const double *sc, double A, double Bm[3][6]);
+
 __global__ void __launch_bounds__(CB_TPB)
 k_shell_init_keb(CbDev d, double *__restrict__ keb)
 {
@@ -143,6 +146,32 @@ k_shell_init_keb(CbDev d, double *__restrict__ keb)
             for (int k = 0; k < 9; ++k) sum += Q[i][k] * aT[j][k];
             SOA(keb, CB_KEB(i, j), e, d.NE_SH) = sum / (2 * A0);
         }
+    // membrane: the three columns of ke_m (shell.c:487-531) that the membrane displacement vector
+    // dm = (0,0,dm2,0,dm4,dm5) multiplies, the plane-stress coefficients and t*A0*C/(2 A0)^2
+    double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    plane_stress(sc[0], sc[1], C[0][0], C[0][1], C[2][2]);
+    C[1][1] = C[0][0]; C[1][0] = C[0][1];
+    double Bm[3][6];
+    membrane_B(sc, sc[4], Bm);
+    const int col[3] = {2, 4, 5};
+    for (int i = 0; i < 6; ++i) {
+        double BC[3];
+        for (int j = 0; j < 3; ++j) {           // Bm_C[i][j] (shell.c:513-521)
+            double sum = 0;
+            for (int k = 0; k < 3; ++k) sum += Bm[k][i] * C[k][j];
+            BC[j] = sum;
+        }
+        for (int jc = 0; jc < 3; ++jc) {
+            double sum = 0;                      // ke_m[i][j] (shell.c:522-530)
+            for (int k = 0; k < 3; ++k) sum += BC[k] * Bm[k][col[jc]];
+            SOA(d.sh_der, i * 3 + jc, e, d.NE_SH) = sc[2] * sc[4] * sum;
+        }
+    }
+    SOA(d.sh_der, 18, e, d.NE_SH) = C[0][0]; SOA(d.sh_der, 19, e, d.NE_SH) = C[0][1];
+    SOA(d.sh_der, 20, e, d.NE_SH) = C[2][2];
+    const double smc = sc[2] / (4 * sc[4]);
+    SOA(d.sh_der, 21, e, d.NE_SH) = smc * C[0][0]; SOA(d.sh_der, 22, e, d.NE_SH) = smc * C[0][1];
+    SOA(d.sh_der, 23, e, d.NE_SH) = smc * C[2][2];
 }
 
 int cbk_shell_init_keb(const CbDev &d, double *keb_out, cudaStream_t s)
@@ -230,32 +259,27 @@ __device__ __forceinline__ void membrane_dm(const double *xj, const double *xk, 
 // gathered per contribution by the assembly kernel, so it is stored AoS [NE][18]; the 32
 // records of a warp are transposed through shared memory and written as one contiguous run.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void shell_krec(const double *sc, const double *R /*[10]*/, double dm2,
-                                           double dm4, double dm5, int anaflag, double *kr)
+__device__ __forceinline__ void shell_krec(double X2, double X3, double Y3, double thick,
+                                           const double *R /*[10]*/, const double *cst /*C00,C01,C22,
+                                           smc*C00, smc*C01, smc*C22*/, double dm2, double dm4,
+                                           double dm5, int anaflag, double *kr)
 {
-    double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    plane_stress(sc[0], sc[1], C[0][0], C[0][1], C[2][2]);
-    C[1][1] = C[0][0]; C[1][0] = C[0][1];
-    double Bm[3][6];
-    membrane_B(sc, R[9], Bm);
-    const double dm[6] = {0, 0, dm2, 0, dm4, dm5};
-    double Nm[3];
-    for (int i = 0; i < 3; ++i) {
-        double sum = 0;
-        for (int j = 0; j < 6; ++j) {
-            double cb = 0;                      // C_Bm[i][j] (shell.c:689-697)
-            for (int k = 0; k < 3; ++k) cb += C[i][k] * Bm[k][j];
-            sum += cb * dm[j];
-        }
-        Nm[i] = sc[2] * sum;
-    }
+    // membrane strains with the deformed area (Bm of shell.c:678-686 applied to dm), then
+    // Nm = t C eps.  Nm only feeds the geometric stiffness (1e-12 tolerance), so it is evaluated
+    // in its cheapest form; dm itself is the reference-rounded quantity.
+    const double i2a = 1.0 / (2 * R[9]);
+    const double exx = Y3 * dm2 * i2a;
+    const double eyy = X2 * dm5 * i2a;
+    const double gxy = (X2 * dm4 - X3 * dm2) * i2a;
+    const double Nx = thick * (cst[0] * exx + cst[1] * eyy);
+    const double Ny = thick * (cst[1] * exx + cst[0] * eyy);
+    const double Nxy = thick * cst[2] * gxy;
 #pragma unroll
     for (int i = 0; i < 9; ++i) kr[i] = R[i];
-    kr[9] = sc[5]; kr[10] = sc[6]; kr[11] = sc[7];
-    const double smc = sc[2] / (4 * sc[4]);
-    kr[12] = smc * C[0][0]; kr[13] = smc * C[0][1]; kr[14] = smc * C[2][2];
-    const double gs = (anaflag == 2) ? 1.0 / (4 * R[9]) : 0.0;
-    kr[15] = gs * Nm[0]; kr[16] = gs * Nm[1]; kr[17] = gs * Nm[2];
+    kr[9] = X2; kr[10] = X3; kr[11] = Y3;
+    kr[12] = cst[3]; kr[13] = cst[4]; kr[14] = cst[5];
+    const double gs = (anaflag == 2) ? 0.5 * i2a : 0.0;          // 1 / (4 A_def)
+    kr[15] = gs * Nx; kr[16] = gs * Ny; kr[17] = gs * Nxy;
 }
 
 // all 32 lanes of the warp must call this (kr may be garbage for lanes past the last element)
@@ -298,7 +322,10 @@ k_shell_prep(CbDev d, const double *__restrict__ x, const double *__restrict__ f
         }
         double dm2, dm4, dm5;
         membrane_dm(xj, xk, xl, R, sc, dm2, dm4, dm5);
-        shell_krec(sc, R, dm2, dm4, dm5, d.ANAFLAG, kr);
+        double cst[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) cst[i] = SOA(d.sh_der, 18 + i, e, d.NE_SH);
+        shell_krec(sc[5], sc[6], sc[7], sc[2], R, cst, dm2, dm4, dm5, d.ANAFLAG, kr);
     }
     warp_store_krec(d.sh_Nm, e - (threadIdx.x & 31), d.NE_SH, kr, tile[threadIdx.x >> 5]);
 }
@@ -402,8 +429,9 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
     }
     if (live) {
     double sc[CB_SH_CONST], Rp[CB_SH_FRAME], Ri[CB_SH_FRAME], dsl[3];
+    sc[2] = __ldg(&SOA(d.sh_const, 2, e, d.NE_SH));               // thickness
 #pragma unroll
-    for (int i = 0; i < CB_SH_CONST; ++i) sc[i] = __ldg(&SOA(d.sh_const, i, e, d.NE_SH));
+    for (int i = 5; i < 8; ++i) sc[i] = __ldg(&SOA(d.sh_const, i, e, d.NE_SH));   // x2, x3, y3
 #pragma unroll
     for (int i = 0; i < CB_SH_FRAME; ++i) Rp[i] = __ldg(&SOA(frame_ip, i, e, d.NE_SH));
     const int4 nd = reinterpret_cast<const int4 *>(d.sh_nodes)[e];
@@ -421,30 +449,22 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
     membrane_dm(X[0], X[1], X[2], Ri, sc, dm2, dm4, dm5);
     // record for the next stiffness pass: after `_ip <- _i` this triad / area / dm are exactly
     // what stiff_sh evaluates (shell.c:159-171)
-    shell_krec(sc, Ri, dm2, dm4, dm5, d.ANAFLAG, kr);
-    double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    plane_stress(sc[0], sc[1], C[0][0], C[0][1], C[2][2]);
-    C[1][1] = C[0][0]; C[1][0] = C[0][1];
-    double Bm[3][6];
-    membrane_B(sc, sc[4], Bm);
-    double ef_temp[6];
     {
-        const double dmv[6] = {0, 0, dm2, 0, dm4, dm5};
-        for (int i = 0; i < 6; ++i) {
-            double BC[3];
-            for (int j = 0; j < 3; ++j) {       // Bm_C[i][j] (shell.c:513-521)
-                double sum = 0;
-                for (int k = 0; k < 3; ++k) sum += Bm[k][i] * C[k][j];
-                BC[j] = sum;
-            }
-            double acc = 0;
-            for (int j = 0; j < 6; ++j) {
-                double sum = 0;                  // ke_m[i][j] (shell.c:522-530)
-                for (int k = 0; k < 3; ++k) sum += BC[k] * Bm[k][j];
-                acc += (sc[2] * sc[4] * sum) * dmv[j];
-            }
-            ef_temp[i] = acc;
-        }
+        double cst[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) cst[i] = __ldg(&SOA(d.sh_der, 18 + i, e, d.NE_SH));
+        shell_krec(sc[5], sc[6], sc[7], sc[2], Ri, cst, dm2, dm4, dm5, d.ANAFLAG, kr);
+    }
+    // ke_m * dm with the geometry-constant membrane columns (shell.c:1767-1775): the structural
+    // zeros of dm add nothing, the remaining three terms keep the reference's order
+    double ef_temp[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double acc = 0;
+        acc += __ldg(&SOA(d.sh_der, i * 3 + 0, e, d.NE_SH)) * dm2;
+        acc += __ldg(&SOA(d.sh_der, i * 3 + 1, e, d.NE_SH)) * dm4;
+        acc += __ldg(&SOA(d.sh_der, i * 3 + 2, e, d.NE_SH)) * dm5;
+        ef_temp[i] = acc;
     }
 
     // bending: incremental force ke_b * ddb, ddb = T_ip * DD on the bending DOFs (1746-1785)

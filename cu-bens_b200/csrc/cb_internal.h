@@ -99,6 +99,7 @@ struct CbWork {       // 16 bytes, self-contained: no dependent load of the cont
     uint8_t a1, b1, s1, pad1;   // ... contribution 1
 };
 
+#define CB_SH_DER 24
 #define CB_SH_KREC 18   // per-shell record for the stiffness pass: R[9], X2,X3,Y3, cm00,cm01,cm22, n0,n1,n2
 
 // one element corner touching a node (node -> corner CSR), used by the f_int / mass gathers
@@ -133,6 +134,9 @@ struct CbDev {
     const int32_t *sh_nodes; // [NE][4] 0-based
     const double *sh_const;  // [CB_SH_CONST][NE]
     const double *sh_keb;    // [81][NE], component = CB_KEB(i,j)
+    double *sh_der;          // [CB_SH_DER][NE] geometry-constant derived data (k_shell_init_keb):
+                             // 0-17 ke_m[i][{2,4,5}] (the membrane columns dm multiplies), 18-20
+                             // plane-stress C00,C01,C22, 21-23 t/(4 A0) * C
     double *sh_Nm;           // [NE][CB_SH_KREC] stiffness-pass record written by k_shell_prep
     double *sh_fg;           // [3][NE][6] element force in global axes (staging for the gather)
     // frames

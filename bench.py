@@ -332,7 +332,7 @@ def run_gpu(a):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("k_assemble_tiles_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("k_assemble_shell_tiles_dram_bytes_per_launch")
         except Exception:
             traffic = None
     line = {
@@ -349,7 +349,7 @@ def run_gpu(a):
         "clocks": clk, "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / a.steps,
         "split_ms": {"stiff_total": float(np.median(st_ms)), "assemble_kernel": k_ms,
                      "update_forces": float(np.median(fo_ms))},
-        "roofline": {"kernel": "k_assemble_tiles", "bound": "hbm", "achieved": ach, "peak": peak,
+        "roofline": {"kernel": "k_assemble_shell_tiles", "bound": "hbm", "achieved": ach, "peak": peak,
                      "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALG_BYTES_KT * n_local,

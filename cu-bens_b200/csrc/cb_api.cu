@@ -74,7 +74,7 @@ struct Plan {
     DevBuf<CbTPair> tpairs;
     long ntiles = 0;
     DevBuf<CbTile2> tiles2; DevBuf<CbWork> works; DevBuf<CbTPair> tpairs2; DevBuf<int32_t> telems;
-    long ntiles2 = 0;
+    long ntiles2 = 0, nworks = 0;
     int tile_smem_out = 0;
 };
 
@@ -111,7 +111,8 @@ struct cb_handle {
     // device: nodes and vectors
     DevBuf<int32_t> jc;
     DevBuf<double> x, x_temp, x_ip;
-    DevBuf<double> dd, f_temp, f, d, d_temp, sm;
+    DevBuf<double> dd, f_temp, f, d, d_temp, sm, qvec, sums, sums_part;
+    long eq0 = 0, eq1 = 0;        // equation range of the owned joints
     // shells
     DevBuf<int32_t> sh_nodes;
     DevBuf<double> sh_const, sh_keb, sh_kebc, sh_der, sh_Nm, sh_fg, sh_dens;
@@ -412,7 +413,7 @@ extern "C" void cb_destroy(cb_handle *h)
     cudaSetDevice(h->fl.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf<double> *b : {&h->x, &h->x_temp, &h->x_ip, &h->dd, &h->f_temp, &h->f, &h->d,
-                              &h->d_temp, &h->sm, &h->sh_const, &h->sh_keb, &h->sh_kebc, &h->sh_der, &h->sh_Nm, &h->sh_fg,
+                              &h->d_temp, &h->sm, &h->qvec, &h->sums, &h->sums_part, &h->sh_const, &h->sh_keb, &h->sh_kebc, &h->sh_der, &h->sh_Nm, &h->sh_fg,
                               &h->sh_dens, &h->tr_const, &h->tr_fg, &h->tr_dens, &h->fr_const,
                               &h->fr_offset, &h->fr_efFE_ref, &h->fr_fg, &h->fr_dens, &h->br_const,
                               &h->Ax, &h->ss})
@@ -617,20 +618,62 @@ static int build_plan(cb_handle *h)
     if (plan2_ok) {
         CbTile2 cur{}; bool open2 = false;
         std::vector<int32_t> curel;               // distinct shells of the open tile
-        int cur_slots = 0;
+        int cur_gmax = 1;
         auto close_tile = [&]() {
-            // pair records that need the partial-sum reduction first; remap the direct items
-            std::vector<int> perm(cur.np), inv(cur.np);
-            int k = 0;
-            for (int i = 0; i < cur.np; ++i) if (tp2[cur.p0 + i].cnt > 0) perm[k++] = i;
-            cur.nm = k;
-            for (int i = 0; i < cur.np; ++i) if (tp2[cur.p0 + i].cnt == 0) perm[k++] = i;
-            std::vector<CbTPair> tmp(cur.np);
-            for (int i = 0; i < cur.np; ++i) { tmp[i] = tp2[cur.p0 + perm[i]]; inv[perm[i]] = i; }
-            for (int i = 0; i < cur.np; ++i) tp2[cur.p0 + i] = tmp[i];
-            for (int i = 0; i < cur.nw; ++i) {
-                CbWork &w = works[cur.w0 + i];
-                if (w.kind == 0) w.dst = (uint16_t)inv[w.dst];
+            // lane assignment.  A complete block is written into the image with 16-byte stores, eight
+            // lanes per shared-memory wavefront: the lanes of one aligned group of eight get blocks
+            // whose image offsets fall into distinct 16-byte bank groups (no store conflicts).  The
+            // partial sums of a group (kind 2 leader + kind 3 followers) sit in consecutive
+            // lanes of one warp; idle items (kind 4) pad a warp whose tail is too short for a group.
+            {
+                const int shift = (int)(cur.out0 & 1);
+                std::vector<CbWork> src(works.begin() + cur.w0, works.end());
+                const int ns = (int)src.size();
+                auto key_of = [&](const CbWork &w) {
+                    if (w.kind != 0 && w.kind != 2) return -1;
+                    const CbTPair &tp = tp2[cur.p0 + w.dst];
+                    if (tp.maskA != 0x3f || tp.maskB != 0x3f || ((shift + tp.rel) & 1) || (tp.colh & 1)) return -1;
+                    return ((shift + tp.rel) >> 1) & 7;
+                };
+                struct Unit { int first, size, key; };
+                std::vector<Unit> units;
+                for (int i2 = 0; i2 < ns;) {
+                    const int sz = src[i2].kind == 2 ? src[i2].pad0 : 1;
+                    units.push_back({i2, sz, key_of(src[i2])});
+                    i2 += sz;
+                }
+                std::vector<uint8_t> done(units.size(), 0);
+                std::vector<CbWork> out;
+                size_t head = 0;
+                uint8_t used[8] = {0};
+                CbWork idle{}; idle.kind = 4;
+                while (head < units.size()) {
+                    const int lane = (int)out.size();
+                    if ((lane & 7) == 0) std::fill(used, used + 8, 0);
+                    const int room = 32 - (lane & 31);
+                    int pick = -1, fit = -1;
+                    for (size_t u = head, seen = 0; u < units.size() && seen < 24; ++u) {
+                        if (done[u]) continue;
+                        ++seen;
+                        if (units[u].size > room) continue;
+                        if (fit < 0) fit = (int)u;
+                        if (units[u].key < 0 || !used[units[u].key]) { pick = (int)u; break; }
+                    }
+                    if (pick < 0) pick = fit;
+                    if (pick < 0) { out.push_back(idle); continue; }
+                    const Unit &un = units[pick];
+                    if (un.key >= 0) used[un.key] = 1;
+                    for (int k2 = 0; k2 < un.size; ++k2) {
+                        if (k2 && ((out.size() & 7) == 0)) std::fill(used, used + 8, 0);
+                        out.push_back(src[un.first + k2]);
+                    }
+                    done[pick] = 1;
+                    while (head < units.size() && done[head]) ++head;
+                }
+                if (out.size() > (size_t)CB_TILE_T) { plan2_ok = false; return; }
+                works.resize(cur.w0);
+                works.insert(works.end(), out.begin(), out.end());
+                cur.nw = (int32_t)out.size();
             }
             cur.ne = (int32_t)curel.size();
             telems.insert(telems.end(), curel.begin(), curel.end());
@@ -642,12 +685,12 @@ static int build_plan(cb_handle *h)
             size_t g1 = i;
             const int32_t B = pair_B[i];
             while (g1 < pairs_csc.size() && pair_B[g1] == B) ++g1;
-            int items_n = 0, slots_n = 0;
+            int items_n = 0, gmax_n = 1;
             std::vector<int32_t> newel;
             for (size_t q = i; q < g1; ++q) {
                 const CbPair &p = pairs_csc[q];
                 const int parts = (p.ccount + 1) / 2;
-                items_n += parts; if (p.ccount > 2) slots_n += parts;
+                items_n += parts; gmax_n = std::max(gmax_n, parts);
                 for (int c = 0; c < p.ccount; ++c) {
                     const int32_t e = contribs[p.cstart + c].e;
                     if (std::find(curel.begin(), curel.end(), e) == curel.end() &&
@@ -657,11 +700,12 @@ static int build_plan(cb_handle *h)
             }
             const long out_n = (long)h->h_nfree[B] * h->colh[B];
             const int pairs_n = (int)(g1 - i);
-            auto fits = [&](int nw, long nout, int slots, int np, size_t ne) {
-                return nw <= CB_TILE_T && nout <= CB_T2_OUT && slots <= CB_T2_SLOTS && np <= CB_TILE_T &&
-                       ne <= (size_t)CB_T2_ELEMS;
+            auto fits = [&](int nw, long nout, int gmax, int np, size_t ne) {
+                // slack: a warp tail too short for a group is padded with idle items
+                return gmax <= CB_T2_GROUP && nw + 3 * (gmax - 1) <= CB_TILE_T && nout <= CB_T2_OUT &&
+                       np <= CB_TILE_T && ne <= (size_t)CB_T2_ELEMS;
             };
-            if (open2 && (!fits(cur.nw + items_n, cur.nout + out_n, cur_slots + slots_n, cur.np + pairs_n,
+            if (open2 && (!fits(cur.nw + items_n, cur.nout + out_n, std::max(cur_gmax, gmax_n), cur.np + pairs_n,
                                 curel.size() + newel.size()) ||
                           h->base[B] - h->ax_base != cur.out0 + cur.nout)) {
                 close_tile();
@@ -673,8 +717,8 @@ static int build_plan(cb_handle *h)
                     }
             }
             if (!open2) {
-                curel.clear(); cur_slots = 0;
-                if (!fits(items_n, out_n, slots_n, pairs_n, newel.size())) { plan2_ok = false; break; }
+                curel.clear(); cur_gmax = 1;
+                if (!fits(items_n, out_n, gmax_n, pairs_n, newel.size())) { plan2_ok = false; break; }
                 cur = CbTile2{}; cur.out0 = h->base[B] - h->ax_base; cur.nout = 0;
                 cur.w0 = (int32_t)works.size(); cur.nw = 0; cur.p0 = (int32_t)tp2.size(); cur.np = 0;
                 cur.e0 = (int32_t)telems.size(); open2 = true;
@@ -686,7 +730,7 @@ static int build_plan(cb_handle *h)
                 tp.rel = (int32_t)(p.off - cur.out0); tp.colh = p.colh; tp.maskA = p.maskA; tp.maskB = p.maskB;
                 const int parts = (p.ccount + 1) / 2;
                 tp.cs = 0; tp.cnt = 0;
-                if (p.ccount > 2) { tp.cs = (uint16_t)cur_slots; tp.cnt = (uint16_t)parts; }
+                cur_gmax = std::max(cur_gmax, parts);
                 for (int k = 0; k < parts; ++k) {
                     CbWork w{}; w.c0 = p.cstart + 2 * k; w.n = (uint8_t)((2 * k + 1 < p.ccount) ? 2 : 1);
                     for (int u = 0; u < w.n; ++u) {
@@ -695,11 +739,11 @@ static int build_plan(cb_handle *h)
                         if (u == 0) { w.a0 = cu.a; w.b0 = cu.b; w.s0 = slot; }
                         else { w.a1 = cu.a; w.b1 = cu.b; w.s1 = slot; }
                     }
-                    if (p.ccount > 2) { w.kind = 1; w.dst = (uint16_t)(cur_slots + k); }
-                    else { w.kind = 0; w.dst = (uint16_t)cur.np; }
+                    w.dst = (uint16_t)cur.np;
+                    if (parts == 1) w.kind = 0;
+                    else { w.kind = (uint8_t)(k == 0 ? 2 : 3); w.pad0 = (uint8_t)parts; w.pad1 = (uint8_t)k; }
                     works.push_back(w);
                 }
-                if (p.ccount > 2) cur_slots += parts;
                 for (int c = 0; c < p.ccount; ++c) {
                     CbContrib &ct = contribs[p.cstart + c];
                     ct.pad = (uint8_t)(std::find(curel.begin(), curel.end(), ct.e) - curel.begin());
@@ -732,7 +776,7 @@ static int build_plan(cb_handle *h)
         if (h->plan_csc.tiles2.upload(tiles2) || h->plan_csc.works.upload(works) ||
             h->plan_csc.tpairs2.upload(tp2) || h->plan_csc.telems.upload(telems))
             return CB_ERR_CUDA;
-        h->plan_csc.ntiles2 = (long)tiles2.size();
+        h->plan_csc.ntiles2 = (long)tiles2.size(); h->plan_csc.nworks = (long)works.size();
         h->plan_csc.tile_smem_out = (max_tile_out + 3) & ~1;   // room for the parity shift, kept even
         if (h->Ax.alloc((size_t)nnz)) return CB_ERR_CUDA;
         cudaMemset(h->Ax.p, 0, (size_t)nnz * sizeof(double));
@@ -764,9 +808,16 @@ static int ensure_keb(cb_handle *h)
     if (cbk_shell_init_keb(d, h->sh_keb.p, h->stream)) return fail(CB_ERR_CUDA, "keb init launch");
     if (h->sz.NE_SH) ++h->launches;
     if (h->sz.NE_SH && h->plan_ready && (h->plan_csc.ntiles || h->plan_csc.ntiles2)) {
-        if (!h->sh_kebc.p && h->sh_kebc.alloc((size_t)h->ncontrib * 10)) return CB_ERR_CUDA;
-        if (cbk_shell_init_kebc(d, h->contribs.p, h->ncontrib, h->sh_kebc.p, h->stream))
-            return fail(CB_ERR_CUDA, "kebc init launch");
+        if (h->plan_csc.ntiles2) {
+            if (!h->sh_kebc.p && h->sh_kebc.alloc((size_t)h->plan_csc.nworks * 18)) return CB_ERR_CUDA;
+            if (cbk_shell_init_kebc2(d, h->plan_csc.tiles2.p, h->plan_csc.ntiles2, h->plan_csc.works.p,
+                                     h->contribs.p, h->sh_kebc.p, h->stream))
+                return fail(CB_ERR_CUDA, "kebc init launch");
+        } else {
+            if (!h->sh_kebc.p && h->sh_kebc.alloc((size_t)h->ncontrib * 10)) return CB_ERR_CUDA;
+            if (cbk_shell_init_kebc(d, h->contribs.p, h->ncontrib, h->sh_kebc.p, h->stream))
+                return fail(CB_ERR_CUDA, "kebc init launch");
+        }
         ++h->launches;
     }
     h->keb_dirty = false;
@@ -879,6 +930,35 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     h->stiff_timed = true;
     return CB_OK;
+}
+
+// two-stage fixed-order reduction of the three convergence sums (misc.c:187-250)
+__global__ void __launch_bounds__(256)
+k_resid_sums1(long e0, long e1, double lpf, const double *__restrict__ q, const double *__restrict__ f,
+              const double *__restrict__ dd, double *__restrict__ part)
+{
+    __shared__ double sh[3][256];
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (long i = e0 + blockIdx.x * 256L + threadIdx.x; i < e1; i += 256L * gridDim.x) {
+        const double r = lpf * q[i] - f[i], di = dd[i];
+        a0 += r * r; a1 += di * di; a2 += di * r;
+    }
+    sh[0][threadIdx.x] = a0; sh[1][threadIdx.x] = a1; sh[2][threadIdx.x] = a2;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+            for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) part[blockIdx.x * 3 + threadIdx.x] = sh[threadIdx.x][0];
+}
+__global__ void k_resid_sums2(int nblk, const double *__restrict__ part, double *__restrict__ out)
+{
+    if (threadIdx.x < 3) {
+        double s = 0;
+        for (int b = 0; b < nblk; ++b) s += part[b * 3 + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
 }
 
 __global__ void k_axpy1(long n, const double *__restrict__ x, double *__restrict__ y)
@@ -1092,6 +1172,47 @@ extern "C" int cb_get_f(cb_handle *h, double *f)
     cudaSetDevice(h->fl.device);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaMemcpy(f, h->f_temp.p, h->sz.NEQ * sizeof(double), cudaMemcpyDeviceToHost));
+    return CB_OK;
+}
+
+#define CB_SUM_BLOCKS 592
+extern "C" int cb_set_q(cb_handle *h, const double *q)
+{
+    if (!h || !q) return fail(CB_ERR_ARG, "null argument");
+    cudaSetDevice(h->fl.device);
+    if (!h->qvec.p && (h->qvec.alloc(h->sz.NEQ) || h->sums.alloc(4) || h->sums_part.alloc(CB_SUM_BLOCKS * 3)))
+        return CB_ERR_CUDA;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(h->qvec.p, q, h->sz.NEQ * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaDeviceSynchronize());
+    // equations of the owned joints are one contiguous range (joint-by-joint numbering)
+    h->eq0 = h->sz.NEQ; h->eq1 = 0;
+    for (long j = h->j0; j < h->j1; ++j)
+        if (h->h_nfree[j]) {
+            if (h->h_first[j] - 1 < h->eq0) h->eq0 = h->h_first[j] - 1;
+            if (h->h_first[j] - 1 + h->h_nfree[j] > h->eq1) h->eq1 = h->h_first[j] - 1 + h->h_nfree[j];
+        }
+    if (h->eq1 < h->eq0) h->eq0 = h->eq1 = 0;
+    return CB_OK;
+}
+extern "C" int cb_residual_sums(cb_handle *h, double lpf)
+{
+    if (!h || !h->qvec.p) return fail(CB_ERR_ARG, "cb_set_q has not been called");
+    cudaSetDevice(h->fl.device);
+    k_resid_sums1<<<CB_SUM_BLOCKS, 256, 0, h->stream>>>(h->eq0, h->eq1, lpf, h->qvec.p, h->f_temp.p,
+                                                         h->dd.p, h->sums_part.p);
+    k_resid_sums2<<<1, 32, 0, h->stream>>>(CB_SUM_BLOCKS, h->sums_part.p, h->sums.p);
+    h->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return CB_OK;
+}
+extern "C" double *cb_dev_sums(cb_handle *h) { return h ? h->sums.p : nullptr; }
+extern "C" int cb_get_sums(cb_handle *h, double *s3)
+{
+    if (!h || !s3 || !h->sums.p) return fail(CB_ERR_ARG, "null argument");
+    cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(s3, h->sums.p, 3 * sizeof(double), cudaMemcpyDeviceToHost));
     return CB_OK;
 }
 

@@ -211,6 +211,34 @@ int cbk_shell_init_kebc(const CbDev &d, const CbContrib *contribs, long ncontrib
     return cudaGetLastError() != cudaSuccess;
 }
 
+// duo plan: the same sub-blocks in work-major order, kebc[18 * w0 + (u * 9 + i) * nw + t] for work
+// item t of a tile (u = its contribution 0/1): one CTA per tile
+__global__ void __launch_bounds__(CB_TILE_T)
+k_shell_init_kebc2(CbDev d, const CbTile2 *__restrict__ tiles, const CbWork *__restrict__ works,
+                   const CbContrib *__restrict__ contribs, double *__restrict__ kebc)
+{
+    const CbTile2 tl = tiles[blockIdx.x];
+    const int t = threadIdx.x;
+    if (t >= tl.nw) return;
+    const CbWork w = works[tl.w0 + t];
+    double *o = kebc + 18L * tl.w0 + t;
+    for (int u = 0; u < 2; ++u) {
+        const int a = u ? w.a1 : w.a0, b = u ? w.b1 : w.b0;
+        const long e = (u < w.n) ? contribs[w.c0 + u].e : -1;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            o[(long)(u * 9 + i) * tl.nw] = (e >= 0) ? SOA(d.sh_keb, (3 * a + b) * 9 + i, e, d.NE_SH) : 0.0;
+    }
+}
+
+int cbk_shell_init_kebc2(const CbDev &d, const CbTile2 *tiles, long ntiles, const CbWork *works,
+                         const CbContrib *contribs, double *kebc, cudaStream_t s)
+{
+    if (ntiles == 0 || d.NE_SH == 0) return 0;
+    k_shell_init_kebc2<<<(unsigned)ntiles, CB_TILE_T, 0, s>>>(d, tiles, works, contribs, kebc);
+    return cudaGetLastError() != cudaSuccess;
+}
+
 // plane-stress constitutive coefficients (shell.c:497-501 / 672-676)
 __device__ __forceinline__ void plane_stress(double E, double nu, double &C00, double &C01,
                                              double &C22)

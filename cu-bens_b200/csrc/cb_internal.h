@@ -6,7 +6,8 @@
 //   per-element shell arrays touched by one thread per element are component-major (SoA):
 //   constants [12][NE], frame state [10][NE] and end forces [18][NE] per generation, deformed side
 //   lengths [3][NE], DKT bending matrix [81][NE]; the stiffness-pass record krec [NE][18] and the
-//   contribution-ordered DKT blocks kebc [ncontrib][10] are gathered per contribution and stay AoS.
+//   DKT blocks in assembly order (kebc): general tile kernel [ncontrib][10] AoS; duo plan
+//   work-major SoA, kebc[18*w0 + (u*9+i)*nw + t] for work item t of a tile (coalesced).
 //   NEQ vectors   dd, f_temp, d_temp, d, f, sm.
 //   tangent matrix: CSC values Ax[nnz] (node-block structural pattern) and/or the reference's
 //   skyline vector ss[lss].
@@ -80,24 +81,29 @@ struct CbTPair {
 // contributions of one joint-pair block and sums them in registers; blocks with more than two
 // contributions are split into partial sums that are combined through shared memory
 #define CB_T2_OUT 3072           // max doubles of Ax per tile staged in shared memory
-#define CB_T2_SLOTS 40           // max partial sums per tile
 #define CB_T2_ELEMS 56           // max distinct shells per tile (their krec records are staged)
+#define CB_T2_GROUP 16           // max partial sums of one block (a group of lanes of one warp)
 struct CbTile2 {
     int64_t out0;     // first Ax index of the tile's contiguous output range
     int32_t nout;
     int32_t w0, nw;   // work items (<= CB_TILE_T)
-    int32_t p0, np;   // pair records; the first nm need the partial-sum reduction
-    int32_t nm;
+    int32_t p0, np;   // pair records
+    int32_t nm;       // (unused)
     int32_t e0, ne;   // distinct shells of the tile
 };
 struct CbWork {       // 16 bytes, self-contained: no dependent load of the contribution records
-    int32_t c0;       // first contribution (the second, if any, is c0 + 1): index into kebc
+    int32_t c0;       // first contribution (the second, if any, is c0 + 1)
     uint8_t n;        // 1 or 2 contributions
-    uint8_t kind;     // 0: complete block -> written straight into the output image; 1: partial sum
-    uint16_t dst;     // kind 0: pair record index inside the tile; kind 1: partial-sum slot
+    uint8_t kind;     // 0: complete block; 2: leader of a group of pad0 partial sums of one block (its
+                      // followers, kind 3 with pad1 = 1, 2, ... sit in the next lanes of the same
+                      // warp and add to the image in that order); 4: idle lane
+    uint16_t dst;     // pair record index inside the tile
     uint8_t a0, b0, s0, pad0;   // local row / column joint and tile-local shell slot, contribution 0
     uint8_t a1, b1, s1, pad1;   // ... contribution 1
 };
+
+static_assert(sizeof(CbWork) == 16 && sizeof(CbTPair) == 16, "records are copied as 16-byte units");
+static_assert(sizeof(CbTile2) == 40, "tile records are prefetched as five 8-byte words");
 
 #define CB_SH_DER 24
 #define CB_SH_KREC 18   // per-shell record for the stiffness pass: R[9], X2,X3,Y3, cm00,cm01,cm22, n0,n1,n2
@@ -167,7 +173,7 @@ struct CbStiffArgs {
     const CbPair *pairs; long npairs;
     const CbContrib *contribs;
     const CbTile *tiles; long ntiles; const CbTPair *tpairs;
-    const double *kebc;      // [ncontrib][10] DKT 3x3 sub-block of each shell contribution (static)
+    const double *kebc;      // DKT 3x3 sub-blocks in assembly order (static; layouts above)
     const CbTile2 *tiles2; long ntiles2; const CbWork *works; const CbTPair *tpairs2;
     const int32_t *tile_elems;
     int tile_smem_out;       // doubles of output staging per tile
@@ -202,6 +208,8 @@ extern "C++" {
 #endif
 // cb_forces.cu  (compiled with -fmad=false: reference operation order, IEEE mul/add)
 int cbk_shell_init_keb(const CbDev &d, double *keb_out, cudaStream_t s);
+int cbk_shell_init_kebc2(const CbDev &d, const CbTile2 *tiles, long ntiles, const CbWork *works,
+                         const CbContrib *contribs, double *kebc, cudaStream_t s);
 int cbk_shell_init_kebc(const CbDev &d, const CbContrib *contribs, long ncontrib, double *kebc,
                         cudaStream_t s);
 int cbk_shell_prep(const CbDev &d, const double *x, const double *sh_frame, cudaStream_t s);

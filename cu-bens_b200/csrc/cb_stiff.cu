@@ -428,203 +428,265 @@ k_assemble_tiles(CbStiffArgs A)
 }
 
 // ------------------------------------------------------------------------------------------
-// CSC, shell-only models: "duo" tile kernel.  One persistent CTA per run of consecutive joints.
-//   * the krec records of the tile's distinct shells are brought into shared memory once, by
-//     cp.async, double-buffered: the next tile's records land while this tile is processed;
-//   * phase 1: a thread evaluates up to two consecutive contributions of one joint-pair block and
-//     adds them in registers; a complete block goes straight into the tile's output image, a
-//     partial sum of a larger block (diagonal blocks: one contribution per adjacent shell) into
-//     the small partial-sum stage;
-//   * phase 2: the partial sums of those blocks are added in list order;
-//   * phase 3: the image is streamed to HBM with aligned 16-byte stores.
-// shared memory: obuf[CB_T2_OUT+2] | stage[36][CB_T2_SLOTS+1] | skrec[2][CB_T2_ELEMS][18] |
-//                spair[CB_TILE_T]
+// CSC, shell-only models: "duo" tile kernel.  One persistent CTA walks tiles (runs of consecutive
+// joints whose CSC columns are one contiguous slice of Ax), software-pipelined:
+//   * the krec records of the tile's distinct shells and its pair records are brought into shared
+//     memory by cp.async, double-buffered (the next tile's land while this tile is processed);
+//     the work item and the DKT sub-blocks of the next tile are prefetched into registers;
+//   * a thread evaluates up to two consecutive contributions of one joint-pair block, three
+//     columns at a time, adds them in registers and writes the result into the tile's output
+//     image in shared memory with 16-byte stores (lanes arranged by the planner so that the
+//     stores of a quarter-warp hit distinct bank groups);
+//   * a block with more than two contributions (diagonal blocks: one per adjacent shell) is a
+//     group of consecutive lanes of one warp: the leader stores, the followers add their partial
+//     sums to the image one after the other (list order, __syncwarp between the rounds);
+//   * the finished image leaves as ONE bulk asynchronous copy shared -> global (TMA engine,
+//     cp.async.bulk): no thread touches the output on its way to HBM.
+// shared memory: obuf[CB_T2_OUT+2] | skrec[2][CB_T2_ELEMS][18] | spair[2][CB_TILE_T]
 // ------------------------------------------------------------------------------------------
-#define CB_T2_SSTR (CB_T2_SLOTS + 1)
 
-// K_ab (6x6) of one shell contribution, accumulated into blk[36] (row-major)
-__device__ __forceinline__ void shell_block_acc(const double *kr, const double *kb, int a, int b,
-                                                double *blk, bool first)
+#define CB_T2_CTAS 3              // resident CTAs per SM the kernel is compiled for
+
+// Columns 0..2 (LEFT) or 3..5 of K_ab (6x6, global axes) of one shell contribution:
+// top[9] = rows 0..2 (translations), bot[9] = rows 3..5 (rotations), row-major 3x3; kb = the 3x3
+// DKT sub-block for (a,b).  first: overwrite, else accumulate (second contribution of the block).
+template <bool LEFT>
+__device__ __forceinline__ void shell_half_acc(const double *kr, const double *kb, int a, int b,
+                                               double *top, double *bot, bool first)
 {
     const double *R = kr;
-    double bxa, bya, bxb, byb;
-    cst_grad(a, kr[9], kr[10], kr[11], bxa, bya);
-    cst_grad(b, kr[9], kr[10], kr[11], bxb, byb);
-    const double m00 = kr[12] * bxa * bxb + kr[14] * bya * byb;
-    const double m01 = kr[13] * bxa * byb + kr[14] * bya * bxb;
-    const double m10 = kr[13] * bya * bxb + kr[14] * bxa * byb;
-    const double m11 = kr[12] * bya * byb + kr[14] * bxa * bxb;
-    const double g = bxa * (kr[15] * bxb + kr[17] * byb) + bya * (kr[17] * bxb + kr[16] * byb);
-    const double drill = (a == b) ? kb[4] / 10000 : 0.0;
     double s[9];
-#define CB_PUT(r0, c0)                                                                            \
-    _Pragma("unroll") for (int p = 0; p < 3; ++p) _Pragma("unroll") for (int q = 0; q < 3; ++q) {  \
-        if (first) blk[((r0) + p) * 6 + (c0) + q] = s[p * 3 + q];                                   \
-        else blk[((r0) + p) * 6 + (c0) + q] += s[p * 3 + q];                                        \
+#define CB_PUT(dst)                                                                               \
+    _Pragma("unroll") for (int i = 0; i < 9; ++i) { if (first) dst[i] = s[i]; else dst[i] += s[i]; }
+    if (LEFT) {
+        double bxa, bya, bxb, byb;
+        cst_grad(a, kr[9], kr[10], kr[11], bxa, bya);
+        cst_grad(b, kr[9], kr[10], kr[11], bxb, byb);
+        const double m00 = kr[12] * bxa * bxb + kr[14] * bya * byb;
+        const double m01 = kr[13] * bxa * byb + kr[14] * bya * bxb;
+        const double m10 = kr[13] * bya * bxb + kr[14] * bxa * byb;
+        const double m11 = kr[12] * bya * byb + kr[14] * bxa * bxb;
+        const double g = bxa * (kr[15] * bxb + kr[17] * byb) + bya * (kr[17] * bxb + kr[16] * byb);
+        rtsr_diag(R, m00 + g, m01, m10, m11 + g, kb[0] + g, s, 3);
+        CB_PUT(top)
+        rtsr_col(R, kb[3], kb[6], s, 3);
+        CB_PUT(bot)
+    } else {
+        const double drill = (a == b) ? kb[4] / 10000 : 0.0;
+        rtsr_row(R, kb[1], kb[2], s, 3);
+        CB_PUT(top)
+        rtsr_diag(R, kb[4], kb[5], kb[7], kb[8], drill, s, 3);
+        CB_PUT(bot)
     }
-    rtsr_diag(R, m00 + g, m01, m10, m11 + g, kb[0] + g, s, 3);
-    CB_PUT(0, 0)
-    rtsr_row(R, kb[1], kb[2], s, 3);
-    CB_PUT(0, 3)
-    rtsr_col(R, kb[3], kb[6], s, 3);
-    CB_PUT(3, 0)
-    rtsr_diag(R, kb[4], kb[5], kb[7], kb[8], drill, s, 3);
-    CB_PUT(3, 3)
 #undef CB_PUT
 }
 
-__device__ __forceinline__ void t2_issue_krec(const CbStiffArgs &A, const CbTile2 &tl, double *dstbuf)
+// shell records of a tile (9 chunks of 16 bytes each) + its pair records -> shared memory, async.
+// eid[k] = element of copy item t + k * CB_TILE_T, loaded by t2_load_eids well before
+#define CB_T2_EIDS ((CB_T2_ELEMS * 9 + CB_TILE_T - 1) / CB_TILE_T)
+__device__ __forceinline__ void t2_load_eids(const CbStiffArgs &A, const CbTile2 &tl, int *eid)
 {
-    // 9 chunks of 16 bytes per shell record
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(dstbuf);
-    for (int i = threadIdx.x; i < tl.ne * 9; i += CB_TILE_T) {
-        const int es = i / 9, ch = i - es * 9;
-        const long e = A.tile_elems[tl.e0 + es];
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (es * CB_SH_KREC * 8 + ch * 16)),
-                     "l"(A.d.sh_Nm + e * CB_SH_KREC + ch * 2));
+#pragma unroll
+    for (int k = 0; k < CB_T2_EIDS; ++k) {
+        const int i = threadIdx.x + k * CB_TILE_T;
+        eid[k] = (i < tl.ne * 9) ? __ldg(A.tile_elems + tl.e0 + i / 9) : 0;
     }
+}
+__device__ __forceinline__ void t2_issue_stage(const CbStiffArgs &A, const CbTile2 &tl, const int *eid,
+                                               double *krec_dst, CbTPair *pair_dst)
+{
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(krec_dst);
+#pragma unroll
+    for (int k = 0; k < CB_T2_EIDS; ++k) {
+        const int i = threadIdx.x + k * CB_TILE_T;
+        if (i < tl.ne * 9) {
+            const int es = i / 9, ch = i - es * 9;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (es * CB_SH_KREC * 8 + ch * 16)),
+                         "l"(A.d.sh_Nm + (long)eid[k] * CB_SH_KREC + ch * 2));
+        }
+    }
+    if (threadIdx.x < tl.np)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                         (unsigned)__cvta_generic_to_shared(pair_dst + threadIdx.x)),
+                     "l"(A.tpairs2 + tl.p0 + threadIdx.x));
     asm volatile("cp.async.commit_group;");
 }
 
-__device__ __forceinline__ void t2_load_kb(const CbStiffArgs &A, long c, double *kb)
+// DKT sub-blocks of the two contributions of work item t of a tile: work-major SoA
+// kebc[18 * w0 + (u * 9 + i) * nw + t] (u = contribution 0/1, i = 3x3 entry) - every load of a warp
+// is one contiguous 256-byte run, and the address needs nothing but the tile record
+__device__ __forceinline__ void t2_load_kb(const CbStiffArgs &A, const CbTile2 &tl, int t, double *kb)
 {
-    const double2 *kb2 = reinterpret_cast<const double2 *>(A.kebc + c * 10);
+    const double *src = A.kebc + 18L * tl.w0 + t;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) { double2 v = __ldg(kb2 + i); kb[2 * i] = v.x; kb[2 * i + 1] = v.y; }
+    for (int i = 0; i < 18; ++i) kb[i] = __ldg(src + (long)i * tl.nw);
 }
 
-__global__ void __launch_bounds__(CB_TILE_T, 4)
+// columns c0..c0+2 of a block into the tile image (ACC: added to what is there); top/bot as in
+// shell_half_acc
+template <bool ACC>
+__device__ __forceinline__ void t2_store_half(double *obuf, int shift, const CbTPair &pr, int c0,
+                                              const double *top, const double *bot)
+{
+    double *img = obuf + shift + pr.rel;
+    if (pr.maskA == 0x3f && pr.maskB == 0x3f) {
+        if ((((shift + pr.rel) | pr.colh) & 1) == 0) {          // 16-byte aligned columns
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                double2 *col = reinterpret_cast<double2 *>(img + (c0 + q) * pr.colh);
+                double2 v0 = make_double2(top[q], top[3 + q]);
+                double2 v1 = make_double2(top[6 + q], bot[q]);
+                double2 v2 = make_double2(bot[3 + q], bot[6 + q]);
+                if (ACC) {
+                    // one column at a time (keeps the live range of the old values short)
+                    asm volatile("" ::: "memory");
+                    const double2 o0 = col[0], o1 = col[1], o2 = col[2];
+                    v0.x = o0.x + v0.x; v0.y = o0.y + v0.y; v1.x = o1.x + v1.x; v1.y = o1.y + v1.y;
+                    v2.x = o2.x + v2.x; v2.y = o2.y + v2.y;
+                }
+                col[0] = v0; col[1] = v1; col[2] = v2;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                double *col = img + (c0 + q) * pr.colh;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    if (ACC) { col[r] += top[r * 3 + q]; col[3 + r] += bot[r * 3 + q]; }
+                    else { col[r] = top[r * 3 + q]; col[3 + r] = bot[r * 3 + q]; }
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int c = c0 + q;
+            if (!((pr.maskB >> c) & 1)) continue;
+            double *col = img + __popc(pr.maskB & ((1u << c) - 1)) * pr.colh;
+            int rr = 0;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                if ((pr.maskA >> r) & 1) { if (ACC) col[rr++] += top[r * 3 + q]; else col[rr++] = top[r * 3 + q]; }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                if ((pr.maskA >> (3 + r)) & 1) { if (ACC) col[rr++] += bot[r * 3 + q]; else col[rr++] = bot[r * 3 + q]; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CB_TILE_T, CB_T2_CTAS)
 k_assemble_shell_tiles(CbStiffArgs A)
 {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     double *obuf = smem;                                              // [CB_T2_OUT + 2]
-    double *stage = obuf + CB_T2_OUT + 2;                             // [36][CB_T2_SSTR]
-    double *skrec = stage + 36 * CB_T2_SSTR + (36 * CB_T2_SSTR & 1);   // [2][CB_T2_ELEMS*18], 16 B aligned
-    CbTPair *spair = reinterpret_cast<CbTPair *>(skrec + 2 * CB_T2_ELEMS * CB_SH_KREC);
-    const int t = threadIdx.x;
+    double *skrec = obuf + CB_T2_OUT + 2;                             // [2][CB_T2_ELEMS*18], 16 B aligned
+    CbTPair *spair2 = reinterpret_cast<CbTPair *>(skrec + 2 * CB_T2_ELEMS * CB_SH_KREC);   // [2][CB_TILE_T]
+    const int t = threadIdx.x, lane = t & 31;
     long tile = blockIdx.x;
     if (tile >= A.ntiles2) return;
-    CbTile2 tl = A.tiles2[tile];
+    // software pipeline over the CTA's tiles: tile records two ahead, element ids / shell records /
+    // pair records / work item / DKT blocks one ahead
+    CbTile2 tl = A.tiles2[tile], tln = tl;
+    if (tile + gridDim.x < A.ntiles2) tln = A.tiles2[tile + gridDim.x];
     int buf = 0;
-    t2_issue_krec(A, tl, skrec);
-    CbWork w{};
-    if (t < tl.nw) w = A.works[tl.w0 + t];
+    int eid[CB_T2_EIDS];
+    t2_load_eids(A, tl, eid);
+    t2_issue_stage(A, tl, eid, skrec, spair2);
+    int4 wraw = make_int4(0, 0, 0, 0);
+    double kb[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) kb[i] = 0.0;
+    if (t < tl.nw) {
+        wraw = __ldg(reinterpret_cast<const int4 *>(A.works + tl.w0 + t));
+        t2_load_kb(A, tl, t, kb);
+    }
 
     for (;;) {
-        const long next = tile + gridDim.x;
+        const long next = tile + gridDim.x, next2 = next + gridDim.x;
         const bool has_next = next < A.ntiles2;
-        CbTile2 tln = tl;
-        if (has_next) tln = A.tiles2[next];
-        if (t < tl.np) spair[t] = A.tpairs2[tl.p0 + t];
+        // tile record two ahead: lane i of every warp fetches word i; the words are broadcast at the
+        // end of this iteration, so that the wait for the load sits there and not here
+        int tword = 0;
+        if (next2 < A.ntiles2 && lane < 10) tword = __ldg(reinterpret_cast<const int *>(A.tiles2 + next2) + lane);
+        if (has_next) t2_load_eids(A, tln, eid);
+        // the previous tile's image must have been read out by the copy engine
+        if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                                   // krec of this tile + spair visible
-        if (has_next) t2_issue_krec(A, tln, skrec + (buf ^ 1) * CB_T2_ELEMS * CB_SH_KREC);
+        __syncthreads();                   // shell + pair records of this tile visible; obuf free
+        // the work item is unpacked only now: its load was issued a whole tile ago
+        asm volatile("" : "+r"(wraw.x), "+r"(wraw.y), "+r"(wraw.z), "+r"(wraw.w));
+        CbWork w;
+        *reinterpret_cast<int4 *>(&w) = wraw;
         const int shift = (int)(tl.out0 & 1);
+        const CbTPair *spair = spair2 + buf * CB_TILE_T;
 
-        // ---- phase 1 ---------------------------------------------------------------------------
+        // ---- phase 1: the block (or partial sum) of this thread, three columns at a time --------
+        const unsigned amask = __ballot_sync(0xffffffffu, t < tl.nw);
         if (t < tl.nw) {
             const double *kr0 = skrec + buf * CB_T2_ELEMS * CB_SH_KREC;
-            double blk[36];
-            {
-                double kb[10];
-                t2_load_kb(A, w.c0, kb);
-                shell_block_acc(kr0 + w.s0 * CB_SH_KREC, kb, w.a0, w.b0, blk, true);
+            CbTPair pr{};
+            if (w.kind != 4) pr = spair[w.dst];
+            // largest group of this warp (0: none)
+            const int gmax = __reduce_max_sync(amask, w.kind == 2 ? (int)w.pad0 : 0);
+            double top[9], bot[9];
+#define CB_T2_HALF(LEFT, C0)                                                                       \
+            if (w.n >= 1) {                                                                        \
+                shell_half_acc<LEFT>(kr0 + w.s0 * CB_SH_KREC, kb, w.a0, w.b0, top, bot, true);     \
+                if (w.n == 2)                                                                      \
+                    shell_half_acc<LEFT>(kr0 + w.s1 * CB_SH_KREC, kb + 9, w.a1, w.b1, top, bot, false); \
+                if (w.kind != 3) t2_store_half<false>(obuf, shift, pr, C0, top, bot);              \
+            }                                                                                      \
+            for (int q = 1; q < gmax; ++q) {        /* warp-uniform */                             \
+                __syncwarp(amask);                                                                 \
+                if (w.kind == 3 && w.pad1 == q) t2_store_half<true>(obuf, shift, pr, C0, top, bot); \
             }
-            if (w.n == 2) {
-                double kb[10];
-                t2_load_kb(A, w.c0 + 1, kb);
-                shell_block_acc(kr0 + w.s1 * CB_SH_KREC, kb, w.a1, w.b1, blk, false);
-            }
-            if (w.kind == 0) {
-                const CbTPair pr = spair[w.dst];
-                double *img = obuf + shift + pr.rel;
-                if (pr.maskA == 0x3f && pr.maskB == 0x3f) {
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) {
-                        double *col = img + c * pr.colh;
-#pragma unroll
-                        for (int r = 0; r < 6; ++r) col[r] = blk[r * 6 + c];
-                    }
-                } else {
-                    int cc = 0;
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) {
-                        if (!((pr.maskB >> c) & 1)) continue;
-                        double *col = img + cc * pr.colh;
-                        int rr = 0;
-#pragma unroll
-                        for (int r = 0; r < 6; ++r)
-                            if ((pr.maskA >> r) & 1) col[rr++] = blk[r * 6 + c];
-                        ++cc;
-                    }
-                }
-            } else {
-                double *stg = stage + w.dst;
-#pragma unroll
-                for (int i = 0; i < 36; ++i) stg[i * CB_T2_SSTR] = blk[i];
+            CB_T2_HALF(true, 0)
+            CB_T2_HALF(false, 3)
+#undef CB_T2_HALF
+        }
+        // next tile: records by cp.async into the other buffers, work item and DKT blocks into
+        // registers - all in flight while the image leaves
+        if (has_next) {
+            t2_issue_stage(A, tln, eid, skrec + (buf ^ 1) * CB_T2_ELEMS * CB_SH_KREC,
+                           spair2 + (buf ^ 1) * CB_TILE_T);
+            if (t < tln.nw) {
+                wraw = __ldg(reinterpret_cast<const int4 *>(A.works + tln.w0 + t));
+                t2_load_kb(A, tln, t, kb);
             }
         }
-        // next tile's work item: requested now, used after the reduction below
-        CbWork wn{};
-        if (has_next && t < tln.nw) wn = A.works[tln.w0 + t];
+        // writes of the image (generic proxy) ordered before the copy engine's reads (async proxy)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
 
-        // ---- phase 2: blocks with more than two contributions: add their partial sums ----------
-        for (int it = t; it < tl.nm * 6; it += CB_TILE_T) {
-            const int p = it / 6, c = it - p * 6;
-            const CbTPair pr = spair[p];
-            if (!((pr.maskB >> c) & 1)) continue;
-            const int cc = __popc(pr.maskB & ((1u << c) - 1));
-            double *dst = obuf + shift + pr.rel + cc * pr.colh;
-            const double *src = stage + c * CB_T2_SSTR + pr.cs;
-            double acc[6];
-#pragma unroll
-            for (int r = 0; r < 6; ++r) acc[r] = src[r * 6 * CB_T2_SSTR];
-            for (int q = 1; q < pr.cnt; ++q) {
-#pragma unroll
-                for (int r = 0; r < 6; ++r) acc[r] += src[r * 6 * CB_T2_SSTR + q];
-            }
-            if (pr.maskA == 0x3f) {
-#pragma unroll
-                for (int r = 0; r < 6; ++r) dst[r] = acc[r];
-            } else {
-                int rr = 0;
-#pragma unroll
-                for (int r = 0; r < 6; ++r)
-                    if ((pr.maskA >> r) & 1) dst[rr++] = acc[r];
-            }
-        }
-        __syncthreads();
-
-        // the next tile's DKT blocks: pulled into L2 now so the loads of the next phase 1 are short
-        if (has_next && t < tln.nw) {
-            const double *pk = A.kebc + (long)wn.c0 * 10;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pk));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pk + 16));
-        }
-
-        // ---- phase 3: stream the tile's output image to HBM -------------------------------------
-        {
+        // ---- phase 2: the image leaves as one bulk copy (16-byte aligned middle part) -----------
+        if (t == 0) {
             double *dst = A.out + tl.out0;
             const double *img = obuf + shift;
-            if (shift && t == 0) dst[0] = img[0];
             const int nv = (tl.nout - shift) >> 1;
-            const double2 *img2 = reinterpret_cast<const double2 *>(img + shift);
-            double2 *dst2 = reinterpret_cast<double2 *>(dst + shift);
-            for (int i = t; i < nv; i += CB_TILE_T) dst2[i] = img2[i];
+            if (nv > 0)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + shift),
+                             "r"((unsigned)__cvta_generic_to_shared(img + shift)), "r"(nv * 16)
+                             : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (shift) dst[0] = img[0];
             const int tail = shift + 2 * nv;
-            if (tail < tl.nout && t == CB_TILE_T - 1) dst[tail] = img[tail];
+            if (tail < tl.nout) dst[tail] = img[tail];
         }
         if (!has_next) break;
-        tile = next; tl = tln; w = wn; buf ^= 1;
-        __syncthreads();
+        tile = next; tl = tln; buf ^= 1;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const int v = __shfl_sync(0xffffffffu, tword, i);
+            if (next2 < A.ntiles2) reinterpret_cast<int *>(&tln)[i] = v;
+        }
     }
+    if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 static int launch_shell_tiles(const CbStiffArgs &a, cudaStream_t s)
 {
-    const size_t smem = (size_t)(CB_T2_OUT + 2 + 36 * CB_T2_SSTR + 1 + 2 * CB_T2_ELEMS * CB_SH_KREC) * sizeof(double) +
-                        CB_TILE_T * sizeof(CbTPair);
+    const size_t smem = (size_t)(CB_T2_OUT + 2 + 2 * CB_T2_ELEMS * CB_SH_KREC) * sizeof(double) +
+                        2 * CB_TILE_T * sizeof(CbTPair);
     static int grid_cache = 0;
     if (!grid_cache) {
         if (cudaFuncSetAttribute(k_assemble_shell_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize,

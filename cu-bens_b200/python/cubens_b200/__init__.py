@@ -33,7 +33,8 @@ EXPORTS = [
     "cb_get_mass", "cb_get_f", "cb_dev_Ax", "cb_dev_skyline", "cb_dev_f", "cb_dev_dd",
     "cb_dev_Ap", "cb_dev_Ai", "cb_download", "cb_upload", "cb_launch_count",
     "cb_last_stiff_ms", "cb_last_forces_ms", "cb_last_assemble_ms", "cb_timer_start", "cb_timer_stop_ms", "cb_set_dd", "cb_host_alloc",
-    "cb_host_free", "cb_map_bytes", "cb_sync", "cb_stream",
+    "cb_host_free", "cb_map_bytes", "cb_sync", "cb_stream", "cb_set_q", "cb_residual_sums",
+    "cb_dev_sums", "cb_get_sums",
 ]
 
 
@@ -85,7 +86,7 @@ def load_library(path=None):
     lib.cb_host_free.restype = None
     lib.cb_host_free.argtypes = [C.c_void_p]
     for n in ("cb_dev_Ax", "cb_dev_skyline", "cb_dev_f", "cb_dev_dd", "cb_dev_Ap", "cb_dev_Ai",
-              "cb_stream"):
+              "cb_stream", "cb_dev_sums"):
         getattr(lib, n).restype = C.c_void_p
     lib.cb_destroy.restype = None
     _lib = lib
@@ -261,6 +262,17 @@ class Assembler:
 
     def sync(self):
         self._check(self.lib.cb_sync(self.h))
+
+    def set_q(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        self._check(self.lib.cb_set_q(self.h, _p(q)))
+
+    def residual_sums(self, lpf=1.0, fetch=False):
+        self._check(self.lib.cb_residual_sums(self.h, C.c_double(lpf)))
+        if fetch:
+            s = np.zeros(3)
+            self._check(self.lib.cb_get_sums(self.h, _p(s)))
+            return s
 
     def set_dd(self, dd):
         dd = np.ascontiguousarray(dd, dtype=np.float64)

@@ -156,6 +156,17 @@ double *cb_dev_dd(cb_handle *h);
 const int *cb_dev_Ap(cb_handle *h);
 const int *cb_dev_Ai(cb_handle *h);       /* built lazily on first use                     */
 
+/* ---- convergence sums on the device ("next" row 2: the NEQ-vector work between the kernels) --
+ * cb_set_q stages the reference load vector q [NEQ]; cb_residual_sums leaves, in the device
+ * buffer cb_dev_sums() (3 doubles), the sums test() needs (misc.c:201, 217-220, 235-237) over
+ * the equations of the owned joints:  |lpf*q - f_temp|^2,  |dd|^2,  dd.(lpf*q - f_temp).
+ * Fixed-order two-stage reduction (bit-reproducible).  With several GPUs the launcher all-reduces
+ * the 3 doubles (NCCL) - the only per-iteration collective.                */
+int     cb_set_q(cb_handle *h, const double *q);
+int     cb_residual_sums(cb_handle *h, double lpf);
+double *cb_dev_sums(cb_handle *h);
+int     cb_get_sums(cb_handle *h, double *sums3);
+
 /* ---- state transfer for output()/checkPoint()/restartStep() (misc.c:345,494,605) ------ */
 enum {
     CB_ARR_X = 1, CB_ARR_X_TEMP, CB_ARR_X_IP,

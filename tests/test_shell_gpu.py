@@ -80,3 +80,20 @@ def test_repeatable(gpu):
         out.append((asm.csc()[2].copy(), f))
         asm.close()
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+def test_residual_sums(gpu):
+    """fused convergence sums (misc.c:187-250) on the device vs numpy"""
+    m = meshgen.plate_model(20, 15, z_bump=0.02)
+    asm = cb.Assembler(m, layout=cb.CB_MAT_CSC)
+    asm.begin_increment()
+    dd = meshgen.perturbation(m)
+    f, *_ = asm.update_forces(dd)
+    asm.set_q(m.q)
+    s = asm.residual_sums(0.7, fetch=True)
+    r = 0.7 * m.q - f
+    want = np.array([r @ r, dd @ dd, dd @ r])
+    assert np.allclose(s, want, rtol=1e-12, atol=0)
+    s2 = asm.residual_sums(0.7, fetch=True)
+    assert np.array_equal(s, s2)
+    asm.close()

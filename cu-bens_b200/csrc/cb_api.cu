@@ -809,7 +809,7 @@ static int ensure_keb(cb_handle *h)
     if (h->sz.NE_SH) ++h->launches;
     if (h->sz.NE_SH && h->plan_ready && (h->plan_csc.ntiles || h->plan_csc.ntiles2)) {
         if (h->plan_csc.ntiles2) {
-            if (!h->sh_kebc.p && h->sh_kebc.alloc((size_t)h->plan_csc.nworks * 18)) return CB_ERR_CUDA;
+            if (!h->sh_kebc.p && h->sh_kebc.alloc((size_t)h->plan_csc.ntiles2 * 18 * CB_TILE_T)) return CB_ERR_CUDA;
             if (cbk_shell_init_kebc2(d, h->plan_csc.tiles2.p, h->plan_csc.ntiles2, h->plan_csc.works.p,
                                      h->contribs.p, h->sh_kebc.p, h->stream))
                 return fail(CB_ERR_CUDA, "kebc init launch");

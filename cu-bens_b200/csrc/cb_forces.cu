@@ -211,8 +211,8 @@ int cbk_shell_init_kebc(const CbDev &d, const CbContrib *contribs, long ncontrib
     return cudaGetLastError() != cudaSuccess;
 }
 
-// duo plan: the same sub-blocks in work-major order, kebc[18 * w0 + (u * 9 + i) * nw + t] for work
-// item t of a tile (u = its contribution 0/1): one CTA per tile
+// duo plan: the same sub-blocks in work-major order, kebc[(T * 18 + u * 9 + i) * CB_TILE_T + t] for
+// work item t of tile T (u = its contribution 0/1): one CTA per tile
 __global__ void __launch_bounds__(CB_TILE_T)
 k_shell_init_kebc2(CbDev d, const CbTile2 *__restrict__ tiles, const CbWork *__restrict__ works,
                    const CbContrib *__restrict__ contribs, double *__restrict__ kebc)
@@ -221,13 +221,13 @@ k_shell_init_kebc2(CbDev d, const CbTile2 *__restrict__ tiles, const CbWork *__r
     const int t = threadIdx.x;
     if (t >= tl.nw) return;
     const CbWork w = works[tl.w0 + t];
-    double *o = kebc + 18L * tl.w0 + t;
+    double *o = kebc + blockIdx.x * (18L * CB_TILE_T) + t;
     for (int u = 0; u < 2; ++u) {
         const int a = u ? w.a1 : w.a0, b = u ? w.b1 : w.b0;
         const long e = (u < w.n) ? contribs[w.c0 + u].e : -1;
 #pragma unroll
         for (int i = 0; i < 9; ++i)
-            o[(long)(u * 9 + i) * tl.nw] = (e >= 0) ? SOA(d.sh_keb, (3 * a + b) * 9 + i, e, d.NE_SH) : 0.0;
+            o[(u * 9 + i) * CB_TILE_T] = (e >= 0) ? SOA(d.sh_keb, (3 * a + b) * 9 + i, e, d.NE_SH) : 0.0;
     }
 }
 

@@ -7,7 +7,7 @@
 //   constants [12][NE], frame state [10][NE] and end forces [18][NE] per generation, deformed side
 //   lengths [3][NE], DKT bending matrix [81][NE]; the stiffness-pass record krec [NE][18] and the
 //   DKT blocks in assembly order (kebc): general tile kernel [ncontrib][10] AoS; duo plan
-//   work-major SoA, kebc[18*w0 + (u*9+i)*nw + t] for work item t of a tile (coalesced).
+//   work-major SoA, kebc[(T*18 + u*9+i)*128 + t] for work item t of tile T (coalesced).
 //   NEQ vectors   dd, f_temp, d_temp, d, f, sm.
 //   tangent matrix: CSC values Ax[nnz] (node-block structural pattern) and/or the reference's
 //   skyline vector ss[lss].

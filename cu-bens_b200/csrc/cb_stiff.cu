@@ -442,7 +442,8 @@ k_assemble_tiles(CbStiffArgs A)
 //     sums to the image one after the other (list order, __syncwarp between the rounds);
 //   * the finished image leaves as ONE bulk asynchronous copy shared -> global (TMA engine,
 //     cp.async.bulk): no thread touches the output on its way to HBM.
-// shared memory: obuf[CB_T2_OUT+2] | skrec[2][CB_T2_ELEMS][18] | spair[2][CB_TILE_T]
+// shared memory: image | shell records x2 | DKT entries | pair records x2 | work items | element
+// ids | ring of tile records
 // ------------------------------------------------------------------------------------------
 
 #define CB_T2_CTAS 3              // resident CTAs per SM the kernel is compiled for
@@ -481,45 +482,46 @@ __device__ __forceinline__ void shell_half_acc(const double *kr, const double *k
 #undef CB_PUT
 }
 
-// shell records of a tile (9 chunks of 16 bytes each) + its pair records -> shared memory, async.
-// eid[k] = element of copy item t + k * CB_TILE_T, loaded by t2_load_eids well before
+// ---- asynchronous staging (cp.async: no register scoreboard is held while a copy is in flight) ----
 #define CB_T2_EIDS ((CB_T2_ELEMS * 9 + CB_TILE_T - 1) / CB_TILE_T)
-__device__ __forceinline__ void t2_load_eids(const CbStiffArgs &A, const CbTile2 &tl, int *eid)
+__device__ __forceinline__ unsigned t2_saddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+#define CB_CPA(BYTES, CACHE, dst, src)                                                              \
+    asm volatile("cp.async." CACHE ".shared.global [%0], [%1], " #BYTES ";" ::"r"(t2_saddr(dst)), "l"(src))
+#define CB_CPA_COMMIT() asm volatile("cp.async.commit_group;")
+
+// element ids of a tile's copy items (item t + k * CB_TILE_T -> seid[k][t], private to thread t)
+__device__ __forceinline__ void t2_issue_eids(const CbStiffArgs &A, const CbTile2 &tl, int *seid)
 {
 #pragma unroll
     for (int k = 0; k < CB_T2_EIDS; ++k) {
         const int i = threadIdx.x + k * CB_TILE_T;
-        eid[k] = (i < tl.ne * 9) ? __ldg(A.tile_elems + tl.e0 + i / 9) : 0;
+        if (i < tl.ne * 9) CB_CPA(4, "ca", seid + k * CB_TILE_T + threadIdx.x, A.tile_elems + tl.e0 + i / 9);
     }
 }
+// shell records of a tile (9 chunks of 16 bytes each) + its pair records
 __device__ __forceinline__ void t2_issue_stage(const CbStiffArgs &A, const CbTile2 &tl, const int *eid,
                                                double *krec_dst, CbTPair *pair_dst)
 {
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(krec_dst);
 #pragma unroll
     for (int k = 0; k < CB_T2_EIDS; ++k) {
         const int i = threadIdx.x + k * CB_TILE_T;
         if (i < tl.ne * 9) {
             const int es = i / 9, ch = i - es * 9;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (es * CB_SH_KREC * 8 + ch * 16)),
-                         "l"(A.d.sh_Nm + (long)eid[k] * CB_SH_KREC + ch * 2));
+            CB_CPA(16, "cg", krec_dst + es * CB_SH_KREC + ch * 2, A.d.sh_Nm + (long)eid[k] * CB_SH_KREC + ch * 2);
         }
     }
-    if (threadIdx.x < tl.np)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
-                         (unsigned)__cvta_generic_to_shared(pair_dst + threadIdx.x)),
-                     "l"(A.tpairs2 + tl.p0 + threadIdx.x));
-    asm volatile("cp.async.commit_group;");
+    if (threadIdx.x < tl.np) CB_CPA(16, "cg", pair_dst + threadIdx.x, A.tpairs2 + tl.p0 + threadIdx.x);
 }
-
-// DKT sub-blocks of the two contributions of work item t of a tile: work-major SoA
-// kebc[18 * w0 + (u * 9 + i) * nw + t] (u = contribution 0/1, i = 3x3 entry) - every load of a warp
-// is one contiguous 256-byte run, and the address needs nothing but the tile record
-__device__ __forceinline__ void t2_load_kb(const CbStiffArgs &A, const CbTile2 &tl, int t, double *kb)
+// DKT sub-blocks of the two contributions of work item t of tile T: kebc[(T * 18 + u * 9 + i) *
+// CB_TILE_T + t] (u = contribution 0/1, i = 3x3 entry) -> skb[u * 9 + i][t], private to thread t.
+// The left half of a block takes entries 0,3,6, the right half the other six.
+template <bool LEFT>
+__device__ __forceinline__ void t2_issue_kb(const CbStiffArgs &A, long T, int t, double *skb)
 {
-    const double *src = A.kebc + 18L * tl.w0 + t;
+    const double *src = A.kebc + T * (18L * CB_TILE_T) + t;
 #pragma unroll
-    for (int i = 0; i < 18; ++i) kb[i] = __ldg(src + (long)i * tl.nw);
+    for (int i = 0; i < 18; ++i)
+        if (((i % 3) == 0) == LEFT) CB_CPA(8, "ca", skb + i * CB_TILE_T + t, src + i * CB_TILE_T);
 }
 
 // columns c0..c0+2 of a block into the tile image (ACC: added to what is there); top/bot as in
@@ -574,63 +576,96 @@ __device__ __forceinline__ void t2_store_half(double *obuf, int shift, const CbT
     }
 }
 
+#define CB_T2_SMEM_DOUBLES (CB_T2_OUT + 2 + 2 * CB_T2_ELEMS * CB_SH_KREC + 18 * CB_TILE_T)
+#define CB_T2_SMEM_BYTES (CB_T2_SMEM_DOUBLES * 8 + 2 * CB_TILE_T * 16 + CB_TILE_T * 16 + CB_T2_EIDS * CB_TILE_T * 4 + 4 * 48)
+
 __global__ void __launch_bounds__(CB_TILE_T, CB_T2_CTAS)
 k_assemble_shell_tiles(CbStiffArgs A)
 {
     extern __shared__ __align__(16) double smem[];
     double *obuf = smem;                                              // [CB_T2_OUT + 2]
     double *skrec = obuf + CB_T2_OUT + 2;                             // [2][CB_T2_ELEMS*18], 16 B aligned
-    CbTPair *spair2 = reinterpret_cast<CbTPair *>(skrec + 2 * CB_T2_ELEMS * CB_SH_KREC);   // [2][CB_TILE_T]
-    const int t = threadIdx.x, lane = t & 31;
+    double *skb = skrec + 2 * CB_T2_ELEMS * CB_SH_KREC;               // [18][CB_TILE_T]
+    CbTPair *spair2 = reinterpret_cast<CbTPair *>(skb + 18 * CB_TILE_T);   // [2][CB_TILE_T]
+    int4 *swork = reinterpret_cast<int4 *>(spair2 + 2 * CB_TILE_T);   // [CB_TILE_T]
+    int *seid = reinterpret_cast<int *>(swork + CB_TILE_T);           // [CB_T2_EIDS][CB_TILE_T]
+    int *sring = seid + CB_T2_EIDS * CB_TILE_T;                       // [4][12] tile records
+    const int t = threadIdx.x;
+    const long G = gridDim.x, N = A.ntiles2;
     long tile = blockIdx.x;
-    if (tile >= A.ntiles2) return;
-    // software pipeline over the CTA's tiles: tile records two ahead, element ids / shell records /
-    // pair records / work item / DKT blocks one ahead
-    CbTile2 tl = A.tiles2[tile], tln = tl;
-    if (tile + gridDim.x < A.ntiles2) tln = A.tiles2[tile + gridDim.x];
-    int buf = 0;
-    int eid[CB_T2_EIDS];
-    t2_load_eids(A, tl, eid);
-    t2_issue_stage(A, tl, eid, skrec, spair2);
-    int4 wraw = make_int4(0, 0, 0, 0);
-    double kb[18];
+    if (tile >= N) return;
+    // Software pipeline over the CTA's tiles k, k+G, ...  Everything the loop reads from global
+    // memory arrives through cp.async, issued half a tile or more before it is needed:
+    //   tile record three ahead (ring of four in shared memory); element ids two ahead; the work
+    //   item, the shell + pair records and the DKT entries of the left halves of the next tile in
+    //   one group, committed after this tile's left halves; the DKT entries of its right halves in
+    //   a second group after this tile's right halves.  At most the newest group is in flight at
+    //   the two points where data is needed (cp.async.wait_group 1).
+    CbTile2 tl = A.tiles2[tile];
+    int it = 0;                                                        // iteration count = ring position
+    {
+        if (t < 20) {                                                  // records k+1, k+2 into the ring
+            const int r = 1 + t / 10, wd = t % 10;
+            if (tile + r * G < N) sring[r * 12 + wd] = reinterpret_cast<const int *>(A.tiles2 + tile + r * G)[wd];
+        }
+        int eid[CB_T2_EIDS];
 #pragma unroll
-    for (int i = 0; i < 18; ++i) kb[i] = 0.0;
-    if (t < tl.nw) {
-        wraw = __ldg(reinterpret_cast<const int4 *>(A.works + tl.w0 + t));
-        t2_load_kb(A, tl, t, kb);
+        for (int k = 0; k < CB_T2_EIDS; ++k) {
+            const int i = t + k * CB_TILE_T;
+            eid[k] = (i < tl.ne * 9) ? A.tile_elems[tl.e0 + i / 9] : 0;
+        }
+        t2_issue_stage(A, tl, eid, skrec, spair2);
+        if (tile + G < N) t2_issue_eids(A, A.tiles2[tile + G], seid);
+        if (t < tl.nw) {
+            CB_CPA(16, "cg", swork + t, A.works + tl.w0 + t);
+            t2_issue_kb<true>(A, tile, t, skb);
+        }
+        CB_CPA_COMMIT();
+        if (t < tl.nw) t2_issue_kb<false>(A, tile, t, skb);
+        CB_CPA_COMMIT();
     }
+    int buf = 0;
 
     for (;;) {
-        const long next = tile + gridDim.x, next2 = next + gridDim.x;
-        const bool has_next = next < A.ntiles2;
-        // tile record two ahead: lane i of every warp fetches word i; the words are broadcast at the
-        // end of this iteration, so that the wait for the load sits there and not here
-        int tword = 0;
-        if (next2 < A.ntiles2 && lane < 10) tword = __ldg(reinterpret_cast<const int *>(A.tiles2 + next2) + lane);
-        if (has_next) t2_load_eids(A, tln, eid);
+        const long next = tile + G;
+        const bool has_next = next < N, has_next2 = next + G < N, has_next3 = next + 2 * G < N;
         // the previous tile's image must have been read out by the copy engine
         if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                   // shell + pair records of this tile visible; obuf free
-        // the work item is unpacked only now: its load was issued a whole tile ago
-        asm volatile("" : "+r"(wraw.x), "+r"(wraw.y), "+r"(wraw.z), "+r"(wraw.w));
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();            // this tile's shell + pair records visible; image + buffers free
         CbWork w;
-        *reinterpret_cast<int4 *>(&w) = wraw;
+        *reinterpret_cast<int4 *>(&w) = swork[t];
+        CbTile2 tln = tl, tlnn = tl;
+        if (has_next) {
+#pragma unroll
+            for (int i = 0; i < 10; ++i) reinterpret_cast<int *>(&tln)[i] = sring[((it + 1) & 3) * 12 + i];
+        }
+        if (has_next2) {
+#pragma unroll
+            for (int i = 0; i < 10; ++i) reinterpret_cast<int *>(&tlnn)[i] = sring[((it + 2) & 3) * 12 + i];
+        }
+        if (has_next3 && t < 10)
+            CB_CPA(4, "ca", sring + ((it + 3) & 3) * 12 + t, reinterpret_cast<const int *>(A.tiles2 + next + 2 * G) + t);
         const int shift = (int)(tl.out0 & 1);
         const CbTPair *spair = spair2 + buf * CB_TILE_T;
+        const double *kr0 = skrec + buf * CB_T2_ELEMS * CB_SH_KREC;
+        const bool active = t < tl.nw;
+        const unsigned amask = __ballot_sync(0xffffffffu, active);
+        CbTPair pr{};
+        int gmax = 0;
+        if (active) {
+            if (w.kind != 4) pr = spair[w.dst];
+            gmax = __reduce_max_sync(amask, w.kind == 2 ? (int)w.pad0 : 0);   // largest group of the warp
+        }
 
         // ---- phase 1: the block (or partial sum) of this thread, three columns at a time --------
-        const unsigned amask = __ballot_sync(0xffffffffu, t < tl.nw);
-        if (t < tl.nw) {
-            const double *kr0 = skrec + buf * CB_T2_ELEMS * CB_SH_KREC;
-            CbTPair pr{};
-            if (w.kind != 4) pr = spair[w.dst];
-            // largest group of this warp (0: none)
-            const int gmax = __reduce_max_sync(amask, w.kind == 2 ? (int)w.pad0 : 0);
-            double top[9], bot[9];
 #define CB_T2_HALF(LEFT, C0)                                                                       \
+        if (active) {                                                                              \
+            double top[9], bot[9];                                                                 \
             if (w.n >= 1) {                                                                        \
+                double kb[18];                                                                     \
+                _Pragma("unroll") for (int i = 0; i < 18; ++i)                                     \
+                    if (((i % 3) == 0) == LEFT) kb[i] = skb[i * CB_TILE_T + t];                    \
                 shell_half_acc<LEFT>(kr0 + w.s0 * CB_SH_KREC, kb, w.a0, w.b0, top, bot, true);     \
                 if (w.n == 2)                                                                      \
                     shell_half_acc<LEFT>(kr0 + w.s1 * CB_SH_KREC, kb + 9, w.a1, w.b1, top, bot, false); \
@@ -639,21 +674,28 @@ k_assemble_shell_tiles(CbStiffArgs A)
             for (int q = 1; q < gmax; ++q) {        /* warp-uniform */                             \
                 __syncwarp(amask);                                                                 \
                 if (w.kind == 3 && w.pad1 == q) t2_store_half<true>(obuf, shift, pr, C0, top, bot); \
-            }
-            CB_T2_HALF(true, 0)
-            CB_T2_HALF(false, 3)
-#undef CB_T2_HALF
+            }                                                                                      \
         }
-        // next tile: records by cp.async into the other buffers, work item and DKT blocks into
-        // registers - all in flight while the image leaves
+        CB_T2_HALF(true, 0)
+        // group 1 for the next tile (its left DKT entries go where this thread's were)
         if (has_next) {
+            int eid[CB_T2_EIDS];
+#pragma unroll
+            for (int k = 0; k < CB_T2_EIDS; ++k) eid[k] = seid[k * CB_TILE_T + t];
             t2_issue_stage(A, tln, eid, skrec + (buf ^ 1) * CB_T2_ELEMS * CB_SH_KREC,
                            spair2 + (buf ^ 1) * CB_TILE_T);
+            if (has_next2) t2_issue_eids(A, tlnn, seid);
             if (t < tln.nw) {
-                wraw = __ldg(reinterpret_cast<const int4 *>(A.works + tln.w0 + t));
-                t2_load_kb(A, tln, t, kb);
+                CB_CPA(16, "cg", swork + t, A.works + tln.w0 + t);
+                t2_issue_kb<true>(A, next, t, skb);
             }
         }
+        CB_CPA_COMMIT();
+        asm volatile("cp.async.wait_group 1;" ::: "memory");     // this tile's right DKT entries
+        CB_T2_HALF(false, 3)
+#undef CB_T2_HALF
+        if (has_next && t < tln.nw) t2_issue_kb<false>(A, next, t, skb);
+        CB_CPA_COMMIT();
         // writes of the image (generic proxy) ordered before the copy engine's reads (async proxy)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
@@ -665,7 +707,7 @@ k_assemble_shell_tiles(CbStiffArgs A)
             const int nv = (tl.nout - shift) >> 1;
             if (nv > 0)
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + shift),
-                             "r"((unsigned)__cvta_generic_to_shared(img + shift)), "r"(nv * 16)
+                             "r"(t2_saddr(img + shift)), "r"(nv * 16)
                              : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             if (shift) dst[0] = img[0];
@@ -673,20 +715,14 @@ k_assemble_shell_tiles(CbStiffArgs A)
             if (tail < tl.nout) dst[tail] = img[tail];
         }
         if (!has_next) break;
-        tile = next; tl = tln; buf ^= 1;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-            const int v = __shfl_sync(0xffffffffu, tword, i);
-            if (next2 < A.ntiles2) reinterpret_cast<int *>(&tln)[i] = v;
-        }
+        tile = next; tl = tln; buf ^= 1; ++it;
     }
     if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 static int launch_shell_tiles(const CbStiffArgs &a, cudaStream_t s)
 {
-    const size_t smem = (size_t)(CB_T2_OUT + 2 + 2 * CB_T2_ELEMS * CB_SH_KREC) * sizeof(double) +
-                        2 * CB_TILE_T * sizeof(CbTPair);
+    const size_t smem = CB_T2_SMEM_BYTES;
     static int grid_cache = 0;
     if (!grid_cache) {
         if (cudaFuncSetAttribute(k_assemble_shell_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -71,6 +71,7 @@ struct Plan {
     DevBuf<CbPair> pairs;
     long npairs = 0;
     DevBuf<CbTile> tiles;
+    DevBuf<CbContrib> tcontribs;
     DevBuf<CbTPair> tpairs;
     long ntiles = 0;
     DevBuf<CbTile2> tiles2; DevBuf<CbWork> works; DevBuf<CbTPair> tpairs2; DevBuf<int32_t> telems;
@@ -428,7 +429,7 @@ extern "C" void cb_destroy(cb_handle *h)
                                &h->fr_mendrel, &h->br_nodes, &h->node_cstart})
         b->release();
     h->corners.release(); h->contribs.release(); h->plan_csc.pairs.release();
-    h->plan_csc.tiles.release(); h->plan_csc.tpairs.release();
+    h->plan_csc.tiles.release(); h->plan_csc.tpairs.release(); h->plan_csc.tcontribs.release();
     h->plan_csc.tiles2.release(); h->plan_csc.works.release(); h->plan_csc.tpairs2.release();
     h->plan_csc.telems.release();
     h->plan_sky.pairs.release(); h->Ap.release(); h->Ai.release(); h->maxa.release();
@@ -527,7 +528,10 @@ static int build_plan(cb_handle *h)
     std::vector<CbTile> tiles;
     std::vector<CbContrib> contribs;
     contribs.reserve((size_t)ncorner * 3);
-    const int OUTMAX = 2046;                 // doubles of tile output staged in shared memory (+2 pad)
+    // doubles of tile output staged in shared memory (+2 pad).  Frame joints carry 7 equations and
+    // their blocks are the costliest to evaluate: a larger image lets a tile hold enough blocks of
+    // each kind to fill whole warps (lattice joint: 343 doubles, 12 blocks)
+    const int OUTMAX = h->sz.NE_FR ? 2760 : 2046;
     bool tiles_ok = (h->layout & CB_MAT_CSC) != 0;
     CbTile cur{}; cur.nc = cur.np = cur.nout = 0; bool open = false;
     int max_tile_out = 0;
@@ -598,6 +602,48 @@ static int build_plan(cb_handle *h)
                          [](const CbTPair &x, const CbTPair &y) { return x.cnt > y.cnt; });
     if (contribs.size() > 0x7fffffffUL) return fail(CB_ERR_OVERFLOW, "too many contributions");
     h->ncontrib = (long)contribs.size();
+    // thread slots of the general tile kernel: the contributions of a tile regrouped by kind of
+    // block (element type, local joints) so that a warp's lanes run the same code; a group that
+    // would straddle a warp boundary starts at the next one when the tile has the lanes to spare
+    std::vector<CbContrib> tcontribs;
+    if (tiles_ok) {
+        tcontribs.reserve(contribs.size() + contribs.size() / 8);
+        std::vector<int> idx;
+        for (CbTile &tl : tiles) {
+            idx.resize(tl.nc);
+            for (int i = 0; i < tl.nc; ++i) idx[i] = i;
+            auto kind = [&](int i) {
+                const CbContrib &c = contribs[tl.c0 + i];
+                return ((int)c.type << 8) | ((int)c.a << 4) | (int)c.b;
+            };
+            std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return kind(x) < kind(y); });
+            std::vector<std::pair<int, int>> groups;          // [first, count) in idx
+            for (int i = 0; i < tl.nc;) {
+                int j = i; while (j < tl.nc && kind(idx[j]) == kind(idx[i])) ++j;
+                groups.push_back({i, j - i}); i = j;
+            }
+            // lanes lost if every group that straddles a boundary is moved to the next warp
+            int need = 0;
+            for (auto &g : groups) {
+                if (g.second <= 32 && (need & 31) + g.second > 32) need = (need + 31) & ~31;
+                need += g.second;
+            }
+            const bool align = need <= CB_TILE_T;
+            tl.t0 = (int32_t)tcontribs.size();
+            int slot = 0;
+            CbContrib idle{}; idle.type = 0xff;
+            for (auto &g : groups) {
+                if (align && g.second <= 32 && (slot & 31) + g.second > 32)
+                    while (slot & 31) { tcontribs.push_back(idle); ++slot; }
+                for (int i = 0; i < g.second; ++i) {
+                    CbContrib c = contribs[tl.c0 + idx[g.first + i]];
+                    c.pad = (uint8_t)idx[g.first + i];
+                    tcontribs.push_back(c); ++slot;
+                }
+            }
+            tl.ns = (uint16_t)slot;
+        }
+    }
     {
         // ND must cover the highest free DOF of any joint (a brick-only joint still carries the
         // three rotational equations struc() leaves free), `mixed` = some element type brings
@@ -765,13 +811,16 @@ static int build_plan(cb_handle *h)
     bucket(pairs_sky);
     if (tiles_ok) pairs_csc.clear(); else { bucket(pairs_csc); tiles.clear(); tpairs.clear(); }
     if (plan2_ok) { tiles.clear(); tpairs.clear(); }
+    if (tiles.empty()) tcontribs.clear();
 
     if (h->node_cstart.upload(cstart) || h->corners.upload(corners) || h->contribs.upload(contribs))
         return CB_ERR_CUDA;
     if (h->layout & CB_MAT_CSC) {
         if (h->plan_csc.pairs.upload(pairs_csc)) return CB_ERR_CUDA;
         h->plan_csc.npairs = (long)pairs_csc.size();
-        if (h->plan_csc.tiles.upload(tiles) || h->plan_csc.tpairs.upload(tpairs)) return CB_ERR_CUDA;
+        if (h->plan_csc.tiles.upload(tiles) || h->plan_csc.tpairs.upload(tpairs) ||
+            h->plan_csc.tcontribs.upload(tcontribs))
+            return CB_ERR_CUDA;
         h->plan_csc.ntiles = (long)tiles.size();
         if (h->plan_csc.tiles2.upload(tiles2) || h->plan_csc.works.upload(works) ||
             h->plan_csc.tpairs2.upload(tp2) || h->plan_csc.telems.upload(telems))
@@ -792,6 +841,7 @@ static int build_plan(cb_handle *h)
     }
     h->map_bytes = (long)((pairs_csc.size() + pairs_sky.size()) * sizeof(CbPair) +
                           tiles.size() * sizeof(CbTile) + tpairs.size() * sizeof(CbTPair) +
+                          tcontribs.size() * sizeof(CbContrib) +
                           tiles2.size() * sizeof(CbTile2) + works.size() * sizeof(CbWork) +
                           tp2.size() * sizeof(CbTPair) + telems.size() * sizeof(int32_t) +
                           contribs.size() * sizeof(CbContrib));
@@ -913,7 +963,7 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
     if (h->layout & CB_MAT_CSC) {
         a.pairs = h->plan_csc.pairs.p; a.npairs = h->plan_csc.npairs;
         a.tiles = h->plan_csc.ntiles ? h->plan_csc.tiles.p : nullptr; a.ntiles = h->plan_csc.ntiles;
-        a.tpairs = h->plan_csc.tpairs.p; a.kebc = h->sh_kebc.p;
+        a.tpairs = h->plan_csc.tpairs.p; a.kebc = h->sh_kebc.p; a.tcontribs = h->plan_csc.tcontribs.p;
         a.tiles2 = h->plan_csc.ntiles2 ? h->plan_csc.tiles2.p : nullptr; a.ntiles2 = h->plan_csc.ntiles2;
         a.works = h->plan_csc.works.p; a.tpairs2 = h->plan_csc.tpairs2.p; a.tile_elems = h->plan_csc.telems.p;
         a.tile_smem_out = h->plan_csc.tile_smem_out;

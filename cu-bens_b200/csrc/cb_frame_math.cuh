@@ -81,6 +81,85 @@ __device__ __forceinline__ void frame_geometric(double (*k)[14], const double *e
 #undef CB_SUB
 }
 
+// ---- stiffness-path variants: the same closed forms with every division replaced by a product with
+// a reciprocal formed once (three FP64 divisions per block instead of ~60, each of which is a
+// ~30-instruction sequence on the FP64 pipe).  K_t has no cancellation beyond its own magnitude, so
+// the 1-2 ulp per entry this moves stays far inside the 1e-12 norm-wise tolerance; the force path
+// keeps the reference's rounding sequence above.
+__device__ __forceinline__ void frame_elastic_rcp(double (*k)[14], const double *fc)
+{
+    const double E = fc[0], G = fc[1], A = fc[2], L = fc[3];
+    const double Iz = fc[6], Iy = fc[7], J = fc[8], Cw = fc[9];
+    const double iL = 1.0 / L, iL2 = iL * iL, iL3 = iL2 * iL;
+    const double EIz = E * Iz, EIy = E * Iy, GJ = G * J, ECw = E * Cw;
+#define CB_SYM(i, j, v) k[i][j] = k[j][i] = (v)
+    k[0][0] = k[7][7] = E * A * iL;                CB_SYM(7, 0, -k[0][0]);
+    k[1][1] = k[8][8] = 12 * EIz * iL3;            CB_SYM(8, 1, -k[1][1]);
+    k[2][2] = k[9][9] = 12 * EIy * iL3;            CB_SYM(9, 2, -k[2][2]);
+    k[3][3] = k[10][10] = 1.2 * GJ * iL + 12 * ECw * iL3;   CB_SYM(10, 3, -k[3][3]);
+    k[5][5] = k[12][12] = 4 * EIz * iL;
+    k[4][4] = k[11][11] = 4 * EIy * iL;
+    k[6][6] = k[13][13] = (2.0 / 15.0) * GJ * L + 4 * ECw * iL;
+    CB_SYM(5, 1, 6 * EIz * iL2); CB_SYM(12, 1, k[5][1]);
+    CB_SYM(8, 5, -k[5][1]);      CB_SYM(12, 8, -k[5][1]);
+    CB_SYM(9, 4, 6 * EIy * iL2); CB_SYM(11, 9, k[9][4]);
+    CB_SYM(4, 2, -k[9][4]);      CB_SYM(11, 2, -k[9][4]);
+    CB_SYM(6, 3, 0.1 * GJ + 6 * ECw * iL2); CB_SYM(13, 3, k[6][3]);
+    CB_SYM(10, 6, -k[6][3]);     CB_SYM(13, 10, -k[6][3]);
+    CB_SYM(12, 5, 2 * EIz * iL);
+    CB_SYM(11, 4, 2 * EIy * iL);
+    CB_SYM(13, 6, -(GJ * L * (1.0 / 30.0) - 2 * ECw * iL));
+#undef CB_SYM
+}
+
+__device__ __forceinline__ void frame_geometric_rcp(double (*k)[14], const double *ef, double L,
+                                                    double A, double J)
+{
+    const double P = ef[7], M4 = ef[4], M5 = ef[5], M10 = ef[10], M11 = ef[11], M12 = ef[12];
+    const double iL = 1.0 / L, JA = J / A;
+    const double PL = P * iL, PL65 = 1.2 * PL, PJ = P * JA, PL30 = P * L * (1.0 / 30.0);
+    const double L30 = L * (1.0 / 30.0), iL10 = 0.1 * iL;
+#define CB_ADD(i, j, v) do { const double v_ = (v); k[i][j] += v_; k[j][i] += v_; } while (0)
+#define CB_SUB(i, j, v) do { const double v_ = (v); k[i][j] -= v_; k[j][i] -= v_; } while (0)
+    k[0][0] += PL; k[7][7] += PL; CB_SUB(7, 0, PL);
+    k[1][1] += PL65; k[8][8] += PL65;
+    k[2][2] += PL65; k[9][9] += PL65;
+    CB_SUB(8, 1, PL65); CB_SUB(9, 2, PL65);
+    k[3][3] += PL65 * JA; k[10][10] += PL65 * JA;
+    CB_SUB(10, 3, PL65 * JA);
+    k[4][4] += 4 * PL30; k[11][11] += 4 * PL30;
+    k[5][5] += 4 * PL30; k[12][12] += 4 * PL30;
+    k[6][6] += (2.0 / 15.0) * PJ; k[13][13] += (2.0 / 15.0) * PJ;
+    CB_ADD(3, 1, (11 * M4 - M11) * iL10); CB_SUB(8, 3, (11 * M4 - M11) * iL10);
+    CB_ADD(4, 1, M10 * iL); CB_ADD(5, 2, M10 * iL); CB_ADD(11, 8, M10 * iL); CB_ADD(12, 9, M10 * iL);
+    CB_SUB(11, 1, M10 * iL); CB_SUB(12, 2, M10 * iL); CB_SUB(8, 4, M10 * iL); CB_SUB(9, 5, M10 * iL);
+    CB_ADD(5, 1, 0.1 * P); CB_ADD(12, 1, 0.1 * P); CB_ADD(9, 4, 0.1 * P); CB_ADD(11, 9, 0.1 * P);
+    CB_SUB(4, 2, 0.1 * P); CB_SUB(11, 2, 0.1 * P); CB_SUB(8, 5, 0.1 * P); CB_SUB(12, 8, 0.1 * P);
+    CB_ADD(6, 1, 0.1 * M4); CB_SUB(8, 6, 0.1 * M4);
+    CB_ADD(10, 8, (M4 - 11 * M11) * iL10); CB_SUB(10, 1, (M4 - 11 * M11) * iL10);
+    CB_ADD(13, 8, 0.1 * M11); CB_SUB(13, 1, 0.1 * M11);
+    CB_ADD(3, 2, (11 * M5 - M12) * iL10); CB_SUB(9, 3, (11 * M5 - M12) * iL10);
+    CB_ADD(6, 2, 0.1 * M5); CB_SUB(9, 6, 0.1 * M5);
+    CB_ADD(10, 9, (M5 - 11 * M12) * iL10); CB_SUB(10, 2, (M5 - 11 * M12) * iL10);
+    CB_ADD(13, 9, 0.1 * M12); CB_SUB(13, 2, 0.1 * M12);
+    CB_SUB(4, 3, (2 * M5 - M12) * 0.2); CB_ADD(5, 3, (2 * M4 - M11) * 0.2);
+    CB_ADD(6, 3, 0.1 * PJ); CB_ADD(13, 3, 0.1 * PJ);
+    CB_SUB(10, 6, 0.1 * PJ); CB_SUB(13, 10, 0.1 * PJ);
+    CB_SUB(11, 3, (2 * M5 + M12) * 0.1); CB_ADD(12, 3, (2 * M4 + M11) * 0.1);
+    CB_SUB(6, 4, (3 * M5 - M12) * L30); CB_SUB(10, 4, (M5 + 2 * M12) * 0.1);
+    CB_SUB(11, 4, PL30); CB_SUB(12, 5, PL30);
+    CB_ADD(12, 4, 0.5 * M10); CB_SUB(11, 5, 0.5 * M10);
+    CB_ADD(13, 4, M5 * L30);
+    CB_ADD(6, 5, (3 * M4 - M11) * L30); CB_ADD(10, 5, (M4 + 2 * M11) * 0.1);
+    CB_SUB(13, 5, M4 * L30);
+    CB_SUB(11, 6, M12 * L30); CB_ADD(12, 6, M11 * L30);
+    CB_SUB(13, 6, PJ * (1.0 / 30.0));
+    CB_ADD(11, 10, (M5 - 2 * M12) * 0.2); CB_SUB(12, 10, (M4 - 2 * M11) * 0.2);
+    CB_SUB(13, 11, (M5 - 3 * M12) * L30); CB_ADD(13, 12, (M4 - 3 * M11) * L30);
+#undef CB_ADD
+#undef CB_SUB
+}
+
 // Gauss-Jordan inverse without pivoting, as misc.c:284-343 behaves for SPD input (n <= 4)
 __device__ __forceinline__ void gj_inverse4(double *A, int n)
 {

@@ -55,12 +55,17 @@ struct CbPair {
 struct CbTile {
     int64_t out0;     // first Ax index of the tile's (contiguous) output range
     int32_t nout;     // number of Ax entries
-    int32_t c0;       // first contribution
-    int32_t nc;       // contributions (<= CB_TILE_T)
+    int32_t c0;       // first contribution (reference order: the order phase 2 sums in)
     int32_t p0;       // first pair
-    int32_t np;       // pairs
-    int32_t pad;
+    int32_t t0;       // first thread slot in tcontribs
+    uint16_t nc;      // contributions (<= CB_TILE_T)
+    uint16_t np;      // pairs
+    uint16_t ns;      // thread slots (nc <= ns <= CB_TILE_T): the contributions regrouped so that the
+                      // lanes of a warp evaluate the same kind of block (element type, local joints);
+                      // slot record = CbContrib with pad = tile-local contribution index, type 0xff idle
+    uint16_t pad;
 };
+static_assert(sizeof(CbTile) == 32, "tile record");
 struct CbTPair {
     int32_t rel;      // offset of (first free row of A, first free column of B) in the tile output
     int32_t colh;     // column height of joint B
@@ -173,6 +178,7 @@ struct CbStiffArgs {
     const CbPair *pairs; long npairs;
     const CbContrib *contribs;
     const CbTile *tiles; long ntiles; const CbTPair *tpairs;
+    const CbContrib *tcontribs;   // thread slots of the general tile kernel (see CbTile)
     const double *kebc;      // DKT 3x3 sub-blocks in assembly order (static; layouts above)
     const CbTile2 *tiles2; long ntiles2; const CbWork *works; const CbTPair *tpairs2;
     const int32_t *tile_elems;

@@ -156,6 +156,68 @@ __device__ __noinline__ void frame_block(const CbStiffArgs &A, int e, int a, int
         for (int j = 0; j < 7; ++j) blk[i * ld + j] = K[i][j];
 }
 
+// Same block with the local joints known at compile time: every index into the 14x14 local matrix
+// is static, so it lives in registers and the three quarters of it this block does not need are
+// never computed (the generic version above keeps it in local memory: 4 KB of stack per thread).
+// Members with end releases (static condensation, runtime pivots) take the generic path.
+template <int LA, int LB>
+__device__ __noinline__ void frame_block_t(const CbStiffArgs &A, int e, double *stg, int str)
+{
+    double k[14][14], eft[14];
+    const double *fr = A.fr_frame + (long)e * CB_FR_FRAME;
+    const double *fc = A.d.fr_const + (long)e * CB_FR_CONST;
+#pragma unroll
+    for (int i = 0; i < 14; ++i) {
+#pragma unroll
+        for (int j = 0; j < 14; ++j) k[i][j] = 0;
+        eft[i] = A.fr_ef[(long)e * 14 + i] + A.fr_efFE[(long)e * 14 + i];
+    }
+    frame_elastic_rcp(k, fc);
+    if (A.d.ANAFLAG == 2) frame_geometric_rcp(k, eft, fr[9], fc[2], fc[8]);
+    double R[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = fr[i];
+    double W[7][7], K[7][7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {                     // W = k_ab T_b
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                W[i][3 * q + j] = k[7 * LA + i][7 * LB + 3 * q] * R[j] + k[7 * LA + i][7 * LB + 3 * q + 1] * R[3 + j] +
+                                  k[7 * LA + i][7 * LB + 3 * q + 2] * R[6 + j];
+        W[i][6] = k[7 * LA + i][7 * LB + 6];
+    }
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {                     // K = T_a^T W
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                K[3 * p + i][j] = R[i] * W[3 * p][j] + R[3 + i] * W[3 * p + 1][j] + R[6 + i] * W[3 * p + 2][j];
+        K[6][j] = W[6][j];
+    }
+    if (A.d.fr_osflag[e] != 0) {
+        const double *oa = A.d.fr_offset + (long)e * 6 + 3 * LA, *ob = A.d.fr_offset + (long)e * 6 + 3 * LB;
+        const double Sa[3][3] = {{0, oa[2], -oa[1]}, {-oa[2], 0, oa[0]}, {oa[1], -oa[0], 0}};
+        const double Sb[3][3] = {{0, ob[2], -ob[1]}, {-ob[2], 0, ob[0]}, {ob[1], -ob[0], 0}};
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                K[i][3 + j] += K[i][0] * Sb[0][j] + K[i][1] * Sb[1][j] + K[i][2] * Sb[2][j];
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                K[3 + i][j] += Sa[0][i] * K[0][j] + Sa[1][i] * K[1][j] + Sa[2][i] * K[2][j];
+    }
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) stg[(i * 7 + j) * str] = K[i][j];
+}
+
 // K_ab (3x3) of 8-node brick e: 2x2x2 Gauss, B_a^T C B_b detJ (brick.c:79-397, jacob 541-699).
 // For the isotropic C of brick.c:127-141 (lambda = e1, mu = e2, lambda + 2 mu = e3) the 6x24
 // strain-displacement product collapses to
@@ -313,10 +375,10 @@ k_assemble_tiles(CbStiffArgs A)
     long tile = blockIdx.x;
     if (tile >= A.ntiles) return;
     CbTile tl = A.tiles[tile];
-    CbContrib ct{};
-    if (t < tl.nc) ct = A.contribs[tl.c0 + t];
+    CbContrib ct{}; ct.type = 0xff;
+    if (t < tl.ns) ct = A.tcontribs[tl.t0 + t];
     ShellIn in;
-    if (ND >= 6 && t < tl.nc && (SHELL_ONLY || ct.type == CB_T_SHELL)) shell_load(A, ct, (long)tl.c0 + t, in);
+    if (ND >= 6 && ct.type == CB_T_SHELL) shell_load(A, ct, (long)tl.c0 + ct.pad, in);
 
     for (;;) {
         const long next = tile + gridDim.x;
@@ -326,9 +388,10 @@ k_assemble_tiles(CbStiffArgs A)
         if (t < tl.np) spair[t] = A.tpairs[tl.p0 + t];
 
         // ---- phase 1: one contribution per thread -> its column of `stage` ---------------------
-        if (t < tl.nc) {
-            double *stg = stage + t;
-            if (SHELL_ONLY || ct.type == CB_T_SHELL) {
+        if (ct.type != 0xff) {
+            double *stg = stage + ct.pad;
+            const int col = ct.pad;             // column of `stage` / entry of ndof: reference order
+            if (ct.type == CB_T_SHELL) {
                 if constexpr (ND >= 6) {
                     if (ND > 6) {
 #pragma unroll
@@ -336,16 +399,22 @@ k_assemble_tiles(CbStiffArgs A)
                     }
                     shell_block_stage<ND>(in, ct.a, ct.b, stg);
                 }
-                ndof[t] = 6;
+                ndof[col] = 6;
             } else if (SHELL_ONLY) {
             } else if (ct.type == CB_T_FRAME) {
                 if constexpr (ND >= 7) {
-                    double blk[49];
-                    frame_block(A, ct.e, ct.a, ct.b, blk, 7);
+                    if (A.d.fr_mendrel[(long)ct.e * 5] == 1) {
+                        double blk[49];
+                        frame_block(A, ct.e, ct.a, ct.b, blk, 7);
 #pragma unroll
-                    for (int i = 0; i < 49; ++i) stg[i * STR] = blk[i];
+                        for (int i = 0; i < 49; ++i) stg[i * STR] = blk[i];
+                    } else if (ct.a == 0) {
+                        if (ct.b == 0) frame_block_t<0, 0>(A, ct.e, stg, STR); else frame_block_t<0, 1>(A, ct.e, stg, STR);
+                    } else {
+                        if (ct.b == 0) frame_block_t<1, 0>(A, ct.e, stg, STR); else frame_block_t<1, 1>(A, ct.e, stg, STR);
+                    }
                 }
-                ndof[t] = 7;
+                ndof[col] = 7;
             } else {
                 double blk[9];
 #pragma unroll
@@ -358,16 +427,15 @@ k_assemble_tiles(CbStiffArgs A)
                 for (int p = 0; p < 3; ++p)
 #pragma unroll
                     for (int q = 0; q < 3; ++q) stg[(p * ND + q) * STR] = blk[p * 3 + q];
-                ndof[t] = 3;
+                ndof[col] = 3;
             }
         }
         // request the next tile's contribution record, then its element inputs; they land while
         // this tile is reduced and written out
-        CbContrib ctn{};
-        if (has_next && t < tln.nc) ctn = A.contribs[tln.c0 + t];
+        CbContrib ctn{}; ctn.type = 0xff;
+        if (has_next && t < tln.ns) ctn = A.tcontribs[tln.t0 + t];
         __syncthreads();
-        if (ND >= 6 && has_next && t < tln.nc && (SHELL_ONLY || ctn.type == CB_T_SHELL))
-            shell_load(A, ctn, (long)tln.c0 + t, in);
+        if (ND >= 6 && ctn.type == CB_T_SHELL) shell_load(A, ctn, (long)tln.c0 + ctn.pad, in);
 
         // ---- phase 2: segmented reduction over the sorted contribution list, one thread per
         // (joint-pair block, column): ND rows of `stage` summed over the block's contributions in

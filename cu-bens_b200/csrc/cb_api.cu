@@ -127,6 +127,9 @@ struct cb_handle {
     DevBuf<int32_t> fr_nodes, fr_osflag, fr_mendrel;
     DevBuf<double> fr_const, fr_offset, fr_efFE_ref, fr_fg, fr_dens;
     DevBuf<double> fr_frame[3], fr_xfr[3], fr_efFE[3], fr_ef[3];
+    // ANAFLAG 3
+    DevBuf<double> fr_plast, fr_tau, tr_py;
+    DevBuf<int32_t> fr_yldflag, fr_ynew, fr_code, fr_trip;
     // bricks
     DevBuf<int32_t> br_nodes;
     DevBuf<double> br_const;
@@ -168,6 +171,8 @@ static CbDev make_dev(cb_handle *h)
     d.fr_nodes = h->fr_nodes.p; d.fr_const = h->fr_const.p; d.fr_offset = h->fr_offset.p;
     d.fr_osflag = h->fr_osflag.p; d.fr_mendrel = h->fr_mendrel.p;
     d.fr_efFE_ref = h->fr_efFE_ref.p; d.fr_fg = h->fr_fg.p;
+    d.fr_plast = h->fr_plast.p; d.fr_yldflag = h->fr_yldflag.p; d.fr_ynew = h->fr_ynew.p;
+    d.fr_code = h->fr_code.p; d.fr_tau = h->fr_tau.p; d.fr_trip = h->fr_trip.p; d.tr_py = h->tr_py.p;
     d.tr_nodes = h->tr_nodes.p; d.tr_const = h->tr_const.p; d.tr_fg = h->tr_fg.p;
     d.br_nodes = h->br_nodes.p; d.br_const = h->br_const.p;
     return d;
@@ -187,10 +192,17 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
 {
     if (!sz || !fl || !m || !out) return fail(CB_ERR_ARG, "cb_create: null argument");
     *out = nullptr;
-    if (fl->ANAFLAG != 1 && fl->ANAFLAG != 2)
-        return fail(CB_ERR_UNSUPPORTED, "ANAFLAG=%d: only 1 (elastic) and 2 (geometric "
-                    "nonlinear) are built; 3 (plasticity) / 4 (FSI) are listed in DESIGN.md",
-                    fl->ANAFLAG);
+    if (fl->ANAFLAG < 1 || fl->ANAFLAG > 3)
+        return fail(CB_ERR_UNSUPPORTED, "ANAFLAG=%d: 1 (elastic), 2 (geometric nonlinear) and 3 "
+                    "(material nonlinear, trusses and frames) are built; 4 (FSI) is listed in "
+                    "DESIGN.md", fl->ANAFLAG);
+    if (fl->ANAFLAG == 3 && sz->NE_SH)
+        return fail(CB_ERR_UNSUPPORTED, "ANAFLAG=3 with shells: the Ivanov-yield shell path "
+                    "(shell.c:842-1503, 1786-2325) is not built yet (DESIGN.md section 7)");
+    if (fl->ANAFLAG == 3 && (sz->NE_TR || sz->NE_FR) && !m->yield)
+        return fail(CB_ERR_ARG, "ANAFLAG=3 needs the yield stresses");
+    if (fl->ANAFLAG == 3 && sz->NE_FR && (!m->zstrong || !m->zweak))
+        return fail(CB_ERR_ARG, "ANAFLAG=3 needs the plastic section moduli zstrong / zweak");
     if (sz->NE_FBR != 0) return fail(CB_ERR_UNSUPPORTED, "fluid bricks (FSI) are out of scope");
     if (sz->NJ <= 0 || sz->NEQ <= 0) return fail(CB_ERR_ARG, "NJ and NEQ must be positive");
     if (sz->NJ > 0x7fffffffL / 8 || sz->NEQ > 0x7ffffff0L)
@@ -320,6 +332,11 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
         }
         if (h->tr_const.upload(c) || h->tr_dens.upload(dn) || h->tr_fg.alloc((size_t)TR * 6))
             BAIL(CB_ERR_CUDA);
+        if (fl->ANAFLAG == 3) {                         // Py = carea * yield (truss.c:120)
+            std::vector<double> py(TR);
+            for (long e = 0; e < TR; ++e) py[e] = m->carea[e] * m->yield[e];
+            if (h->tr_py.upload(py)) BAIL(CB_ERR_CUDA);
+        }
         for (int g = 0; g < 3; ++g) {
             if (h->tr_frame[g].upload(fr) || h->tr_ef[g].alloc((size_t)TR * 2)) BAIL(CB_ERR_CUDA);
             cudaMemset(h->tr_ef[g].p, 0, (size_t)TR * 2 * sizeof(double));
@@ -363,6 +380,19 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
             h->fr_mendrel.upload(rel) || h->fr_efFE_ref.upload(fe) || h->fr_dens.upload(dn) ||
             h->fr_fg.alloc((size_t)FR * 14))
             BAIL(CB_ERR_CUDA);
+        if (fl->ANAFLAG == 3) {                         // frame.c:588-590
+            std::vector<double> pl((size_t)FR * 3);
+            for (long e = 0; e < FR; ++e) {
+                pl[e * 3] = m->carea[TR + e] * m->yield[TR + e];
+                pl[e * 3 + 1] = m->zweak[e] * m->yield[TR + e];
+                pl[e * 3 + 2] = m->zstrong[e] * m->yield[TR + e];
+            }
+            if (h->fr_plast.upload(pl) || h->fr_yldflag.alloc((size_t)FR * 2) || h->fr_ynew.alloc((size_t)FR * 2) ||
+                h->fr_code.alloc(FR) || h->fr_tau.alloc(FR) || h->fr_trip.alloc(4))
+                BAIL(CB_ERR_CUDA);
+            cudaMemset(h->fr_yldflag.p, 0, (size_t)FR * 2 * sizeof(int32_t));   // main.c:1692
+            cudaMemset(h->fr_trip.p, 0, 4 * sizeof(int32_t));
+        }
         for (int g = 0; g < 3; ++g) {
             if (h->fr_frame[g].upload(fr) || h->fr_xfr[g].upload(xfr) ||
                 h->fr_efFE[g].alloc((size_t)FR * 14) || h->fr_ef[g].alloc((size_t)FR * 14))
@@ -417,8 +447,9 @@ extern "C" void cb_destroy(cb_handle *h)
                               &h->d_temp, &h->sm, &h->qvec, &h->sums, &h->sums_part, &h->sh_const, &h->sh_keb, &h->sh_kebc, &h->sh_der, &h->sh_Nm, &h->sh_fg,
                               &h->sh_dens, &h->tr_const, &h->tr_fg, &h->tr_dens, &h->fr_const,
                               &h->fr_offset, &h->fr_efFE_ref, &h->fr_fg, &h->fr_dens, &h->br_const,
-                              &h->Ax, &h->ss})
+                              &h->Ax, &h->ss, &h->fr_plast, &h->fr_tau, &h->tr_py})
         b->release();
+    for (DevBuf<int32_t> *b : {&h->fr_yldflag, &h->fr_ynew, &h->fr_code, &h->fr_trip}) b->release();
     for (int g = 0; g < 3; ++g) {
         h->sh_frame[g].release(); h->sh_dsl[g].release(); h->sh_ef[g].release();
         h->tr_frame[g].release(); h->tr_ef[g].release();
@@ -910,6 +941,13 @@ extern "C" int cb_end_iteration(cb_handle *h)
     return CB_OK;
 }
 
+// main.c:2105-2113: yldflag 2 (elastic unloading) -> 0 once the increment has converged
+__global__ void k_yld_reset(long n, int32_t *y)
+{
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n && y[i] == 2) y[i] = 0;
+}
+
 extern "C" int cb_commit(cb_handle *h)
 {
     if (!h) return fail(CB_ERR_ARG, "null handle");
@@ -930,6 +968,10 @@ extern "C" int cb_commit(cb_handle *h)
     bad |= d2d(h->fr_efFE[0].p, h->fr_efFE[gi].p, (size_t)FR * 14, s);
     bad |= d2d(h->fr_xfr[0].p, h->fr_xfr[1].p, (size_t)FR * 6, s);
     bad |= d2d(h->fr_ef[0].p, h->fr_ef[h->eP].p, (size_t)FR * 14, s);
+    if (h->fl.ANAFLAG == 3 && FR) {                  // unloaded ends start the next increment elastic
+        k_yld_reset<<<(unsigned)((FR * 2 + 255) / 256), 256, 0, s>>>(FR * 2, h->fr_yldflag.p);
+        ++h->launches;
+    }
     if (bad) return fail(CB_ERR_CUDA, "cb_commit: device copy failed");
     return CB_OK;
 }
@@ -1064,6 +1106,40 @@ extern "C" int cb_update_forces_dev(cb_handle *h, const double *dd_dev, double *
     CUDA_TRY(cudaEventRecord(h->ev5, s));
     std::swap(h->eP, h->eN);                      // ef_ip <- ef_i (main.c:1982-1984) by renaming
     h->forces_timed = true; h->krec_fresh = true;
+    if (h->fl.ANAFLAG == 3 && h->sz.NE_FR) {
+        // forces_fr's return code and its rescaling of dlpf (frame.c:1199-1201, 1218-1220, 1260-1268)
+        struct { int32_t first, code; double tau; } trip;
+        CUDA_TRY(cudaMemcpyAsync(&trip, h->fr_trip.p, sizeof trip, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (trip.first != 0x7fffffff) {
+            if (frcchk_fr) *frcchk_fr = trip.code;
+            if (trip.code == 1 && dlpf_inout) *dlpf_inout *= trip.tau;
+        }
+    }
+    return CB_OK;
+}
+
+extern "C" int cb_get_yldflag(cb_handle *h, int *yldflag, long n)
+{
+    if (!h) return fail(CB_ERR_ARG, "null handle");
+    if (n != h->sz.NE_FR * 2) return fail(CB_ERR_ARG, "yldflag holds 2 flags per frame");
+    if (n == 0) return CB_OK;
+    if (!yldflag) return fail(CB_ERR_ARG, "null argument");
+    cudaSetDevice(h->fl.device);
+    if (h->fl.ANAFLAG != 3 || !n) { for (long i = 0; i < n; ++i) yldflag[i] = 0; return CB_OK; }
+    CUDA_TRY(cudaMemcpyAsync(yldflag, h->fr_yldflag.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return CB_OK;
+}
+
+extern "C" int cb_set_yldflag(cb_handle *h, const int *yldflag, long n)
+{
+    if (!h || !yldflag) return fail(CB_ERR_ARG, "null argument");
+    if (n != h->sz.NE_FR * 2) return fail(CB_ERR_ARG, "yldflag holds 2 flags per frame");
+    if (h->fl.ANAFLAG != 3) return fail(CB_ERR_ARG, "yldflag exists for ANAFLAG 3 only");
+    cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaMemcpyAsync(h->fr_yldflag.p, yldflag, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     return CB_OK;
 }
 

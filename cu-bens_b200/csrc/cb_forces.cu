@@ -664,8 +664,14 @@ k_truss_forces(CbDev d, const double *__restrict__ x_temp, double *__restrict__ 
     frame_i[e * 4 + 3] = dl;
     const double E = d.tr_const[e * 4 + 0], A = d.tr_const[e * 4 + 1], L0 = d.tr_const[e * 4 + 2];
     const double strain = (dl - L0) / L0;
-    const double ef0 = E * A * (strain + 0.5 * (strain * strain)) * dl / L0;
-    const double ef1 = -ef0;
+    double ef0 = E * A * (strain + 0.5 * (strain * strain)) * dl / L0;
+    double ef1 = -ef0;
+    if (d.ANAFLAG == 3) {                   // axial force capped at the squash load (truss.c:335-347)
+        const double Py = d.tr_py[e], r = ef0 / Py;
+        if (r * r >= 1 - 1e-4) {
+            if (ef0 < 0) { ef0 = -Py; ef1 = Py; } else { ef0 = Py; ef1 = -Py; }
+        }
+    }
     ef_i[e * 2] = ef0; ef_i[e * 2 + 1] = ef1;
 #pragma unroll
     for (int m = 0; m < 3; ++m) {           // f_temp -= ef * c  (truss.c:351-375)
@@ -825,7 +831,12 @@ k_frame_forces(CbDev d, const double *__restrict__ x_new, const double *__restri
     double efl[14], fel[14], efn[14];
 #pragma unroll
     for (int i = 0; i < 14; ++i) { efl[i] = ef_ip[e * 14 + i]; fel[i] = efFE_ip[e * 14 + i]; }
-    const bool addref = (itecnt == 0);
+    // the increment of the fixed-end forces enters on the first iteration, for the ends that have
+    // not yielded (frame.c:1100-1155; yldflag is 0 throughout for ANAFLAG 1 / 2)
+    int y0 = 0, y1 = 0;
+    if (!INPLACE && d.ANAFLAG == 3) { y0 = d.fr_yldflag[e * 2]; y1 = d.fr_yldflag[e * 2 + 1]; }
+    const bool addref0 = (itecnt == 0) && y0 == 0, addref1 = (itecnt == 0) && y1 == 0;
+    double feo[14];
     // frame.c:1090-1096 then 1100-1155; with INPLACE later rows see the rows already rewritten
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
@@ -834,6 +845,7 @@ k_frame_forces(CbDev d, const double *__restrict__ x_new, const double *__restri
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int o = (g < 2) ? 3 * g : 7 + 3 * (g - 2);
+            const bool addref = (g < 2) ? addref0 : addref1;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 double v[3];
@@ -847,6 +859,7 @@ k_frame_forces(CbDev d, const double *__restrict__ x_new, const double *__restri
         }
 #pragma unroll
         for (int w = 6; w < 14; w += 7) {
+            const bool addref = (w == 6) ? addref0 : addref1;
             const double v = pass == 0 ? (cur[w] + def[w])
                                        : (addref ? (cur[w] + dlpf * d.fr_efFE_ref[e * 14 + w]) : cur[w]);
             out[w] = 0.0 + 1.0 * v;
@@ -855,8 +868,50 @@ k_frame_forces(CbDev d, const double *__restrict__ x_new, const double *__restri
 #pragma unroll
         for (int i = 0; i < 14; ++i) {
             if (pass == 0) { ef_i[e * 14 + i] = out[i]; efn[i] = out[i]; }
-            else efFE_i[e * 14 + i] = out[i];
+            else { efFE_i[e * 14 + i] = out[i]; feo[i] = out[i]; }
         }
+    }
+    if (!INPLACE && d.ANAFLAG == 3) {
+        // yield check, return to the surface, elastic unloading (frame.c:1157-1268).  The reference
+        // returns from the middle of its element loop; here every member reports what it would do
+        // and k_frame_trip keeps the flags of the members up to the first one that trips.
+        const double *pl = d.fr_plast + e * 3;
+        const double Py = pl[0], Mpy = pl[1], Mpz = pl[2];
+        double eti[14];
+#pragma unroll
+        for (int i = 0; i < 14; ++i) eti[i] = efn[i] + feo[i];
+        double p[2] = {eti[0] / Py, eti[7] / Py}, my[2] = {eti[4] / Mpy, eti[11] / Mpy};
+        double mz[2] = {eti[5] / Mpz, eti[12] / Mpz};
+        const double phi[2] = {fr_phi(p[0], my[0], mz[0]), fr_phi(p[1], my[1], mz[1])};
+        int code = 0; double tau = 1.0;
+        if (phi[0] > phi[1] && phi[0] > 1 + CB_PHITOL && y0 != 2) {
+            tau = fr_regula_falsi(eft[0] / Py, (eti[0] - eft[0]) / Py, eft[4] / Mpy, (eti[4] - eft[4]) / Mpy,
+                                  eft[5] / Mpz, (eti[5] - eft[5]) / Mpz);
+            y0 = 1; code = 1;
+        } else if (phi[1] > phi[0] && phi[1] > 1 + CB_PHITOL && y1 != 2) {
+            tau = fr_regula_falsi(eft[7] / Py, (eti[7] - eft[7]) / Py, eft[11] / Mpy, (eti[11] - eft[11]) / Mpy,
+                                  eft[12] / Mpz, (eti[12] - eft[12]) / Mpz);
+            y1 = 1; code = 1;
+        } else if ((phi[0] >= 1 - CB_PHITOL && y0 != 2) && (phi[1] >= 1 - CB_PHITOL && y1 != 2)) {
+            y0 = y1 = 1;
+        } else if (phi[0] >= 1 - CB_PHITOL && y0 != 2) {
+            y0 = 1;
+        } else if (phi[1] >= 1 - CB_PHITOL && y1 != 2) {
+            y1 = 1;
+        }
+        if (code == 0 && (y0 == 1 || y1 == 1)) {
+            for (int i = 0; i < 14; ++i)
+                for (int j = 0; j < 14; ++j) k[i][j] = 0;
+            frame_elastic(k, fc);
+            frame_geometric(k, eft, Rp[9], fc[2], fc[8]);
+            const int u = fr_unload(phi, p, my, mz, pl, k, dl);
+            if (u == 1) { y0 = y1 = 2; code = 2; }
+            else if (u == 2) { y0 = 2; code = 2; }
+            else if (u == 3) { y1 = 2; code = 2; }
+        }
+        d.fr_ynew[e * 2] = y0; d.fr_ynew[e * 2 + 1] = y1;
+        d.fr_code[e] = code; d.fr_tau[e] = tau;
+        if (code != 0) atomicMin(d.fr_trip, (int)e);
     }
     double EF[14];
     frame_Tt_apply(Ri, efn, EF);
@@ -878,6 +933,20 @@ k_frame_forces(CbDev d, const double *__restrict__ x_new, const double *__restri
 // thread per node; reproduces the reference's summation order (all trusses, frames, shells)
 // without atomics (replaces the `f_temp[mcode-1] += ...` scatters).
 // ------------------------------------------------------------------------------------------
+// ANAFLAG 3: forces_fr returns at the first member (lowest index) that overshoots the yield surface
+// or unloads, having mutated yldflag of the members before it and of that member (frame.c:1184-
+// 1268).  trip[0] = that index (INT_MAX if none).  The flags proposed by the force pass are kept
+// for the members up to it; trip[1] / fr_tau of that member go back to the host.
+__global__ void __launch_bounds__(256)
+k_frame_trip(CbDev d)
+{
+    const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (e >= d.NE_FR) return;
+    const int first = d.fr_trip[0];
+    if (e <= first) { d.fr_yldflag[e * 2] = d.fr_ynew[e * 2]; d.fr_yldflag[e * 2 + 1] = d.fr_ynew[e * 2 + 1]; }
+    if (e == first) { d.fr_trip[1] = d.fr_code[e]; reinterpret_cast<double *>(d.fr_trip + 2)[0] = d.fr_tau[e]; }
+}
+
 __global__ void __launch_bounds__(256)
 k_gather_f(CbDev d, const int32_t *__restrict__ cstart, const CbCorner *__restrict__ corners,
            double *__restrict__ f)
@@ -886,6 +955,8 @@ k_gather_f(CbDev d, const int32_t *__restrict__ cstart, const CbCorner *__restri
     if (n >= d.NJ) return;
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
     const int c0 = cstart[n], c1 = cstart[n + 1];
+    // members from the first tripping one onwards never reach the scatter in the reference
+    const int fr_end = (d.ANAFLAG == 3 && d.fr_trip) ? d.fr_trip[0] : 0x7fffffff;
     for (int c = c0; c < c1; ++c) {
         const CbCorner cr = corners[c];
         if (cr.type == CB_T_SHELL) {
@@ -893,6 +964,7 @@ k_gather_f(CbDev d, const int32_t *__restrict__ cstart, const CbCorner *__restri
 #pragma unroll
             for (int r = 0; r < 6; ++r) acc[r] += p[r];
         } else if (cr.type == CB_T_FRAME) {
+            if (cr.e >= fr_end) continue;
             const double *p = d.fr_fg + (long)cr.e * 14 + cr.b * 7;
 #pragma unroll
             for (int r = 0; r < 7; ++r) acc[r] += p[r];
@@ -926,10 +998,18 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
     }
     if (d.NE_FR) {
         unsigned g = (unsigned)((d.NE_FR + 63) / 64);
+        if (d.ANAFLAG == 3) {
+            static const int init[4] = {0x7fffffff, 0, 0, 0};
+            if (cudaMemcpyAsync(d.fr_trip, init, sizeof init, cudaMemcpyHostToDevice, s) != cudaSuccess) return 1;
+        }
         k_frame_forces<false><<<g, 64, 0, s>>>(d, a.x_temp, a.dd, a.fr_frame_ip, a.fr_frame_i,
                                                a.fr_xfr_i, a.fr_ef_ip, a.fr_ef_i, a.fr_efFE_ip,
                                                a.fr_efFE_i, a.dlpf, a.itecnt);
         ++*launches;
+        if (d.ANAFLAG == 3) {
+            k_frame_trip<<<(unsigned)((d.NE_FR + 255) / 256), 256, 0, s>>>(d);
+            ++*launches;
+        }
     }
     if (d.NE_SH) {
         unsigned g = (unsigned)((d.NE_SH + CB_TPB - 1) / CB_TPB);

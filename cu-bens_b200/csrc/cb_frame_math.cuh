@@ -160,6 +160,144 @@ __device__ __forceinline__ void frame_geometric_rcp(double (*k)[14], const doubl
 #undef CB_SUB
 }
 
+// ---- concentrated plasticity (ANAFLAG 3): yield surface of frame.c:617-621, its gradients
+// (frame.c:625-648) and the plastic reduction of the tangent, stiffm_fr frame.c:581-796.
+// The reference evaluates the powers with libm pow(); products are used here (<= 2 ulp apart).
+#define CB_PHITOL 1e-4                      // frame.c:37
+__device__ __forceinline__ double fr_phi(double p, double my, double mz)
+{
+    const double p2 = p * p, mz2 = mz * mz, my2 = my * my;
+    return p2 + mz2 + my2 * my2 + 3.5 * p2 * mz2 + 3 * (p2 * p2 * p2) * my2 + 4.5 * (mz2 * mz2) * my2;
+}
+// gradient w.r.t. (axial force, weak-axis moment, strong-axis moment) of one member end
+__device__ __forceinline__ void fr_grad(double p, double my, double mz, double Py, double Mpy,
+                                        double Mpz, double *g)
+{
+    const double p2 = p * p, mz2 = mz * mz, my2 = my * my;
+    g[0] = 2 * p / Py + 7 * p * mz2 / Py + 18 * (p2 * p2 * p) * my2 / Py;
+    g[1] = 4 * (my2 * my) / Mpy + 6 * (p2 * p2 * p2) * my / Mpy + 9 * (mz2 * mz2) * my / Mpy;
+    g[2] = 2 * mz / Mpz + 7 * p2 * mz / Mpz + 18 * (mz2 * mz) * my2 / Mpz;
+}
+
+// k <- k - kG (G^T k G)^-1 G^T k with G the yield-surface gradients of the ends on the surface.
+// pl = Py, Mpy, Mpz; y0, y1 = yldflag of the two ends.  Every index is static.
+__device__ __forceinline__ void frame_plastic(double (*k)[14], const double *eft, int y0, int y1,
+                                              const double *pl)
+{
+    const double Py = pl[0], Mpy = pl[1], Mpz = pl[2];
+    const double p0 = eft[0] / Py, p1 = eft[7] / Py, my0 = eft[4] / Mpy, my1 = eft[11] / Mpy;
+    const double mz0 = eft[5] / Mpz, mz1 = eft[12] / Mpz;
+    const double phi0 = fr_phi(p0, my0, mz0), phi1 = fr_phi(p1, my1, mz1);
+    const bool on0 = phi0 >= 1 - CB_PHITOL, on1 = phi1 >= 1 - CB_PHITOL;
+    if (on0 && on1) {
+        double g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0};
+        if (y0 != 2) fr_grad(p0, my0, mz0, Py, Mpy, Mpz, g0);
+        if (y1 != 2) fr_grad(p1, my1, mz1, Py, Mpy, Mpz, g1);
+        double kG[14][2];
+#pragma unroll
+        for (int i = 0; i < 14; ++i) {
+            kG[i][0] = k[i][0] * g0[0] + k[i][4] * g0[1] + k[i][5] * g0[2];
+            kG[i][1] = k[i][7] * g1[0] + k[i][11] * g1[1] + k[i][12] * g1[2];
+        }
+        double a00 = kG[0][0] * g0[0] + kG[4][0] * g0[1] + kG[5][0] * g0[2];
+        double a01 = kG[7][0] * g1[0] + kG[11][0] * g1[1] + kG[12][0] * g1[2];
+        double a10 = kG[0][1] * g0[0] + kG[4][1] * g0[1] + kG[5][1] * g0[2];
+        double a11 = kG[7][1] * g1[0] + kG[11][1] * g1[1] + kG[12][1] * g1[2];
+        const double det = a00 * a11 - a01 * a10, tmp = a00;
+        a00 = a11 / det; a11 = tmp / det; a01 *= -1 / det; a10 *= -1 / det;
+#pragma unroll
+        for (int i = 0; i < 14; ++i) {
+            const double w0 = kG[i][0] * a00 + kG[i][1] * a10, w1 = kG[i][0] * a01 + kG[i][1] * a11;
+#pragma unroll
+            for (int j = 0; j < 14; ++j) k[i][j] -= w0 * kG[j][0] + w1 * kG[j][1];
+        }
+    } else if (on0 && y0 != 2) {
+        double g[3], kG[14];
+        fr_grad(p0, my0, mz0, Py, Mpy, Mpz, g);
+#pragma unroll
+        for (int i = 0; i < 14; ++i) kG[i] = k[i][0] * g[0] + k[i][4] * g[1] + k[i][5] * g[2];
+        const double inv = 1 / (kG[0] * g[0] + kG[4] * g[1] + kG[5] * g[2]);
+#pragma unroll
+        for (int i = 0; i < 14; ++i) {
+            const double w = kG[i] * inv;
+#pragma unroll
+            for (int j = 0; j < 14; ++j) k[i][j] -= w * kG[j];
+        }
+    } else if (on1 && y1 != 2) {
+        double g[3], kG[14];
+        fr_grad(p1, my1, mz1, Py, Mpy, Mpz, g);
+#pragma unroll
+        for (int i = 0; i < 14; ++i) kG[i] = k[i][7] * g[0] + k[i][11] * g[1] + k[i][12] * g[2];
+        const double inv = 1 / (kG[7] * g[0] + kG[11] * g[1] + kG[12] * g[2]);
+#pragma unroll
+        for (int i = 0; i < 14; ++i) {
+            const double w = kG[i] * inv;
+#pragma unroll
+            for (int j = 0; j < 14; ++j) k[i][j] -= w * kG[j];
+        }
+    }
+}
+
+// scale of the load increment that brings a member end back onto the yield surface
+// (regula_falsi, frame.c:1397-1455; its loop condition is never true, App. B.8: one refinement)
+__device__ __forceinline__ double fr_regula_falsi(double p, double dp, double my, double dmy,
+                                                  double mz, double dmz)
+{
+    double tau_u = 1, tau_l = 0;
+    double phi_u = fr_phi(p + tau_u * dp, my + tau_u * dmy, mz + tau_u * dmz);
+    double phi_l = fr_phi(p + tau_l * dp, my + tau_l * dmy, mz + tau_l * dmz);
+    double tau_r = tau_u - (phi_u - 1) * (tau_l - tau_u) / (phi_l - phi_u);
+    double phi_r = fr_phi(p + tau_r * dp, my + tau_r * dmy, mz + tau_r * dmz);
+    if ((phi_l - 1 > 0 && phi_r - 1 > 0) || (phi_l - 1 < 0 && phi_r - 1 < 0)) { tau_l = tau_r; phi_l = phi_r; }
+    else { tau_u = tau_r; phi_u = phi_r; }
+    tau_r = tau_u - (phi_u - 1) * (tau_l - tau_u) / (phi_l - phi_u);
+    return tau_r;
+}
+
+// elastic unloading test of yielded member ends (unload, frame.c:1457-1658): sign of the plastic
+// multipliers lambda = (G^T k G)^-1 G^T k dd.  k = elastic + geometric tangent, dl = local
+// displacement increment.  Returns 0, or 1 / 2 / 3 = both ends / end 1 / end 2 unload.
+__device__ __forceinline__ int fr_unload(const double *phi, const double *p, const double *my,
+                                         const double *mz, const double *pl, double (*k)[14],
+                                         const double *dl)
+{
+    const double Py = pl[0], Mpy = pl[1], Mpz = pl[2];
+    const bool on0 = phi[0] >= 1 - CB_PHITOL, on1 = phi[1] >= 1 - CB_PHITOL;
+    if (on0 && on1) {
+        double g0[3], g1[3], Gk[2][14];
+        fr_grad(p[0], my[0], mz[0], Py, Mpy, Mpz, g0);
+        fr_grad(p[1], my[1], mz[1], Py, Mpy, Mpz, g1);
+        for (int j = 0; j < 14; ++j) {
+            Gk[0][j] = g0[0] * k[0][j] + g0[1] * k[4][j] + g0[2] * k[5][j];
+            Gk[1][j] = g1[0] * k[7][j] + g1[1] * k[11][j] + g1[2] * k[12][j];
+        }
+        double a00 = Gk[0][0] * g0[0] + Gk[0][4] * g0[1] + Gk[0][5] * g0[2];
+        double a01 = Gk[0][7] * g1[0] + Gk[0][11] * g1[1] + Gk[0][12] * g1[2];
+        double a10 = Gk[1][0] * g0[0] + Gk[1][4] * g0[1] + Gk[1][5] * g0[2];
+        double a11 = Gk[1][7] * g1[0] + Gk[1][11] * g1[1] + Gk[1][12] * g1[2];
+        const double det = a00 * a11 - a01 * a10, tmp = a00;
+        a00 = a11 / det; a11 = tmp / det; a01 *= -1 / det; a10 *= -1 / det;
+        double l0 = 0, l1 = 0;
+        for (int j = 0; j < 14; ++j) {
+            l0 += (a00 * Gk[0][j] + a01 * Gk[1][j]) * dl[j];
+            l1 += (a10 * Gk[0][j] + a11 * Gk[1][j]) * dl[j];
+        }
+        if (l0 < -1e-8 && l1 < -1e-8) return 1;
+        if (l0 < -1e-8) return 2;
+        if (l1 < -1e-8) return 3;
+    } else if (on0 || on1) {
+        const int o = on0 ? 0 : 7, e = on0 ? 0 : 1;
+        double g[3], Gk[14];
+        fr_grad(p[e], my[e], mz[e], Py, Mpy, Mpz, g);
+        for (int j = 0; j < 14; ++j) Gk[j] = g[0] * k[o][j] + g[1] * k[o + 4][j] + g[2] * k[o + 5][j];
+        const double inv = 1 / (Gk[o] * g[0] + Gk[o + 4] * g[1] + Gk[o + 5] * g[2]);
+        double lam = 0;
+        for (int j = 0; j < 14; ++j) lam += (inv * Gk[j]) * dl[j];
+        if (lam < -1e-8) return on0 ? 2 : 3;
+    }
+    return 0;
+}
+
 // Gauss-Jordan inverse without pivoting, as misc.c:284-343 behaves for SPD input (n <= 4)
 __device__ __forceinline__ void gj_inverse4(double *A, int n)
 {
@@ -220,7 +358,11 @@ __device__ __forceinline__ void frame_local_k(const CbDev &d, long e, const doub
         eftot[i] = ef_ip[e * 14 + i] + efFE_ip[e * 14 + i];
     }
     frame_elastic(k, fc);
-    if (d.ANAFLAG == 2) frame_geometric(k, eftot, defllen_ip, fc[2], fc[8]);
+    if (d.ANAFLAG >= 2) frame_geometric(k, eftot, defllen_ip, fc[2], fc[8]);
+    if (d.ANAFLAG == 3) {                            // frame.c:268-277
+        const int y0 = d.fr_yldflag[e * 2], y1 = d.fr_yldflag[e * 2 + 1];
+        if (y0 != 2 || y1 != 2) frame_plastic(k, eftot, y0, y1, d.fr_plast + e * 3);
+    }
     if (d.fr_mendrel[e * 5] == 1) frame_release(k, d.fr_mendrel + e * 5 + 1);
 }
 

@@ -158,6 +158,14 @@ struct CbDev {
     const int32_t *fr_mendrel; // [NE][5]
     const double *fr_efFE_ref; // [NE][14]
     double *fr_fg;           // [NE][14]
+    // ANAFLAG 3 (concentrated plasticity), else nullptr
+    const double *fr_plast;  // [NE][3] squash load Py, plastic moments Mpy (weak), Mpz (strong)
+    int32_t *fr_yldflag;     // [NE][2] 0 elastic, 1 on the yield surface, 2 unloading (frame.c:1184-1268)
+    int32_t *fr_ynew;        // [NE][2] flags proposed by the force pass (committed up to the first trip)
+    int32_t *fr_code;        // [NE] return code of the force pass for this member: 0, 1, 2
+    double *fr_tau;          // [NE] regula-falsi scale of dlpf when code == 1
+    int32_t *fr_trip;        // [4] lowest member index with code != 0 (INT_MAX if none), its code
+    const double *tr_py;     // [NE_TR] squash loads of the trusses
     // trusses
     const int32_t *tr_nodes; // [NE][2]
     const double *tr_const;  // [NE][CB_TR_CONST]

@@ -173,7 +173,11 @@ __device__ __noinline__ void frame_block_t(const CbStiffArgs &A, int e, double *
         eft[i] = A.fr_ef[(long)e * 14 + i] + A.fr_efFE[(long)e * 14 + i];
     }
     frame_elastic_rcp(k, fc);
-    if (A.d.ANAFLAG == 2) frame_geometric_rcp(k, eft, fr[9], fc[2], fc[8]);
+    if (A.d.ANAFLAG >= 2) frame_geometric_rcp(k, eft, fr[9], fc[2], fc[8]);
+    if (A.d.ANAFLAG == 3) {
+        const int y0 = A.d.fr_yldflag[(long)e * 2], y1 = A.d.fr_yldflag[(long)e * 2 + 1];
+        if (y0 != 2 || y1 != 2) frame_plastic(k, eft, y0, y1, A.d.fr_plast + (long)e * 3);
+    }
     double R[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = fr[i];
@@ -287,11 +291,25 @@ __device__ __noinline__ void truss_block(const CbStiffArgs &A, int e, int a, int
         gN = A.tr_ef[(long)e * 2] / dl;
     }
     const double s = (a == b) ? 1.0 : -1.0;
+    double kab = s * k;
+    if (A.d.ANAFLAG == 3) {
+        // stiffm_tr (truss.c:206-229): plastic reduction of the 2x2 axial matrix beyond the squash
+        // load; the geometric term only once the member is on the yield surface (truss.c:155-156)
+        const double Py = A.d.tr_py[e], f0 = A.tr_ef[(long)e * 2], f1 = A.tr_ef[(long)e * 2 + 1];
+        const double r2 = (f0 / Py) * (f0 / Py);
+        if (r2 > 1 + 1e-4) {
+            const double G0 = 2 * f0 / (Py * Py), G1 = 2 * f1 / (Py * Py);
+            const double kg0 = k * G0 - k * G1, kg1 = -k * G0 + k * G1;
+            const double gkg = kg0 * G0 + kg1 * G1;
+            kab -= (a == 0 ? kg0 : kg1) * (b == 0 ? kg0 : kg1) / gkg;
+        }
+        if (!(r2 >= 1 - 1e-4)) gN = 0.0;
+    }
 #pragma unroll
     for (int p = 0; p < 3; ++p)
 #pragma unroll
         for (int q = 0; q < 3; ++q)
-            blk[p * ld + q] = s * (k * c[p] * c[q] + ((p == q) ? gN : 0.0));
+            blk[p * ld + q] = kab * c[p] * c[q] + ((p == q) ? s * gN : 0.0);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -34,7 +34,7 @@ EXPORTS = [
     "cb_dev_Ap", "cb_dev_Ai", "cb_download", "cb_upload", "cb_launch_count",
     "cb_last_stiff_ms", "cb_last_forces_ms", "cb_last_assemble_ms", "cb_timer_start", "cb_timer_stop_ms", "cb_set_dd", "cb_host_alloc",
     "cb_host_free", "cb_map_bytes", "cb_sync", "cb_stream", "cb_set_q", "cb_residual_sums",
-    "cb_dev_sums", "cb_get_sums",
+    "cb_dev_sums", "cb_get_sums", "cb_get_yldflag", "cb_set_yldflag",
 ]
 
 
@@ -48,7 +48,8 @@ class cb_flags(C.Structure):
 
 _MODEL_FIELDS = ["x", "minc", "jcode", "mcode", "maxa", "emod", "dens", "carea", "llength", "c1",
                  "c2", "c3", "nu", "thick", "farea", "slength", "xlocal", "gmod", "istrong",
-                 "iweak", "ipolar", "iwarp", "auxpt", "offset", "osflag", "mendrel", "efFE_ref"]
+                 "iweak", "ipolar", "iwarp", "auxpt", "offset", "osflag", "mendrel", "efFE_ref", "yield",
+                 "zstrong", "zweak"]
 
 
 class cb_model(C.Structure):
@@ -111,7 +112,7 @@ class Assembler:
         keep = {}
         cm = cb_model()
         for n in _MODEL_FIELDS:
-            a = getattr(m, n, None)
+            a = getattr(m, "yld" if n == "yield" else n, None)
             if a is not None:
                 dt = np.int32 if n in ("osflag", "mendrel") else (np.int64 if n in ("minc", "jcode", "mcode", "maxa") else np.float64)
                 a = np.ascontiguousarray(a, dtype=dt)
@@ -182,6 +183,15 @@ class Assembler:
 
     def end_iteration(self):
         self._check(self.lib.cb_end_iteration(self.h))
+
+    def yldflag(self):
+        y = np.zeros(2 * self.m.NE_FR, dtype=np.int32)
+        self._check(self.lib.cb_get_yldflag(self.h, _p(y), C.c_long(y.size)))
+        return y
+
+    def set_yldflag(self, y):
+        y = np.ascontiguousarray(y, dtype=np.int32)
+        self._check(self.lib.cb_set_yldflag(self.h, _p(y), C.c_long(y.size)))
 
     def commit(self):
         self._check(self.lib.cb_commit(self.h))

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 1
+#define CB_ABI_VERSION 2
 
 /* status codes (the reference uses 0 = ok / 1 = error, solve.c:558-562, frame.c:1201) */
 enum {
@@ -64,8 +64,10 @@ typedef struct cb_sizes {
     long NJ, NE_TR, NE_FR, NE_SH, NE_SBR, NE_FBR, NEQ;
 } cb_sizes;
 
-/* ANAFLAG 1 = first-order elastic, 2 = geometric nonlinear (main.c:63-90).  ANAFLAG 3
- * (material nonlinear) and 4 (FSI) return CB_ERR_UNSUPPORTED from cb_create.            */
+/* ANAFLAG 1 = first-order elastic, 2 = geometric nonlinear, 3 = geometric + material nonlinear
+ * (main.c:63-90).  ANAFLAG 3 is built for trusses and frames (concentrated plasticity: stiffm_tr,
+ * stiffm_fr, yield check / regula_falsi / unload in forces_fr); with shells, and ANAFLAG 4 (FSI),
+ * cb_create returns CB_ERR_UNSUPPORTED.                                                     */
 typedef struct cb_flags {
     int ANAFLAG, ALGFLAG, SLVFLAG;
     int matrix_layout;      /* CB_MAT_*; 0 picks SKYLINE when SLVFLAG==0 else CSC          */
@@ -98,6 +100,9 @@ typedef struct cb_model {
     const int    *osflag;    /* [FR]                                                        */
     const int    *mendrel;   /* [FR*5]                                                      */
     const double *efFE_ref;  /* [FR*14] reference fixed-end forces from load()              */
+    /* material nonlinear analysis (ANAFLAG 3), may be NULL otherwise */
+    const double *yield;     /* [TR+FR+SH+BR] yield stress           truss.c:66 frame.c:177 */
+    const double *zstrong, *zweak;   /* [FR] plastic section moduli  frame.c:177            */
 } cb_model;
 
 typedef struct cb_handle cb_handle;
@@ -132,6 +137,14 @@ int  cb_update_forces_dev(cb_handle *h, const double *dd_dev, double *dlpf_inout
                           int *frcchk_fr, int *frcchk_sh);
 int  cb_forces_linear(cb_handle *h, const double *d, double *f_out);  /* main.c:1774-1793  */
 int  cb_end_iteration(cb_handle *h);                                  /* main.c:2006-2028  */
+/* ANAFLAG 3: the member-end yield flags forces_fr mutates (main.c:802, frame.c:1184-1268):
+ * 0 elastic, 1 on the yield surface, 2 unloading.  n = 2*NE_FR.  cb_update_forces reproduces the
+ * reference's early return: frcchk_fr = 1 (overshoot; *dlpf_inout rescaled by regula_falsi) or
+ * 2 (elastic unloading) comes from the lowest-numbered member that trips, the flags of the
+ * members up to and including it are updated, and - as in the reference - f_temp then lacks the
+ * members from that one on.  cb_commit resets 2 -> 0 (main.c:2105-2113).                     */
+int  cb_get_yldflag(cb_handle *h, int *yldflag, long n);
+int  cb_set_yldflag(cb_handle *h, const int *yldflag, long n);
 int  cb_commit(cb_handle *h);                                         /* main.c:2074-2134  */
 
 /* ---- results -------------------------------------------------------------------------- */

@@ -486,6 +486,14 @@ void orc_mass_sh(const orc_dims *D, double *sm, const double *dens, const double
     }
 }
 
+/* ---------------------------------------------------------- ANAFLAG 3 (material nonlinear) */
+#define PHITOL 1e-4                                    /* frame.c:37, truss.c:100 */
+static struct { const double *yield, *zstrong, *zweak; int *yldflag; } g_pl;
+void orc_set_plastic(const double *yield, const double *zstrong, const double *zweak, int *yldflag)
+{   /* the arrays main.c owns for ANAFLAG 3 (main.c:559-571, 802) */
+    g_pl.yield = yield; g_pl.zstrong = zstrong; g_pl.zweak = zweak; g_pl.yldflag = yldflag;
+}
+
 /* --------------------------------------------------------------------------------- truss.c */
 void orc_stiff_tr(const orc_dims *D, double *ss, const double *emod, const double *carea,
                   const double *llength, const double *defllen_ip, const double *c1_ip,
@@ -493,13 +501,23 @@ void orc_stiff_tr(const orc_dims *D, double *ss, const double *emod, const doubl
                   const long *mcode)
 {   /* stiff_tr, truss.c:82-204 */
     for (long n = 0; n < D->NE_TR; ++n) {
-        double k2[2][2], T[2][6], Tk[6][2], K[36];
+        double k2[2][2], T[2][6], Tk[6][2], K[36], Py = 1;
         if (D->ANAFLAG == 1) {
             k2[0][0] = k2[1][1] = emod[n] * carea[n] / llength[n];
             k2[0][1] = k2[1][0] = -(emod[n] * carea[n] / llength[n]);
         } else {
             k2[0][0] = k2[1][1] = emod[n] * carea[n] * (defllen_ip[n] * defllen_ip[n]) / pow(llength[n], 3);
             k2[0][1] = k2[1][0] = -(emod[n] * carea[n] * (defllen_ip[n] * defllen_ip[n]) / pow(llength[n], 3));
+            if (D->ANAFLAG == 3) {                      /* stiffm_tr, truss.c:206-229 */
+                Py = carea[n] * g_pl.yield[n];
+                if (pow(ef_ip[n * 2] / Py, 2) > 1 + PHITOL) {
+                    const double G[2] = {2 * ef_ip[n * 2] / pow(Py, 2), 2 * ef_ip[n * 2 + 1] / pow(Py, 2)};
+                    const double kG[2] = {k2[0][0] * G[0] + k2[0][1] * G[1], k2[1][0] * G[0] + k2[1][1] * G[1]};
+                    const double GkG = kG[0] * G[0] + kG[1] * G[1];
+                    k2[0][0] -= pow(kG[0], 2) / GkG; k2[0][1] -= kG[0] * kG[1] / GkG;
+                    k2[1][0] -= kG[1] * kG[0] / GkG; k2[1][1] -= pow(kG[1], 2) / GkG;
+                }
+            }
         }
         memset(T, 0, sizeof T);
         T[0][0] = T[1][3] = c1_ip[n]; T[0][1] = T[1][4] = c2_ip[n]; T[0][2] = T[1][5] = c3_ip[n];
@@ -515,7 +533,8 @@ void orc_stiff_tr(const orc_dims *D, double *ss, const double *emod, const doubl
                 for (int q = 0; q < 2; ++q) s += Tk[i][q] * T[q][j];
                 K[i * 6 + j] = s;
             }
-        if (D->ANAFLAG == 2) {                         /* truss.c:155-166 */
+        if (D->ANAFLAG == 2 ||                         /* truss.c:155-166 */
+            (D->ANAFLAG == 3 && pow(ef_ip[n * 2] / Py, 2) >= 1 - PHITOL)) {
             const double g = ef_ip[n * 2] / defllen_ip[n];
             for (int i = 0; i < 6; ++i) K[i * 6 + i] += g;
             for (int i = 0; i < 3; ++i) { K[i * 6 + i + 3] -= g; K[(i + 3) * 6 + i] -= g; }
@@ -544,6 +563,13 @@ void orc_forces_tr(const orc_dims *D, double *f_temp, double *ef_i, const double
             const double strain = (defllen_i[n] - llength[n]) / llength[n];
             ef_i[n * 2] = emod[n] * carea[n] * (strain + 0.5 * (strain * strain)) * defllen_i[n] / llength[n];
             ef_i[n * 2 + 1] = -ef_i[n * 2];
+            if (D->ANAFLAG == 3) {                     /* truss.c:335-347: capped at the squash load */
+                const double Py = g_pl.yield[n] * carea[n];
+                if (pow(ef_i[n * 2] / Py, 2) >= 1 - PHITOL) {
+                    if (ef_i[n * 2] < 0) { ef_i[n * 2] = -Py; ef_i[n * 2 + 1] = Py; }
+                    else { ef_i[n * 2] = Py; ef_i[n * 2 + 1] = -Py; }
+                }
+            }
         }
         for (int j = 0; j < 6; ++j)
             if (mc[j] != 0) f_temp[mc[j] - 1] -= ef_i[n * 2 + j / 3] * c[j % 3];
@@ -667,6 +693,143 @@ static void frame_release(double k[14][14], const int *rel4)
         }
 }
 
+static double fr_phi(double p, double my, double mz)
+{   /* yield function, frame.c:617-621 */
+    return pow(p, 2) + pow(mz, 2) + pow(my, 4) + 3.5 * pow(p, 2) * pow(mz, 2) +
+           3 * pow(p, 6) * pow(my, 2) + 4.5 * pow(mz, 4) * pow(my, 2);
+}
+
+static void fr_grad(double p, double my, double mz, double Py, double Mpy, double Mpz, double *g)
+{   /* yield-surface gradients w.r.t. axial force, weak- and strong-axis moment, frame.c:625-648 */
+    g[0] = 2 * p / Py + 7 * p * pow(mz, 2) / Py + 18 * pow(p, 5) * pow(my, 2) / Py;
+    g[1] = 4 * pow(my, 3) / Mpy + 6 * pow(p, 6) * my / Mpy + 9 * pow(mz, 4) * my / Mpy;
+    g[2] = 2 * mz / Mpz + 7 * pow(p, 2) * mz / Mpz + 18 * pow(mz, 3) * pow(my, 2) / Mpz;
+}
+
+static void frame_plastic(double k[14][14], const double *eft, const int *yld, double Py, double Mpy,
+                          double Mpz)
+{   /* stiffm_fr, frame.c:581-796: k -= kG (G^T k G)^-1 G^T k */
+    const double p[2] = {eft[0] / Py, eft[7] / Py}, my[2] = {eft[4] / Mpy, eft[11] / Mpy};
+    const double mz[2] = {eft[5] / Mpz, eft[12] / Mpz};
+    const double phi[2] = {fr_phi(p[0], my[0], mz[0]), fr_phi(p[1], my[1], mz[1])};
+    double G[14][2], kG[14][2], A[2][2], W[14][2];
+    memset(G, 0, sizeof G);
+    int nc;
+    if (phi[0] >= 1 - PHITOL && phi[1] >= 1 - PHITOL) {
+        double g[3];
+        if (yld[0] != 2) { fr_grad(p[0], my[0], mz[0], Py, Mpy, Mpz, g); G[0][0] = g[0]; G[4][0] = g[1]; G[5][0] = g[2]; }
+        if (yld[1] != 2) { fr_grad(p[1], my[1], mz[1], Py, Mpy, Mpz, g); G[7][1] = g[0]; G[11][1] = g[1]; G[12][1] = g[2]; }
+        nc = 2;
+    } else if (phi[0] >= 1 - PHITOL && yld[0] != 2) {
+        double g[3];
+        fr_grad(p[0], my[0], mz[0], Py, Mpy, Mpz, g); G[0][0] = g[0]; G[4][0] = g[1]; G[5][0] = g[2];
+        nc = 1;
+    } else if (phi[1] >= 1 - PHITOL && yld[1] != 2) {
+        double g[3];
+        fr_grad(p[1], my[1], mz[1], Py, Mpy, Mpz, g); G[7][0] = g[0]; G[11][0] = g[1]; G[12][0] = g[2];
+        nc = 1;
+    } else return;
+    for (int i = 0; i < 14; ++i)
+        for (int j = 0; j < nc; ++j) {
+            double s = 0;
+            for (int q = 0; q < 14; ++q) s += k[i][q] * G[q][j];
+            kG[i][j] = s;
+        }
+    for (int i = 0; i < nc; ++i)
+        for (int j = 0; j < nc; ++j) {
+            double s = 0;
+            for (int q = 0; q < 14; ++q) s += kG[q][i] * G[q][j];
+            A[i][j] = s;
+        }
+    if (nc == 2) {
+        const double det = A[0][0] * A[1][1] - A[0][1] * A[1][0], t = A[0][0];
+        A[0][0] = A[1][1] / det; A[1][1] = t / det; A[0][1] *= -1 / det; A[1][0] *= -1 / det;
+        for (int i = 0; i < 14; ++i)
+            for (int j = 0; j < 2; ++j) {
+                double s = 0;
+                for (int q = 0; q < 2; ++q) s += kG[i][q] * A[q][j];
+                W[i][j] = s;
+            }
+        for (int i = 0; i < 14; ++i)
+            for (int j = 0; j < 14; ++j) {
+                double s = 0;
+                for (int q = 0; q < 2; ++q) s += W[i][q] * kG[j][q];
+                k[i][j] -= s;
+            }
+    } else {
+        A[0][0] = 1 / A[0][0];
+        for (int i = 0; i < 14; ++i) W[i][0] = kG[i][0] * A[0][0];
+        for (int i = 0; i < 14; ++i)
+            for (int j = 0; j < 14; ++j) k[i][j] -= W[i][0] * kG[j][0];
+    }
+}
+
+static double regula_falsi(double p, double dp, double my, double dmy, double mz, double dmz)
+{   /* frame.c:1397-1455.  The loop condition (phi_r <= 1-tol && phi_r >= 1+tol) is never true:
+     * exactly one refinement of the secant estimate is made. */
+    double tau_u = 1, tau_l = 0;
+    double phi_u = fr_phi(p + tau_u * dp, my + tau_u * dmy, mz + tau_u * dmz);
+    double phi_l = fr_phi(p + tau_l * dp, my + tau_l * dmy, mz + tau_l * dmz);
+    double tau_r = tau_u - (phi_u - 1) * (tau_l - tau_u) / (phi_l - phi_u);
+    double phi_r = fr_phi(p + tau_r * dp, my + tau_r * dmy, mz + tau_r * dmz);
+    if ((phi_l - 1 > 0 && phi_r - 1 > 0) || (phi_l - 1 < 0 && phi_r - 1 < 0)) { tau_l = tau_r; phi_l = phi_r; }
+    else { tau_u = tau_r; phi_u = phi_r; }
+    return tau_u - (phi_u - 1) * (tau_l - tau_u) / (phi_l - phi_u);
+}
+
+static int frame_unload(const double *phi, const double *p, const double *my, const double *mz,
+                        double Py, double Mpy, double Mpz, double k[14][14], const double *dl)
+{   /* unload, frame.c:1457-1658: sign of the plastic multipliers (G^T k G)^-1 G^T k dd */
+    double G[14][2], Gk[2][14], A[2][2], g[3];
+    memset(G, 0, sizeof G);
+    int nc, code1;
+    if (phi[0] >= 1 - PHITOL && phi[1] >= 1 - PHITOL) {
+        fr_grad(p[0], my[0], mz[0], Py, Mpy, Mpz, g); G[0][0] = g[0]; G[4][0] = g[1]; G[5][0] = g[2];
+        fr_grad(p[1], my[1], mz[1], Py, Mpy, Mpz, g); G[7][1] = g[0]; G[11][1] = g[1]; G[12][1] = g[2];
+        nc = 2; code1 = 0;
+    } else if (phi[0] >= 1 - PHITOL) {
+        fr_grad(p[0], my[0], mz[0], Py, Mpy, Mpz, g); G[0][0] = g[0]; G[4][0] = g[1]; G[5][0] = g[2];
+        nc = 1; code1 = 2;
+    } else if (phi[1] >= 1 - PHITOL) {
+        fr_grad(p[1], my[1], mz[1], Py, Mpy, Mpz, g); G[7][0] = g[0]; G[11][0] = g[1]; G[12][0] = g[2];
+        nc = 1; code1 = 3;
+    } else return 0;
+    for (int i = 0; i < nc; ++i)
+        for (int j = 0; j < 14; ++j) {
+            double s = 0;
+            for (int q = 0; q < 14; ++q) s += G[q][i] * k[q][j];
+            Gk[i][j] = s;
+        }
+    for (int i = 0; i < nc; ++i)
+        for (int j = 0; j < nc; ++j) {
+            double s = 0;
+            for (int q = 0; q < 14; ++q) s += Gk[i][q] * G[q][j];
+            A[i][j] = s;
+        }
+    if (nc == 2) {
+        double lam[2];
+        const double det = A[0][0] * A[1][1] - A[0][1] * A[1][0], t = A[0][0];
+        A[0][0] = A[1][1] / det; A[1][1] = t / det; A[0][1] *= -1 / det; A[1][0] *= -1 / det;
+        for (int i = 0; i < 2; ++i) {
+            double s = 0;
+            for (int j = 0; j < 14; ++j) {
+                double w = 0;
+                for (int q = 0; q < 2; ++q) w += A[i][q] * Gk[q][j];
+                s += w * dl[j];
+            }
+            lam[i] = s;
+        }
+        if (lam[0] < -1e-8 && lam[1] < -1e-8) return 1;
+        if (lam[0] < -1e-8) return 2;
+        if (lam[1] < -1e-8) return 3;
+        return 0;
+    }
+    A[0][0] = 1 / A[0][0];
+    double s = 0;
+    for (int j = 0; j < 14; ++j) s += (A[0][0] * Gk[0][j]) * dl[j];
+    return (s < -1e-8) ? code1 : 0;
+}
+
 static void frame_T(double T[14][14], const double *c1, const double *c2, const double *c3)
 {   /* frame.c:286-295 */
     static const int b0[4] = {0, 3, 7, 10};
@@ -699,7 +862,11 @@ static void frame_local_k(const orc_dims *D, long n, double k[14][14], double *e
     for (int i = 0; i < 14; ++i) eftot[i] = ef_ip[2 * T0 + n * 14 + i] + efFE_ip[n * 14 + i];
     frame_elastic(k, emod[T0 + n], gmod[n], carea[T0 + n], llength[T0 + n], istrong[n], iweak[n],
                   ipolar[n], iwarp[n]);
-    if (D->ANAFLAG == 2) frame_geometric(k, eftot, defllen_ip[T0 + n], carea[T0 + n], ipolar[n]);
+    if (D->ANAFLAG == 2 || D->ANAFLAG == 3)
+        frame_geometric(k, eftot, defllen_ip[T0 + n], carea[T0 + n], ipolar[n]);
+    if (D->ANAFLAG == 3 && (g_pl.yldflag[n * 2] != 2 || g_pl.yldflag[n * 2 + 1] != 2))   /* frame.c:268-277 */
+        frame_plastic(k, eftot, g_pl.yldflag + n * 2, carea[T0 + n] * g_pl.yield[T0 + n],
+                      g_pl.zweak[n] * g_pl.yield[T0 + n], g_pl.zstrong[n] * g_pl.yield[T0 + n]);
     if (mendrel[n * 5] == 1) frame_release(k, mendrel + n * 5 + 1);
 }
 
@@ -728,15 +895,15 @@ void orc_stiff_fr(const orc_dims *D, double *ss, const double *emod, const doubl
     }
 }
 
-void orc_forces_fr(const orc_dims *D, double *f_temp, const double *ef_ip, double *ef_i,
+int orc_forces_fr(const orc_dims *D, double *f_temp, const double *ef_ip, double *ef_i,
                    const double *efFE_ref, const double *efFE_ip, double *efFE_i, const double *dd,
                    const double *emod, const double *gmod, const double *carea, const double *offset,
                    const int *osflag, const double *llength, const double *defllen_ip,
                    const double *istrong, const double *iweak, const double *ipolar,
                    const double *iwarp, const double *c1_ip, const double *c2_ip, const double *c3_ip,
                    const double *c1_i, const double *c2_i, const double *c3_i, const int *mendrel,
-                   const long *mcode, double dlpf, int itecnt)
-{   /* forces_fr, frame.c:902-1312, ANAFLAG 1 / 2 (yldflag == 0 throughout).  ef_ip / ef_i and
+                   const long *mcode, double *pdlpf, int itecnt)
+{   /* forces_fr, frame.c:902-1312 (ANAFLAG 3: yldflag etc. from orc_set_plastic).  ef_ip / ef_i and
      * efFE_ip / efFE_i may alias, as in the linear call of main.c:1782 - rows are then updated in
      * place exactly like the reference does. */
     const long T0 = D->NE_TR;
@@ -772,12 +939,52 @@ void orc_forces_fr(const orc_dims *D, double *f_temp, const double *ef_ip, doubl
             for (int j = 0; j < 14; ++j) s += M[i][j] * (efp[j] + def[j]);
             efi[i] = s;
         }
-        for (int i = 0; i < 14; ++i) {                 /* frame.c:1100-1155 with yldflag == 0 */
+        const int *yld = (D->ANAFLAG == 3) ? g_pl.yldflag + n * 2 : NULL;
+        double eti[14];
+        for (int i = 0; i < 14; ++i) {                 /* frame.c:1100-1155 */
+            const int yend = yld ? yld[i / 7] : 0;      /* an end that has yielded takes no increment */
+            const double dlpf = *pdlpf;
             double s = 0;
             for (int j = 0; j < 14; ++j)
-                s += M[i][j] * ((itecnt == 0) ? (efFE_ip[n * 14 + j] + dlpf * efFE_ref[n * 14 + j])
-                                              : efFE_ip[n * 14 + j]);
+                s += M[i][j] * ((itecnt == 0 && yend == 0) ? (efFE_ip[n * 14 + j] + dlpf * efFE_ref[n * 14 + j])
+                                                           : efFE_ip[n * 14 + j]);
             efFE_i[n * 14 + i] = s;
+            eti[i] = efi[i] + s;
+        }
+        if (D->ANAFLAG == 3) {                         /* frame.c:1157-1268 */
+            int *y = g_pl.yldflag + n * 2;
+            const double Py = carea[T0 + n] * g_pl.yield[T0 + n], Mpy = g_pl.zweak[n] * g_pl.yield[T0 + n],
+                         Mpz = g_pl.zstrong[n] * g_pl.yield[T0 + n];
+            const double p[2] = {eti[0] / Py, eti[7] / Py}, my[2] = {eti[4] / Mpy, eti[11] / Mpy};
+            const double mz[2] = {eti[5] / Mpz, eti[12] / Mpz};
+            const double phi[2] = {fr_phi(p[0], my[0], mz[0]), fr_phi(p[1], my[1], mz[1])};
+            if (phi[0] > phi[1] && phi[0] > 1 + PHITOL && y[0] != 2) {
+                *pdlpf *= regula_falsi(eft[0] / Py, (eti[0] - eft[0]) / Py, eft[4] / Mpy, (eti[4] - eft[4]) / Mpy,
+                                       eft[5] / Mpz, (eti[5] - eft[5]) / Mpz);
+                y[0] = 1;
+                return 1;
+            } else if (phi[1] > phi[0] && phi[1] > 1 + PHITOL && y[1] != 2) {
+                *pdlpf *= regula_falsi(eft[7] / Py, (eti[7] - eft[7]) / Py, eft[11] / Mpy, (eti[11] - eft[11]) / Mpy,
+                                       eft[12] / Mpz, (eti[12] - eft[12]) / Mpz);
+                y[1] = 1;
+                return 1;
+            } else if ((phi[0] >= 1 - PHITOL && y[0] != 2) && (phi[1] >= 1 - PHITOL && y[1] != 2)) {
+                y[0] = y[1] = 1;
+            } else if (phi[0] >= 1 - PHITOL && y[0] != 2) {
+                y[0] = 1;
+            } else if (phi[1] >= 1 - PHITOL && y[1] != 2) {
+                y[1] = 1;
+            }
+            if (y[0] == 1 || y[1] == 1) {
+                memset(k, 0, sizeof k);
+                frame_elastic(k, emod[T0 + n], gmod[n], carea[T0 + n], llength[T0 + n], istrong[n], iweak[n],
+                              ipolar[n], iwarp[n]);
+                frame_geometric(k, eft, defllen_ip[T0 + n], carea[T0 + n], ipolar[n]);
+                const int u = frame_unload(phi, p, my, mz, Py, Mpy, Mpz, k, dl);
+                if (u == 1) { y[0] = y[1] = 2; return 2; }
+                if (u == 2) { y[0] = 2; return 2; }
+                if (u == 3) { y[1] = 2; return 2; }
+            }
         }
         for (int i = 0; i < 14; ++i) {                 /* frame.c:1273-1309 */
             double s = 0;
@@ -793,6 +1000,7 @@ void orc_forces_fr(const orc_dims *D, double *f_temp, const double *ef_ip, doubl
             if (mc[i] != 0) f_temp[mc[i] - 1] += s;
         }
     }
+    return 0;
 }
 
 void orc_mass_fr(const orc_dims *D, double *sm, const double *carea, double *llength, const double *dens,

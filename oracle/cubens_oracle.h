@@ -51,6 +51,10 @@ void orc_shell_element_K(const orc_dims *D, long n, double *K18, const double *e
                          const double *c1_ip, const double *c2_ip, const double *c3_ip,
                          const long *minc);
 
+/* ANAFLAG 3: the material arrays main.c owns (yield [TR+FR+SH+BR], zstrong / zweak [FR]) and the
+ * member-end flags yldflag [FR*2] that forces_fr mutates; read by the truss and frame routines */
+void orc_set_plastic(const double *yield, const double *zstrong, const double *zweak, int *yldflag);
+
 /* truss.c */
 void orc_stiff_tr(const orc_dims *D, double *ss, const double *emod, const double *carea,
                   const double *llength, const double *defllen_ip, const double *c1_ip,
@@ -69,14 +73,15 @@ void orc_stiff_fr(const orc_dims *D, double *ss, const double *emod, const doubl
                   const double *ipolar, const double *iwarp, const double *c1_ip, const double *c2_ip,
                   const double *c3_ip, const double *ef_ip, const double *efFE_ip, const int *mendrel,
                   const long *maxa, const long *mcode);
-void orc_forces_fr(const orc_dims *D, double *f_temp, const double *ef_ip, double *ef_i,
+/* returns forces_fr's code: 0, 1 (yield surface overshot, *dlpf rescaled), 2 (elastic unloading) */
+int  orc_forces_fr(const orc_dims *D, double *f_temp, const double *ef_ip, double *ef_i,
                    const double *efFE_ref, const double *efFE_ip, double *efFE_i, const double *dd,
                    const double *emod, const double *gmod, const double *carea, const double *offset,
                    const int *osflag, const double *llength, const double *defllen_ip,
                    const double *istrong, const double *iweak, const double *ipolar,
                    const double *iwarp, const double *c1_ip, const double *c2_ip, const double *c3_ip,
                    const double *c1_i, const double *c2_i, const double *c3_i, const int *mendrel,
-                   const long *mcode, double dlpf, int itecnt);
+                   const long *mcode, double *dlpf, int itecnt);
 void orc_mass_fr(const orc_dims *D, double *sm, const double *carea, double *llength, const double *dens,
                  const int *osflag, const double *offset, const double *x, double *xfr,
                  const long *minc, const long *mcode);

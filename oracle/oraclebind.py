@@ -45,9 +45,15 @@ def _gen(s, gen):
     return (s.c1, s.c2, s.c3, s.ef, s.defllen, s.deffarea, s.efFE, s.x)
 
 
+def _plastic(l, m, s):
+    if m.ANAFLAG == 3:
+        l.orc_set_plastic(P(m.yld), P(m.zstrong), P(m.zweak), P(s.yldflag))
+
+
 def stiff(m, s, SLVFLAG=None, gen="ip"):
     slv = m.SLVFLAG if SLVFLAG is None else SLVFLAG
     l = lib(); D = dims(m, SLVFLAG=slv)
+    _plastic(l, m, s)
     ss = np.zeros(m.lss if slv == 0 else m.NEQ * m.NEQ)
     c1, c2, c3, ef, dl, dfa, efFE, x = _gen(s, gen)
     if m.NE_TR:
@@ -80,6 +86,9 @@ def shell_element_K(m, s, n, gen="ip"):
 
 def update_forces(m, s, dd, dlpf=1.0, itecnt=0):
     l = lib(); D = dims(m)
+    _plastic(l, m, s)
+    fr = 0
+    cdl = C.c_double(dlpf)
     dd = np.ascontiguousarray(dd, dtype=np.float64)
     s.d_temp += dd
     s.f_temp[:] = 0
@@ -90,11 +99,11 @@ def update_forces(m, s, dd, dlpf=1.0, itecnt=0):
         l.orc_forces_tr(C.byref(D), P(s.f_temp), P(s.ef_i), P(s.d), P(m.emod), P(m.carea),
                         P(s.llength), P(s.defllen_i), P(s.c1_i), P(s.c2_i), P(s.c3_i), P(m.mcode))
     if m.NE_FR:
-        l.orc_forces_fr(C.byref(D), P(s.f_temp), P(s.ef_ip), P(s.ef_i), P(m.efFE_ref), P(s.efFE_ip),
+        fr = l.orc_forces_fr(C.byref(D), P(s.f_temp), P(s.ef_ip), P(s.ef_i), P(m.efFE_ref), P(s.efFE_ip),
                         P(s.efFE_i), P(dd), P(m.emod), P(m.gmod), P(m.carea), P(m.offset),
                         P(m.osflag), P(s.llength), P(s.defllen_ip), P(m.istrong), P(m.iweak),
                         P(m.ipolar), P(m.iwarp), P(s.c1_ip), P(s.c2_ip), P(s.c3_ip), P(s.c1_i),
-                        P(s.c2_i), P(s.c3_i), P(m.mendrel), P(m.mcode), C.c_double(dlpf),
+                        P(s.c2_i), P(s.c3_i), P(m.mendrel), P(m.mcode), C.byref(cdl),
                         C.c_int(itecnt))
     if m.NE_SH:
         l.orc_forces_sh(C.byref(D), P(s.f_temp), P(s.ef_ip), P(s.ef_i), P(dd), P(s.d_temp),
@@ -102,7 +111,7 @@ def update_forces(m, s, dd, dlpf=1.0, itecnt=0):
                         P(s.slength), P(s.c1_ip), P(s.c2_ip), P(s.c3_ip), P(s.c1_i), P(s.c2_i),
                         P(s.c3_i), P(m.minc), P(m.mcode))
     s.ef_ip[:] = s.ef_i
-    return 0, 0, dlpf
+    return fr, 0, cdl.value
 
 
 def forces_linear(m, s, d, dlpf=0.0):
@@ -117,7 +126,7 @@ def forces_linear(m, s, d, dlpf=0.0):
                         P(m.emod), P(m.gmod), P(m.carea), P(m.offset), P(m.osflag), P(s.llength),
                         P(s.defllen), P(m.istrong), P(m.iweak), P(m.ipolar), P(m.iwarp), P(s.c1),
                         P(s.c2), P(s.c3), P(s.c1), P(s.c2), P(s.c3), P(m.mendrel), P(m.mcode),
-                        C.c_double(dlpf), C.c_int(0))
+                        C.byref(C.c_double(dlpf)), C.c_int(0))
     if m.NE_SH:
         l.orc_forces_sh(C.byref(D), P(f), P(s.ef), P(s.ef), P(d), P(d), P(s.x), P(m.emod), P(m.nu),
                         P(m.xlocal), P(m.thick), P(s.farea), P(s.slength), P(s.c1), P(s.c2),

@@ -33,6 +33,8 @@ def cases():
         "lattice_3": ("lattice_model", dict(n=3), "fe"),
         "lattice_3_offsets_releases": ("lattice_model", dict(n=3), "offrel"),
         "lattice_lin_3": ("lattice_model", dict(n=3, ANAFLAG=1), None),
+        "lattice_3_plastic": ("lattice_model", dict(n=3, ANAFLAG=3, load=200.0), "fe"),
+        "truss_3_plastic": ("truss_model", dict(n=3, ANAFLAG=3, load=50.0), None),
         "brick_2x2x2": ("brick_model", dict(nx=2, ny=2, nz=2, distort=0.1), None),
         "brick_skin_2x2x1": ("brick_model", dict(nx=2, ny=2, nz=1, distort=0.05, skin=True), None),
     }
@@ -76,6 +78,8 @@ def record(name, B=R, n_iter=3):
         out["f_lin"] = B.forces_linear(m, s, d)
         out["ef_lin"] = s.ef.copy()
         return m, out
+    if m.ANAFLAG == 3:
+        return m, record_plastic(m, s, out, B)
     s.begin_increment()
     for it in range(n_iter):
         out[f"K_sky_{it}"] = B.stiff(m, s, SLVFLAG=0)
@@ -92,6 +96,41 @@ def record(name, B=R, n_iter=3):
     s.commit()
     out["mass"] = B.mass(m, s, SLVFLAG=0) if B is R else B.mass(m, s)
     return m, out
+
+
+PLASTIC_STEPS = [0.004] * 3 + [-0.0003] * 3 + [0.002] * 2 + [-0.004] * 2
+
+
+def record_plastic(m, s, out, B):
+    """material-nonlinear walk (ANAFLAG 3): displacement increments steps[k] * base; after forces_fr
+    returns 1 (yield surface overshot) the increment is retried scaled by the factor it left in
+    dlpf, after 2 (elastic unloading) it is repeated - from the committed state, as
+    main.c:2030-2063 does.  Every call's K_t, f_temp, ef_i, return code, dlpf and yldflag are kept."""
+    base = np.random.default_rng(11).uniform(-1.0, 1.0, size=m.NEQ)
+    steps = PLASTIC_STEPS if m.NE_FR else [0.3, 0.2, -0.4, 0.1]
+    out["base"] = base; out["steps"] = np.array(steps)
+    s.begin_increment()
+    k, scale, call = 0, 1.0, 0
+    while k < len(steps) and call < 80:
+        dd = steps[k] * scale * base
+        out[f"K_sky_{call}"] = B.stiff(m, s, SLVFLAG=0)
+        fr, _, dl = B.update_forces(m, s, dd, dlpf=1.0, itecnt=0)
+        out[f"dd_{call}"] = dd; out[f"f_{call}"] = s.f_temp.copy()
+        out[f"ret_{call}"] = np.array([fr, dl]); out[f"yld_{call}"] = s.yldflag.copy()
+        if fr == 0:
+            out[f"ef_{call}"] = s.ef_i.copy()
+            if m.NE_FR:
+                out[f"efFE_{call}"] = s.efFE_i.copy()
+        call += 1
+        if fr != 0:
+            if fr == 1:
+                scale *= dl
+            s.begin_increment()
+            continue
+        s.end_iteration(); s.commit(); s.begin_increment()
+        k += 1; scale = 1.0
+    out["ncalls"] = call
+    return out
 
 
 DECKS = "/root/reference/Sample_Input_Files/"

@@ -119,6 +119,9 @@ struct cb_handle {
     DevBuf<double> sh_const, sh_keb, sh_kebc, sh_der, sh_Nm, sh_fg, sh_dens;
     long ncontrib = 0;
     DevBuf<double> sh_frame[3], sh_dsl[3], sh_ef[3];   // 0 = committed, 1/2 = iterate ping-pong
+    // ANAFLAG 3: yield stress, chi/efN/efM [NE][21] (0 = committed, 1 = *_temp), stiffness-pass data
+    DevBuf<double> sh_yield, sh_pl[2], sh_kpl;
+    DevBuf<int32_t> sh_yv, sh_trip;
     // trusses
     DevBuf<int32_t> tr_nodes;
     DevBuf<double> tr_const, tr_fg, tr_dens;
@@ -172,6 +175,8 @@ static CbDev make_dev(cb_handle *h)
     d.fr_osflag = h->fr_osflag.p; d.fr_mendrel = h->fr_mendrel.p;
     d.fr_efFE_ref = h->fr_efFE_ref.p; d.fr_fg = h->fr_fg.p;
     d.fr_plast = h->fr_plast.p; d.fr_yldflag = h->fr_yldflag.p; d.fr_ynew = h->fr_ynew.p;
+    d.sh_yield = h->sh_yield.p; d.sh_pl = h->sh_pl[1].p; d.sh_yv = h->sh_yv.p; d.sh_kpl = h->sh_kpl.p;
+    d.sh_trip = h->sh_trip.p;
     d.fr_code = h->fr_code.p; d.fr_tau = h->fr_tau.p; d.fr_trip = h->fr_trip.p; d.tr_py = h->tr_py.p;
     d.tr_nodes = h->tr_nodes.p; d.tr_const = h->tr_const.p; d.tr_fg = h->tr_fg.p;
     d.br_nodes = h->br_nodes.p; d.br_const = h->br_const.p;
@@ -196,10 +201,7 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
         return fail(CB_ERR_UNSUPPORTED, "ANAFLAG=%d: 1 (elastic), 2 (geometric nonlinear) and 3 "
                     "(material nonlinear, trusses and frames) are built; 4 (FSI) is listed in "
                     "DESIGN.md", fl->ANAFLAG);
-    if (fl->ANAFLAG == 3 && sz->NE_SH)
-        return fail(CB_ERR_UNSUPPORTED, "ANAFLAG=3 with shells: the Ivanov-yield shell path "
-                    "(shell.c:842-1503, 1786-2325) is not built yet (DESIGN.md section 7)");
-    if (fl->ANAFLAG == 3 && (sz->NE_TR || sz->NE_FR) && !m->yield)
+    if (fl->ANAFLAG == 3 && (sz->NE_TR || sz->NE_FR || sz->NE_SH) && !m->yield)
         return fail(CB_ERR_ARG, "ANAFLAG=3 needs the yield stresses");
     if (fl->ANAFLAG == 3 && sz->NE_FR && (!m->zstrong || !m->zweak))
         return fail(CB_ERR_ARG, "ANAFLAG=3 needs the plastic section moduli zstrong / zweak");
@@ -431,6 +433,16 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
                 BAIL(CB_ERR_CUDA);
             cudaMemset(h->sh_ef[g].p, 0, (size_t)SH * 18 * sizeof(double));
         }
+        if (fl->ANAFLAG == 3) {
+            std::vector<double> fy(m->yield + pe, m->yield + pe + SH);
+            if (h->sh_yield.upload(fy) || h->sh_pl[0].alloc((size_t)SH * 21) || h->sh_pl[1].alloc((size_t)SH * 21) ||
+                h->sh_kpl.alloc((size_t)SH * 324) || h->sh_yv.alloc(SH) || h->sh_trip.alloc(4))
+                BAIL(CB_ERR_CUDA);
+            cudaMemset(h->sh_pl[0].p, 0, (size_t)SH * 21 * sizeof(double));     // main.c:1703-1712
+            cudaMemset(h->sh_pl[1].p, 0, (size_t)SH * 21 * sizeof(double));
+            cudaMemset(h->sh_yv.p, 0, (size_t)SH * sizeof(int32_t));
+            cudaMemset(h->sh_trip.p, 0, 4 * sizeof(int32_t));
+        }
     }
     CUDA_TRY(cudaDeviceSynchronize());
     *out = h;
@@ -449,7 +461,9 @@ extern "C" void cb_destroy(cb_handle *h)
                               &h->fr_offset, &h->fr_efFE_ref, &h->fr_fg, &h->fr_dens, &h->br_const,
                               &h->Ax, &h->ss, &h->fr_plast, &h->fr_tau, &h->tr_py})
         b->release();
-    for (DevBuf<int32_t> *b : {&h->fr_yldflag, &h->fr_ynew, &h->fr_code, &h->fr_trip}) b->release();
+    for (DevBuf<int32_t> *b : {&h->fr_yldflag, &h->fr_ynew, &h->fr_code, &h->fr_trip, &h->sh_yv, &h->sh_trip})
+        b->release();
+    h->sh_yield.release(); h->sh_pl[0].release(); h->sh_pl[1].release(); h->sh_kpl.release();
     for (int g = 0; g < 3; ++g) {
         h->sh_frame[g].release(); h->sh_dsl[g].release(); h->sh_ef[g].release();
         h->tr_frame[g].release(); h->tr_ef[g].release();
@@ -691,7 +705,7 @@ static int build_plan(cb_handle *h)
     std::vector<CbTile2> tiles2; std::vector<CbWork> works; std::vector<CbTPair> tp2;
     std::vector<int32_t> telems;
     bool plan2_ok = tiles_ok && h->sz.NE_SH && !h->sz.NE_TR && !h->sz.NE_FR && !h->NE_BR &&
-                    h->max_dof == 6 && !h->mixed;
+                    h->max_dof == 6 && !h->mixed && h->fl.ANAFLAG != 3;   // yielded shells: general kernel
     if (plan2_ok) {
         CbTile2 cur{}; bool open2 = false;
         std::vector<int32_t> curel;               // distinct shells of the open tile
@@ -929,6 +943,7 @@ extern "C" int cb_begin_increment(cb_handle *h)
     bad |= d2d(h->fr_ef[h->eP].p, h->fr_ef[0].p, (size_t)FR * 14, s);
     bad |= d2d(h->sh_ef[h->eP].p, h->sh_ef[0].p, (size_t)SH * 18, s);
     bad |= d2d(h->tr_ef[h->eP].p, h->tr_ef[0].p, (size_t)TR * 2, s);
+    if (h->fl.ANAFLAG == 3) bad |= d2d(h->sh_pl[1].p, h->sh_pl[0].p, (size_t)SH * 21, s);   // chi, efN, efM
     h->i_is_ip = true; h->krec_fresh = false;
     if (bad) return fail(CB_ERR_CUDA, "cb_begin_increment: device copy failed");
     return CB_OK;
@@ -968,6 +983,7 @@ extern "C" int cb_commit(cb_handle *h)
     bad |= d2d(h->fr_efFE[0].p, h->fr_efFE[gi].p, (size_t)FR * 14, s);
     bad |= d2d(h->fr_xfr[0].p, h->fr_xfr[1].p, (size_t)FR * 6, s);
     bad |= d2d(h->fr_ef[0].p, h->fr_ef[h->eP].p, (size_t)FR * 14, s);
+    if (h->fl.ANAFLAG == 3) bad |= d2d(h->sh_pl[0].p, h->sh_pl[1].p, (size_t)SH * 21, s);
     if (h->fl.ANAFLAG == 3 && FR) {                  // unloaded ends start the next increment elastic
         k_yld_reset<<<(unsigned)((FR * 2 + 255) / 256), 256, 0, s>>>(FR * 2, h->fr_yldflag.p);
         ++h->launches;
@@ -999,6 +1015,13 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
         if (cbk_shell_prep(a.d, a.x, a.sh_frame, h->stream)) return fail(CB_ERR_CUDA, "prep launch");
         ++h->launches;
         h->krec_fresh = (gen != CB_GEN_COMMITTED) && h->i_is_ip;
+    }
+    if (h->fl.ANAFLAG == 3 && h->sz.NE_SH) {          // yield check + stiffm_sh (shell.c:171-262)
+        const int gd = (gen == CB_GEN_COMMITTED) ? 0 : h->gP;
+        if (cbk_shell_plastic_prep(a.d, h->sh_frame[gd].p, h->sh_dsl[gd].p,
+                                   h->sh_pl[gen == CB_GEN_COMMITTED ? 0 : 1].p, h->stream))
+            return fail(CB_ERR_CUDA, "plastic prep launch");
+        ++h->launches;
     }
     a.max_dof = h->max_dof; a.mixed = h->mixed;
     CUDA_TRY(cudaEventRecord(h->ev2, h->stream));
@@ -1065,7 +1088,7 @@ static CbForceArgs force_args(cb_handle *h)
     a.d = make_dev(h);
     a.x_temp = h->x_temp.p; a.x_ip = h->x_ip.p; a.dd = h->dd.p;
     a.sh_frame_ip = h->sh_frame[h->gP].p; a.sh_frame_i = h->sh_frame[h->gN].p;
-    a.sh_dsl_i = h->sh_dsl[h->gN].p;
+    a.sh_dsl_i = h->sh_dsl[h->gN].p; a.sh_dsl_ip = h->sh_dsl[h->gP].p;
     a.sh_ef_ip = h->sh_ef[h->eP].p; a.sh_ef_i = h->sh_ef[h->eN].p;
     a.tr_frame_i = h->tr_frame[h->gN].p; a.tr_ef_i = h->tr_ef[h->eN].p;
     a.fr_frame_ip = h->fr_frame[h->gP].p; a.fr_frame_i = h->fr_frame[h->gN].p;
@@ -1106,6 +1129,12 @@ extern "C" int cb_update_forces_dev(cb_handle *h, const double *dd_dev, double *
     CUDA_TRY(cudaEventRecord(h->ev5, s));
     std::swap(h->eP, h->eN);                      // ef_ip <- ef_i (main.c:1982-1984) by renaming
     h->forces_timed = true; h->krec_fresh = true;
+    if (h->fl.ANAFLAG == 3 && h->sz.NE_SH) {          // forces_sh returns 1 (shell.c:2044-2046)
+        int32_t first = 0;
+        CUDA_TRY(cudaMemcpyAsync(&first, h->sh_trip.p, sizeof first, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (first != 0x7fffffff && frcchk_sh) *frcchk_sh = 1;
+    }
     if (h->fl.ANAFLAG == 3 && h->sz.NE_FR) {
         // forces_fr's return code and its rescaling of dlpf (frame.c:1199-1201, 1218-1220, 1260-1268)
         struct { int32_t first, code; double tau; } trip;
@@ -1433,6 +1462,17 @@ static int make_view(cb_handle *h, int which, View &v)
     case CB_ARR_EFFE_IP: v.n = 14 * FR; v.flat = h->fr_efFE[gp].p; break;
     case CB_ARR_FAREA: v.n = SH; v.part[0] = {h->sh_const.p, SH, CB_SH_CONST, 4, 1, true}; v.nparts = 1; break;
     case CB_ARR_SLENGTH: v.n = 3 * SH; v.part[0] = {h->sh_const.p, SH, CB_SH_CONST, 8, 3, true}; v.nparts = 1; break;
+    case CB_ARR_CHI: case CB_ARR_CHI_TEMP: case CB_ARR_EFN: case CB_ARR_EFN_TEMP:
+    case CB_ARR_EFM: case CB_ARR_EFM_TEMP: {
+        if (h->fl.ANAFLAG != 3) return fail(CB_ERR_ARG, "chi / efN / efM exist for ANAFLAG 3 only");
+        const bool tmp = which == CB_ARR_CHI_TEMP || which == CB_ARR_EFN_TEMP || which == CB_ARR_EFM_TEMP;
+        const bool isN = which == CB_ARR_EFN || which == CB_ARR_EFN_TEMP;
+        const bool isC = which == CB_ARR_CHI || which == CB_ARR_CHI_TEMP;
+        const int cnt = isC ? 3 : 9, off = isC ? 0 : (isN ? 3 : 12);
+        v.n = (long)cnt * SH;
+        v.part[0] = {h->sh_pl[tmp ? 1 : 0].p, SH, 21, off, cnt, false}; v.nparts = 1;
+        break;
+    }
     case CB_ARR_LLENGTH:
         v.n = TR + FR;
         v.part[0] = {h->tr_const.p, TR, CB_TR_CONST, 2, 1, false};

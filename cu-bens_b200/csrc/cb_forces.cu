@@ -306,7 +306,7 @@ __device__ __forceinline__ void shell_krec(double X2, double X3, double Y3, doub
     for (int i = 0; i < 9; ++i) kr[i] = R[i];
     kr[9] = X2; kr[10] = X3; kr[11] = Y3;
     kr[12] = cst[3]; kr[13] = cst[4]; kr[14] = cst[5];
-    const double gs = (anaflag == 2) ? 0.5 * i2a : 0.0;          // 1 / (4 A_def)
+    const double gs = (anaflag >= 2) ? 0.5 * i2a : 0.0;          // 1 / (4 A_def)
     kr[15] = gs * Nx; kr[16] = gs * Ny; kr[17] = gs * Nxy;
 }
 
@@ -569,6 +569,238 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
     }
     __syncthreads();          // everyone is done with sbuf before it becomes the krec tile
     warp_store_krec(d.sh_Nm, e - (threadIdx.x & 31), d.NE_SH, kr, tile[threadIdx.x >> 5]);
+}
+
+// ------------------------------------------------------------------------------------------
+// ANAFLAG 3 shells.  k_shell_plastic_prep: what stiff_sh does before it builds the matrix
+// (shell.c:171-283) - Ivanov's criterion at the three vertices from the current stress resultants,
+// choice of the controlling vertex, and for a yielded shell the local elasto-plastic matrix
+// (stiffm_sh) left in sh_kpl for the assembly kernels.  k_shell_forces_pl: updatc's shell block +
+// forces_sh for ANAFLAG 3 (shell.c:1786-2325, 2349-2397), one thread per element; it updates the
+// vertex stress resultants / equivalent plastic curvature in place like the reference does.
+// ------------------------------------------------------------------------------------------
+#include "cb_shell_plastic.cuh"
+
+__global__ void __launch_bounds__(64)
+k_shell_plastic_prep(CbDev d, const double *__restrict__ frame, const double *__restrict__ dsl,
+                     const double *__restrict__ pl)
+{
+    const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (e >= d.NE_SH) return;
+    double sc[CB_SH_CONST];
+    for (int i = 0; i < CB_SH_CONST; ++i) sc[i] = SOA(d.sh_const, i, e, d.NE_SH);
+    const double E = sc[0], nu = sc[1], t = sc[2], fy = d.sh_yield[e], No = fy * t;
+    const double *P = pl + e * CB_SH_PL;
+    Ivanov iv[3];
+    double phi[3];
+    int yv = 0;
+    for (int i = 0; i < 3; ++i) {
+        iv[i].r = iv[i].s = iv[i].phi = 0; iv[i].h = 0;
+        ivanov_eval(iv[i], P + 3 + 3 * i, P + 12 + 3 * i, P[i], fy, t, No);
+        phi[i] = (iv[i].q >= 1e-4) ? iv[i].phi : 0;
+        if (iv[i].q >= 1e-4 && phi[i] >= 1 - CB_SH_PHITOL) pick_vertex(yv, phi, i);
+    }
+    d.sh_yv[e] = yv;
+    if (yv == 0) return;
+    const int v = yv - 1;
+    double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    plane_stress(E, nu, C[0][0], C[0][1], C[2][2]);
+    C[1][1] = C[0][0]; C[1][0] = C[0][1];
+    IvFlow fl;
+    ivanov_flow(fl, iv[v], P + 3 + 3 * v, P + 12 + 3 * v, C, E, t, fy, P[v], No);
+    for (int i = 0; i < 3; ++i) sc[8 + i] = SOA(dsl, i, e, d.NE_SH);       // deformed side lengths
+    double k[18][18];
+    for (int i = 0; i < 18; ++i)
+        for (int j = 0; j < 18; ++j) k[i][j] = 0;
+    shell_plastic_k(k, fl, C, sc, t, SOA(frame, 9, e, d.NE_SH));
+    double *out = d.sh_kpl + e * 324;
+    for (int i = 0; i < 18; ++i)
+        for (int j = 0; j < 18; ++j) out[i * 18 + j] = k[i][j];
+}
+
+int cbk_shell_plastic_prep(const CbDev &d, const double *sh_frame, const double *sh_dsl,
+                           const double *sh_pl, cudaStream_t s)
+{
+    if (d.NE_SH == 0) return 0;
+    k_shell_plastic_prep<<<(unsigned)((d.NE_SH + 63) / 64), 64, 0, s>>>(d, sh_frame, sh_dsl, sh_pl);
+    return cudaGetLastError() != cudaSuccess;
+}
+
+__global__ void __launch_bounds__(64)
+k_shell_forces_pl(CbDev d, const double *__restrict__ x_temp, const double *__restrict__ x_ip,
+                  const double *__restrict__ dd, const double *__restrict__ frame_ip,
+                  double *__restrict__ frame_i, const double *__restrict__ dsl_ip,
+                  double *__restrict__ dsl_i, const double *__restrict__ ef_ip, double *__restrict__ ef_i)
+{
+    const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (e >= d.NE_SH) return;
+    const int FM[6] = {0, 1, 6, 7, 12, 13}, FB[9] = {2, 3, 4, 8, 9, 10, 14, 15, 16};
+    double sc[CB_SH_CONST], Rp[CB_SH_FRAME], Ri[CB_SH_FRAME], dsl[3];
+    for (int i = 0; i < CB_SH_CONST; ++i) sc[i] = SOA(d.sh_const, i, e, d.NE_SH);
+    for (int i = 0; i < CB_SH_FRAME; ++i) Rp[i] = SOA(frame_ip, i, e, d.NE_SH);
+    const double E = sc[0], nu = sc[1], t = sc[2], t3 = t * t * t, fy = d.sh_yield[e], No = fy * t;
+    const int4 nd = reinterpret_cast<const int4 *>(d.sh_nodes)[e];
+    const int nn[3] = {nd.x, nd.y, nd.z};
+    double X[3][3], Xp[3][3];
+    for (int a = 0; a < 3; ++a)
+        for (int m = 0; m < 3; ++m) { X[a][m] = x_temp[(long)nn[a] * 3 + m]; Xp[a][m] = x_ip[(long)nn[a] * 3 + m]; }
+    shell_triad(X[0], X[1], X[2], Ri, dsl);                      // updatc, misc.c:153-184
+
+    // total membrane displacements w.r.t. the reference shape (record for the next stiffness pass)
+    double dm2, dm4, dm5;
+    membrane_dm(X[0], X[1], X[2], Ri, sc, dm2, dm4, dm5);
+    {
+        double cst[6], kr[CB_SH_KREC];
+        for (int i = 0; i < 6; ++i) cst[i] = SOA(d.sh_der, 18 + i, e, d.NE_SH);
+        shell_krec(sc[5], sc[6], sc[7], t, Ri, cst, dm2, dm4, dm5, d.ANAFLAG, kr);
+        for (int i = 0; i < CB_SH_KREC; ++i) d.sh_Nm[e * CB_SH_KREC + i] = kr[i];
+    }
+    // incremental membrane displacements: local coordinates now minus those of the previous
+    // iterate in the previous frame (shell.c:1787-1799)
+    double ddm[6] = {0, 0, 0, 0, 0, 0};
+    {
+        const double zero[CB_SH_CONST] = {0};
+        double a2, a4, a5, b2, b4, b5;
+        membrane_dm(X[0], X[1], X[2], Ri, zero, a2, a4, a5);
+        membrane_dm(Xp[0], Xp[1], Xp[2], Rp, zero, b2, b4, b5);
+        ddm[2] = a2 - b2; ddm[4] = a4 - b4; ddm[5] = a5 - b5;
+    }
+    double DD[3][6], ddl[18], ddb[9];
+    for (int a = 0; a < 3; ++a) {
+        gather_node6(d.jc, dd, nn[a], DD[a]);
+        for (int r = 0; r < 3; ++r) {
+            ddl[6 * a + r] = dot3(Rp + 3 * r, DD[a]);
+            ddl[6 * a + 3 + r] = dot3(Rp + 3 * r, DD[a] + 3);
+        }
+    }
+    for (int i = 0; i < 9; ++i) ddb[i] = ddl[FB[i]];
+    double scd[CB_SH_CONST];                                     // constants with the deformed sides
+    for (int i = 0; i < CB_SH_CONST; ++i) scd[i] = sc[i];
+    for (int i = 0; i < 3; ++i) scd[8 + i] = SOA(dsl_ip, i, e, d.NE_SH);
+    const double Adef = Rp[9];
+    double strn[3], curv[3][3];
+    strain_curvature(strn, curv, ddm, ddb, scd, Adef);
+    double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    plane_stress(E, nu, C[0][0], C[0][1], C[2][2]);
+    C[1][1] = C[0][0]; C[1][0] = C[0][1];
+
+    double *P = d.sh_pl + e * CB_SH_PL;
+    Ivanov iv[3];
+    double phi[3] = {0, 0, 0};
+    int yv = 0, code = 0;
+    for (int i = 0; i < 3 && code == 0; ++i) {
+        double *chi = P + i, *N = P + 3 + 3 * i, *M = P + 12 + 3 * i;
+        iv[i].r = iv[i].s = iv[i].phi = 0; iv[i].h = 0;
+        ivanov_eval(iv[i], N, M, *chi, fy, t, No);
+        if (iv[i].q >= 1e-4 && iv[i].phi >= 1 - CB_SH_PHITOL) {   // shell.c:1877-1992
+            IvFlow fl;
+            ivanov_flow(fl, iv[i], N, M, C, E, t, fy, *chi, No);
+            double fs = 0, fc = 0;
+            for (int j = 0; j < 3; ++j) { fs += fl.fnC[j] * strn[j]; fc += fl.fmC[j] * curv[i][j]; }
+            fs *= t; fc *= t3 / 12;
+            const double lambda = (fs + fc) / (fl.jf + fl.kf - fl.Bf * fl.df_da * fl.da_dchi);
+            *chi += sqrt(sq((E * t) / (3 * fy)) * sq(fl.Bf * lambda));
+            for (int j = 0; j < 3; ++j) {
+                double s1 = 0, s2 = 0;
+                for (int q = 0; q < 3; ++q) {
+                    s1 += C[j][q] * (strn[q] - lambda * fl.fn[q]);
+                    s2 += C[j][q] * (curv[i][q] - lambda * fl.fm[q]);
+                }
+                N[j] += t * s1; M[j] += t3 * s2 / 12;
+            }
+        } else {                                                 // elastic increment
+            for (int j = 0; j < 3; ++j) {
+                double s1 = 0, s2 = 0;
+                for (int q = 0; q < 3; ++q) { s1 += C[j][q] * strn[q]; s2 += C[j][q] * curv[i][q]; }
+                N[j] += t * s1; M[j] += t3 * s2 / 12;
+            }
+        }
+        ivanov_eval(iv[i], N, M, *chi, fy, t, No);               // shell.c:1994-2041
+        if (iv[i].q >= 1e-4) {
+            phi[i] = iv[i].phi;
+            if (phi[i] > 1 + 10 * CB_SH_PHITOL) {
+                code = 1;                                        // shell.c:2044-2046
+            } else if (phi[i] > 1 + CB_SH_PHITOL) {              // return to the surface
+                int guard = 0;
+                do {
+                    IvFlow fl;
+                    ivanov_flow(fl, iv[i], N, M, C, E, t, fy, *chi, No);
+                    const double lambda = (phi[i] - 1) / (fl.jf + fl.kf - fl.Bf * fl.df_da * fl.da_dchi);
+                    for (int j = 0; j < 3; ++j) {
+                        double s1 = 0, s2 = 0;
+                        for (int q = 0; q < 3; ++q) {
+                            s1 += C[j][q] * (-lambda * fl.fn[q]);
+                            s2 += C[j][q] * (-lambda * fl.fm[q]);
+                        }
+                        N[j] += t * s1; M[j] += t3 * s2 / 12;
+                    }
+                    ivanov_eval(iv[i], N, M, *chi, fy, t, No);
+                    if (iv[i].q >= 1e-4) phi[i] = iv[i].phi;
+                    // the reference would spin for ever on a non-converging return; the device
+                    // gives up and asks for a smaller increment instead
+                    if (++guard > 200) { code = 1; break; }
+                } while (phi[i] > 1 + CB_SH_PHITOL);
+                if (code == 0) pick_vertex(yv, phi, i);
+            } else if (phi[i] >= 1 - CB_SH_PHITOL) {
+                pick_vertex(yv, phi, i);
+            }
+        } else {
+            phi[i] = 0;
+        }
+    }
+    if (code != 0) atomicMin(d.sh_trip, (int)e);
+
+    // M = R_i R_ip^T: T_i T_ip^T is block diagonal (shell.c:2352-2362)
+    double M3[3][3];
+    for (int r = 0; r < 3; ++r)
+        for (int s2 = 0; s2 < 3; ++s2) M3[r][s2] = dot3(Ri + 3 * r, Rp + 3 * s2);
+    double def[18], eft[18], efp[18], efi[18];
+    for (int i = 0; i < 18; ++i) { def[i] = 0; eft[i] = 0; efp[i] = SOA(ef_ip, i, e, d.NE_SH); }
+    if (yv == 0) {                                               // shell.c:2215-2278 (= ANAFLAG 2)
+        for (int i = 0; i < 6; ++i) {
+            double acc = 0;
+            acc += SOA(d.sh_der, i * 3 + 0, e, d.NE_SH) * dm2;
+            acc += SOA(d.sh_der, i * 3 + 1, e, d.NE_SH) * dm4;
+            acc += SOA(d.sh_der, i * 3 + 2, e, d.NE_SH) * dm5;
+            eft[FM[i]] = acc;
+            efp[FM[i]] = 0;
+        }
+        for (int i = 0; i < 9; ++i) {
+            double sum = 0;
+            for (int j = 0; j < 9; ++j) sum += SOA(d.sh_keb, CB_KEB(i, j), e, d.NE_SH) * ddb[j];
+            def[FB[i]] = sum;
+        }
+    } else {                                                     // shell.c:2279-2306
+        const int v = yv - 1;
+        IvFlow fl;
+        ivanov_flow(fl, iv[v], P + 3 + 3 * v, P + 12 + 3 * v, C, E, t, fy, P[v], No);
+        double k[18][18];
+        for (int i = 0; i < 18; ++i)
+            for (int j = 0; j < 18; ++j) k[i][j] = 0;
+        shell_plastic_k(k, fl, C, scd, t, Adef);
+        for (int i = 0; i < 18; ++i) {
+            double sum = 0;
+            for (int j = 0; j < 18; ++j) sum += k[i][j] * ddl[j];
+            def[i] = sum;
+        }
+    }
+    // ef_i = [ef_temp +] Ti_Tip (def + ef_ip)   (shell.c:2364-2384)
+    for (int g = 0; g < 6; ++g) {
+        double v3[3];
+        for (int c = 0; c < 3; ++c) v3[c] = def[3 * g + c] + efp[3 * g + c];
+        for (int r = 0; r < 3; ++r) efi[3 * g + r] = eft[3 * g + r] + dot3(M3[r], v3);
+    }
+    for (int i = 0; i < 18; ++i) SOA(ef_i, i, e, d.NE_SH) = efi[i];
+    for (int g = 0; g < 6; ++g)
+        for (int c = 0; c < 3; ++c) {
+            double sum = 0;
+            sum += Ri[c] * efi[3 * g];
+            sum += Ri[3 + c] * efi[3 * g + 1];
+            sum += Ri[6 + c] * efi[3 * g + 2];
+            CB_FG(d.sh_fg, g / 2, e, d.NE_SH)[(g % 2) * 3 + c] = sum;
+        }
+    for (int i = 0; i < CB_SH_FRAME; ++i) SOA(frame_i, i, e, d.NE_SH) = Ri[i];
+    for (int i = 0; i < 3; ++i) SOA(dsl_i, i, e, d.NE_SH) = dsl[i];
 }
 
 // forces_sh, ANAFLAG 1 (shell.c:1695-1727, 2386-2397): ef = k_sh (T D), total displacements
@@ -957,9 +1189,11 @@ k_gather_f(CbDev d, const int32_t *__restrict__ cstart, const CbCorner *__restri
     const int c0 = cstart[n], c1 = cstart[n + 1];
     // members from the first tripping one onwards never reach the scatter in the reference
     const int fr_end = (d.ANAFLAG == 3 && d.fr_trip) ? d.fr_trip[0] : 0x7fffffff;
+    const int sh_end = (d.ANAFLAG == 3 && d.sh_trip) ? d.sh_trip[0] : 0x7fffffff;
     for (int c = c0; c < c1; ++c) {
         const CbCorner cr = corners[c];
         if (cr.type == CB_T_SHELL) {
+            if (cr.e >= sh_end) continue;
             const double *p = CB_FG(d.sh_fg, cr.b, cr.e, d.NE_SH);
 #pragma unroll
             for (int r = 0; r < 6; ++r) acc[r] += p[r];
@@ -1021,6 +1255,13 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
                 return 1;
             configured = true;
         }
+        if (d.ANAFLAG == 3) {
+            static const int init[4] = {0x7fffffff, 0, 0, 0};
+            if (cudaMemcpyAsync(d.sh_trip, init, sizeof init, cudaMemcpyHostToDevice, s) != cudaSuccess) return 1;
+            k_shell_forces_pl<<<(unsigned)((d.NE_SH + 63) / 64), 64, 0, s>>>(
+                d, a.x_temp, a.x_ip, a.dd, a.sh_frame_ip, a.sh_frame_i, a.sh_dsl_ip, a.sh_dsl_i,
+                a.sh_ef_ip, a.sh_ef_i);
+        } else
         k_shell_forces<<<g, CB_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
                                                a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i);
         ++*launches;

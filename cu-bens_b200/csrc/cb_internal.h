@@ -166,6 +166,12 @@ struct CbDev {
     double *fr_tau;          // [NE] regula-falsi scale of dlpf when code == 1
     int32_t *fr_trip;        // [4] lowest member index with code != 0 (INT_MAX if none), its code
     const double *tr_py;     // [NE_TR] squash loads of the trusses
+    // shells, ANAFLAG 3 (Ivanov yield criterion in stress resultants)
+    const double *sh_yield;  // [NE] yield stress
+    double *sh_pl;           // [NE][21] chi[3], efN[3][3], efM[3][3]: the *_temp generation
+    int32_t *sh_yv;          // [NE] controlling yielded vertex (1..3) for the stiffness pass, 0 elastic
+    double *sh_kpl;          // [NE][18*18] local elasto-plastic matrix (stiffm_sh) of yielded shells
+    int32_t *sh_trip;        // [4] lowest shell index whose force pass returned 1 (INT_MAX if none)
     // trusses
     const int32_t *tr_nodes; // [NE][2]
     const double *tr_const;  // [NE][CB_TR_CONST]
@@ -203,7 +209,7 @@ struct CbForceArgs {
     double *x_temp, *x_ip;
     const double *dd;        // [NEQ] device
     // shells
-    const double *sh_frame_ip; double *sh_frame_i; double *sh_dsl_i;
+    const double *sh_frame_ip; double *sh_frame_i; double *sh_dsl_i; const double *sh_dsl_ip;
     const double *sh_ef_ip; double *sh_ef_i;
     // frames
     const double *fr_frame_ip; double *fr_frame_i; double *fr_xfr_i;
@@ -227,6 +233,8 @@ int cbk_shell_init_kebc2(const CbDev &d, const CbTile2 *tiles, long ntiles, cons
 int cbk_shell_init_kebc(const CbDev &d, const CbContrib *contribs, long ncontrib, double *kebc,
                         cudaStream_t s);
 int cbk_shell_prep(const CbDev &d, const double *x, const double *sh_frame, cudaStream_t s);
+int cbk_shell_plastic_prep(const CbDev &d, const double *sh_frame, const double *sh_dsl,
+                           const double *sh_pl, cudaStream_t s);
 int cbk_node_update(const CbForceArgs &a, cudaStream_t s);
 int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches);
 int cbk_forces_linear(const CbForceArgs &a, const double *d_total, cudaStream_t s, long *launches);

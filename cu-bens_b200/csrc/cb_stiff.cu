@@ -79,11 +79,42 @@ __device__ __forceinline__ void cst_grad(int n, double X2, double X3, double Y3,
     by = (n == 0) ? (X3 - X2) : (n == 1 ? -X3 : X2);
 }
 
+// K_ab (6x6, global axes) of a yielded shell (ANAFLAG 3): the local elasto-plastic block left in
+// sh_kpl by k_shell_plastic_prep (stiffm_sh, shell.c:842-1133) is full - membrane and bending
+// couple - plus the geometric term g on the translations (stiffg_sh), rotated by blockdiag(R, R).
+// out(p, q) is written through the caller's indexing: out[p * ldr + q * ldc].
+__device__ __noinline__ void shell_block_plastic(const CbDev &d, int e, int a, int b, double *out,
+                                                 int ldr, int ldc)
+{
+    const double *kr = d.sh_Nm + (long)e * CB_SH_KREC;
+    double R[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = kr[i];
+    double bxa, bya, bxb, byb;
+    cst_grad(a, kr[9], kr[10], kr[11], bxa, bya);
+    cst_grad(b, kr[9], kr[10], kr[11], bxb, byb);
+    const double g = bxa * (kr[15] * bxb + kr[17] * byb) + bya * (kr[17] * bxb + kr[16] * byb);
+    const double *S = d.sh_kpl + (long)e * 324 + (6 * a) * 18 + 6 * b;
+    for (int bi = 0; bi < 2; ++bi)
+        for (int bj = 0; bj < 2; ++bj) {
+            double s[3][3], W[3][3];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j)
+                    s[i][j] = S[(3 * bi + i) * 18 + 3 * bj + j] + ((bi == 0 && bj == 0 && i == j) ? g : 0.0);
+            for (int i = 0; i < 3; ++i)
+                for (int q = 0; q < 3; ++q) W[i][q] = s[i][0] * R[q] + s[i][1] * R[3 + q] + s[i][2] * R[6 + q];
+            for (int p = 0; p < 3; ++p)
+                for (int q = 0; q < 3; ++q)
+                    out[(3 * bi + p) * ldr + (3 * bj + q) * ldc] = R[p] * W[0][q] + R[3 + p] * W[1][q] + R[6 + p] * W[2][q];
+        }
+}
+
 // K_ab (6x6, global axes) of shell e -> blk (row-major, leading dimension ld)
 // membrane  shell.c:487-531, DKT bending (precomputed) shell.c:533-658, drilling shell.c:482-484,
 // geometric shell.c:660-840, rotation shell.c:285-305 + misc.c:41-69
 __device__ __forceinline__ void shell_block(const CbDev &d, int e, int a, int b, double *blk, int ld)
 {
+    if (d.ANAFLAG == 3 && d.sh_yv[e] != 0) { shell_block_plastic(d, e, a, b, blk, ld, 1); return; }
     const double2 *kr2 = reinterpret_cast<const double2 *>(d.sh_Nm + (long)e * CB_SH_KREC);
     double kr[CB_SH_KREC];
 #pragma unroll
@@ -415,7 +446,10 @@ k_assemble_tiles(CbStiffArgs A)
 #pragma unroll
                         for (int i = 0; i < NN; ++i) stg[i * STR] = 0.0;
                     }
-                    shell_block_stage<ND>(in, ct.a, ct.b, stg);
+                    if (A.d.ANAFLAG == 3 && A.d.sh_yv[ct.e] != 0)
+                        shell_block_plastic(A.d, ct.e, ct.a, ct.b, stg, ND * STR, STR);
+                    else
+                        shell_block_stage<ND>(in, ct.a, ct.b, stg);
                 }
                 ndof[col] = 6;
             } else if (SHELL_ONLY) {

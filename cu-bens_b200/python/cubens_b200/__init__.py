@@ -23,7 +23,8 @@ ARR = dict(X=1, X_TEMP=2, X_IP=3, C1=4, C2=5, C3=6, C1_I=7, C2_I=8, C3_I=9, C1_I
            C3_IP=12, EF=13, EF_I=14, EF_IP=15, DEFLLEN=16, DEFLLEN_I=17, DEFLLEN_IP=18,
            DEFFAREA=19, DEFFAREA_I=20, DEFFAREA_IP=21, DEFSLEN=22, DEFSLEN_I=23, DEFSLEN_IP=24,
            XFR=25, XFR_TEMP=26, EFFE=27, EFFE_I=28, EFFE_IP=29, D=30, D_TEMP=31, F=32, F_TEMP=33,
-           LLENGTH=34, FAREA=35, SLENGTH=36)
+           LLENGTH=34, FAREA=35, SLENGTH=36, CHI=37, CHI_TEMP=38, EFN=39, EFN_TEMP=40, EFM=41,
+           EFM_TEMP=42)
 
 EXPORTS = [
     "cb_abi_version", "cb_last_error", "cb_device_count", "cb_create", "cb_destroy",
@@ -229,6 +230,10 @@ class Assembler:
         if n is None:
             if name.startswith("C"):
                 n = m.n_c
+            elif name.startswith("CHI"):
+                n = 3 * m.NE_SH
+            elif name.startswith("EFN") or name.startswith("EFM"):
+                n = 9 * m.NE_SH
             elif name.startswith("EFFE"):
                 n = 14 * m.NE_FR
             elif name.startswith("EF"):

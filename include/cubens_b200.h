@@ -65,9 +65,9 @@ typedef struct cb_sizes {
 } cb_sizes;
 
 /* ANAFLAG 1 = first-order elastic, 2 = geometric nonlinear, 3 = geometric + material nonlinear
- * (main.c:63-90).  ANAFLAG 3 is built for trusses and frames (concentrated plasticity: stiffm_tr,
- * stiffm_fr, yield check / regula_falsi / unload in forces_fr); with shells, and ANAFLAG 4 (FSI),
- * cb_create returns CB_ERR_UNSUPPORTED.                                                     */
+ * (main.c:63-90): trusses and frames with concentrated plasticity (stiffm_tr, stiffm_fr, yield check /
+ * regula_falsi / unload in forces_fr), DKT shells with Ivanov's yield criterion in stress resultants
+ * (stiffm_sh, strn_curv, the return mapping of forces_sh).  ANAFLAG 4 (FSI): CB_ERR_UNSUPPORTED. */
 typedef struct cb_flags {
     int ANAFLAG, ALGFLAG, SLVFLAG;
     int matrix_layout;      /* CB_MAT_*; 0 picks SKYLINE when SLVFLAG==0 else CSC          */
@@ -193,7 +193,10 @@ enum {
     CB_ARR_XFR, CB_ARR_XFR_TEMP,
     CB_ARR_EFFE, CB_ARR_EFFE_I, CB_ARR_EFFE_IP,
     CB_ARR_D, CB_ARR_D_TEMP, CB_ARR_F, CB_ARR_F_TEMP,
-    CB_ARR_LLENGTH, CB_ARR_FAREA, CB_ARR_SLENGTH     /* mass_* overwrite these (App. B.5)    */
+    CB_ARR_LLENGTH, CB_ARR_FAREA, CB_ARR_SLENGTH,    /* mass_* overwrite these (App. B.5)    */
+    /* ANAFLAG 3 shells: equivalent plastic curvature [SH*3] and the membrane-force / moment
+     * resultants at the three vertices [SH*9] (main.c:889-913), committed and *_temp        */
+    CB_ARR_CHI, CB_ARR_CHI_TEMP, CB_ARR_EFN, CB_ARR_EFN_TEMP, CB_ARR_EFM, CB_ARR_EFM_TEMP
 };
 /* n = number of doubles of the reference array (checked) */
 int  cb_download(cb_handle *h, int which, double *dst, long n);

@@ -209,6 +209,24 @@ void orc_updatc(const orc_dims *D, double *x_temp, double *x_ip, double *xfr_tem
     }
 }
 
+/* ---------------------------------------------------------- ANAFLAG 3 (material nonlinear) */
+#define PHITOL 1e-4                                    /* frame.c:37, truss.c:100, shell.c:37 */
+static struct {
+    const double *yield, *zstrong, *zweak; int *yldflag;             /* trusses, frames */
+    double *chi_temp, *efN_temp, *efM_temp;                         /* shells: main.c:889-913 */
+    const double *x_ip, *deffarea_ip, *defslen_ip;
+} g_pl;
+void orc_set_plastic(const double *yield, const double *zstrong, const double *zweak, int *yldflag)
+{   /* the arrays main.c owns for ANAFLAG 3 (main.c:559-571, 802) */
+    g_pl.yield = yield; g_pl.zstrong = zstrong; g_pl.zweak = zweak; g_pl.yldflag = yldflag;
+}
+void orc_set_plastic_sh(double *chi_temp, double *efN_temp, double *efM_temp, const double *x_ip,
+                        const double *deffarea_ip, const double *defslen_ip)
+{   /* the extra arguments stiff_sh / forces_sh take for ANAFLAG 3 (prototypes.h:187-191, 246-251) */
+    g_pl.chi_temp = chi_temp; g_pl.efN_temp = efN_temp; g_pl.efM_temp = efM_temp;
+    g_pl.x_ip = x_ip; g_pl.deffarea_ip = deffarea_ip; g_pl.defslen_ip = defslen_ip;
+}
+
 /* --------------------------------------------------------------------------------- shell.c */
 static const int FM[6] = {0, 1, 6, 7, 12, 13};              /* membrane DOFs  (shell.c:1603) */
 static const int FB[9] = {2, 3, 4, 8, 9, 10, 14, 15, 16};   /* bending DOFs   (shell.c:1604) */
@@ -251,13 +269,42 @@ static void cst_membrane(double ke[6][6], double E, double nu, const double *xl,
         }
 }
 
+static void dkt_alpha_T(double aT[9][9], const double *xl, const double *sl);
+
 static void dkt_bending(double kb[9][9], double E, double nu, const double *xl, double t, double A,
                         const double *sl)
 {   /* stiffe_b_sh, shell.c:533-658: Batoz' explicit DKT matrix, kb = Q alpha^T / (2A) */
-    const double X2 = xl[0], X3 = xl[1], Y3 = xl[2];
     const double E1 = E * pow(t, 3) / (12 * (1 - nu * nu)), E3 = E1;
     const double E2 = E * pow(t, 3) / (12 * (1 - nu * nu)) * nu;
     const double E4 = E * pow(t, 3) / (12 * (1 - nu * nu)) * (1 - nu) / 2;
+    double aT[9][9];
+    dkt_alpha_T(aT, xl, sl);
+    double Q[9][9];
+    for (int i = 0; i < 9; ++i) {        /* shell.c:610-648: the three row blocks are alike */
+        double b1 = 0, b2 = 0, b3 = 0;
+        for (int j = 0; j < 3; ++j) {
+            b1 += E1 * aT[i][j] + E2 * aT[i][j + 3];
+            b2 += E2 * aT[i][j] + E3 * aT[i][j + 3];
+            b3 += E4 * aT[i][j + 6];
+        }
+        for (int j = 0; j < 3; ++j) {
+            Q[i][j] = (E1 * aT[i][j] + E2 * aT[i][j + 3] + b1) / 24;
+            Q[i][j + 3] = (E2 * aT[i][j] + E3 * aT[i][j + 3] + b2) / 24;
+            Q[i][j + 6] = (E4 * aT[i][j + 6] + b3) / 24;
+        }
+    }
+    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j < 9; ++j) {
+            double s = 0;
+            for (int k = 0; k < 9; ++k) s += Q[i][k] * aT[j][k];
+            kb[i][j] = s / (2 * A);
+        }
+}
+
+static void dkt_alpha_T(double aT_out[9][9], const double *xl, const double *sl)
+{   /* transpose of Batoz' alpha matrix, shell.c:545-607 (= 1249-1311, 1424-1486); the rows of
+     * strn_curv's LL_alpha (shell.c:2489-2540) are its columns: LL_alpha[v][j][k] = aT[k][3j+v] */
+    const double X2 = xl[0], X3 = xl[1], Y3 = xl[2];
     const double x23 = X2 - X3, l12 = sl[0] * sl[0], l23 = sl[1] * sl[1], l31 = sl[2] * sl[2];
     const double p4 = -6 * x23 / l23, p5 = -6 * X3 / l31, p6 = 6 * X2 / l12;
     const double t4 = 6 * Y3 / l23, t5 = -6 * Y3 / l31;
@@ -282,26 +329,7 @@ static void dkt_bending(double kb[9][9], double E, double nu, const double *xl, 
          X2 * q4, -x23 * q5 - X3 * q4 + Y3 * (r4 - r5)},
         {0, 0, Y3 * (r4 - r5), -(X2 * q5), -(X2 * q4), X3 * q4 + x23 * q5, X2 * (r5 - 2),
          X2 * (r4 - 2), -x23 * r5 - X3 * r4 + 4 * X2 + Y3 * (q5 - q4)}};
-    double Q[9][9];
-    for (int i = 0; i < 9; ++i) {        /* shell.c:610-648: the three row blocks are alike */
-        double b1 = 0, b2 = 0, b3 = 0;
-        for (int j = 0; j < 3; ++j) {
-            b1 += E1 * aT[i][j] + E2 * aT[i][j + 3];
-            b2 += E2 * aT[i][j] + E3 * aT[i][j + 3];
-            b3 += E4 * aT[i][j + 6];
-        }
-        for (int j = 0; j < 3; ++j) {
-            Q[i][j] = (E1 * aT[i][j] + E2 * aT[i][j + 3] + b1) / 24;
-            Q[i][j + 3] = (E2 * aT[i][j] + E3 * aT[i][j + 3] + b2) / 24;
-            Q[i][j + 6] = (E4 * aT[i][j + 6] + b3) / 24;
-        }
-    }
-    for (int i = 0; i < 9; ++i)
-        for (int j = 0; j < 9; ++j) {
-            double s = 0;
-            for (int k = 0; k < 9; ++k) s += Q[i][k] * aT[j][k];
-            kb[i][j] = s / (2 * A);
-        }
+    memcpy(aT_out, aT, sizeof aT);
 }
 
 static void shell_elastic(double k[18][18], double E, double nu, const double *xl, double t, double A,
@@ -366,6 +394,204 @@ static void shell_geometric(double k[18][18], double E, double nu, const double 
         }
 }
 
+/* ---- Ivanov yield criterion in stress resultants, ANAFLAG 3 ---------------------------- */
+typedef struct { double alpha, Me, Nbar, Mbar, MNbar, q, r, s, phi; int h; } ivanov;
+
+static void ivanov_eval(ivanov *v, const double *N, const double *M, double chi, double fy, double t,
+                        double No)
+{   /* shell.c:178-234 (the same block at 1833-1876, 1996-2041 and 2145-2188).  r, s, h keep their
+     * previous values when q < 1e-4, as the reference's per-vertex arrays do. */
+    v->alpha = 1.0 - 0.4 * exp(-2.6 * sqrt(chi));
+    v->Me = v->alpha * 0.25 * fy * pow(t, 2);
+    v->Nbar = pow(N[0], 2) + pow(N[1], 2) - N[0] * N[1] + 3 * pow(N[2], 2);
+    v->Mbar = pow(M[0], 2) + pow(M[1], 2) - M[0] * M[1] + 3 * pow(M[2], 2);
+    v->MNbar = M[0] * N[0] + M[1] * N[1] - 0.5 * M[0] * N[1] - 0.5 * M[1] * N[0] + 3 * M[2] * N[2];
+    v->q = v->Nbar * pow(v->Me, 2) + 0.48 * v->Mbar * pow(No, 2);
+    if (v->q >= 1e-4) {
+        v->r = sqrt(pow(No, 2) * pow(v->Mbar, 2) + 4 * pow(v->Me, 2) * pow(v->MNbar, 2));
+        v->h = (v->r / (2 * pow(v->Me, 2) * No) >= 1e-4) ? 1 : 0;
+        v->s = v->Nbar * v->Mbar - pow(v->MNbar, 2);
+        if (v->h == 1)
+            v->phi = v->Nbar / pow(No, 2) + 0.5 * v->Mbar / pow(v->Me, 2) - 0.25 * v->s / v->q +
+                     v->r / (2 * pow(v->Me, 2) * No);
+        else
+            v->phi = v->Nbar / pow(No, 2) + 0.5 * v->Mbar / pow(v->Me, 2) - 0.25 * v->s / v->q;
+    }
+}
+
+typedef struct { double fn[3], fm[3], fnC[3], fmC[3], jf, kf, Bf, df_da, da_dchi; } ivflow;
+
+static void ivanov_flow(ivflow *f, const ivanov *v, const double *N, const double *M, double C[3][3],
+                        double E, double t, double fy, double chi, double No)
+{   /* plastic flow directions and the factors of the elasto-plastic moduli, shell.c:868-937
+     * (the same block at 1880-1960 and 2052-2122) */
+    const double c_fact = 1 / pow(No, 2) - v->Mbar / (4 * v->q) + v->s * pow(v->Me, 2) / (4 * pow(v->q, 2));
+    double g_fact, d_fact;
+    if (v->h == 1) {
+        g_fact = v->MNbar * (1 / (4 * v->q) + 1 / (No * v->r));
+        d_fact = 1 / (2 * pow(v->Me, 2)) - v->Nbar / (4 * v->q) + 0.12 * pow(No, 2) * v->s / pow(v->q, 2) +
+                 v->Mbar * No / (2 * pow(v->Me, 2) * v->r);
+    } else {
+        g_fact = v->MNbar / (4 * v->q);
+        d_fact = 1 / (2 * pow(v->Me, 2)) - v->Nbar / (4 * v->q) + 0.12 * pow(No, 2) * v->s / pow(v->q, 2);
+    }
+    const double gN[3] = {2 * N[0] - N[1], 2 * N[1] - N[0], 6 * N[2]};
+    const double gM[3] = {2 * M[0] - M[1], 2 * M[1] - M[0], 6 * M[2]};
+    for (int j = 0; j < 3; ++j) {
+        f->fn[j] = c_fact * gN[j] + g_fact * gM[j];
+        f->fm[j] = g_fact * gN[j] + d_fact * gM[j];
+    }
+    for (int j = 0; j < 3; ++j) {
+        double s1 = 0, s2 = 0;
+        for (int k = 0; k < 3; ++k) { s1 += f->fn[k] * C[k][j]; s2 += f->fm[k] * C[k][j]; }
+        f->fnC[j] = s1; f->fmC[j] = s2;
+    }
+    double s1 = 0, s2 = 0;
+    for (int j = 0; j < 3; ++j) { s1 += f->fnC[j] * f->fn[j]; s2 += f->fmC[j] * f->fm[j]; }
+    f->jf = t * s1;
+    f->kf = pow(t, 3) * s2 / 12;
+    f->Bf = 2 * sqrt(pow(g_fact, 2) * v->Nbar + pow(d_fact, 2) * v->Mbar + 2 * d_fact * g_fact * v->MNbar);
+    if (v->h == 1)
+        f->df_da = -(v->Mbar / (v->alpha * pow(v->Me, 2))) +
+                   v->s * v->Nbar * pow(v->Me, 2) / (2 * pow(v->q, 2) * v->alpha) -
+                   v->r / (v->alpha * pow(v->Me, 2) * No) + 2 * pow(v->MNbar, 2) / (v->alpha * No * v->r);
+    else
+        f->df_da = -(v->Mbar / (v->alpha * pow(v->Me, 2))) +
+                   v->s * v->Nbar * pow(v->Me, 2) / (2 * pow(v->q, 2) * v->alpha);
+    if (chi >= 1e-6) f->da_dchi = 0.52 * E * t * exp(-2.6 * sqrt(chi)) / (3 * fy * sqrt(chi));
+    else f->da_dchi = 0;
+}
+
+static void shell_plastic(double k[18][18], const ivflow *f, double C[3][3], const double *xl, double t,
+                          double Adef, const double *dsl)
+{   /* stiffm_sh + stiffm_m_sh + stiffm_b_sh + stiffm_mb_sh, shell.c:842-1503: elasto-plastic
+     * membrane, bending and coupling blocks at the controlling yielded vertex (entries are
+     * assigned, the geometric part is added afterwards by the caller) */
+    const double den = f->jf + f->kf - f->Bf * f->df_da * f->da_dchi;
+    double Bm[3][6], aT[9][9];
+    membrane_B(xl, Adef, Bm);
+    dkt_alpha_T(aT, xl, dsl);
+    {   /* membrane, shell.c:1134-1199 */
+        const double xi = t / den;
+        double xNC[3][3], Cs[3][3], BC[6][3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = 0;
+                for (int q = 0; q < 3; ++q) s += (f->fn[i] * f->fn[q]) * C[q][j];
+                xNC[i][j] = xi * s;
+            }
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = 0;
+                for (int q = 0; q < 3; ++q) s += C[i][q] * xNC[q][j];
+                Cs[i][j] = t * (C[i][j] - s);
+            }
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = 0;
+                for (int q = 0; q < 3; ++q) s += Bm[q][i] * Cs[q][j];
+                BC[i][j] = s;
+            }
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) {
+                double s = 0;
+                for (int q = 0; q < 3; ++q) s += BC[i][q] * Bm[q][j];
+                k[FM[i]][FM[j]] = Adef * s;
+            }
+    }
+    {   /* bending, shell.c:1201-1368 */
+        const double xi = pow(t, 3) / (12 * den);
+        double xMC[3][3], Ds[3][3], Q[9][9], kb[9][9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = 0;
+                for (int q = 0; q < 3; ++q) s += (f->fm[i] * f->fm[q]) * C[q][j];
+                xMC[i][j] = xi * s;
+            }
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = 0;
+                for (int q = 0; q < 3; ++q) s += C[i][q] * xMC[q][j];
+                Ds[i][j] = pow(t, 3) * (C[i][j] - s) / 12;
+            }
+        for (int i = 0; i < 9; ++i) {    /* shell.c:1314-1357: the three row blocks are alike */
+            double b[3];
+            for (int j = 0; j < 3; ++j) {
+                b[j] = 0;
+                for (int q = 0; q < 3; ++q)
+                    b[j] += Ds[j][0] * aT[i][q] + Ds[j][1] * aT[i][q + 3] + Ds[j][2] * aT[i][q + 6];
+            }
+            for (int j = 0; j < 3; ++j) {
+                Q[i][j] = (Ds[0][0] * aT[i][j] + Ds[1][0] * aT[i][j + 3] + Ds[2][0] * aT[i][j + 6] + b[0]) / 24;
+                Q[i][j + 3] = (Ds[0][1] * aT[i][j] + Ds[1][1] * aT[i][j + 3] + Ds[2][1] * aT[i][j + 6] + b[1]) / 24;
+                Q[i][j + 6] = (Ds[0][2] * aT[i][j] + Ds[1][2] * aT[i][j + 3] + Ds[2][2] * aT[i][j + 6] + b[2]) / 24;
+            }
+        }
+        for (int i = 0; i < 9; ++i)
+            for (int j = 0; j < 9; ++j) {
+                double s = 0;
+                for (int q = 0; q < 9; ++q) s += Q[i][q] * aT[j][q];
+                kb[i][j] = s / (2 * Adef);
+            }
+        for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) k[FB[i]][FB[j]] = kb[i][j];
+        k[5][5] = kb[1][1] / 10000; k[11][11] = kb[4][4] / 10000; k[17][17] = kb[7][7] / 10000;
+    }
+    {   /* membrane-bending coupling, shell.c:1370-1503 */
+        const double xi = -pow(t, 4) / (12 * den);
+        double xNMC[3][3], cd[3][3], cdL[3][9], BcL[6][9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = 0;
+                for (int q = 0; q < 3; ++q) s += (f->fn[i] * f->fm[q]) * C[q][j];
+                xNMC[i][j] = xi * s;
+            }
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = 0;
+                for (int q = 0; q < 3; ++q) s += C[i][q] * xNMC[q][j];
+                cd[i][j] = s;
+            }
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) cdL[i][j * 3] = cdL[i][j * 3 + 1] = cdL[i][j * 3 + 2] = cd[i][j] / 6;
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 9; ++j) {
+                double s = 0;
+                for (int q = 0; q < 3; ++q) s += Bm[q][i] * cdL[q][j];
+                BcL[i][j] = s;
+            }
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 9; ++j) {
+                double s = 0;
+                for (int q = 0; q < 9; ++q) s += BcL[i][q] * aT[j][q];
+                k[FM[i]][FB[j]] = k[FB[j]][FM[i]] = s;
+            }
+    }
+}
+
+static void strain_curvature(double *strn, double curv[3][3], const double *ddm, const double *ddb,
+                             const double *xl, double Adef, const double *dsl)
+{   /* strn_curv, shell.c:2448-2553: membrane strain increment and the curvature increments at
+     * the three vertices */
+    double Bm[3][6], aT[9][9];
+    membrane_B(xl, Adef, Bm);
+    for (int i = 0; i < 3; ++i) strn[i] = dotn(Bm[i], ddm, 6);
+    dkt_alpha_T(aT, xl, dsl);
+    for (int v = 0; v < 3; ++v)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0;
+            for (int q = 0; q < 9; ++q) s += aT[q][3 * j + v] * ddb[q];
+            curv[v][j] = s / (2 * Adef);
+        }
+}
+
+/* the yielded vertex that controls the element: the one with the smallest phi among those on
+ * the surface (shell.c:214-222) */
+static void pick_vertex(int *yv, const double *phi, int i)
+{
+    if (*yv == 0) *yv = i + 1;
+    else if (phi[i] < phi[*yv - 1]) *yv = i + 1;
+}
+
 static void triad18(double T[18][18], const double *c1, const double *c2, const double *c3)
 {   /* shell.c:285-302 */
     memset(T, 0, 18 * 18 * sizeof(double));
@@ -384,8 +610,29 @@ void orc_shell_element_K(const orc_dims *D, long n, double *K18, const double *e
     const long pe = D->NE_TR + D->NE_FR, pm = 2 * D->NE_TR + 2 * D->NE_FR, pc = D->NE_TR + 3 * D->NE_FR;
     double k[18][18], T[18][18];
     memset(k, 0, sizeof k);
-    shell_elastic(k, emod[pe + n], nu[n], xlocal + n * 3, thick[n], farea[n], slength + n * 3);
-    if (D->ANAFLAG == 2) {
+    int yv = 0;
+    if (D->ANAFLAG == 3) {                             /* shell.c:171-235 */
+        const double fy = g_pl.yield[pe + n], No = fy * thick[n];
+        ivanov iv[3]; double phi[3];
+        memset(iv, 0, sizeof iv);
+        for (int i = 0; i < 3; ++i) {
+            const double *N = g_pl.efN_temp + n * 9 + i * 3, *M = g_pl.efM_temp + n * 9 + i * 3;
+            ivanov_eval(&iv[i], N, M, g_pl.chi_temp[n * 3 + i], fy, thick[n], No);
+            phi[i] = (iv[i].q >= 1e-4) ? iv[i].phi : 0;
+            if (iv[i].q >= 1e-4 && phi[i] >= 1 - PHITOL) pick_vertex(&yv, phi, i);
+        }
+        if (yv != 0) {                                 /* shell.c:255-262 */
+            const int v = yv - 1;
+            double C[3][3]; ivflow fl;
+            plane_stress(emod[pe + n], nu[n], C);
+            ivanov_flow(&fl, &iv[v], g_pl.efN_temp + n * 9 + v * 3, g_pl.efM_temp + n * 9 + v * 3, C,
+                        emod[pe + n], thick[n], fy, g_pl.chi_temp[n * 3 + v], No);
+            shell_plastic(k, &fl, C, xlocal + n * 3, thick[n], deffarea_ip[n], g_pl.defslen_ip + n * 3);
+        }
+    }
+    if (yv == 0)
+        shell_elastic(k, emod[pe + n], nu[n], xlocal + n * 3, thick[n], farea[n], slength + n * 3);
+    if (D->ANAFLAG == 2 || D->ANAFLAG == 3) {
         double cur[3], dm[6] = {0, 0, 0, 0, 0, 0};
         local_membrane_coords(cur, x_temp, minc[pm + n * 3] - 1, minc[pm + n * 3 + 1] - 1,
                               minc[pm + n * 3 + 2] - 1, c1_ip + pc + n * 3, c2_ip + pc + n * 3);
@@ -413,13 +660,13 @@ void orc_stiff_sh(const orc_dims *D, double *ss, const double *emod, const doubl
     }
 }
 
-void orc_forces_sh(const orc_dims *D, double *f_temp, double *ef_ip, double *ef_i, const double *dd,
+int orc_forces_sh(const orc_dims *D, double *f_temp, double *ef_ip, double *ef_i, const double *dd,
                    const double *d_temp, const double *x_temp, const double *emod, const double *nu,
                    const double *xlocal, const double *thick, const double *farea,
                    const double *slength, const double *c1_ip, const double *c2_ip,
                    const double *c3_ip, const double *c1_i, const double *c2_i, const double *c3_i,
                    const long *minc, const long *mcode)
-{   /* forces_sh, shell.c:1593-2400, ANAFLAG 1 and 2 */
+{   /* forces_sh, shell.c:1593-2400 (ANAFLAG 3: extra arrays from orc_set_plastic[_sh]) */
     const long pe = D->NE_TR + D->NE_FR, pm = 2 * D->NE_TR + 2 * D->NE_FR, pc = D->NE_TR + 3 * D->NE_FR;
     const long pmc = 6 * D->NE_TR + 14 * D->NE_FR, pef = 2 * D->NE_TR + 14 * D->NE_FR;
     for (long n = 0; n < D->NE_SH; ++n) {
@@ -438,6 +685,91 @@ void orc_forces_sh(const orc_dims *D, double *f_temp, double *ef_ip, double *ef_
             for (int i = 0; i < 18; ++i) efi[i] = dotn(k[i], dl, 18);
         } else {                                       /* shell.c:1728-1785, 2326-2348 */
             double km[6][6], kb[9][9], cur[3], dm[6] = {0, 0, 0, 0, 0, 0}, ddb[9];
+            int yv = 0;
+            if (D->ANAFLAG == 3) {                     /* shell.c:1786-2213 */
+                const double E = emod[pe + n], t = thick[n], fy = g_pl.yield[pe + n], No = fy * t;
+                const long j0 = minc[pm + n * 3] - 1, k0 = minc[pm + n * 3 + 1] - 1, l0 = minc[pm + n * 3 + 2] - 1;
+                double xi_[3], xp_[3], ddm[6] = {0, 0, 0, 0, 0, 0}, strn[3], curv[3][3], C[3][3], phi[3];
+                local_membrane_coords(xi_, x_temp, j0, k0, l0, c1_i + pc + n * 3, c2_i + pc + n * 3);
+                local_membrane_coords(xp_, g_pl.x_ip, j0, k0, l0, c1_ip + pc + n * 3, c2_ip + pc + n * 3);
+                ddm[2] = xi_[0] - xp_[0]; ddm[4] = xi_[1] - xp_[1]; ddm[5] = xi_[2] - xp_[2];
+                for (int i = 0; i < 18; ++i) V[i] = mc[i] ? dd[mc[i] - 1] : 0.0;
+                for (int i = 0; i < 9; ++i) ddb[i] = dotn(Tp[FB[i]], V, 18);
+                strain_curvature(strn, curv, ddm, ddb, xlocal + n * 3, g_pl.deffarea_ip[n],
+                                 g_pl.defslen_ip + n * 3);
+                plane_stress(E, nu[n], C);
+                ivanov iv[3]; memset(iv, 0, sizeof iv);
+                for (int i = 0; i < 3; ++i) {
+                    double *N = g_pl.efN_temp + n * 9 + i * 3, *M = g_pl.efM_temp + n * 9 + i * 3;
+                    double *chi = g_pl.chi_temp + n * 3 + i;
+                    ivanov_eval(&iv[i], N, M, *chi, fy, t, No);
+                    if (iv[i].q >= 1e-4 && iv[i].phi >= 1 - PHITOL) {          /* shell.c:1877-1992 */
+                        ivflow fl;
+                        ivanov_flow(&fl, &iv[i], N, M, C, E, t, fy, *chi, No);
+                        double fs = 0, fc = 0;
+                        for (int j = 0; j < 3; ++j) { fs += fl.fnC[j] * strn[j]; fc += fl.fmC[j] * curv[i][j]; }
+                        fs *= t; fc *= pow(t, 3) / 12;
+                        const double lambda = (fs + fc) / (fl.jf + fl.kf - fl.Bf * fl.df_da * fl.da_dchi);
+                        *chi += sqrt(pow((E * t) / (3 * fy), 2) * pow(fl.Bf * lambda, 2));
+                        for (int j = 0; j < 3; ++j) {
+                            double s1 = 0, s2 = 0;
+                            for (int q = 0; q < 3; ++q) {
+                                s1 += C[j][q] * (strn[q] - lambda * fl.fn[q]);
+                                s2 += C[j][q] * (curv[i][q] - lambda * fl.fm[q]);
+                            }
+                            N[j] += t * s1; M[j] += pow(t, 3) * s2 / 12;
+                        }
+                    } else {                                                 /* elastic increment */
+                        for (int j = 0; j < 3; ++j) {
+                            double s1 = 0, s2 = 0;
+                            for (int q = 0; q < 3; ++q) { s1 += C[j][q] * strn[q]; s2 += C[j][q] * curv[i][q]; }
+                            N[j] += t * s1; M[j] += pow(t, 3) * s2 / 12;
+                        }
+                    }
+                    ivanov_eval(&iv[i], N, M, *chi, fy, t, No);                /* shell.c:1994-2041 */
+                    if (iv[i].q >= 1e-4) {
+                        phi[i] = iv[i].phi;
+                        if (phi[i] > 1 + 10 * PHITOL) return 1;
+                        else if (phi[i] > 1 + PHITOL) {                       /* return to the surface */
+                            do {
+                                ivflow fl;
+                                ivanov_flow(&fl, &iv[i], N, M, C, E, t, fy, *chi, No);
+                                const double lambda = (phi[i] - 1) / (fl.jf + fl.kf - fl.Bf * fl.df_da * fl.da_dchi);
+                                for (int j = 0; j < 3; ++j) {
+                                    double s1 = 0, s2 = 0;
+                                    for (int q = 0; q < 3; ++q) {
+                                        s1 += C[j][q] * (-lambda * fl.fn[q]);
+                                        s2 += C[j][q] * (-lambda * fl.fm[q]);
+                                    }
+                                    N[j] += t * s1; M[j] += pow(t, 3) * s2 / 12;
+                                }
+                                ivanov_eval(&iv[i], N, M, *chi, fy, t, No);
+                                if (iv[i].q >= 1e-4) phi[i] = iv[i].phi;
+                            } while (phi[i] > 1 + PHITOL);
+                            pick_vertex(&yv, phi, i);
+                        } else if (phi[i] >= 1 - PHITOL) pick_vertex(&yv, phi, i);
+                    } else phi[i] = 0;
+                }
+                if (yv != 0) {                         /* shell.c:2279-2306, 2371-2384 */
+                    const int v = yv - 1;
+                    double k[18][18], dl[18], M18[18][18];
+                    ivflow fl;
+                    memset(k, 0, sizeof k);
+                    ivanov_flow(&fl, &iv[v], g_pl.efN_temp + n * 9 + v * 3, g_pl.efM_temp + n * 9 + v * 3, C,
+                                E, t, fy, g_pl.chi_temp[n * 3 + v], No);
+                    shell_plastic(k, &fl, C, xlocal + n * 3, t, g_pl.deffarea_ip[n], g_pl.defslen_ip + n * 3);
+                    for (int i = 0; i < 18; ++i) dl[i] = dotn(Tp[i], V, 18);
+                    for (int i = 0; i < 18; ++i) def[i] = dotn(k[i], dl, 18);
+                    for (int i = 0; i < 18; ++i)
+                        for (int j = 0; j < 18; ++j) M18[i][j] = dotn(Ti[i], Tp[j], 18);
+                    for (int i = 0; i < 18; ++i) {
+                        double s = 0;
+                        for (int j = 0; j < 18; ++j) s += M18[i][j] * (def[j] + efp[j]);
+                        efi[i] = s;
+                    }
+                }
+            }
+            if (yv == 0) {
             cst_membrane(km, emod[pe + n], nu[n], xlocal + n * 3, thick[n], farea[n]);
             dkt_bending(kb, emod[pe + n], nu[n], xlocal + n * 3, thick[n], farea[n], slength + n * 3);
             local_membrane_coords(cur, x_temp, minc[pm + n * 3] - 1, minc[pm + n * 3 + 1] - 1,
@@ -460,6 +792,7 @@ void orc_forces_sh(const orc_dims *D, double *f_temp, double *ef_ip, double *ef_
                 for (int j = 0; j < 18; ++j) s += M[i][j] * (def[j] + efp[j]);
                 efi[i] = eft[i] + s;
             }
+            }
         }
         for (int i = 0; i < 18; ++i) {                 /* shell.c:2388-2397 */
             double s = 0;
@@ -467,6 +800,7 @@ void orc_forces_sh(const orc_dims *D, double *f_temp, double *ef_ip, double *ef_
             if (mc[i] != 0) f_temp[mc[i] - 1] += s;
         }
     }
+    return 0;
 }
 
 void orc_mass_sh(const orc_dims *D, double *sm, const double *dens, const double *thick, double *farea,
@@ -484,14 +818,6 @@ void orc_mass_sh(const orc_dims *D, double *sm, const double *dens, const double
             if (j != 0) sm[j - 1] += mv;
         }
     }
-}
-
-/* ---------------------------------------------------------- ANAFLAG 3 (material nonlinear) */
-#define PHITOL 1e-4                                    /* frame.c:37, truss.c:100 */
-static struct { const double *yield, *zstrong, *zweak; int *yldflag; } g_pl;
-void orc_set_plastic(const double *yield, const double *zstrong, const double *zweak, int *yldflag)
-{   /* the arrays main.c owns for ANAFLAG 3 (main.c:559-571, 802) */
-    g_pl.yield = yield; g_pl.zstrong = zstrong; g_pl.zweak = zweak; g_pl.yldflag = yldflag;
 }
 
 /* --------------------------------------------------------------------------------- truss.c */

@@ -36,7 +36,8 @@ void orc_stiff_sh(const orc_dims *D, double *ss, const double *emod, const doubl
                   const double *farea, const double *deffarea_ip, const double *slength,
                   const double *c1_ip, const double *c2_ip, const double *c3_ip, const long *maxa,
                   const long *minc, const long *mcode);
-void orc_forces_sh(const orc_dims *D, double *f_temp, double *ef_ip, double *ef_i, const double *dd,
+/* returns forces_sh's code: 0, or 1 when a vertex ends beyond 1 + 10*phitol (shell.c:2044-2046) */
+int  orc_forces_sh(const orc_dims *D, double *f_temp, double *ef_ip, double *ef_i, const double *dd,
                    const double *d_temp, const double *x_temp, const double *emod, const double *nu,
                    const double *xlocal, const double *thick, const double *farea,
                    const double *slength, const double *c1_ip, const double *c2_ip,
@@ -54,6 +55,10 @@ void orc_shell_element_K(const orc_dims *D, long n, double *K18, const double *e
 /* ANAFLAG 3: the material arrays main.c owns (yield [TR+FR+SH+BR], zstrong / zweak [FR]) and the
  * member-end flags yldflag [FR*2] that forces_fr mutates; read by the truss and frame routines */
 void orc_set_plastic(const double *yield, const double *zstrong, const double *zweak, int *yldflag);
+/* shells: equivalent plastic curvature chi_temp [SH*3] and vertex stress resultants efN_temp /
+ * efM_temp [SH*9] (mutated by orc_forces_sh), previous-iterate coordinates, deformed area / sides */
+void orc_set_plastic_sh(double *chi_temp, double *efN_temp, double *efM_temp, const double *x_ip,
+                        const double *deffarea_ip, const double *defslen_ip);
 
 /* truss.c */
 void orc_stiff_tr(const orc_dims *D, double *ss, const double *emod, const double *carea,

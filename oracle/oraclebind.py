@@ -45,15 +45,20 @@ def _gen(s, gen):
     return (s.c1, s.c2, s.c3, s.ef, s.defllen, s.deffarea, s.efFE, s.x)
 
 
-def _plastic(l, m, s):
+def _plastic(l, m, s, gen="ip"):
     if m.ANAFLAG == 3:
         l.orc_set_plastic(P(m.yld), P(m.zstrong), P(m.zweak), P(s.yldflag))
+        if gen == "ip":
+            l.orc_set_plastic_sh(P(s.chi_temp), P(s.efN_temp), P(s.efM_temp), P(s.x_ip),
+                                 P(s.deffarea_ip), P(s.defslen_ip))
+        else:
+            l.orc_set_plastic_sh(P(s.chi), P(s.efN), P(s.efM), P(s.x), P(s.deffarea), P(s.defslen))
 
 
 def stiff(m, s, SLVFLAG=None, gen="ip"):
     slv = m.SLVFLAG if SLVFLAG is None else SLVFLAG
     l = lib(); D = dims(m, SLVFLAG=slv)
-    _plastic(l, m, s)
+    _plastic(l, m, s, gen)
     ss = np.zeros(m.lss if slv == 0 else m.NEQ * m.NEQ)
     c1, c2, c3, ef, dl, dfa, efFE, x = _gen(s, gen)
     if m.NE_TR:
@@ -87,7 +92,7 @@ def shell_element_K(m, s, n, gen="ip"):
 def update_forces(m, s, dd, dlpf=1.0, itecnt=0):
     l = lib(); D = dims(m)
     _plastic(l, m, s)
-    fr = 0
+    fr = sh = 0
     cdl = C.c_double(dlpf)
     dd = np.ascontiguousarray(dd, dtype=np.float64)
     s.d_temp += dd
@@ -106,12 +111,12 @@ def update_forces(m, s, dd, dlpf=1.0, itecnt=0):
                         P(s.c2_i), P(s.c3_i), P(m.mendrel), P(m.mcode), C.byref(cdl),
                         C.c_int(itecnt))
     if m.NE_SH:
-        l.orc_forces_sh(C.byref(D), P(s.f_temp), P(s.ef_ip), P(s.ef_i), P(dd), P(s.d_temp),
+        sh = l.orc_forces_sh(C.byref(D), P(s.f_temp), P(s.ef_ip), P(s.ef_i), P(dd), P(s.d_temp),
                         P(s.x_temp), P(m.emod), P(m.nu), P(m.xlocal), P(m.thick), P(s.farea),
                         P(s.slength), P(s.c1_ip), P(s.c2_ip), P(s.c3_ip), P(s.c1_i), P(s.c2_i),
                         P(s.c3_i), P(m.minc), P(m.mcode))
     s.ef_ip[:] = s.ef_i
-    return fr, 0, cdl.value
+    return fr, sh, cdl.value
 
 
 def forces_linear(m, s, d, dlpf=0.0):

@@ -35,6 +35,7 @@ def cases():
         "lattice_lin_3": ("lattice_model", dict(n=3, ANAFLAG=1), None),
         "lattice_3_plastic": ("lattice_model", dict(n=3, ANAFLAG=3, load=200.0), "fe"),
         "truss_3_plastic": ("truss_model", dict(n=3, ANAFLAG=3, load=50.0), None),
+        "plate_4x3_plastic": ("plate_model", dict(nx=4, ny=3, z_bump=0.03, ANAFLAG=3), None),
         "brick_2x2x2": ("brick_model", dict(nx=2, ny=2, nz=2, distort=0.1), None),
         "brick_skin_2x2x1": ("brick_model", dict(nx=2, ny=2, nz=1, distort=0.05, skin=True), None),
     }
@@ -78,6 +79,8 @@ def record(name, B=R, n_iter=3):
         out["f_lin"] = B.forces_linear(m, s, d)
         out["ef_lin"] = s.ef.copy()
         return m, out
+    if m.ANAFLAG == 3 and m.NE_SH:
+        return m, record_plastic_shell(m, s, out, B)
     if m.ANAFLAG == 3:
         return m, record_plastic(m, s, out, B)
     s.begin_increment()
@@ -129,6 +132,35 @@ def record_plastic(m, s, out, B):
             continue
         s.end_iteration(); s.commit(); s.begin_increment()
         k += 1; scale = 1.0
+    out["ncalls"] = call
+    return out
+
+
+def record_plastic_shell(m, s, out, B, n_steps=16):
+    """material-nonlinear shells (ANAFLAG 3, Ivanov's criterion).  forces_sh returns 1 whenever a
+    vertex ends more than 10*phitol beyond the yield surface, so the walk does what main.c:2035-2063
+    does: halve the increment and repeat it from the committed state; converged increments grow by
+    1.5, the direction reverses after step 10 (unloading).  Every call's K_t, return code, f_temp,
+    ef_i and the plastic state (chi, efN, efM) are kept."""
+    base = np.random.default_rng(5).uniform(-1.0, 1.0, size=m.NEQ)
+    out["base"] = base
+    s.begin_increment()
+    scale, done, call, dds = 2e-4, 0, 0, []
+    while done < n_steps and call < 150:
+        dd = (1.0 if done < 10 else -1.0) * scale * base
+        out[f"K_sky_{call}"] = B.stiff(m, s, SLVFLAG=0)
+        fr, sh, dl = B.update_forces(m, s, dd, itecnt=0)
+        out[f"dd_{call}"] = dd; out[f"ret_{call}"] = np.array([fr, sh])
+        if sh == 0:
+            out[f"f_{call}"] = s.f_temp.copy(); out[f"ef_{call}"] = s.ef_i.copy()
+            out[f"chi_{call}"] = s.chi_temp.copy(); out[f"efN_{call}"] = s.efN_temp.copy()
+            out[f"efM_{call}"] = s.efM_temp.copy()
+        call += 1
+        if sh != 0:
+            scale /= 2; s.begin_increment()
+            continue
+        s.end_iteration(); s.commit(); s.begin_increment()
+        done += 1; scale *= 1.5
     out["ncalls"] = call
     return out
 

@@ -171,3 +171,94 @@ def test_plastic_golden_walk(gpu, name):
     if m.NE_FR:
         assert seen == {0, 1, 2}
     asm.close()
+
+
+def test_shell_plastic_golden_walk(gpu):
+    """DKT shells with Ivanov's yield criterion (stiff_sh shell.c:171-283 + stiffm_sh, forces_sh
+    shell.c:1786-2325) against the fixture recorded from the unmodified reference: K_t (elastic and
+    elasto-plastic), return codes, f_temp, ef_i and the plastic state after every call"""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as G
+    name = "plate_4x3_plastic"
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    m = G.build(name)
+    asm = cb.Assembler(m, layout=cb.CB_MAT_BOTH)
+    asm.begin_increment()
+    codes, plastic_K = [], 0
+    for c in range(int(g["ncalls"])):
+        asm.stiff()
+        assert relerr(asm.skyline(), g[f"K_sky_{c}"]) < TOL, c
+        f, fr, sh, _ = asm.update_forces(g[f"dd_{c}"], itecnt=0)
+        assert (fr, sh) == tuple(int(v) for v in g[f"ret_{c}"]), c
+        codes.append(sh)
+        if sh != 0:
+            asm.begin_increment()
+            continue
+        assert relerr(f, g[f"f_{c}"]) < TOL, c
+        assert relerr(asm.download("EF_I"), g[f"ef_{c}"]) < TOL, c
+        assert relerr(asm.download("EFN_TEMP"), g[f"efN_{c}"]) < TOL, c
+        assert relerr(asm.download("EFM_TEMP"), g[f"efM_{c}"]) < TOL, c
+        chi = g[f"chi_{c}"]
+        assert np.allclose(asm.download("CHI_TEMP"), chi, rtol=1e-9, atol=1e-18), c
+        plastic_K += int((chi > 0).any())
+        asm.end_iteration(); asm.commit(); asm.begin_increment()
+        assert relerr(asm.download("EFN"), g[f"efN_{c}"]) < TOL
+    assert 1 in codes and 0 in codes and plastic_K > 0
+    asm.close()
+
+
+def test_shell_plastic_lockstep_csc(gpu, ref):
+    """a larger plate through the CSC tile kernel, reference and device in lockstep"""
+    m = meshgen.plate_model(6, 5, z_bump=0.05, ANAFLAG=3, SLVFLAG=2)
+    base = np.random.default_rng(21).uniform(-1.0, 1.0, size=m.NEQ)
+    asm = cb.Assembler(m, layout=cb.CB_MAT_CSC)
+    s = ref.RefState(m)
+    s.begin_increment(); asm.begin_increment()
+    scale, done, calls, yielded = 2e-4, 0, 0, 0
+    while done < 12 and calls < 120:
+        calls += 1
+        K_ref = ref.stiff(m, s, SLVFLAG=2).reshape(m.NEQ, m.NEQ)
+        asm.stiff()
+        Ap, Ai, Ax = asm.csc()
+        K = np.zeros((m.NEQ, m.NEQ))
+        for c in range(m.NEQ):
+            K[Ai[Ap[c]:Ap[c + 1]], c] = Ax[Ap[c]:Ap[c + 1]]
+        assert relerr(K, K_ref.T) < TOL, calls
+        dd = scale * base
+        fr, sh, _ = ref.update_forces(m, s, dd, itecnt=0)
+        f, gfr, gsh, _ = asm.update_forces(dd, itecnt=0)
+        assert (gfr, gsh) == (fr, sh), calls
+        if sh:
+            scale /= 2
+            s.begin_increment(); asm.begin_increment()
+            continue
+        assert relerr(f, s.f_temp) < TOL, calls
+        assert relerr(asm.download("EFN_TEMP"), s.efN_temp) < TOL
+        assert relerr(asm.download("EFM_TEMP"), s.efM_temp) < TOL
+        yielded = int((s.chi_temp > 0).sum())
+        s.end_iteration(); asm.end_iteration(); s.commit(); asm.commit()
+        s.begin_increment(); asm.begin_increment()
+        done += 1; scale *= 1.5
+    assert done == 12 and yielded > 0
+    asm.close()
+
+
+def test_shell_plastic_newton(gpu, ref):
+    """load-controlled NR of a shallow shell through first yield: forces_sh's return code 1 drives
+    the sub-incrementation of main.c:2035-2063; same history, displacements to 1e-9"""
+    m = meshgen.plate_model(6, 6, props=(2.1e11, 0.3, 0.05, 8050.0, 3.45e8), load=-1.2e7, z_bump=0.1,
+                            ANAFLAG=3)
+    kw = dict(lpfmax=0.12, lpf=0.03, dlpf=0.03, dlpfmax=0.03, dlpfmin=1e-6, solmin=1, toldisp=1e-6,
+              tolforc=1e-6, tolener=1e-6, itemax=60, submax=40,
+              hist_dof=int(m.jcode.reshape(-1, 7)[m.meta["centre"] - 1, 2] - 1))
+    asm = cb.Assembler(m, layout=cb.CB_MAT_SKYLINE)
+    d, res, hist = cb.newton_static(asm, m.q, **kw)
+    d_ref, stat, hist_ref = ref_newton(m, ref, m.q, **kw)
+    assert (res.status, res.increments, res.iterations) == (stat["status"], stat["increments"], stat["iterations"])
+    assert res.status == 0 and res.increments > 50
+    assert np.allclose(hist[:, 0], hist_ref[:, 0], rtol=1e-9, atol=0)
+    assert np.array_equal(hist[:, 1], hist_ref[:, 1])
+    assert relerr(d, d_ref) < 1e-9
+    assert (asm.download("CHI") > 0).sum() >= 5            # really went plastic
+    asm.close()

@@ -148,7 +148,7 @@ struct cb_handle {
     Plan plan_csc, plan_sky;
     DevBuf<int> Ap, Ai;
     DevBuf<long> maxa;
-    DevBuf<double> Ax, ss;
+    DevBuf<double> Ax, ss, Mx;    // Mx: full-order mass on the CSC pattern (models with bricks)
     long map_bytes = 0;
 };
 
@@ -347,7 +347,10 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
     // ---- bricks (linear, stiffness only; brick.c:127-129 reads emod/nu at TR+FR+SH+i) -------
     if (BR) {
         std::vector<double> c((size_t)BR * 4, 0.0);
-        for (long e = 0; e < BR; ++e) { c[e * 4] = m->emod[TR + FR + SH + e]; c[e * 4 + 1] = m->nu[SH + e]; }
+        for (long e = 0; e < BR; ++e) {
+            c[e * 4] = m->emod[TR + FR + SH + e]; c[e * 4 + 1] = m->nu[SH + e];
+            if (m->dens) c[e * 4 + 2] = m->dens[TR + FR + SH + e];   // mass_br: pdens+ptr+i (brick.c:510)
+        }
         if (h->br_const.upload(c)) BAIL(CB_ERR_CUDA);
     }
     // ---- frames ----------------------------------------------------------------------------
@@ -459,7 +462,7 @@ extern "C" void cb_destroy(cb_handle *h)
                               &h->d_temp, &h->sm, &h->qvec, &h->sums, &h->sums_part, &h->sh_const, &h->sh_keb, &h->sh_kebc, &h->sh_der, &h->sh_Nm, &h->sh_fg,
                               &h->sh_dens, &h->tr_const, &h->tr_fg, &h->tr_dens, &h->fr_const,
                               &h->fr_offset, &h->fr_efFE_ref, &h->fr_fg, &h->fr_dens, &h->br_const,
-                              &h->Ax, &h->ss, &h->fr_plast, &h->fr_tau, &h->tr_py})
+                              &h->Ax, &h->ss, &h->Mx, &h->fr_plast, &h->fr_tau, &h->tr_py})
         b->release();
     for (DevBuf<int32_t> *b : {&h->fr_yldflag, &h->fr_ynew, &h->fr_code, &h->fr_trip, &h->sh_yv, &h->sh_trip})
         b->release();
@@ -1225,9 +1228,32 @@ extern "C" int cb_mass(cb_handle *h)
         return fail(CB_ERR_CUDA, "mass launch");
     h->keb_dirty = true;      // farea / slength were refreshed from x (App. B.5)
     h->krec_fresh = false;
+    if (h->NE_BR && (h->layout & CB_MAT_CSC) && h->plan_csc.ntiles) {
+        // bricks: the reference only has the full-order [NEQ][NEQ] mass (mass_br, brick.c:525-536);
+        // it is assembled here on the CSC pattern of K_t by the same tile kernel
+        if (!h->Mx.p && h->Mx.alloc((size_t)h->nnz)) return CB_ERR_CUDA;
+        CbStiffArgs a{};
+        a.d = d; a.x = h->x.p; a.sh_frame = h->sh_frame[0].p; a.contribs = h->contribs.p;
+        a.tiles = h->plan_csc.tiles.p; a.ntiles = h->plan_csc.ntiles; a.tpairs = h->plan_csc.tpairs.p;
+        a.tcontribs = h->plan_csc.tcontribs.p; a.tile_smem_out = h->plan_csc.tile_smem_out;
+        a.max_dof = h->max_dof; a.mixed = h->mixed; a.out = h->Mx.p; a.mass_mode = 1;
+        a.sh_dens = h->sh_dens.p;
+        if (cbk_stiff(a, h->stream, &h->launches)) return fail(CB_ERR_CUDA, "mass assembly launch");
+    }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return CB_OK;
 }
+
+extern "C" int cb_get_mass_csc_values(cb_handle *h, double *Mx)
+{
+    if (!h || !Mx) return fail(CB_ERR_ARG, "null argument");
+    if (!h->Mx.p) return fail(CB_ERR_ARG, "no CSC mass matrix: cb_mass assembles one for models with bricks");
+    cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(Mx, h->Mx.p, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToHost));
+    return CB_OK;
+}
+extern "C" double *cb_dev_Mx(cb_handle *h) { return h ? h->Mx.p : nullptr; }
 
 // ------------------------------------------------------------------------------------------
 // results

@@ -202,6 +202,11 @@ struct CbStiffArgs {
     double *out;             // Ax or ss
     const long *maxa;        // device copy (skyline mode) or nullptr
     int skyline;
+    // mass mode (cb_mass with bricks): the same tiles assemble the full-order mass matrix of the
+    // reference's dense layout - consistent brick mass (mass_br, brick.c:399-537), lumped shell
+    // mass on the diagonal (mass_sh, shell.c:1576-1588) - onto the CSC pattern of K_t
+    int mass_mode;
+    const double *sh_dens;   // [NE_SH]
 };
 
 struct CbForceArgs {

@@ -306,6 +306,40 @@ __device__ __noinline__ void brick_block(const CbStiffArgs &A, int e, int a, int
         for (int j = 0; j < 3; ++j) blk[i * ld + j] = K[i][j];
 }
 
+// M_ab (3x3) of 8-node brick e: consistent mass rho * sum_gp h_a h_b detJ on the diagonal
+// (mass_br, brick.c:399-537; H^T H couples equal displacement components only)
+__device__ __noinline__ void brick_mass_block(const CbStiffArgs &A, int e, int a, int b, double *blk, int ld)
+{
+    const int sr[8] = {+1, -1, -1, +1, +1, -1, -1, +1};
+    const int ss[8] = {+1, +1, -1, -1, +1, +1, -1, -1};
+    const int st[8] = {+1, +1, +1, +1, -1, -1, -1, -1};
+    const double rho = A.d.br_const[(long)e * 4 + 2];
+    double X[8][3];
+    for (int n = 0; n < 8; ++n) {
+        const long jt = A.d.br_nodes[(long)e * 8 + n];
+        for (int m = 0; m < 3; ++m) X[n][m] = A.x[jt * 3 + m];
+    }
+    const double gp = 0.57735026918962576451;
+    double mab = 0;
+    for (int q = 0; q < 8; ++q) {
+        const double R = (q & 4) ? -gp : gp, S = (q & 2) ? -gp : gp, T = (q & 1) ? -gp : gp;
+        double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int n = 0; n < 8; ++n) {
+            const double dr = sr[n] * (1 + ss[n] * S) * (1 + st[n] * T) / 8.0;
+            const double ds = ss[n] * (1 + sr[n] * R) * (1 + st[n] * T) / 8.0;
+            const double dt = st[n] * (1 + sr[n] * R) * (1 + ss[n] * S) / 8.0;
+            for (int m = 0; m < 3; ++m) { J[0][m] += dr * X[n][m]; J[1][m] += ds * X[n][m]; J[2][m] += dt * X[n][m]; }
+        }
+        const double det = J[0][0] * J[1][1] * J[2][2] - J[0][0] * J[1][2] * J[2][1] - J[0][1] * J[1][0] * J[2][2] +
+                           J[0][1] * J[1][2] * J[2][0] + J[0][2] * J[1][0] * J[2][1] - J[0][2] * J[1][1] * J[2][0];
+        const double ha = (1 + sr[a] * R) * (1 + ss[a] * S) * (1 + st[a] * T) / 8.0;
+        const double hb = (1 + sr[b] * R) * (1 + ss[b] * S) * (1 + st[b] * T) / 8.0;
+        mab += rho * (ha * hb) * det;
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) blk[i * ld + j] = (i == j) ? mab : 0.0;
+}
+
 // K_ab (3x3) of truss e (truss.c:102-166)
 __device__ __noinline__ void truss_block(const CbStiffArgs &A, int e, int a, int b, double *blk,
                                             int ld)
@@ -427,7 +461,7 @@ k_assemble_tiles(CbStiffArgs A)
     CbContrib ct{}; ct.type = 0xff;
     if (t < tl.ns) ct = A.tcontribs[tl.t0 + t];
     ShellIn in;
-    if (ND >= 6 && ct.type == CB_T_SHELL) shell_load(A, ct, (long)tl.c0 + ct.pad, in);
+    if (ND >= 6 && ct.type == CB_T_SHELL && !A.mass_mode) shell_load(A, ct, (long)tl.c0 + ct.pad, in);
 
     for (;;) {
         const long next = tile + gridDim.x;
@@ -440,7 +474,28 @@ k_assemble_tiles(CbStiffArgs A)
         if (ct.type != 0xff) {
             double *stg = stage + ct.pad;
             const int col = ct.pad;             // column of `stage` / entry of ndof: reference order
-            if (ct.type == CB_T_SHELL) {
+            if (A.mass_mode) {
+#pragma unroll
+                for (int i = 0; i < NN; ++i) stg[i * STR] = 0.0;
+                if (ct.type == CB_T_BRICK) {
+                    double blk[9];
+                    brick_mass_block(A, ct.e, ct.a, ct.b, blk, 3);
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) stg[(p * ND + p) * STR] = blk[p * 3 + p];
+                    ndof[col] = 3;
+                } else if (ct.type == CB_T_SHELL && ND >= 6) {
+                    if (ct.a == ct.b) {         // lumped: rho A t / 3, rotations * t^2 / 12
+                        const double th = SOA(A.d.sh_const, 2, ct.e, A.d.NE_SH);
+                        const double Mtot = A.sh_dens[ct.e] * SOA(A.d.sh_const, 4, ct.e, A.d.NE_SH) * th;
+#pragma unroll
+                        for (int p = 0; p < 6; ++p)
+                            stg[(p * ND + p) * STR] = (p < 3) ? Mtot / 3 : Mtot / 3 * (th * th) / 12;
+                    }
+                    ndof[col] = 6;
+                } else {
+                    ndof[col] = (ct.type == CB_T_FRAME) ? 7 : 3;
+                }
+            } else if (ct.type == CB_T_SHELL) {
                 if constexpr (ND >= 6) {
                     if (ND > 6) {
 #pragma unroll
@@ -487,7 +542,7 @@ k_assemble_tiles(CbStiffArgs A)
         CbContrib ctn{}; ctn.type = 0xff;
         if (has_next && t < tln.ns) ctn = A.tcontribs[tln.t0 + t];
         __syncthreads();
-        if (ND >= 6 && ctn.type == CB_T_SHELL) shell_load(A, ctn, (long)tln.c0 + ctn.pad, in);
+        if (ND >= 6 && ctn.type == CB_T_SHELL && !A.mass_mode) shell_load(A, ctn, (long)tln.c0 + ctn.pad, in);
 
         // ---- phase 2: segmented reduction over the sorted contribution list, one thread per
         // (joint-pair block, column): ND rows of `stage` summed over the block's contributions in

@@ -35,7 +35,7 @@ EXPORTS = [
     "cb_dev_Ap", "cb_dev_Ai", "cb_download", "cb_upload", "cb_launch_count",
     "cb_last_stiff_ms", "cb_last_forces_ms", "cb_last_assemble_ms", "cb_timer_start", "cb_timer_stop_ms", "cb_set_dd", "cb_host_alloc",
     "cb_host_free", "cb_map_bytes", "cb_sync", "cb_stream", "cb_set_q", "cb_residual_sums",
-    "cb_dev_sums", "cb_get_sums", "cb_get_yldflag", "cb_set_yldflag",
+    "cb_dev_sums", "cb_get_sums", "cb_get_yldflag", "cb_set_yldflag", "cb_get_mass_csc_values", "cb_dev_Mx",
 ]
 
 
@@ -87,7 +87,7 @@ def load_library(path=None):
     lib.cb_host_alloc.argtypes = [C.c_ulong]
     lib.cb_host_free.restype = None
     lib.cb_host_free.argtypes = [C.c_void_p]
-    for n in ("cb_dev_Ax", "cb_dev_skyline", "cb_dev_f", "cb_dev_dd", "cb_dev_Ap", "cb_dev_Ai",
+    for n in ("cb_dev_Mx", "cb_dev_Ax", "cb_dev_skyline", "cb_dev_f", "cb_dev_dd", "cb_dev_Ap", "cb_dev_Ai",
               "cb_stream", "cb_dev_sums"):
         getattr(lib, n).restype = C.c_void_p
     lib.cb_destroy.restype = None
@@ -158,6 +158,13 @@ class Assembler:
         sm = np.zeros(self.m.NEQ)
         self._check(self.lib.cb_get_mass(self.h, _p(sm)))
         return sm
+
+    def mass_csc(self):
+        """full-order mass matrix values on the CSC pattern of K_t (models with bricks)"""
+        self._check(self.lib.cb_mass(self.h))
+        Mx = np.zeros(self.lib.cb_csc_nnz(self.h))
+        self._check(self.lib.cb_get_mass_csc_values(self.h, _p(Mx)))
+        return Mx
 
     def update_forces(self, dd, dlpf=1.0, itecnt=0, want_f=True):
         dd = np.ascontiguousarray(dd, dtype=np.float64)

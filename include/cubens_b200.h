@@ -159,6 +159,11 @@ int  cb_get_csc_values(cb_handle *h, double *Ax);
 /* returns the compacted nnz (Ap/Ai/Ax sized for cb_csc_nnz), or -1                        */
 long cb_csc_compact(cb_handle *h, double drop_tol, int *Ap, int *Ai, double *Ax);
 int  cb_get_mass(cb_handle *h, double *sm_diag);       /* diagonal [NEQ], SLVFLAG 0 layout */
+/* models with bricks: cb_mass also assembles the reference's full-order mass matrix (consistent
+ * mass_br brick.c:399-537, lumped mass_sh on the diagonal shell.c:1576-1588; dense [NEQ][NEQ] in
+ * the reference) on the CSC pattern of K_t: Mx[nnz], same Ap / Ai                            */
+int  cb_get_mass_csc_values(cb_handle *h, double *Mx);
+double *cb_dev_Mx(cb_handle *h);
 int  cb_get_f(cb_handle *h, double *f_temp);           /* [NEQ]                            */
 
 /* device-resident views for consumers that stay on the GPU (no copies): */

@@ -815,7 +815,9 @@ void orc_mass_sh(const orc_dims *D, double *sm, const double *dens, const double
         for (int ie = 0; ie < 18; ++ie) {
             long j = mcode[i * 18 + ie];
             double mv = (ie % 6 < 3) ? Mtot / 3 : Mtot / 3 * (thick[i] * thick[i]) / 12;
-            if (j != 0) sm[j - 1] += mv;
+            if (j == 0) continue;
+            if (D->SLVFLAG == 0) sm[j - 1] += mv;
+            else sm[(j - 1) * D->NEQ + j - 1] += mv;   /* full-order layout, shell.c:1576-1588 */
         }
     }
 }
@@ -1430,6 +1432,51 @@ void orc_stiff_br(const orc_dims *D, double *ss, const double *x, const double *
             for (int je = 0; je < 24; ++je) {
                 long j = mcode[pmc + e * 24 + ie], k = mcode[pmc + e * 24 + je];
                 if (j != 0 && k != 0) ss[(j - 1) * D->NEQ + k - 1] += kbr[je][ie];
+            }
+    }
+}
+
+void orc_mass_br(const orc_dims *D, double *sm, const double *dens, const double *x, const long *minc,
+                 const long *mcode)
+{   /* mass_br + jacob, brick.c:399-537: consistent mass rho H^T H detJ, full-order scatter */
+    const long pe = D->NE_TR + D->NE_FR + D->NE_SH;
+    const long pm = 2 * D->NE_TR + 2 * D->NE_FR + 3 * D->NE_SH;
+    const long pmc = 6 * D->NE_TR + 14 * D->NE_FR + 18 * D->NE_SH;
+    const double gp[2] = {1.0 / sqrt(3), -1.0 / sqrt(3)};
+    for (long e = 0; e < D->NE_BR; ++e) {
+        double mbr[24][24];
+        memset(mbr, 0, sizeof mbr);
+        for (int r = 0; r < 2; ++r) for (int s = 0; s < 2; ++s) for (int t = 0; t < 2; ++t) {
+            const double R = gp[r], S = gp[s], T = gp[t];
+            double jac[9], h[8];
+            memset(jac, 0, sizeof jac);
+            for (int n = 0; n < 8; ++n) {              /* jacob, brick.c:572-697 */
+                const long jt = minc[pm + e * 8 + n] - 1;
+                const double cr = (BG[n] * ((S + BS[n]) * (T + BT[n]))) / 8.0;
+                const double cs = (BG[n] * (R / 8.0 + BR[n] * (1.0 / 8.0))) * (T + BT[n]);
+                const double ct = (BG[n] * (R / 8.0 + BR[n] * (1.0 / 8.0))) * (S + BS[n]);
+                for (int m = 0; m < 3; ++m) {
+                    jac[0 + m] += cr * x[jt * 3 + m];
+                    jac[3 + m] += cs * x[jt * 3 + m];
+                    jac[6 + m] += ct * x[jt * 3 + m];
+                }
+            }
+            const double detJ = jac[0] * jac[4] * jac[8] - jac[0] * jac[5] * jac[7] - jac[1] * jac[3] * jac[8] +
+                                jac[1] * jac[5] * jac[6] + jac[2] * jac[3] * jac[7] - jac[2] * jac[4] * jac[6];
+            for (int n = 0; n < 8; ++n)                /* brick.c:468-475 */
+                h[n] = (1.0 + BR[n] * R) * (1.0 + BS[n] * S) * (1.0 + BT[n] * T) / 8.0;
+            for (int l = 0; l < 24; ++l)               /* brick.c:505-522 */
+                for (int j = 0; j < 24; ++j) {
+                    double sum = 0;
+                    for (int q = 0; q < 3; ++q)
+                        sum += ((j % 3 == q) ? h[j / 3] : 0.0) * ((l % 3 == q) ? h[l / 3] : 0.0);
+                    mbr[j][l] += dens[pe + e] * sum * detJ;
+                }
+        }
+        for (int ie = 0; ie < 24; ++ie)                /* brick.c:525-536 */
+            for (int je = 0; je < 24; ++je) {
+                long j = mcode[pmc + e * 24 + ie], k = mcode[pmc + e * 24 + je];
+                if (j != 0 && k != 0) sm[(j - 1) * D->NEQ + k - 1] += mbr[je][ie];
             }
     }
 }

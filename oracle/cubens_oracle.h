@@ -95,6 +95,9 @@ void orc_mass_fr(const orc_dims *D, double *sm, const double *carea, double *lle
 void orc_stiff_br(const orc_dims *D, double *ss, const double *x, const double *emod, const double *nu,
                   const long *minc, const long *mcode);
 
+void orc_mass_br(const orc_dims *D, double *sm, const double *dens, const double *x, const long *minc,
+                 const long *mcode);
+
 /* solve.c:110-119: dense row-major [NEQ][NEQ] -> Ap/Ai/Ax with |a| > tol; returns nnz */
 long orc_dense_to_csc(long neq, const double *ss, double tol, int *Ap, int *Ai, double *Ax);
 

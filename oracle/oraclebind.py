@@ -139,9 +139,10 @@ def forces_linear(m, s, d, dlpf=0.0):
     return f
 
 
-def mass(m, s):
-    l = lib(); D = dims(m, SLVFLAG=0)
-    sm = np.zeros(m.NEQ)
+def mass(m, s, SLVFLAG=0):
+    l = lib(); D = dims(m, SLVFLAG=SLVFLAG)
+    sm = np.zeros(m.NEQ if SLVFLAG == 0 else m.NEQ * m.NEQ)
+
     if m.NE_TR:
         l.orc_mass_tr(C.byref(D), P(sm), P(m.carea), P(s.llength), P(m.dens), P(s.x), P(m.minc),
                       P(m.mcode))
@@ -151,6 +152,9 @@ def mass(m, s):
     if m.NE_SH:
         l.orc_mass_sh(C.byref(D), P(sm), P(m.dens), P(m.thick), P(s.farea), P(s.slength), P(s.x),
                       P(m.minc), P(m.mcode))
+    if m.NE_BR:
+        assert SLVFLAG != 0 and not (m.NE_TR or m.NE_FR)
+        l.orc_mass_br(C.byref(D), P(sm), P(m.dens), P(s.x), P(m.minc), P(m.mcode))
     return sm
 
 

@@ -71,6 +71,7 @@ def record(name, B=R, n_iter=3):
     rng = np.random.default_rng(2026)
     if m.NE_BR:
         out["K_dense"] = B.stiff(m, s, SLVFLAG=2, gen="c")
+        out["M_dense"] = B.mass(m, s, SLVFLAG=2)
         return m, out
     if m.ANAFLAG == 1:
         out["K_sky"] = B.stiff(m, s, SLVFLAG=0, gen="c")

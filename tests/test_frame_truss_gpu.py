@@ -89,3 +89,21 @@ def test_brick_stiffness(gpu, ref, name):
     gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
     assert relerr(K, gold["K_dense"].reshape(m.NEQ, m.NEQ).T) < TOL
     asm.close()
+
+
+@pytest.mark.parametrize("name", ["brick_2x2x2", "brick_skin_2x2x1"])
+def test_brick_mass(gpu, ref, name):
+    """mass_br (consistent, brick.c:399-537) + lumped mass_sh of the skin in the reference's
+    full-order layout vs the CSC mass matrix the device assembles on the pattern of K_t"""
+    m = G.build(name)
+    asm = cb.Assembler(m, layout=cb.CB_MAT_CSC)
+    s = ref.RefState(m)
+    dense = ref.mass(m, s, SLVFLAG=2).reshape(m.NEQ, m.NEQ)
+    Mx = asm.mass_csc()
+    Ap, Ai, _ = asm.csc()
+    M = csc_to_dense(m.NEQ, Ap, Ai, Mx)
+    assert relerr(M, dense.T) < TOL
+    assert np.abs(M - M.T).max() <= 1e-14 * np.abs(M).max() and np.abs(M).max() > 0
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    assert relerr(M, gold["M_dense"].reshape(m.NEQ, m.NEQ).T) < TOL
+    asm.close()

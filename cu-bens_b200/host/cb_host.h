@@ -41,6 +41,19 @@ int cb_newton_static(cb_handle *h, long neq, const long *maxa, long lss, const d
                      const cb_nr_params *p, double *d_out, cb_nr_result *res, double *hist,
                      int max_hist, long hist_dof);
 
+/* ---- transient drivers (cb_newmark.c) --------------------------------------------------------
+ * pinpt [NEQ][ntstps]: the load histories load() stores (model.c:1490-1535), dt = ttot / (ntstps-1),
+ * alpham / alphaf: generalized-alpha parameters (main.c:3337-3351).  hist receives one row per time
+ * step: time, iterations, d[0..NEQ) - what the reference hands to output().  Models with
+ * prescribed support motion (NBC != 0) are not supported.                                       */
+void cb_sky_mult(long neq, const long *maxa, const double *ss, double *v);   /* solve.c:700-756 */
+int cb_newmark_nonlinear(cb_handle *h, long neq, const long *maxa, long lss, const double *pinpt,
+                         long ntstps, double dt, double alpham, double alphaf,
+                         const cb_nr_params *p, double *hist, cb_nr_result *res);
+int cb_newmark_linear(cb_handle *h, long neq, const long *maxa, long lss, const double *pinpt,
+                      long ntstps, double dt, double alpham, double alphaf, const double *um0,
+                      const double *vm0, const double *am0, double *hist, cb_nr_result *res);
+
 #ifdef __cplusplus
 }
 #endif

@@ -372,3 +372,31 @@ def sky_factor_solve(maxa, ss, rhs):
         raise CubensError("non-positive definite stiffness matrix")
     hl.cb_sky_solve(C.c_long(neq), _p(maxa), _p(ss), _p(v))
     return v
+
+
+def newmark(asm, dyn, nonlinear=True):
+    """the C host drivers cb_newmark_nonlinear / cb_newmark_linear (main.c:3305-3960 /
+    main.c:3143-3303 + solve.c:199-458 on the device path).  dyn = deck.parse_dynamic_tail(...).
+    Returns (hist [ntstps][2+NEQ], result)."""
+    hl = load_host_library()
+    m = asm.m
+    if dyn["nbc"]:
+        raise CubensError("prescribed support motion (NBC != 0) is not supported by the host drivers")
+    nt = int(dyn["ntstps"])
+    hist = np.zeros((nt, m.NEQ + 2))
+    res = cb_nr_result()
+    pin = np.ascontiguousarray(dyn["pinpt"], dtype=np.float64)
+    maxa = np.ascontiguousarray(m.maxa, dtype=np.int64)
+    if nonlinear:
+        q = dyn["params"]
+        p = cb_nr_params(q["lpfmax"], q["lpf"], q["dlpf"], q["dlpfmax"], q["dlpfmin"], q["itemax"],
+                         q["submax"], q["solmin"], q["toldisp"], q["tolforc"], q["tolener"], 1)
+        hl.cb_newmark_nonlinear(asm.h, C.c_long(m.NEQ), _p(maxa), C.c_long(m.lss), _p(pin), C.c_long(nt),
+                                C.c_double(dyn["dt"]), C.c_double(dyn["alpham"]), C.c_double(dyn["alphaf"]),
+                                C.byref(p), _p(hist), C.byref(res))
+    else:
+        um, vm, am = (np.ascontiguousarray(dyn[k], dtype=np.float64) for k in ("um", "vm", "am"))
+        hl.cb_newmark_linear(asm.h, C.c_long(m.NEQ), _p(maxa), C.c_long(m.lss), _p(pin), C.c_long(nt),
+                             C.c_double(dyn["dt"]), C.c_double(dyn["alpham"]), C.c_double(dyn["alphaf"]),
+                             _p(um), _p(vm), _p(am), _p(hist), C.byref(res))
+    return hist, res

@@ -81,6 +81,7 @@ def read_deck(text):
                           algflag=ALGFLAG)
     else:
         tail = [r for r in it]
+    dyn_tail = tail
     m = build_model(x, trusses=trusses or None, frames=frames or None, shells=shells or None,
                     bricks=bricks or None, fixed=fixed, truss_props=np.array(tp) if tp else None,
                     frame_props=np.array(fp) if fp else None, shell_props=np.array(sp) if sp else None,
@@ -98,4 +99,62 @@ def read_deck(text):
             s = slice(m.NE_TR, m.NE_TR + m.NE_FR); cs = slice(m.NE_TR, m.NE_TR + 3 * m.NE_FR)
             m.xfr[:] = xfr.reshape(-1); m.llength[s] = ll
             m.c1[cs], m.c2[cs], m.c3[cs] = lx.reshape(-1), ly.reshape(-1), lz.reshape(-1)
+    if dyn_tail is not None:
+        tail = parse_dynamic_tail(m, dyn_tail, ALGFLAG)
     return m, params, tail
+
+
+def parse_dynamic_tail(m, rows, ALGFLAG):
+    """the transient part of the deck: `ntstpsinpt, ttot` (main.c:1604-1608), the load histories,
+    prescribed support motion and initial conditions that load() reads (model.c:1490-1606), the
+    Newmark options (main.c:3160-3180 / 3319-3351) and, for ALGFLAG 5, the Newton controls."""
+    it = iter(rows)
+    r = next(it)
+    nin = int(r[0]); ttot = float(r[1])
+    dt = ttot / nin
+    nt = nin + 1
+    jc = m.jcode.reshape(-1, 7)
+    pinpt = np.zeros((m.NEQ, nt)); pdisp = np.zeros((m.NEQ, nt))
+
+    def series(dst, zero_to_tiny):
+        kps, i = 0, 0
+        while True:
+            r = next(it)
+            jt, dr, mag = int(r[0]), int(r[1]), float(r[2])
+            if jt == 0:
+                return
+            if zero_to_tiny and mag == 0:
+                mag = 1e-30                              # model.c:1517-1521, 1570-1572
+            ks = int(jc[jt - 1, dr - 1])
+            if ks != kps:
+                i = 0
+            if ks != 0:
+                dst[ks - 1, i] = mag
+            kps = ks; i += 1
+    series(pinpt, ALGFLAG == 5)
+    series(pdisp, True)
+    um = np.zeros(m.NEQ); vm = np.zeros(m.NEQ); am = np.zeros(m.NEQ)
+    while True:
+        r = next(it)
+        jt = int(r[0])
+        if jt == 0:
+            break
+        k = int(jc[jt - 1, int(r[1]) - 1])
+        if k:
+            dv, vv, av = float(r[2]), float(r[3]), float(r[4])
+            if dv != 0: um[k - 1] = dv
+            if vv != 0: vm[k - 1] = vv
+            if av != 0: am[k - 1] = av
+    r = next(it)
+    numopt, rho = float(r[0]), float(r[1])
+    if numopt == 0: alpham, alphaf = 0.0, 0.0                      # main.c:3337-3351
+    elif numopt == 1: alpham, alphaf = (2 * rho - 1) / (rho + 1), rho / (rho + 1)
+    elif numopt == 2: alpham, alphaf = 0.0, (1 - rho) / (1 + rho)
+    else: alpham, alphaf = (rho - 1) / (rho + 1), 0.0
+    out = dict(ntstps=nt, dt=dt, pinpt=pinpt, pdisp=pdisp, um=um, vm=vm, am=am, alpham=alpham,
+               alphaf=alphaf, nbc=int((pdisp != 0).any()))
+    if ALGFLAG == 5:
+        a = [float(v) for v in next(it)]; b = [int(v) for v in next(it)]; c = [float(v) for v in next(it)]
+        out["params"] = dict(lpfmax=a[0], lpf=a[1], dlpf=a[2], dlpfmax=a[3], dlpfmin=a[4], itemax=b[0],
+                             submax=b[1], solmin=b[2], toldisp=c[0], tolforc=c[1], tolener=c[2])
+    return out

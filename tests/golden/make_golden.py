@@ -220,7 +220,41 @@ def record_deck(name, B=R):
     return m, out
 
 
+def run_cases():
+    """full transient runs of the shipped decks through the UNMODIFIED reference driver
+    (oracle/_ref/ben_capture.exe = main.c with its output() rows recorded at full precision)"""
+    return {"run_5b_frame": "model_def_5b_frame.txt", "run_5c_shell": "model_def_5c_shell.txt"}
+
+
+def record_run(name):
+    import subprocess, tempfile
+    from cubens_b200 import deck
+    from cubens_b200.model import model_to_dict
+    text = open(DECKS + run_cases()[name]).read().replace("\r", "")
+    m, _, dyn = deck.read_deck(text)
+    out = model_to_dict(m)
+    for k, v in dyn.items():
+        if k == "params":
+            out["dyn_params"] = np.array([v[q] for q in ("lpfmax", "lpf", "dlpf", "dlpfmax", "dlpfmin",
+                                          "itemax", "submax", "solmin", "toldisp", "tolforc", "tolener")])
+        else:
+            out["dyn_" + k] = np.asarray(v)
+    exe = os.path.join(ROOT, "oracle", "_ref", "ben_capture.exe")
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "model_def.txt"), "w").write(text)
+        subprocess.check_call([exe], cwd=td, stdout=subprocess.DEVNULL)
+        raw = open(os.path.join(td, "capture.bin"), "rb").read()
+    neq, nrows = np.frombuffer(raw[:16], dtype=np.int64)
+    assert neq == m.NEQ
+    out["hist"] = np.frombuffer(raw[16:], dtype=np.float64).reshape(nrows, neq + 2).copy()
+    return m, out
+
+
 if __name__ == "__main__":
+    for name in run_cases():
+        m, out = record_run(name)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "NEQ", m.NEQ, "rows", out["hist"].shape[0])
     assert R.available(), "build oracle/_ref first (make -C oracle ref)"
     for name in deck_cases():
         m, out = record_deck(name)

@@ -1,0 +1,68 @@
+"""Full transient runs of the reference's shipped decks on the device path, against the
+displacement history of the UNMODIFIED reference driver (tests/golden/run_*.npz, recorded by
+oracle/_ref/ben_capture.exe = main.c with every output() row captured at full double precision):
+
+  model_def_5b_frame.txt  ANAFLAG 3 / ALGFLAG 5: inelastic (plastic-hinge) frames, nonlinear
+                          Newmark with generalized-alpha damping (rho = 0.9), 17 time steps; K_t, lumped
+                          mass and f_int rebuilt on the device every Newton iteration
+  model_def_5c_shell.txt  ANAFLAG 1 / ALGFLAG 4 (BASELINE.json configs[1]): DKT shells, linear Newmark
+
+through the C host drivers cb_newmark_nonlinear / cb_newmark_linear (main.c:3305-3960, 3143-3303 +
+solve.c:139-536).  Tolerance: 1e-9 relative on every time step's displacement vector."""
+import os
+
+import numpy as np
+import pytest
+
+import cubens_b200 as cb
+from cubens_b200.model import model_from_dict
+from util import relerr
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    m = model_from_dict(g)
+    dyn = {k[4:]: g[k] for k in g.files if k.startswith("dyn_") and k != "dyn_params"}
+    for k in ("ntstps", "nbc"):
+        dyn[k] = int(dyn[k])
+    for k in ("dt", "alpham", "alphaf"):
+        dyn[k] = float(dyn[k])
+    if "dyn_params" in g.files:
+        keys = ("lpfmax", "lpf", "dlpf", "dlpfmax", "dlpfmin", "itemax", "submax", "solmin", "toldisp",
+                "tolforc", "tolener")
+        dyn["params"] = dict(zip(keys, g["dyn_params"]))
+        for k in ("itemax", "submax", "solmin"):
+            dyn["params"][k] = int(dyn["params"][k])
+    return g, m, dyn
+
+
+def test_deck_5b_inelastic_frame_newmark(gpu):
+    g, m, dyn = _load("run_5b_frame")
+    assert (m.ANAFLAG, m.ALGFLAG) == (3, 5)
+    asm = cb.Assembler(m, layout=cb.CB_MAT_SKYLINE)
+    hist, res = cb.newmark(asm, dyn, nonlinear=True)
+    ref = g["hist"]
+    assert res.status == 0 and hist.shape == ref.shape
+    assert np.allclose(hist[:, 0], ref[:, 0], rtol=1e-12, atol=0)         # times
+    assert np.array_equal(hist[:, 1], ref[:, 1])                          # Newton iterations per step
+    for k in range(ref.shape[0]):
+        assert relerr(hist[k, 2:], ref[k, 2:]) < 1e-9, k
+    assert np.abs(ref[-1, 2:]).max() > 0
+    asm.close()
+
+
+def test_deck_5c_shell_linear_newmark(gpu):
+    g, m, dyn = _load("run_5c_shell")
+    assert (m.ANAFLAG, m.ALGFLAG) == (1, 4)
+    asm = cb.Assembler(m, layout=cb.CB_MAT_SKYLINE)
+    hist, res = cb.newmark(asm, dyn, nonlinear=False)
+    ref = g["hist"][:-1]          # the reference's last row is its final output() of the (zero) d
+    assert res.status == 0 and hist.shape == ref.shape
+    assert np.allclose(hist[:, 0], ref[:, 0], rtol=1e-12, atol=0)
+    for k in range(1, ref.shape[0]):
+        assert relerr(hist[k, 2:], ref[k, 2:]) < 1e-9, k
+    assert np.abs(ref[-1, 2:]).max() > 0
+    asm.close()

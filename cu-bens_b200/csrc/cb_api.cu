@@ -22,6 +22,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <unordered_map>
+#include <cstring>
+#include <cstdlib>
 
 static thread_local char g_err[512] = "";
 
@@ -119,6 +122,12 @@ struct cb_handle {
     DevBuf<double> sh_const, sh_keb, sh_kebc, sh_der, sh_Nm, sh_fg, sh_dens;
     long ncontrib = 0;
     DevBuf<double> sh_frame[3], sh_dsl[3], sh_ef[3];   // 0 = committed, 1/2 = iterate ping-pong
+    // geometry classes (cb_internal.h): class of each shell, representatives, tables, work records
+    DevBuf<int32_t> sh_class, cls_rep;
+    DevBuf<double> keb_tab, der_tab;
+    DevBuf<CbWork> works_cls;
+    int ncls = 0;
+    bool cls_on = false;
     // ANAFLAG 3: yield stress, chi/efN/efM [NE][21] (0 = committed, 1 = *_temp), stiffness-pass data
     DevBuf<double> sh_yield, sh_pl[2], sh_kpl;
     DevBuf<int32_t> sh_yv, sh_trip;
@@ -175,6 +184,7 @@ static CbDev make_dev(cb_handle *h)
     d.fr_osflag = h->fr_osflag.p; d.fr_mendrel = h->fr_mendrel.p;
     d.fr_efFE_ref = h->fr_efFE_ref.p; d.fr_fg = h->fr_fg.p;
     d.fr_plast = h->fr_plast.p; d.fr_yldflag = h->fr_yldflag.p; d.fr_ynew = h->fr_ynew.p;
+    if (h->cls_on) { d.sh_class = h->sh_class.p; d.keb_tab = h->keb_tab.p; d.der_tab = h->der_tab.p; }
     d.sh_yield = h->sh_yield.p; d.sh_pl = h->sh_pl[1].p; d.sh_yv = h->sh_yv.p; d.sh_kpl = h->sh_kpl.p;
     d.sh_trip = h->sh_trip.p;
     d.fr_code = h->fr_code.p; d.fr_tau = h->fr_tau.p; d.fr_trip = h->fr_trip.p; d.tr_py = h->tr_py.p;
@@ -427,6 +437,44 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
             F(9, e) = m->farea[e];                       // deffarea = farea (main.c:1700)
             if (m->dens) dn[e] = m->dens[e];             // pdens+i, shell.c:61 / 1551
         }
+        {   // geometry classes: shells with bit-identical geometry-constant inputs
+            struct Key { double v[11]; };
+            auto hash = [](const Key &k) {
+                uint64_t hsh = 1469598103934665603ULL;
+                for (int i = 0; i < 11; ++i) {
+                    uint64_t b; memcpy(&b, &k.v[i], 8);
+                    hsh = (hsh ^ b) * 1099511628211ULL; hsh ^= hsh >> 29;
+                }
+                return (size_t)hsh;
+            };
+            auto eq = [](const Key &a, const Key &b) { return memcmp(a.v, b.v, sizeof a.v) == 0; };
+            std::unordered_map<Key, int32_t, decltype(hash), decltype(eq)> seen(1024, hash, eq);
+            std::vector<int32_t> cls(SH), rep;
+            // tables (840 B per class) must stay cache-resident, and sharing must pay: at most 1024
+            // classes with at least 8 shells each on average.  A structured plate has a few
+            // hundred bit-distinct classes (rounding of the grid coordinates), two of which hold
+            // > 90 % of the shells.
+            const int CLS_MAX = (int)std::min<long>(1024, std::max<long>(1, SH / 8));
+            bool ok = true;
+            for (long e = 0; e < SH && ok; ++e) {
+                Key k;
+                for (int i = 0; i < 11; ++i) k.v[i] = C(i, e);
+                auto it = seen.find(k);
+                if (it == seen.end()) {
+                    if ((int)rep.size() == CLS_MAX) { ok = false; break; }
+                    it = seen.emplace(k, (int32_t)rep.size()).first;
+                    rep.push_back((int32_t)e);
+                }
+                cls[e] = it->second;
+            }
+            if (ok && getenv("CB_NO_GEOMETRY_CLASSES") == nullptr) {
+                h->ncls = (int)rep.size();
+                if (h->sh_class.upload(cls) || h->cls_rep.upload(rep) || h->keb_tab.alloc((size_t)h->ncls * 81) ||
+                    h->der_tab.alloc((size_t)h->ncls * CB_SH_DER))
+                    BAIL(CB_ERR_CUDA);
+                h->cls_on = true;
+            }
+        }
         if (h->sh_const.upload(c) || h->sh_dens.upload(dn) || h->sh_keb.alloc((size_t)SH * 81) || h->sh_der.alloc((size_t)SH * CB_SH_DER) ||
             h->sh_Nm.alloc((size_t)SH * CB_SH_KREC) || h->sh_fg.alloc((size_t)SH * 18))
             BAIL(CB_ERR_CUDA);
@@ -464,6 +512,7 @@ extern "C" void cb_destroy(cb_handle *h)
                               &h->fr_offset, &h->fr_efFE_ref, &h->fr_fg, &h->fr_dens, &h->br_const,
                               &h->Ax, &h->ss, &h->Mx, &h->fr_plast, &h->fr_tau, &h->tr_py})
         b->release();
+    h->sh_class.release(); h->cls_rep.release(); h->keb_tab.release(); h->der_tab.release(); h->works_cls.release();
     for (DevBuf<int32_t> *b : {&h->fr_yldflag, &h->fr_ynew, &h->fr_code, &h->fr_trip, &h->sh_yv, &h->sh_trip})
         b->release();
     h->sh_yield.release(); h->sh_pl[0].release(); h->sh_pl[1].release(); h->sh_kpl.release();
@@ -905,7 +954,17 @@ static int ensure_keb(cb_handle *h)
     CbDev d = make_dev(h);
     if (cbk_shell_init_keb(d, h->sh_keb.p, h->stream)) return fail(CB_ERR_CUDA, "keb init launch");
     if (h->sz.NE_SH) ++h->launches;
-    if (h->sz.NE_SH && h->plan_ready && (h->plan_csc.ntiles || h->plan_csc.ntiles2)) {
+    if (h->sz.NE_SH && h->cls_on) {
+        const bool duo = h->plan_ready && h->plan_csc.ntiles2;
+        if (duo && !h->works_cls.p && h->works_cls.alloc((size_t)h->plan_csc.nworks)) return CB_ERR_CUDA;
+        if (cbk_shell_class_tables(d, h->cls_rep.p, h->ncls, h->keb_tab.p, h->der_tab.p,
+                                   duo ? h->plan_csc.works.p : nullptr, duo ? h->plan_csc.nworks : 0,
+                                   h->contribs.p, h->works_cls.p, h->stream))
+            return fail(CB_ERR_CUDA, "class table launch");
+        h->launches += duo ? 2 : 1;
+    }
+    if (h->sz.NE_SH && h->plan_ready && (h->plan_csc.ntiles || h->plan_csc.ntiles2) &&
+        !(h->cls_on && h->plan_csc.ntiles2)) {
         if (h->plan_csc.ntiles2) {
             if (!h->sh_kebc.p && h->sh_kebc.alloc((size_t)h->plan_csc.ntiles2 * 18 * CB_TILE_T)) return CB_ERR_CUDA;
             if (cbk_shell_init_kebc2(d, h->plan_csc.tiles2.p, h->plan_csc.ntiles2, h->plan_csc.works.p,
@@ -1033,7 +1092,8 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
         a.tiles = h->plan_csc.ntiles ? h->plan_csc.tiles.p : nullptr; a.ntiles = h->plan_csc.ntiles;
         a.tpairs = h->plan_csc.tpairs.p; a.kebc = h->sh_kebc.p; a.tcontribs = h->plan_csc.tcontribs.p;
         a.tiles2 = h->plan_csc.ntiles2 ? h->plan_csc.tiles2.p : nullptr; a.ntiles2 = h->plan_csc.ntiles2;
-        a.works = h->plan_csc.works.p; a.tpairs2 = h->plan_csc.tpairs2.p; a.tile_elems = h->plan_csc.telems.p;
+        a.works = (h->cls_on && h->works_cls.p) ? h->works_cls.p : h->plan_csc.works.p;
+        a.tpairs2 = h->plan_csc.tpairs2.p; a.tile_elems = h->plan_csc.telems.p;
         a.tile_smem_out = h->plan_csc.tile_smem_out;
         a.out = h->Ax.p; a.skyline = 0; a.maxa = nullptr;
         if (cbk_stiff(a, h->stream, &h->launches)) return fail(CB_ERR_CUDA, "assembly launch");
@@ -1228,6 +1288,7 @@ extern "C" int cb_mass(cb_handle *h)
         return fail(CB_ERR_CUDA, "mass launch");
     h->keb_dirty = true;      // farea / slength were refreshed from x (App. B.5)
     h->krec_fresh = false;
+    h->cls_on = false;        // ... so the shells no longer fall into the initial geometry classes
     if (h->NE_BR && (h->layout & CB_MAT_CSC) && h->plan_csc.ntiles) {
         // bricks: the reference only has the full-order [NEQ][NEQ] mass (mass_br, brick.c:525-536);
         // it is assembled here on the CSC pattern of K_t by the same tile kernel

@@ -239,6 +239,41 @@ int cbk_shell_init_kebc2(const CbDev &d, const CbTile2 *tiles, long ntiles, cons
     return cudaGetLastError() != cudaSuccess;
 }
 
+// geometry classes: one copy of the DKT matrix / derived membrane data per class, and the work
+// records of the duo plan with the classes of their two contributions packed into c0
+__global__ void __launch_bounds__(128)
+k_class_tables(CbDev d, const int32_t *__restrict__ rep, int ncls, double *__restrict__ keb_tab,
+               double *__restrict__ der_tab)
+{
+    const int k = blockIdx.x, c = threadIdx.x;
+    if (k >= ncls) return;
+    const long e = rep[k];
+    if (c < 81) keb_tab[k * 81 + c] = SOA(d.sh_keb, c, e, d.NE_SH);
+    if (c < CB_SH_DER) der_tab[k * CB_SH_DER + c] = SOA(d.sh_der, c, e, d.NE_SH);
+}
+__global__ void __launch_bounds__(256)
+k_works_set_class(const CbWork *__restrict__ works, long nworks, const CbContrib *__restrict__ contribs,
+                  const int32_t *__restrict__ cls, CbWork *__restrict__ out)
+{
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= nworks) return;
+    CbWork w = works[i];
+    int c0 = 0, c1 = 0;
+    if (w.kind != 4 && w.n >= 1) c0 = cls[contribs[w.c0].e];
+    if (w.kind != 4 && w.n >= 2) c1 = cls[contribs[w.c0 + 1].e];
+    w.c0 = c0 | (c1 << 16);
+    out[i] = w;
+}
+int cbk_shell_class_tables(const CbDev &d, const int32_t *rep, int ncls, double *keb_tab, double *der_tab,
+                           const CbWork *works, long nworks, const CbContrib *contribs, CbWork *works_cls,
+                           cudaStream_t s)
+{
+    k_class_tables<<<ncls, 128, 0, s>>>(d, rep, ncls, keb_tab, der_tab);
+    if (nworks && works_cls)
+        k_works_set_class<<<(unsigned)((nworks + 255) / 256), 256, 0, s>>>(works, nworks, contribs, d.sh_class, works_cls);
+    return cudaGetLastError() != cudaSuccess;
+}
+
 // plane-stress constitutive coefficients (shell.c:497-501 / 672-676)
 __device__ __forceinline__ void plane_stress(double E, double nu, double &C00, double &C01,
                                              double &C22)
@@ -428,6 +463,7 @@ __device__ __forceinline__ void shell_triad(const double *xj, const double *xk, 
 // forces_sh, ANAFLAG 2 (shell.c:1728-1785, 2305-2347, 2386-2397) fused with the shell block of
 // updatc.  One thread per element.
 // ------------------------------------------------------------------------------------------
+template <bool CLS>
 __global__ void __launch_bounds__(CB_TPB, 2)
 k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restrict__ dd,
                const double *__restrict__ frame_ip, double *__restrict__ frame_i,
@@ -443,12 +479,30 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
     const bool live = e < d.NE_SH;
     double kr[CB_SH_KREC];
     double *mycol = sbuf + threadIdx.x;
+    // geometry-constant data: per element, or one L1-resident copy per geometry class
+    const double *kebsrc = nullptr, *der = nullptr;
+    long kstr = 0, dstr = 0;
+    if (live) {
+        if (CLS) {
+            const int cls = __ldg(d.sh_class + e);
+            kebsrc = d.keb_tab + (long)cls * 81; kstr = 1;
+            der = d.der_tab + (long)cls * CB_SH_DER; dstr = 1;
+        } else {
+            kebsrc = d.sh_keb + e; kstr = d.NE_SH;
+            der = d.sh_der + e; dstr = d.NE_SH;
+        }
+    }
     if (live) {
         const unsigned sdst = (unsigned)__cvta_generic_to_shared(mycol);
+        // per-element matrix: staged in this thread's column.  Class table: read in place later -
+        // the lanes of a warp mostly share a class, so those loads are L1 broadcasts, whereas
+        // 81 private copies per thread would saturate the L1 data pipe with identical bytes.
+        if (!CLS) {
 #pragma unroll
         for (int c = 0; c < 81; ++c)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + c * CB_TPB * 8),
-                         "l"(d.sh_keb + (long)c * d.NE_SH + e));
+                         "l"(kebsrc + (long)c * kstr));
+        }
 #pragma unroll
         for (int c = 0; c < 18; ++c)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + (81 + c) * CB_TPB * 8),
@@ -480,7 +534,7 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
     {
         double cst[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) cst[i] = __ldg(&SOA(d.sh_der, 18 + i, e, d.NE_SH));
+        for (int i = 0; i < 6; ++i) cst[i] = __ldg(der + (18 + i) * dstr);
         shell_krec(sc[5], sc[6], sc[7], sc[2], Ri, cst, dm2, dm4, dm5, d.ANAFLAG, kr);
     }
     // ke_m * dm with the geometry-constant membrane columns (shell.c:1767-1775): the structural
@@ -489,9 +543,9 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         double acc = 0;
-        acc += __ldg(&SOA(d.sh_der, i * 3 + 0, e, d.NE_SH)) * dm2;
-        acc += __ldg(&SOA(d.sh_der, i * 3 + 1, e, d.NE_SH)) * dm4;
-        acc += __ldg(&SOA(d.sh_der, i * 3 + 2, e, d.NE_SH)) * dm5;
+        acc += __ldg(der + (i * 3 + 0) * dstr) * dm2;
+        acc += __ldg(der + (i * 3 + 1) * dstr) * dm4;
+        acc += __ldg(der + (i * 3 + 2) * dstr) * dm5;
         ef_temp[i] = acc;
     }
 
@@ -512,7 +566,8 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
     for (int i = 0; i < 9; ++i) {
         double sum = 0;
 #pragma unroll
-        for (int j = 0; j < 9; ++j) sum += mycol[CB_KEB(i, j) * CB_TPB] * ddb[j];
+        for (int j = 0; j < 9; ++j)
+            sum += (CLS ? __ldg(kebsrc + CB_KEB(i, j)) : mycol[CB_KEB(i, j) * CB_TPB]) * ddb[j];
         defb[i] = sum;
     }
     double efp[18];
@@ -1250,7 +1305,9 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
         const size_t smem = (size_t)99 * CB_TPB * sizeof(double);
         static bool configured = false;
         if (!configured) {
-            if (cudaFuncSetAttribute(k_shell_forces, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            if (cudaFuncSetAttribute(k_shell_forces<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem) != cudaSuccess ||
+                cudaFuncSetAttribute(k_shell_forces<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem) != cudaSuccess)
                 return 1;
             configured = true;
@@ -1261,9 +1318,12 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
             k_shell_forces_pl<<<(unsigned)((d.NE_SH + 63) / 64), 64, 0, s>>>(
                 d, a.x_temp, a.x_ip, a.dd, a.sh_frame_ip, a.sh_frame_i, a.sh_dsl_ip, a.sh_dsl_i,
                 a.sh_ef_ip, a.sh_ef_i);
-        } else
-        k_shell_forces<<<g, CB_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
-                                               a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i);
+        } else if (d.sh_class)
+            k_shell_forces<true><<<g, CB_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
+                                                         a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i);
+        else
+            k_shell_forces<false><<<g, CB_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
+                                                          a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i);
         ++*launches;
     }
     return cudaGetLastError() != cudaSuccess;

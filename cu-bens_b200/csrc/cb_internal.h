@@ -150,6 +150,13 @@ struct CbDev {
                              // plane-stress C00,C01,C22, 21-23 t/(4 A0) * C
     double *sh_Nm;           // [NE][CB_SH_KREC] stiffness-pass record written by k_shell_prep
     double *sh_fg;           // [3][NE][6] element force in global axes (staging for the gather)
+    // geometry classes: shells whose geometry-constant inputs (E, nu, t, A0, local coordinates, side
+    // lengths) are bit-identical share one copy of the DKT matrix and of sh_der - structured meshes
+    // have a handful of classes, so the per-element 105 doubles never leave L1.  nullptr when the
+    // model has too many classes (or after mass_* rewrote the reference geometry, App. B.5).
+    const int32_t *sh_class; // [NE] class of each shell
+    const double *keb_tab;   // [ncls][81] component order of sh_keb (CB_KEB)
+    const double *der_tab;   // [ncls][CB_SH_DER]
     // frames
     const int32_t *fr_nodes; // [NE][2]
     const double *fr_const;  // [NE][CB_FR_CONST]
@@ -238,6 +245,9 @@ int cbk_shell_init_kebc2(const CbDev &d, const CbTile2 *tiles, long ntiles, cons
 int cbk_shell_init_kebc(const CbDev &d, const CbContrib *contribs, long ncontrib, double *kebc,
                         cudaStream_t s);
 int cbk_shell_prep(const CbDev &d, const double *x, const double *sh_frame, cudaStream_t s);
+int cbk_shell_class_tables(const CbDev &d, const int32_t *rep, int ncls, double *keb_tab, double *der_tab,
+                           const CbWork *works, long nworks, const CbContrib *contribs, CbWork *works_cls,
+                           cudaStream_t s);
 int cbk_shell_plastic_prep(const CbDev &d, const double *sh_frame, const double *sh_dsl,
                            const double *sh_pl, cudaStream_t s);
 int cbk_node_update(const CbForceArgs &a, cudaStream_t s);

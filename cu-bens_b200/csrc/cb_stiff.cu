@@ -754,6 +754,10 @@ __device__ __forceinline__ void t2_store_half(double *obuf, int shift, const CbT
 #define CB_T2_SMEM_DOUBLES (CB_T2_OUT + 2 + 2 * CB_T2_ELEMS * CB_SH_KREC + 18 * CB_TILE_T)
 #define CB_T2_SMEM_BYTES (CB_T2_SMEM_DOUBLES * 8 + 2 * CB_TILE_T * 16 + CB_TILE_T * 16 + CB_T2_EIDS * CB_TILE_T * 4 + 4 * 48)
 
+// CLS: the DKT sub-blocks come from the geometry-class table (L1-resident) instead of the
+// work-ordered per-contribution copy in HBM; the classes of a work item's two contributions are
+// packed in its c0 field.
+template <bool CLS>
 __global__ void __launch_bounds__(CB_TILE_T, CB_T2_CTAS)
 k_assemble_shell_tiles(CbStiffArgs A)
 {
@@ -793,10 +797,10 @@ k_assemble_shell_tiles(CbStiffArgs A)
         if (tile + G < N) t2_issue_eids(A, A.tiles2[tile + G], seid);
         if (t < tl.nw) {
             CB_CPA(16, "cg", swork + t, A.works + tl.w0 + t);
-            t2_issue_kb<true>(A, tile, t, skb);
+            if (!CLS) t2_issue_kb<true>(A, tile, t, skb);
         }
         CB_CPA_COMMIT();
-        if (t < tl.nw) t2_issue_kb<false>(A, tile, t, skb);
+        if (!CLS && t < tl.nw) t2_issue_kb<false>(A, tile, t, skb);
         CB_CPA_COMMIT();
     }
     int buf = 0;
@@ -839,8 +843,18 @@ k_assemble_shell_tiles(CbStiffArgs A)
             double top[9], bot[9];                                                                 \
             if (w.n >= 1) {                                                                        \
                 double kb[18];                                                                     \
+                if (CLS) {                                                                         \
+                    const double *k0 = A.d.keb_tab + (w.c0 & 0xffff) * 81 + (3 * w.a0 + w.b0) * 9;  \
+                    const double *k1 = A.d.keb_tab + ((unsigned)w.c0 >> 16) * 81 + (3 * w.a1 + w.b1) * 9; \
+                    _Pragma("unroll") for (int i = 0; i < 9; ++i)                                  \
+                        if (((i % 3) == 0) == LEFT) {                                              \
+                            kb[i] = __ldg(k0 + i);                                                 \
+                            kb[9 + i] = (w.n == 2) ? __ldg(k1 + i) : 0.0;                          \
+                        }                                                                          \
+                } else {                                                                           \
                 _Pragma("unroll") for (int i = 0; i < 18; ++i)                                     \
                     if (((i % 3) == 0) == LEFT) kb[i] = skb[i * CB_TILE_T + t];                    \
+                }                                                                                  \
                 shell_half_acc<LEFT>(kr0 + w.s0 * CB_SH_KREC, kb, w.a0, w.b0, top, bot, true);     \
                 if (w.n == 2)                                                                      \
                     shell_half_acc<LEFT>(kr0 + w.s1 * CB_SH_KREC, kb + 9, w.a1, w.b1, top, bot, false); \
@@ -862,14 +876,14 @@ k_assemble_shell_tiles(CbStiffArgs A)
             if (has_next2) t2_issue_eids(A, tlnn, seid);
             if (t < tln.nw) {
                 CB_CPA(16, "cg", swork + t, A.works + tln.w0 + t);
-                t2_issue_kb<true>(A, next, t, skb);
+                if (!CLS) t2_issue_kb<true>(A, next, t, skb);
             }
         }
         CB_CPA_COMMIT();
         asm volatile("cp.async.wait_group 1;" ::: "memory");     // this tile's right DKT entries
         CB_T2_HALF(false, 3)
 #undef CB_T2_HALF
-        if (has_next && t < tln.nw) t2_issue_kb<false>(A, next, t, skb);
+        if (!CLS && has_next && t < tln.nw) t2_issue_kb<false>(A, next, t, skb);
         CB_CPA_COMMIT();
         // writes of the image (generic proxy) ordered before the copy engine's reads (async proxy)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -895,25 +909,26 @@ k_assemble_shell_tiles(CbStiffArgs A)
     if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+template <bool CLS>
 static int launch_shell_tiles(const CbStiffArgs &a, cudaStream_t s)
 {
     const size_t smem = CB_T2_SMEM_BYTES;
     static int grid_cache = 0;
     if (!grid_cache) {
-        if (cudaFuncSetAttribute(k_assemble_shell_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(k_assemble_shell_tiles<CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return 1;
         int per_sm = 0, dev = 0, nsm = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_shell_tiles, CB_TILE_T, smem) !=
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_shell_tiles<CLS>, CB_TILE_T, smem) !=
                 cudaSuccess || per_sm < 1)
             per_sm = 1;
         grid_cache = per_sm * nsm;
     }
     long grid = grid_cache;
     if (grid > a.ntiles2) grid = a.ntiles2;
-    k_assemble_shell_tiles<<<(unsigned)grid, CB_TILE_T, smem, s>>>(a);
+    k_assemble_shell_tiles<CLS><<<(unsigned)grid, CB_TILE_T, smem, s>>>(a);
     return cudaGetLastError() != cudaSuccess;
 }
 
@@ -1017,7 +1032,10 @@ static int launch_tiles(const CbStiffArgs &a, cudaStream_t s)
 
 int cbk_stiff(const CbStiffArgs &a, cudaStream_t s, long *launches)
 {
-    if (!a.skyline && a.ntiles2 > 0 && a.tiles2) { ++*launches; return launch_shell_tiles(a, s); }
+    if (!a.skyline && a.ntiles2 > 0 && a.tiles2) {
+        ++*launches;
+        return a.d.keb_tab ? launch_shell_tiles<true>(a, s) : launch_shell_tiles<false>(a, s);
+    }
     if (a.skyline || a.tiles == nullptr) {
         if (a.npairs == 0) return 0;
         unsigned g = (unsigned)((a.npairs + CB_TPB_K - 1) / CB_TPB_K);

@@ -321,6 +321,39 @@ def run_gpu(a):
                "note": "dd pinned host->device; f_temp and all CSC values device->pinned host each "
                        "step (what the host-side solve() consumes); steps=%d" % ke}
 
+    ncls = asm.geometry_classes
+    map_bytes = asm.map_bytes
+
+    # ---- the same plate with every interior joint moved (seeded): no two shells share their
+    # geometry, so every shell streams its own DKT matrix from HBM (N=1, shorter run) -----------
+    unstructured = None
+    if world == 1 and not a.no_unstructured:
+        asm.close()
+        mu = meshgen.plate_model(n, n, SLVFLAG=2, jitter=0.2)
+        au = cb.Assembler(mu, layout=cb.CB_MAT_CSC, device=local)
+        ddu = meshgen.perturbation(mu)
+        au.begin_increment(); au.update_forces(ddu, want_f=False); au.end_iteration()
+        au.set_dd(ddu * 1e-3)
+
+        def ustep():
+            au.stiff(); au.update_forces_dev(); au.end_iteration()
+        for _ in range(5):
+            ustep()
+        au.sync()
+        ku = max(10, a.steps // 2)
+        au.timer_start()
+        for _ in range(ku):
+            ustep()
+        u_ms = au.timer_stop_ms() / ku
+        au.stiff(); ka = au.last_assemble_ms; au.update_forces_dev(); kf = au.last_forces_ms
+        unstructured = {"value": mu.NE_SH / (u_ms * 1e-3), "unit": UNIT, "ms_per_step": u_ms,
+                        "geometry_classes": au.geometry_classes, "steps": ku,
+                        "split_ms": {"assemble_kernel": ka, "update_forces": kf},
+                        "roofline_frac": ALG_BYTES_KT * mu.NE_SH / (ka * 1e-3) / 1e9 / measured_peak()[0],
+                        "workload": "same plate, interior joints moved in-plane by up to 0.2 cell "
+                                    "(rng 7): every shell has its own geometry"}
+        au.close()
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -345,7 +378,10 @@ def run_gpu(a):
                                "assembly (BASELINE.json configs[2])",
                    "matrix": f"device CSC, nnz {nnz} per rank", "parallelism": f"element-partition x{world}",
                    "l2": "inputs and outputs (2 GB CSC + 1.7 GB element state per GPU) exceed the 126 MB L2",
-                   "seed": 20261017},
+                   "seed": 20261017,
+                   "geometry_classes": f"{ncls} (shells with bit-identical geometry share one cached DKT "
+                                       "matrix; `unstructured` repeats the run on a jittered plate where "
+                                       "none do)" if ncls else "0 (every shell streams its own DKT matrix)"},
         "clocks": clk, "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / a.steps,
         "split_ms": {"stiff_total": float(np.median(st_ms)), "assemble_kernel": k_ms,
                      "update_forces": float(np.median(fo_ms))},
@@ -354,8 +390,10 @@ def run_gpu(a):
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALG_BYTES_KT * n_local,
                      "whole_step_frac": (ALG_BYTES_KT + ALG_BYTES_FINT) * n_local / (ms_step * 1e-3) / 1e9 / peak,
-                     "map_bytes_per_launch": asm.map_bytes},
+                     "map_bytes_per_launch": map_bytes},
     }
+    if unstructured is not None:
+        line["unstructured"] = unstructured
     if e2e is not None:
         line["e2e"] = e2e
     if cpu is not None:
@@ -375,6 +413,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--detail", action="store_true")
+    ap.add_argument("--no-unstructured", action="store_true",
+                    help="skip the second (jittered-plate) measurement")
     ap.add_argument("--strong", action="store_true",
                     help="N>1: split ONE n x n plate across the ranks (default: weak scaling, every "
                          "rank owns an n x n-cell strip of an (n*N) x n plate)")

@@ -1657,6 +1657,7 @@ extern "C" void *cb_host_alloc(unsigned long bytes)
 }
 extern "C" void cb_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" long cb_map_bytes(cb_handle *h) { return h ? h->map_bytes : 0; }
+extern "C" int cb_geometry_classes(cb_handle *h) { return (h && h->cls_on) ? h->ncls : 0; }
 extern "C" int cb_sync(cb_handle *h)
 {
     if (!h) return fail(CB_ERR_ARG, "null handle");

@@ -15,9 +15,13 @@
 // inlined in each of them, mass_tr/fr/sh truss.c:381, frame.c:1314, shell.c:1505; once per model:
 // stiffe_b_sh shell.c:533-658 (DKT bending matrix, geometry-constant).
 #include "cb_internal.h"
+#include <algorithm>
 #include "cb_frame_math.cuh"
 
 #define CB_TPB 128
+#ifndef CB_FORCES_STAGE_KEB
+#define CB_FORCES_STAGE_KEB 0     // 1: per-element DKT matrix staged by cp.async (see k_shell_forces)
+#endif
 #ifndef CB_FORCES_MINB
 #define CB_FORCES_MINB 4
 #endif
@@ -463,8 +467,11 @@ __device__ __forceinline__ void shell_triad(const double *xj, const double *xk, 
 // forces_sh, ANAFLAG 2 (shell.c:1728-1785, 2305-2347, 2386-2397) fused with the shell block of
 // updatc.  One thread per element.
 // ------------------------------------------------------------------------------------------
+#ifndef CB_FORCES_CTAS
+#define CB_FORCES_CTAS 4          // class tables: latency-bound, 4 resident CTAs per SM (128 registers)
+#endif                            // per-element matrices: HBM-bound, 2 CTAs with 254 registers measure faster
 template <bool CLS>
-__global__ void __launch_bounds__(CB_TPB, 2)
+__global__ void __launch_bounds__(CB_TPB, CLS ? CB_FORCES_CTAS : 2)
 k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restrict__ dd,
                const double *__restrict__ frame_ip, double *__restrict__ frame_i,
                double *__restrict__ dsl_i, const double *__restrict__ ef_ip,
@@ -479,6 +486,7 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
     const bool live = e < d.NE_SH;
     double kr[CB_SH_KREC];
     double *mycol = sbuf + threadIdx.x;
+    constexpr int KOFF = (CLS || !CB_FORCES_STAGE_KEB) ? 0 : 81;   // first column of the staged ef_ip
     // geometry-constant data: per element, or one L1-resident copy per geometry class
     const double *kebsrc = nullptr, *der = nullptr;
     long kstr = 0, dstr = 0;
@@ -497,7 +505,7 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
         // per-element matrix: staged in this thread's column.  Class table: read in place later -
         // the lanes of a warp mostly share a class, so those loads are L1 broadcasts, whereas
         // 81 private copies per thread would saturate the L1 data pipe with identical bytes.
-        if (!CLS) {
+        if (!CLS && CB_FORCES_STAGE_KEB) {
 #pragma unroll
         for (int c = 0; c < 81; ++c)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + c * CB_TPB * 8),
@@ -505,7 +513,7 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
         }
 #pragma unroll
         for (int c = 0; c < 18; ++c)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + (81 + c) * CB_TPB * 8),
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + (KOFF + c) * CB_TPB * 8),
                          "l"(ef_ip + (long)c * d.NE_SH + e));
         asm volatile("cp.async.commit_group;");
     }
@@ -567,12 +575,13 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
         double sum = 0;
 #pragma unroll
         for (int j = 0; j < 9; ++j)
-            sum += (CLS ? __ldg(kebsrc + CB_KEB(i, j)) : mycol[CB_KEB(i, j) * CB_TPB]) * ddb[j];
+            sum += ((CLS || !CB_FORCES_STAGE_KEB) ? __ldg(kebsrc + CB_KEB(i, j) * kstr)
+                                                  : mycol[CB_KEB(i, j) * CB_TPB]) * ddb[j];
         defb[i] = sum;
     }
     double efp[18];
 #pragma unroll
-    for (int i = 0; i < 18; ++i) efp[i] = (i % 6 >= 2) ? mycol[(81 + i) * CB_TPB] : 0.0;
+    for (int i = 0; i < 18; ++i) efp[i] = (i % 6 >= 2) ? mycol[(KOFF + i) * CB_TPB] : 0.0;
 
     // T_i * T_ip^T is block diagonal with M = R_i R_ip^T (shell.c:2326-2338)
     double M[3][3];
@@ -1302,7 +1311,10 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
     }
     if (d.NE_SH) {
         unsigned g = (unsigned)((d.NE_SH + CB_TPB - 1) / CB_TPB);
-        const size_t smem = (size_t)99 * CB_TPB * sizeof(double);
+        // staged columns per thread (ef_ip, + the DKT matrix when CB_FORCES_STAGE_KEB) or the krec
+        // transposition tile, whichever is larger
+        const size_t cols = CB_FORCES_STAGE_KEB ? 99 : 18;
+        const size_t smem = std::max(cols * CB_TPB, (size_t)(CB_TPB / 32) * 32 * (CB_SH_KREC + 1)) * sizeof(double);
         static bool configured = false;
         if (!configured) {
             if (cudaFuncSetAttribute(k_shell_forces<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,

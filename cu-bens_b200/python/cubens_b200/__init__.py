@@ -36,6 +36,7 @@ EXPORTS = [
     "cb_last_stiff_ms", "cb_last_forces_ms", "cb_last_assemble_ms", "cb_timer_start", "cb_timer_stop_ms", "cb_set_dd", "cb_host_alloc",
     "cb_host_free", "cb_map_bytes", "cb_sync", "cb_stream", "cb_set_q", "cb_residual_sums",
     "cb_dev_sums", "cb_get_sums", "cb_get_yldflag", "cb_set_yldflag", "cb_get_mass_csc_values", "cb_dev_Mx",
+    "cb_geometry_classes",
 ]
 
 
@@ -309,6 +310,10 @@ class Assembler:
         self._pinned = getattr(self, "_pinned", []) + [ptr]
         buf = (C.c_char * max(nbytes, 8)).from_address(ptr)
         return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    @property
+    def geometry_classes(self):
+        return self.lib.cb_geometry_classes(self.h)
 
     @property
     def map_bytes(self):

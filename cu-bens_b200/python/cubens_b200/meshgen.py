@@ -23,10 +23,17 @@ BRICK_DEF = (2.1e11, 0.3, 8050.0, 3.45e8)           # E, nu, rho, fy
 
 
 def plate_model(nx, ny, lx=1.0, ly=1.0, props=SHELL_5C, load=-1000.0, ANAFLAG=2, ALGFLAG=1,
-                SLVFLAG=0, pinned=True, z_bump=0.0):
+                SLVFLAG=0, pinned=True, z_bump=0.0, jitter=0.0, jitter_seed=7):
+    """``jitter``: interior joints moved in-plane by up to that fraction of a cell (seeded) - an
+    unstructured variant of the same plate in which no two shells share their geometry"""
     i, j = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="ij")
     xs = (i * (lx / nx)).astype(F64)
     ys = (j * (ly / ny)).astype(F64)
+    if jitter:
+        rng = np.random.default_rng(jitter_seed)
+        inner = (i > 0) & (i < nx) & (j > 0) & (j < ny)
+        xs = xs + inner * rng.uniform(-jitter, jitter, xs.shape) * (lx / nx)
+        ys = ys + inner * rng.uniform(-jitter, jitter, ys.shape) * (ly / ny)
     zs = np.zeros_like(xs)
     if z_bump:
         zs = z_bump * np.sin(np.pi * xs / lx) * np.sin(np.pi * ys / ly)

@@ -217,6 +217,11 @@ double cb_last_stiff_ms(cb_handle *h);
 double cb_last_forces_ms(cb_handle *h);
 /* bytes of implementation-only maps read per cb_stiff (reported next to the roofline)      */
 long cb_map_bytes(cb_handle *h);
+/* number of geometry classes in use (shells whose geometry-constant inputs are bit-identical share
+ * one cache-resident copy of the DKT matrix), 0 when every shell keeps its own copy: more than
+ * 1024 classes, or after cb_mass rewrote the reference geometry.  Setting the
+ * environment variable CB_NO_GEOMETRY_CLASSES disables the sharing.                          */
+int  cb_geometry_classes(cb_handle *h);
 /* CUDA-event time in ms of the block-assembly kernel alone (the dominant kernel; roofline)  */
 double cb_last_assemble_ms(cb_handle *h);
 /* CUDA events on this handle's stream bracketing any sequence of calls (device timeline)     */

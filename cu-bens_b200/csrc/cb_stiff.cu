@@ -621,7 +621,12 @@ k_assemble_tiles(CbStiffArgs A)
 // ids | ring of tile records
 // ------------------------------------------------------------------------------------------
 
+#ifndef CB_T2_CTAS
 #define CB_T2_CTAS 3              // resident CTAs per SM the kernel is compiled for
+#endif
+#ifndef CB_T2_CTAS_CLS
+#define CB_T2_CTAS_CLS 3          // ... with the class table (4 CTAs of 128 registers measured slower: spills)
+#endif
 
 // Columns 0..2 (LEFT) or 3..5 of K_ab (6x6, global axes) of one shell contribution:
 // top[9] = rows 0..2 (translations), bot[9] = rows 3..5 (rotations), row-major 3x3; kb = the 3x3
@@ -751,21 +756,23 @@ __device__ __forceinline__ void t2_store_half(double *obuf, int shift, const CbT
     }
 }
 
-#define CB_T2_SMEM_DOUBLES (CB_T2_OUT + 2 + 2 * CB_T2_ELEMS * CB_SH_KREC + 18 * CB_TILE_T)
-#define CB_T2_SMEM_BYTES (CB_T2_SMEM_DOUBLES * 8 + 2 * CB_TILE_T * 16 + CB_TILE_T * 16 + CB_T2_EIDS * CB_TILE_T * 4 + 4 * 48)
+// the DKT staging columns (skb) are not needed when the blocks come from the class table
+#define CB_T2_SKB(CLS) ((CLS) ? 0 : 18 * CB_TILE_T)
+#define CB_T2_SMEM_DOUBLES(CLS) (CB_T2_OUT + 2 + 2 * CB_T2_ELEMS * CB_SH_KREC + CB_T2_SKB(CLS))
+#define CB_T2_SMEM_BYTES(CLS) (CB_T2_SMEM_DOUBLES(CLS) * 8 + 2 * CB_TILE_T * 16 + CB_TILE_T * 16 + CB_T2_EIDS * CB_TILE_T * 4 + 4 * 48)
 
 // CLS: the DKT sub-blocks come from the geometry-class table (L1-resident) instead of the
 // work-ordered per-contribution copy in HBM; the classes of a work item's two contributions are
 // packed in its c0 field.
 template <bool CLS>
-__global__ void __launch_bounds__(CB_TILE_T, CB_T2_CTAS)
+__global__ void __launch_bounds__(CB_TILE_T, CLS ? CB_T2_CTAS_CLS : CB_T2_CTAS)
 k_assemble_shell_tiles(CbStiffArgs A)
 {
     extern __shared__ __align__(16) double smem[];
     double *obuf = smem;                                              // [CB_T2_OUT + 2]
     double *skrec = obuf + CB_T2_OUT + 2;                             // [2][CB_T2_ELEMS*18], 16 B aligned
     double *skb = skrec + 2 * CB_T2_ELEMS * CB_SH_KREC;               // [18][CB_TILE_T]
-    CbTPair *spair2 = reinterpret_cast<CbTPair *>(skb + 18 * CB_TILE_T);   // [2][CB_TILE_T]
+    CbTPair *spair2 = reinterpret_cast<CbTPair *>(skb + CB_T2_SKB(CLS));   // [2][CB_TILE_T]
     int4 *swork = reinterpret_cast<int4 *>(spair2 + 2 * CB_TILE_T);   // [CB_TILE_T]
     int *seid = reinterpret_cast<int *>(swork + CB_TILE_T);           // [CB_T2_EIDS][CB_TILE_T]
     int *sring = seid + CB_T2_EIDS * CB_TILE_T;                       // [4][12] tile records
@@ -912,7 +919,7 @@ k_assemble_shell_tiles(CbStiffArgs A)
 template <bool CLS>
 static int launch_shell_tiles(const CbStiffArgs &a, cudaStream_t s)
 {
-    const size_t smem = CB_T2_SMEM_BYTES;
+    const size_t smem = CB_T2_SMEM_BYTES(CLS);
     static int grid_cache = 0;
     if (!grid_cache) {
         if (cudaFuncSetAttribute(k_assemble_shell_tiles<CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize,

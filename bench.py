@@ -232,7 +232,7 @@ def run_gpu(a):
     def step():
         asm.stiff()                      # K_t  -> device CSC
         asm.update_forces_dev()          # updatc + f_int -> device f_temp
-        if exchange is not None:
+        if exchange is not None and not os.environ.get("BENCH_NO_EXCHANGE"):
             exchange.reduce()            # interface residual sums over NVLink (NCCL)
         asm.end_iteration()
 

@@ -117,6 +117,7 @@ struct cb_handle {
     DevBuf<double> x, x_temp, x_ip;
     DevBuf<double> dd, f_temp, f, d, d_temp, sm, qvec, sums, sums_part;
     long eq0 = 0, eq1 = 0;        // equation range of the owned joints
+    long jl0 = 0, jl1 = 0, ql0 = 0, ql1 = 0;   // joints touched by local elements, their equations
     // shells
     DevBuf<int32_t> sh_nodes;
     DevBuf<double> sh_const, sh_keb, sh_kebc, sh_der, sh_Nm, sh_fg, sh_dens;
@@ -581,6 +582,19 @@ static int build_plan(cb_handle *h)
                     corners[fill[j]++] = c;
                 }
     }
+    // joints touched by this rank's elements and their equation range
+    h->jl0 = NJ; h->jl1 = 0; h->ql0 = h->sz.NEQ; h->ql1 = 0;
+    for (long j = 0; j < NJ; ++j)
+        if (cstart[j + 1] > cstart[j]) {
+            if (j < h->jl0) h->jl0 = j;
+            h->jl1 = j + 1;
+            if (h->h_nfree[j]) {
+                if (h->h_first[j] - 1 < h->ql0) h->ql0 = h->h_first[j] - 1;
+                if (h->h_first[j] - 1 + h->h_nfree[j] > h->ql1) h->ql1 = h->h_first[j] - 1 + h->h_nfree[j];
+            }
+        }
+    if (h->jl1 <= h->jl0) { h->jl0 = h->jl1 = 0; }
+    if (h->ql1 <= h->ql0) { h->ql0 = h->ql1 = 0; }
     // joint adjacency (sorted unique, includes the joint itself when it has elements)
     h->adj_start.assign(NJ + 1, 0);
     h->adj.clear();
@@ -1159,6 +1173,11 @@ static CbForceArgs force_args(cb_handle *h)
     a.fr_ef_ip = h->fr_ef[h->eP].p; a.fr_ef_i = h->fr_ef[h->eN].p;
     a.fr_efFE_ip = h->fr_efFE[h->gP].p; a.fr_efFE_i = h->fr_efFE[h->gN].p;
     a.node_cstart = h->node_cstart.p; a.corners = h->corners.p; a.f_temp = h->f_temp.p;
+    a.jl0 = h->jl0; a.jl1 = h->jl1; a.ql0 = h->ql0; a.ql1 = h->ql1;
+    a.jo0 = std::max(h->j0, h->jl0); a.jo1 = std::min(h->j1, h->jl1);
+    if (h->j0 == 0 && h->j1 == h->sz.NJ) {               // unpartitioned: every joint
+        a.jo0 = a.jl0 = 0; a.jo1 = a.jl1 = h->sz.NJ;
+    }
     return a;
 }
 
@@ -1181,8 +1200,12 @@ extern "C" int cb_update_forces_dev(cb_handle *h, const double *dd_dev, double *
     a.dlpf = dlpf_inout ? *dlpf_inout : 0.0; a.itecnt = itecnt;
     CUDA_TRY(cudaEventRecord(h->ev4, s));
     {   // d_temp += dd (main.c:1949)
-        unsigned g = (unsigned)((h->sz.NEQ + 255) / 256);
-        k_axpy1<<<g, 256, 0, s>>>(h->sz.NEQ, h->dd.p, h->d_temp.p); ++h->launches;
+        const bool whole = h->j0 == 0 && h->j1 == h->sz.NJ;
+        const long q0 = whole ? 0 : h->ql0, nq = whole ? h->sz.NEQ : h->ql1 - h->ql0;
+        if (nq > 0) {
+            unsigned g = (unsigned)((nq + 255) / 256);
+            k_axpy1<<<g, 256, 0, s>>>(nq, h->dd.p + q0, h->d_temp.p + q0); ++h->launches;
+        }
     }
     if (cbk_node_update(a, s)) return fail(CB_ERR_CUDA, "node update launch");
     ++h->launches;

@@ -423,9 +423,10 @@ k_node_update(long NJ, const int32_t *__restrict__ jc, const double *__restrict_
 
 int cbk_node_update(const CbForceArgs &a, cudaStream_t s)
 {
-    long n = a.d.NJ * 3;
+    const long nj = a.jl1 - a.jl0, n = nj * 3;
+    if (n <= 0) return 0;
     unsigned g = (unsigned)((n + 255) / 256);
-    k_node_update<<<g, 256, 0, s>>>(a.d.NJ, a.d.jc, a.dd, a.x_temp, a.x_ip);
+    k_node_update<<<g, 256, 0, s>>>(nj, a.d.jc + a.jl0 * 8, a.dd, a.x_temp + a.jl0 * 3, a.x_ip + a.jl0 * 3);
     return cudaGetLastError() != cudaSuccess;
 }
 
@@ -1244,11 +1245,11 @@ k_frame_trip(CbDev d)
 }
 
 __global__ void __launch_bounds__(256)
-k_gather_f(CbDev d, const int32_t *__restrict__ cstart, const CbCorner *__restrict__ corners,
-           double *__restrict__ f)
+k_gather_f(CbDev d, long j0, long j1, const int32_t *__restrict__ cstart,
+           const CbCorner *__restrict__ corners, double *__restrict__ f)
 {
-    long n = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (n >= d.NJ) return;
+    long n = j0 + blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (n >= j1) return;
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
     const int c0 = cstart[n], c1 = cstart[n + 1];
     // members from the first tripping one onwards never reach the scatter in the reference
@@ -1281,8 +1282,10 @@ k_gather_f(CbDev d, const int32_t *__restrict__ cstart, const CbCorner *__restri
 
 int cbk_gather_f(const CbForceArgs &a, cudaStream_t s)
 {
-    unsigned g = (unsigned)((a.d.NJ + 255) / 256);
-    k_gather_f<<<g, 256, 0, s>>>(a.d, a.node_cstart, a.corners, a.f_temp);
+    const long nj = a.jo1 - a.jo0;
+    if (nj <= 0) return 0;
+    unsigned g = (unsigned)((nj + 255) / 256);
+    k_gather_f<<<g, 256, 0, s>>>(a.d, a.jo0, a.jo1, a.node_cstart, a.corners, a.f_temp);
     return cudaGetLastError() != cudaSuccess;
 }
 

@@ -230,6 +230,10 @@ struct CbForceArgs {
     // trusses
     double *tr_frame_i; double *tr_ef_i;
     double dlpf; int itecnt;
+    // joints touched by this rank's elements [jl0, jl1), joints it owns [jo0, jo1), equations of the
+    // touched joints [ql0, ql1): the nodal kernels run over these ranges only, so that with the mesh
+    // partitioned over several GPUs (global numbering kept) their cost does not grow with the ranks
+    long jl0, jl1, jo0, jo1, ql0, ql1;
     // gather
     const int32_t *node_cstart; const CbCorner *corners;
     double *f_temp;

@@ -1039,6 +1039,19 @@ __global__ void k_yld_reset(long n, int32_t *y)
     if (i < n && y[i] == 2) y[i] = 0;
 }
 
+// The arc-length driver does not advance the *_ip generation on the iteration that converges
+// (main.c:2925-2940: the `_ip <- _i` / `ef_ip <- ef_i` copies sit in the non-converged branch only),
+// so the next increment's predictor still reads the second-to-last iterate as *_ip.  cb_keep_ip
+// undoes the ef_ip <- ef_i renaming of the last cb_update_forces to reproduce exactly that; call
+// it after cb_commit and instead of cb_end_iteration.
+extern "C" int cb_keep_ip(cb_handle *h)
+{
+    if (!h) return fail(CB_ERR_ARG, "null handle");
+    std::swap(h->eP, h->eN);
+    h->krec_fresh = false;
+    return CB_OK;
+}
+
 extern "C" int cb_commit(cb_handle *h)
 {
     if (!h) return fail(CB_ERR_ARG, "null handle");

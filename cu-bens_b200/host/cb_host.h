@@ -54,6 +54,23 @@ int cb_newmark_linear(cb_handle *h, long neq, const long *maxa, long lss, const 
                       long ntstps, double dt, double alpham, double alphaf, const double *um0,
                       const double *vm0, const double *am0, double *hist, cb_nr_result *res);
 
+/* ---- modified spherical arc-length driver (cb_arclength.c) = main.c:2158-3141 (ALGFLAG 3) --------
+ * Bathe & Dvorkin's arc-length iteration with Crisfield & Shi's psi factor: first increment by a
+ * prescribed displacement dk at equation dkdof (0-based, msal() arc.c:41-68), then arc-length
+ * controlled increments until |lpf| > lpfmax or |d[dkdof]| > dkimax.  K_t is assembled from the
+ * committed state once per increment (cb_stiff(CB_GEN_COMMITTED)), factorised with the indefinite
+ * skyline LDL^T (pivots -> psi, sign of the determinant -> direction), f_int every iteration.     */
+typedef struct cb_arc_params {
+    double dk; long dkdof;
+    double alpha, psi_thresh; int iteopt;
+    double lpfmax, dkimax;
+    int itemax, submax, imagmax, negmax;
+    double toldisp, tolforc, tolener;
+} cb_arc_params;
+/* hist: up to max_rows rows (lpf, iterations, d[0..NEQ)); res->increments = rows written */
+int cb_arclength_static(cb_handle *h, long neq, const long *maxa, long lss, const double *q,
+                        const cb_arc_params *p, double *hist, int max_rows, cb_nr_result *res);
+
 #ifdef __cplusplus
 }
 #endif

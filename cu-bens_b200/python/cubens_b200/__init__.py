@@ -36,7 +36,7 @@ EXPORTS = [
     "cb_last_stiff_ms", "cb_last_forces_ms", "cb_last_assemble_ms", "cb_timer_start", "cb_timer_stop_ms", "cb_set_dd", "cb_host_alloc",
     "cb_host_free", "cb_map_bytes", "cb_sync", "cb_stream", "cb_set_q", "cb_residual_sums",
     "cb_dev_sums", "cb_get_sums", "cb_get_yldflag", "cb_set_yldflag", "cb_get_mass_csc_values", "cb_dev_Mx",
-    "cb_geometry_classes",
+    "cb_geometry_classes", "cb_keep_ip",
 ]
 
 
@@ -405,3 +405,27 @@ def newmark(asm, dyn, nonlinear=True):
                              C.c_double(dyn["dt"]), C.c_double(dyn["alpham"]), C.c_double(dyn["alphaf"]),
                              _p(um), _p(vm), _p(am), _p(hist), C.byref(res))
     return hist, res
+
+
+class cb_arc_params(C.Structure):
+    _fields_ = [("dk", C.c_double), ("dkdof", C.c_long), ("alpha", C.c_double), ("psi_thresh", C.c_double),
+                ("iteopt", C.c_int), ("lpfmax", C.c_double), ("dkimax", C.c_double), ("itemax", C.c_int),
+                ("submax", C.c_int), ("imagmax", C.c_int), ("negmax", C.c_int), ("toldisp", C.c_double),
+                ("tolforc", C.c_double), ("tolener", C.c_double)]
+
+
+def arclength_static(asm, q, dk, dkdof, alpha, psi_thresh, iteopt, lpfmax, dkimax, itemax, submax,
+                     imagmax, negmax, toldisp, tolforc, tolener, max_rows=4096):
+    """the C host driver cb_arclength_static (main.c:2158-3141 on the device path).
+    Returns (hist [rows][2+NEQ], result)."""
+    hl = load_host_library()
+    m = asm.m
+    p = cb_arc_params(dk, dkdof, alpha, psi_thresh, iteopt, lpfmax, dkimax, itemax, submax, imagmax,
+                      negmax, toldisp, tolforc, tolener)
+    res = cb_nr_result()
+    hist = np.zeros((max_rows, m.NEQ + 2))
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    maxa = np.ascontiguousarray(m.maxa, dtype=np.int64)
+    hl.cb_arclength_static(asm.h, C.c_long(m.NEQ), _p(maxa), C.c_long(m.lss), _p(q), C.byref(p), _p(hist),
+                           C.c_int(max_rows), C.byref(res))
+    return hist[:res.increments].copy(), res

@@ -158,3 +158,25 @@ def parse_dynamic_tail(m, rows, ALGFLAG):
         out["params"] = dict(lpfmax=a[0], lpf=a[1], dlpf=a[2], dlpfmax=a[3], dlpfmin=a[4], itemax=b[0],
                              submax=b[1], solmin=b[2], toldisp=c[0], tolforc=c[1], tolener=c[2])
     return out
+
+
+def write_shell_deck(m, props, loads, tail_lines, ALGFLAG=None):
+    """text of a `model_def.txt` for a shell-only static model (order fixed by main.c:340-427,
+    model.c:95-264, main.c:1394-1396, shell.c:61, model.c:1313-1335): used to run generated meshes
+    through the unmodified reference driver.  ``tail_lines``: the solver-control lines that follow
+    the joint loads (NR/MNR: main.c:1809-1812; arc-length: arc.c:48 + main.c:2240-2245)."""
+    assert m.NE_TR == 0 and m.NE_FR == 0 and m.NE_SBR + m.NE_FBR == 0
+    L = [str(m.ANAFLAG), str(m.ALGFLAG if ALGFLAG is None else ALGFLAG), "0", "1", str(m.NJ),
+         f"0,0,{m.NE_SH},0,0"]
+    L += [",".join(str(int(v)) for v in r) for r in m.minc.reshape(-1, 3)]
+    jc = m.jcode.reshape(-1, 7)
+    for j in range(m.NJ):
+        for r in range(6):
+            if jc[j, r] == 0:
+                L.append(f"{j + 1},{r + 1}")
+    L.append("0,0")
+    L += ["%.17g,%.17g,%.17g" % tuple(r) for r in m.x.reshape(-1, 3)]
+    L += ["%.17g,%.17g,%.17g,%.17g,%.17g" % tuple(props)] * m.NE_SH
+    L += ["%d,%d,%.17g" % (j, r, v) for (j, r, v) in loads] + ["0,0,0"]
+    L += list(tail_lines)
+    return "\n".join(L) + "\n"

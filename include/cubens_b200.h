@@ -146,6 +146,10 @@ int  cb_end_iteration(cb_handle *h);                                  /* main.c:
 int  cb_get_yldflag(cb_handle *h, int *yldflag, long n);
 int  cb_set_yldflag(cb_handle *h, const int *yldflag, long n);
 int  cb_commit(cb_handle *h);                                         /* main.c:2074-2134  */
+/* arc-length only: the reference does not advance *_ip on the iteration that converges
+ * (main.c:2925-2940), so the next predictor still sees the second-to-last iterate as *_ip; call
+ * this after cb_commit, instead of cb_end_iteration, to reproduce that                      */
+int  cb_keep_ip(cb_handle *h);
 
 /* ---- results -------------------------------------------------------------------------- */
 /* skyline vector in the reference's layout; n must equal lss = maxa[NEQ]-1                */

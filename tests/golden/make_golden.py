@@ -226,6 +226,40 @@ def run_cases():
     return {"run_5b_frame": "model_def_5b_frame.txt", "run_5c_shell": "model_def_5c_shell.txt"}
 
 
+ARC_SHELL = (2.1e11, 0.3, 0.02, 8050.0, 3.45e8)
+ARC = dict(dk=-0.0005, alpha=1.0, psi_thresh=0.1, iteopt=5, lpfmax=1.7102, dkimax=0.01, itemax=50,
+           submax=10, imagmax=10, negmax=10, toldisp=1e-3, tolforc=1e-3, tolener=1e-3)
+
+
+def arc_model():
+    """shallow 4x4 shell cap for the arc-length (ALGFLAG 3) run; the reference's arc length
+    collapses to tiny increments after the first one (beta, main.c:2626-2629), so lpfmax is set just
+    above the first increment's load factor: one prescribed-displacement increment + ~15 MSAL ones"""
+    return meshgen.plate_model(4, 4, props=ARC_SHELL, load=-1.0e5, z_bump=0.1, ALGFLAG=3)
+
+
+def record_arc():
+    import subprocess, tempfile
+    from cubens_b200 import deck
+    m = arc_model()
+    c = m.meta["centre"]
+    a = ARC
+    tail = [f"{c},3,{a['dk']!r}", repr(a["alpha"]), repr(a["psi_thresh"]), str(a["iteopt"]),
+            f"{a['lpfmax']!r},{a['dkimax']!r}", f"{a['itemax']},{a['submax']},{a['imagmax']},{a['negmax']}",
+            f"{a['toldisp']!r},{a['tolforc']!r},{a['tolener']!r}"]
+    text = deck.write_shell_deck(m, ARC_SHELL, [(c, 3, -1.0e5)], tail)
+    exe = os.path.join(ROOT, "oracle", "_ref", "ben_capture.exe")
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "model_def.txt"), "w").write(text)
+        subprocess.run([exe], cwd=td, stdout=subprocess.DEVNULL, timeout=60, check=True)
+        raw = open(os.path.join(td, "capture.bin"), "rb").read()
+        ok = "Solution successful" in open(os.path.join(td, "results1.txt")).read()
+    neq, nrows = np.frombuffer(raw[:16], dtype=np.int64)
+    assert neq == m.NEQ and ok
+    hist = np.frombuffer(raw[16:], dtype=np.float64).reshape(nrows, neq + 2).copy()
+    return m, {"hist": hist, "dkdof": int(m.jcode.reshape(-1, 7)[c - 1, 2] - 1)}
+
+
 def record_run(name):
     import subprocess, tempfile
     from cubens_b200 import deck
@@ -251,6 +285,9 @@ def record_run(name):
 
 
 if __name__ == "__main__":
+    m, out = record_arc()
+    np.savez_compressed(os.path.join(HERE, "run_arc_shell.npz"), **out)
+    print("run_arc_shell NEQ", m.NEQ, "rows", out["hist"].shape[0])
     for name in run_cases():
         m, out = record_run(name)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)

@@ -66,3 +66,25 @@ def test_deck_5c_shell_linear_newmark(gpu):
         assert relerr(hist[k, 2:], ref[k, 2:]) < 1e-9, k
     assert np.abs(ref[-1, 2:]).max() > 0
     asm.close()
+
+
+def test_arclength_shell_cap(gpu):
+    """modified spherical arc-length (ALGFLAG 3, main.c:2158-3141 + quad() arc.c:70): a shallow DKT
+    shell cap through the C host driver cb_arclength_static against the unmodified reference driver
+    (run_arc_shell.npz): the prescribed-displacement increment, then 20 MSAL increments - load
+    factors, iteration counts and displacement vectors"""
+    import sys
+    sys.path.insert(0, GOLD)
+    import make_golden as G
+    g = np.load(os.path.join(GOLD, "run_arc_shell.npz"))
+    ref = g["hist"]
+    m = G.arc_model()
+    a = dict(G.ARC)
+    asm = cb.Assembler(m, layout=cb.CB_MAT_SKYLINE)
+    hist, res = cb.arclength_static(asm, m.q, dkdof=int(g["dkdof"]), **a)
+    assert res.status == 0 and hist.shape == ref.shape
+    assert np.array_equal(hist[:, 1], ref[:, 1])
+    assert np.allclose(hist[:, 0], ref[:, 0], rtol=1e-9, atol=0)
+    for k in range(ref.shape[0]):
+        assert relerr(hist[k, 2:], ref[k, 2:]) < 1e-9, k
+    asm.close()

@@ -44,12 +44,17 @@ int cb_newton_static(cb_handle *h, long neq, const long *maxa, long lss, const d
 /* ---- transient drivers (cb_newmark.c) --------------------------------------------------------
  * pinpt [NEQ][ntstps]: the load histories load() stores (model.c:1490-1535), dt = ttot / (ntstps-1),
  * alpham / alphaf: generalized-alpha parameters (main.c:3337-3351).  hist receives one row per time
- * step: time, iterations, d[0..NEQ) - what the reference hands to output().  Models with
- * prescribed support motion (NBC != 0) are not supported.                                       */
+ * step: time, iterations, d[0..NEQ) - what the reference hands to output().                      */
 void cb_sky_mult(long neq, const long *maxa, const double *ss, double *v);   /* solve.c:700-756 */
 int cb_newmark_nonlinear(cb_handle *h, long neq, const long *maxa, long lss, const double *pinpt,
                          long ntstps, double dt, double alpham, double alphaf,
                          const cb_nr_params *p, double *hist, cb_nr_result *res);
+/* same with prescribed support motion: pdisp [NEQ][ntstps] (model.c:1537-1572) and pmot [NEQ] = 1 at
+ * the equations listed as moved supports (skylin(), model.c:1149-1201); the effective matrix is
+ * partitioned as matpart() does (solve.c:758-824).  pdisp / pmot may be NULL (no support motion). */
+int cb_newmark_nonlinear_bc(cb_handle *h, long neq, const long *maxa, long lss, const double *pinpt,
+                            const double *pdisp, const int *pmot, long ntstps, double dt, double alpham,
+                            double alphaf, const cb_nr_params *p, double *hist, cb_nr_result *res);
 int cb_newmark_linear(cb_handle *h, long neq, const long *maxa, long lss, const double *pinpt,
                       long ntstps, double dt, double alpham, double alphaf, const double *um0,
                       const double *vm0, const double *am0, double *hist, cb_nr_result *res);

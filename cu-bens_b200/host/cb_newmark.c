@@ -10,8 +10,9 @@
  *                         assembly, one factorisation, a time loop of effective-load solves.
  *
  * Both follow the reference statement by statement (same operation order), because the parity
- * target is its displacement history to 1e-9.  Prescribed support motion (NBC != 0: matpart,
- * solve.c:758-824) is not carried over: the caller must not pass such a model. */
+ * target is its displacement history to 1e-9.  Prescribed support motion (NBC != 0) is carried by
+ * cb_newmark_nonlinear_bc: heavy masses at the moved supports, matpart() (solve.c:758-824) on the
+ * effective matrix, inertial reactions (main.c:3707-3727); not by the linear driver. */
 #include "cb_host.h"
 #include <math.h>
 #include <stdlib.h>
@@ -85,12 +86,72 @@ static void newmark_constants(double alpham, double alphaf, double dt_temp, doub
     a[7] = delta * (dt_temp);
 }
 
+/* matpart(), solve.c:758-824: rows / columns of the moved supports are taken out of the skyline
+ * matrix (unit diagonal), their known displacements uc go to the right-hand side.  ii / ij = the
+ * equations without / with support motion (main.c:1341-1353).  Statement order as the reference. */
+static void matpart(long neq, long nbc, const long *maxa, double *ss, double *qtot, const double *uc,
+                    const long *ii, const long *ij)
+{
+    long n = ij[nbc - 1] + 1;
+    for (long i = 1; i <= nbc; ++i) {
+        const long kl = maxa[n - 1] + 1, ku = maxa[n] - 1;
+        if (ku - kl >= 0) {
+            long k = n - 1;
+            for (long kk = kl; kk <= ku; ++kk) {
+                --k;
+                for (long j = 0; j < nbc; ++j)
+                    if (k == ij[j]) ss[kk - 1] = 0;
+            }
+            k = n - 1;
+            for (long kk = kl; kk <= ku; ++kk) {
+                --k;
+                qtot[k] -= ss[kk - 1] * uc[n - 1];
+                ss[kk - 1] = 0;
+            }
+        }
+        if (i < nbc) n = ij[nbc - 1 - i] + 1;
+    }
+    for (long m = 0; m < nbc; ++m) ss[maxa[ij[m]] - 1] = 1;
+    const long nf = neq - nbc;
+    if (nf <= 0) return;
+    n = ii[nf - 1] + 1;
+    for (long i = 1; i <= nf; ++i) {
+        const long kl = maxa[n - 1] + 1, ku = maxa[n] - 1;
+        if (ku - kl >= 0) {
+            long k = n;
+            for (long kk = kl; kk <= ku; ++kk) {
+                --k;
+                for (long j = 0; j < nbc; ++j)
+                    if (k - 1 == ij[j]) { qtot[n - 1] -= ss[kk - 1] * uc[k - 1]; ss[kk - 1] = 0; }
+            }
+        }
+        if (i < nf) n = ii[nf - 1 - i] + 1;
+    }
+}
+
 int cb_newmark_nonlinear(cb_handle *h, long neq, const long *maxa, long lss, const double *pinpt,
                          long ntstps, double dt, double alpham, double alphaf,
                          const cb_nr_params *p, double *hist, cb_nr_result *res)
 {
+    return cb_newmark_nonlinear_bc(h, neq, maxa, lss, pinpt, NULL, NULL, ntstps, dt, alpham, alphaf, p, hist, res);
+}
+
+int cb_newmark_nonlinear_bc(cb_handle *h, long neq, const long *maxa, long lss, const double *pinpt,
+                            const double *pdisp, const int *pmot, long ntstps, double dt, double alpham,
+                            double alphaf, const cb_nr_params *p, double *hist, cb_nr_result *res)
+{
     if (!h || !maxa || !pinpt || !p || !hist || !res) return CB_ERR_ARG;
     memset(res, 0, sizeof *res);
+    long nbc = 0, *ii = NULL, *ij = NULL;
+    if (pmot && pdisp) {
+        for (long i = 0; i < neq; ++i) nbc += pmot[i] != 0;
+        if (nbc) {
+            ii = (long *)malloc((size_t)(neq - nbc + 1) * sizeof(long));
+            ij = (long *)malloc((size_t)nbc * sizeof(long));
+            long ci = 0, cj = 0;
+            for (long i = 0; i < neq; ++i) { if (pmot[i] == 0) ii[ci++] = i; else ij[cj++] = i; }
+        }
+    }
     double *buf = (double *)calloc((size_t)neq * 20 + 2 * (size_t)lss, sizeof(double));
     if (!buf) return CB_ERR_ARG;
     double *qtot = buf, *d = qtot + neq, *d_temp = d + neq, *f = d_temp + neq, *f_temp = f + neq,
@@ -121,6 +182,9 @@ int cb_newmark_nonlinear(cb_handle *h, long neq, const long *maxa, long lss, con
                 itecnt = 0;
                 frcchk_fr = frcchk_sh = 0;
                 do {                                         /* iterations, main.c:3544 */
+                    if (nbc)                                 /* moved supports, main.c:3546-3551 */
+                        for (long i = 0; i < neq; ++i)
+                            if (pdisp[i * ntstps + k] != 0) uc_i[i] = (pdisp[i * ntstps + k] - um[i]) * sub_dt * lpf;
                     if (itecnt == 0) {                       /* predictor, main.c:3553-3571 */
                         if (k == 0) {
                             for (long i = 0; i < neq; ++i) {
@@ -150,11 +214,21 @@ int cb_newmark_nonlinear(cb_handle *h, long neq, const long *maxa, long lss, con
                     if (lss == 1) {
                         dd[0] = r[0] / ss[0];
                     } else {                                 /* solve(), solve.c:139-186, 470-536 */
+                        if (nbc)                             /* heavy masses at the moved supports */
+                            for (long i = 0; i < neq; ++i)
+                                if (pdisp[i * ntstps + k] != 0) sm[i] = 1000000 * sm[i];
                         for (long i = 0; i < lss; ++i) Keff[i] = ss[i];
                         for (long i = 0; i < neq; ++i) Keff[maxa[i] - 1] += a[0] * (1 - alpham) * sm[i] / (1 - alphaf);
-                        if (cb_sky_factor(neq, maxa, Keff, NULL, NULL, 0)) FAIL(2);
-                        for (long i = 0; i < neq; ++i)
-                            dd[i] = r[i] + sm[i] * ((1 - alpham) * (vc_i[i] * a[2] + ac_i[i] * a[3]) - alpham * ac_i[i]) / (1 - alphaf);
+                        if (!nbc && cb_sky_factor(neq, maxa, Keff, NULL, NULL, 0)) FAIL(2);
+                        for (long i = 0; i < neq; ++i) {
+                            if (nbc && pdisp[i * ntstps + k] != 0 && itecnt > 0) dd[i] = 0;
+                            else if (nbc && pdisp[i * ntstps + k] != 0 && itecnt == 0) dd[i] = uc_i[i];
+                            else dd[i] = r[i] + sm[i] * ((1 - alpham) * (vc_i[i] * a[2] + ac_i[i] * a[3]) - alpham * ac_i[i]) / (1 - alphaf);
+                        }
+                        if (nbc) {
+                            matpart(neq, nbc, maxa, Keff, dd, uc_i, ii, ij);
+                            if (cb_sky_factor(neq, maxa, Keff, NULL, NULL, 0)) FAIL(2);
+                        }
                         cb_sky_solve(neq, maxa, Keff, dd);
                     }
                     for (long i = 0; i < neq; ++i) {         /* main.c:3642-3656 */
@@ -175,6 +249,9 @@ int cb_newmark_nonlinear(cb_handle *h, long neq, const long *maxa, long lss, con
                         intener1 = 0;
                         for (long i = 0; i < neq; ++i) intener1 += dd[i] * (dyn[i] - fp[i]);
                     }
+                    if (nbc)                                 /* main.c:3707-3727 */
+                        for (long i = 0; i < neq; ++i)
+                            if (pmot[i] != 0) f_temp[i] = -sm[i] * ac_i[i];
                     if (conv_test(neq, d_temp, dd, f_temp, fp, dyn, f_ip, intener1, p, &convchk)) FAIL(3);
                     if ((rc = cb_end_iteration(h)) != CB_OK) FAIL(100 + rc);
                     ++itecnt;
@@ -228,6 +305,7 @@ int cb_newmark_nonlinear(cb_handle *h, long neq, const long *maxa, long lss, con
     } while (k < ntstps);
 done:
     res->status = status; res->lpf = lpf;
+    free(ii); free(ij);
     free(buf);
     return status == 0 ? CB_OK : CB_ERR_ARG;
 #undef FAIL

@@ -385,8 +385,8 @@ def newmark(asm, dyn, nonlinear=True):
     Returns (hist [ntstps][2+NEQ], result)."""
     hl = load_host_library()
     m = asm.m
-    if dyn["nbc"]:
-        raise CubensError("prescribed support motion (NBC != 0) is not supported by the host drivers")
+    if dyn["nbc"] and not nonlinear:
+        raise CubensError("prescribed support motion (NBC != 0) is not supported by the linear driver")
     nt = int(dyn["ntstps"])
     hist = np.zeros((nt, m.NEQ + 2))
     res = cb_nr_result()
@@ -396,9 +396,11 @@ def newmark(asm, dyn, nonlinear=True):
         q = dyn["params"]
         p = cb_nr_params(q["lpfmax"], q["lpf"], q["dlpf"], q["dlpfmax"], q["dlpfmin"], q["itemax"],
                          q["submax"], q["solmin"], q["toldisp"], q["tolforc"], q["tolener"], 1)
-        hl.cb_newmark_nonlinear(asm.h, C.c_long(m.NEQ), _p(maxa), C.c_long(m.lss), _p(pin), C.c_long(nt),
-                                C.c_double(dyn["dt"]), C.c_double(dyn["alpham"]), C.c_double(dyn["alphaf"]),
-                                C.byref(p), _p(hist), C.byref(res))
+        pdisp = np.ascontiguousarray(dyn["pdisp"], dtype=np.float64)
+        pmot = np.ascontiguousarray(dyn["pmot"], dtype=np.int32)
+        hl.cb_newmark_nonlinear_bc(asm.h, C.c_long(m.NEQ), _p(maxa), C.c_long(m.lss), _p(pin), _p(pdisp),
+                                   _p(pmot), C.c_long(nt), C.c_double(dyn["dt"]), C.c_double(dyn["alpham"]),
+                                   C.c_double(dyn["alphaf"]), C.byref(p), _p(hist), C.byref(res))
     else:
         um, vm, am = (np.ascontiguousarray(dyn[k], dtype=np.float64) for k in ("um", "vm", "am"))
         hl.cb_newmark_linear(asm.h, C.c_long(m.NEQ), _p(maxa), C.c_long(m.lss), _p(pin), C.c_long(nt),

@@ -41,11 +41,13 @@ def read_deck(text):
         if int(r[0]) == 0:
             break
         fixed.append((int(r[0]), int(r[1])))
+    moved = []
     if ANAFLAG != 4 and ALGFLAG > 3:            # prescribed-displacement DOFs (model.c:1156-1201)
         while True:
             r = nxt()
             if int(r[0]) == 0:
                 break
+            moved.append((int(r[0]), int(r[1])))
     x = np.array([[float(v) for v in nxt()] for _ in range(NJ)])
     tp = [[float(v) for v in nxt()] for _ in range(NE_TR)]
     fp = None; aux = None; offsets = {}; releases = {}
@@ -101,6 +103,12 @@ def read_deck(text):
             m.c1[cs], m.c2[cs], m.c3[cs] = lx.reshape(-1), ly.reshape(-1), lz.reshape(-1)
     if dyn_tail is not None:
         tail = parse_dynamic_tail(m, dyn_tail, ALGFLAG)
+        pmot = np.zeros(m.NEQ, dtype=np.int32)              # skylin(), model.c:1149-1201
+        jc = m.jcode.reshape(-1, 7)
+        for j, k in moved:
+            pmot[jc[j - 1, k - 1] - 1] = 1
+        tail["pmot"] = pmot
+        tail["nbc"] = int(pmot.sum())
     return m, params, tail
 
 

@@ -223,7 +223,8 @@ def record_deck(name, B=R):
 def run_cases():
     """full transient runs of the shipped decks through the UNMODIFIED reference driver
     (oracle/_ref/ben_capture.exe = main.c with its output() rows recorded at full precision)"""
-    return {"run_5b_frame": "model_def_5b_frame.txt", "run_5c_shell": "model_def_5c_shell.txt"}
+    return {"run_5b_frame": "model_def_5b_frame.txt", "run_5c_shell": "model_def_5c_shell.txt",
+            "run_5d_shell": "model_def_5d_shell.txt"}
 
 
 ARC_SHELL = (2.1e11, 0.3, 0.02, 8050.0, 3.45e8)
@@ -265,6 +266,8 @@ def record_run(name):
     from cubens_b200 import deck
     from cubens_b200.model import model_to_dict
     text = open(DECKS + run_cases()[name]).read().replace("\r", "")
+    if name == "run_5d_shell":      # shipped with RFLAG = 1 (restart from a results8.txt that is not shipped)
+        lines = text.split("\n"); assert lines[2] == "4,1"; lines[2] = "4,0"; text = "\n".join(lines)
     m, _, dyn = deck.read_deck(text)
     out = model_to_dict(m)
     for k, v in dyn.items():
@@ -276,7 +279,7 @@ def record_run(name):
     exe = os.path.join(ROOT, "oracle", "_ref", "ben_capture.exe")
     with tempfile.TemporaryDirectory() as td:
         open(os.path.join(td, "model_def.txt"), "w").write(text)
-        subprocess.check_call([exe], cwd=td, stdout=subprocess.DEVNULL)
+        subprocess.run([exe], cwd=td, stdout=subprocess.DEVNULL, timeout=120, check=True)
         raw = open(os.path.join(td, "capture.bin"), "rb").read()
     neq, nrows = np.frombuffer(raw[:16], dtype=np.int64)
     assert neq == m.NEQ

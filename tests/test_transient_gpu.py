@@ -88,3 +88,20 @@ def test_arclength_shell_cap(gpu):
     for k in range(ref.shape[0]):
         assert relerr(hist[k, 2:], ref[k, 2:]) < 1e-9, k
     asm.close()
+
+
+def test_deck_5d_shell_newmark_support_motion(gpu):
+    """model_def_5d_shell.txt (ANAFLAG 2 / ALGFLAG 5, RFLAG set to 0): geometric-nonlinear DKT shells
+    driven by prescribed support motion (NBC = 2: heavy support masses, matpart() on the effective
+    matrix, inertial reactions) - 20 time steps against the unmodified reference driver"""
+    g, m, dyn = _load("run_5d_shell")
+    assert (m.ANAFLAG, m.ALGFLAG) == (2, 5) and dyn["nbc"] == 2
+    asm = cb.Assembler(m, layout=cb.CB_MAT_SKYLINE)
+    hist, res = cb.newmark(asm, dyn, nonlinear=True)
+    ref = g["hist"]
+    assert res.status == 0 and hist.shape == ref.shape
+    assert np.array_equal(hist[:, 1], ref[:, 1])
+    for k in range(ref.shape[0]):
+        assert relerr(hist[k, 2:], ref[k, 2:]) < 1e-9, k
+    assert np.abs(ref[-1, 2:]).max() > 1e-3
+    asm.close()

@@ -1063,8 +1063,48 @@ __device__ __forceinline__ void frame_rigid_link(const double *off, double (*Tr)
     Tr[12][7] = -off[4]; Tr[12][8] = off[3];
 }
 
+// def = k dl with the local tangent of frame e, generic version (plasticity, end releases, rigid end
+// offsets: runtime indices, local memory)
+__device__ __noinline__ void frame_def_generic(const CbDev &d, long e, const double *ef_ip,
+                                               const double *efFE_ip, const double *Rp, const double *DD12,
+                                               int os, double *dl, double *eft, double *def)
+{
+    double k[14][14];
+    frame_local_k(d, e, ef_ip, efFE_ip, Rp[9], k, eft);
+    if (os == 0) {
+        frame_T_apply(Rp, DD12, dl);
+    } else {
+        double DDij[14], Tr[14][14];
+        frame_rigid_link(d.fr_offset + e * 6, Tr);
+        for (int i = 0; i < 14; ++i) {
+            double s = 0;
+            for (int j = 0; j < 14; ++j) s += Tr[j][i] * DD12[j];
+            DDij[i] = s;
+        }
+        frame_T_apply(Rp, DDij, dl);
+    }
+    for (int i = 0; i < 14; ++i) {
+        double s = 0;
+        for (int j = 0; j < 14; ++j) s += k[i][j] * dl[j];
+        def[i] = s;
+    }
+}
+
+// EF <- T_rl EF (frame.c:1290-1309)
+__device__ __noinline__ void frame_rigid_link_apply(const double *off, double *EF)
+{
+    double Tr[14][14], G2[14];
+    frame_rigid_link(off, Tr);
+    for (int i = 0; i < 14; ++i) {
+        double s = 0;
+        for (int j = 0; j < 14; ++j) s += Tr[i][j] * EF[j];
+        G2[i] = s;
+    }
+    for (int i = 0; i < 14; ++i) EF[i] = G2[i];
+}
+
 template <bool INPLACE>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(CB_FR_TPB, 4)
 k_frame_forces(CbDev d, const double *__restrict__ x_new, const double *__restrict__ dd,
                const double *frame_ip, double *frame_i, double *xfr_i, const double *ef_ip,
                double *ef_i, const double *efFE_ip, double *efFE_i, double dlpf, int itecnt)
@@ -1093,31 +1133,36 @@ k_frame_forces(CbDev d, const double *__restrict__ x_new, const double *__restri
 #pragma unroll
         for (int i = 0; i < CB_FR_FRAME; ++i) Ri[i] = Rp[i];
     }
-    double k[14][14], eft[14];
-    frame_local_k(d, e, ef_ip, efFE_ip, Rp[9], k, eft);
-    double DD12[14], dl[14], def[14];
+    double eft[14], DD12[14], dl[14], def[14];
 #pragma unroll
     for (int r = 0; r < 7; ++r) {
         int q = d.jc[(long)nj * 8 + r]; DD12[r] = q ? dd[q - 1] : 0.0;
         q = d.jc[(long)nk * 8 + r];     DD12[7 + r] = q ? dd[q - 1] : 0.0;
     }
-    double Tr[14][14];
-    if (os == 0) {
+    if (os == 0 && d.ANAFLAG != 3 && d.fr_mendrel[e * 5] != 1) {
+        // no plasticity, end releases or rigid offsets: the local tangent (upper triangle) is built in
+        // this thread's column of shared memory with static indices.  The generic path keeps 14x14
+        // doubles per thread in LOCAL memory, which the L2 writes back to HBM (2.7 GB for 0.7 GB of
+        // results on a 1.5 M-frame lattice, profiles/r01c_prof_frame_forces.txt).
+        extern __shared__ double sk_all[];
+        double *sk = sk_all + threadIdx.x;
+        const double *fc2 = d.fr_const + e * CB_FR_CONST;
+#pragma unroll
+        for (int i = 0; i < 105; ++i) sk[i * CB_FR_TPB] = 0;
+#pragma unroll
+        for (int i = 0; i < 14; ++i) eft[i] = ef_ip[e * 14 + i] + efFE_ip[e * 14 + i];
+        frame_elastic_packed(sk, fc2);
+        if (d.ANAFLAG == 2) frame_geometric_packed(sk, eft, Rp[9], fc2[2], fc2[8]);
         frame_T_apply(Rp, DD12, dl);
-    } else {
-        double DDij[14];
-        frame_rigid_link(d.fr_offset + e * 6, Tr);
+#pragma unroll
         for (int i = 0; i < 14; ++i) {
             double s = 0;
-            for (int j = 0; j < 14; ++j) s += Tr[j][i] * DD12[j];
-            DDij[i] = s;
+#pragma unroll
+            for (int j = 0; j < 14; ++j) s += KP(i, j) * dl[j];
+            def[i] = s;
         }
-        frame_T_apply(Rp, DDij, dl);
-    }
-    for (int i = 0; i < 14; ++i) {
-        double s = 0;
-        for (int j = 0; j < 14; ++j) s += k[i][j] * dl[j];
-        def[i] = s;
+    } else {
+        frame_def_generic(d, e, ef_ip, efFE_ip, Rp, DD12, os, dl, eft, def);
     }
     // M = T_i T_ip^T: four copies of R_i R_ip^T and 1 on the warping DOFs (frame.c:1078-1086)
     double M[3][3];
@@ -1197,6 +1242,7 @@ k_frame_forces(CbDev d, const double *__restrict__ x_new, const double *__restri
             y1 = 1;
         }
         if (code == 0 && (y0 == 1 || y1 == 1)) {
+            double k[14][14];
             for (int i = 0; i < 14; ++i)
                 for (int j = 0; j < 14; ++j) k[i][j] = 0;
             frame_elastic(k, fc);
@@ -1212,15 +1258,7 @@ k_frame_forces(CbDev d, const double *__restrict__ x_new, const double *__restri
     }
     double EF[14];
     frame_Tt_apply(Ri, efn, EF);
-    if (os != 0) {
-        double G2[14];
-        for (int i = 0; i < 14; ++i) {
-            double s = 0;
-            for (int j = 0; j < 14; ++j) s += Tr[i][j] * EF[j];
-            G2[i] = s;
-        }
-        for (int i = 0; i < 14; ++i) EF[i] = G2[i];
-    }
+    if (os != 0) frame_rigid_link_apply(d.fr_offset + e * 6, EF);
 #pragma unroll
     for (int i = 0; i < 14; ++i) d.fr_fg[e * 14 + i] = EF[i];
 }
@@ -1289,9 +1327,22 @@ int cbk_gather_f(const CbForceArgs &a, cudaStream_t s)
     return cudaGetLastError() != cudaSuccess;
 }
 
+#define CB_FR_SMEM (105 * CB_FR_TPB * sizeof(double))
+static int frame_forces_configure()
+{
+    static bool done = false;
+    if (done) return 0;
+    if (cudaFuncSetAttribute(k_frame_forces<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB_FR_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_frame_forces<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB_FR_SMEM) != cudaSuccess)
+        return 1;
+    done = true;
+    return 0;
+}
+
 int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
 {
     const CbDev &d = a.d;
+    if (d.NE_FR && frame_forces_configure()) return 1;
     if (d.NE_TR) {
         unsigned g = (unsigned)((d.NE_TR + CB_TPB - 1) / CB_TPB);
         k_truss_forces<<<g, CB_TPB, 0, s>>>(d, a.x_temp, a.tr_frame_i, a.tr_ef_i);
@@ -1303,7 +1354,7 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
             static const int init[4] = {0x7fffffff, 0, 0, 0};
             if (cudaMemcpyAsync(d.fr_trip, init, sizeof init, cudaMemcpyHostToDevice, s) != cudaSuccess) return 1;
         }
-        k_frame_forces<false><<<g, 64, 0, s>>>(d, a.x_temp, a.dd, a.fr_frame_ip, a.fr_frame_i,
+        k_frame_forces<false><<<g, CB_FR_TPB, CB_FR_SMEM, s>>>(d, a.x_temp, a.dd, a.fr_frame_ip, a.fr_frame_i,
                                                a.fr_xfr_i, a.fr_ef_ip, a.fr_ef_i, a.fr_efFE_ip,
                                                a.fr_efFE_i, a.dlpf, a.itecnt);
         ++*launches;
@@ -1347,6 +1398,7 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
 int cbk_forces_linear(const CbForceArgs &a, const double *d_total, cudaStream_t s, long *launches)
 {
     const CbDev &d = a.d;
+    if (d.NE_FR && frame_forces_configure()) return 1;
     if (d.NE_TR) {
         unsigned g = (unsigned)((d.NE_TR + CB_TPB - 1) / CB_TPB);
         k_truss_forces_linear<<<g, CB_TPB, 0, s>>>(d, d_total, a.tr_frame_i, a.tr_ef_i);
@@ -1354,7 +1406,7 @@ int cbk_forces_linear(const CbForceArgs &a, const double *d_total, cudaStream_t 
     }
     if (d.NE_FR) {
         unsigned g = (unsigned)((d.NE_FR + 63) / 64);
-        k_frame_forces<true><<<g, 64, 0, s>>>(d, a.x_temp, d_total, a.fr_frame_i, a.fr_frame_i,
+        k_frame_forces<true><<<g, CB_FR_TPB, CB_FR_SMEM, s>>>(d, a.x_temp, d_total, a.fr_frame_i, a.fr_frame_i,
                                               a.fr_xfr_i, a.fr_ef_i, a.fr_ef_i, a.fr_efFE_i,
                                               a.fr_efFE_i, 0.0, 0);
         ++*launches;

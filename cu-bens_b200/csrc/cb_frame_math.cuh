@@ -81,6 +81,83 @@ __device__ __forceinline__ void frame_geometric(double (*k)[14], const double *e
 #undef CB_SUB
 }
 
+// ---- packed variants for the force path: elastic + geometric tangent in a thread-private column of
+// SHARED memory, upper triangle only (both are bitwise symmetric: every entry and its mirror get
+// the same values in the same order, frame.c:364-579), entry (i, j) of thread t at
+// sk[tri(i, j) * CB_FR_TPB + t].  Same expressions and operation order as frame_elastic /
+// frame_geometric above; the point is that the 14x14 matrix never lives in local memory.
+#define CB_FR_TPB 64
+#define CB_FR_TRI(i, j) ((i) >= (j) ? (i) * ((i) + 1) / 2 + (j) : (j) * ((j) + 1) / 2 + (i))
+#define KP(i, j) sk[CB_FR_TRI(i, j) * CB_FR_TPB]
+__device__ __forceinline__ void frame_elastic_packed(double *sk, const double *fc)
+{
+    const double E = fc[0], G = fc[1], A = fc[2], L = fc[3], L3 = fc[5];
+    const double Iz = fc[6], Iy = fc[7], J = fc[8], Cw = fc[9];
+#define CB_SYM(i, j, v) KP(i, j) = (v)
+    KP(0, 0) = KP(7, 7) = E * A / L;                 CB_SYM(7, 0, -KP(0, 0));
+    KP(1, 1) = KP(8, 8) = 12 * E * Iz / L3;          CB_SYM(8, 1, -KP(1, 1));
+    KP(2, 2) = KP(9, 9) = 12 * E * Iy / L3;          CB_SYM(9, 2, -KP(2, 2));
+    KP(3, 3) = KP(10, 10) = 6 * G * J / (5 * L) + 12 * E * Cw / L3;   CB_SYM(10, 3, -KP(3, 3));
+    KP(5, 5) = KP(12, 12) = 4 * E * Iz / L;
+    KP(4, 4) = KP(11, 11) = 4 * E * Iy / L;
+    KP(6, 6) = KP(13, 13) = 2 * G * J * L / 15 + 4 * E * Cw / L;
+    CB_SYM(5, 1, 6 * E * Iz / (L * L)); CB_SYM(12, 1, KP(5, 1));
+    CB_SYM(8, 5, -KP(5, 1));             CB_SYM(12, 8, -KP(5, 1));
+    CB_SYM(9, 4, 6 * E * Iy / (L * L)); CB_SYM(11, 9, KP(9, 4));
+    CB_SYM(4, 2, -KP(9, 4));             CB_SYM(11, 2, -KP(9, 4));
+    CB_SYM(6, 3, G * J / 10 + 6 * E * Cw / (L * L)); CB_SYM(13, 3, KP(6, 3));
+    CB_SYM(10, 6, -KP(6, 3));            CB_SYM(13, 10, -KP(6, 3));
+    CB_SYM(12, 5, 2 * E * Iz / L);
+    CB_SYM(11, 4, 2 * E * Iy / L);
+    CB_SYM(13, 6, -(G * J * L / 30 - 2 * E * Cw / L));
+#undef CB_SYM
+}
+
+__device__ __forceinline__ void frame_geometric_packed(double *sk, const double *ef, double L, double A,
+                                                       double J)
+{
+    const double P = ef[7], M4 = ef[4], M5 = ef[5], M10 = ef[10], M11 = ef[11], M12 = ef[12];
+#define CB_ADD(i, j, v) do { KP(i, j) += (v); } while (0)
+#define CB_SUB(i, j, v) do { KP(i, j) -= (v); } while (0)
+    KP(0, 0) += P / L; KP(7, 7) += P / L; CB_SUB(7, 0, P / L);
+    KP(1, 1) += 6 * P / (5 * L); KP(8, 8) += 6 * P / (5 * L);
+    KP(2, 2) += 6 * P / (5 * L); KP(9, 9) += 6 * P / (5 * L);
+    CB_SUB(8, 1, 6 * P / (5 * L)); CB_SUB(9, 2, 6 * P / (5 * L));
+    KP(3, 3) += 6 * P * J / (5 * A * L); KP(10, 10) += 6 * P * J / (5 * A * L);
+    CB_SUB(10, 3, 6 * P * J / (5 * A * L));
+    KP(4, 4) += 2 * P * L / 15; KP(11, 11) += 2 * P * L / 15;
+    KP(5, 5) += 2 * P * L / 15; KP(12, 12) += 2 * P * L / 15;
+    KP(6, 6) += 2 * P * J / (15 * A); KP(13, 13) += 2 * P * J / (15 * A);
+    CB_ADD(3, 1, (11 * M4 - M11) / (10 * L)); CB_SUB(8, 3, (11 * M4 - M11) / (10 * L));
+    CB_ADD(4, 1, M10 / L); CB_ADD(5, 2, M10 / L); CB_ADD(11, 8, M10 / L); CB_ADD(12, 9, M10 / L);
+    CB_SUB(11, 1, M10 / L); CB_SUB(12, 2, M10 / L); CB_SUB(8, 4, M10 / L); CB_SUB(9, 5, M10 / L);
+    CB_ADD(5, 1, P / 10); CB_ADD(12, 1, P / 10); CB_ADD(9, 4, P / 10); CB_ADD(11, 9, P / 10);
+    CB_SUB(4, 2, P / 10); CB_SUB(11, 2, P / 10); CB_SUB(8, 5, P / 10); CB_SUB(12, 8, P / 10);
+    CB_ADD(6, 1, M4 / 10); CB_SUB(8, 6, M4 / 10);
+    CB_ADD(10, 8, (M4 - 11 * M11) / (10 * L)); CB_SUB(10, 1, (M4 - 11 * M11) / (10 * L));
+    CB_ADD(13, 8, M11 / 10); CB_SUB(13, 1, M11 / 10);
+    CB_ADD(3, 2, (11 * M5 - M12) / (10 * L)); CB_SUB(9, 3, (11 * M5 - M12) / (10 * L));
+    CB_ADD(6, 2, M5 / 10); CB_SUB(9, 6, M5 / 10);
+    CB_ADD(10, 9, (M5 - 11 * M12) / (10 * L)); CB_SUB(10, 2, (M5 - 11 * M12) / (10 * L));
+    CB_ADD(13, 9, M12 / 10); CB_SUB(13, 2, M12 / 10);
+    CB_SUB(4, 3, (2 * M5 - M12) / 5); CB_ADD(5, 3, (2 * M4 - M11) / 5);
+    CB_ADD(6, 3, P * J / (10 * A)); CB_ADD(13, 3, P * J / (10 * A));
+    CB_SUB(10, 6, P * J / (10 * A)); CB_SUB(13, 10, P * J / (10 * A));
+    CB_SUB(11, 3, (2 * M5 + M12) / 10); CB_ADD(12, 3, (2 * M4 + M11) / 10);
+    CB_SUB(6, 4, (3 * M5 - M12) * L / 30); CB_SUB(10, 4, (M5 + 2 * M12) / 10);
+    CB_SUB(11, 4, P * L / 30); CB_SUB(12, 5, P * L / 30);
+    CB_ADD(12, 4, M10 / 2); CB_SUB(11, 5, M10 / 2);
+    CB_ADD(13, 4, M5 * L / 30);
+    CB_ADD(6, 5, (3 * M4 - M11) * L / 30); CB_ADD(10, 5, (M4 + 2 * M11) / 10);
+    CB_SUB(13, 5, M4 * L / 30);
+    CB_SUB(11, 6, M12 * L / 30); CB_ADD(12, 6, M11 * L / 30);
+    CB_SUB(13, 6, P * J / (30 * A));
+    CB_ADD(11, 10, (M5 - 2 * M12) / 5); CB_SUB(12, 10, (M4 - 2 * M11) / 5);
+    CB_SUB(13, 11, (M5 - 3 * M12) * L / 30); CB_ADD(13, 12, (M4 - 3 * M11) * L / 30);
+#undef CB_ADD
+#undef CB_SUB
+}
+
 // ---- stiffness-path variants: the same closed forms with every division replaced by a product with
 // a reciprocal formed once (three FP64 divisions per block instead of ~60, each of which is a
 // ~30-instruction sequence on the FP64 pipe).  K_t has no cancellation beyond its own magnitude, so

@@ -191,7 +191,7 @@ __device__ __noinline__ void frame_block(const CbStiffArgs &A, int e, int a, int
 // is static, so it lives in registers and the three quarters of it this block does not need are
 // never computed (the generic version above keeps it in local memory: 4 KB of stack per thread).
 // Members with end releases (static condensation, runtime pivots) take the generic path.
-template <int LA, int LB>
+template <int LA, int LB, bool PL>
 __device__ __noinline__ void frame_block_t(const CbStiffArgs &A, int e, double *stg, int str)
 {
     double k[14][14], eft[14];
@@ -205,7 +205,7 @@ __device__ __noinline__ void frame_block_t(const CbStiffArgs &A, int e, double *
     }
     frame_elastic_rcp(k, fc);
     if (A.d.ANAFLAG >= 2) frame_geometric_rcp(k, eft, fr[9], fc[2], fc[8]);
-    if (A.d.ANAFLAG == 3) {
+    if (PL) {                     // ANAFLAG 3 only: its own instantiation (register pressure)
         const int y0 = A.d.fr_yldflag[(long)e * 2], y1 = A.d.fr_yldflag[(long)e * 2 + 1];
         if (y0 != 2 || y1 != 2) frame_plastic(k, eft, y0, y1, A.d.fr_plast + (long)e * 3);
     }
@@ -440,6 +440,31 @@ __device__ __forceinline__ void shell_block_stage(const ShellIn &in, int a, int 
         for (int q = 0; q < 3; ++q) stg[((3 + p) * ND + 3 + q) * STR] = s[p * 3 + q];
 }
 
+// mass mode of the tile kernel (cb_mass with bricks): consistent brick mass, lumped shell mass on
+// the diagonal of the joint's own block; returns the DOF count of the contribution's joints
+template <int ND>
+__device__ __noinline__ int mass_block_stage(const CbStiffArgs &A, const CbContrib &ct, double *stg)
+{
+    constexpr int STR = CB_TILE_T + 1;
+    for (int i = 0; i < ND * ND; ++i) stg[i * STR] = 0.0;
+    if (ct.type == CB_T_BRICK) {
+        double blk[9];
+        brick_mass_block(A, ct.e, ct.a, ct.b, blk, 3);
+        for (int p = 0; p < 3; ++p) stg[(p * ND + p) * STR] = blk[p * 3 + p];
+        return 3;
+    }
+    if (ct.type == CB_T_SHELL && ND >= 6) {
+        if (ct.a == ct.b) {             // lumped: rho A t / 3, rotations * t^2 / 12 (shell.c:1548-1558)
+            const double th = SOA(A.d.sh_const, 2, ct.e, A.d.NE_SH);
+            const double Mtot = A.sh_dens[ct.e] * SOA(A.d.sh_const, 4, ct.e, A.d.NE_SH) * th;
+            for (int p = 0; p < 6; ++p)
+                stg[(p * ND + p) * STR] = (p < 3) ? Mtot / 3 : Mtot / 3 * (th * th) / 12;
+        }
+        return 6;
+    }
+    return (ct.type == CB_T_FRAME) ? 7 : 3;
+}
+
 // SHELL_ONLY: the model holds nothing but DKT shells - the other element branches are compiled
 // out so that they cannot cost the hot configuration registers
 template <int ND, bool SHELL_ONLY>
@@ -475,26 +500,7 @@ k_assemble_tiles(CbStiffArgs A)
             double *stg = stage + ct.pad;
             const int col = ct.pad;             // column of `stage` / entry of ndof: reference order
             if (A.mass_mode) {
-#pragma unroll
-                for (int i = 0; i < NN; ++i) stg[i * STR] = 0.0;
-                if (ct.type == CB_T_BRICK) {
-                    double blk[9];
-                    brick_mass_block(A, ct.e, ct.a, ct.b, blk, 3);
-#pragma unroll
-                    for (int p = 0; p < 3; ++p) stg[(p * ND + p) * STR] = blk[p * 3 + p];
-                    ndof[col] = 3;
-                } else if (ct.type == CB_T_SHELL && ND >= 6) {
-                    if (ct.a == ct.b) {         // lumped: rho A t / 3, rotations * t^2 / 12
-                        const double th = SOA(A.d.sh_const, 2, ct.e, A.d.NE_SH);
-                        const double Mtot = A.sh_dens[ct.e] * SOA(A.d.sh_const, 4, ct.e, A.d.NE_SH) * th;
-#pragma unroll
-                        for (int p = 0; p < 6; ++p)
-                            stg[(p * ND + p) * STR] = (p < 3) ? Mtot / 3 : Mtot / 3 * (th * th) / 12;
-                    }
-                    ndof[col] = 6;
-                } else {
-                    ndof[col] = (ct.type == CB_T_FRAME) ? 7 : 3;
-                }
+                ndof[col] = (unsigned char)mass_block_stage<ND>(A, ct, stg);
             } else if (ct.type == CB_T_SHELL) {
                 if constexpr (ND >= 6) {
                     if (ND > 6) {
@@ -515,10 +521,16 @@ k_assemble_tiles(CbStiffArgs A)
                         frame_block(A, ct.e, ct.a, ct.b, blk, 7);
 #pragma unroll
                         for (int i = 0; i < 49; ++i) stg[i * STR] = blk[i];
+                    } else if (A.d.ANAFLAG == 3) {
+                        if (ct.a == 0) {
+                            if (ct.b == 0) frame_block_t<0, 0, true>(A, ct.e, stg, STR); else frame_block_t<0, 1, true>(A, ct.e, stg, STR);
+                        } else {
+                            if (ct.b == 0) frame_block_t<1, 0, true>(A, ct.e, stg, STR); else frame_block_t<1, 1, true>(A, ct.e, stg, STR);
+                        }
                     } else if (ct.a == 0) {
-                        if (ct.b == 0) frame_block_t<0, 0>(A, ct.e, stg, STR); else frame_block_t<0, 1>(A, ct.e, stg, STR);
+                        if (ct.b == 0) frame_block_t<0, 0, false>(A, ct.e, stg, STR); else frame_block_t<0, 1, false>(A, ct.e, stg, STR);
                     } else {
-                        if (ct.b == 0) frame_block_t<1, 0>(A, ct.e, stg, STR); else frame_block_t<1, 1>(A, ct.e, stg, STR);
+                        if (ct.b == 0) frame_block_t<1, 0, false>(A, ct.e, stg, STR); else frame_block_t<1, 1, false>(A, ct.e, stg, STR);
                     }
                 }
                 ndof[col] = 7;

@@ -46,6 +46,9 @@ int cb_newton_static(cb_handle *h, long neq, const long *maxa, long lss, const d
  * alpham / alphaf: generalized-alpha parameters (main.c:3337-3351).  hist receives one row per time
  * step: time, iterations, d[0..NEQ) - what the reference hands to output().                      */
 void cb_sky_mult(long neq, const long *maxa, const double *ss, double *v);   /* solve.c:700-756 */
+/* matpart() (solve.c:758-824): ii / ij = equations without / with prescribed motion (0-based)  */
+void cb_sky_partition(long neq, long nbc, const long *maxa, double *ss, double *qtot, const double *uc,
+                      const long *ii, const long *ij);
 int cb_newmark_nonlinear(cb_handle *h, long neq, const long *maxa, long lss, const double *pinpt,
                          long ntstps, double dt, double alpham, double alphaf,
                          const cb_nr_params *p, double *hist, cb_nr_result *res);

@@ -89,8 +89,8 @@ static void newmark_constants(double alpham, double alphaf, double dt_temp, doub
 /* matpart(), solve.c:758-824: rows / columns of the moved supports are taken out of the skyline
  * matrix (unit diagonal), their known displacements uc go to the right-hand side.  ii / ij = the
  * equations without / with support motion (main.c:1341-1353).  Statement order as the reference. */
-static void matpart(long neq, long nbc, const long *maxa, double *ss, double *qtot, const double *uc,
-                    const long *ii, const long *ij)
+void cb_sky_partition(long neq, long nbc, const long *maxa, double *ss, double *qtot, const double *uc,
+                      const long *ii, const long *ij)
 {
     long n = ij[nbc - 1] + 1;
     for (long i = 1; i <= nbc; ++i) {
@@ -226,7 +226,7 @@ int cb_newmark_nonlinear_bc(cb_handle *h, long neq, const long *maxa, long lss, 
                             else dd[i] = r[i] + sm[i] * ((1 - alpham) * (vc_i[i] * a[2] + ac_i[i] * a[3]) - alpham * ac_i[i]) / (1 - alphaf);
                         }
                         if (nbc) {
-                            matpart(neq, nbc, maxa, Keff, dd, uc_i, ii, ij);
+                            cb_sky_partition(neq, nbc, maxa, Keff, dd, uc_i, ii, ij);
                             if (cb_sky_factor(neq, maxa, Keff, NULL, NULL, 0)) FAIL(2);
                         }
                         cb_sky_solve(neq, maxa, Keff, dd);

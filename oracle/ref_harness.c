@@ -35,6 +35,7 @@ void ref_set_flags(int anaflag, int algflag, int slvflag, int optflag)
 long ref_get_NEQ(void)  { return NEQ; }
 long ref_get_NBC(void)  { return NBC; }
 void ref_set_NEQ(long n) { NEQ = n; }
+void ref_set_NBC(long n) { NBC = n; }   /* skylin() counts it from the deck (model.c:1149-1201) */
 
 /* The reference writes its echo / error text to OFP[0..7] (results1..8.txt, main.c:373-379). */
 int ref_open_sinks(void)

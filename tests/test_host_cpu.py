@@ -116,3 +116,46 @@ def test_host_skyline_solver_matches_reference(ref):
         x_ref, _, _ = ref.skyline_solve(m, ss.copy(), rhs)
         x = cb.sky_factor_solve(m.maxa, ss.copy(), rhs)
         assert np.array_equal(x, x_ref)
+
+
+def test_host_skyline_indefinite_mult_partition_match_reference(ref):
+    """the other skyline services of solve.c the host drivers use, bit for bit against the
+    reference's own routines: the indefinite factorisation of the arc-length driver (pivots ssd and
+    sign of the determinant, skyfact with ALGFLAG 3, solve.c:563-572), skymult (solve.c:700-756,
+    generalized-alpha Newmark) and matpart (solve.c:758-824, prescribed support motion)"""
+    import ctypes as C
+    import cubens_b200 as cb
+    from cubens_b200 import meshgen
+    hl = cb.load_host_library()
+    P = ref.P
+    m = meshgen.plate_model(6, 5, z_bump=0.05)
+    s = ref.RefState(m)
+    ss0 = ref.stiff(m, s, SLVFLAG=0, gen="c")
+    n = m.NEQ
+    maxa = np.ascontiguousarray(m.maxa, dtype=np.int64)
+    rng = np.random.default_rng(3)
+    # an indefinite matrix: shift the diagonal so that some pivots turn negative
+    ss = ss0.copy()
+    ss[maxa[:-1] - 1] -= 0.3 * np.abs(ss0[maxa[:-1] - 1]).mean()
+    l = ref.set_model(m, SLVFLAG=0)
+    l.ref_set_flags(C.c_int(2), C.c_int(3), C.c_int(0), C.c_int(1))          # ALGFLAG 3
+    a = ss.copy(); ssd_ref = np.zeros(n); dd = np.zeros(n); det_ref = C.c_int(0)
+    assert l.skyfact(P(maxa), P(a), P(ssd_ref), P(dd), C.c_int(0), C.byref(det_ref)) == 0
+    b = ss.copy(); ssd = np.zeros(n); det = C.c_int(0)
+    assert hl.cb_sky_factor(C.c_long(n), P(maxa), P(b), P(ssd), C.byref(det), C.c_int(1)) == 0
+    assert np.array_equal(a, b) and np.array_equal(ssd, ssd_ref) and det.value == det_ref.value == 1
+    # skymult
+    l.ref_set_flags(C.c_int(2), C.c_int(1), C.c_int(0), C.c_int(1))
+    v = rng.normal(size=n); v_ref = v.copy()
+    l.skymult(P(maxa), P(ss0), P(v_ref))
+    hl.cb_sky_mult(C.c_long(n), P(maxa), P(ss0), P(v))
+    assert np.array_equal(v, v_ref)
+    # matpart: three prescribed equations
+    pm = np.zeros(n, dtype=bool); pm[[4, 17, n - 2]] = True
+    ij32 = np.flatnonzero(pm).astype(np.int32); ii32 = np.flatnonzero(~pm).astype(np.int32)
+    l.ref_set_NBC(C.c_long(3))
+    K_ref = ss0.copy(); q_ref = rng.normal(size=n); uc = rng.normal(size=n); q = q_ref.copy(); K = ss0.copy()
+    l.matpart(P(maxa), P(m.kht), P(K_ref), P(q_ref), P(uc), P(ii32), P(ij32))
+    ii64, ij64 = ii32.astype(np.int64), ij32.astype(np.int64)      # keep alive across the call
+    hl.cb_sky_partition(C.c_long(n), C.c_long(3), P(maxa), P(K), P(q), P(uc), P(ii64), P(ij64))
+    assert np.array_equal(K, K_ref) and np.array_equal(q, q_ref)

@@ -1353,6 +1353,84 @@ extern "C" int cb_get_mass_csc_values(cb_handle *h, double *Mx)
 extern "C" double *cb_dev_Mx(cb_handle *h) { return h ? h->Mx.p : nullptr; }
 
 // ------------------------------------------------------------------------------------------
+// checkpoint / restart of the device-resident committed state.  The reference
+// writes its state as "%e" text (misc.c:494-603: 7 digits, a restarted run drifts); here the
+// committed generation - everything cb_begin_increment starts an increment from, including the
+// reference lengths / areas that mass_* rewrite and the yield flags / plastic state - goes to a
+// binary side file bit for bit.  The host keeps writing its own results8.txt from cb_download.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct CkItem { void *p; size_t bytes; };
+std::vector<CkItem> ck_items(cb_handle *h)
+{
+    std::vector<CkItem> v;
+    auto add = [&](auto &b) { if (b.p && b.n) v.push_back({(void *)b.p, b.n * sizeof(*b.p)}); };
+    add(h->x); add(h->d); add(h->f); add(h->sm);
+    add(h->sh_frame[0]); add(h->sh_dsl[0]); add(h->sh_ef[0]); add(h->sh_const);
+    add(h->tr_frame[0]); add(h->tr_ef[0]); add(h->tr_const);
+    add(h->fr_frame[0]); add(h->fr_xfr[0]); add(h->fr_efFE[0]); add(h->fr_ef[0]); add(h->fr_const);
+    add(h->fr_yldflag); add(h->sh_pl[0]);
+    return v;
+}
+struct CkHeader { char magic[8]; long sizes[7]; int anaflag, cls_on; long nitems, total; };
+}
+
+extern "C" int cb_checkpoint_save(cb_handle *h, const char *path)
+{
+    if (!h || !path) return fail(CB_ERR_ARG, "null argument");
+    cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    std::vector<CkItem> items = ck_items(h);
+    CkHeader hd{};
+    memcpy(hd.magic, "CBCKPT1", 8);
+    const long sz[7] = {h->sz.NJ, h->sz.NE_TR, h->sz.NE_FR, h->sz.NE_SH, h->sz.NE_SBR, h->sz.NE_FBR, h->sz.NEQ};
+    memcpy(hd.sizes, sz, sizeof sz);
+    hd.anaflag = h->fl.ANAFLAG; hd.cls_on = h->cls_on ? 1 : 0; hd.nitems = (long)items.size();
+    for (auto &it : items) hd.total += (long)it.bytes;
+    FILE *fp = fopen(path, "wb");
+    if (!fp) return fail(CB_ERR_ARG, "cannot open %s for writing", path);
+    bool ok = fwrite(&hd, sizeof hd, 1, fp) == 1;
+    std::vector<char> buf;
+    for (auto &it : items) {
+        buf.resize(it.bytes);
+        if (cudaMemcpy(buf.data(), it.p, it.bytes, cudaMemcpyDeviceToHost) != cudaSuccess) { fclose(fp); return fail(CB_ERR_CUDA, "checkpoint copy"); }
+        long nb = (long)it.bytes;
+        ok = ok && fwrite(&nb, sizeof nb, 1, fp) == 1 && fwrite(buf.data(), 1, it.bytes, fp) == it.bytes;
+    }
+    ok = (fclose(fp) == 0) && ok;
+    return ok ? CB_OK : fail(CB_ERR_ARG, "short write to %s", path);
+}
+
+extern "C" int cb_checkpoint_load(cb_handle *h, const char *path)
+{
+    if (!h || !path) return fail(CB_ERR_ARG, "null argument");
+    cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return fail(CB_ERR_ARG, "cannot open %s", path);
+    CkHeader hd{};
+    std::vector<CkItem> items = ck_items(h);
+    const long sz[7] = {h->sz.NJ, h->sz.NE_TR, h->sz.NE_FR, h->sz.NE_SH, h->sz.NE_SBR, h->sz.NE_FBR, h->sz.NEQ};
+    if (fread(&hd, sizeof hd, 1, fp) != 1 || memcmp(hd.magic, "CBCKPT1", 8) != 0 ||
+        memcmp(hd.sizes, sz, sizeof sz) != 0 || hd.anaflag != h->fl.ANAFLAG || hd.nitems != (long)items.size()) {
+        fclose(fp);
+        return fail(CB_ERR_ARG, "%s is not a checkpoint of this model", path);
+    }
+    std::vector<char> buf;
+    for (auto &it : items) {
+        long nb = 0;
+        if (fread(&nb, sizeof nb, 1, fp) != 1 || nb != (long)it.bytes) { fclose(fp); return fail(CB_ERR_ARG, "checkpoint layout mismatch"); }
+        buf.resize(it.bytes);
+        if (fread(buf.data(), 1, it.bytes, fp) != it.bytes) { fclose(fp); return fail(CB_ERR_ARG, "short read from %s", path); }
+        if (cudaMemcpy(it.p, buf.data(), it.bytes, cudaMemcpyHostToDevice) != cudaSuccess) { fclose(fp); return fail(CB_ERR_CUDA, "checkpoint copy"); }
+    }
+    fclose(fp);
+    h->keb_dirty = true; h->krec_fresh = false;      // the reference geometry may have been rewritten
+    if (!hd.cls_on) h->cls_on = false;
+    return cb_begin_increment(h);                    // *_temp / *_i / *_ip <- committed
+}
+
+// ------------------------------------------------------------------------------------------
 // results
 // ------------------------------------------------------------------------------------------
 extern "C" int cb_get_skyline(cb_handle *h, double *ss, long n)

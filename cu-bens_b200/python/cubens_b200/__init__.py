@@ -36,7 +36,7 @@ EXPORTS = [
     "cb_last_stiff_ms", "cb_last_forces_ms", "cb_last_assemble_ms", "cb_timer_start", "cb_timer_stop_ms", "cb_set_dd", "cb_host_alloc",
     "cb_host_free", "cb_map_bytes", "cb_sync", "cb_stream", "cb_set_q", "cb_residual_sums",
     "cb_dev_sums", "cb_get_sums", "cb_get_yldflag", "cb_set_yldflag", "cb_get_mass_csc_values", "cb_dev_Mx",
-    "cb_geometry_classes", "cb_keep_ip",
+    "cb_geometry_classes", "cb_keep_ip", "cb_checkpoint_save", "cb_checkpoint_load",
 ]
 
 
@@ -192,6 +192,12 @@ class Assembler:
 
     def end_iteration(self):
         self._check(self.lib.cb_end_iteration(self.h))
+
+    def checkpoint_save(self, path):
+        self._check(self.lib.cb_checkpoint_save(self.h, str(path).encode()))
+
+    def checkpoint_load(self, path):
+        self._check(self.lib.cb_checkpoint_load(self.h, str(path).encode()))
 
     def yldflag(self):
         y = np.zeros(2 * self.m.NE_FR, dtype=np.int32)

@@ -211,6 +211,14 @@ enum {
 int  cb_download(cb_handle *h, int which, double *dst, long n);
 int  cb_upload(cb_handle *h, int which, const double *src, long n);
 
+/* Binary checkpoint of the committed device state (bit for bit, unlike the reference's "%e" text
+ * results8.txt, misc.c:494-716): everything an increment / time step starts from, including the
+ * reference geometry mass_* rewrites, yldflag and the shell plastic state.  cb_checkpoint_load
+ * restores it into a handle created from the same model and ends with cb_begin_increment.  The
+ * host's own vectors (uc, vc, ac, load factor, step number) stay the host's to save.            */
+int  cb_checkpoint_save(cb_handle *h, const char *path);
+int  cb_checkpoint_load(cb_handle *h, const char *path);
+
 /* ---- instrumentation ------------------------------------------------------------------- */
 /* kernels launched by this handle since creation (bench.py's gpu_launches)                 */
 long cb_launch_count(cb_handle *h);

@@ -262,3 +262,27 @@ def test_shell_plastic_newton(gpu, ref):
     assert relerr(d, d_ref) < 1e-9
     assert (asm.download("CHI") > 0).sum() >= 5            # really went plastic
     asm.close()
+
+
+def test_frame_plastic_with_offsets_and_releases(gpu, ref):
+    """inelastic frames whose members also carry rigid end offsets and bending releases: the generic
+    (runtime-indexed) stiffness / force paths with the plastic reduction, reference and device in
+    lockstep (stiffm_fr before release(), frame.c:268-282)"""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as G
+    m = G.build("lattice_3_offsets_releases")
+    m.ANAFLAG = 3
+    base = np.random.default_rng(4).uniform(-1.0, 1.0, size=m.NEQ)
+    asm = cb.Assembler(m, layout=cb.CB_MAT_BOTH)
+    codes, s = lockstep(m, ref, asm, base, [0.004] * 3 + [-0.0003] * 2 + [0.003] * 2)
+    assert 1 in codes and 0 in codes and (s.yldflag == 1).any()
+    # CSC of the final state against the dense scatter
+    K_ref = ref.stiff(m, s, SLVFLAG=2).reshape(m.NEQ, m.NEQ)
+    asm.stiff()
+    Ap, Ai, Ax = asm.csc()
+    K = np.zeros((m.NEQ, m.NEQ))
+    for c in range(m.NEQ):
+        K[Ai[Ap[c]:Ap[c + 1]], c] = Ax[Ap[c]:Ap[c + 1]]
+    assert relerr(K, K_ref.T) < TOL
+    asm.close()

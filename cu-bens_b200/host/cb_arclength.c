@@ -74,23 +74,27 @@ static int quad(long neq, double a, double b, double c, double *dt, const double
 
 /* solve() for ALGFLAG 3 / SLVFLAG 0 (solve.c:71-82): dd <- r; skyfact (fact == 0) + skysolve.
  * skyfact resets *det on every call, also when it does not factorise (solve.c:545). */
-static int sky_solve3(long neq, const long *maxa, double *ss, double *ssd, const double *r, double *out,
+static int sky_solve3(cb_lin *L, long neq, double *ss, double *ssd, const double *r, double *out,
                       int fact, int *det)
 {
     for (long i = 0; i < neq; ++i) out[i] = r[i];
     *det = 0;
-    if (fact == 0 && cb_sky_factor(neq, maxa, ss, ssd, det, 1)) return 1;
-    cb_sky_solve(neq, maxa, ss, out);
+    if (fact == 0 && cb_lin_factor(L, ss, ssd, det, 1)) return 1;
+    cb_lin_solve(L, ss, out);
     return 0;
 }
 
 int cb_arclength_static(cb_handle *h, long neq, const long *maxa, long lss, const double *q,
                         const cb_arc_params *p, double *hist, int max_rows, cb_nr_result *res)
 {
-    if (!h || !maxa || !q || !p || !hist || !res) return CB_ERR_ARG;
+    if (!h || !q || !p || !hist || !res) return CB_ERR_ARG;
     memset(res, 0, sizeof *res);
+    cb_lin *L = NULL;                                       /* skyline, or CSC when maxa == NULL */
+    if (cb_lin_create(h, neq, maxa, lss, &L) != CB_OK) return CB_ERR_ARG;
+    lss = cb_lin_nval(L);
+    const int scalar = cb_lin_is_scalar(L);
     double *buf = (double *)calloc((size_t)neq * 17 + (size_t)lss, sizeof(double));
-    if (!buf) return CB_ERR_ARG;
+    if (!buf) { cb_lin_destroy(L); return CB_ERR_ARG; }
     double *d = buf, *dp = d + neq, *dpp = dp + neq, *f = dpp + neq, *fp = f + neq, *dd = fp + neq,
            *ddq = dd + neq, *ddr = ddq + neq, *ssd_o = ddr + neq, *ssd = ssd_o + neq, *qtot = ssd + neq,
            *r = qtot + neq, *f_ip = r + neq, *d_temp = f_ip + neq, *f_temp = d_temp + neq,
@@ -107,10 +111,10 @@ int cb_arclength_static(cb_handle *h, long neq, const long *maxa, long lss, cons
     /* ---- first increment: prescribed displacement dk at DOF k (main.c:2297-2560) ------------- */
     if ((rc = cb_begin_increment(h)) != CB_OK) FAIL(100 + rc);
     if ((rc = cb_stiff(h, CB_GEN_COMMITTED)) != CB_OK) FAIL(100 + rc);
-    if ((rc = cb_get_skyline(h, ss, lss)) != CB_OK) FAIL(100 + rc);
+    if ((rc = cb_lin_fetch(L, h, ss)) != CB_OK) FAIL(100 + rc);
     ++res->stiff_calls;
-    if (lss == 1) { ddq[0] = q[0] / ss[0]; ssd[0] = ss[0]; }
-    else if (sky_solve3(neq, maxa, ss, ssd, q, ddq, 0, &det)) FAIL(2);
+    if (scalar) { ddq[0] = q[0] / ss[0]; ssd[0] = ss[0]; }
+    else if (sky_solve3(L, neq, ss, ssd, q, ddq, 0, &det)) FAIL(2);
     lpf = p->dk / ddq[k];
     for (long i = 0; i < neq; ++i) {
         d[i] = dd[i] = lpf * ddq[i];
@@ -125,8 +129,8 @@ int cb_arclength_static(cb_handle *h, long neq, const long *maxa, long lss, cons
     frcchk_fr = frcchk_sh = 0;
     do {
         for (long i = 0; i < neq; ++i) { qtot[i] = q[i] * lpf; r[i] = qtot[i] - f[i]; }
-        if (lss == 1) { ddr[0] = r[0] / ss[0]; ssd[0] = ss[0]; }
-        else if (sky_solve3(neq, maxa, ss, ssd, r, ddr, 1, &det)) FAIL(2);
+        if (scalar) { ddr[0] = r[0] / ss[0]; ssd[0] = ss[0]; }
+        else if (sky_solve3(L, neq, ss, ssd, r, ddr, 1, &det)) FAIL(2);
         dlpf = -ddr[k] / ddq[k];
         lpf += dlpf;
         for (long i = 0; i < neq; ++i) { dd[i] = ddr[i] + dlpf * ddq[i]; d[i] += dd[i]; f_ip[i] = f[i]; }
@@ -164,10 +168,10 @@ int cb_arclength_static(cb_handle *h, long neq, const long *maxa, long lss, cons
             errchk2 = 0;
         }
         if ((rc = cb_stiff(h, CB_GEN_COMMITTED)) != CB_OK) FAIL(100 + rc);
-        if ((rc = cb_get_skyline(h, ss, lss)) != CB_OK) FAIL(100 + rc);
+        if ((rc = cb_lin_fetch(L, h, ss)) != CB_OK) FAIL(100 + rc);
         ++res->stiff_calls;
-        if (lss == 1) { ddq[0] = q[0] / ss[0]; ssd[0] = ss[0]; det = (ss[0] > 0) ? 0 : 1; }
-        else if (sky_solve3(neq, maxa, ss, ssd, q, ddq, 0, &det)) FAIL(2);
+        if (scalar) { ddq[0] = q[0] / ss[0]; ssd[0] = ss[0]; det = (ss[0] > 0) ? 0 : 1; }
+        else if (sky_solve3(L, neq, ss, ssd, q, ddq, 0, &det)) FAIL(2);
         if (psi >= p->psi_thresh) a = dotv(q, q, neq) + dotv(ddq, ddq, neq);
         else a = dotv(ddq, ddq, neq);
         if (det == 0) dlpf = arc * sqrt(1 / a);
@@ -193,8 +197,8 @@ int cb_arclength_static(cb_handle *h, long neq, const long *maxa, long lss, cons
                 r[i] = qtot[i] - f_temp[i];
                 f_ip[i] = f_temp[i];
             }
-            if (lss == 1) ddr[0] = r[0] / ss[0];
-            else if (sky_solve3(neq, maxa, ss, ssd, r, ddr, 1, &det)) FAIL(2);
+            if (scalar) ddr[0] = r[0] / ss[0];
+            else if (sky_solve3(L, neq, ss, ssd, r, ddr, 1, &det)) FAIL(2);
             if (psi >= p->psi_thresh) {
                 b = 2 * (dotv(d_temp, ddq, neq) - dotv(dp, ddq, neq) + dotv(ddr, ddq, neq) +
                          (lpf_temp - lpfp) * dotv(q, q, neq));
@@ -271,6 +275,7 @@ int cb_arclength_static(cb_handle *h, long neq, const long *maxa, long lss, cons
 done:
     res->status = status; res->increments = nrow; res->lpf = (nrow > 0) ? hist[(long)(nrow - 1) * (neq + 2)] : 0;
     free(buf);
+    cb_lin_destroy(L);
     return status == 0 ? CB_OK : CB_ERR_ARG;
 #undef FAIL
 #undef ROW

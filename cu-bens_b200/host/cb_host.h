@@ -18,6 +18,40 @@ int  cb_sky_factor(long neq, const long *maxa, double *ss, double *ssd, int *det
                    int allow_indefinite);
 void cb_sky_solve(long neq, const long *maxa, const double *ss, double *rhs);
 
+/* ---- the CSC hand-off to the solver (cb_sparse.c) = solve.c:107-135, 199-243 without the dense
+ * NEQ^2 scan: Ap / Ai once from cb_csc_pattern, Ax from cb_get_csc_values at every refactorisation.
+ * Back ends: UMFPACK (the reference's calls, -DCB_HAVE_UMFPACK) or the built-in sparse LDL^T
+ * (natural ordering, no pivoting - the sparse twin of skyfact / skysolve, solve.c:539-698, so the
+ * pivots and determinant sign of the arc-length branch, solve.c:563-572, are available).        */
+typedef struct cb_csc_solver cb_csc_solver;
+int  cb_csc_solver_create(long n, const int *Ap, const int *Ai, cb_csc_solver **out);
+int  cb_csc_solver_factor(cb_csc_solver *s, const double *Ax, int allow_indefinite, int *det_neg,
+                          double *pivots);                       /* 0 / 1 like skyfact            */
+int  cb_csc_solver_solve(cb_csc_solver *s, double *rhs);
+long cb_csc_solver_lnz(const cb_csc_solver *s);
+void cb_csc_solver_destroy(cb_csc_solver *s);
+void cb_csc_mult(long n, const int *Ap, const int *Ai, const double *Ax, double *v, double *tmp);
+void cb_csc_diag(long n, const int *Ap, const int *Ai, long *diag);
+void cb_csc_partition(long n, const int *Ap, const int *Ai, double *Ax, double *qtot, const double *uc,
+                      const int *pmot);
+
+/* what the drivers below factorise: the skyline of SLVFLAG 0 (maxa != NULL) or the device-built CSC
+ * of SLVFLAG 2 (maxa == NULL; the handle must own a CSC layout).  Every driver takes (maxa, lss):
+ * pass maxa = NULL, lss = 0 to run it on the CSC hand-off.                                        */
+typedef struct cb_lin cb_lin;
+int    cb_lin_create(cb_handle *h, long neq, const long *maxa, long lss, cb_lin **out);
+void   cb_lin_destroy(cb_lin *L);
+long   cb_lin_nval(const cb_lin *L);
+int    cb_lin_is_scalar(const cb_lin *L);
+int    cb_lin_fetch(cb_lin *L, cb_handle *h, double *K);
+void   cb_lin_add_diag(const cb_lin *L, double *K, double num, double den, const double *m);
+double cb_lin_diag0(const cb_lin *L, const double *K);
+int    cb_lin_factor(cb_lin *L, double *K, double *pivots, int *det_neg, int allow_indefinite);
+void   cb_lin_solve(cb_lin *L, const double *K, double *rhs);
+void   cb_lin_mult(cb_lin *L, const double *K, double *v);
+void   cb_lin_partition(cb_lin *L, double *K, double *qtot, const double *uc, const int *pmot, long nbc,
+                        const long *ii, const long *ij);
+
 /* the solver controls main.c reads after the loads (main.c:1809-1812) */
 typedef struct cb_nr_params {
     double lpfmax, lpf, dlpf, dlpfmax, dlpfmin;

@@ -140,8 +140,11 @@ int cb_newmark_nonlinear_bc(cb_handle *h, long neq, const long *maxa, long lss, 
                             const double *pdisp, const int *pmot, long ntstps, double dt, double alpham,
                             double alphaf, const cb_nr_params *p, double *hist, cb_nr_result *res)
 {
-    if (!h || !maxa || !pinpt || !p || !hist || !res) return CB_ERR_ARG;
+    if (!h || !pinpt || !p || !hist || !res) return CB_ERR_ARG;
     memset(res, 0, sizeof *res);
+    cb_lin *L = NULL;                                       /* skyline, or CSC when maxa == NULL */
+    if (cb_lin_create(h, neq, maxa, lss, &L) != CB_OK) return CB_ERR_ARG;
+    lss = cb_lin_nval(L);
     long nbc = 0, *ii = NULL, *ij = NULL;
     if (pmot && pdisp) {
         for (long i = 0; i < neq; ++i) nbc += pmot[i] != 0;
@@ -153,7 +156,7 @@ int cb_newmark_nonlinear_bc(cb_handle *h, long neq, const long *maxa, long lss, 
         }
     }
     double *buf = (double *)calloc((size_t)neq * 20 + 2 * (size_t)lss, sizeof(double));
-    if (!buf) return CB_ERR_ARG;
+    if (!buf) { cb_lin_destroy(L); free(ii); free(ij); return CB_ERR_ARG; }
     double *qtot = buf, *d = qtot + neq, *d_temp = d + neq, *f = d_temp + neq, *f_temp = f + neq,
            *fp = f_temp + neq, *f_ip = fp + neq, *r = f_ip + neq, *dd = r + neq, *sm = dd + neq,
            *uc = sm + neq, *vc = uc + neq, *ac = vc + neq, *uc_i = ac + neq, *vc_i = uc_i + neq,
@@ -207,29 +210,29 @@ int cb_newmark_nonlinear_bc(cb_handle *h, long neq, const long *maxa, long lss, 
                     }
                     /* ss = sm = 0; stiff_xx then mass_xx per element type (main.c:3590-3619) */
                     if ((rc = cb_stiff(h, CB_GEN_IP)) != CB_OK) FAIL(100 + rc);
-                    if ((rc = cb_get_skyline(h, ss, lss)) != CB_OK) FAIL(100 + rc);
+                    if ((rc = cb_lin_fetch(L, h, ss)) != CB_OK) FAIL(100 + rc);
                     if ((rc = cb_mass(h)) != CB_OK) FAIL(100 + rc);
                     if ((rc = cb_get_mass(h, sm)) != CB_OK) FAIL(100 + rc);
                     ++res->stiff_calls;
-                    if (lss == 1) {
+                    if (cb_lin_is_scalar(L)) {
                         dd[0] = r[0] / ss[0];
                     } else {                                 /* solve(), solve.c:139-186, 470-536 */
                         if (nbc)                             /* heavy masses at the moved supports */
                             for (long i = 0; i < neq; ++i)
                                 if (pdisp[i * ntstps + k] != 0) sm[i] = 1000000 * sm[i];
                         for (long i = 0; i < lss; ++i) Keff[i] = ss[i];
-                        for (long i = 0; i < neq; ++i) Keff[maxa[i] - 1] += a[0] * (1 - alpham) * sm[i] / (1 - alphaf);
-                        if (!nbc && cb_sky_factor(neq, maxa, Keff, NULL, NULL, 0)) FAIL(2);
+                        cb_lin_add_diag(L, Keff, a[0] * (1 - alpham), 1 - alphaf, sm);
+                        if (!nbc && cb_lin_factor(L, Keff, NULL, NULL, 0)) FAIL(2);
                         for (long i = 0; i < neq; ++i) {
                             if (nbc && pdisp[i * ntstps + k] != 0 && itecnt > 0) dd[i] = 0;
                             else if (nbc && pdisp[i * ntstps + k] != 0 && itecnt == 0) dd[i] = uc_i[i];
                             else dd[i] = r[i] + sm[i] * ((1 - alpham) * (vc_i[i] * a[2] + ac_i[i] * a[3]) - alpham * ac_i[i]) / (1 - alphaf);
                         }
                         if (nbc) {
-                            cb_sky_partition(neq, nbc, maxa, Keff, dd, uc_i, ii, ij);
-                            if (cb_sky_factor(neq, maxa, Keff, NULL, NULL, 0)) FAIL(2);
+                            cb_lin_partition(L, Keff, dd, uc_i, pmot, nbc, ii, ij);
+                            if (cb_lin_factor(L, Keff, NULL, NULL, 0)) FAIL(2);
                         }
-                        cb_sky_solve(neq, maxa, Keff, dd);
+                        cb_lin_solve(L, Keff, dd);
                     }
                     for (long i = 0; i < neq; ++i) {         /* main.c:3642-3656 */
                         if (itecnt > 0) dd[i] = dd[i] * (-1);
@@ -307,6 +310,7 @@ done:
     res->status = status; res->lpf = lpf;
     free(ii); free(ij);
     free(buf);
+    cb_lin_destroy(L);
     return status == 0 ? CB_OK : CB_ERR_ARG;
 #undef FAIL
 }
@@ -315,10 +319,13 @@ int cb_newmark_linear(cb_handle *h, long neq, const long *maxa, long lss, const 
                       long ntstps, double dt, double alpham, double alphaf, const double *um0,
                       const double *vm0, const double *am0, double *hist, cb_nr_result *res)
 {
-    if (!h || !maxa || !pinpt || !hist || !res) return CB_ERR_ARG;
+    if (!h || !pinpt || !hist || !res) return CB_ERR_ARG;
     memset(res, 0, sizeof *res);
+    cb_lin *L = NULL;                                       /* skyline, or CSC when maxa == NULL */
+    if (cb_lin_create(h, neq, maxa, lss, &L) != CB_OK) return CB_ERR_ARG;
+    lss = cb_lin_nval(L);
     double *buf = (double *)calloc((size_t)neq * 10 + 2 * (size_t)lss, sizeof(double));
-    if (!buf) return CB_ERR_ARG;
+    if (!buf) { cb_lin_destroy(L); return CB_ERR_ARG; }
     double *sm = buf, *um = sm + neq, *vm = um + neq, *am = vm + neq, *uc = am + neq, *vc = uc + neq,
            *ac = vc + neq, *Meff = ac + neq, *Reff = Meff + neq, *dd = Reff + neq, *ss = dd + neq,
            *Keff = ss + lss;
@@ -327,7 +334,7 @@ int cb_newmark_linear(cb_handle *h, long neq, const long *maxa, long lss, const 
 #define FAIL(code) do { status = (code); goto done; } while (0)
     /* main.c:3226-3254: one stiffness + mass assembly at the initial configuration */
     if ((rc = cb_stiff(h, CB_GEN_COMMITTED)) != CB_OK) FAIL(100 + rc);
-    if ((rc = cb_get_skyline(h, ss, lss)) != CB_OK) FAIL(100 + rc);
+    if ((rc = cb_lin_fetch(L, h, ss)) != CB_OK) FAIL(100 + rc);
     if ((rc = cb_mass(h)) != CB_OK) FAIL(100 + rc);
     if ((rc = cb_get_mass(h, sm)) != CB_OK) FAIL(100 + rc);
     ++res->stiff_calls;
@@ -336,8 +343,8 @@ int cb_newmark_linear(cb_handle *h, long neq, const long *maxa, long lss, const 
     }
     newmark_constants(alpham, alphaf, dt, a);
     for (long i = 0; i < lss; ++i) Keff[i] = ss[i];          /* solve.c:199-207 */
-    for (long i = 0; i < neq; ++i) Keff[maxa[i] - 1] += a[0] * (1 - alpham) * sm[i] / (1 - alphaf);
-    if (cb_sky_factor(neq, maxa, Keff, NULL, NULL, 0)) FAIL(2);
+    cb_lin_add_diag(L, Keff, a[0] * (1 - alpham), 1 - alphaf, sm);
+    if (cb_lin_factor(L, Keff, NULL, NULL, 0)) FAIL(2);
     for (long k = 0; k < ntstps; ++k) {                      /* solve.c:291-433 */
         for (long i = 0; i < neq; ++i) {
             dd[i] = um[i];
@@ -350,10 +357,10 @@ int cb_newmark_linear(cb_handle *h, long neq, const long *maxa, long lss, const 
                 Reff[i] = pinpt[i * ntstps + k] + alphaf / (1 - alphaf) * pinpt[i * ntstps + k - 1] + Meff[i];
         }
         if (alphaf != 0) {
-            cb_sky_mult(neq, maxa, ss, dd);
+            cb_lin_mult(L, ss, dd);
             for (long i = 0; i < neq; ++i) Reff[i] -= alphaf / (1 - alphaf) * dd[i];
         }
-        cb_sky_solve(neq, maxa, Keff, Reff);
+        cb_lin_solve(L, Keff, Reff);
         for (long i = 0; i < neq; ++i) {
             uc[i] = Reff[i];
             ac[i] = a[0] * (uc[i] - um[i]) - a[2] * vm[i] - a[3] * am[i];
@@ -367,6 +374,7 @@ int cb_newmark_linear(cb_handle *h, long neq, const long *maxa, long lss, const 
 done:
     res->status = status;
     free(buf);
+    cb_lin_destroy(L);
     return status == 0 ? CB_OK : CB_ERR_ARG;
 #undef FAIL
 }

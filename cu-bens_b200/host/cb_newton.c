@@ -42,10 +42,13 @@ int cb_newton_static(cb_handle *h, long neq, const long *maxa, long lss, const d
                      const cb_nr_params *p, double *d_out, cb_nr_result *res, double *hist,
                      int max_hist, long hist_dof)
 {
-    if (!h || !maxa || !q || !p || !d_out || !res) return CB_ERR_ARG;
+    if (!h || !q || !p || !d_out || !res) return CB_ERR_ARG;
     memset(res, 0, sizeof *res);
+    cb_lin *L = NULL;                                       /* skyline, or CSC when maxa == NULL */
+    if (cb_lin_create(h, neq, maxa, lss, &L) != CB_OK) return CB_ERR_ARG;
+    lss = cb_lin_nval(L);
     double *buf = (double *)calloc((size_t)neq * 9 + (size_t)lss, sizeof(double));
-    if (!buf) return CB_ERR_ARG;
+    if (!buf) { cb_lin_destroy(L); return CB_ERR_ARG; }
     double *qtot = buf, *d = qtot + neq, *d_temp = d + neq, *f = d_temp + neq, *f_temp = f + neq,
            *fp = f_temp + neq, *f_ip = fp + neq, *r = f_ip + neq, *dd = r + neq, *ss = dd + neq;
     double lpf = p->lpf, dlpf = p->dlpf, dlpfp, intener1 = 0;
@@ -66,15 +69,15 @@ int cb_newton_static(cb_handle *h, long neq, const long *maxa, long lss, const d
             const int refactor = (p->algflag == 1 || (p->algflag == 2 && itecnt == 0));
             if (refactor) {                                 /* main.c:1897-1922 */
                 if ((rc = cb_stiff(h, CB_GEN_IP)) != CB_OK) FAIL(100 + rc);
-                if ((rc = cb_get_skyline(h, ss, lss)) != CB_OK) FAIL(100 + rc);
+                if ((rc = cb_lin_fetch(L, h, ss)) != CB_OK) FAIL(100 + rc);
                 ++res->stiff_calls;
             }
             for (long i = 0; i < neq; ++i) dd[i] = r[i];    /* solve.c:71-73 */
-            if (lss == 1) {
+            if (cb_lin_is_scalar(L)) {
                 dd[0] = r[0] / ss[0];                       /* main.c:1925-1928 */
             } else {
-                if (refactor && cb_sky_factor(neq, maxa, ss, NULL, NULL, 0)) FAIL(2);
-                cb_sky_solve(neq, maxa, ss, dd);
+                if (refactor && cb_lin_factor(L, ss, NULL, NULL, 0)) FAIL(2);
+                cb_lin_solve(L, ss, dd);
             }
             for (long i = 0; i < neq; ++i) { d_temp[i] += dd[i]; f_ip[i] = f_temp[i]; }
             /* main.c:1949-1984: f_temp <- 0; updatc; forces_*; ef_ip <- ef_i */
@@ -125,6 +128,7 @@ done:
     memcpy(d_out, d, (size_t)neq * sizeof(double));
     res->status = status;
     free(buf);
+    cb_lin_destroy(L);
     return status == 0 ? CB_OK : CB_ERR_ARG;
 #undef FAIL
 }

@@ -353,9 +353,18 @@ def load_host_library():
     return _hostlib
 
 
+def _solver_args(m, csc):
+    """(maxa, lss) of the skyline solver, or (NULL, 0): the drivers then factorise the device-built
+    CSC matrix (cb_csc_pattern / cb_get_csc_values -> sparse LDL^T or UMFPACK, host/cb_sparse.c)"""
+    if csc:
+        return None, C.c_void_p(0), C.c_long(0)
+    maxa = np.ascontiguousarray(m.maxa, dtype=np.int64)
+    return maxa, _p(maxa), C.c_long(m.lss)
+
+
 def newton_static(asm, q, lpfmax=1.0, lpf=0.1, dlpf=0.1, dlpfmax=0.5, dlpfmin=1e-4, itemax=20,
                   submax=5, solmin=10, toldisp=1e-8, tolforc=1e-8, tolener=1e-8, algflag=1,
-                  hist_dof=-1):
+                  hist_dof=-1, csc=False):
     """the C host driver cb_newton_static (main.c:1824-2152 on the device path)"""
     hl = load_host_library()
     m = asm.m
@@ -365,8 +374,8 @@ def newton_static(asm, q, lpfmax=1.0, lpf=0.1, dlpf=0.1, dlpfmax=0.5, dlpfmin=1e
     d = np.zeros(m.NEQ)
     hist = np.zeros(3 * 4096)
     q = np.ascontiguousarray(q, dtype=np.float64)
-    maxa = np.ascontiguousarray(m.maxa, dtype=np.int64)
-    hl.cb_newton_static(asm.h, C.c_long(m.NEQ), _p(maxa), C.c_long(m.lss), _p(q), C.byref(p), _p(d),
+    _keep, maxa_p, lss = _solver_args(m, csc)
+    hl.cb_newton_static(asm.h, C.c_long(m.NEQ), maxa_p, lss, _p(q), C.byref(p), _p(d),
                         C.byref(res), _p(hist), C.c_int(4096), C.c_long(hist_dof))
     n = res.increments
     return d, res, hist[:3 * n].reshape(-1, 3).copy()
@@ -385,7 +394,7 @@ def sky_factor_solve(maxa, ss, rhs):
     return v
 
 
-def newmark(asm, dyn, nonlinear=True):
+def newmark(asm, dyn, nonlinear=True, csc=False):
     """the C host drivers cb_newmark_nonlinear / cb_newmark_linear (main.c:3305-3960 /
     main.c:3143-3303 + solve.c:199-458 on the device path).  dyn = deck.parse_dynamic_tail(...).
     Returns (hist [ntstps][2+NEQ], result)."""
@@ -397,19 +406,19 @@ def newmark(asm, dyn, nonlinear=True):
     hist = np.zeros((nt, m.NEQ + 2))
     res = cb_nr_result()
     pin = np.ascontiguousarray(dyn["pinpt"], dtype=np.float64)
-    maxa = np.ascontiguousarray(m.maxa, dtype=np.int64)
+    _keep, maxa_p, lss = _solver_args(m, csc)
     if nonlinear:
         q = dyn["params"]
         p = cb_nr_params(q["lpfmax"], q["lpf"], q["dlpf"], q["dlpfmax"], q["dlpfmin"], q["itemax"],
                          q["submax"], q["solmin"], q["toldisp"], q["tolforc"], q["tolener"], 1)
         pdisp = np.ascontiguousarray(dyn["pdisp"], dtype=np.float64)
         pmot = np.ascontiguousarray(dyn["pmot"], dtype=np.int32)
-        hl.cb_newmark_nonlinear_bc(asm.h, C.c_long(m.NEQ), _p(maxa), C.c_long(m.lss), _p(pin), _p(pdisp),
+        hl.cb_newmark_nonlinear_bc(asm.h, C.c_long(m.NEQ), maxa_p, lss, _p(pin), _p(pdisp),
                                    _p(pmot), C.c_long(nt), C.c_double(dyn["dt"]), C.c_double(dyn["alpham"]),
                                    C.c_double(dyn["alphaf"]), C.byref(p), _p(hist), C.byref(res))
     else:
         um, vm, am = (np.ascontiguousarray(dyn[k], dtype=np.float64) for k in ("um", "vm", "am"))
-        hl.cb_newmark_linear(asm.h, C.c_long(m.NEQ), _p(maxa), C.c_long(m.lss), _p(pin), C.c_long(nt),
+        hl.cb_newmark_linear(asm.h, C.c_long(m.NEQ), maxa_p, lss, _p(pin), C.c_long(nt),
                              C.c_double(dyn["dt"]), C.c_double(dyn["alpham"]), C.c_double(dyn["alphaf"]),
                              _p(um), _p(vm), _p(am), _p(hist), C.byref(res))
     return hist, res
@@ -423,7 +432,7 @@ class cb_arc_params(C.Structure):
 
 
 def arclength_static(asm, q, dk, dkdof, alpha, psi_thresh, iteopt, lpfmax, dkimax, itemax, submax,
-                     imagmax, negmax, toldisp, tolforc, tolener, max_rows=4096):
+                     imagmax, negmax, toldisp, tolforc, tolener, max_rows=4096, csc=False):
     """the C host driver cb_arclength_static (main.c:2158-3141 on the device path).
     Returns (hist [rows][2+NEQ], result)."""
     hl = load_host_library()
@@ -433,7 +442,7 @@ def arclength_static(asm, q, dk, dkdof, alpha, psi_thresh, iteopt, lpfmax, dkima
     res = cb_nr_result()
     hist = np.zeros((max_rows, m.NEQ + 2))
     q = np.ascontiguousarray(q, dtype=np.float64)
-    maxa = np.ascontiguousarray(m.maxa, dtype=np.int64)
-    hl.cb_arclength_static(asm.h, C.c_long(m.NEQ), _p(maxa), C.c_long(m.lss), _p(q), C.byref(p), _p(hist),
+    _keep, maxa_p, lss = _solver_args(m, csc)
+    hl.cb_arclength_static(asm.h, C.c_long(m.NEQ), maxa_p, lss, _p(q), C.byref(p), _p(hist),
                            C.c_int(max_rows), C.byref(res))
     return hist[:res.increments].copy(), res

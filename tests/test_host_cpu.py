@@ -159,3 +159,86 @@ def test_host_skyline_indefinite_mult_partition_match_reference(ref):
     ii64, ij64 = ii32.astype(np.int64), ij32.astype(np.int64)      # keep alive across the call
     hl.cb_sky_partition(C.c_long(n), C.c_long(3), P(maxa), P(K), P(q), P(uc), P(ii64), P(ij64))
     assert np.array_equal(K, K_ref) and np.array_equal(q, q_ref)
+
+
+def _sky_to_csc(maxa, ss, n):
+    """full (unsymmetric-storage) CSC of a skyline matrix, every in-profile entry kept"""
+    import scipy.sparse as sp
+    rows, cols, vals = [], [], []
+    for j in range(n):
+        h = maxa[j + 1] - maxa[j]
+        for k in range(h):
+            i = j - k
+            rows.append(i); cols.append(j); vals.append(ss[maxa[j] - 1 + k])
+            if i != j:
+                rows.append(j); cols.append(i); vals.append(ss[maxa[j] - 1 + k])
+    A = sp.csc_matrix((vals, (rows, cols)), shape=(n, n))
+    A.sort_indices()
+    return A
+
+
+def test_host_csc_solver_services_match_skyline(ref):
+    """the CSC hand-off (host/cb_sparse.c): sparse LDL^T (definite and the
+    indefinite arc-length branch with pivots / determinant sign), K v and matpart on the full CSC
+    against the skyline services pinned to the reference above, on a real stiffness matrix"""
+    import ctypes as C
+    import cubens_b200 as cb
+    from cubens_b200 import meshgen
+    hl = cb.load_host_library()
+    hl.cb_csc_solver_lnz.restype = C.c_long
+    P = ref.P
+    rng = np.random.default_rng(5)
+    for m in (meshgen.plate_model(6, 5, z_bump=0.05), meshgen.lattice_model(3)):
+        s = ref.RefState(m)
+        ss0 = ref.stiff(m, s, SLVFLAG=0, gen="c")
+        n = m.NEQ
+        maxa = np.ascontiguousarray(m.maxa, dtype=np.int64)
+        A = _sky_to_csc(maxa, ss0, n)
+        Ap, Ai = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+        Ax = np.ascontiguousarray(A.data, dtype=np.float64)
+        S = C.c_void_p()
+        assert hl.cb_csc_solver_create(C.c_long(n), P(Ap), P(Ai), C.byref(S)) == 0
+        # no fill beyond the skyline profile with the natural ordering
+        assert hl.cb_csc_solver_lnz(S) <= int(maxa[-1] - 1) - n
+        # positive definite solve
+        rhs = rng.normal(size=n)
+        x_sky = cb.sky_factor_solve(m.maxa, ss0.copy(), rhs)
+        x = rhs.copy()
+        assert hl.cb_csc_solver_factor(S, P(Ax), C.c_int(0), C.c_void_p(0), C.c_void_p(0)) == 0
+        assert hl.cb_csc_solver_solve(S, P(x)) == 0
+        assert np.abs(A @ x - rhs).max() <= 1e-9 * np.abs(rhs).max()
+        assert np.abs(x - x_sky).max() <= 1e-8 * np.abs(x_sky).max()
+        # indefinite: pivots and determinant sign as skyfact's ALGFLAG 3 branch
+        shift = 0.3 * np.abs(ss0[maxa[:-1] - 1]).mean()
+        ss = ss0.copy(); ss[maxa[:-1] - 1] -= shift
+        dpos = np.array([A.indptr[j] + int(np.searchsorted(A.indices[A.indptr[j]:A.indptr[j + 1]], j))
+                         for j in range(n)])
+        Axs = Ax.copy(); Axs[dpos] -= shift
+        ssd = np.zeros(n); det = C.c_int(0)
+        assert hl.cb_sky_factor(C.c_long(n), P(maxa), P(ss), P(ssd), C.byref(det), C.c_int(1)) == 0
+        piv = np.zeros(n); det2 = C.c_int(0)
+        assert hl.cb_csc_solver_factor(S, P(Axs), C.c_int(1), C.byref(det2), P(piv)) == 0
+        assert det.value == det2.value == 1
+        assert np.array_equal(np.sign(piv), np.sign(ssd))
+        assert np.abs(piv - ssd).max() <= 1e-7 * np.abs(ssd).max()
+        # the definite factorisation rejects it, like skyfact
+        assert hl.cb_csc_solver_factor(S, P(Axs), C.c_int(0), C.c_void_p(0), C.c_void_p(0)) == 1
+        # K v
+        v = rng.normal(size=n); v_sky = v.copy(); tmp = np.zeros(n)
+        hl.cb_sky_mult(C.c_long(n), P(maxa), P(ss0), P(v_sky))
+        hl.cb_csc_mult(C.c_long(n), P(Ap), P(Ai), P(Ax), P(v), P(tmp))
+        assert np.abs(v - v_sky).max() <= 1e-13 * np.abs(v_sky).max()
+        # diagonal addresses
+        diag = np.zeros(n, dtype=np.int64)
+        hl.cb_csc_diag(C.c_long(n), P(Ap), P(Ai), P(diag))
+        assert np.array_equal(Ax[diag], ss0[maxa[:-1] - 1])
+        # matpart
+        pm = np.zeros(n, dtype=np.int32); pm[[4, 17, n - 2]] = 1
+        ij = np.flatnonzero(pm).astype(np.int64); ii = np.flatnonzero(pm == 0).astype(np.int64)
+        K = ss0.copy(); q = rng.normal(size=n); uc = rng.normal(size=n); q2 = q.copy(); Ax2 = Ax.copy()
+        hl.cb_sky_partition(C.c_long(n), C.c_long(3), P(maxa), P(K), P(q), P(uc), P(ii), P(ij))
+        hl.cb_csc_partition(C.c_long(n), P(Ap), P(Ai), P(Ax2), P(q2), P(uc), P(pm))
+        B = _sky_to_csc(maxa, K, n)
+        assert np.array_equal(B.indices, A.indices) and np.array_equal(B.data, Ax2)
+        assert np.abs(q2 - q).max() <= 1e-13 * np.abs(q).max()
+        hl.cb_csc_solver_destroy(S)

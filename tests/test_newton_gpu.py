@@ -13,9 +13,13 @@ pytestmark = pytest.mark.gpu
 TOL_CONV = 1e-9
 
 
-def _compare(m, ref, **kw):
-    asm = cb.Assembler(m, layout=cb.CB_MAT_SKYLINE)
-    d, res, hist = cb.newton_static(asm, m.q, **kw)
+SOLVERS = ("skyline", "csc")      # csc: device-built CSC -> host sparse LDL^T
+
+
+def _compare(m, ref, solver="skyline", **kw):
+    csc = solver == "csc"
+    asm = cb.Assembler(m, layout=cb.CB_MAT_CSC if csc else cb.CB_MAT_SKYLINE)
+    d, res, hist = cb.newton_static(asm, m.q, csc=csc, **kw)
     d_ref, stat, hist_ref = ref_newton(m, ref, m.q, **kw)
     assert res.status == 0 and stat["status"] == 0
     assert res.increments == stat["increments"] and res.iterations == stat["iterations"]
@@ -35,23 +39,27 @@ SHELL = (2.1e11, 0.3, 0.05, 8050.0, 3.45e8)
 TOLS = dict(toldisp=1e-6, tolforc=1e-6, tolener=1e-6, itemax=60)
 
 
-def test_shell_newton(gpu, ref):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_shell_newton(gpu, ref, solver):
     m = meshgen.plate_model(8, 6, props=SHELL, load=-2.0e6, z_bump=0.1)
-    d = _compare(m, ref, lpf=0.25, dlpf=0.25, hist_dof=m.jcode.reshape(-1, 7)[m.meta["centre"] - 1, 2] - 1,
+    d = _compare(m, ref, solver, lpf=0.25, dlpf=0.25, hist_dof=m.jcode.reshape(-1, 7)[m.meta["centre"] - 1, 2] - 1,
                  **TOLS)
     assert np.abs(d).max() > 1e-2          # really nonlinear: deflection ~ a third of the thickness
 
 
-def test_shell_modified_newton(gpu, ref):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_shell_modified_newton(gpu, ref, solver):
     m = meshgen.plate_model(6, 6, props=SHELL, load=-1.0e5, z_bump=0.1)
-    _compare(m, ref, lpf=0.25, dlpf=0.25, algflag=2, **TOLS)
+    _compare(m, ref, solver, lpf=0.25, dlpf=0.25, algflag=2, **TOLS)
 
 
-def test_truss_newton_sample_like(gpu, ref):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_truss_newton_sample_like(gpu, ref, solver):
     m = meshgen.truss_model(3, load=50.0)
-    _compare(m, ref, lpf=0.1, dlpf=0.1, algflag=2)
+    _compare(m, ref, solver, lpf=0.1, dlpf=0.1, algflag=2)
 
 
-def test_frame_newton(gpu, ref):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_frame_newton(gpu, ref, solver):
     m = meshgen.lattice_model(3, load=20.0)
-    _compare(m, ref, lpf=0.25, dlpf=0.25)
+    _compare(m, ref, solver, lpf=0.25, dlpf=0.25)

@@ -39,11 +39,19 @@ def _load(name):
     return g, m, dyn
 
 
-def test_deck_5b_inelastic_frame_newmark(gpu):
+SOLVERS = ("skyline", "csc")      # csc: device-built CSC -> host sparse LDL^T
+
+
+def _asm(m, solver):
+    return cb.Assembler(m, layout=cb.CB_MAT_CSC if solver == "csc" else cb.CB_MAT_SKYLINE)
+
+
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_deck_5b_inelastic_frame_newmark(gpu, solver):
     g, m, dyn = _load("run_5b_frame")
     assert (m.ANAFLAG, m.ALGFLAG) == (3, 5)
-    asm = cb.Assembler(m, layout=cb.CB_MAT_SKYLINE)
-    hist, res = cb.newmark(asm, dyn, nonlinear=True)
+    asm = _asm(m, solver)
+    hist, res = cb.newmark(asm, dyn, nonlinear=True, csc=solver == "csc")
     ref = g["hist"]
     assert res.status == 0 and hist.shape == ref.shape
     assert np.allclose(hist[:, 0], ref[:, 0], rtol=1e-12, atol=0)         # times
@@ -54,11 +62,12 @@ def test_deck_5b_inelastic_frame_newmark(gpu):
     asm.close()
 
 
-def test_deck_5c_shell_linear_newmark(gpu):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_deck_5c_shell_linear_newmark(gpu, solver):
     g, m, dyn = _load("run_5c_shell")
     assert (m.ANAFLAG, m.ALGFLAG) == (1, 4)
-    asm = cb.Assembler(m, layout=cb.CB_MAT_SKYLINE)
-    hist, res = cb.newmark(asm, dyn, nonlinear=False)
+    asm = _asm(m, solver)
+    hist, res = cb.newmark(asm, dyn, nonlinear=False, csc=solver == "csc")
     ref = g["hist"][:-1]          # the reference's last row is its final output() of the (zero) d
     assert res.status == 0 and hist.shape == ref.shape
     assert np.allclose(hist[:, 0], ref[:, 0], rtol=1e-12, atol=0)
@@ -68,7 +77,8 @@ def test_deck_5c_shell_linear_newmark(gpu):
     asm.close()
 
 
-def test_arclength_shell_cap(gpu):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_arclength_shell_cap(gpu, solver):
     """modified spherical arc-length (ALGFLAG 3, main.c:2158-3141 + quad() arc.c:70): a shallow DKT
     shell cap through the C host driver cb_arclength_static against the unmodified reference driver
     (run_arc_shell.npz): the prescribed-displacement increment, then 20 MSAL increments - load
@@ -80,8 +90,8 @@ def test_arclength_shell_cap(gpu):
     ref = g["hist"]
     m = G.arc_model()
     a = dict(G.ARC)
-    asm = cb.Assembler(m, layout=cb.CB_MAT_SKYLINE)
-    hist, res = cb.arclength_static(asm, m.q, dkdof=int(g["dkdof"]), **a)
+    asm = _asm(m, solver)
+    hist, res = cb.arclength_static(asm, m.q, dkdof=int(g["dkdof"]), csc=solver == "csc", **a)
     assert res.status == 0 and hist.shape == ref.shape
     assert np.array_equal(hist[:, 1], ref[:, 1])
     assert np.allclose(hist[:, 0], ref[:, 0], rtol=1e-9, atol=0)
@@ -90,14 +100,15 @@ def test_arclength_shell_cap(gpu):
     asm.close()
 
 
-def test_deck_5d_shell_newmark_support_motion(gpu):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_deck_5d_shell_newmark_support_motion(gpu, solver):
     """model_def_5d_shell.txt (ANAFLAG 2 / ALGFLAG 5, RFLAG set to 0): geometric-nonlinear DKT shells
     driven by prescribed support motion (NBC = 2: heavy support masses, matpart() on the effective
     matrix, inertial reactions) - 20 time steps against the unmodified reference driver"""
     g, m, dyn = _load("run_5d_shell")
     assert (m.ANAFLAG, m.ALGFLAG) == (2, 5) and dyn["nbc"] == 2
-    asm = cb.Assembler(m, layout=cb.CB_MAT_SKYLINE)
-    hist, res = cb.newmark(asm, dyn, nonlinear=True)
+    asm = _asm(m, solver)
+    hist, res = cb.newmark(asm, dyn, nonlinear=True, csc=solver == "csc")
     ref = g["hist"]
     assert res.status == 0 and hist.shape == ref.shape
     assert np.array_equal(hist[:, 1], ref[:, 1])

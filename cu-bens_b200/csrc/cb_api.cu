@@ -138,6 +138,7 @@ struct cb_handle {
     DevBuf<double> tr_frame[3], tr_ef[3];
     // frames
     DevBuf<int32_t> fr_nodes, fr_osflag, fr_mendrel;
+    int fr_simple = 0;
     DevBuf<double> fr_const, fr_offset, fr_efFE_ref, fr_fg, fr_dens;
     DevBuf<double> fr_frame[3], fr_xfr[3], fr_efFE[3], fr_ef[3];
     // ANAFLAG 3
@@ -182,7 +183,7 @@ static CbDev make_dev(cb_handle *h)
     d.sh_nodes = h->sh_nodes.p; d.sh_const = h->sh_const.p; d.sh_keb = h->sh_keb.p;
     d.sh_Nm = h->sh_Nm.p; d.sh_fg = h->sh_fg.p; d.sh_der = h->sh_der.p;
     d.fr_nodes = h->fr_nodes.p; d.fr_const = h->fr_const.p; d.fr_offset = h->fr_offset.p;
-    d.fr_osflag = h->fr_osflag.p; d.fr_mendrel = h->fr_mendrel.p;
+    d.fr_osflag = h->fr_osflag.p; d.fr_mendrel = h->fr_mendrel.p; d.fr_simple = h->fr_simple;
     d.fr_efFE_ref = h->fr_efFE_ref.p; d.fr_fg = h->fr_fg.p;
     d.fr_plast = h->fr_plast.p; d.fr_yldflag = h->fr_yldflag.p; d.fr_ynew = h->fr_ynew.p;
     if (h->cls_on) { d.sh_class = h->sh_class.p; d.keb_tab = h->keb_tab.p; d.der_tab = h->der_tab.p; }
@@ -392,6 +393,9 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
             if (m->efFE_ref) for (int k = 0; k < 14; ++k) fe[e * 14 + k] = m->efFE_ref[e * 14 + k];
             if (m->dens) dn[e] = m->dens[e];             // prop_fr: pdens+i (frame.c:62)
         }
+        h->fr_simple = fl->ANAFLAG != 3 && !getenv("CB_NO_FRAME_SIMPLE");
+        for (long e = 0; e < FR && h->fr_simple; ++e)
+            if (osf[e] != 0 || rel[e * 5] == 1) h->fr_simple = 0;
         if (h->fr_const.upload(c) || h->fr_offset.upload(off) || h->fr_osflag.upload(osf) ||
             h->fr_mendrel.upload(rel) || h->fr_efFE_ref.upload(fe) || h->fr_dens.upload(dn) ||
             h->fr_fg.alloc((size_t)FR * 14))

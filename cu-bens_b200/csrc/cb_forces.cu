@@ -17,6 +17,7 @@
 #include "cb_internal.h"
 #include <algorithm>
 #include "cb_frame_math.cuh"
+#include "cb_frame_def_gen.cuh"
 
 #define CB_TPB 128
 #ifndef CB_FORCES_STAGE_KEB
@@ -1103,6 +1104,118 @@ __device__ __noinline__ void frame_rigid_link_apply(const double *off, double *E
     for (int i = 0; i < 14; ++i) EF[i] = G2[i];
 }
 
+// ------------------------------------------------------------------------------------------
+// Frames of a model without rigid offsets, end releases or plasticity (CbDev::fr_simple): the same
+// updatc + forces_fr arithmetic as k_frame_forces below, statement for statement, but
+//   * def = K dl comes from frame_def_direct (cb_frame_def_gen.cuh): every tangent entry lives in a
+//     register for the two products it feeds - no 14x14 array in local or shared memory, so the
+//     resident warps are limited by registers only (k_frame_forces: 8 warps / SM behind its 54 KB
+//     shared-memory columns, 255 registers + spills, profiles/r01e_prof_frame_forces.txt);
+//   * the phases are fenced so that each one's inputs are loaded when it starts, not hoisted to the
+//     top of the kernel (which is what pushed the single-phase kernel to 236 registers).
+// ------------------------------------------------------------------------------------------
+#ifndef CB_FR_SIMPLE_CTAS
+#define CB_FR_SIMPLE_CTAS 6      // 168 registers: 2.25 ms at 5 M frames (8 CTAs / 128 registers + spills: 2.41 ms)
+#endif
+#define CB_PHASE_FENCE() asm volatile("" ::: "memory")
+
+template <bool INPLACE>
+__global__ void __launch_bounds__(CB_FR_TPB, CB_FR_SIMPLE_CTAS)
+k_frame_forces_simple(CbDev d, const double *__restrict__ x_new, const double *__restrict__ dd,
+                      const double *frame_ip, double *frame_i, double *xfr_i, const double *ef_ip,
+                      double *ef_i, const double *efFE_ip, double *efFE_i, double dlpf, int itecnt)
+{
+    const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (e >= d.NE_FR) return;
+    const double *fc = d.fr_const + e * CB_FR_CONST;
+    const int nj = d.fr_nodes[e * 2], nk = d.fr_nodes[e * 2 + 1];
+    double def[14];
+    {   // ---- phase 1: def = (k_e + k_g) T_ip DD (frame.c:1013-1060) ------------------------------
+        double DD12[14], dl[14], eft[14], Rp[CB_FR_FRAME];
+#pragma unroll
+        for (int i = 0; i < CB_FR_FRAME; ++i) Rp[i] = frame_ip[e * CB_FR_FRAME + i];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            int q = d.jc[(long)nj * 8 + r]; DD12[r] = q ? dd[q - 1] : 0.0;
+            q = d.jc[(long)nk * 8 + r];     DD12[7 + r] = q ? dd[q - 1] : 0.0;
+        }
+        frame_T_apply(Rp, DD12, dl);
+#pragma unroll
+        for (int i = 0; i < 14; ++i) eft[i] = 0;
+#pragma unroll
+        for (int i = 4; i < 13; ++i)      // the geometric tangent reads P, M4, M5, M10, M11, M12 only
+            if (i == 4 || i == 5 || i == 7 || i >= 10) eft[i] = ef_ip[e * 14 + i] + efFE_ip[e * 14 + i];
+        if (d.ANAFLAG == 2) frame_def_direct<true>(fc, eft, Rp[9], dl, def);
+        else frame_def_direct<false>(fc, eft, Rp[9], dl, def);
+    }
+    CB_PHASE_FENCE();
+    double Ri[CB_FR_FRAME], Rp[CB_FR_FRAME];
+#pragma unroll
+    for (int i = 0; i < CB_FR_FRAME - 1; ++i) Rp[i] = frame_ip[e * CB_FR_FRAME + i];
+    if (!INPLACE) {   // ---- phase 2: updatc, frame block (misc.c:108-147) ---------------------------
+        double xa[3], xb[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            xa[m] = x_new[(long)nj * 3 + m]; xb[m] = x_new[(long)nk * 3 + m];
+            xfr_i[e * 6 + m] = xa[m]; xfr_i[e * 6 + 3 + m] = xb[m];
+        }
+        frame_triad(xa, xb, fc + 10, Ri);
+#pragma unroll
+        for (int i = 0; i < CB_FR_FRAME; ++i) frame_i[e * CB_FR_FRAME + i] = Ri[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < CB_FR_FRAME - 1; ++i) Ri[i] = Rp[i];
+    }
+    // M = T_i T_ip^T: four copies of R_i R_ip^T and 1 on the warping DOFs (frame.c:1078-1086)
+    double M[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2) M[r][s2] = dot3(Ri + 3 * r, Rp + 3 * s2);
+    CB_PHASE_FENCE();
+    const bool addref = (itecnt == 0);          // yldflag is 0 throughout for ANAFLAG 1 / 2
+    // ---- phase 3 (pass 0): ef_i = M (ef_ip + def), f = T_i^T ef_i; phase 4 (pass 1): fixed-end
+    // forces (frame.c:1090-1155); with INPLACE later rows see the rows already rewritten
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        double cur[14], out[14];
+#pragma unroll
+        for (int i = 0; i < 14; ++i) cur[i] = pass == 0 ? ef_ip[e * 14 + i] : efFE_ip[e * 14 + i];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int o = (g < 2) ? 3 * g : 7 + 3 * (g - 2);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                double v[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    v[c] = pass == 0 ? (cur[o + c] + def[o + c])
+                                     : (addref ? (cur[o + c] + dlpf * d.fr_efFE_ref[e * 14 + o + c]) : cur[o + c]);
+                out[o + r] = dot3(M[r], v);
+                if (INPLACE) cur[o + r] = out[o + r];
+            }
+        }
+#pragma unroll
+        for (int w = 6; w < 14; w += 7) {
+            const double v = pass == 0 ? (cur[w] + def[w])
+                                       : (addref ? (cur[w] + dlpf * d.fr_efFE_ref[e * 14 + w]) : cur[w]);
+            out[w] = 0.0 + 1.0 * v;
+        }
+#pragma unroll
+        for (int i = 0; i < 14; ++i) {
+            if (pass == 0) ef_i[e * 14 + i] = out[i];
+            else efFE_i[e * 14 + i] = out[i];
+        }
+        if (pass == 0) {
+            double EF[14];
+            frame_Tt_apply(Ri, out, EF);
+#pragma unroll
+            for (int i = 0; i < 14; ++i) d.fr_fg[e * 14 + i] = EF[i];
+        }
+        CB_PHASE_FENCE();
+    }
+}
+
 template <bool INPLACE>
 __global__ void __launch_bounds__(CB_FR_TPB, 4)
 k_frame_forces(CbDev d, const double *__restrict__ x_new, const double *__restrict__ dd,
@@ -1354,7 +1467,12 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
             static const int init[4] = {0x7fffffff, 0, 0, 0};
             if (cudaMemcpyAsync(d.fr_trip, init, sizeof init, cudaMemcpyHostToDevice, s) != cudaSuccess) return 1;
         }
-        k_frame_forces<false><<<g, CB_FR_TPB, CB_FR_SMEM, s>>>(d, a.x_temp, a.dd, a.fr_frame_ip, a.fr_frame_i,
+        if (d.fr_simple)
+            k_frame_forces_simple<false><<<g, CB_FR_TPB, 0, s>>>(d, a.x_temp, a.dd, a.fr_frame_ip, a.fr_frame_i,
+                                               a.fr_xfr_i, a.fr_ef_ip, a.fr_ef_i, a.fr_efFE_ip,
+                                               a.fr_efFE_i, a.dlpf, a.itecnt);
+        else
+            k_frame_forces<false><<<g, CB_FR_TPB, CB_FR_SMEM, s>>>(d, a.x_temp, a.dd, a.fr_frame_ip, a.fr_frame_i,
                                                a.fr_xfr_i, a.fr_ef_ip, a.fr_ef_i, a.fr_efFE_ip,
                                                a.fr_efFE_i, a.dlpf, a.itecnt);
         ++*launches;
@@ -1406,7 +1524,12 @@ int cbk_forces_linear(const CbForceArgs &a, const double *d_total, cudaStream_t 
     }
     if (d.NE_FR) {
         unsigned g = (unsigned)((d.NE_FR + 63) / 64);
-        k_frame_forces<true><<<g, CB_FR_TPB, CB_FR_SMEM, s>>>(d, a.x_temp, d_total, a.fr_frame_i, a.fr_frame_i,
+        if (d.fr_simple)
+            k_frame_forces_simple<true><<<g, CB_FR_TPB, 0, s>>>(d, a.x_temp, d_total, a.fr_frame_i, a.fr_frame_i,
+                                              a.fr_xfr_i, a.fr_ef_i, a.fr_ef_i, a.fr_efFE_i,
+                                              a.fr_efFE_i, 0.0, 0);
+        else
+            k_frame_forces<true><<<g, CB_FR_TPB, CB_FR_SMEM, s>>>(d, a.x_temp, d_total, a.fr_frame_i, a.fr_frame_i,
                                               a.fr_xfr_i, a.fr_ef_i, a.fr_ef_i, a.fr_efFE_i,
                                               a.fr_efFE_i, 0.0, 0);
         ++*launches;

@@ -163,6 +163,8 @@ struct CbDev {
     const double *fr_offset; // [NE][6]
     const int32_t *fr_osflag;
     const int32_t *fr_mendrel; // [NE][5]
+    int fr_simple;           // no member has rigid offsets or end releases and ANAFLAG != 3: the force
+                             // pass runs its register-only specialisation (k_frame_forces<*, true>)
     const double *fr_efFE_ref; // [NE][14]
     double *fr_fg;           // [NE][14]
     // ANAFLAG 3 (concentrated plasticity), else nullptr

@@ -70,7 +70,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("CUBENS_LIB") or LIB_PATH      # CUBENS_LIB: kernel-variant builds (development)
     if not os.path.exists(path):
         raise CubensError(f"{path} not found - build it with `make -C cu-bens_b200` "
                           "(or __graft_entry__.build()); there is no CPU fallback")

@@ -6,8 +6,8 @@ rows = list(csv.reader(out.splitlines()))
 h = rows[0]; ix = {k: i for i, k in enumerate(h)}
 name = None
 for r in rows[1:]:
-    if len(r) < len(h):
-        continue
+    if len(r) <= ix["Metric Value"] or not r[ix["Metric Name"]]:
+        continue                  # rule rows / truncated rows carry no metric
     if r[ix["Kernel Name"]] != name:
         name = r[ix["Kernel Name"]]
         print("kernel:", name)

@@ -85,8 +85,12 @@ struct CbTPair {
 // ---- shell-only tile assembly ("duo" plan): a thread evaluates up to two consecutive
 // contributions of one joint-pair block and sums them in registers; blocks with more than two
 // contributions are split into partial sums that are combined through shared memory
-#define CB_T2_OUT 3072           // max doubles of Ax per tile staged in shared memory
+#ifndef CB_T2_OUT
+#define CB_T2_OUT 3328           // max doubles of Ax per tile staged in shared memory (13 plate joints: 117 of 128 lanes busy; 3072 = 12 joints measured 5 % slower)
+#endif
+#ifndef CB_T2_ELEMS
 #define CB_T2_ELEMS 56           // max distinct shells per tile (their krec records are staged)
+#endif
 #define CB_T2_GROUP 16           // max partial sums of one block (a group of lanes of one warp)
 struct CbTile2 {
     int64_t out0;     // first Ax index of the tile's contiguous output range

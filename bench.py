@@ -174,6 +174,73 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+# SURVEY.md 8(d), "Frame / truss / brick bytes (same method)"
+ALG_BYTES_FR_KT = 1215.0      # 915 B of CSC written (114 nnz / frame on the lattice) + 300 B read
+ALG_BYTES_FR_FINT = 700.0
+ALG_BYTES_BR_K = 1968.0       # 243 nnz / brick written + 8 joints' coordinates
+
+
+def other_configs(cb, meshgen, device, peak):
+    """BASELINE.json configs[3] and configs[4] shapes on one GPU (not the bench metric; same timing
+    method: CUDA events on the library's stream, inputs far larger than the 126 MB L2):
+    119^3 joint frame lattice (5 012 994 frames, 7 DOF / joint, geometric nonlinear) - K_t, f_int and
+    the lumped mass the Newmark loop refreshes every iteration; 80^3 bricks + 12 800 skin shells -
+    stiff_br (+ stiff_sh) and the consistent mass on the same CSC pattern (linear, assembled once in
+    the reference)."""
+    out = {}
+    m = meshgen.lattice_model(119, SLVFLAG=2)
+    a = cb.Assembler(m, layout=cb.CB_MAT_CSC, device=device)
+    a.begin_increment(); a.stiff(); a.sync()
+    dd = meshgen.perturbation(m, scale=1e-3)
+    a.update_forces(dd, want_f=False); a.end_iteration()
+    a.set_dd(dd * 0.01)
+    ks, fs = [], []
+    for _ in range(3):
+        a.stiff(); a.update_forces_dev(); a.end_iteration()
+    K = 20
+    a.sync(); a.timer_start()
+    for _ in range(K):
+        a.stiff(); a.update_forces_dev(); a.end_iteration()
+    step_ms = a.timer_stop_ms() / K
+    for _ in range(5):
+        a.stiff(); ks.append(a.last_stiff_ms); a.update_forces_dev(); fs.append(a.last_forces_ms)
+        a.end_iteration()
+    a.sync(); a.timer_start()
+    for _ in range(5):
+        a._check(a.lib.cb_mass(a.h))
+    mass_ms = a.timer_stop_ms() / 5
+    k_ms, f_ms = float(np.median(ks)), float(np.median(fs))
+    out["frame_lattice"] = {
+        "workload": f"119^3-joint cubic frame lattice, {m.NE_FR} frames, NEQ {m.NEQ}, nnz "
+                    f"{a.lib.cb_csc_nnz(a.h)}, ANAFLAG 2 (BASELINE.json configs[3] shape)",
+        "value": m.NE_FR / (step_ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms, "steps": K,
+        "split_ms": {"stiff_total": k_ms, "update_forces": f_ms, "mass_refresh": mass_ms},
+        "roofline_frac": {"K_t": ALG_BYTES_FR_KT * m.NE_FR / (k_ms * 1e-3) / 1e9 / peak,
+                          "f_int": ALG_BYTES_FR_FINT * m.NE_FR / (f_ms * 1e-3) / 1e9 / peak,
+                          "step": (ALG_BYTES_FR_KT + ALG_BYTES_FR_FINT) * m.NE_FR / (step_ms * 1e-3) / 1e9 / peak}}
+    a.close()
+    m = meshgen.brick_model(80, 80, 80, skin=True)
+    a = cb.Assembler(m, layout=cb.CB_MAT_CSC, device=device)
+    a.stiff(cb.CB_GEN_COMMITTED); a.sync()
+    ks = []
+    for _ in range(5):
+        a.stiff(cb.CB_GEN_COMMITTED); ks.append(a.last_stiff_ms)
+    a._check(a.lib.cb_mass(a.h)); a.sync(); a.timer_start()
+    for _ in range(3):
+        a._check(a.lib.cb_mass(a.h))
+    mass_ms = a.timer_stop_ms() / 3
+    k_ms = float(np.median(ks))
+    out["brick_skin"] = {
+        "workload": f"80^3 8-node bricks + {m.NE_SH} DKT skin shells, NEQ {m.NEQ}, nnz "
+                    f"{a.lib.cb_csc_nnz(a.h)} (BASELINE.json configs[4] shape without the dense FSI "
+                    "coupling of fsi.c, which is out of scope)",
+        "value": m.NE_SBR / (k_ms * 1e-3), "unit": "bricks/s", "ms_stiff": k_ms,
+        "ms_consistent_mass": mass_ms,
+        "roofline_frac": ALG_BYTES_BR_K * m.NE_SBR / (k_ms * 1e-3) / 1e9 / peak}
+    a.close()
+    return out
+
+
 def partition_rows(n, world, rank):
     """contiguous strips of cell rows (along i); returns (i0, i1)"""
     per = n // world
@@ -359,6 +426,11 @@ def run_gpu(a):
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peak()
+    others = None
+    if world == 1 and not a.no_others:
+        if unstructured is None:
+            asm.close()
+        others = other_configs(cb, meshgen, local, peak)
     k_ms = float(np.median(asm_ms))
     ach = ALG_BYTES_KT * n_local / (k_ms * 1e-3) / 1e9
     traffic = None
@@ -394,6 +466,8 @@ def run_gpu(a):
     }
     if unstructured is not None:
         line["unstructured"] = unstructured
+    if others is not None:
+        line["other_configs"] = others
     if e2e is not None:
         line["e2e"] = e2e
     if cpu is not None:
@@ -415,6 +489,8 @@ def main():
     ap.add_argument("--detail", action="store_true")
     ap.add_argument("--no-unstructured", action="store_true",
                     help="skip the second (jittered-plate) measurement")
+    ap.add_argument("--no-others", action="store_true",
+                    help="skip the frame-lattice / brick measurements (BASELINE configs[3], [4] shapes)")
     ap.add_argument("--strong", action="store_true",
                     help="N>1: split ONE n x n plate across the ranks (default: weak scaling, every "
                          "rank owns an n x n-cell strip of an (n*N) x n plate)")

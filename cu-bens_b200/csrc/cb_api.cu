@@ -137,7 +137,9 @@ struct cb_handle {
     DevBuf<double> tr_const, tr_fg, tr_dens;
     DevBuf<double> tr_frame[3], tr_ef[3];
     // frames
-    DevBuf<int32_t> fr_nodes, fr_osflag, fr_mendrel;
+    DevBuf<int32_t> fr_nodes, fr_osflag, fr_mendrel, fr_gid, sh_gid;
+    bool forces_open = false;        // between cb_update_forces_begin and _end
+    int32_t trip_in[2] = {-1, -1};   // staging of the agreed trip indices (async H2D source)
     int fr_simple = 0;
     DevBuf<double> fr_const, fr_offset, fr_efFE_ref, fr_fg, fr_dens;
     DevBuf<double> fr_frame[3], fr_xfr[3], fr_efFE[3], fr_ef[3];
@@ -190,6 +192,7 @@ static CbDev make_dev(cb_handle *h)
     d.sh_yield = h->sh_yield.p; d.sh_pl = h->sh_pl[1].p; d.sh_yv = h->sh_yv.p; d.sh_kpl = h->sh_kpl.p;
     d.sh_trip = h->sh_trip.p;
     d.fr_code = h->fr_code.p; d.fr_tau = h->fr_tau.p; d.fr_trip = h->fr_trip.p; d.tr_py = h->tr_py.p;
+    d.fr_gid = h->fr_gid.p; d.sh_gid = h->sh_gid.p;
     d.tr_nodes = h->tr_nodes.p; d.tr_const = h->tr_const.p; d.tr_fg = h->tr_fg.p;
     d.br_nodes = h->br_nodes.p; d.br_const = h->br_const.p;
     return d;
@@ -527,7 +530,7 @@ extern "C" void cb_destroy(cb_handle *h)
         h->fr_frame[g].release(); h->fr_xfr[g].release(); h->fr_efFE[g].release();
         h->fr_ef[g].release();
     }
-    for (DevBuf<int32_t> *b : {&h->jc, &h->sh_nodes, &h->tr_nodes, &h->fr_nodes, &h->fr_osflag,
+    for (DevBuf<int32_t> *b : {&h->fr_gid, &h->sh_gid, &h->jc, &h->sh_nodes, &h->tr_nodes, &h->fr_nodes, &h->fr_osflag,
                                &h->fr_mendrel, &h->br_nodes, &h->node_cstart})
         b->release();
     h->corners.release(); h->contribs.release(); h->plan_csc.pairs.release();
@@ -1198,15 +1201,55 @@ static CbForceArgs force_args(cb_handle *h)
     return a;
 }
 
+// ---- the force pass in two halves (element-partitioned ANAFLAG 3 runs) ------------
+// forces_fr / forces_sh return from the middle of their element loops at the first member / shell
+// that overshoots the yield surface or unloads (fact 0.8).  On one GPU cb_update_forces_dev finds
+// that element itself.  On several, every rank evaluates its own elements
+// (cb_update_forces_begin), the ranks agree on the lowest GLOBAL index (min over ranks of
+// first_fr / first_sh - one all-reduce of two integers), and cb_update_forces_end commits the
+// flags up to it, gathers f_temp without the elements from it on and returns the code and dlpf
+// factor of that member where this rank holds it (code 0, factor 1 elsewhere: the caller takes the
+// max code and the min factor over the ranks).
+extern "C" int cb_set_element_ids(cb_handle *h, const int *fr_gid, const int *sh_gid)
+{
+    if (!h) return fail(CB_ERR_ARG, "null handle");
+    cudaSetDevice(h->fl.device);
+    if (fr_gid && h->sz.NE_FR) {
+        std::vector<int32_t> v(fr_gid, fr_gid + h->sz.NE_FR);
+        for (long e = 1; e < h->sz.NE_FR; ++e)
+            if (v[e] <= v[e - 1]) return fail(CB_ERR_ARG, "global member indices must ascend");
+        h->fr_gid.release();
+        if (h->fr_gid.upload(v)) return fail(CB_ERR_CUDA, "fr_gid upload");
+    }
+    if (sh_gid && h->sz.NE_SH) {
+        std::vector<int32_t> v(sh_gid, sh_gid + h->sz.NE_SH);
+        for (long e = 1; e < h->sz.NE_SH; ++e)
+            if (v[e] <= v[e - 1]) return fail(CB_ERR_ARG, "global shell indices must ascend");
+        h->sh_gid.release();
+        if (h->sh_gid.upload(v)) return fail(CB_ERR_CUDA, "sh_gid upload");
+    }
+    return CB_OK;
+}
+
 extern "C" int cb_update_forces_dev(cb_handle *h, const double *dd_dev, double *dlpf_inout,
                                     int itecnt, int *frcchk_fr, int *frcchk_sh)
+{
+    const int rc = cb_update_forces_begin(h, dd_dev, dlpf_inout ? *dlpf_inout : 0.0, itecnt,
+                                          nullptr, nullptr);
+    if (rc != CB_OK) return rc;
+    // one GPU: the local minima (still on the device) are the global ones - no read-back here
+    return cb_update_forces_end(h, -1, -1, dlpf_inout, frcchk_fr, frcchk_sh);
+}
+
+extern "C" int cb_update_forces_begin(cb_handle *h, const double *dd_dev, double dlpf, int itecnt,
+                                      int *first_fr, int *first_sh)
 {
     if (!h) return fail(CB_ERR_ARG, "null handle");
     cudaSetDevice(h->fl.device);
     int rc = build_plan(h); if (rc) return rc;
     rc = ensure_keb(h); if (rc) return rc;
-    if (frcchk_fr) *frcchk_fr = 0;
-    if (frcchk_sh) *frcchk_sh = 0;
+    if (first_fr) *first_fr = 0x7fffffff;
+    if (first_sh) *first_sh = 0x7fffffff;
     if (h->fl.ANAFLAG == 1)
         return fail(CB_ERR_ARG, "ANAFLAG 1 recovers forces with cb_forces_linear (main.c:1774-1793)");
     cudaStream_t s = h->stream;
@@ -1214,7 +1257,7 @@ extern "C" int cb_update_forces_dev(cb_handle *h, const double *dd_dev, double *
     if (h->i_is_ip) h->i_is_ip = false;
     CbForceArgs a = force_args(h);
     if (dd_dev && dd_dev != h->dd.p) { if (d2d(h->dd.p, dd_dev, h->sz.NEQ, s)) return fail(CB_ERR_CUDA, "dd copy"); }
-    a.dlpf = dlpf_inout ? *dlpf_inout : 0.0; a.itecnt = itecnt;
+    a.dlpf = dlpf; a.itecnt = itecnt;
     CUDA_TRY(cudaEventRecord(h->ev4, s));
     {   // d_temp += dd (main.c:1949)
         const bool whole = h->j0 == 0 && h->j1 == h->sz.NJ;
@@ -1227,6 +1270,42 @@ extern "C" int cb_update_forces_dev(cb_handle *h, const double *dd_dev, double *
     if (cbk_node_update(a, s)) return fail(CB_ERR_CUDA, "node update launch");
     ++h->launches;
     if (cbk_forces(a, s, &h->launches)) return fail(CB_ERR_CUDA, "forces launch");
+    h->forces_open = true;
+    if (h->fl.ANAFLAG == 3 && (first_fr || first_sh)) {
+        int32_t f = 0x7fffffff, g = 0x7fffffff;
+        if (h->sz.NE_FR) CUDA_TRY(cudaMemcpyAsync(&f, h->fr_trip.p, sizeof f, cudaMemcpyDeviceToHost, s));
+        if (h->sz.NE_SH) CUDA_TRY(cudaMemcpyAsync(&g, h->sh_trip.p, sizeof g, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (first_fr) *first_fr = f;
+        if (first_sh) *first_sh = g;
+    }
+    return CB_OK;
+}
+
+extern "C" int cb_update_forces_end(cb_handle *h, int first_fr, int first_sh, double *dlpf_inout,
+                                    int *frcchk_fr, int *frcchk_sh)
+{
+    if (!h) return fail(CB_ERR_ARG, "null handle");
+    if (!h->forces_open) return fail(CB_ERR_ARG, "cb_update_forces_end without cb_update_forces_begin");
+    cudaSetDevice(h->fl.device);
+    h->forces_open = false;
+    if (frcchk_fr) *frcchk_fr = 0;
+    if (frcchk_sh) *frcchk_sh = 0;
+    cudaStream_t s = h->stream;
+    CbForceArgs a = force_args(h);
+    if (h->fl.ANAFLAG == 3) {                         // the agreed global minima (negative: keep the local ones)
+        h->trip_in[0] = first_fr; h->trip_in[1] = first_sh;
+        if (first_fr >= 0 && h->sz.NE_FR)
+            CUDA_TRY(cudaMemcpyAsync(h->fr_trip.p, &h->trip_in[0], sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        if (first_sh >= 0 && h->sz.NE_SH)
+            CUDA_TRY(cudaMemcpyAsync(h->sh_trip.p, &h->trip_in[1], sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        if (h->sz.NE_FR) {                            // a rank that does not hold the member reports 0 / 1.0
+            static const int32_t zero = 0; static const double one = 1.0;
+            CUDA_TRY(cudaMemcpyAsync(h->fr_trip.p + 1, &zero, sizeof zero, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(h->fr_trip.p + 2, &one, sizeof one, cudaMemcpyHostToDevice, s));
+        }
+    }
+    if (cbk_frame_trip(a.d, s, &h->launches)) return fail(CB_ERR_CUDA, "frame trip launch");
     if (cbk_gather_f(a, s)) return fail(CB_ERR_CUDA, "gather launch");
     ++h->launches;
     CUDA_TRY(cudaEventRecord(h->ev5, s));

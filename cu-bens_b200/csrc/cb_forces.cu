@@ -814,7 +814,7 @@ k_shell_forces_pl(CbDev d, const double *__restrict__ x_temp, const double *__re
             phi[i] = 0;
         }
     }
-    if (code != 0) atomicMin(d.sh_trip, (int)e);
+    if (code != 0) atomicMin(d.sh_trip, d.sh_gid ? d.sh_gid[e] : (int)e);
 
     // M = R_i R_ip^T: T_i T_ip^T is block diagonal (shell.c:2352-2362)
     double M3[3][3];
@@ -1367,7 +1367,7 @@ k_frame_forces(CbDev d, const double *__restrict__ x_new, const double *__restri
         }
         d.fr_ynew[e * 2] = y0; d.fr_ynew[e * 2 + 1] = y1;
         d.fr_code[e] = code; d.fr_tau[e] = tau;
-        if (code != 0) atomicMin(d.fr_trip, (int)e);
+        if (code != 0) atomicMin(d.fr_trip, d.fr_gid ? d.fr_gid[e] : (int)e);
     }
     double EF[14];
     frame_Tt_apply(Ri, efn, EF);
@@ -1391,8 +1391,9 @@ k_frame_trip(CbDev d)
     const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (e >= d.NE_FR) return;
     const int first = d.fr_trip[0];
-    if (e <= first) { d.fr_yldflag[e * 2] = d.fr_ynew[e * 2]; d.fr_yldflag[e * 2 + 1] = d.fr_ynew[e * 2 + 1]; }
-    if (e == first) { d.fr_trip[1] = d.fr_code[e]; reinterpret_cast<double *>(d.fr_trip + 2)[0] = d.fr_tau[e]; }
+    const int g = d.fr_gid ? d.fr_gid[e] : (int)e;
+    if (g <= first) { d.fr_yldflag[e * 2] = d.fr_ynew[e * 2]; d.fr_yldflag[e * 2 + 1] = d.fr_ynew[e * 2 + 1]; }
+    if (g == first) { d.fr_trip[1] = d.fr_code[e]; reinterpret_cast<double *>(d.fr_trip + 2)[0] = d.fr_tau[e]; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -1409,12 +1410,12 @@ k_gather_f(CbDev d, long j0, long j1, const int32_t *__restrict__ cstart,
     for (int c = c0; c < c1; ++c) {
         const CbCorner cr = corners[c];
         if (cr.type == CB_T_SHELL) {
-            if (cr.e >= sh_end) continue;
+            if ((d.sh_gid && sh_end != 0x7fffffff ? d.sh_gid[cr.e] : cr.e) >= sh_end) continue;
             const double *p = CB_FG(d.sh_fg, cr.b, cr.e, d.NE_SH);
 #pragma unroll
             for (int r = 0; r < 6; ++r) acc[r] += p[r];
         } else if (cr.type == CB_T_FRAME) {
-            if (cr.e >= fr_end) continue;
+            if ((d.fr_gid && fr_end != 0x7fffffff ? d.fr_gid[cr.e] : cr.e) >= fr_end) continue;
             const double *p = d.fr_fg + (long)cr.e * 14 + cr.b * 7;
 #pragma unroll
             for (int r = 0; r < 7; ++r) acc[r] += p[r];
@@ -1452,6 +1453,16 @@ static int frame_forces_configure()
     return 0;
 }
 
+// ANAFLAG 3, after the force kernels (and, on several GPUs, after the lowest tripping member index
+// has been agreed on): keep the flags of the members up to it, publish its code and dlpf factor
+int cbk_frame_trip(const CbDev &d, cudaStream_t s, long *launches)
+{
+    if (d.ANAFLAG != 3 || !d.NE_FR) return 0;
+    k_frame_trip<<<(unsigned)((d.NE_FR + 255) / 256), 256, 0, s>>>(d);
+    ++*launches;
+    return cudaGetLastError() != cudaSuccess;
+}
+
 int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
 {
     const CbDev &d = a.d;
@@ -1476,10 +1487,6 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
                                                a.fr_xfr_i, a.fr_ef_ip, a.fr_ef_i, a.fr_efFE_ip,
                                                a.fr_efFE_i, a.dlpf, a.itecnt);
         ++*launches;
-        if (d.ANAFLAG == 3) {
-            k_frame_trip<<<(unsigned)((d.NE_FR + 255) / 256), 256, 0, s>>>(d);
-            ++*launches;
-        }
     }
     if (d.NE_SH) {
         unsigned g = (unsigned)((d.NE_SH + CB_TPB - 1) / CB_TPB);

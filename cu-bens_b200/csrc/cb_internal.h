@@ -177,6 +177,10 @@ struct CbDev {
     int32_t *fr_ynew;        // [NE][2] flags proposed by the force pass (committed up to the first trip)
     int32_t *fr_code;        // [NE] return code of the force pass for this member: 0, 1, 2
     double *fr_tau;          // [NE] regula-falsi scale of dlpf when code == 1
+    // element-partitioned runs (cb_set_element_ids): GLOBAL index of every local member / shell, so
+    // that "the first element that trips"  means the same element on every rank;
+    // nullptr = local index
+    const int32_t *fr_gid, *sh_gid;
     int32_t *fr_trip;        // [4] lowest member index with code != 0 (INT_MAX if none), its code
     const double *tr_py;     // [NE_TR] squash loads of the trusses
     // shells, ANAFLAG 3 (Ivanov yield criterion in stress resultants)
@@ -262,6 +266,7 @@ int cbk_shell_plastic_prep(const CbDev &d, const double *sh_frame, const double 
                            const double *sh_pl, cudaStream_t s);
 int cbk_node_update(const CbForceArgs &a, cudaStream_t s);
 int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches);
+int cbk_frame_trip(const CbDev &d, cudaStream_t s, long *launches);
 int cbk_forces_linear(const CbForceArgs &a, const double *d_total, cudaStream_t s, long *launches);
 int cbk_gather_f(const CbForceArgs &a, cudaStream_t s);
 int cbk_mass(const CbDev &d, const double *x, double *sh_const_mut, double *tr_const_mut,

@@ -37,6 +37,7 @@ EXPORTS = [
     "cb_host_free", "cb_map_bytes", "cb_sync", "cb_stream", "cb_set_q", "cb_residual_sums",
     "cb_dev_sums", "cb_get_sums", "cb_get_yldflag", "cb_set_yldflag", "cb_get_mass_csc_values", "cb_dev_Mx",
     "cb_geometry_classes", "cb_keep_ip", "cb_checkpoint_save", "cb_checkpoint_load",
+    "cb_set_element_ids", "cb_update_forces_begin", "cb_update_forces_end",
 ]
 
 
@@ -174,6 +175,33 @@ class Assembler:
         self._check(self.lib.cb_update_forces(self.h, _p(dd), C.byref(cdl), C.c_int(itecnt),
                                               _p(f) if want_f else C.c_void_p(0), C.byref(fr),
                                               C.byref(sh)))
+        return f, fr.value, sh.value, cdl.value
+
+    # ---- element-partitioned ANAFLAG 3: the force pass in two halves around the exchange of the
+    # lowest tripping element index (include/cubens_b200.h, cb_update_forces_begin / _end)
+    def set_element_ids(self, fr_gid=None, sh_gid=None):
+        fr = None if fr_gid is None else np.ascontiguousarray(fr_gid, dtype=np.int32)
+        sh = None if sh_gid is None else np.ascontiguousarray(sh_gid, dtype=np.int32)
+        self._check(self.lib.cb_set_element_ids(self.h, _p(fr), _p(sh)))
+
+    def update_forces_begin(self, dd, dlpf=1.0, itecnt=0):
+        """dd: host [NEQ] (uploaded) or None (already in cb_dev_dd()).  Returns (first_fr, first_sh):
+        lowest global index of a frame / shell that trips on this rank (INT_MAX: none)."""
+        if dd is not None:
+            self.set_dd(dd)
+        ffr = C.c_int(0); fsh = C.c_int(0)
+        self._check(self.lib.cb_update_forces_begin(self.h, C.c_void_p(0), C.c_double(dlpf), C.c_int(itecnt),
+                                                    C.byref(ffr), C.byref(fsh)))
+        return ffr.value, fsh.value
+
+    def update_forces_end(self, first_fr, first_sh, dlpf=1.0, want_f=True):
+        cdl = C.c_double(dlpf); fr = C.c_int(0); sh = C.c_int(0)
+        self._check(self.lib.cb_update_forces_end(self.h, C.c_int(first_fr), C.c_int(first_sh), C.byref(cdl),
+                                                  C.byref(fr), C.byref(sh)))
+        f = None
+        if want_f:
+            f = np.zeros(self.m.NEQ)
+            self._check(self.lib.cb_get_f(self.h, _p(f)))
         return f, fr.value, sh.value, cdl.value
 
     def update_forces_dev(self, dlpf=1.0, itecnt=0):

@@ -57,6 +57,87 @@ def plate_partition(nx_local, ny, world, rank, weak=True, props=meshgen.SHELL_5C
     return m, (j0, j1), 2 * ny * (i1 - i0)
 
 
+def partition_model(m, world, rank):
+    """Generic element partition of a truss / frame / shell model (no bricks) by contiguous joint
+    ranges: rank r owns joints [j0, j1) and gets every element that touches one of them (its own
+    elements plus the halo), with the GLOBAL joint / equation numbering.  Returns
+    (sub_model, (j0, j1), ids) with ids = dict(tr=, fr=, sh=) the global 0-based element indices of
+    the local elements (ascending; what cb_set_element_ids takes) and ids['own_*'] boolean masks of
+    the elements counted on this rank (first joint owned)."""
+    from .model import Model
+    if m.NE_BR:
+        raise ValueError("partition_model: bricks are assembled once and are not partitioned")
+    per = -(-m.NJ // world)
+    j0, j1 = min(rank * per, m.NJ), min((rank + 1) * per, m.NJ)
+    TR, FR, SH = m.NE_TR, m.NE_FR, m.NE_SH
+    o_fr, o_sh = 2 * TR, 2 * TR + 2 * FR
+    conn = {"tr": m.minc[:o_fr].reshape(-1, 2), "fr": m.minc[o_fr:o_sh].reshape(-1, 2),
+            "sh": m.minc[o_sh:o_sh + 3 * SH].reshape(-1, 3)}
+    ids = {}
+    for k, c in conn.items():
+        owned = (c - 1 >= j0) & (c - 1 < j1)
+        ids[k] = np.flatnonzero(owned.any(axis=1)).astype(I64)
+        ids["own_" + k] = owned[ids[k], 0] if len(c) else np.zeros(0, dtype=bool)
+    tr, fr, sh = ids["tr"], ids["fr"], ids["sh"]
+    ntr, nfr, nsh = len(tr), len(fr), len(sh)
+    s = Model(NJ=m.NJ, NE_TR=ntr, NE_FR=nfr, NE_SH=nsh, NEQ=m.NEQ, ANAFLAG=m.ANAFLAG, ALGFLAG=m.ALGFLAG,
+              SLVFLAG=2, x=m.x, jcode=m.jcode, q=m.q, lss=0,
+              meta=dict(m.meta, kind="partition", rank=rank, world=world, joints=(j0, j1)))
+    s.minc = np.concatenate([conn["tr"][tr].reshape(-1), conn["fr"][fr].reshape(-1), conn["sh"][sh].reshape(-1)])
+    jc = m.jcode.reshape(-1, 7)
+    s.mcode = np.concatenate([jc[conn["tr"][tr] - 1][:, :, :3].reshape(-1),      # model.c:992-1142
+                              jc[conn["fr"][fr] - 1].reshape(-1),
+                              jc[conn["sh"][sh] - 1][:, :, :6].reshape(-1)]).astype(I64)
+    by_el = np.concatenate([tr, TR + fr, TR + FR + sh])                  # emod / yld
+    s.emod, s.yld = m.emod[by_el], m.yld[by_el]
+    # dens[n] is indexed by the element's number WITHIN its type for every type (App. B.4)
+    s.dens = np.zeros(ntr + nfr + nsh)
+    for idx in (tr, fr, sh):
+        s.dens[:len(idx)] = m.dens[idx]
+    lin = np.concatenate([tr, TR + fr])
+    s.carea, s.llength = m.carea[lin], m.llength[lin]
+    three = lambda idx: (idx[:, None] * 3 + np.arange(3)).reshape(-1)
+    cs = np.concatenate([tr, TR + three(fr), TR + 3 * FR + three(sh)]).astype(I64)
+    s.c1, s.c2, s.c3 = m.c1[cs], m.c2[cs], m.c3[cs]
+    s.nu, s.thick, s.farea = m.nu[sh], m.thick[sh], m.farea[sh]
+    s.slength, s.xlocal = m.slength[three(sh)], m.xlocal[three(sh)]
+    rows = lambda a, idx, k: np.ascontiguousarray(np.asarray(a).reshape(-1, k)[idx].reshape(-1))
+    for name, k in (("gmod", 1), ("istrong", 1), ("iweak", 1), ("ipolar", 1), ("iwarp", 1), ("zstrong", 1),
+                    ("zweak", 1), ("auxpt", 3), ("offset", 6), ("osflag", 1), ("mendrel", 5), ("xfr", 6),
+                    ("efFE_ref", 14)):
+        a = getattr(m, name)
+        setattr(s, name, rows(a, fr, k) if a is not None else None)
+    return s, (j0, j1), ids
+
+
+def reduce_trip(firsts):
+    """the exchange between cb_update_forces_begin and _end: element-wise minimum of the ranks'
+    (first_fr, first_sh) - host-side form for several handles in one process; under
+    torch.distributed the same thing is one all_reduce(MIN) of two int32 (TripExchange)"""
+    return min(f[0] for f in firsts), min(f[1] for f in firsts)
+
+
+class TripExchange:
+    """ANAFLAG 3 on several GPUs: agree on the first tripping frame / shell (all-reduce MIN of two
+    integers), then on the return code (MAX) and the rescaled dlpf (MIN) - 24 bytes per force pass."""
+
+    def __init__(self, asm, dist, device=None):
+        import torch
+        self.torch, self.dist, self.asm = torch, dist, asm
+        self.dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+
+    def update_forces(self, dd, dlpf=1.0, itecnt=0, want_f=True):
+        t, dist = self.torch, self.dist
+        first = t.tensor(self.asm.update_forces_begin(dd, dlpf, itecnt), dtype=t.int32, device=self.dev)
+        dist.all_reduce(first, op=dist.ReduceOp.MIN)
+        f, fr, sh, dl = self.asm.update_forces_end(int(first[0]), int(first[1]), dlpf, want_f)
+        code = t.tensor([fr, sh], dtype=t.int32, device=self.dev)
+        dist.all_reduce(code, op=dist.ReduceOp.MAX)
+        dmin = t.tensor([dl], dtype=t.float64, device=self.dev)
+        dist.all_reduce(dmin, op=dist.ReduceOp.MIN)
+        return f, int(code[0]), int(code[1]), float(dmin[0])
+
+
 class _DevVec:
     """torch view of a device buffer owned by the C library (no copy)"""
 

@@ -135,6 +135,24 @@ int  cb_update_forces(cb_handle *h, const double *dd, double *dlpf_inout, int it
 /* same with dd / f_temp already resident on the device (no PCIe traffic)                  */
 int  cb_update_forces_dev(cb_handle *h, const double *dd_dev, double *dlpf_inout, int itecnt,
                           int *frcchk_fr, int *frcchk_sh);
+/* Element-partitioned ANAFLAG 3: forces_fr (frame.c:1184-1268) and
+ * forces_sh (shell.c:2044-2046) return at the FIRST element that trips, so the ranks must agree on
+ * the lowest global element index before flags are committed and f_temp is gathered.
+ *   cb_set_element_ids     global (whole-model, 0-based, ascending) index of every local frame /
+ *                          shell; either pointer may be NULL (= local numbering)
+ *   cb_update_forces_begin = updatc + the element loops of forces_*; first_fr / first_sh (may be
+ *                          NULL) receive the lowest tripping global index on this rank (INT_MAX: none)
+ *   ... the caller takes the minimum of first_fr, first_sh over the ranks (one all-reduce) ...
+ *   cb_update_forces_end   commits yldflag up to first_fr, gathers f_temp without the elements
+ *                          from the trip on; frcchk_fr / *dlpf_inout are set where this rank holds
+ *                          that member (0 / unchanged elsewhere: take the max code and the min of
+ *                          dlpf over the ranks), frcchk_sh on every rank.  first_* < 0: keep the
+ *                          rank-local minima (what cb_update_forces_dev does on one GPU).        */
+int  cb_set_element_ids(cb_handle *h, const int *fr_gid, const int *sh_gid);
+int  cb_update_forces_begin(cb_handle *h, const double *dd_dev, double dlpf, int itecnt,
+                            int *first_fr, int *first_sh);
+int  cb_update_forces_end(cb_handle *h, int first_fr, int first_sh, double *dlpf_inout,
+                          int *frcchk_fr, int *frcchk_sh);
 int  cb_forces_linear(cb_handle *h, const double *d, double *f_out);  /* main.c:1774-1793  */
 int  cb_end_iteration(cb_handle *h);                                  /* main.c:2006-2028  */
 /* ANAFLAG 3: the member-end yield flags forces_fr mutates (main.c:802, frame.c:1184-1268):

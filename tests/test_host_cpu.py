@@ -242,3 +242,77 @@ def test_host_csc_solver_services_match_skyline(ref):
         assert np.array_equal(B.indices, A.indices) and np.array_equal(B.data, Ax2)
         assert np.abs(q2 - q).max() <= 1e-13 * np.abs(q).max()
         hl.cb_csc_solver_destroy(S)
+
+
+def test_partition_model_generic():
+    """partition_model (frames / shells / trusses by joint ranges): global numbering kept, halo
+    complete, every element owned once, per-element arrays cut consistently with the type offsets"""
+    from cubens_b200 import meshgen
+    from cubens_b200.partition import partition_model
+    for m, key, k in ((meshgen.lattice_model(3, ANAFLAG=3), "fr", 14), (meshgen.plate_model(6, 5, z_bump=0.05), "sh", 18),
+                      (meshgen.truss_model(3), "tr", 6)):
+        ne = {"fr": m.NE_FR, "sh": m.NE_SH, "tr": m.NE_TR}[key]
+        for world in (2, 3):
+            own_total, cover = 0, np.zeros(m.NJ, dtype=int)
+            for r in range(world):
+                s, (j0, j1), ids = partition_model(m, world, r)
+                cover[j0:j1] += 1
+                assert s.NEQ == m.NEQ and s.jcode is m.jcode and s.x is m.x
+                gid = ids[key]
+                assert np.all(np.diff(gid) > 0)
+                own_total += int(ids["own_" + key].sum())
+                assert np.array_equal(s.mcode, m.mcode.reshape(-1, k)[gid].reshape(-1))
+                nn = 3 if key == "sh" else 2
+                conn = m.minc.reshape(-1, nn)
+                need = np.flatnonzero(np.any((conn - 1 >= j0) & (conn - 1 < j1), axis=1))
+                assert np.array_equal(need, gid)
+                assert np.array_equal(s.minc.reshape(-1, nn), conn[gid])
+                off = {"tr": 0, "fr": m.NE_TR, "sh": m.NE_TR + m.NE_FR}[key]
+                assert np.array_equal(s.emod, m.emod[off + gid])
+                if key == "fr":
+                    assert np.array_equal(s.auxpt.reshape(-1, 3), m.auxpt.reshape(-1, 3)[gid])
+                    assert np.array_equal(s.c2.reshape(-1, 3), m.c2[m.NE_TR:].reshape(-1, 3)[gid])
+                    assert np.array_equal(s.llength, m.llength[m.NE_TR + gid])
+                if key == "sh":
+                    assert np.array_equal(s.xlocal.reshape(-1, 3), m.xlocal.reshape(-1, 3)[gid])
+                    assert np.array_equal(s.c3.reshape(-1, 3), m.c3.reshape(-1, 3)[gid])
+            assert np.all(cover == 1) and own_total == ne
+
+
+TRIP_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.path.join(%(root)r, "cu-bens_b200", "python"))
+import torch.distributed as dist
+from cubens_b200.partition import TripExchange
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+BIG = 0x7fffffff
+
+
+class FakeAsm:
+    """stands in for the device handle: rank 1 holds tripping member 17 (code 1, factor 0.25) and
+    member 40, rank 0 holds member 23; shells trip on rank 0 only"""
+    def update_forces_begin(self, dd, dlpf, itecnt):
+        return (23, 5) if rank == 0 else (17, BIG)
+    def update_forces_end(self, ffr, fsh, dlpf, want_f):
+        assert (ffr, fsh) == (17, 5), (ffr, fsh)
+        holds = rank == 1
+        return None, (1 if holds else 0), 1, (dlpf * 0.25 if holds else dlpf)
+
+
+f, fr, sh, dl = TripExchange(FakeAsm(), dist).update_forces(None, dlpf=0.5, want_f=False)
+assert (fr, sh, dl) == (1, 1, 0.125), (fr, sh, dl)
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_trip_exchange_gloo_world2(tmp_path):
+    """the ANAFLAG 3 exchange of cb_update_forces_begin / _end under torch.distributed (gloo, 2 ranks)"""
+    script = tmp_path / "t.py"
+    script.write_text(TRIP_WORKER % {"root": ROOT})
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+                          "29733", str(script)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2

@@ -191,7 +191,9 @@ __device__ __noinline__ void frame_block(const CbStiffArgs &A, int e, int a, int
 // is static, so it lives in registers and the three quarters of it this block does not need are
 // never computed (the generic version above keeps it in local memory: 4 KB of stack per thread).
 // Members with end releases (static condensation, runtime pivots) take the generic path.
-template <int LA, int LB, bool PL>
+// OFF = false: the model has no member-end offsets (CbDev::fr_simple) - the rigid-link branch and its
+// osflag load are compiled out.
+template <int LA, int LB, bool PL, bool OFF = true>
 __device__ __noinline__ void frame_block_t(const CbStiffArgs &A, int e, double *stg, int str)
 {
     double k[14][14], eft[14];
@@ -232,7 +234,7 @@ __device__ __noinline__ void frame_block_t(const CbStiffArgs &A, int e, double *
                 K[3 * p + i][j] = R[i] * W[3 * p][j] + R[3 + i] * W[3 * p + 1][j] + R[6 + i] * W[3 * p + 2][j];
         K[6][j] = W[6][j];
     }
-    if (A.d.fr_osflag[e] != 0) {
+    if (OFF && A.d.fr_osflag[e] != 0) {
         const double *oa = A.d.fr_offset + (long)e * 6 + 3 * LA, *ob = A.d.fr_offset + (long)e * 6 + 3 * LB;
         const double Sa[3][3] = {{0, oa[2], -oa[1]}, {-oa[2], 0, oa[0]}, {oa[1], -oa[0], 0}};
         const double Sb[3][3] = {{0, ob[2], -ob[1]}, {-ob[2], 0, ob[0]}, {ob[1], -ob[0], 0}};
@@ -466,8 +468,11 @@ __device__ __noinline__ int mass_block_stage(const CbStiffArgs &A, const CbContr
 }
 
 // SHELL_ONLY: the model holds nothing but DKT shells - the other element branches are compiled
-// out so that they cannot cost the hot configuration registers
-template <int ND, bool SHELL_ONLY>
+// out so that they cannot cost the hot configuration registers.  FRAME_SIMPLE: nothing but frames
+// without end releases, rigid offsets or plasticity (CbDev::fr_simple, BASELINE config 4): no
+// dependent load of the release flags ahead of the element data, no generic 14x14 path (4 KB of
+// stack), no mixed-DOF reduction.
+template <int ND, bool SHELL_ONLY, bool FRAME_SIMPLE = false>
 __global__ void __launch_bounds__(CB_TILE_T, (ND <= 6) ? 4 : 3)
 k_assemble_tiles(CbStiffArgs A)
 {
@@ -486,7 +491,7 @@ k_assemble_tiles(CbStiffArgs A)
     CbContrib ct{}; ct.type = 0xff;
     if (t < tl.ns) ct = A.tcontribs[tl.t0 + t];
     ShellIn in;
-    if (ND >= 6 && ct.type == CB_T_SHELL && !A.mass_mode) shell_load(A, ct, (long)tl.c0 + ct.pad, in);
+    if (!FRAME_SIMPLE && ND >= 6 && ct.type == CB_T_SHELL && !A.mass_mode) shell_load(A, ct, (long)tl.c0 + ct.pad, in);
 
     for (;;) {
         const long next = tile + gridDim.x;
@@ -499,7 +504,13 @@ k_assemble_tiles(CbStiffArgs A)
         if (ct.type != 0xff) {
             double *stg = stage + ct.pad;
             const int col = ct.pad;             // column of `stage` / entry of ndof: reference order
-            if (A.mass_mode) {
+            if constexpr (FRAME_SIMPLE) {
+                if (ct.a == 0) {
+                    if (ct.b == 0) frame_block_t<0, 0, false, false>(A, ct.e, stg, STR); else frame_block_t<0, 1, false, false>(A, ct.e, stg, STR);
+                } else {
+                    if (ct.b == 0) frame_block_t<1, 0, false, false>(A, ct.e, stg, STR); else frame_block_t<1, 1, false, false>(A, ct.e, stg, STR);
+                }
+            } else if (A.mass_mode) {
                 ndof[col] = (unsigned char)mass_block_stage<ND>(A, ct, stg);
             } else if (ct.type == CB_T_SHELL) {
                 if constexpr (ND >= 6) {
@@ -554,7 +565,7 @@ k_assemble_tiles(CbStiffArgs A)
         CbContrib ctn{}; ctn.type = 0xff;
         if (has_next && t < tln.ns) ctn = A.tcontribs[tln.t0 + t];
         __syncthreads();
-        if (ND >= 6 && ctn.type == CB_T_SHELL && !A.mass_mode) shell_load(A, ctn, (long)tln.c0 + ctn.pad, in);
+        if (!FRAME_SIMPLE && ND >= 6 && ctn.type == CB_T_SHELL && !A.mass_mode) shell_load(A, ctn, (long)tln.c0 + ctn.pad, in);
 
         // ---- phase 2: segmented reduction over the sorted contribution list, one thread per
         // (joint-pair block, column): ND rows of `stage` summed over the block's contributions in
@@ -566,7 +577,7 @@ k_assemble_tiles(CbStiffArgs A)
             const int p = it / ND, c = it - p * ND;
             const CbTPair pr = spair[p];
             constexpr unsigned FULL = (1u << ND) - 1u;
-            if (pr.maskA == FULL && pr.maskB == FULL && !A.mixed) {
+            if (pr.maskA == FULL && pr.maskB == FULL && (FRAME_SIMPLE || !A.mixed)) {
                 const double *src = stage + c * STR + pr.cs;
                 double acc[ND];
 #pragma unroll
@@ -588,7 +599,7 @@ k_assemble_tiles(CbStiffArgs A)
                     const double *src = stage + (r * ND + c) * STR + pr.cs;
                     double sum = 0.0;
                     for (int q = 0; q < pr.cnt; ++q)
-                        if (!A.mixed || (r < ndof[pr.cs + q] && c < ndof[pr.cs + q])) sum += src[q];
+                        if (FRAME_SIMPLE || !A.mixed || (r < ndof[pr.cs + q] && c < ndof[pr.cs + q])) sum += src[q];
                     dst[rr++] = sum;
                 }
             }
@@ -1024,14 +1035,14 @@ k_assemble_blocks(CbStiffArgs A)
     }
 }
 
-template <int ND, bool SHELL_ONLY>
+template <int ND, bool SHELL_ONLY, bool FRAME_SIMPLE = false>
 static int launch_tiles(const CbStiffArgs &a, cudaStream_t s)
 {
     const size_t smem = (size_t)(((ND * ND * (CB_TILE_T + 1) + 1) & ~1) + a.tile_smem_out) * sizeof(double) +
                         CB_TILE_T * sizeof(CbTPair) + CB_TILE_T;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_assemble_tiles<ND, SHELL_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(k_assemble_tiles<ND, SHELL_ONLY, FRAME_SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  200 * 1024) != cudaSuccess)
             return 1;
         configured = true;
@@ -1040,12 +1051,12 @@ static int launch_tiles(const CbStiffArgs &a, cudaStream_t s)
     int per_sm = 0, dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_tiles<ND, SHELL_ONLY>, CB_TILE_T, smem) !=
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_tiles<ND, SHELL_ONLY, FRAME_SIMPLE>, CB_TILE_T, smem) !=
             cudaSuccess || per_sm < 1)
         per_sm = 1;
     long grid = (long)per_sm * nsm;                    // persistent: one wave of resident CTAs
     if (grid > a.ntiles) grid = a.ntiles;
-    k_assemble_tiles<ND, SHELL_ONLY><<<(unsigned)grid, CB_TILE_T, smem, s>>>(a);
+    k_assemble_tiles<ND, SHELL_ONLY, FRAME_SIMPLE><<<(unsigned)grid, CB_TILE_T, smem, s>>>(a);
     return cudaGetLastError() != cudaSuccess;
 }
 
@@ -1067,5 +1078,7 @@ int cbk_stiff(const CbStiffArgs &a, cudaStream_t s, long *launches)
     const bool shell_only = a.d.NE_SH && !a.d.NE_TR && !a.d.NE_FR && !a.d.NE_BR && !a.mixed;
     if (a.max_dof <= 3) return launch_tiles<3, false>(a, s);
     if (a.max_dof <= 6) return shell_only ? launch_tiles<6, true>(a, s) : launch_tiles<6, false>(a, s);
-    return launch_tiles<7, false>(a, s);
+    const bool frame_simple = a.d.fr_simple && a.d.NE_FR && !a.d.NE_SH && !a.d.NE_TR && !a.d.NE_BR && !a.mixed &&
+                              !a.mass_mode;
+    return frame_simple ? launch_tiles<7, false, true>(a, s) : launch_tiles<7, false>(a, s);
 }

@@ -217,6 +217,7 @@ struct CbStiffArgs {
     int max_dof;             // 3, 6 or 7: largest DOF count per joint among the model's elements
     int mixed;               // element types with different DOF counts per joint are present
     double *out;             // Ax or ss
+    int out_par;             // parity of `out` in 16-byte units (Ax.p + 1 double when most blocks sit on odd indices)
     const long *maxa;        // device copy (skyline mode) or nullptr
     int skyline;
     // mass mode (cb_mass with bricks): the same tiles assemble the full-order mass matrix of the

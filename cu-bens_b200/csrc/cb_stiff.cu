@@ -571,7 +571,7 @@ k_assemble_tiles(CbStiffArgs A)
         // (joint-pair block, column): ND rows of `stage` summed over the block's contributions in
         // reference order, written as one contiguous column run of the tile's output image.  The
         // image is shifted by the parity of out0 so phase 3 can use aligned 16-byte accesses.
-        const int shift = (int)(tl.out0 & 1);
+        const int shift = (int)((tl.out0 + A.out_par) & 1);
         const int nitems = tl.np * ND;
         for (int it = t; it < nitems; it += CB_TILE_T) {
             const int p = it / ND, c = it - p * ND;
@@ -855,7 +855,7 @@ k_assemble_shell_tiles(CbStiffArgs A)
         }
         if (has_next3 && t < 10)
             CB_CPA(4, "ca", sring + ((it + 3) & 3) * 12 + t, reinterpret_cast<const int *>(A.tiles2 + next + 2 * G) + t);
-        const int shift = (int)(tl.out0 & 1);
+        const int shift = (int)((tl.out0 + A.out_par) & 1);
         const CbTPair *spair = spair2 + buf * CB_TILE_T;
         const double *kr0 = skrec + buf * CB_T2_ELEMS * CB_SH_KREC;
         const bool active = t < tl.nw;

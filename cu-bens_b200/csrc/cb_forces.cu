@@ -1127,44 +1127,52 @@ k_frame_forces_simple(CbDev d, const double *__restrict__ x_new, const double *_
 {
     const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (e >= d.NE_FR) return;
-    const double *fc = d.fr_const + e * CB_FR_CONST;
-    const int nj = d.fr_nodes[e * 2], nk = d.fr_nodes[e * 2 + 1];
+    const int2 nn = reinterpret_cast<const int2 *>(d.fr_nodes)[e];
+    const int nj = nn.x, nk = nn.y;
     double def[14];
     {   // ---- phase 1: def = (k_e + k_g) T_ip DD (frame.c:1013-1060) ------------------------------
-        double DD12[14], dl[14], eft[14], Rp[CB_FR_FRAME];
+        double DD12[14], dl[14], eft[14], Rp[CB_FR_FRAME], fc[10];
+        ldv2<CB_FR_FRAME>(frame_ip + e * CB_FR_FRAME, Rp);
+        ldv2<10>(d.fr_const + e * CB_FR_CONST, fc);
+        {
+            const int4 a0 = reinterpret_cast<const int4 *>(d.jc + (long)nj * 8)[0], a1 = reinterpret_cast<const int4 *>(d.jc + (long)nj * 8)[1];
+            const int4 b0 = reinterpret_cast<const int4 *>(d.jc + (long)nk * 8)[0], b1 = reinterpret_cast<const int4 *>(d.jc + (long)nk * 8)[1];
+            const int qa[7] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z}, qb[7] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z};
 #pragma unroll
-        for (int i = 0; i < CB_FR_FRAME; ++i) Rp[i] = frame_ip[e * CB_FR_FRAME + i];
-#pragma unroll
-        for (int r = 0; r < 7; ++r) {
-            int q = d.jc[(long)nj * 8 + r]; DD12[r] = q ? dd[q - 1] : 0.0;
-            q = d.jc[(long)nk * 8 + r];     DD12[7 + r] = q ? dd[q - 1] : 0.0;
+            for (int r = 0; r < 7; ++r) {
+                DD12[r] = qa[r] ? dd[qa[r] - 1] : 0.0;
+                DD12[7 + r] = qb[r] ? dd[qb[r] - 1] : 0.0;
+            }
         }
         frame_T_apply(Rp, DD12, dl);
+        {   // the geometric tangent reads P = eft[7], M4, M5, M10, M11, M12 only
+            double a[14], b[14];
 #pragma unroll
-        for (int i = 0; i < 14; ++i) eft[i] = 0;
+            for (int i = 0; i < 14; ++i) { a[i] = 0; b[i] = 0; eft[i] = 0; }
+            ldv2<2>(ef_ip + e * 14 + 4, a + 4);   ldv2<2>(efFE_ip + e * 14 + 4, b + 4);
+            ldv2<2>(ef_ip + e * 14 + 6, a + 6);   ldv2<2>(efFE_ip + e * 14 + 6, b + 6);
+            ldv2<4>(ef_ip + e * 14 + 10, a + 10); ldv2<4>(efFE_ip + e * 14 + 10, b + 10);
 #pragma unroll
-        for (int i = 4; i < 13; ++i)      // the geometric tangent reads P, M4, M5, M10, M11, M12 only
-            if (i == 4 || i == 5 || i == 7 || i >= 10) eft[i] = ef_ip[e * 14 + i] + efFE_ip[e * 14 + i];
+            for (int i = 4; i < 13; ++i)
+                if (i == 4 || i == 5 || i == 7 || i >= 10) eft[i] = a[i] + b[i];
+        }
         if (d.ANAFLAG == 2) frame_def_direct<true>(fc, eft, Rp[9], dl, def);
         else frame_def_direct<false>(fc, eft, Rp[9], dl, def);
     }
     CB_PHASE_FENCE();
     double Ri[CB_FR_FRAME], Rp[CB_FR_FRAME];
-#pragma unroll
-    for (int i = 0; i < CB_FR_FRAME - 1; ++i) Rp[i] = frame_ip[e * CB_FR_FRAME + i];
+    ldv2<CB_FR_FRAME>(frame_ip + e * CB_FR_FRAME, Rp);
     if (!INPLACE) {   // ---- phase 2: updatc, frame block (misc.c:108-147) ---------------------------
-        double xa[3], xb[3];
+        double xab[6], aux[4];
 #pragma unroll
-        for (int m = 0; m < 3; ++m) {
-            xa[m] = x_new[(long)nj * 3 + m]; xb[m] = x_new[(long)nk * 3 + m];
-            xfr_i[e * 6 + m] = xa[m]; xfr_i[e * 6 + 3 + m] = xb[m];
-        }
-        frame_triad(xa, xb, fc + 10, Ri);
-#pragma unroll
-        for (int i = 0; i < CB_FR_FRAME; ++i) frame_i[e * CB_FR_FRAME + i] = Ri[i];
+        for (int m = 0; m < 3; ++m) { xab[m] = x_new[(long)nj * 3 + m]; xab[3 + m] = x_new[(long)nk * 3 + m]; }
+        stv2<6>(xfr_i + e * 6, xab);
+        ldv2<4>(d.fr_const + e * CB_FR_CONST + 10, aux);
+        frame_triad(xab, xab + 3, aux, Ri);
+        stv2<CB_FR_FRAME>(frame_i + e * CB_FR_FRAME, Ri);
     } else {
 #pragma unroll
-        for (int i = 0; i < CB_FR_FRAME - 1; ++i) Ri[i] = Rp[i];
+        for (int i = 0; i < CB_FR_FRAME; ++i) Ri[i] = Rp[i];
     }
     // M = T_i T_ip^T: four copies of R_i R_ip^T and 1 on the warping DOFs (frame.c:1078-1086)
     double M[3][3];
@@ -1178,9 +1186,9 @@ k_frame_forces_simple(CbDev d, const double *__restrict__ x_new, const double *_
     // forces (frame.c:1090-1155); with INPLACE later rows see the rows already rewritten
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
-        double cur[14], out[14];
-#pragma unroll
-        for (int i = 0; i < 14; ++i) cur[i] = pass == 0 ? ef_ip[e * 14 + i] : efFE_ip[e * 14 + i];
+        double cur[14], out[14], ref[14];
+        ldv2<14>((pass == 0 ? ef_ip : efFE_ip) + e * 14, cur);
+        if (pass == 1 && addref) ldv2<14>(d.fr_efFE_ref + e * 14, ref);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int o = (g < 2) ? 3 * g : 7 + 3 * (g - 2);
@@ -1190,27 +1198,21 @@ k_frame_forces_simple(CbDev d, const double *__restrict__ x_new, const double *_
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
                     v[c] = pass == 0 ? (cur[o + c] + def[o + c])
-                                     : (addref ? (cur[o + c] + dlpf * d.fr_efFE_ref[e * 14 + o + c]) : cur[o + c]);
+                                     : (addref ? (cur[o + c] + dlpf * ref[o + c]) : cur[o + c]);
                 out[o + r] = dot3(M[r], v);
                 if (INPLACE) cur[o + r] = out[o + r];
             }
         }
 #pragma unroll
         for (int w = 6; w < 14; w += 7) {
-            const double v = pass == 0 ? (cur[w] + def[w])
-                                       : (addref ? (cur[w] + dlpf * d.fr_efFE_ref[e * 14 + w]) : cur[w]);
+            const double v = pass == 0 ? (cur[w] + def[w]) : (addref ? (cur[w] + dlpf * ref[w]) : cur[w]);
             out[w] = 0.0 + 1.0 * v;
         }
-#pragma unroll
-        for (int i = 0; i < 14; ++i) {
-            if (pass == 0) ef_i[e * 14 + i] = out[i];
-            else efFE_i[e * 14 + i] = out[i];
-        }
+        stv2<14>((pass == 0 ? ef_i : efFE_i) + e * 14, out);
         if (pass == 0) {
             double EF[14];
             frame_Tt_apply(Ri, out, EF);
-#pragma unroll
-            for (int i = 0; i < 14; ++i) d.fr_fg[e * 14 + i] = EF[i];
+            stv2<14>(d.fr_fg + e * 14, EF);
         }
         CB_PHASE_FENCE();
     }

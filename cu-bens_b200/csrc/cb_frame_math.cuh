@@ -81,6 +81,26 @@ __device__ __forceinline__ void frame_geometric(double (*k)[14], const double *e
 #undef CB_SUB
 }
 
+// the per-member records are AoS with 16-byte multiples as strides (80, 112, 128, 48 bytes): 16-byte
+// vector accesses halve the sectors each request touches
+template <int N>
+__device__ __forceinline__ void ldv2(const double *p, double *r)
+{
+    static_assert(N % 2 == 0, "even record length");
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const double2 v = reinterpret_cast<const double2 *>(p)[i];
+        r[2 * i] = v.x; r[2 * i + 1] = v.y;
+    }
+}
+template <int N>
+__device__ __forceinline__ void stv2(double *p, const double *r)
+{
+    static_assert(N % 2 == 0, "even record length");
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) reinterpret_cast<double2 *>(p)[i] = make_double2(r[2 * i], r[2 * i + 1]);
+}
+
 // ---- packed variants for the force path: elastic + geometric tangent in a thread-private column of
 // SHARED memory, upper triangle only (both are bitwise symmetric: every entry and its mirror get
 // the same values in the same order, frame.c:364-579), entry (i, j) of thread t at

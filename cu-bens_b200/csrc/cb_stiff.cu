@@ -196,14 +196,19 @@ __device__ __noinline__ void frame_block(const CbStiffArgs &A, int e, int a, int
 template <int LA, int LB, bool PL, bool OFF = true>
 __device__ __noinline__ void frame_block_t(const CbStiffArgs &A, int e, double *stg, int str)
 {
-    double k[14][14], eft[14];
-    const double *fr = A.fr_frame + (long)e * CB_FR_FRAME;
-    const double *fc = A.d.fr_const + (long)e * CB_FR_CONST;
+    double k[14][14], eft[14], fr[CB_FR_FRAME], fc[10];
+    {
+        double ea[14], eb[14];                        // 16-byte vector loads of the AoS records
+        ldv2<CB_FR_FRAME>(A.fr_frame + (long)e * CB_FR_FRAME, fr);
+        ldv2<10>(A.d.fr_const + (long)e * CB_FR_CONST, fc);
+        ldv2<14>(A.fr_ef + (long)e * 14, ea);
+        ldv2<14>(A.fr_efFE + (long)e * 14, eb);
 #pragma unroll
-    for (int i = 0; i < 14; ++i) {
+        for (int i = 0; i < 14; ++i) {
 #pragma unroll
-        for (int j = 0; j < 14; ++j) k[i][j] = 0;
-        eft[i] = A.fr_ef[(long)e * 14 + i] + A.fr_efFE[(long)e * 14 + i];
+            for (int j = 0; j < 14; ++j) k[i][j] = 0;
+            eft[i] = ea[i] + eb[i];
+        }
     }
     frame_elastic_rcp(k, fc);
     if (A.d.ANAFLAG >= 2) frame_geometric_rcp(k, eft, fr[9], fc[2], fc[8]);
@@ -502,9 +507,13 @@ k_assemble_tiles(CbStiffArgs A)
 
         // ---- phase 1: one contribution per thread -> its column of `stage` ---------------------
         if (ct.type != 0xff) {
-            double *stg = stage + ct.pad;
+            // FRAME_SIMPLE: the block goes to the column of the THREAD (consecutive lanes, consecutive
+            // doubles: conflict-free stores; the planner's slots are not in column order) and ndof,
+            // which this instantiation does not need, maps reference-order columns to thread columns
+            double *stg = stage + (FRAME_SIMPLE ? t : ct.pad);
             const int col = ct.pad;             // column of `stage` / entry of ndof: reference order
             if constexpr (FRAME_SIMPLE) {
+                ndof[col] = (unsigned char)t;
                 if (ct.a == 0) {
                     if (ct.b == 0) frame_block_t<0, 0, false, false>(A, ct.e, stg, STR); else frame_block_t<0, 1, false, false>(A, ct.e, stg, STR);
                 } else {
@@ -578,13 +587,15 @@ k_assemble_tiles(CbStiffArgs A)
             const CbTPair pr = spair[p];
             constexpr unsigned FULL = (1u << ND) - 1u;
             if (pr.maskA == FULL && pr.maskB == FULL && (FRAME_SIMPLE || !A.mixed)) {
-                const double *src = stage + c * STR + pr.cs;
+                const double *src = stage + c * STR + (FRAME_SIMPLE ? 0 : pr.cs);
                 double acc[ND];
+                const int s0 = FRAME_SIMPLE ? ndof[pr.cs] : 0;
 #pragma unroll
-                for (int r = 0; r < ND; ++r) acc[r] = src[r * ND * STR];
+                for (int r = 0; r < ND; ++r) acc[r] = src[r * ND * STR + s0];
                 for (int q = 1; q < pr.cnt; ++q) {
+                    const int sq = FRAME_SIMPLE ? ndof[pr.cs + q] : q;
 #pragma unroll
-                    for (int r = 0; r < ND; ++r) acc[r] += src[r * ND * STR + q];
+                    for (int r = 0; r < ND; ++r) acc[r] += src[r * ND * STR + sq];
                 }
                 double *dst = obuf + shift + pr.rel + c * pr.colh;
 #pragma unroll
@@ -596,10 +607,11 @@ k_assemble_tiles(CbStiffArgs A)
                 int rr = 0;
                 for (int r = 0; r < ND; ++r) {
                     if (!((pr.maskA >> r) & 1)) continue;
-                    const double *src = stage + (r * ND + c) * STR + pr.cs;
+                    const double *src = stage + (r * ND + c) * STR + (FRAME_SIMPLE ? 0 : pr.cs);
                     double sum = 0.0;
                     for (int q = 0; q < pr.cnt; ++q)
-                        if (FRAME_SIMPLE || !A.mixed || (r < ndof[pr.cs + q] && c < ndof[pr.cs + q])) sum += src[q];
+                        if (FRAME_SIMPLE) sum += src[ndof[pr.cs + q]];
+                        else if (!A.mixed || (r < ndof[pr.cs + q] && c < ndof[pr.cs + q])) sum += src[q];
                     dst[rr++] = sum;
                 }
             }

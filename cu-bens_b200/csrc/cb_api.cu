@@ -1175,13 +1175,22 @@ k_resid_sums1(long e0, long e1, double lpf, const double *__restrict__ q, const 
     }
     if (threadIdx.x < 3) part[blockIdx.x * 3 + threadIdx.x] = sh[threadIdx.x][0];
 }
-__global__ void k_resid_sums2(int nblk, const double *__restrict__ part, double *__restrict__ out)
+// second stage: 256 threads, fixed strided order + fixed tree (bit-reproducible run to run); the
+// serial version (3 threads x 592 dependent L2 round trips) cost more than the first stage
+__global__ void __launch_bounds__(256)
+k_resid_sums2(int nblk, const double *__restrict__ part, double *__restrict__ out)
 {
-    if (threadIdx.x < 3) {
-        double s = 0;
-        for (int b = 0; b < nblk; ++b) s += part[b * 3 + threadIdx.x];
-        out[threadIdx.x] = s;
+    __shared__ double sh[3][256];
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (int b = threadIdx.x; b < nblk; b += 256) { a0 += part[b * 3]; a1 += part[b * 3 + 1]; a2 += part[b * 3 + 2]; }
+    sh[0][threadIdx.x] = a0; sh[1][threadIdx.x] = a1; sh[2][threadIdx.x] = a2;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+            for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+        __syncthreads();
     }
+    if (threadIdx.x < 3) out[threadIdx.x] = sh[threadIdx.x][0];
 }
 
 __global__ void k_axpy1(long n, const double *__restrict__ x, double *__restrict__ y)
@@ -1651,7 +1660,7 @@ extern "C" int cb_residual_sums(cb_handle *h, double lpf)
     cudaSetDevice(h->fl.device);
     k_resid_sums1<<<CB_SUM_BLOCKS, 256, 0, h->stream>>>(h->eq0, h->eq1, lpf, h->qvec.p, h->f_temp.p,
                                                          h->dd.p, h->sums_part.p);
-    k_resid_sums2<<<1, 32, 0, h->stream>>>(CB_SUM_BLOCKS, h->sums_part.p, h->sums.p);
+    k_resid_sums2<<<1, 256, 0, h->stream>>>(CB_SUM_BLOCKS, h->sums_part.p, h->sums.p);
     h->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return CB_OK;

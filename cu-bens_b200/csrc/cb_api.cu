@@ -75,6 +75,7 @@ struct Plan {
     long npairs = 0;
     DevBuf<CbTile> tiles;
     DevBuf<CbContrib> tcontribs;
+    DevBuf<CbTDst> tdst;
     DevBuf<CbTPair> tpairs;
     long ntiles = 0;
     DevBuf<CbTile2> tiles2; DevBuf<CbWork> works; DevBuf<CbTPair> tpairs2; DevBuf<int32_t> telems;
@@ -536,7 +537,7 @@ extern "C" void cb_destroy(cb_handle *h)
                                &h->fr_mendrel, &h->br_nodes, &h->node_cstart})
         b->release();
     h->corners.release(); h->contribs.release(); h->plan_csc.pairs.release();
-    h->plan_csc.tiles.release(); h->plan_csc.tpairs.release(); h->plan_csc.tcontribs.release();
+    h->plan_csc.tiles.release(); h->plan_csc.tpairs.release(); h->plan_csc.tcontribs.release(); h->plan_csc.tdst.release();
     h->plan_csc.tiles2.release(); h->plan_csc.works.release(); h->plan_csc.tpairs2.release();
     h->plan_csc.telems.release();
     h->plan_sky.pairs.release(); h->Ap.release(); h->Ai.release(); h->maxa.release();
@@ -726,10 +727,16 @@ static int build_plan(cb_handle *h)
     // block (element type, local joints) so that a warp's lanes run the same code; a group that
     // would straddle a warp boundary starts at the next one when the tile has the lanes to spare
     std::vector<CbContrib> tcontribs;
+    std::vector<CbTDst> tdst;
     if (tiles_ok) {
         tcontribs.reserve(contribs.size() + contribs.size() / 8);
+        tdst.reserve(contribs.size() + contribs.size() / 8);
         std::vector<int> idx;
+        std::vector<int> pmap;
         for (CbTile &tl : tiles) {
+            pmap.assign(tl.nc, 0);
+            for (int p = 0; p < tl.np; ++p)
+                for (int q = 0; q < tpairs[tl.p0 + p].cnt; ++q) pmap[tpairs[tl.p0 + p].cs + q] = p;
             idx.resize(tl.nc);
             for (int i = 0; i < tl.nc; ++i) idx[i] = i;
             auto kind = [&](int i) {
@@ -754,11 +761,16 @@ static int build_plan(cb_handle *h)
             CbContrib idle{}; idle.type = 0xff;
             for (auto &g : groups) {
                 if (align && g.second <= 32 && (slot & 31) + g.second > 32)
-                    while (slot & 31) { tcontribs.push_back(idle); ++slot; }
+                    while (slot & 31) { tcontribs.push_back(idle); tdst.push_back(CbTDst{}); ++slot; }
                 for (int i = 0; i < g.second; ++i) {
                     CbContrib c = contribs[tl.c0 + idx[g.first + i]];
                     c.pad = (uint8_t)idx[g.first + i];
                     tcontribs.push_back(c); ++slot;
+                    const CbTPair &tp = tpairs[tl.p0 + pmap[idx[g.first + i]]];
+                    CbTDst d{};
+                    d.rel = tp.rel; d.colh = (uint16_t)tp.colh;
+                    d.direct = (tp.cnt == 1 && tp.maskA == 0x7f && tp.maskB == 0x7f && tp.colh < 65536) ? 1 : 0;
+                    tdst.push_back(d);
                 }
             }
             tl.ns = (uint16_t)slot;
@@ -776,6 +788,15 @@ static int build_plan(cb_handle *h)
         h->max_dof = top <= 3 ? 3 : (top <= 6 ? 6 : 7);
         h->mixed = (has3 && h->max_dof != 3) || (has6 && h->max_dof != 6) || (has7 && h->max_dof != 7);
     }
+    {   // Blocks whose columns start on an odd Ax index fall off the tile kernels' 16-byte store path.
+        // Which parity the bulk of the blocks has depends on the free DOFs of the joints ahead of them
+        // (a partition that starts on a pinned edge joint had ALL interior blocks odd: K_t 0.81 ->
+        // 0.96 ms); shift the whole matrix by one double when the odd ones are the majority.
+        long even = 0, odd = 0;
+        for (const CbPair &p : pairs_csc)
+            if (!(p.colh & 1)) ((p.off & 1) ? odd : even) += p.ccount;
+        h->ax_pad = odd > even ? 1 : 0;
+    }
     // ---- shell-only models: the "duo" tile plan of k_assemble_shell_tiles -------------------
     std::vector<CbTile2> tiles2; std::vector<CbWork> works; std::vector<CbTPair> tp2;
     std::vector<int32_t> telems;
@@ -792,7 +813,7 @@ static int build_plan(cb_handle *h)
             // partial sums of a group (kind 2 leader + kind 3 followers) sit in consecutive
             // lanes of one warp; idle items (kind 4) pad a warp whose tail is too short for a group.
             {
-                const int shift = (int)(cur.out0 & 1);
+                const int shift = (int)((cur.out0 + h->ax_pad) & 1);
                 std::vector<CbWork> src(works.begin() + cur.w0, works.end());
                 const int ns = (int)src.size();
                 auto key_of = [&](const CbWork &w) {
@@ -928,19 +949,10 @@ static int build_plan(cb_handle *h)
         std::stable_sort(v.begin(), v.end(),
                          [](const CbPair &a, const CbPair &b) { return a.ccount > b.ccount; });
     };
-    {   // Blocks whose columns start on an odd Ax index fall off the tile kernels' 16-byte store path.
-        // Which parity the bulk of the blocks has depends on the free DOFs of the joints ahead of them
-        // (a partition that starts on a pinned edge joint had ALL interior blocks odd: K_t 0.81 ->
-        // 0.96 ms); shift the whole matrix by one double when the odd ones are the majority.
-        long even = 0, odd = 0;
-        for (const CbPair &p : pairs_csc)
-            if (!(p.colh & 1)) ((p.off & 1) ? odd : even) += p.ccount;
-        h->ax_pad = odd > even ? 1 : 0;
-    }
     bucket(pairs_sky);
     if (tiles_ok) pairs_csc.clear(); else { bucket(pairs_csc); tiles.clear(); tpairs.clear(); }
     if (plan2_ok) { tiles.clear(); tpairs.clear(); }
-    if (tiles.empty()) tcontribs.clear();
+    if (tiles.empty()) { tcontribs.clear(); tdst.clear(); }
 
     if (h->node_cstart.upload(cstart) || h->corners.upload(corners) || h->contribs.upload(contribs))
         return CB_ERR_CUDA;
@@ -948,7 +960,7 @@ static int build_plan(cb_handle *h)
         if (h->plan_csc.pairs.upload(pairs_csc)) return CB_ERR_CUDA;
         h->plan_csc.npairs = (long)pairs_csc.size();
         if (h->plan_csc.tiles.upload(tiles) || h->plan_csc.tpairs.upload(tpairs) ||
-            h->plan_csc.tcontribs.upload(tcontribs))
+            h->plan_csc.tcontribs.upload(tcontribs) || h->plan_csc.tdst.upload(tdst))
             return CB_ERR_CUDA;
         h->plan_csc.ntiles = (long)tiles.size();
         if (h->plan_csc.tiles2.upload(tiles2) || h->plan_csc.works.upload(works) ||
@@ -970,7 +982,7 @@ static int build_plan(cb_handle *h)
     }
     h->map_bytes = (long)((pairs_csc.size() + pairs_sky.size()) * sizeof(CbPair) +
                           tiles.size() * sizeof(CbTile) + tpairs.size() * sizeof(CbTPair) +
-                          tcontribs.size() * sizeof(CbContrib) +
+                          tcontribs.size() * (sizeof(CbContrib) + sizeof(CbTDst)) +
                           tiles2.size() * sizeof(CbTile2) + works.size() * sizeof(CbWork) +
                           tp2.size() * sizeof(CbTPair) + telems.size() * sizeof(int32_t) +
                           contribs.size() * sizeof(CbContrib));
@@ -1135,7 +1147,7 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
     if (h->layout & CB_MAT_CSC) {
         a.pairs = h->plan_csc.pairs.p; a.npairs = h->plan_csc.npairs;
         a.tiles = h->plan_csc.ntiles ? h->plan_csc.tiles.p : nullptr; a.ntiles = h->plan_csc.ntiles;
-        a.tpairs = h->plan_csc.tpairs.p; a.kebc = h->sh_kebc.p; a.tcontribs = h->plan_csc.tcontribs.p;
+        a.tpairs = h->plan_csc.tpairs.p; a.kebc = h->sh_kebc.p; a.tcontribs = h->plan_csc.tcontribs.p; a.tdst = h->plan_csc.tdst.p;
         a.tiles2 = h->plan_csc.ntiles2 ? h->plan_csc.tiles2.p : nullptr; a.ntiles2 = h->plan_csc.ntiles2;
         a.works = (h->cls_on && h->works_cls.p) ? h->works_cls.p : h->plan_csc.works.p;
         a.tpairs2 = h->plan_csc.tpairs2.p; a.tile_elems = h->plan_csc.telems.p;
@@ -1435,7 +1447,7 @@ extern "C" int cb_mass(cb_handle *h)
         CbStiffArgs a{};
         a.d = d; a.x = h->x.p; a.sh_frame = h->sh_frame[0].p; a.contribs = h->contribs.p;
         a.tiles = h->plan_csc.tiles.p; a.ntiles = h->plan_csc.ntiles; a.tpairs = h->plan_csc.tpairs.p;
-        a.tcontribs = h->plan_csc.tcontribs.p; a.tile_smem_out = h->plan_csc.tile_smem_out;
+        a.tcontribs = h->plan_csc.tcontribs.p; a.tdst = h->plan_csc.tdst.p; a.tile_smem_out = h->plan_csc.tile_smem_out;
         a.max_dof = h->max_dof; a.mixed = h->mixed; a.out = h->Mx.p + h->ax_pad; a.out_par = h->ax_pad; a.mass_mode = 1;
         a.sh_dens = h->sh_dens.p;
         if (cbk_stiff(a, h->stream, &h->launches)) return fail(CB_ERR_CUDA, "mass assembly launch");

@@ -75,6 +75,14 @@ struct CbTPair {
     uint16_t pad;
 };
 
+// where a thread slot's block lands when it is its joint pair's ONLY contribution and every DOF of
+// both joints is free: straight in the tile's output image (frame-only tile kernel), no staging
+struct CbTDst {
+    int32_t rel;      // CbTPair::rel of the slot's joint pair
+    uint16_t colh;    // CbTPair::colh
+    uint16_t direct;  // 1: write the block at image[rel + j * colh + i]; 0: stage + reduce
+};
+
 // Per-element shell arrays read or written by one thread per element are stored component-major
 // ("SoA": component c of element e at [c*NE + e]) so that a warp's accesses are fully coalesced.
 #define SOA(p, comp, e, ne) (p)[(long)(comp) * (ne) + (e)]
@@ -210,6 +218,7 @@ struct CbStiffArgs {
     const CbContrib *contribs;
     const CbTile *tiles; long ntiles; const CbTPair *tpairs;
     const CbContrib *tcontribs;   // thread slots of the general tile kernel (see CbTile)
+    const CbTDst *tdst;           // [slot] direct-write target of the slot (see CbTDst)
     const double *kebc;      // DKT 3x3 sub-blocks in assembly order (static; layouts above)
     const CbTile2 *tiles2; long ntiles2; const CbWork *works; const CbTPair *tpairs2;
     const int32_t *tile_elems;

@@ -193,8 +193,10 @@ __device__ __noinline__ void frame_block(const CbStiffArgs &A, int e, int a, int
 // Members with end releases (static condensation, runtime pivots) take the generic path.
 // OFF = false: the model has no member-end offsets (CbDev::fr_simple) - the rigid-link branch and its
 // osflag load are compiled out.
+// Entry (i, j) of the block goes to stg[i * sr + j * sc]: a stage column (sr = 7 * STR, sc = STR) or
+// the tile's output image itself (sr = 1, sc = column height).
 template <int LA, int LB, bool PL, bool OFF = true>
-__device__ __noinline__ void frame_block_t(const CbStiffArgs &A, int e, double *stg, int str)
+__device__ __noinline__ void frame_block_t(const CbStiffArgs &A, int e, double *stg, int sr, int sc)
 {
     double k[14][14], eft[14], fr[CB_FR_FRAME], fc[10];
     {
@@ -257,7 +259,7 @@ __device__ __noinline__ void frame_block_t(const CbStiffArgs &A, int e, double *
 #pragma unroll
     for (int i = 0; i < 7; ++i)
 #pragma unroll
-        for (int j = 0; j < 7; ++j) stg[(i * 7 + j) * str] = K[i][j];
+        for (int j = 0; j < 7; ++j) stg[i * sr + j * sc] = K[i][j];
 }
 
 // K_ab (3x3) of 8-node brick e: 2x2x2 Gauss, B_a^T C B_b detJ (brick.c:79-397, jacob 541-699).
@@ -494,7 +496,8 @@ k_assemble_tiles(CbStiffArgs A)
     if (tile >= A.ntiles) return;
     CbTile tl = A.tiles[tile];
     CbContrib ct{}; ct.type = 0xff;
-    if (t < tl.ns) ct = A.tcontribs[tl.t0 + t];
+    CbTDst td{};
+    if (t < tl.ns) { ct = A.tcontribs[tl.t0 + t]; if (FRAME_SIMPLE) td = A.tdst[tl.t0 + t]; }
     ShellIn in;
     if (!FRAME_SIMPLE && ND >= 6 && ct.type == CB_T_SHELL && !A.mass_mode) shell_load(A, ct, (long)tl.c0 + ct.pad, in);
 
@@ -514,10 +517,13 @@ k_assemble_tiles(CbStiffArgs A)
             const int col = ct.pad;             // column of `stage` / entry of ndof: reference order
             if constexpr (FRAME_SIMPLE) {
                 ndof[col] = (unsigned char)t;
+                // the only contribution of a fully free joint pair lands in the output image at once
+                int sr = 7 * STR, sc = STR;
+                if (td.direct) { stg = obuf + (int)((tl.out0 + A.out_par) & 1) + td.rel; sr = 1; sc = td.colh; }
                 if (ct.a == 0) {
-                    if (ct.b == 0) frame_block_t<0, 0, false, false>(A, ct.e, stg, STR); else frame_block_t<0, 1, false, false>(A, ct.e, stg, STR);
+                    if (ct.b == 0) frame_block_t<0, 0, false, false>(A, ct.e, stg, sr, sc); else frame_block_t<0, 1, false, false>(A, ct.e, stg, sr, sc);
                 } else {
-                    if (ct.b == 0) frame_block_t<1, 0, false, false>(A, ct.e, stg, STR); else frame_block_t<1, 1, false, false>(A, ct.e, stg, STR);
+                    if (ct.b == 0) frame_block_t<1, 0, false, false>(A, ct.e, stg, sr, sc); else frame_block_t<1, 1, false, false>(A, ct.e, stg, sr, sc);
                 }
             } else if (A.mass_mode) {
                 ndof[col] = (unsigned char)mass_block_stage<ND>(A, ct, stg);
@@ -543,14 +549,14 @@ k_assemble_tiles(CbStiffArgs A)
                         for (int i = 0; i < 49; ++i) stg[i * STR] = blk[i];
                     } else if (A.d.ANAFLAG == 3) {
                         if (ct.a == 0) {
-                            if (ct.b == 0) frame_block_t<0, 0, true>(A, ct.e, stg, STR); else frame_block_t<0, 1, true>(A, ct.e, stg, STR);
+                            if (ct.b == 0) frame_block_t<0, 0, true>(A, ct.e, stg, 7 * STR, STR); else frame_block_t<0, 1, true>(A, ct.e, stg, 7 * STR, STR);
                         } else {
-                            if (ct.b == 0) frame_block_t<1, 0, true>(A, ct.e, stg, STR); else frame_block_t<1, 1, true>(A, ct.e, stg, STR);
+                            if (ct.b == 0) frame_block_t<1, 0, true>(A, ct.e, stg, 7 * STR, STR); else frame_block_t<1, 1, true>(A, ct.e, stg, 7 * STR, STR);
                         }
                     } else if (ct.a == 0) {
-                        if (ct.b == 0) frame_block_t<0, 0, false>(A, ct.e, stg, STR); else frame_block_t<0, 1, false>(A, ct.e, stg, STR);
+                        if (ct.b == 0) frame_block_t<0, 0, false>(A, ct.e, stg, 7 * STR, STR); else frame_block_t<0, 1, false>(A, ct.e, stg, 7 * STR, STR);
                     } else {
-                        if (ct.b == 0) frame_block_t<1, 0, false>(A, ct.e, stg, STR); else frame_block_t<1, 1, false>(A, ct.e, stg, STR);
+                        if (ct.b == 0) frame_block_t<1, 0, false>(A, ct.e, stg, 7 * STR, STR); else frame_block_t<1, 1, false>(A, ct.e, stg, 7 * STR, STR);
                     }
                 }
                 ndof[col] = 7;
@@ -572,7 +578,8 @@ k_assemble_tiles(CbStiffArgs A)
         // request the next tile's contribution record, then its element inputs; they land while
         // this tile is reduced and written out
         CbContrib ctn{}; ctn.type = 0xff;
-        if (has_next && t < tln.ns) ctn = A.tcontribs[tln.t0 + t];
+        CbTDst tdn{};
+        if (has_next && t < tln.ns) { ctn = A.tcontribs[tln.t0 + t]; if (FRAME_SIMPLE) tdn = A.tdst[tln.t0 + t]; }
         __syncthreads();
         if (!FRAME_SIMPLE && ND >= 6 && ctn.type == CB_T_SHELL && !A.mass_mode) shell_load(A, ctn, (long)tln.c0 + ctn.pad, in);
 
@@ -586,6 +593,7 @@ k_assemble_tiles(CbStiffArgs A)
             const int p = it / ND, c = it - p * ND;
             const CbTPair pr = spair[p];
             constexpr unsigned FULL = (1u << ND) - 1u;
+            if (FRAME_SIMPLE && pr.cnt == 1 && pr.maskA == FULL && pr.maskB == FULL) continue;   // written in phase 1
             if (pr.maskA == FULL && pr.maskB == FULL && (FRAME_SIMPLE || !A.mixed)) {
                 const double *src = stage + c * STR + (FRAME_SIMPLE ? 0 : pr.cs);
                 double acc[ND];
@@ -632,7 +640,7 @@ k_assemble_tiles(CbStiffArgs A)
         }
 
         if (!has_next) break;
-        tile = next; tl = tln; ct = ctn;
+        tile = next; tl = tln; ct = ctn; td = tdn;
         __syncthreads();          // obuf / spair are rewritten by the next iteration
     }
 }

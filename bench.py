@@ -129,6 +129,44 @@ def _cpu_worker(args):
     return m.NE_SH, ts[warm:]
 
 
+FRAME_SAMPLE_N = 8        # 8^3-joint lattice per core: 1344 frames, chunk-local skyline of 11 MB
+
+
+def _cpu_worker_frames(args):
+    """the same for the frame path: `reps` iterations of stiff_fr + updatc + forces_fr on a
+    small lattice with the unmodified reference routines"""
+    wid, reps, warm = args
+    from oracle import refbind as R
+    from cubens_b200 import meshgen
+    m = meshgen.lattice_model(FRAME_SAMPLE_N)
+    s = R.RefState(m)
+    s.begin_increment()
+    dd = meshgen.perturbation(m, scale=1e-3, seed=20261017 + wid)
+    R.update_forces(m, s, dd); s.end_iteration()
+    small = dd * 1e-2
+    ts = []
+    for it in range(warm + reps):
+        t0 = time.perf_counter()
+        R.stiff(m, s, SLVFLAG=0)
+        R.update_forces(m, s, small)
+        s.end_iteration()
+        ts.append(time.perf_counter() - t0)
+    return m.NE_FR, ts[warm:]
+
+
+def cpu_sample_frames(steps, warmup, cores=None):
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker_frames, [(w, steps, warmup) for w in range(cores)])
+    ne = res[0][0]
+    total = float(np.max(np.array([r[1] for r in res]), axis=0).sum())
+    return {"value": cores * ne * steps / total, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{cores} independent {FRAME_SAMPLE_N}^3-joint lattices ({ne} frames each, chunk-local "
+                      f"skyline), {steps} iterations per core, unmodified stiff_fr+updatc+forces_fr at gcc -O2"}
+
+
 def cpu_sample(steps, warmup, cell, cores=None):
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
@@ -263,10 +301,16 @@ def run_gpu(a):
 
     # CPU baseline first (rank 0, N=1 only): fork before any CUDA context exists in this process
     cpu = None
+    cpu_frames = None
     if rank == 0 and world == 1 and not a.no_cpu:
         from oracle import refbind as R
         if R.available():
             cpu = cpu_sample(a.cpu_steps, 1, 1.0 / a.n)
+            if not a.no_others:
+                try:
+                    cpu_frames = cpu_sample_frames(max(4, a.cpu_steps // 4), 1)
+                except Exception as e:                       # the frame baseline is an extra, never fatal
+                    cpu_frames = {"unavailable": repr(e)}
 
     import cubens_b200 as cb
     from cubens_b200 import meshgen
@@ -431,6 +475,8 @@ def run_gpu(a):
         if unstructured is None:
             asm.close()
         others = other_configs(cb, meshgen, local, peak)
+        if cpu_frames is not None:
+            others["frame_lattice"]["cpu_baseline"] = cpu_frames
     k_ms = float(np.median(asm_ms))
     ach = ALG_BYTES_KT * n_local / (k_ms * 1e-3) / 1e9
     traffic = None

@@ -151,7 +151,7 @@ struct cb_handle {
     DevBuf<int32_t> fr_yldflag, fr_ynew, fr_code, fr_trip;
     // bricks
     DevBuf<int32_t> br_nodes;
-    DevBuf<double> br_const;
+    DevBuf<double> br_const, br_prep;
     // generation roles: index into the [3] arrays
     int gP = 1, gN = 2;          // frame-like state: _ip buffer, _i buffer
     bool i_is_ip = true;         // *_i currently aliases *_ip (after begin_increment/end_iteration)
@@ -520,7 +520,7 @@ extern "C" void cb_destroy(cb_handle *h)
     for (DevBuf<double> *b : {&h->x, &h->x_temp, &h->x_ip, &h->dd, &h->f_temp, &h->f, &h->d,
                               &h->d_temp, &h->sm, &h->qvec, &h->sums, &h->sums_part, &h->sh_const, &h->sh_keb, &h->sh_kebc, &h->sh_der, &h->sh_Nm, &h->sh_fg,
                               &h->sh_dens, &h->tr_const, &h->tr_fg, &h->tr_dens, &h->fr_const,
-                              &h->fr_offset, &h->fr_efFE_ref, &h->fr_fg, &h->fr_dens, &h->br_const,
+                              &h->fr_offset, &h->fr_efFE_ref, &h->fr_fg, &h->fr_dens, &h->br_const, &h->br_prep,
                               &h->Ax, &h->ss, &h->Mx, &h->fr_plast, &h->fr_tau, &h->tr_py})
         b->release();
     h->sh_class.release(); h->cls_rep.release(); h->keb_tab.release(); h->der_tab.release(); h->works_cls.release();
@@ -1129,6 +1129,8 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
     a.tr_frame = h->tr_frame[g].p; a.tr_ef = h->tr_ef[ge].p;
     a.fr_frame = h->fr_frame[g].p; a.fr_ef = h->fr_ef[ge].p; a.fr_efFE = h->fr_efFE[g].p;
     a.contribs = h->contribs.p;
+    if (h->NE_BR && !h->br_prep.p && h->br_prep.alloc((size_t)h->NE_BR * 80)) return CB_ERR_CUDA;
+    a.br_prep = h->br_prep.p;
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     if (h->sz.NE_SH && !(gen != CB_GEN_COMMITTED && h->krec_fresh && h->i_is_ip)) {
         if (cbk_shell_prep(a.d, a.x, a.sh_frame, h->stream)) return fail(CB_ERR_CUDA, "prep launch");

@@ -219,6 +219,7 @@ struct CbStiffArgs {
     const CbTile *tiles; long ntiles; const CbTPair *tpairs;
     const CbContrib *tcontribs;   // thread slots of the general tile kernel (see CbTile)
     const CbTDst *tdst;           // [slot] direct-write target of the slot (see CbTDst)
+    double *br_prep;              // [NE_BR][8 Gauss points][10]: J^-1 and detJ (k_brick_prep)
     const double *kebc;      // DKT 3x3 sub-blocks in assembly order (static; layouts above)
     const CbTile2 *tiles2; long ntiles2; const CbWork *works; const CbTPair *tpairs2;
     const int32_t *tile_elems;

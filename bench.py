@@ -434,6 +434,7 @@ def run_gpu(a):
 
     ncls = asm.geometry_classes
     map_bytes = asm.map_bytes
+    asm_lib = asm.lib
 
     # ---- the same plate with every interior joint moved (seeded): no two shells share their
     # geometry, so every shell streams its own DKT matrix from HBM (N=1, shorter run) -----------
@@ -480,12 +481,28 @@ def run_gpu(a):
     k_ms = float(np.median(asm_ms))
     ach = ALG_BYTES_KT * n_local / (k_ms * 1e-3) / 1e9
     traffic = None
+    fl_a = fl_f = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("k_assemble_shell_tiles_dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("k_assemble_shell_tiles_dram_bytes_per_launch")
+            fl_a = tj.get("k_assemble_shell_tiles_fp64_flops_per_launch")
+            fl_f = tj.get("k_shell_forces_fp64_flops_per_launch")
         except Exception:
             traffic = None
+    # FP64 side of the roofline (north_star: achieved FP64 FLOP/s against the B200 peak): peak from the
+    # DFMA micro-kernel measured now, executed flops per launch from the committed ncu capture
+    fp64 = None
+    try:
+        pk = float(asm_lib.cb_measure_fp64_tflops(local))
+        fp64 = {"peak_tflops": pk, "peak_source": "DFMA micro-kernel, this run (cb_measure_fp64_tflops)",
+                "k_assemble_shell_tiles": None if not fl_a else
+                {"executed_flops_per_launch": fl_a, "achieved_tflops": fl_a / (k_ms * 1e-3) / 1e12,
+                 "frac": fl_a / (k_ms * 1e-3) / 1e12 / pk},
+                "flops_source": "ncu r01f (dadd + dmul + 2 x dfma thread instructions), profiles/traffic.json"}
+    except Exception as e:
+        fp64 = {"unavailable": repr(e)}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -510,6 +527,7 @@ def run_gpu(a):
                      "whole_step_frac": (ALG_BYTES_KT + ALG_BYTES_FINT) * n_local / (ms_step * 1e-3) / 1e9 / peak,
                      "map_bytes_per_launch": map_bytes},
     }
+    line["fp64"] = fp64
     if unstructured is not None:
         line["unstructured"] = unstructured
     if others is not None:

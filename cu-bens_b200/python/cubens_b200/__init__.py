@@ -37,7 +37,7 @@ EXPORTS = [
     "cb_host_free", "cb_map_bytes", "cb_sync", "cb_stream", "cb_set_q", "cb_residual_sums",
     "cb_dev_sums", "cb_get_sums", "cb_get_yldflag", "cb_set_yldflag", "cb_get_mass_csc_values", "cb_dev_Mx",
     "cb_geometry_classes", "cb_keep_ip", "cb_checkpoint_save", "cb_checkpoint_load",
-    "cb_set_element_ids", "cb_update_forces_begin", "cb_update_forces_end",
+    "cb_set_element_ids", "cb_update_forces_begin", "cb_update_forces_end", "cb_measure_fp64_tflops",
 ]
 
 
@@ -85,6 +85,7 @@ def load_library(path=None):
     lib.cb_last_forces_ms.restype = C.c_double
     lib.cb_last_assemble_ms.restype = C.c_double
     lib.cb_timer_stop_ms.restype = C.c_double
+    lib.cb_measure_fp64_tflops.restype = C.c_double
     lib.cb_host_alloc.restype = C.c_void_p
     lib.cb_host_alloc.argtypes = [C.c_ulong]
     lib.cb_host_free.restype = None

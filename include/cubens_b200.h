@@ -264,6 +264,9 @@ void *cb_host_alloc(unsigned long bytes);
 void  cb_host_free(void *p);
 /* block the host until all work queued on this handle's stream has finished                */
 int  cb_sync(cb_handle *h);
+/* FP64 DFMA throughput of the device in TFLOP/s (micro-kernel, CUDA events, best of 5): the FP64
+ * roofline denominator bench.py reports next to the HBM one; < 0 on failure     */
+double cb_measure_fp64_tflops(int device);
 /* the CUDA stream (cudaStream_t cast to void*) all of this handle's kernels run on         */
 void *cb_stream(cb_handle *h);
 

@@ -94,3 +94,82 @@ def test_fullsize_properties(gpu):
     assert np.array_equal(Axp, Ax[Ap[first_eq]:])
     assert np.array_equal(fp[first_eq:], f[first_eq:])
     p.close()
+
+
+def _frame_state(m, generic=False, owned=None, ids=None):
+    if generic:
+        os.environ["CB_NO_FRAME_SIMPLE"] = "1"
+    try:
+        a = cb.Assembler(m, layout=cb.CB_MAT_CSC)
+    finally:
+        os.environ.pop("CB_NO_FRAME_SIMPLE", None)
+    if owned is not None:
+        a.set_owned_joints(*owned)
+    dd = meshgen.perturbation(m, scale=1e-3)
+    a.begin_increment()
+    a.update_forces(dd, want_f=False); a.end_iteration()
+    a.stiff()
+    f, *_ = a.update_forces(dd * 1e-2)
+    a.end_iteration()
+    a.stiff()
+    Ax = np.zeros(a.lib.cb_csc_nnz(a.h))
+    a._check(a.lib.cb_get_csc_values(a.h, cb._p(Ax)))
+    return a, Ax, f
+
+
+def test_fullsize_frame_lattice_properties(gpu):
+    """BASELINE.json configs[3] size: 119^3-joint lattice, 5 012 994 frames, NEQ 11 696 986, nnz 5.7e8 -
+    determinism, the frame-only specialisations (register-only force kernel, frame-only tile kernel
+    with direct image writes) against the generic kernels, symmetry, rigid-body null space and
+    partition invariance"""
+    n = 119
+    m = meshgen.lattice_model(n, SLVFLAG=2)
+    assert m.NE_FR == 5_012_994
+    a, Ax, f = _frame_state(m)
+    a.stiff()
+    Ax2 = np.zeros_like(Ax)
+    a._check(a.lib.cb_get_csc_values(a.h, cb._p(Ax2)))
+    assert np.array_equal(Ax, Ax2)                                   # determinism
+    del Ax2
+    ef = a.download("EF_I")
+    import scipy.sparse as sp
+    Ap = np.zeros(m.NEQ + 1, dtype=np.int32); Ai = np.zeros(Ax.size, dtype=np.int32)
+    a._check(a.lib.cb_csc_pattern(a.h, cb._p(Ap), cb._p(Ai)))
+    a.close()
+    scale = np.abs(Ax).max()
+    # generic kernels (what a model with offsets / releases runs): same numbers
+    b, Axb, fb = _frame_state(m, generic=True)
+    assert np.abs(Axb - Ax).max() <= 1e-13 * scale
+    assert np.abs(fb - f).max() <= 1e-13 * np.abs(f).max()
+    assert np.abs(b.download("EF_I") - ef).max() <= 1e-13 * np.abs(ef).max()
+    b.close()
+    del Axb
+    K = sp.csc_matrix((Ax, Ai, Ap), shape=(m.NEQ, m.NEQ), copy=False)
+    rng = np.random.default_rng(2)
+    u = rng.normal(size=m.NEQ); v = rng.normal(size=m.NEQ)
+    Kv = K @ v
+    uKv, vKu = float(u @ Kv), float(v @ (K @ u))
+    assert abs(uKv - vKu) <= 1e-11 * np.sqrt(float(Kv @ Kv)) * np.sqrt(float(u @ u))
+    # rigid translations: rows of joints at least two levels above the clamped base plane
+    jc = m.jcode.reshape(-1, 7)
+    kk = np.arange(m.NJ) % n
+    inner = kk > 1
+    for c in range(3):
+        t = np.zeros(m.NEQ)
+        eq = jc[:, c]
+        t[eq[eq > 0] - 1] = 1.0
+        r = K @ t
+        rows = jc[inner].reshape(-1) - 1
+        assert np.abs(r[rows]).max() <= 1e-9 * scale, c
+    del K
+    # partition invariance: rank 1 of 2 (generic joint-range partition, halo members included)
+    from cubens_b200.partition import partition_model
+    m1, owned, ids = partition_model(m, 2, 1)
+    p, Axp, fp = _frame_state(m1, owned=owned)
+    q = jc[owned[0]:owned[1]].reshape(-1)
+    q = q[q > 0] - 1
+    first_eq = int(q.min())
+    assert q.max() == m.NEQ - 1 and q.size == m.NEQ - first_eq
+    assert np.array_equal(Axp, Ax[Ap[first_eq]:])
+    assert np.array_equal(fp[first_eq:], f[first_eq:])
+    p.close()

@@ -694,6 +694,9 @@ k_assemble_tiles(CbStiffArgs A)
 // ids | ring of tile records
 // ------------------------------------------------------------------------------------------
 
+#ifndef CB_T2_MBAR
+#define CB_T2_MBAR 1              // the wait for the previous image's bulk read-out is taken off the CTA barrier
+#endif
 #ifndef CB_T2_CTAS
 #define CB_T2_CTAS 3              // resident CTAs per SM the kernel is compiled for
 #endif
@@ -829,10 +832,23 @@ __device__ __forceinline__ void t2_store_half(double *obuf, int shift, const CbT
     }
 }
 
+// spin until the phase of the "image may be overwritten" mbarrier with this parity has completed
+__device__ __forceinline__ void t2_wait_image(unsigned long long *bar, int parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "T2_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra T2_WAIT_%=;\n"
+        "}\n" ::"r"(t2_saddr(bar)), "r"(parity)
+        : "memory");
+}
+
 // the DKT staging columns (skb) are not needed when the blocks come from the class table
 #define CB_T2_SKB(CLS) ((CLS) ? 0 : 18 * CB_TILE_T)
 #define CB_T2_SMEM_DOUBLES(CLS) (CB_T2_OUT + 2 + 2 * CB_T2_ELEMS * CB_SH_KREC + CB_T2_SKB(CLS))
-#define CB_T2_SMEM_BYTES(CLS) (CB_T2_SMEM_DOUBLES(CLS) * 8 + 2 * CB_TILE_T * 16 + CB_TILE_T * 16 + CB_T2_EIDS * CB_TILE_T * 4 + 4 * 48)
+#define CB_T2_SMEM_BYTES(CLS) (CB_T2_SMEM_DOUBLES(CLS) * 8 + 2 * CB_TILE_T * 16 + CB_TILE_T * 16 + CB_T2_EIDS * CB_TILE_T * 4 + 4 * 48 + 16)
 
 // CLS: the DKT sub-blocks come from the geometry-class table (L1-resident) instead of the
 // work-ordered per-contribution copy in HBM; the classes of a work item's two contributions are
@@ -849,7 +865,16 @@ k_assemble_shell_tiles(CbStiffArgs A)
     int4 *swork = reinterpret_cast<int4 *>(spair2 + 2 * CB_TILE_T);   // [CB_TILE_T]
     int *seid = reinterpret_cast<int *>(swork + CB_TILE_T);           // [CB_T2_EIDS][CB_TILE_T]
     int *sring = seid + CB_T2_EIDS * CB_TILE_T;                       // [4][12] tile records
+    // mbarrier "the image may be overwritten": thread 0 arrives once the copy engine has read the
+    // previous tile's image out; every thread checks it right before its first image store, by which
+    // time (half a tile later) the phase has long completed - so nobody waits for the read-out at the
+    // CTA barrier at the top of the loop any more
+    unsigned long long *sbar = reinterpret_cast<unsigned long long *>(sring + 48);
     const int t = threadIdx.x;
+    if (CB_T2_MBAR && t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(t2_saddr(sbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     const long G = gridDim.x, N = A.ntiles2;
     long tile = blockIdx.x;
     if (tile >= N) return;
@@ -889,9 +914,13 @@ k_assemble_shell_tiles(CbStiffArgs A)
         const long next = tile + G;
         const bool has_next = next < N, has_next2 = next + G < N, has_next3 = next + 2 * G < N;
         // the previous tile's image must have been read out by the copy engine
-        if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (!CB_T2_MBAR && t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();            // this tile's shell + pair records visible; image + buffers free
+        if (CB_T2_MBAR && t == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t2_saddr(sbar)) : "memory");
+        }
         CbWork w;
         *reinterpret_cast<int4 *>(&w) = swork[t];
         CbTile2 tln = tl, tlnn = tl;
@@ -938,6 +967,7 @@ k_assemble_shell_tiles(CbStiffArgs A)
                 shell_half_acc<LEFT>(kr0 + w.s0 * CB_SH_KREC, kb, w.a0, w.b0, top, bot, true);     \
                 if (w.n == 2)                                                                      \
                     shell_half_acc<LEFT>(kr0 + w.s1 * CB_SH_KREC, kb + 9, w.a1, w.b1, top, bot, false); \
+                if (CB_T2_MBAR && LEFT) t2_wait_image(sbar, it & 1);                               \
                 if (w.kind != 3) t2_store_half<false>(obuf, shift, pr, C0, top, bot);              \
             }                                                                                      \
             for (int q = 1; q < gmax; ++q) {        /* warp-uniform */                             \

@@ -1293,13 +1293,10 @@ extern "C" int cb_update_forces_begin(cb_handle *h, const double *dd_dev, double
     if (dd_dev && dd_dev != h->dd.p) { if (d2d(h->dd.p, dd_dev, h->sz.NEQ, s)) return fail(CB_ERR_CUDA, "dd copy"); }
     a.dlpf = dlpf; a.itecnt = itecnt;
     CUDA_TRY(cudaEventRecord(h->ev4, s));
-    {   // d_temp += dd (main.c:1949)
+    {   // d_temp += dd (main.c:1949): folded into the nodal kernel
         const bool whole = h->j0 == 0 && h->j1 == h->sz.NJ;
         const long q0 = whole ? 0 : h->ql0, nq = whole ? h->sz.NEQ : h->ql1 - h->ql0;
-        if (nq > 0) {
-            unsigned g = (unsigned)((nq + 255) / 256);
-            k_axpy1<<<g, 256, 0, s>>>(nq, h->dd.p + q0, h->d_temp.p + q0); ++h->launches;
-        }
+        a.axpy_n = nq > 0 ? nq : 0; a.axpy_x = h->dd.p + q0; a.axpy_y = h->d_temp.p + q0;
     }
     if (cbk_node_update(a, s)) return fail(CB_ERR_CUDA, "node update launch");
     ++h->launches;

@@ -238,6 +238,9 @@ struct CbStiffArgs {
 };
 
 struct CbForceArgs {
+    long axpy_n;             // d_temp[i] += dd[i] for i < axpy_n, done by the nodal kernel (0: none)
+    const double *axpy_x;
+    double *axpy_y;
     CbDev d;
     double *x_temp, *x_ip;
     const double *dd;        // [NEQ] device

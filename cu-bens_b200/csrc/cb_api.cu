@@ -1207,11 +1207,6 @@ k_resid_sums2(int nblk, const double *__restrict__ part, double *__restrict__ ou
     if (threadIdx.x < 3) out[threadIdx.x] = sh[threadIdx.x][0];
 }
 
-__global__ void k_axpy1(long n, const double *__restrict__ x, double *__restrict__ y)
-{
-    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (i < n) y[i] += x[i];
-}
 
 static CbForceArgs force_args(cb_handle *h)
 {

@@ -520,7 +520,7 @@ k_assemble_tiles(CbStiffArgs A)
     double *obuf = smem + ((NN * STR + 1) & ~1);           // 16-byte aligned
     CbTPair *spair = reinterpret_cast<CbTPair *>(obuf + A.tile_smem_out);       // [CB_TILE_T]
     unsigned char *ndof = reinterpret_cast<unsigned char *>(spair + CB_TILE_T);
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int t = threadIdx.x;
 
     long tile = blockIdx.x;
     if (tile >= A.ntiles) return;

@@ -135,3 +135,29 @@ def test_shell_plastic_partitioned(gpu, world):
     for a, ids in zip(P.asm, P.ids):
         assert np.array_equal(a.download("CHI").reshape(-1, 3), chi[ids["sh"]])
     one.close(); P.close()
+
+
+def test_force_pass_halves_misuse(gpu):
+    """error behaviour of the split force pass: _end without _begin, non-ascending element ids; and
+    begin + end with negative firsts is exactly cb_update_forces_dev"""
+    m = meshgen.lattice_model(3, ANAFLAG=3, load=200.0, SLVFLAG=2)
+    a = cb.Assembler(m, layout=cb.CB_MAT_CSC)
+    b = cb.Assembler(m, layout=cb.CB_MAT_CSC)
+    with pytest.raises(cb.CubensError):
+        a.update_forces_end(-1, -1)
+    with pytest.raises(cb.CubensError):
+        a.set_element_ids(fr_gid=np.arange(m.NE_FR)[::-1].copy())
+    a.set_element_ids(fr_gid=np.arange(m.NE_FR) * 3 + 5)          # any ascending numbering
+    dd = 0.004 * np.random.default_rng(11).uniform(-1.0, 1.0, size=m.NEQ)
+    a.begin_increment(); b.begin_increment()
+    for it in range(3):
+        first = a.update_forces_begin(dd, 1.0, it)
+        fa, fra, sha, dla = a.update_forces_end(-1, -1, 1.0)
+        fb, frb, shb, dlb = b.update_forces(dd, dlpf=1.0, itecnt=it)
+        assert (fra, sha, dla) == (frb, shb, dlb) and np.array_equal(fa, fb)
+        assert np.array_equal(a.yldflag(), b.yldflag())
+        if fra:
+            assert first[0] % 3 == 2 and first[0] != 0x7fffffff      # reported in the caller's numbering
+            break
+        a.end_iteration(); b.end_iteration()
+    a.close(); b.close()

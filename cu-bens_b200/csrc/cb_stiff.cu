@@ -924,13 +924,21 @@ k_assemble_shell_tiles(CbStiffArgs A)
         CbWork w;
         *reinterpret_cast<int4 *>(&w) = swork[t];
         CbTile2 tln = tl, tlnn = tl;
+        // ring slots are 48 bytes, 16-byte aligned: three 16-byte broadcast loads per record instead of
+        // ten 4-byte ones (the kernel is bound by shared-memory wavefronts)
         if (has_next) {
+            const int4 *r4 = reinterpret_cast<const int4 *>(sring + ((it + 1) & 3) * 12);
+            const int4 q0 = r4[0], q1 = r4[1], q2 = r4[2];
+            const int v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
 #pragma unroll
-            for (int i = 0; i < 10; ++i) reinterpret_cast<int *>(&tln)[i] = sring[((it + 1) & 3) * 12 + i];
+            for (int i = 0; i < 10; ++i) reinterpret_cast<int *>(&tln)[i] = v[i];
         }
         if (has_next2) {
+            const int4 *r4 = reinterpret_cast<const int4 *>(sring + ((it + 2) & 3) * 12);
+            const int4 q0 = r4[0], q1 = r4[1], q2 = r4[2];
+            const int v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
 #pragma unroll
-            for (int i = 0; i < 10; ++i) reinterpret_cast<int *>(&tlnn)[i] = sring[((it + 2) & 3) * 12 + i];
+            for (int i = 0; i < 10; ++i) reinterpret_cast<int *>(&tlnn)[i] = v[i];
         }
         if (has_next3 && t < 10)
             CB_CPA(4, "ca", sring + ((it + 3) & 3) * 12 + t, reinterpret_cast<const int *>(A.tiles2 + next + 2 * G) + t);

@@ -316,3 +316,12 @@ def test_trip_exchange_gloo_world2(tmp_path):
                           "29733", str(script)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_fp64_probe_needs_a_device():
+    """cb_measure_fp64_tflops (the FP64 roofline denominator of bench.py) reports failure, not a made-up
+    number, where no CUDA device exists"""
+    import cubens_b200 as cb
+    lib = cb.load_library()
+    if lib.cb_device_count() == 0:
+        assert lib.cb_measure_fp64_tflops(0) < 0

@@ -857,7 +857,7 @@ static int build_plan(cb_handle *h)
                     done[pick] = 1;
                     while (head < units.size() && done[head]) ++head;
                 }
-                if (out.size() > (size_t)CB_TILE_T) { plan2_ok = false; return; }
+                if (out.size() > (size_t)CB_T2_T) { plan2_ok = false; return; }
                 works.resize(cur.w0);
                 works.insert(works.end(), out.begin(), out.end());
                 cur.nw = (int32_t)out.size();
@@ -889,8 +889,8 @@ static int build_plan(cb_handle *h)
             const int pairs_n = (int)(g1 - i);
             auto fits = [&](int nw, long nout, int gmax, int np, size_t ne) {
                 // slack: a warp tail too short for a group is padded with idle items
-                return gmax <= CB_T2_GROUP && nw + 3 * (gmax - 1) <= CB_TILE_T && nout <= CB_T2_OUT &&
-                       np <= CB_TILE_T && ne <= (size_t)CB_T2_ELEMS;
+                return gmax <= CB_T2_GROUP && nw + 3 * (gmax - 1) <= CB_T2_T && nout <= CB_T2_OUT &&
+                       np <= CB_T2_T && ne <= (size_t)CB_T2_ELEMS;
             };
             if (open2 && (!fits(cur.nw + items_n, cur.nout + out_n, std::max(cur_gmax, gmax_n), cur.np + pairs_n,
                                 curel.size() + newel.size()) ||
@@ -1010,7 +1010,7 @@ static int ensure_keb(cb_handle *h)
     if (h->sz.NE_SH && h->plan_ready && (h->plan_csc.ntiles || h->plan_csc.ntiles2) &&
         !(h->cls_on && h->plan_csc.ntiles2)) {
         if (h->plan_csc.ntiles2) {
-            if (!h->sh_kebc.p && h->sh_kebc.alloc((size_t)h->plan_csc.ntiles2 * 18 * CB_TILE_T)) return CB_ERR_CUDA;
+            if (!h->sh_kebc.p && h->sh_kebc.alloc((size_t)h->plan_csc.ntiles2 * 18 * CB_T2_T)) return CB_ERR_CUDA;
             if (cbk_shell_init_kebc2(d, h->plan_csc.tiles2.p, h->plan_csc.ntiles2, h->plan_csc.works.p,
                                      h->contribs.p, h->sh_kebc.p, h->stream))
                 return fail(CB_ERR_CUDA, "kebc init launch");

@@ -216,9 +216,9 @@ int cbk_shell_init_kebc(const CbDev &d, const CbContrib *contribs, long ncontrib
     return cudaGetLastError() != cudaSuccess;
 }
 
-// duo plan: the same sub-blocks in work-major order, kebc[(T * 18 + u * 9 + i) * CB_TILE_T + t] for
+// duo plan: the same sub-blocks in work-major order, kebc[(T * 18 + u * 9 + i) * CB_T2_T + t] for
 // work item t of tile T (u = its contribution 0/1): one CTA per tile
-__global__ void __launch_bounds__(CB_TILE_T)
+__global__ void __launch_bounds__(CB_T2_T)
 k_shell_init_kebc2(CbDev d, const CbTile2 *__restrict__ tiles, const CbWork *__restrict__ works,
                    const CbContrib *__restrict__ contribs, double *__restrict__ kebc)
 {
@@ -226,13 +226,13 @@ k_shell_init_kebc2(CbDev d, const CbTile2 *__restrict__ tiles, const CbWork *__r
     const int t = threadIdx.x;
     if (t >= tl.nw) return;
     const CbWork w = works[tl.w0 + t];
-    double *o = kebc + blockIdx.x * (18L * CB_TILE_T) + t;
+    double *o = kebc + blockIdx.x * (18L * CB_T2_T) + t;
     for (int u = 0; u < 2; ++u) {
         const int a = u ? w.a1 : w.a0, b = u ? w.b1 : w.b0;
         const long e = (u < w.n) ? contribs[w.c0 + u].e : -1;
 #pragma unroll
         for (int i = 0; i < 9; ++i)
-            o[(u * 9 + i) * CB_TILE_T] = (e >= 0) ? SOA(d.sh_keb, (3 * a + b) * 9 + i, e, d.NE_SH) : 0.0;
+            o[(u * 9 + i) * CB_T2_T] = (e >= 0) ? SOA(d.sh_keb, (3 * a + b) * 9 + i, e, d.NE_SH) : 0.0;
     }
 }
 
@@ -240,7 +240,7 @@ int cbk_shell_init_kebc2(const CbDev &d, const CbTile2 *tiles, long ntiles, cons
                          const CbContrib *contribs, double *kebc, cudaStream_t s)
 {
     if (ntiles == 0 || d.NE_SH == 0) return 0;
-    k_shell_init_kebc2<<<(unsigned)ntiles, CB_TILE_T, 0, s>>>(d, tiles, works, contribs, kebc);
+    k_shell_init_kebc2<<<(unsigned)ntiles, CB_T2_T, 0, s>>>(d, tiles, works, contribs, kebc);
     return cudaGetLastError() != cudaSuccess;
 }
 

@@ -51,7 +51,9 @@ struct CbPair {
 };
 
 // ---- tile assembly (CSC): one CTA owns a run of consecutive joints ------------------------
+#ifndef CB_TILE_T
 #define CB_TILE_T 128            // threads per CTA = max contributions per tile
+#endif
 struct CbTile {
     int64_t out0;     // first Ax index of the tile's (contiguous) output range
     int32_t nout;     // number of Ax entries
@@ -93,11 +95,16 @@ struct CbTDst {
 // ---- shell-only tile assembly ("duo" plan): a thread evaluates up to two consecutive
 // contributions of one joint-pair block and sums them in registers; blocks with more than two
 // contributions are split into partial sums that are combined through shared memory
+#ifndef CB_T2_T
+#define CB_T2_T 96               // threads per CTA of the duo kernel = work items per tile: 4 CTAs of 3 warps per SM
+                                 // (0.770 ms) beat 3 of 4 warps (0.790) and 2 of 6 (0.78): more independent CTAs
+                                 // hide each other's barrier stalls, and 10 joints fill 90 of 96 lanes
+#endif
 #ifndef CB_T2_OUT
-#define CB_T2_OUT 3328           // max doubles of Ax per tile staged in shared memory (13 plate joints: 117 of 128 lanes busy; 3072 = 12 joints measured 5 % slower)
+#define CB_T2_OUT 2560           // max doubles of Ax per tile staged in shared memory (10 plate joints x 252)
 #endif
 #ifndef CB_T2_ELEMS
-#define CB_T2_ELEMS 56           // max distinct shells per tile (their krec records are staged)
+#define CB_T2_ELEMS 44           // max distinct shells per tile (their krec records are staged)
 #endif
 #define CB_T2_GROUP 16           // max partial sums of one block (a group of lanes of one warp)
 struct CbTile2 {

@@ -698,10 +698,10 @@ k_assemble_tiles(CbStiffArgs A)
 #define CB_T2_MBAR 1              // the wait for the previous image's bulk read-out is taken off the CTA barrier
 #endif
 #ifndef CB_T2_CTAS
-#define CB_T2_CTAS 3              // resident CTAs per SM the kernel is compiled for
+#define CB_T2_CTAS 4              // resident CTAs per SM the kernel is compiled for (96 threads each)
 #endif
 #ifndef CB_T2_CTAS_CLS
-#define CB_T2_CTAS_CLS 3          // ... with the class table (4 CTAs of 128 registers measured slower: spills)
+#define CB_T2_CTAS_CLS 4          // ... with the class table
 #endif
 
 // Columns 0..2 (LEFT) or 3..5 of K_ab (6x6, global axes) of one shell contribution:
@@ -739,19 +739,19 @@ __device__ __forceinline__ void shell_half_acc(const double *kr, const double *k
 }
 
 // ---- asynchronous staging (cp.async: no register scoreboard is held while a copy is in flight) ----
-#define CB_T2_EIDS ((CB_T2_ELEMS * 9 + CB_TILE_T - 1) / CB_TILE_T)
+#define CB_T2_EIDS ((CB_T2_ELEMS * 9 + CB_T2_T - 1) / CB_T2_T)
 __device__ __forceinline__ unsigned t2_saddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 #define CB_CPA(BYTES, CACHE, dst, src)                                                              \
     asm volatile("cp.async." CACHE ".shared.global [%0], [%1], " #BYTES ";" ::"r"(t2_saddr(dst)), "l"(src))
 #define CB_CPA_COMMIT() asm volatile("cp.async.commit_group;")
 
-// element ids of a tile's copy items (item t + k * CB_TILE_T -> seid[k][t], private to thread t)
+// element ids of a tile's copy items (item t + k * CB_T2_T -> seid[k][t], private to thread t)
 __device__ __forceinline__ void t2_issue_eids(const CbStiffArgs &A, const CbTile2 &tl, int *seid)
 {
 #pragma unroll
     for (int k = 0; k < CB_T2_EIDS; ++k) {
-        const int i = threadIdx.x + k * CB_TILE_T;
-        if (i < tl.ne * 9) CB_CPA(4, "ca", seid + k * CB_TILE_T + threadIdx.x, A.tile_elems + tl.e0 + i / 9);
+        const int i = threadIdx.x + k * CB_T2_T;
+        if (i < tl.ne * 9) CB_CPA(4, "ca", seid + k * CB_T2_T + threadIdx.x, A.tile_elems + tl.e0 + i / 9);
     }
 }
 // shell records of a tile (9 chunks of 16 bytes each) + its pair records
@@ -760,7 +760,7 @@ __device__ __forceinline__ void t2_issue_stage(const CbStiffArgs &A, const CbTil
 {
 #pragma unroll
     for (int k = 0; k < CB_T2_EIDS; ++k) {
-        const int i = threadIdx.x + k * CB_TILE_T;
+        const int i = threadIdx.x + k * CB_T2_T;
         if (i < tl.ne * 9) {
             const int es = i / 9, ch = i - es * 9;
             CB_CPA(16, "cg", krec_dst + es * CB_SH_KREC + ch * 2, A.d.sh_Nm + (long)eid[k] * CB_SH_KREC + ch * 2);
@@ -769,15 +769,15 @@ __device__ __forceinline__ void t2_issue_stage(const CbStiffArgs &A, const CbTil
     if (threadIdx.x < tl.np) CB_CPA(16, "cg", pair_dst + threadIdx.x, A.tpairs2 + tl.p0 + threadIdx.x);
 }
 // DKT sub-blocks of the two contributions of work item t of tile T: kebc[(T * 18 + u * 9 + i) *
-// CB_TILE_T + t] (u = contribution 0/1, i = 3x3 entry) -> skb[u * 9 + i][t], private to thread t.
+// CB_T2_T + t] (u = contribution 0/1, i = 3x3 entry) -> skb[u * 9 + i][t], private to thread t.
 // The left half of a block takes entries 0,3,6, the right half the other six.
 template <bool LEFT>
 __device__ __forceinline__ void t2_issue_kb(const CbStiffArgs &A, long T, int t, double *skb)
 {
-    const double *src = A.kebc + T * (18L * CB_TILE_T) + t;
+    const double *src = A.kebc + T * (18L * CB_T2_T) + t;
 #pragma unroll
     for (int i = 0; i < 18; ++i)
-        if (((i % 3) == 0) == LEFT) CB_CPA(8, "ca", skb + i * CB_TILE_T + t, src + i * CB_TILE_T);
+        if (((i % 3) == 0) == LEFT) CB_CPA(8, "ca", skb + i * CB_T2_T + t, src + i * CB_T2_T);
 }
 
 // columns c0..c0+2 of a block into the tile image (ACC: added to what is there); top/bot as in
@@ -846,25 +846,25 @@ __device__ __forceinline__ void t2_wait_image(unsigned long long *bar, int parit
 }
 
 // the DKT staging columns (skb) are not needed when the blocks come from the class table
-#define CB_T2_SKB(CLS) ((CLS) ? 0 : 18 * CB_TILE_T)
+#define CB_T2_SKB(CLS) ((CLS) ? 0 : 18 * CB_T2_T)
 #define CB_T2_SMEM_DOUBLES(CLS) (CB_T2_OUT + 2 + 2 * CB_T2_ELEMS * CB_SH_KREC + CB_T2_SKB(CLS))
-#define CB_T2_SMEM_BYTES(CLS) (CB_T2_SMEM_DOUBLES(CLS) * 8 + 2 * CB_TILE_T * 16 + CB_TILE_T * 16 + CB_T2_EIDS * CB_TILE_T * 4 + 4 * 48 + 16)
+#define CB_T2_SMEM_BYTES(CLS) (CB_T2_SMEM_DOUBLES(CLS) * 8 + 2 * CB_T2_T * 16 + CB_T2_T * 16 + CB_T2_EIDS * CB_T2_T * 4 + 4 * 48 + 16)
 
 // CLS: the DKT sub-blocks come from the geometry-class table (L1-resident) instead of the
 // work-ordered per-contribution copy in HBM; the classes of a work item's two contributions are
 // packed in its c0 field.
 template <bool CLS>
-__global__ void __launch_bounds__(CB_TILE_T, CLS ? CB_T2_CTAS_CLS : CB_T2_CTAS)
+__global__ void __launch_bounds__(CB_T2_T, CLS ? CB_T2_CTAS_CLS : CB_T2_CTAS)
 k_assemble_shell_tiles(CbStiffArgs A)
 {
     extern __shared__ __align__(16) double smem[];
     double *obuf = smem;                                              // [CB_T2_OUT + 2]
     double *skrec = obuf + CB_T2_OUT + 2;                             // [2][CB_T2_ELEMS*18], 16 B aligned
-    double *skb = skrec + 2 * CB_T2_ELEMS * CB_SH_KREC;               // [18][CB_TILE_T]
-    CbTPair *spair2 = reinterpret_cast<CbTPair *>(skb + CB_T2_SKB(CLS));   // [2][CB_TILE_T]
-    int4 *swork = reinterpret_cast<int4 *>(spair2 + 2 * CB_TILE_T);   // [CB_TILE_T]
-    int *seid = reinterpret_cast<int *>(swork + CB_TILE_T);           // [CB_T2_EIDS][CB_TILE_T]
-    int *sring = seid + CB_T2_EIDS * CB_TILE_T;                       // [4][12] tile records
+    double *skb = skrec + 2 * CB_T2_ELEMS * CB_SH_KREC;               // [18][CB_T2_T]
+    CbTPair *spair2 = reinterpret_cast<CbTPair *>(skb + CB_T2_SKB(CLS));   // [2][CB_T2_T]
+    int4 *swork = reinterpret_cast<int4 *>(spair2 + 2 * CB_T2_T);   // [CB_T2_T]
+    int *seid = reinterpret_cast<int *>(swork + CB_T2_T);           // [CB_T2_EIDS][CB_T2_T]
+    int *sring = seid + CB_T2_EIDS * CB_T2_T;                       // [4][12] tile records
     // mbarrier "the image may be overwritten": thread 0 arrives once the copy engine has read the
     // previous tile's image out; every thread checks it right before its first image store, by which
     // time (half a tile later) the phase has long completed - so nobody waits for the read-out at the
@@ -895,7 +895,7 @@ k_assemble_shell_tiles(CbStiffArgs A)
         int eid[CB_T2_EIDS];
 #pragma unroll
         for (int k = 0; k < CB_T2_EIDS; ++k) {
-            const int i = t + k * CB_TILE_T;
+            const int i = t + k * CB_T2_T;
             eid[k] = (i < tl.ne * 9) ? A.tile_elems[tl.e0 + i / 9] : 0;
         }
         t2_issue_stage(A, tl, eid, skrec, spair2);
@@ -943,7 +943,7 @@ k_assemble_shell_tiles(CbStiffArgs A)
         if (has_next3 && t < 10)
             CB_CPA(4, "ca", sring + ((it + 3) & 3) * 12 + t, reinterpret_cast<const int *>(A.tiles2 + next + 2 * G) + t);
         const int shift = (int)((tl.out0 + A.out_par) & 1);
-        const CbTPair *spair = spair2 + buf * CB_TILE_T;
+        const CbTPair *spair = spair2 + buf * CB_T2_T;
         const double *kr0 = skrec + buf * CB_T2_ELEMS * CB_SH_KREC;
         const bool active = t < tl.nw;
         const unsigned amask = __ballot_sync(0xffffffffu, active);
@@ -970,7 +970,7 @@ k_assemble_shell_tiles(CbStiffArgs A)
                         }                                                                          \
                 } else {                                                                           \
                 _Pragma("unroll") for (int i = 0; i < 18; ++i)                                     \
-                    if (((i % 3) == 0) == LEFT) kb[i] = skb[i * CB_TILE_T + t];                    \
+                    if (((i % 3) == 0) == LEFT) kb[i] = skb[i * CB_T2_T + t];                    \
                 }                                                                                  \
                 shell_half_acc<LEFT>(kr0 + w.s0 * CB_SH_KREC, kb, w.a0, w.b0, top, bot, true);     \
                 if (w.n == 2)                                                                      \
@@ -988,9 +988,9 @@ k_assemble_shell_tiles(CbStiffArgs A)
         if (has_next) {
             int eid[CB_T2_EIDS];
 #pragma unroll
-            for (int k = 0; k < CB_T2_EIDS; ++k) eid[k] = seid[k * CB_TILE_T + t];
+            for (int k = 0; k < CB_T2_EIDS; ++k) eid[k] = seid[k * CB_T2_T + t];
             t2_issue_stage(A, tln, eid, skrec + (buf ^ 1) * CB_T2_ELEMS * CB_SH_KREC,
-                           spair2 + (buf ^ 1) * CB_TILE_T);
+                           spair2 + (buf ^ 1) * CB_T2_T);
             if (has_next2) t2_issue_eids(A, tlnn, seid);
             if (t < tln.nw) {
                 CB_CPA(16, "cg", swork + t, A.works + tln.w0 + t);
@@ -1039,14 +1039,14 @@ static int launch_shell_tiles(const CbStiffArgs &a, cudaStream_t s)
         int per_sm = 0, dev = 0, nsm = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_shell_tiles<CLS>, CB_TILE_T, smem) !=
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_shell_tiles<CLS>, CB_T2_T, smem) !=
                 cudaSuccess || per_sm < 1)
             per_sm = 1;
         grid_cache = per_sm * nsm;
     }
     long grid = grid_cache;
     if (grid > a.ntiles2) grid = a.ntiles2;
-    k_assemble_shell_tiles<CLS><<<(unsigned)grid, CB_TILE_T, smem, s>>>(a);
+    k_assemble_shell_tiles<CLS><<<(unsigned)grid, CB_T2_T, smem, s>>>(a);
     return cudaGetLastError() != cudaSuccess;
 }
 

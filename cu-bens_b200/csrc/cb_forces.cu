@@ -19,7 +19,9 @@
 #include "cb_frame_math.cuh"
 #include "cb_frame_def_gen.cuh"
 
+#ifndef CB_TPB
 #define CB_TPB 128
+#endif
 #ifndef CB_FORCES_STAGE_KEB
 #define CB_FORCES_STAGE_KEB 0     // 1: per-element DKT matrix staged by cp.async (see k_shell_forces)
 #endif

@@ -45,13 +45,22 @@ static int fail(int code, const char *fmt, ...)
                         __FILE__, __LINE__);                                                   \
     } while (0)
 
+// cb_plan_selfcheck builds the host side of a handle (joint scan, element-to-nonzero maps, tile plans)
+// without any device: every DevBuf allocation / upload is then a no-op
+static thread_local bool g_host_only = false;
+
+static void dev_zero(void *p, size_t bytes)
+{
+    if (p && bytes && !g_host_only) cudaMemset(p, 0, bytes);
+}
+
 template <typename T> struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
     int alloc(size_t count)
     {
         n = count;
-        if (count == 0) { p = nullptr; return 0; }
+        if (count == 0 || g_host_only) { p = nullptr; return 0; }
         cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
         if (e != cudaSuccess) {
             fail(CB_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T),
@@ -64,7 +73,7 @@ template <typename T> struct DevBuf {
     int upload(const std::vector<T> &v)
     {
         if (alloc(v.size())) return 1;
-        if (v.empty()) return 0;
+        if (v.empty() || g_host_only) return 0;
         return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess;
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
@@ -80,6 +89,9 @@ struct Plan {
     long ntiles = 0;
     DevBuf<CbTile2> tiles2; DevBuf<CbWork> works; DevBuf<CbTPair> tpairs2; DevBuf<int32_t> telems;
     long ntiles2 = 0, nworks = 0;
+    // stream plan (k_assemble_shell_stream)
+    DevBuf<CbTileS> tilesS; DevBuf<uint32_t> stepsS, pairsS; DevBuf<int32_t> elemsS;
+    long ntilesS = 0, nrowsS = 0;
     int tile_smem_out = 0;
 };
 
@@ -126,6 +138,7 @@ struct cb_handle {
     DevBuf<double> sh_frame[3], sh_dsl[3], sh_ef[3];   // 0 = committed, 1/2 = iterate ping-pong
     // geometry classes (cb_internal.h): class of each shell, representatives, tables, work records
     DevBuf<int32_t> sh_class, cls_rep;
+    std::vector<int32_t> h_cls;   // host copy of sh_class (the stream plan packs it into its step records)
     DevBuf<double> keb_tab, der_tab;
     DevBuf<CbWork> works_cls;
     int ncls = 0;
@@ -227,11 +240,27 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
     if (sz->NJ <= 0 || sz->NEQ <= 0) return fail(CB_ERR_ARG, "NJ and NEQ must be positive");
     if (sz->NJ > 0x7fffffffL / 8 || sz->NEQ > 0x7ffffff0L)
         return fail(CB_ERR_OVERFLOW, "NJ / NEQ exceed 32-bit device indices");
-    int ndev = cb_device_count();
-    if (ndev <= 0) return fail(CB_ERR_CUDA, "no CUDA device available (no CPU fallback exists)");
-    if (fl->device < 0 || fl->device >= ndev) return fail(CB_ERR_ARG, "bad device ordinal");
-    CUDA_TRY(cudaSetDevice(fl->device));
+    if (!g_host_only) {
+        int ndev = cb_device_count();
+        if (ndev <= 0) return fail(CB_ERR_CUDA, "no CUDA device available (no CPU fallback exists)");
+        if (fl->device < 0 || fl->device >= ndev) return fail(CB_ERR_ARG, "bad device ordinal");
+        CUDA_TRY(cudaSetDevice(fl->device));
+    }
 
+    {   // required host arrays per element type (a partially filled cb_model is an argument error)
+        const bool lin = sz->NE_TR || sz->NE_FR, any = lin || sz->NE_SH || sz->NE_SBR;
+        const char *miss = nullptr;
+        if (!m->x) miss = "x"; else if (!m->jcode) miss = "jcode"; else if (any && !m->minc) miss = "minc";
+        else if (any && !m->emod) miss = "emod";
+        else if (lin && !m->carea) miss = "carea"; else if (lin && !m->llength) miss = "llength";
+        else if ((lin || sz->NE_SH) && (!m->c1 || !m->c2 || !m->c3)) miss = "c1 / c2 / c3";
+        else if ((sz->NE_SH || sz->NE_SBR) && !m->nu) miss = "nu";
+        else if (sz->NE_SH && !m->thick) miss = "thick"; else if (sz->NE_SH && !m->farea) miss = "farea";
+        else if (sz->NE_SH && !m->slength) miss = "slength"; else if (sz->NE_SH && !m->xlocal) miss = "xlocal";
+        else if (sz->NE_FR && (!m->gmod || !m->istrong || !m->iweak || !m->ipolar || !m->iwarp)) miss = "gmod / istrong / iweak / ipolar / iwarp";
+        else if (sz->NE_FR && !m->auxpt) miss = "auxpt";
+        if (miss) return fail(CB_ERR_ARG, "cb_create: cb_model.%s is NULL but the model needs it", miss);
+    }
     cb_handle *h = new cb_handle();
     h->sz = *sz; h->fl = *fl;
     h->NE_BR = sz->NE_SBR + sz->NE_FBR;
@@ -254,7 +283,8 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
     }
 
 #define BAIL(code) do { int c_ = (code); cb_destroy(h); return c_; } while (0)
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+    if (g_host_only) {
+    } else if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
         cudaEventCreate(&h->ev2) != cudaSuccess || cudaEventCreate(&h->ev3) != cudaSuccess ||
         cudaEventCreate(&h->ev4) != cudaSuccess || cudaEventCreate(&h->ev5) != cudaSuccess ||
@@ -285,7 +315,7 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
         BAIL(CB_ERR_CUDA);
     for (DevBuf<double> *b : {&h->dd, &h->f_temp, &h->f, &h->d, &h->d_temp, &h->sm}) {
         if (b->alloc(sz->NEQ)) BAIL(CB_ERR_CUDA);
-        cudaMemset(b->p, 0, sz->NEQ * sizeof(double));
+        dev_zero(b->p, sz->NEQ * sizeof(double));
     }
     if (h->layout & CB_MAT_SKYLINE) {
         h->h_maxa.assign(m->maxa, m->maxa + sz->NEQ + 1);
@@ -343,7 +373,8 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
     // ---- trusses ---------------------------------------------------------------------------
     if (TR) {
         std::vector<double> c((size_t)TR * CB_TR_CONST), fr((size_t)TR * CB_TR_FRAME),
-            dn(m->dens ? m->dens : m->emod, (m->dens ? m->dens : m->emod) + TR);
+            dn((size_t)TR, 0.0);                         // no densities: zero mass, like frames and shells
+        if (m->dens) dn.assign(m->dens, m->dens + TR);
         for (long e = 0; e < TR; ++e) {
             c[e * 4 + 0] = m->emod[e]; c[e * 4 + 1] = m->carea[e]; c[e * 4 + 2] = m->llength[e];
             c[e * 4 + 3] = pow(m->llength[e], 3);       // libm, as truss.c:109 evaluates it
@@ -359,7 +390,7 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
         }
         for (int g = 0; g < 3; ++g) {
             if (h->tr_frame[g].upload(fr) || h->tr_ef[g].alloc((size_t)TR * 2)) BAIL(CB_ERR_CUDA);
-            cudaMemset(h->tr_ef[g].p, 0, (size_t)TR * 2 * sizeof(double));
+            dev_zero(h->tr_ef[g].p, (size_t)TR * 2 * sizeof(double));
         }
     }
     // ---- bricks (linear, stiffness only; brick.c:127-129 reads emod/nu at TR+FR+SH+i) -------
@@ -416,15 +447,15 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
             if (h->fr_plast.upload(pl) || h->fr_yldflag.alloc((size_t)FR * 2) || h->fr_ynew.alloc((size_t)FR * 2) ||
                 h->fr_code.alloc(FR) || h->fr_tau.alloc(FR) || h->fr_trip.alloc(4))
                 BAIL(CB_ERR_CUDA);
-            cudaMemset(h->fr_yldflag.p, 0, (size_t)FR * 2 * sizeof(int32_t));   // main.c:1692
-            cudaMemset(h->fr_trip.p, 0, 4 * sizeof(int32_t));
+            dev_zero(h->fr_yldflag.p, (size_t)FR * 2 * sizeof(int32_t));   // main.c:1692
+            dev_zero(h->fr_trip.p, 4 * sizeof(int32_t));
         }
         for (int g = 0; g < 3; ++g) {
             if (h->fr_frame[g].upload(fr) || h->fr_xfr[g].upload(xfr) ||
                 h->fr_efFE[g].alloc((size_t)FR * 14) || h->fr_ef[g].alloc((size_t)FR * 14))
                 BAIL(CB_ERR_CUDA);
-            cudaMemset(h->fr_efFE[g].p, 0, (size_t)FR * 14 * sizeof(double));
-            cudaMemset(h->fr_ef[g].p, 0, (size_t)FR * 14 * sizeof(double));
+            dev_zero(h->fr_efFE[g].p, (size_t)FR * 14 * sizeof(double));
+            dev_zero(h->fr_ef[g].p, (size_t)FR * 14 * sizeof(double));
         }
     }
     // ---- shells ----------------------------------------------------------------------------
@@ -480,6 +511,7 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
             }
             if (ok && getenv("CB_NO_GEOMETRY_CLASSES") == nullptr) {
                 h->ncls = (int)rep.size();
+                h->h_cls = cls;
                 if (h->sh_class.upload(cls) || h->cls_rep.upload(rep) || h->keb_tab.alloc((size_t)h->ncls * 81) ||
                     h->der_tab.alloc((size_t)h->ncls * CB_SH_DER))
                     BAIL(CB_ERR_CUDA);
@@ -493,20 +525,20 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
             if (h->sh_frame[g].upload(fr) || h->sh_dsl[g].upload(dsl) ||
                 h->sh_ef[g].alloc((size_t)SH * 18))
                 BAIL(CB_ERR_CUDA);
-            cudaMemset(h->sh_ef[g].p, 0, (size_t)SH * 18 * sizeof(double));
+            dev_zero(h->sh_ef[g].p, (size_t)SH * 18 * sizeof(double));
         }
         if (fl->ANAFLAG == 3) {
             std::vector<double> fy(m->yield + pe, m->yield + pe + SH);
             if (h->sh_yield.upload(fy) || h->sh_pl[0].alloc((size_t)SH * 21) || h->sh_pl[1].alloc((size_t)SH * 21) ||
                 h->sh_kpl.alloc((size_t)SH * 324) || h->sh_yv.alloc(SH) || h->sh_trip.alloc(4))
                 BAIL(CB_ERR_CUDA);
-            cudaMemset(h->sh_pl[0].p, 0, (size_t)SH * 21 * sizeof(double));     // main.c:1703-1712
-            cudaMemset(h->sh_pl[1].p, 0, (size_t)SH * 21 * sizeof(double));
-            cudaMemset(h->sh_yv.p, 0, (size_t)SH * sizeof(int32_t));
-            cudaMemset(h->sh_trip.p, 0, 4 * sizeof(int32_t));
+            dev_zero(h->sh_pl[0].p, (size_t)SH * 21 * sizeof(double));     // main.c:1703-1712
+            dev_zero(h->sh_pl[1].p, (size_t)SH * 21 * sizeof(double));
+            dev_zero(h->sh_yv.p, (size_t)SH * sizeof(int32_t));
+            dev_zero(h->sh_trip.p, 4 * sizeof(int32_t));
         }
     }
-    CUDA_TRY(cudaDeviceSynchronize());
+    if (!g_host_only) CUDA_TRY(cudaDeviceSynchronize());
     *out = h;
     return CB_OK;
 #undef BAIL
@@ -515,7 +547,7 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
 extern "C" void cb_destroy(cb_handle *h)
 {
     if (!h) return;
-    cudaSetDevice(h->fl.device);
+    if (!g_host_only) cudaSetDevice(h->fl.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf<double> *b : {&h->x, &h->x_temp, &h->x_ip, &h->dd, &h->f_temp, &h->f, &h->d,
                               &h->d_temp, &h->sm, &h->qvec, &h->sums, &h->sums_part, &h->sh_const, &h->sh_keb, &h->sh_kebc, &h->sh_der, &h->sh_Nm, &h->sh_fg,
@@ -540,6 +572,7 @@ extern "C" void cb_destroy(cb_handle *h)
     h->plan_csc.tiles.release(); h->plan_csc.tpairs.release(); h->plan_csc.tcontribs.release(); h->plan_csc.tdst.release();
     h->plan_csc.tiles2.release(); h->plan_csc.works.release(); h->plan_csc.tpairs2.release();
     h->plan_csc.telems.release();
+    h->plan_csc.tilesS.release(); h->plan_csc.stepsS.release(); h->plan_csc.pairsS.release(); h->plan_csc.elemsS.release();
     h->plan_sky.pairs.release(); h->Ap.release(); h->Ai.release(); h->maxa.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -802,6 +835,161 @@ static int build_plan(cb_handle *h)
     std::vector<int32_t> telems;
     bool plan2_ok = tiles_ok && h->sz.NE_SH && !h->sz.NE_TR && !h->sz.NE_FR && !h->NE_BR &&
                     h->max_dof == 6 && !h->mixed && h->fl.ANAFLAG != 3;   // yielded shells: general kernel
+    // ---- shell-only models, first choice: the "stream" plan of k_assemble_shell_stream ----------------
+    // (cb_internal.h, CbTileS).  Tiles are runs of consecutive joints; the joint-pair blocks of a tile are
+    // handed to the 32 lanes of one warp WHOLE and in their natural order (next-fit with capacity S =
+    // max(6, largest contribution count in the tile)): a lane's steps are the contributions of its blocks
+    // in reference order, the last step of a block carries the store flag.
+    std::vector<CbTileS> tilesS; std::vector<uint32_t> stepsS, pairsS; std::vector<int32_t> elemsS;
+    std::vector<int32_t> blkS;                // pairs_csc index of every pair record (plan check)
+    const char *kt_env = getenv("CB_KT");
+    bool planS_ok = plan2_ok && !(kt_env && strcmp(kt_env, "duo") == 0);
+    if (planS_ok) {
+        std::vector<size_t> blocks;           // pairs_csc indices of the open tile
+        std::vector<int32_t> curel;
+        int64_t out0 = 0; long nout = 0; int smax = 6; bool open = false;
+        auto lanes_needed = [&](const std::vector<size_t> &bl, size_t extra0, size_t extra1, int S) {
+            int lanes = 0, load = S + 1;      // forces a new lane for the first block
+            auto put = [&](int cnt) { if (load + cnt > S) { ++lanes; load = 0; } load += cnt; };
+            for (size_t q : bl) put(pairs_csc[q].ccount);
+            for (size_t q = extra0; q < extra1; ++q) put(pairs_csc[q].ccount);
+            return lanes;
+        };
+        auto close_tile = [&]() {
+            CbTileS t{};
+            t.out0 = out0; t.nout = (int32_t)nout; t.r0 = (int32_t)(stepsS.size() / 32);
+            t.p0 = (int32_t)pairsS.size(); t.e0 = (int32_t)elemsS.size();
+            t.np = (uint8_t)blocks.size(); t.ne = (uint8_t)curel.size();
+            // lane loads first (nsteps = the longest lane), then the records
+            int lane = -1, load = smax + 1, nsteps = 0;
+            std::vector<std::pair<int, int>> where(blocks.size());      // (lane, first step) of each block
+            for (size_t k = 0; k < blocks.size(); ++k) {
+                const int cnt = pairs_csc[blocks[k]].ccount;
+                if (load + cnt > smax) { ++lane; load = 0; }
+                where[k] = {lane, load};
+                load += cnt; nsteps = std::max(nsteps, load);
+            }
+            t.nsteps = (uint8_t)nsteps;
+            stepsS.resize(stepsS.size() + (size_t)nsteps * 32, CB_S_IDLE);
+            for (size_t k = 0; k < blocks.size(); ++k) {
+                const CbPair &p = pairs_csc[blocks[k]];
+                for (int c = 0; c < p.ccount; ++c) {
+                    const CbContrib &ct = contribs[p.cstart + c];
+                    const int slot = (int)(std::find(curel.begin(), curel.end(), ct.e) - curel.begin());
+                    const int cls = h->cls_on ? h->h_cls[ct.e] : 0;
+                    stepsS[((size_t)t.r0 + where[k].second + c) * 32 + where[k].first] =
+                        CB_S_REC(slot, ct.a, ct.b, c == p.ccount - 1, k, cls);
+                }
+                pairsS.push_back(CB_S_PAIR(p.off - out0, p.colh, p.maskA, p.maskB));
+                blkS.push_back((int32_t)blocks[k]);
+            }
+            while (pairsS.size() & 3) { pairsS.push_back(0); blkS.push_back(-1); }
+            elemsS.insert(elemsS.end(), curel.begin(), curel.end());
+            tilesS.push_back(t);
+            open = false; blocks.clear(); curel.clear();
+        };
+        size_t i = 0;
+        while (i < pairs_csc.size() && planS_ok) {
+            size_t g1 = i;
+            const int32_t B = pair_B[i];
+            while (g1 < pairs_csc.size() && pair_B[g1] == B) ++g1;
+            int smax_n = 6;
+            std::vector<int32_t> newel;
+            auto collect = [&](const std::vector<int32_t> &have) {
+                newel.clear();
+                for (size_t q = i; q < g1; ++q)
+                    for (int c = 0; c < pairs_csc[q].ccount; ++c) {
+                        const int32_t e = contribs[pairs_csc[q].cstart + c].e;
+                        if (std::find(have.begin(), have.end(), e) == have.end() &&
+                            std::find(newel.begin(), newel.end(), e) == newel.end())
+                            newel.push_back(e);
+                    }
+            };
+            for (size_t q = i; q < g1; ++q) smax_n = std::max(smax_n, (int)pairs_csc[q].ccount);
+            const long out_n = (long)h->h_nfree[B] * h->colh[B];
+            if (smax_n > CB_S_MAXSTEPS || h->colh[B] > 255 || (int)(g1 - i) > CB_S_PAIRS || out_n > CB_S_IMG) {
+                planS_ok = false; break;
+            }
+            auto fits = [&](const std::vector<size_t> &bl, long no, int S, size_t ne) {
+                return lanes_needed(bl, i, g1, S) <= 32 && no <= CB_S_IMG && ne <= (size_t)CB_S_SLOTS &&
+                       bl.size() + (g1 - i) <= (size_t)CB_S_PAIRS;
+            };
+            collect(curel);
+            if (open && (!fits(blocks, nout + out_n, std::max(smax, smax_n), curel.size() + newel.size()) ||
+                         h->base[B] - h->ax_base != out0 + nout))
+                close_tile();
+            if (!open) {
+                collect(curel);                                   // curel is empty now
+                if (!fits(blocks, out_n, smax_n, newel.size())) { planS_ok = false; break; }
+                out0 = h->base[B] - h->ax_base; nout = 0; smax = 6; open = true;
+            }
+            smax = std::max(smax, smax_n);
+            curel.insert(curel.end(), newel.begin(), newel.end());
+            for (size_t q = i; q < g1; ++q) blocks.push_back(q);
+            nout += out_n;
+            i = g1;
+        }
+        if (planS_ok && open) close_tile();
+        if (planS_ok && tilesS.empty()) planS_ok = false;
+        if (planS_ok && stepsS.size() / 32 > 0x7fffffffUL / 9) planS_ok = false;
+        if (!planS_ok) { tilesS.clear(); stepsS.clear(); pairsS.clear(); elemsS.clear(); blkS.clear(); }
+    }
+    // Interpreter check of the stream plan (always in cb_plan_selfcheck, or with CB_PLAN_CHECK set): walk
+    // the records exactly as the kernel does and verify that every joint-pair block is accumulated from
+    // precisely its contribution list (reference order), stored once, that the blocks of a tile tile its
+    // output range without overlap or gap, and that the tiles cover the owned slice of Ax contiguously.
+    if (planS_ok && (g_host_only || getenv("CB_PLAN_CHECK"))) {
+        int64_t expect = 0;
+        for (size_t ti = 0; ti < tilesS.size(); ++ti) {
+            const CbTileS &t = tilesS[ti];
+            if (t.out0 != expect) return fail(CB_ERR_ARG, "stream plan: tile %zu starts at %ld, expected %ld", ti, (long)t.out0, (long)expect);
+            expect += t.nout;
+            std::vector<std::vector<CbContrib>> acc(32);
+            std::vector<int> stored(t.np, 0);
+            std::vector<uint8_t> cover(t.nout, 0);
+            for (int st = 0; st < t.nsteps; ++st)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const uint32_t r = stepsS[((size_t)t.r0 + st) * 32 + lane];
+                    const unsigned slot = r & 63u;
+                    if (slot == CB_S_IDLE) continue;
+                    if ((int)slot >= t.ne) return fail(CB_ERR_ARG, "stream plan: slot out of range in tile %zu", ti);
+                    CbContrib c{}; c.e = elemsS[t.e0 + slot]; c.a = (r >> 6) & 3; c.b = (r >> 8) & 3;
+                    if (h->cls_on && (int)(r >> 18) != h->h_cls[c.e]) return fail(CB_ERR_ARG, "stream plan: class id mismatch");
+                    acc[lane].push_back(c);
+                    if (!((r >> 10) & 1u)) continue;
+                    const int dst = (r >> 11) & 127;
+                    if (dst >= t.np || blkS[t.p0 + dst] < 0) return fail(CB_ERR_ARG, "stream plan: bad pair index");
+                    const CbPair &p = pairs_csc[blkS[t.p0 + dst]];
+                    if ((int)acc[lane].size() != p.ccount) return fail(CB_ERR_ARG, "stream plan: block of tile %zu stored with %zu of %d contributions", ti, acc[lane].size(), (int)p.ccount);
+                    for (int k = 0; k < p.ccount; ++k) {
+                        const CbContrib &w = contribs[p.cstart + k];
+                        if (w.e != acc[lane][k].e || w.a != acc[lane][k].a || w.b != acc[lane][k].b || w.type != CB_T_SHELL)
+                            return fail(CB_ERR_ARG, "stream plan: contribution order differs in tile %zu", ti);
+                    }
+                    ++stored[dst]; acc[lane].clear();
+                    const uint32_t pr = pairsS[t.p0 + dst];
+                    const int rel = pr & 0xfff, colh = (pr >> 12) & 0xff;
+                    const unsigned mA = (pr >> 20) & 0x3f, mB = pr >> 26;
+                    if (rel != p.off - t.out0 || colh != p.colh || mA != p.maskA || mB != p.maskB)
+                        return fail(CB_ERR_ARG, "stream plan: pair record does not match its block");
+                    const int nra = __builtin_popcount(mA), ncb = __builtin_popcount(mB);
+                    for (int cc = 0; cc < ncb; ++cc)
+                        for (int rr = 0; rr < nra; ++rr) {
+                            const long idx = (long)rel + (long)cc * colh + rr;
+                            if (idx < 0 || idx >= t.nout || cover[idx]) return fail(CB_ERR_ARG, "stream plan: image overlap / overflow in tile %zu", ti);
+                            cover[idx] = 1;
+                        }
+                }
+            for (int lane = 0; lane < 32; ++lane)
+                if (!acc[lane].empty()) return fail(CB_ERR_ARG, "stream plan: unfinished block in tile %zu", ti);
+            for (int k = 0; k < t.np; ++k)
+                if (stored[k] != 1) return fail(CB_ERR_ARG, "stream plan: block stored %d times in tile %zu", stored[k], ti);
+            for (long k = 0; k < t.nout; ++k)
+                if (!cover[k]) return fail(CB_ERR_ARG, "stream plan: image gap in tile %zu", ti);
+        }
+        if (expect != h->nnz) return fail(CB_ERR_ARG, "stream plan: tiles cover %ld of %ld entries", (long)expect, h->nnz);
+    }
+    if (planS_ok) plan2_ok = false;           // the duo plan is the fallback (CB_KT=duo, or blocks too large)
     if (plan2_ok) {
         CbTile2 cur{}; bool open2 = false;
         std::vector<int32_t> curel;               // distinct shells of the open tile
@@ -951,7 +1139,7 @@ static int build_plan(cb_handle *h)
     };
     bucket(pairs_sky);
     if (tiles_ok) pairs_csc.clear(); else { bucket(pairs_csc); tiles.clear(); tpairs.clear(); }
-    if (plan2_ok) { tiles.clear(); tpairs.clear(); }
+    if (plan2_ok || planS_ok) { tiles.clear(); tpairs.clear(); }
     if (tiles.empty()) { tcontribs.clear(); tdst.clear(); }
 
     if (h->node_cstart.upload(cstart) || h->corners.upload(corners) || h->contribs.upload(contribs))
@@ -967,9 +1155,13 @@ static int build_plan(cb_handle *h)
             h->plan_csc.tpairs2.upload(tp2) || h->plan_csc.telems.upload(telems))
             return CB_ERR_CUDA;
         h->plan_csc.ntiles2 = (long)tiles2.size(); h->plan_csc.nworks = (long)works.size();
+        if (h->plan_csc.tilesS.upload(tilesS) || h->plan_csc.stepsS.upload(stepsS) ||
+            h->plan_csc.pairsS.upload(pairsS) || h->plan_csc.elemsS.upload(elemsS))
+            return CB_ERR_CUDA;
+        h->plan_csc.ntilesS = (long)tilesS.size(); h->plan_csc.nrowsS = (long)(stepsS.size() / 32);
         h->plan_csc.tile_smem_out = (max_tile_out + 3) & ~1;   // room for the parity shift, kept even
         if (h->Ax.alloc((size_t)nnz + 1)) return CB_ERR_CUDA;
-        cudaMemset(h->Ax.p, 0, ((size_t)nnz + 1) * sizeof(double));
+        dev_zero(h->Ax.p, ((size_t)nnz + 1) * sizeof(double));
         std::vector<int> Ap(h->sz.NEQ + 1, 0);
         host_pattern(h, Ap.data(), nullptr);
         if (h->Ap.upload(Ap)) return CB_ERR_CUDA;
@@ -978,18 +1170,42 @@ static int build_plan(cb_handle *h)
         if (h->plan_sky.pairs.upload(pairs_sky)) return CB_ERR_CUDA;
         h->plan_sky.npairs = (long)pairs_sky.size();
         if (h->ss.alloc((size_t)h->lss)) return CB_ERR_CUDA;
-        cudaMemset(h->ss.p, 0, (size_t)h->lss * sizeof(double));
+        dev_zero(h->ss.p, (size_t)h->lss * sizeof(double));
     }
     h->map_bytes = (long)((pairs_csc.size() + pairs_sky.size()) * sizeof(CbPair) +
                           tiles.size() * sizeof(CbTile) + tpairs.size() * sizeof(CbTPair) +
                           tcontribs.size() * (sizeof(CbContrib) + sizeof(CbTDst)) +
                           tiles2.size() * sizeof(CbTile2) + works.size() * sizeof(CbWork) +
                           tp2.size() * sizeof(CbTPair) + telems.size() * sizeof(int32_t) +
+                          tilesS.size() * sizeof(CbTileS) + (stepsS.size() + pairsS.size() + elemsS.size()) * 4 +
                           contribs.size() * sizeof(CbContrib));
     // uploads above went through the legacy default stream; the handle's stream is non-blocking
-    if (cudaDeviceSynchronize() != cudaSuccess) return fail(CB_ERR_CUDA, "sync after map upload");
+    if (!g_host_only && cudaDeviceSynchronize() != cudaSuccess) return fail(CB_ERR_CUDA, "sync after map upload");
     h->plan_ready = true;
     return CB_OK;
+}
+
+// Host-only consistency check of the element-to-nonzero maps and tile plans of a model (no device
+// needed): builds everything cb_create + the first cb_stiff would build on the host side and runs the
+// plan interpreter.  Used by the CPU tests; returns CB_OK or the failure (text in cb_last_error).
+extern "C" int cb_plan_selfcheck(const cb_sizes *sz, const cb_flags *fl, const cb_model *m, long j0, long j1,
+                                 long *stats /* [6] or NULL: nnz, tiles, step rows, pairs, max steps, kind */)
+{
+    g_host_only = true;
+    cb_handle *h = nullptr;
+    int rc = cb_create(sz, fl, m, &h);
+    if (rc == CB_OK && (j0 != 0 || j1 != 0)) rc = cb_set_owned_joints(h, j0, j1);
+    if (rc == CB_OK) rc = build_plan(h);
+    if (rc == CB_OK && stats) {
+        stats[0] = h->nnz;
+        stats[1] = h->plan_csc.ntilesS ? h->plan_csc.ntilesS : (h->plan_csc.ntiles2 ? h->plan_csc.ntiles2 : h->plan_csc.ntiles);
+        stats[2] = h->plan_csc.nrowsS; stats[3] = (long)h->plan_csc.pairsS.n;
+        stats[4] = h->plan_csc.ntilesS ? (h->plan_csc.nrowsS + h->plan_csc.ntilesS - 1) / h->plan_csc.ntilesS : 0;
+        stats[5] = h->plan_csc.ntilesS ? 3 : (h->plan_csc.ntiles2 ? 2 : (h->plan_csc.ntiles ? 1 : 0));
+    }
+    if (h) cb_destroy(h);
+    g_host_only = false;
+    return rc;
 }
 
 static int ensure_keb(cb_handle *h)
@@ -1007,9 +1223,15 @@ static int ensure_keb(cb_handle *h)
             return fail(CB_ERR_CUDA, "class table launch");
         h->launches += duo ? 2 : 1;
     }
-    if (h->sz.NE_SH && h->plan_ready && (h->plan_csc.ntiles || h->plan_csc.ntiles2) &&
-        !(h->cls_on && h->plan_csc.ntiles2)) {
-        if (h->plan_csc.ntiles2) {
+    if (h->sz.NE_SH && h->plan_ready && (h->plan_csc.ntiles || h->plan_csc.ntiles2 || h->plan_csc.ntilesS) &&
+        !(h->cls_on && (h->plan_csc.ntiles2 || h->plan_csc.ntilesS))) {
+        if (h->plan_csc.ntilesS) {
+            // stream plan: the 3x3 DKT block of every step, kebc[((row * 9) + i) * 32 + lane]
+            if (!h->sh_kebc.p && h->sh_kebc.alloc((size_t)h->plan_csc.nrowsS * 9 * 32)) return CB_ERR_CUDA;
+            if (cbk_shell_init_kebcS(d, h->plan_csc.tilesS.p, h->plan_csc.ntilesS, h->plan_csc.stepsS.p,
+                                     h->plan_csc.elemsS.p, h->sh_kebc.p, h->stream))
+                return fail(CB_ERR_CUDA, "kebc init launch");
+        } else if (h->plan_csc.ntiles2) {
             if (!h->sh_kebc.p && h->sh_kebc.alloc((size_t)h->plan_csc.ntiles2 * 18 * CB_T2_T)) return CB_ERR_CUDA;
             if (cbk_shell_init_kebc2(d, h->plan_csc.tiles2.p, h->plan_csc.ntiles2, h->plan_csc.works.p,
                                      h->contribs.p, h->sh_kebc.p, h->stream))
@@ -1153,6 +1375,8 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
         a.tiles2 = h->plan_csc.ntiles2 ? h->plan_csc.tiles2.p : nullptr; a.ntiles2 = h->plan_csc.ntiles2;
         a.works = (h->cls_on && h->works_cls.p) ? h->works_cls.p : h->plan_csc.works.p;
         a.tpairs2 = h->plan_csc.tpairs2.p; a.tile_elems = h->plan_csc.telems.p;
+        a.tilesS = h->plan_csc.ntilesS ? h->plan_csc.tilesS.p : nullptr; a.ntilesS = h->plan_csc.ntilesS;
+        a.stepsS = h->plan_csc.stepsS.p; a.pairsS = h->plan_csc.pairsS.p; a.elemsS = h->plan_csc.elemsS.p;
         a.tile_smem_out = h->plan_csc.tile_smem_out;
         a.out = h->Ax.p + h->ax_pad; a.out_par = h->ax_pad; a.skyline = 0; a.maxa = nullptr;
         if (cbk_stiff(a, h->stream, &h->launches)) return fail(CB_ERR_CUDA, "assembly launch");
@@ -1160,7 +1384,7 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
     CUDA_TRY(cudaEventRecord(h->ev3, h->stream));
     if (h->layout & CB_MAT_SKYLINE) {
         a.pairs = h->plan_sky.pairs.p; a.npairs = h->plan_sky.npairs; a.tiles = nullptr;
-        a.tiles2 = nullptr; a.ntiles2 = 0;
+        a.tiles2 = nullptr; a.ntiles2 = 0; a.tilesS = nullptr; a.ntilesS = 0;
         a.out = h->ss.p; a.skyline = 1; a.maxa = h->maxa.p;
         if (cbk_stiff(a, h->stream, &h->launches)) return fail(CB_ERR_CUDA, "assembly launch");
     }
@@ -1860,10 +2084,27 @@ static int transfer(cb_handle *h, int which, double *host, long n, bool down)
                 if (down) host[pos] = dv; else dv = host[pos];
                 ++pos;
             }
+        if (!down && which == CB_ARR_LLENGTH) {
+            // the powers of the reference length the kernels read next to it (libm pow, truss.c:109,
+            // frame.c:372): what cb_create derives and cb_mass refreshes must follow a restart upload
+            for (long e = 0; e < pt.ne; ++e) {
+                double *rec = &tmp[(size_t)e * pt.stride];
+                if (k == 0) rec[3] = pow(rec[2], 3);
+                else { rec[4] = rec[3] * rec[3]; rec[5] = pow(rec[3], 3); }
+            }
+        }
         if (!down)
             CUDA_TRY(cudaMemcpy(pt.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
-    if (!down) { CUDA_TRY(cudaDeviceSynchronize()); h->krec_fresh = false; }
+    if (!down) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        h->krec_fresh = false;
+        if (which == CB_ARR_FAREA || which == CB_ARR_SLENGTH) {
+            // the DKT matrices / geometry classes are functions of A0 and the side lengths: rebuild them
+            // and leave the classes of the initial geometry, exactly as after cb_mass (App. B.5)
+            h->keb_dirty = true; h->cls_on = false;
+        }
+    }
     return CB_OK;
 }
 

@@ -246,6 +246,34 @@ int cbk_shell_init_kebc2(const CbDev &d, const CbTile2 *tiles, long ntiles, cons
     return cudaGetLastError() != cudaSuccess;
 }
 
+// stream plan: the sub-block of every step, kebc[((row * 9) + i) * 32 + lane] (row = tile.r0 + step): a
+// warp's nine loads per step are nine contiguous 256-byte runs.  One warp per tile.
+__global__ void __launch_bounds__(32)
+k_shell_init_kebcS(CbDev d, const CbTileS *__restrict__ tiles, const uint32_t *__restrict__ steps,
+                   const int32_t *__restrict__ elems, double *__restrict__ kebc)
+{
+    const CbTileS tl = tiles[blockIdx.x];
+    const int lane = threadIdx.x;
+    for (int st = 0; st < tl.nsteps; ++st) {
+        const long row = (long)tl.r0 + st;
+        const uint32_t r = steps[row * 32 + lane];
+        const unsigned slot = r & 63u;
+        const int a = (r >> 6) & 3, b = (r >> 8) & 3;
+        const long e = (slot != CB_S_IDLE) ? elems[tl.e0 + slot] : -1;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            kebc[(row * 9 + i) * 32 + lane] = (e >= 0) ? SOA(d.sh_keb, (3 * a + b) * 9 + i, e, d.NE_SH) : 0.0;
+    }
+}
+
+int cbk_shell_init_kebcS(const CbDev &d, const CbTileS *tiles, long ntiles, const uint32_t *steps,
+                         const int32_t *elems, double *kebc, cudaStream_t s)
+{
+    if (ntiles == 0 || d.NE_SH == 0) return 0;
+    k_shell_init_kebcS<<<(unsigned)ntiles, 32, 0, s>>>(d, tiles, steps, elems, kebc);
+    return cudaGetLastError() != cudaSuccess;
+}
+
 // geometry classes: one copy of the DKT matrix / derived membrane data per class, and the work
 // records of the duo plan with the classes of their two contributions packed into c0
 __global__ void __launch_bounds__(128)
@@ -1453,12 +1481,13 @@ int cbk_gather_f(const CbForceArgs &a, cudaStream_t s)
 #define CB_FR_SMEM (105 * CB_FR_TPB * sizeof(double))
 static int frame_forces_configure()
 {
-    static bool done = false;
+    static CbPerDevice cfg{};
+    int &done = cfg.v[cb_device_slot()];
     if (done) return 0;
     if (cudaFuncSetAttribute(k_frame_forces<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB_FR_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_frame_forces<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB_FR_SMEM) != cudaSuccess)
         return 1;
-    done = true;
+    done = 1;
     return 0;
 }
 
@@ -1503,14 +1532,15 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
         // transposition tile, whichever is larger
         const size_t cols = CB_FORCES_STAGE_KEB ? 99 : 18;
         const size_t smem = std::max(cols * CB_TPB, (size_t)(CB_TPB / 32) * 32 * (CB_SH_KREC + 1)) * sizeof(double);
-        static bool configured = false;
+        static CbPerDevice cfg{};
+        int &configured = cfg.v[cb_device_slot()];
         if (!configured) {
             if (cudaFuncSetAttribute(k_shell_forces<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem) != cudaSuccess ||
                 cudaFuncSetAttribute(k_shell_forces<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem) != cudaSuccess)
                 return 1;
-            configured = true;
+            configured = 1;
         }
         if (d.ANAFLAG == 3) {
             static const int init[4] = {0x7fffffff, 0, 0, 0};

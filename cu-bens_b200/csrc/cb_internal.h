@@ -129,6 +129,44 @@ struct CbWork {       // 16 bytes, self-contained: no dependent load of the cont
 static_assert(sizeof(CbWork) == 16 && sizeof(CbTPair) == 16, "records are copied as 16-byte units");
 static_assert(sizeof(CbTile2) == 40, "tile records are prefetched as five 8-byte words");
 
+// ---- shell-only tile assembly, "stream" plan (k_assemble_shell_stream): one WARP owns a tile (a run of
+// consecutive joints = one contiguous slice of Ax).  Every lane walks a short list of contributions
+// (steps) that covers WHOLE joint-pair blocks, one after the other: it accumulates a block's 6x6 in
+// registers over the block's contributions (reference order) and stores it into the tile image when
+// the block's last contribution has been added - a segmented reduction over the sorted
+// element-to-nonzero map with the segments aligned to lanes, so no partial sums ever meet in shared
+// memory: every shell record is read once per contribution, every image entry is written once.
+#define CB_S_MAXSTEPS 8          // contributions per lane and tile (the plate: 6 = three off-diagonal blocks of
+                                 // two contributions, or one diagonal block of six)
+#define CB_S_IMG 2560            // max doubles of Ax per tile (10 plate joints x 252)
+#define CB_S_SLOTS 44            // max distinct shells per tile (a run of 10 plate joints touches 42); lane l stages
+                                 // the records of slots l and l + 32
+#define CB_S_PAIRS 96            // max joint-pair blocks per tile
+#ifndef CB_S_WARPS
+#define CB_S_WARPS 6             // warps (= concurrent tiles) per CTA, one CTA per SM: 6 x 35.1 KB of shared memory
+#endif
+struct CbTileS {
+    int64_t out0;     // first Ax index of the tile's contiguous output range
+    int32_t nout;
+    int32_t r0;       // first row of the step records: steps[(r0 + s) * 32 + lane]
+    int32_t p0;       // first pair record (multiple of 4: copied as 16-byte units)
+    int32_t e0;       // first entry of tile_elems
+    uint8_t nsteps, np, ne, pad;
+    int32_t pad2;
+};
+static_assert(sizeof(CbTileS) == 32, "tile records are read as two 16-byte words");
+// step record (uint32): bits 0-5 shell slot (CB_S_IDLE = no work), 6-7 local row joint a, 8-9 local column
+// joint b, 10 = last contribution of its block (store + reset), 11-17 pair record index, 18-31 geometry
+// class of the shell (0 when the classes are off)
+#define CB_S_IDLE 63u
+#define CB_S_REC(slot, a, b, last, dst, cls) \
+    ((uint32_t)(slot) | ((uint32_t)(a) << 6) | ((uint32_t)(b) << 8) | ((uint32_t)(last) << 10) | \
+     ((uint32_t)(dst) << 11) | ((uint32_t)(cls) << 18))
+// pair record (uint32): bits 0-11 offset of (first free row of A, first free column of B) in the tile
+// image, 12-19 column height of joint B, 20-25 free-DOF mask of A, 26-31 of B
+#define CB_S_PAIR(rel, colh, ma, mb) \
+    ((uint32_t)(rel) | ((uint32_t)(colh) << 12) | ((uint32_t)(ma) << 20) | ((uint32_t)(mb) << 26))
+
 #define CB_SH_DER 24
 #define CB_SH_KREC 18   // per-shell record for the stiffness pass: R[9], X2,X3,Y3, cm00,cm01,cm22, n0,n1,n2
 
@@ -213,6 +251,20 @@ struct CbDev {
     const double *br_const;  // [NE][4]  E, nu, rho, pad
 };
 
+// Launch configuration that is a property of the DEVICE (cudaFuncSetAttribute opt-ins above 48 KB of
+// dynamic shared memory, persistent grid = resident CTAs x SM count) is cached per device ordinal, not
+// per process: cb_flags.device makes several devices in one process a supported configuration.
+#define CB_MAX_DEVICES 64
+struct CbPerDevice {
+    int v[CB_MAX_DEVICES];           // 0 = not configured yet on that device
+};
+static inline int cb_device_slot()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < CB_MAX_DEVICES) ? dev : 0;
+}
+
 // ---- host launch wrappers implemented in the .cu files ------------------------------------
 struct CbStiffArgs {
     CbDev d;
@@ -230,6 +282,8 @@ struct CbStiffArgs {
     const double *kebc;      // DKT 3x3 sub-blocks in assembly order (static; layouts above)
     const CbTile2 *tiles2; long ntiles2; const CbWork *works; const CbTPair *tpairs2;
     const int32_t *tile_elems;
+    const CbTileS *tilesS; long ntilesS; const uint32_t *stepsS; const uint32_t *pairsS;   // stream plan
+    const int32_t *elemsS;
     int tile_smem_out;       // doubles of output staging per tile
     int max_dof;             // 3, 6 or 7: largest DOF count per joint among the model's elements
     int mixed;               // element types with different DOF counts per joint are present
@@ -279,6 +333,8 @@ int cbk_shell_init_kebc2(const CbDev &d, const CbTile2 *tiles, long ntiles, cons
                          const CbContrib *contribs, double *kebc, cudaStream_t s);
 int cbk_shell_init_kebc(const CbDev &d, const CbContrib *contribs, long ncontrib, double *kebc,
                         cudaStream_t s);
+int cbk_shell_init_kebcS(const CbDev &d, const CbTileS *tiles, long ntiles, const uint32_t *steps,
+                         const int32_t *elems, double *kebc, cudaStream_t s);
 int cbk_shell_prep(const CbDev &d, const double *x, const double *sh_frame, cudaStream_t s);
 int cbk_shell_class_tables(const CbDev &d, const int32_t *rep, int ncls, double *keb_tab, double *der_tab,
                            const CbWork *works, long nworks, const CbContrib *contribs, CbWork *works_cls,

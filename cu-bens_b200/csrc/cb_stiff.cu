@@ -1031,7 +1031,8 @@ template <bool CLS>
 static int launch_shell_tiles(const CbStiffArgs &a, cudaStream_t s)
 {
     const size_t smem = CB_T2_SMEM_BYTES(CLS);
-    static int grid_cache = 0;
+    static CbPerDevice cache{};                      // resident-CTA grid per device (0: not configured)
+    int &grid_cache = cache.v[cb_device_slot()];
     if (!grid_cache) {
         if (cudaFuncSetAttribute(k_assemble_shell_tiles<CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
@@ -1047,6 +1048,276 @@ static int launch_shell_tiles(const CbStiffArgs &a, cudaStream_t s)
     long grid = grid_cache;
     if (grid > a.ntiles2) grid = a.ntiles2;
     k_assemble_shell_tiles<CLS><<<(unsigned)grid, CB_T2_T, smem, s>>>(a);
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------------
+// CSC, shell-only models: "stream" tile kernel (plan: cb_internal.h, CbTileS).  One persistent WARP walks
+// tiles (runs of consecutive joints whose CSC columns are one contiguous slice of Ax); the warps of a CTA
+// share nothing, so there is no CTA barrier anywhere.  Per tile:
+//   * the records of the tile's distinct shells (krec, 144 B each, lane l brings slot l), its step and
+//     pair records arrive by cp.async, double-buffered one tile ahead; tile records and element ids are
+//     register-prefetched two / three tiles ahead;
+//   * every lane walks its steps: one contribution per step, the shell record read ONCE from shared
+//     memory (9 x 16 bytes), the full 6x6 accumulated in registers (FMA chains onto the running sum of
+//     the joint-pair block, reference order), the block written into the tile image ONCE (18 x 16-byte
+//     stores) when its last contribution has been added.  The planner hands whole blocks to lanes, so no
+//     partial sums are ever combined through shared memory (the duo kernel's read-modify-write rounds,
+//     its second read of every record and its CTA barriers are gone);
+//   * the finished image leaves as one bulk asynchronous copy shared -> global (TMA engine).
+// shared memory per warp: image | shell records x2 | step records x2 | pair records x2
+// ------------------------------------------------------------------------------------------
+#define CB_S_IMG_BYTES ((CB_S_IMG + 2) * 8)
+#define CB_S_KREC_BYTES (2 * CB_S_SLOTS * CB_SH_KREC * 8)
+#define CB_S_REC_BYTES (2 * CB_S_MAXSTEPS * 32 * 4)
+#define CB_S_PAIR_BYTES (2 * CB_S_PAIRS * 4)
+#define CB_S_WARP_BYTES (CB_S_IMG_BYTES + CB_S_KREC_BYTES + CB_S_REC_BYTES + CB_S_PAIR_BYTES)
+static_assert(CB_S_WARP_BYTES % 16 == 0 && CB_S_IMG_BYTES % 16 == 0, "per-warp regions stay 16-byte aligned");
+
+__device__ __forceinline__ CbTileS s_load_tile(const CbTileS *p)
+{
+    const int4 a = __ldg(reinterpret_cast<const int4 *>(p)), b = __ldg(reinterpret_cast<const int4 *>(p) + 1);
+    CbTileS t;
+    t.out0 = ((int64_t)(unsigned)a.x) | ((int64_t)a.y << 32);
+    t.nout = a.z; t.r0 = a.w; t.p0 = b.x; t.e0 = b.y;
+    t.nsteps = (uint8_t)(b.z & 0xff); t.np = (uint8_t)((b.z >> 8) & 0xff); t.ne = (uint8_t)((b.z >> 16) & 0xff);
+    t.pad = 0; t.pad2 = 0;
+    return t;
+}
+
+// stage one tile: lane l copies the record of shell slot l (9 x 16 B), two 16-byte chunks of the step
+// records and one of the pair records
+struct SEids { int v[2]; };          // element ids of slots lane and lane + 32
+__device__ __forceinline__ SEids s_load_eids(const CbStiffArgs &A, const CbTileS &tl, int lane)
+{
+    SEids e;
+    e.v[0] = (lane < tl.ne) ? __ldg(A.elemsS + tl.e0 + lane) : 0;
+    e.v[1] = (lane + 32 < tl.ne) ? __ldg(A.elemsS + tl.e0 + lane + 32) : 0;
+    return e;
+}
+__device__ __forceinline__ void s_issue_stage(const CbStiffArgs &A, const CbTileS &tl, const SEids &eid, int lane,
+                                              double *krec_dst, uint32_t *rec_dst, uint32_t *pair_dst)
+{
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int slot = lane + 32 * h;
+        if (slot < tl.ne) {
+            const double *src = A.d.sh_Nm + (long)eid.v[h] * CB_SH_KREC;
+#pragma unroll
+            for (int ch = 0; ch < 9; ++ch) CB_CPA(16, "cg", krec_dst + slot * CB_SH_KREC + ch * 2, src + ch * 2);
+        }
+    }
+    const uint32_t *rs = A.stepsS + (long)tl.r0 * 32;
+#pragma unroll
+    for (int k = 0; k < (CB_S_MAXSTEPS * 8 + 31) / 32; ++k) {
+        const int c = lane + 32 * k;
+        if (c < tl.nsteps * 8) CB_CPA(16, "cg", rec_dst + c * 4, rs + c * 4);
+    }
+    if (lane * 4 < tl.np) CB_CPA(16, "cg", pair_dst + lane * 4, A.pairsS + tl.p0 + lane * 4);
+}
+
+// acc (column-major 6x6: acc[q * 6 + r] = K[r][q]) += R^T-rotated local block (a, b) of one shell
+__device__ __forceinline__ void s_contrib(const double *kr /*shared*/, const double *kb, int a, int b, double *acc)
+{
+    double k[CB_SH_KREC];
+    {
+        const double2 *k2 = reinterpret_cast<const double2 *>(kr);
+#pragma unroll
+        for (int i = 0; i < CB_SH_KREC / 2; ++i) { const double2 v = k2[i]; k[2 * i] = v.x; k[2 * i + 1] = v.y; }
+    }
+    const double *R = k;
+    double bxa, bya, bxb, byb;
+    cst_grad(a, k[9], k[10], k[11], bxa, bya);
+    cst_grad(b, k[9], k[10], k[11], bxb, byb);
+    const double g = bxa * (k[15] * bxb + k[17] * byb) + bya * (k[17] * bxb + k[16] * byb);
+    const double s00 = k[12] * bxa * bxb + k[14] * bya * byb + g;
+    const double s01 = k[13] * bxa * byb + k[14] * bya * bxb;
+    const double s10 = k[13] * bya * bxb + k[14] * bxa * byb;
+    const double s11 = k[12] * bya * byb + k[14] * bxa * bxb + g;
+    const double s22 = kb[0] + g;
+    const double drill = (a == b) ? kb[4] / 10000 : 0.0;
+    double W0[3], W1[3], W2[3], U0[3], U1[3], U2[3], w[3], v[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        W0[q] = s00 * R[q] + s01 * R[3 + q];
+        W1[q] = s10 * R[q] + s11 * R[3 + q];
+        W2[q] = s22 * R[6 + q];
+        U0[q] = kb[4] * R[q] + kb[5] * R[3 + q];
+        U1[q] = kb[7] * R[q] + kb[8] * R[3 + q];
+        U2[q] = drill * R[6 + q];
+        w[q] = kb[1] * R[q] + kb[2] * R[3 + q];          // translation-rotation: e3 (x) (k01 e1 + k02 e2)
+        v[q] = kb[3] * R[q] + kb[6] * R[3 + q];          // rotation-translation: (k10 e1 + k20 e2) (x) e3
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            // three-FMA chains onto the running sum of the block (no separate add)
+            acc[q * 6 + p] = fma(R[6 + p], W2[q], fma(R[3 + p], W1[q], fma(R[p], W0[q], acc[q * 6 + p])));
+            acc[q * 6 + 3 + p] = fma(v[p], R[6 + q], acc[q * 6 + 3 + p]);
+            acc[(3 + q) * 6 + p] = fma(R[6 + p], w[q], acc[(3 + q) * 6 + p]);
+            acc[(3 + q) * 6 + 3 + p] =
+                fma(R[6 + p], U2[q], fma(R[3 + p], U1[q], fma(R[p], U0[q], acc[(3 + q) * 6 + 3 + p])));
+        }
+}
+
+template <bool CLS>
+__global__ void __launch_bounds__(32 * CB_S_WARPS, 1)
+k_assemble_shell_stream(CbStiffArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *wbase = smem_raw + (size_t)warp * CB_S_WARP_BYTES;
+    double *obuf = reinterpret_cast<double *>(wbase);                                           // [CB_S_IMG + 2]
+    double *skrec = reinterpret_cast<double *>(wbase + CB_S_IMG_BYTES);                         // [2][SLOTS][18]
+    uint32_t *srec = reinterpret_cast<uint32_t *>(wbase + CB_S_IMG_BYTES + CB_S_KREC_BYTES);     // [2][MAXSTEPS][32]
+    uint32_t *spair = srec + 2 * CB_S_MAXSTEPS * 32;                                             // [2][PAIRS]
+    const long G = (long)gridDim.x * CB_S_WARPS, N = A.ntilesS;
+    long tile = (long)blockIdx.x * CB_S_WARPS + warp;
+    if (tile >= N) return;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    // prologue: this tile staged directly, the next one's record and element ids in registers
+    CbTileS tl = s_load_tile(A.tilesS + tile), tln = tl, tlnn = tl;
+    SEids eid_n{};
+    {
+        const SEids eid = s_load_eids(A, tl, lane);
+        s_issue_stage(A, tl, eid, lane, skrec, srec, spair);
+        CB_CPA_COMMIT();
+        if (tile + G < N) {
+            tln = s_load_tile(A.tilesS + tile + G);
+            eid_n = s_load_eids(A, tln, lane);
+        }
+        if (tile + 2 * G < N) tlnn = s_load_tile(A.tilesS + tile + 2 * G);
+    }
+    int buf = 0;
+    bool img_busy = false;            // a bulk read-out of the image may still be in flight
+
+    double acc[36];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+
+    for (;;) {
+        const bool has_next = tile + G < N, has_next2 = tile + 2 * G < N, has_next3 = tile + 3 * G < N;
+        // the other buffer was last read by the previous tile (the warp re-converged at its end)
+        if (has_next)
+            s_issue_stage(A, tln, eid_n, lane, skrec + (buf ^ 1) * CB_S_SLOTS * CB_SH_KREC,
+                          srec + (buf ^ 1) * CB_S_MAXSTEPS * 32, spair + (buf ^ 1) * CB_S_PAIRS);
+        CB_CPA_COMMIT();
+        SEids eid_nn{};
+        CbTileS tl3 = tlnn;
+        if (has_next2) eid_nn = s_load_eids(A, tlnn, lane);
+        if (has_next3) tl3 = s_load_tile(A.tilesS + tile + 3 * G);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");       // this tile's records have landed
+        __syncwarp();
+
+        const double *kr0 = skrec + buf * CB_S_SLOTS * CB_SH_KREC;
+        const uint32_t *rec = srec + buf * CB_S_MAXSTEPS * 32 + lane;
+        const uint32_t *pairs = spair + buf * CB_S_PAIRS;
+        const int shift = (int)((tl.out0 + A.out_par) & 1);
+        const int nsteps = tl.nsteps;
+        const double *kbs = CLS ? nullptr : A.kebc + ((long)tl.r0 * 9) * 32 + lane;
+
+        uint32_t r = rec[0];
+#pragma unroll 1
+        for (int st = 0; st < nsteps; ++st) {
+            const uint32_t rn = (st + 1 < nsteps) ? rec[(st + 1) * 32] : CB_S_IDLE;
+            const unsigned slot = r & 63u;
+            if (slot != CB_S_IDLE) {
+                const int a = (r >> 6) & 3, b = (r >> 8) & 3;
+                double kb[9];
+                if (CLS) {
+                    const double *k0 = A.d.keb_tab + (r >> 18) * 81 + (3 * a + b) * 9;
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) kb[i] = __ldg(k0 + i);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) kb[i] = __ldg(kbs + ((long)st * 9 + i) * 32);
+                }
+                s_contrib(kr0 + slot * CB_SH_KREC, kb, a, b, acc);
+            }
+            const bool last = (slot != CB_S_IDLE) && ((r >> 10) & 1u);
+            if (__any_sync(FULL, last)) {
+                if (img_busy) {        // the copy engine must have read the previous image out
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                    img_busy = false;
+                }
+                if (last) {
+                    const uint32_t pr = pairs[(r >> 11) & 127u];
+                    const int rel = pr & 0xfff, colh = (pr >> 12) & 0xff;
+                    const unsigned maskA = (pr >> 20) & 0x3f, maskB = pr >> 26;
+                    double *img = obuf + shift + rel;
+                    if (maskA == 0x3f && maskB == 0x3f && ((((shift + rel) | colh) & 1) == 0)) {
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) {
+                            double2 *col = reinterpret_cast<double2 *>(img + q * colh);
+                            col[0] = make_double2(acc[q * 6], acc[q * 6 + 1]);
+                            col[1] = make_double2(acc[q * 6 + 2], acc[q * 6 + 3]);
+                            col[2] = make_double2(acc[q * 6 + 4], acc[q * 6 + 5]);
+                        }
+                    } else {
+                        int cc = 0;
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) {
+                            if (!((maskB >> q) & 1)) continue;
+                            double *col = img + cc * colh;
+                            int rr = 0;
+#pragma unroll
+                            for (int p = 0; p < 6; ++p)
+                                if ((maskA >> p) & 1) col[rr++] = acc[q * 6 + p];
+                            ++cc;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+                }
+            }
+            r = rn;
+        }
+        // writes of the image (generic proxy) ordered before the copy engine's reads (async proxy)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            double *dst = A.out + tl.out0;
+            const double *im = obuf + shift;
+            const int nv = (tl.nout - shift) >> 1;
+            if (nv > 0)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + shift),
+                             "r"(t2_saddr(im + shift)), "r"(nv * 16)
+                             : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (shift) dst[0] = im[0];
+            const int tail = shift + 2 * nv;
+            if (tail < tl.nout) dst[tail] = im[tail];
+        }
+        img_busy = true;
+        if (!has_next) break;
+        tile += G; tl = tln; tln = tlnn; tlnn = tl3; eid_n = eid_nn; buf ^= 1;
+        __syncwarp();
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <bool CLS>
+static int launch_shell_stream(const CbStiffArgs &a, cudaStream_t s)
+{
+    const size_t smem = (size_t)CB_S_WARPS * CB_S_WARP_BYTES;
+    static CbPerDevice cache{};                      // SM count per device (0: not configured)
+    int &nsm = cache.v[cb_device_slot()];
+    if (!nsm) {
+        if (cudaFuncSetAttribute(k_assemble_shell_stream<CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess)
+            return 1;
+        int dev = 0, n = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        nsm = n;
+    }
+    long grid = nsm;                                 // persistent: one CTA of CB_S_WARPS independent warps per SM
+    const long need = (a.ntilesS + CB_S_WARPS - 1) / CB_S_WARPS;
+    if (grid > need) grid = need;
+    k_assemble_shell_stream<CLS><<<(unsigned)grid, 32 * CB_S_WARPS, smem, s>>>(a);
     return cudaGetLastError() != cudaSuccess;
 }
 
@@ -1128,12 +1399,13 @@ static int launch_tiles(const CbStiffArgs &a, cudaStream_t s)
 {
     const size_t smem = (size_t)(((ND * ND * (CB_TILE_T + 1) + 1) & ~1) + a.tile_smem_out) * sizeof(double) +
                         CB_TILE_T * sizeof(CbTPair) + CB_TILE_T;
-    static bool configured = false;
+    static CbPerDevice cfg{};
+    int &configured = cfg.v[cb_device_slot()];
     if (!configured) {
         if (cudaFuncSetAttribute(k_assemble_tiles<ND, SHELL_ONLY, FRAME_SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  200 * 1024) != cudaSuccess)
             return 1;
-        configured = true;
+        configured = 1;
     }
     if (smem > 200 * 1024) return 1;
     int per_sm = 0, dev = 0, nsm = 148;
@@ -1155,6 +1427,10 @@ int cbk_stiff(const CbStiffArgs &a, cudaStream_t s, long *launches)
         const long n = a.d.NE_BR * 8;
         k_brick_prep<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, a.br_prep);
         ++*launches;
+    }
+    if (!a.skyline && a.ntilesS > 0 && a.tilesS) {
+        ++*launches;
+        return a.d.keb_tab ? launch_shell_stream<true>(a, s) : launch_shell_stream<false>(a, s);
     }
     if (!a.skyline && a.ntiles2 > 0 && a.tiles2) {
         ++*launches;

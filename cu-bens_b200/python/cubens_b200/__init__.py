@@ -38,6 +38,7 @@ EXPORTS = [
     "cb_dev_sums", "cb_get_sums", "cb_get_yldflag", "cb_set_yldflag", "cb_get_mass_csc_values", "cb_dev_Mx",
     "cb_geometry_classes", "cb_keep_ip", "cb_checkpoint_save", "cb_checkpoint_load",
     "cb_set_element_ids", "cb_update_forces_begin", "cb_update_forces_end", "cb_measure_fp64_tflops",
+    "cb_plan_selfcheck",
 ]
 
 
@@ -102,6 +103,35 @@ def _p(a):
     return C.c_void_p(a.ctypes.data) if a is not None and a.size else C.c_void_p(0)
 
 
+def _c_model(m, layout, device):
+    """the C structs of include/cubens_b200.h for a Model (plus the arrays that must stay alive)"""
+    sz = cb_sizes(m.NJ, m.NE_TR, m.NE_FR, m.NE_SH, m.NE_SBR, m.NE_FBR, m.NEQ)
+    fl = cb_flags(m.ANAFLAG, m.ALGFLAG, m.SLVFLAG, layout, device)
+    keep = {}
+    cm = cb_model()
+    for n in _MODEL_FIELDS:
+        a = getattr(m, "yld" if n == "yield" else n, None)
+        if a is not None:
+            dt = np.int32 if n in ("osflag", "mendrel") else (np.int64 if n in ("minc", "jcode", "mcode", "maxa") else np.float64)
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep[n] = a
+        setattr(cm, n, _p(a) if a is not None else C.c_void_p(0))
+    return sz, fl, cm, keep
+
+
+def plan_selfcheck(m, j0=0, j1=0, layout=CB_MAT_CSC):
+    """cb_plan_selfcheck: build the element-to-nonzero maps / tile plans of ``m`` on the host (no device)
+    and interpret them the way the kernels do.  Returns dict(nnz, tiles, rows, pairs, steps, kind);
+    raises CubensError when the plan is inconsistent."""
+    lib = load_library()
+    sz, fl, cm, keep = _c_model(m, layout, 0)
+    st = (C.c_long * 6)()
+    rc = lib.cb_plan_selfcheck(C.byref(sz), C.byref(fl), C.byref(cm), C.c_long(j0), C.c_long(j1), st)
+    if rc != 0:
+        raise CubensError(f"cb_plan_selfcheck error {rc}: {lib.cb_last_error().decode()}")
+    return dict(zip(("nnz", "tiles", "rows", "pairs", "steps", "kind"), list(st)))
+
+
 class Assembler:
     """One model resident on one B200.  Method names follow the reference call sites they
     replace (see include/cubens_b200.h for the file:line table)."""
@@ -111,17 +141,7 @@ class Assembler:
         self.m = m
         if self.lib.cb_device_count() <= 0:
             raise CubensError("no CUDA device visible - the element/assembly path has no CPU fallback")
-        sz = cb_sizes(m.NJ, m.NE_TR, m.NE_FR, m.NE_SH, m.NE_SBR, m.NE_FBR, m.NEQ)
-        fl = cb_flags(m.ANAFLAG, m.ALGFLAG, m.SLVFLAG, layout, device)
-        keep = {}
-        cm = cb_model()
-        for n in _MODEL_FIELDS:
-            a = getattr(m, "yld" if n == "yield" else n, None)
-            if a is not None:
-                dt = np.int32 if n in ("osflag", "mendrel") else (np.int64 if n in ("minc", "jcode", "mcode", "maxa") else np.float64)
-                a = np.ascontiguousarray(a, dtype=dt)
-                keep[n] = a
-            setattr(cm, n, _p(a) if a is not None else C.c_void_p(0))
+        sz, fl, cm, keep = _c_model(m, layout, device)
         h = C.c_void_p(0)
         rc = self.lib.cb_create(C.byref(sz), C.byref(fl), C.byref(cm), C.byref(h))
         self._check(rc)
@@ -255,6 +275,11 @@ class Assembler:
         self._check(self.lib.cb_csc_pattern(self.h, _p(Ap), _p(Ai)))
         self._check(self.lib.cb_get_csc_values(self.h, _p(Ax)))
         return Ap, Ai, Ax
+
+    def csc_values(self):
+        Ax = np.zeros(self.lib.cb_csc_nnz(self.h))
+        self._check(self.lib.cb_get_csc_values(self.h, _p(Ax)))
+        return Ax
 
     def csc_compact(self, drop_tol=1e-10):
         nnz = self.lib.cb_csc_nnz(self.h)

@@ -91,9 +91,17 @@ def partition_model(m, world, rank):
     by_el = np.concatenate([tr, TR + fr, TR + FR + sh])                  # emod / yld
     s.emod, s.yld = m.emod[by_el], m.yld[by_el]
     # dens[n] is indexed by the element's number WITHIN its type for every type (App. B.4)
+    # - the same prefix of one array for trusses, frames and shells.  A mixed-type partition therefore
+    # only has a faithful dens[] when the types agree on those prefixes (uniform density, or one type)
     s.dens = np.zeros(ntr + nfr + nsh)
     for idx in (tr, fr, sh):
-        s.dens[:len(idx)] = m.dens[idx]
+        want = m.dens[idx]
+        have = s.dens[:len(idx)]
+        clash = (have != 0) & (have != want)
+        if clash.any():
+            raise ValueError("partition_model: dens[n] is shared by all element types (reference App. B.4); "
+                             "a mixed-type partition with non-uniform densities cannot be represented")
+        s.dens[:len(idx)] = want
     lin = np.concatenate([tr, TR + fr])
     s.carea, s.llength = m.carea[lin], m.llength[lin]
     three = lambda idx: (idx[:, None] * 3 + np.arange(3)).reshape(-1)

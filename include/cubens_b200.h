@@ -267,6 +267,12 @@ int  cb_sync(cb_handle *h);
 /* FP64 DFMA throughput of the device in TFLOP/s (micro-kernel, CUDA events, best of 5): the FP64
  * roofline denominator bench.py reports next to the HBM one; < 0 on failure     */
 double cb_measure_fp64_tflops(int device);
+/* Host-only consistency check of the element-to-nonzero maps and tile plans a model would get (joint
+ * scan, CSC geometry, tile packing, lane assignment), interpreted the way the kernels walk them; needs
+ * no device.  j0 = j1 = 0: all joints.  stats (may be NULL) receives nnz, tiles, step rows, pair records,
+ * mean steps per tile, plan kind (3 stream, 2 duo, 1 general tiles, 0 block-owner).                 */
+int  cb_plan_selfcheck(const cb_sizes *sz, const cb_flags *fl, const cb_model *m, long j0, long j1,
+                       long *stats);
 /* the CUDA stream (cudaStream_t cast to void*) all of this handle's kernels run on         */
 void *cb_stream(cb_handle *h);
 

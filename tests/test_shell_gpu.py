@@ -97,3 +97,25 @@ def test_residual_sums(gpu):
     s2 = asm.residual_sums(0.7, fetch=True)
     assert np.array_equal(s, s2)
     asm.close()
+
+
+def test_upload_geometry_rebuilds_derived_data(gpu):
+    """restart path: uploading FAREA / SLENGTH must rebuild the cached DKT matrices and
+    drop the geometry classes, exactly as cb_mass does after rewriting them"""
+    m = meshgen.plate_model(8, 6, z_bump=0.03)
+    dd = meshgen.perturbation(m, scale=1e-3)
+    a = cb.Assembler(m, layout=cb.CB_MAT_BOTH)
+    a.begin_increment(); a.update_forces(dd); a.end_iteration(); a.commit()
+    a.mass()                                   # slength / farea <- committed coordinates
+    a.begin_increment(); a.stiff()
+    K1, A1 = a.skyline(), a.csc_values()
+    fa, sl = a.download("FAREA"), a.download("SLENGTH")
+    assert not np.array_equal(fa, m.farea)
+    a.close()
+    b = cb.Assembler(m, layout=cb.CB_MAT_BOTH)
+    b.begin_increment(); b.stiff()             # builds the plan and the initial-geometry tables first
+    b.update_forces(dd); b.end_iteration(); b.commit()
+    b.upload("FAREA", fa); b.upload("SLENGTH", sl)
+    b.begin_increment(); b.stiff()
+    assert np.array_equal(b.skyline(), K1) and np.array_equal(b.csc_values(), A1)
+    b.close()

@@ -30,6 +30,33 @@ def skyline_to_dense(n, maxa, ss):
     return K
 
 
+def csc_vs_skyline(m, Ap, Ai, Ax, ss):
+    """device CSC (full, unsymmetric storage, structural joint-block pattern) against the reference's
+    skyline vector, entry by entry: entry (i <= j) lives at ss[maxa[j-1] + (j-i) - 1] (1-based,
+    model.c:1269-1278; shell.c:307-329 / frame.c:330-352 scatter the element's upper triangle there).
+    The lower triangle of the CSC is compared with the same skyline entries (K_t is symmetric).
+    Structural CSC entries outside the skyline profile must be exactly zero.  Returns
+    (norm-wise relative difference, entry-wise difference scaled by sqrt(K_ii K_jj))."""
+    n = m.NEQ
+    maxa = np.asarray(m.maxa, dtype=np.int64)
+    cols = np.repeat(np.arange(n, dtype=np.int64), np.diff(Ap))
+    rows = np.asarray(Ai, dtype=np.int64)
+    lo, hi = np.minimum(rows, cols), np.maximum(rows, cols)
+    addr = maxa[hi] - 1 + (hi - lo)
+    inside = addr < maxa[hi + 1] - 1
+    assert np.all(Ax[~inside] == 0.0), "non-zero CSC entry outside the reference's skyline profile"
+    # every skyline entry the reference wrote must be present in the CSC pattern
+    seen = np.zeros(ss.size, dtype=bool)
+    seen[addr[inside]] = True
+    assert np.all(ss[~seen] == 0.0), "reference skyline entry missing from the CSC pattern"
+    want = ss[addr[inside]]
+    diff = np.abs(Ax[inside] - want)
+    diag = np.abs(ss[maxa[:-1] - 1])
+    scale = np.sqrt(diag[lo[inside]] * diag[hi[inside]])
+    assert np.all(scale > 0)
+    return diff.max() / np.abs(ss).max(), (diff / scale).max()
+
+
 TOL = 1e-12
 
 

@@ -92,6 +92,7 @@ struct Plan {
     // stream plan (k_assemble_shell_stream)
     DevBuf<CbTileS> tilesS; DevBuf<uint32_t> stepsS, pairsS; DevBuf<int32_t> elemsS;
     long ntilesS = 0, nrowsS = 0;
+    int shapeS = 1; CbStreamShape shape = CB_S_SHAPE_NARROW;
     int tile_smem_out = 0;
 };
 
@@ -139,7 +140,7 @@ struct cb_handle {
     // geometry classes (cb_internal.h): class of each shell, representatives, tables, work records
     DevBuf<int32_t> sh_class, cls_rep;
     std::vector<int32_t> h_cls;   // host copy of sh_class (the stream plan packs it into its step records)
-    DevBuf<double> keb_tab, der_tab;
+    DevBuf<double> keb_tab, keb_tab10, der_tab;
     DevBuf<CbWork> works_cls;
     int ncls = 0;
     bool cls_on = false;
@@ -204,7 +205,7 @@ static CbDev make_dev(cb_handle *h)
     d.fr_osflag = h->fr_osflag.p; d.fr_mendrel = h->fr_mendrel.p; d.fr_simple = h->fr_simple;
     d.fr_efFE_ref = h->fr_efFE_ref.p; d.fr_fg = h->fr_fg.p;
     d.fr_plast = h->fr_plast.p; d.fr_yldflag = h->fr_yldflag.p; d.fr_ynew = h->fr_ynew.p;
-    if (h->cls_on) { d.sh_class = h->sh_class.p; d.keb_tab = h->keb_tab.p; d.der_tab = h->der_tab.p; }
+    if (h->cls_on) { d.sh_class = h->sh_class.p; d.keb_tab = h->keb_tab.p; d.keb_tab10 = h->keb_tab10.p; d.der_tab = h->der_tab.p; }
     d.sh_yield = h->sh_yield.p; d.sh_pl = h->sh_pl[1].p; d.sh_yv = h->sh_yv.p; d.sh_kpl = h->sh_kpl.p;
     d.sh_trip = h->sh_trip.p;
     d.fr_code = h->fr_code.p; d.fr_tau = h->fr_tau.p; d.fr_trip = h->fr_trip.p; d.tr_py = h->tr_py.p;
@@ -512,7 +513,7 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
             if (ok && getenv("CB_NO_GEOMETRY_CLASSES") == nullptr) {
                 h->ncls = (int)rep.size();
                 h->h_cls = cls;
-                if (h->sh_class.upload(cls) || h->cls_rep.upload(rep) || h->keb_tab.alloc((size_t)h->ncls * 81) ||
+                if (h->sh_class.upload(cls) || h->cls_rep.upload(rep) || h->keb_tab.alloc((size_t)h->ncls * 81) || h->keb_tab10.alloc((size_t)h->ncls * 90) ||
                     h->der_tab.alloc((size_t)h->ncls * CB_SH_DER))
                     BAIL(CB_ERR_CUDA);
                 h->cls_on = true;
@@ -555,7 +556,7 @@ extern "C" void cb_destroy(cb_handle *h)
                               &h->fr_offset, &h->fr_efFE_ref, &h->fr_fg, &h->fr_dens, &h->br_const, &h->br_prep,
                               &h->Ax, &h->ss, &h->Mx, &h->fr_plast, &h->fr_tau, &h->tr_py})
         b->release();
-    h->sh_class.release(); h->cls_rep.release(); h->keb_tab.release(); h->der_tab.release(); h->works_cls.release();
+    h->sh_class.release(); h->cls_rep.release(); h->keb_tab.release(); h->keb_tab10.release(); h->der_tab.release(); h->works_cls.release();
     for (DevBuf<int32_t> *b : {&h->fr_yldflag, &h->fr_ynew, &h->fr_code, &h->fr_trip, &h->sh_yv, &h->sh_trip})
         b->release();
     h->sh_yield.release(); h->sh_pl[0].release(); h->sh_pl[1].release(); h->sh_kpl.release();
@@ -836,65 +837,182 @@ static int build_plan(cb_handle *h)
     bool plan2_ok = tiles_ok && h->sz.NE_SH && !h->sz.NE_TR && !h->sz.NE_FR && !h->NE_BR &&
                     h->max_dof == 6 && !h->mixed && h->fl.ANAFLAG != 3;   // yielded shells: general kernel
     // ---- shell-only models, first choice: the "stream" plan of k_assemble_shell_stream ----------------
-    // (cb_internal.h, CbTileS).  Tiles are runs of consecutive joints; the joint-pair blocks of a tile are
-    // handed to the 32 lanes of one warp WHOLE and in their natural order (next-fit with capacity S =
-    // max(6, largest contribution count in the tile)): a lane's steps are the contributions of its blocks
-    // in reference order, the last step of a block carries the store flag.
+    // (cb_internal.h, CbStreamShape / CbTileS).  Tiles are runs of consecutive joints; the joint-pair
+    // blocks of a tile are handed to the 32 lanes of one warp WHOLE (a block with more contributions than
+    // a lane has steps is cut in two, the second part a follower): per joint, parts in decreasing size,
+    // first lane with room (a follower closes its lane).  A lane's steps are the contributions of its
+    // parts in reference order; the last step of a part carries the store flag.
     std::vector<CbTileS> tilesS; std::vector<uint32_t> stepsS, pairsS; std::vector<int32_t> elemsS;
     std::vector<int32_t> blkS;                // pairs_csc index of every pair record (plan check)
     const char *kt_env = getenv("CB_KT");
     bool planS_ok = plan2_ok && !(kt_env && strcmp(kt_env, "duo") == 0);
+    const CbStreamShape shapes[2] = {CB_S_SHAPE_WIDE, CB_S_SHAPE_NARROW};
+    const int shape_id = (kt_env && strcmp(kt_env, "wide") == 0) ? 0 : 1;
+    const CbStreamShape shp = shapes[shape_id];
     if (planS_ok) {
+        struct Part { int32_t blk; uint8_t c0, cnt, follow; };       // blk: index into the tile's block list
+        struct LaneS { int load = 0; bool closed = false; std::vector<Part> parts; };
         std::vector<size_t> blocks;           // pairs_csc indices of the open tile
-        std::vector<int32_t> curel;
-        int64_t out0 = 0; long nout = 0; int smax = 6; bool open = false;
-        auto lanes_needed = [&](const std::vector<size_t> &bl, size_t extra0, size_t extra1, int S) {
-            int lanes = 0, load = S + 1;      // forces a new lane for the first block
-            auto put = [&](int cnt) { if (load + cnt > S) { ++lanes; load = 0; } load += cnt; };
-            for (size_t q : bl) put(pairs_csc[q].ccount);
-            for (size_t q = extra0; q < extra1; ++q) put(pairs_csc[q].ccount);
-            return lanes;
+        std::vector<int32_t> curel, curel_slots; std::vector<int> slot_of;
+        std::vector<LaneS> lanes;
+        int64_t out0 = 0; long nout = 0; bool open = false;
+        const int S = shp.steps;
+        // place the parts of joint blocks [q0, q1) into `ln` (first-fit, decreasing size); false if > 32 lanes
+        auto place = [&](std::vector<LaneS> &ln, size_t q0, size_t q1, int blk0) {
+            std::vector<Part> parts;
+            for (size_t q = q0; q < q1; ++q) {
+                const int cnt = pairs_csc[q].ccount, b = blk0 + (int)(q - q0);
+                if (cnt <= S) parts.push_back({b, 0, (uint8_t)cnt, 0});
+                else {
+                    const int h = (cnt + 1) / 2;
+                    parts.push_back({b, 0, (uint8_t)h, 0});
+                    parts.push_back({b, (uint8_t)h, (uint8_t)(cnt - h), 1});
+                }
+            }
+            std::stable_sort(parts.begin(), parts.end(), [](const Part &x, const Part &y) { return x.cnt > y.cnt; });
+            for (const Part &pt : parts) {
+                size_t l = 0;
+                for (; l < ln.size(); ++l)
+                    if (!ln[l].closed && ln[l].load + pt.cnt <= S) break;
+                if (l == ln.size()) { if (ln.size() == 32) return false; ln.emplace_back(); }
+                ln[l].parts.push_back(pt); ln[l].load += pt.cnt;
+                if (pt.follow) ln[l].closed = true;          // a follower is the last part of its lane
+            }
+            return true;
         };
         auto close_tile = [&]() {
+            const size_t ti = tilesS.size();
             CbTileS t{};
-            t.out0 = out0; t.nout = (int32_t)nout; t.r0 = (int32_t)(stepsS.size() / 32);
-            t.p0 = (int32_t)pairsS.size(); t.e0 = (int32_t)elemsS.size();
+            t.out0 = out0; t.nout = (int32_t)nout;
             t.np = (uint8_t)blocks.size(); t.ne = (uint8_t)curel.size();
-            // lane loads first (nsteps = the longest lane), then the records
-            int lane = -1, load = smax + 1, nsteps = 0;
-            std::vector<std::pair<int, int>> where(blocks.size());      // (lane, first step) of each block
-            for (size_t k = 0; k < blocks.size(); ++k) {
-                const int cnt = pairs_csc[blocks[k]].ccount;
-                if (load + cnt > smax) { ++lane; load = 0; }
-                where[k] = {lane, load};
-                load += cnt; nsteps = std::max(nsteps, load);
-            }
+            int nsteps = 0;
+            for (const LaneS &l : lanes) nsteps = std::max(nsteps, l.load);
             t.nsteps = (uint8_t)nsteps;
-            stepsS.resize(stepsS.size() + (size_t)nsteps * 32, CB_S_IDLE);
+            // ---- lane order and shell slots: performance only (the interpreter check does not care) ----
+            // (1) lanes that store at the same steps sit next to each other, so that a 16-byte store
+            // instruction touches as few quarter-warps as possible (a shared-memory wavefront serves one
+            // quarter-warp); inside such a group the lanes of one aligned octet get blocks whose image
+            // offsets fall into distinct 16-byte bank groups, as far as a greedy pick manages.
+            {
+                const int shift = (int)((out0 + h->ax_pad) & 1);
+                struct LInfo { unsigned sig; int key[CB_S_MAXSTEPS_ANY]; };
+                std::vector<LInfo> info(lanes.size());
+                for (size_t l = 0; l < lanes.size(); ++l) {
+                    LInfo &li = info[l]; li.sig = 0;
+                    for (int k = 0; k < CB_S_MAXSTEPS_ANY; ++k) li.key[k] = -1;
+                    int st = 0;
+                    for (const Part &pt : lanes[l].parts) {
+                        st += pt.cnt;
+                        const CbPair &p = pairs_csc[blocks[pt.blk]];
+                        const int rel = (int)(p.off - out0);
+                        const bool fast = p.maskA == 0x3f && p.maskB == 0x3f && !((shift + rel) & 1) && !(p.colh & 1);
+                        if (pt.follow) li.sig |= 1u << 31;
+                        else { li.sig |= 1u << (st - 1); li.key[st - 1] = fast ? ((shift + rel) >> 1) & 7 : -1; }
+                    }
+                }
+                std::vector<size_t> order(lanes.size());
+                for (size_t l = 0; l < order.size(); ++l) order[l] = l;
+                std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return info[x].sig < info[y].sig; });
+                std::vector<size_t> fin; fin.reserve(order.size());
+                std::vector<uint8_t> taken(order.size(), 0);
+                uint8_t used[CB_S_MAXSTEPS_ANY][8];
+                for (size_t pos = 0; pos < order.size(); ++pos) {
+                    if ((pos & 7) == 0) memset(used, 0, sizeof used);
+                    size_t head = 0;
+                    while (taken[head]) ++head;
+                    const unsigned sig = info[order[head]].sig;
+                    size_t pick = head;
+                    for (size_t c = head, seen = 0; c < order.size() && info[order[c]].sig == sig && seen < 16; ++c) {
+                        if (taken[c]) continue;
+                        ++seen;
+                        bool clash = false;
+                        for (int k = 0; k < CB_S_MAXSTEPS_ANY; ++k) { const int ky = info[order[c]].key[k]; if (ky >= 0 && used[k][ky]) clash = true; }
+                        if (!clash) { pick = c; break; }
+                    }
+                    taken[pick] = 1; fin.push_back(order[pick]);
+                    for (int k = 0; k < CB_S_MAXSTEPS_ANY; ++k) { const int ky = info[order[pick]].key[k]; if (ky >= 0) used[k][ky] = 1; }
+                }
+                std::vector<LaneS> sorted; sorted.reserve(lanes.size());
+                for (size_t l : fin) sorted.push_back(std::move(lanes[l]));
+                lanes.swap(sorted);
+            }
+            // (2) shell slots: the records of the shells read by one aligned octet of lanes in one step
+            // should sit in distinct 16-byte bank groups, i.e. slot numbers distinct modulo 8 (a record is
+            // nine 16-byte units long).  Greedy colouring, then slots handed out per colour.
+            {
+                const int ne = (int)curel.size();
+                std::vector<std::vector<int>> adjc(ne);
+                std::vector<std::vector<int>> byslot(lanes.size());          // per lane: shell index of every step
+                for (size_t l = 0; l < lanes.size(); ++l)
+                    for (const Part &pt : lanes[l].parts) {
+                        const CbPair &p = pairs_csc[blocks[pt.blk]];
+                        for (int c = 0; c < pt.cnt; ++c)
+                            byslot[l].push_back((int)(std::find(curel.begin(), curel.end(), contribs[p.cstart + pt.c0 + c].e) - curel.begin()));
+                    }
+                for (size_t o = 0; o < lanes.size(); o += 8)
+                    for (int st = 0; st < nsteps; ++st)
+                        for (size_t x = o; x < std::min(o + 8, lanes.size()); ++x)
+                            for (size_t y = x + 1; y < std::min(o + 8, lanes.size()); ++y)
+                                if (st < (int)byslot[x].size() && st < (int)byslot[y].size() && byslot[x][st] != byslot[y][st]) {
+                                    adjc[byslot[x][st]].push_back(byslot[y][st]); adjc[byslot[y][st]].push_back(byslot[x][st]);
+                                }
+                std::vector<int> colour(ne, -1), cap(8, 0), cnt(8, 0);
+                for (int k = 0; k < shp.slots; ++k) ++cap[k & 7];
+                std::vector<int> ord(ne);
+                for (int e = 0; e < ne; ++e) ord[e] = e;
+                std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return adjc[x].size() > adjc[y].size(); });
+                for (int e : ord) {
+                    int clash[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    for (int o : adjc[e]) if (colour[o] >= 0) ++clash[colour[o]];
+                    int best = -1;
+                    for (int c = 0; c < 8; ++c)
+                        if (cnt[c] < cap[c] && (best < 0 || clash[c] < clash[best])) best = c;
+                    colour[e] = best; ++cnt[best];
+                }
+                std::vector<int32_t> perm(shp.slots, -1);
+                int nextslot[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+                slot_of.assign(ne, 0);
+                for (int e = 0; e < ne; ++e) { slot_of[e] = nextslot[colour[e]]; perm[slot_of[e]] = curel[e]; nextslot[colour[e]] += 8; }
+                // compact is not required: unused slots repeat a valid shell (they are staged but never read)
+                std::vector<int32_t> ncur(shp.slots, curel[0]);
+                for (int k = 0; k < shp.slots; ++k) if (perm[k] >= 0) ncur[k] = perm[k];
+                curel_slots = ncur;
+            }
+            stepsS.resize((ti + 1) * (size_t)S * 32, CB_S_IDLE);
+            for (size_t l = 0; l < lanes.size(); ++l) {
+                int st = 0;
+                for (const Part &pt : lanes[l].parts) {
+                    const CbPair &p = pairs_csc[blocks[pt.blk]];
+                    for (int c = 0; c < pt.cnt; ++c, ++st) {
+                        const CbContrib &ct = contribs[p.cstart + pt.c0 + c];
+                        const int slot = slot_of[std::find(curel.begin(), curel.end(), ct.e) - curel.begin()];
+                        const int cls = h->cls_on ? h->h_cls[ct.e] : 0;
+                        stepsS[(ti * S + st) * 32 + l] = CB_S_REC(slot, ct.a, ct.b, c == 0, c == pt.cnt - 1, pt.follow, pt.blk, cls);
+                    }
+                }
+            }
+            pairsS.resize((ti + 1) * (size_t)shp.pairs, 0); blkS.resize((ti + 1) * (size_t)shp.pairs, -1);
             for (size_t k = 0; k < blocks.size(); ++k) {
                 const CbPair &p = pairs_csc[blocks[k]];
-                for (int c = 0; c < p.ccount; ++c) {
-                    const CbContrib &ct = contribs[p.cstart + c];
-                    const int slot = (int)(std::find(curel.begin(), curel.end(), ct.e) - curel.begin());
-                    const int cls = h->cls_on ? h->h_cls[ct.e] : 0;
-                    stepsS[((size_t)t.r0 + where[k].second + c) * 32 + where[k].first] =
-                        CB_S_REC(slot, ct.a, ct.b, c == p.ccount - 1, k, cls);
-                }
-                pairsS.push_back(CB_S_PAIR(p.off - out0, p.colh, p.maskA, p.maskB));
-                blkS.push_back((int32_t)blocks[k]);
+                pairsS[ti * shp.pairs + k] = CB_S_PAIR(p.off - out0, p.colh, p.maskA, p.maskB);
+                blkS[ti * shp.pairs + k] = (int32_t)blocks[k];
             }
-            while (pairsS.size() & 3) { pairsS.push_back(0); blkS.push_back(-1); }
-            elemsS.insert(elemsS.end(), curel.begin(), curel.end());
+            elemsS.resize((ti + 1) * (size_t)shp.slots, 0);          // unused slots repeat a valid shell
+            std::copy(curel_slots.begin(), curel_slots.end(), elemsS.begin() + ti * shp.slots);
+            t.ne = (uint8_t)shp.slots;
             tilesS.push_back(t);
-            open = false; blocks.clear(); curel.clear();
+            open = false; blocks.clear(); curel.clear(); lanes.clear();
         };
         size_t i = 0;
+        std::vector<int32_t> newel;
         while (i < pairs_csc.size() && planS_ok) {
             size_t g1 = i;
             const int32_t B = pair_B[i];
             while (g1 < pairs_csc.size() && pair_B[g1] == B) ++g1;
-            int smax_n = 6;
-            std::vector<int32_t> newel;
+            int cmax = 0;
+            for (size_t q = i; q < g1; ++q) cmax = std::max(cmax, (int)pairs_csc[q].ccount);
+            const long out_n = (long)h->h_nfree[B] * h->colh[B];
+            if (cmax > 2 * S || h->colh[B] > 255 || (long)(g1 - i) > shp.pairs || out_n > shp.img) { planS_ok = false; break; }
             auto collect = [&](const std::vector<int32_t> &have) {
                 newel.clear();
                 for (size_t q = i; q < g1; ++q)
@@ -905,25 +1023,21 @@ static int build_plan(cb_handle *h)
                             newel.push_back(e);
                     }
             };
-            for (size_t q = i; q < g1; ++q) smax_n = std::max(smax_n, (int)pairs_csc[q].ccount);
-            const long out_n = (long)h->h_nfree[B] * h->colh[B];
-            if (smax_n > CB_S_MAXSTEPS || h->colh[B] > 255 || (int)(g1 - i) > CB_S_PAIRS || out_n > CB_S_IMG) {
-                planS_ok = false; break;
+            bool placed = false;
+            if (open) {
+                collect(curel);
+                if (h->base[B] - h->ax_base == out0 + nout && nout + out_n <= shp.img &&
+                    curel.size() + newel.size() <= (size_t)shp.slots && blocks.size() + (g1 - i) <= (size_t)shp.pairs) {
+                    std::vector<LaneS> trial = lanes;
+                    if (place(trial, i, g1, (int)blocks.size())) { lanes.swap(trial); placed = true; }
+                }
+                if (!placed) close_tile();
             }
-            auto fits = [&](const std::vector<size_t> &bl, long no, int S, size_t ne) {
-                return lanes_needed(bl, i, g1, S) <= 32 && no <= CB_S_IMG && ne <= (size_t)CB_S_SLOTS &&
-                       bl.size() + (g1 - i) <= (size_t)CB_S_PAIRS;
-            };
-            collect(curel);
-            if (open && (!fits(blocks, nout + out_n, std::max(smax, smax_n), curel.size() + newel.size()) ||
-                         h->base[B] - h->ax_base != out0 + nout))
-                close_tile();
-            if (!open) {
-                collect(curel);                                   // curel is empty now
-                if (!fits(blocks, out_n, smax_n, newel.size())) { planS_ok = false; break; }
-                out0 = h->base[B] - h->ax_base; nout = 0; smax = 6; open = true;
+            if (!placed) {
+                curel.clear(); collect(curel);
+                if (newel.size() > (size_t)shp.slots || !place(lanes, i, g1, 0)) { planS_ok = false; break; }
+                out0 = h->base[B] - h->ax_base; nout = 0; open = true;
             }
-            smax = std::max(smax, smax_n);
             curel.insert(curel.end(), newel.begin(), newel.end());
             for (size_t q = i; q < g1; ++q) blocks.push_back(q);
             nout += out_n;
@@ -931,59 +1045,71 @@ static int build_plan(cb_handle *h)
         }
         if (planS_ok && open) close_tile();
         if (planS_ok && tilesS.empty()) planS_ok = false;
-        if (planS_ok && stepsS.size() / 32 > 0x7fffffffUL / 9) planS_ok = false;
+        if (planS_ok && tilesS.size() * (size_t)S * 9 * 32 > 0x7fffffffffffUL) planS_ok = false;
         if (!planS_ok) { tilesS.clear(); stepsS.clear(); pairsS.clear(); elemsS.clear(); blkS.clear(); }
     }
     // Interpreter check of the stream plan (always in cb_plan_selfcheck, or with CB_PLAN_CHECK set): walk
     // the records exactly as the kernel does and verify that every joint-pair block is accumulated from
-    // precisely its contribution list (reference order), stored once, that the blocks of a tile tile its
-    // output range without overlap or gap, and that the tiles cover the owned slice of Ax contiguously.
+    // precisely its contribution list (reference order; a follower part continues where the first part
+    // stopped), stored once, that the blocks of a tile tile its output range without overlap or gap, and
+    // that the tiles cover the owned slice of Ax contiguously.
     if (planS_ok && (g_host_only || getenv("CB_PLAN_CHECK"))) {
         int64_t expect = 0;
+        const int S = shp.steps;
         for (size_t ti = 0; ti < tilesS.size(); ++ti) {
             const CbTileS &t = tilesS[ti];
             if (t.out0 != expect) return fail(CB_ERR_ARG, "stream plan: tile %zu starts at %ld, expected %ld", ti, (long)t.out0, (long)expect);
             expect += t.nout;
+            if (t.nsteps > S || t.np > shp.pairs || t.ne > shp.slots || t.nout > shp.img)
+                return fail(CB_ERR_ARG, "stream plan: tile %zu exceeds the kernel shape", ti);
             std::vector<std::vector<CbContrib>> acc(32);
-            std::vector<int> stored(t.np, 0);
-            std::vector<uint8_t> cover(t.nout, 0);
+            std::vector<std::vector<CbContrib>> lead(t.np), foll(t.np);
+            std::vector<int> stored(t.np, 0), added(t.np, 0);
+            std::vector<uint8_t> cover(t.nout, 0), held(32, 0);
             for (int st = 0; st < t.nsteps; ++st)
                 for (int lane = 0; lane < 32; ++lane) {
-                    const uint32_t r = stepsS[((size_t)t.r0 + st) * 32 + lane];
+                    const uint32_t r = stepsS[(ti * S + st) * 32 + lane];
                     const unsigned slot = r & 63u;
                     if (slot == CB_S_IDLE) continue;
                     if ((int)slot >= t.ne) return fail(CB_ERR_ARG, "stream plan: slot out of range in tile %zu", ti);
-                    CbContrib c{}; c.e = elemsS[t.e0 + slot]; c.a = (r >> 6) & 3; c.b = (r >> 8) & 3;
-                    if (h->cls_on && (int)(r >> 18) != h->h_cls[c.e]) return fail(CB_ERR_ARG, "stream plan: class id mismatch");
+                    if (held[lane]) return fail(CB_ERR_ARG, "stream plan: work after a follower part in tile %zu", ti);
+                    CbContrib c{}; c.e = elemsS[ti * shp.slots + slot]; c.a = (r >> 6) & 3; c.b = (r >> 8) & 3;
+                    if (h->cls_on && (int)(r >> 20) != h->h_cls[c.e]) return fail(CB_ERR_ARG, "stream plan: class id mismatch");
+                    if (((r >> 19) & 1u) != (acc[lane].empty() ? 1u : 0u)) return fail(CB_ERR_ARG, "stream plan: restart flag misplaced in tile %zu", ti);
                     acc[lane].push_back(c);
                     if (!((r >> 10) & 1u)) continue;
-                    const int dst = (r >> 11) & 127;
-                    if (dst >= t.np || blkS[t.p0 + dst] < 0) return fail(CB_ERR_ARG, "stream plan: bad pair index");
-                    const CbPair &p = pairs_csc[blkS[t.p0 + dst]];
-                    if ((int)acc[lane].size() != p.ccount) return fail(CB_ERR_ARG, "stream plan: block of tile %zu stored with %zu of %d contributions", ti, acc[lane].size(), (int)p.ccount);
-                    for (int k = 0; k < p.ccount; ++k) {
-                        const CbContrib &w = contribs[p.cstart + k];
-                        if (w.e != acc[lane][k].e || w.a != acc[lane][k].a || w.b != acc[lane][k].b || w.type != CB_T_SHELL)
-                            return fail(CB_ERR_ARG, "stream plan: contribution order differs in tile %zu", ti);
-                    }
-                    ++stored[dst]; acc[lane].clear();
-                    const uint32_t pr = pairsS[t.p0 + dst];
-                    const int rel = pr & 0xfff, colh = (pr >> 12) & 0xff;
-                    const unsigned mA = (pr >> 20) & 0x3f, mB = pr >> 26;
-                    if (rel != p.off - t.out0 || colh != p.colh || mA != p.maskA || mB != p.maskB)
-                        return fail(CB_ERR_ARG, "stream plan: pair record does not match its block");
-                    const int nra = __builtin_popcount(mA), ncb = __builtin_popcount(mB);
-                    for (int cc = 0; cc < ncb; ++cc)
-                        for (int rr = 0; rr < nra; ++rr) {
-                            const long idx = (long)rel + (long)cc * colh + rr;
-                            if (idx < 0 || idx >= t.nout || cover[idx]) return fail(CB_ERR_ARG, "stream plan: image overlap / overflow in tile %zu", ti);
-                            cover[idx] = 1;
-                        }
+                    const int dst = (r >> 12) & 127;
+                    if (dst >= t.np || blkS[ti * shp.pairs + dst] < 0) return fail(CB_ERR_ARG, "stream plan: bad pair index");
+                    if ((r >> 11) & 1u) { foll[dst] = acc[lane]; ++added[dst]; held[lane] = 1; }
+                    else { lead[dst] = acc[lane]; ++stored[dst]; }
+                    acc[lane].clear();
                 }
             for (int lane = 0; lane < 32; ++lane)
                 if (!acc[lane].empty()) return fail(CB_ERR_ARG, "stream plan: unfinished block in tile %zu", ti);
-            for (int k = 0; k < t.np; ++k)
-                if (stored[k] != 1) return fail(CB_ERR_ARG, "stream plan: block stored %d times in tile %zu", stored[k], ti);
+            for (int k = 0; k < t.np; ++k) {
+                if (stored[k] != 1 || added[k] > 1) return fail(CB_ERR_ARG, "stream plan: block stored %d / added %d times in tile %zu", stored[k], added[k], ti);
+                const CbPair &p = pairs_csc[blkS[ti * shp.pairs + k]];
+                std::vector<CbContrib> all = lead[k];
+                all.insert(all.end(), foll[k].begin(), foll[k].end());
+                if ((int)all.size() != p.ccount) return fail(CB_ERR_ARG, "stream plan: block of tile %zu has %zu of %d contributions", ti, all.size(), (int)p.ccount);
+                for (int c = 0; c < p.ccount; ++c) {
+                    const CbContrib &w = contribs[p.cstart + c];
+                    if (w.e != all[c].e || w.a != all[c].a || w.b != all[c].b || w.type != CB_T_SHELL)
+                        return fail(CB_ERR_ARG, "stream plan: contribution order differs in tile %zu", ti);
+                }
+                const uint32_t pr = pairsS[ti * shp.pairs + k];
+                const int rel = pr & 0xfff, colh = (pr >> 12) & 0xff;
+                const unsigned mA = (pr >> 20) & 0x3f, mB = pr >> 26;
+                if (rel != p.off - t.out0 || colh != p.colh || mA != p.maskA || mB != p.maskB)
+                    return fail(CB_ERR_ARG, "stream plan: pair record does not match its block");
+                const int nra = __builtin_popcount(mA), ncb = __builtin_popcount(mB);
+                for (int cc = 0; cc < ncb; ++cc)
+                    for (int rr = 0; rr < nra; ++rr) {
+                        const long idx = (long)rel + (long)cc * colh + rr;
+                        if (idx < 0 || idx >= t.nout || cover[idx]) return fail(CB_ERR_ARG, "stream plan: image overlap / overflow in tile %zu", ti);
+                        cover[idx] = 1;
+                    }
+            }
             for (long k = 0; k < t.nout; ++k)
                 if (!cover[k]) return fail(CB_ERR_ARG, "stream plan: image gap in tile %zu", ti);
         }
@@ -1159,6 +1285,7 @@ static int build_plan(cb_handle *h)
             h->plan_csc.pairsS.upload(pairsS) || h->plan_csc.elemsS.upload(elemsS))
             return CB_ERR_CUDA;
         h->plan_csc.ntilesS = (long)tilesS.size(); h->plan_csc.nrowsS = (long)(stepsS.size() / 32);
+        h->plan_csc.shapeS = shape_id; h->plan_csc.shape = shp;
         h->plan_csc.tile_smem_out = (max_tile_out + 3) & ~1;   // room for the parity shift, kept even
         if (h->Ax.alloc((size_t)nnz + 1)) return CB_ERR_CUDA;
         dev_zero(h->Ax.p, ((size_t)nnz + 1) * sizeof(double));
@@ -1200,7 +1327,7 @@ extern "C" int cb_plan_selfcheck(const cb_sizes *sz, const cb_flags *fl, const c
         stats[0] = h->nnz;
         stats[1] = h->plan_csc.ntilesS ? h->plan_csc.ntilesS : (h->plan_csc.ntiles2 ? h->plan_csc.ntiles2 : h->plan_csc.ntiles);
         stats[2] = h->plan_csc.nrowsS; stats[3] = (long)h->plan_csc.pairsS.n;
-        stats[4] = h->plan_csc.ntilesS ? (h->plan_csc.nrowsS + h->plan_csc.ntilesS - 1) / h->plan_csc.ntilesS : 0;
+        stats[4] = h->plan_csc.ntilesS ? h->plan_csc.shape.steps : 0;
         stats[5] = h->plan_csc.ntilesS ? 3 : (h->plan_csc.ntiles2 ? 2 : (h->plan_csc.ntiles ? 1 : 0));
     }
     if (h) cb_destroy(h);
@@ -1217,7 +1344,7 @@ static int ensure_keb(cb_handle *h)
     if (h->sz.NE_SH && h->cls_on) {
         const bool duo = h->plan_ready && h->plan_csc.ntiles2;
         if (duo && !h->works_cls.p && h->works_cls.alloc((size_t)h->plan_csc.nworks)) return CB_ERR_CUDA;
-        if (cbk_shell_class_tables(d, h->cls_rep.p, h->ncls, h->keb_tab.p, h->der_tab.p,
+        if (cbk_shell_class_tables(d, h->cls_rep.p, h->ncls, h->keb_tab.p, h->keb_tab10.p, h->der_tab.p,
                                    duo ? h->plan_csc.works.p : nullptr, duo ? h->plan_csc.nworks : 0,
                                    h->contribs.p, h->works_cls.p, h->stream))
             return fail(CB_ERR_CUDA, "class table launch");
@@ -1228,8 +1355,9 @@ static int ensure_keb(cb_handle *h)
         if (h->plan_csc.ntilesS) {
             // stream plan: the 3x3 DKT block of every step, kebc[((row * 9) + i) * 32 + lane]
             if (!h->sh_kebc.p && h->sh_kebc.alloc((size_t)h->plan_csc.nrowsS * 9 * 32)) return CB_ERR_CUDA;
-            if (cbk_shell_init_kebcS(d, h->plan_csc.tilesS.p, h->plan_csc.ntilesS, h->plan_csc.stepsS.p,
-                                     h->plan_csc.elemsS.p, h->sh_kebc.p, h->stream))
+            if (cbk_shell_init_kebcS(d, h->plan_csc.tilesS.p, h->plan_csc.ntilesS, h->plan_csc.shape.steps,
+                                     h->plan_csc.shape.slots, h->plan_csc.stepsS.p, h->plan_csc.elemsS.p,
+                                     h->sh_kebc.p, h->stream))
                 return fail(CB_ERR_CUDA, "kebc init launch");
         } else if (h->plan_csc.ntiles2) {
             if (!h->sh_kebc.p && h->sh_kebc.alloc((size_t)h->plan_csc.ntiles2 * 18 * CB_T2_T)) return CB_ERR_CUDA;
@@ -1377,9 +1505,11 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
         a.tpairs2 = h->plan_csc.tpairs2.p; a.tile_elems = h->plan_csc.telems.p;
         a.tilesS = h->plan_csc.ntilesS ? h->plan_csc.tilesS.p : nullptr; a.ntilesS = h->plan_csc.ntilesS;
         a.stepsS = h->plan_csc.stepsS.p; a.pairsS = h->plan_csc.pairsS.p; a.elemsS = h->plan_csc.elemsS.p;
+        a.shapeS = h->plan_csc.shapeS;
         a.tile_smem_out = h->plan_csc.tile_smem_out;
         a.out = h->Ax.p + h->ax_pad; a.out_par = h->ax_pad; a.skyline = 0; a.maxa = nullptr;
-        if (cbk_stiff(a, h->stream, &h->launches)) return fail(CB_ERR_CUDA, "assembly launch");
+        if (const int ke = cbk_stiff(a, h->stream, &h->launches))
+            return fail(CB_ERR_CUDA, "assembly launch: %s", ke > 1 ? cudaGetErrorString((cudaError_t)ke) : "failed");
     }
     CUDA_TRY(cudaEventRecord(h->ev3, h->stream));
     if (h->layout & CB_MAT_SKYLINE) {

@@ -246,31 +246,31 @@ int cbk_shell_init_kebc2(const CbDev &d, const CbTile2 *tiles, long ntiles, cons
     return cudaGetLastError() != cudaSuccess;
 }
 
-// stream plan: the sub-block of every step, kebc[((row * 9) + i) * 32 + lane] (row = tile.r0 + step): a
-// warp's nine loads per step are nine contiguous 256-byte runs.  One warp per tile.
+// stream plan: the sub-block of every step, kebc[((tile * S + step) * 9 + i) * 32 + lane]: a warp's nine
+// loads per step are nine contiguous 256-byte runs.  One warp per tile.
 __global__ void __launch_bounds__(32)
-k_shell_init_kebcS(CbDev d, const CbTileS *__restrict__ tiles, const uint32_t *__restrict__ steps,
+k_shell_init_kebcS(CbDev d, const CbTileS *__restrict__ tiles, int S, int slots, const uint32_t *__restrict__ steps,
                    const int32_t *__restrict__ elems, double *__restrict__ kebc)
 {
     const CbTileS tl = tiles[blockIdx.x];
     const int lane = threadIdx.x;
-    for (int st = 0; st < tl.nsteps; ++st) {
-        const long row = (long)tl.r0 + st;
-        const uint32_t r = steps[row * 32 + lane];
+    for (int st = 0; st < S; ++st) {
+        const long row = (long)blockIdx.x * S + st;
+        const uint32_t r = (st < tl.nsteps) ? steps[row * 32 + lane] : CB_S_IDLE;
         const unsigned slot = r & 63u;
         const int a = (r >> 6) & 3, b = (r >> 8) & 3;
-        const long e = (slot != CB_S_IDLE) ? elems[tl.e0 + slot] : -1;
+        const long e = (slot != CB_S_IDLE) ? elems[(long)blockIdx.x * slots + slot] : -1;
 #pragma unroll
         for (int i = 0; i < 9; ++i)
             kebc[(row * 9 + i) * 32 + lane] = (e >= 0) ? SOA(d.sh_keb, (3 * a + b) * 9 + i, e, d.NE_SH) : 0.0;
     }
 }
 
-int cbk_shell_init_kebcS(const CbDev &d, const CbTileS *tiles, long ntiles, const uint32_t *steps,
-                         const int32_t *elems, double *kebc, cudaStream_t s)
+int cbk_shell_init_kebcS(const CbDev &d, const CbTileS *tiles, long ntiles, int steps_per_tile, int slots_per_tile,
+                         const uint32_t *steps, const int32_t *elems, double *kebc, cudaStream_t s)
 {
     if (ntiles == 0 || d.NE_SH == 0) return 0;
-    k_shell_init_kebcS<<<(unsigned)ntiles, 32, 0, s>>>(d, tiles, steps, elems, kebc);
+    k_shell_init_kebcS<<<(unsigned)ntiles, 32, 0, s>>>(d, tiles, steps_per_tile, slots_per_tile, steps, elems, kebc);
     return cudaGetLastError() != cudaSuccess;
 }
 
@@ -278,12 +278,13 @@ int cbk_shell_init_kebcS(const CbDev &d, const CbTileS *tiles, long ntiles, cons
 // records of the duo plan with the classes of their two contributions packed into c0
 __global__ void __launch_bounds__(128)
 k_class_tables(CbDev d, const int32_t *__restrict__ rep, int ncls, double *__restrict__ keb_tab,
-               double *__restrict__ der_tab)
+               double *__restrict__ keb_tab10, double *__restrict__ der_tab)
 {
     const int k = blockIdx.x, c = threadIdx.x;
     if (k >= ncls) return;
     const long e = rep[k];
     if (c < 81) keb_tab[k * 81 + c] = SOA(d.sh_keb, c, e, d.NE_SH);
+    if (c < 90) keb_tab10[k * 90 + c] = (c % 10 < 9) ? SOA(d.sh_keb, (c / 10) * 9 + c % 10, e, d.NE_SH) : 0.0;
     if (c < CB_SH_DER) der_tab[k * CB_SH_DER + c] = SOA(d.sh_der, c, e, d.NE_SH);
 }
 __global__ void __launch_bounds__(256)
@@ -299,11 +300,11 @@ k_works_set_class(const CbWork *__restrict__ works, long nworks, const CbContrib
     w.c0 = c0 | (c1 << 16);
     out[i] = w;
 }
-int cbk_shell_class_tables(const CbDev &d, const int32_t *rep, int ncls, double *keb_tab, double *der_tab,
+int cbk_shell_class_tables(const CbDev &d, const int32_t *rep, int ncls, double *keb_tab, double *keb_tab10, double *der_tab,
                            const CbWork *works, long nworks, const CbContrib *contribs, CbWork *works_cls,
                            cudaStream_t s)
 {
-    k_class_tables<<<ncls, 128, 0, s>>>(d, rep, ncls, keb_tab, der_tab);
+    k_class_tables<<<ncls, 128, 0, s>>>(d, rep, ncls, keb_tab, keb_tab10, der_tab);
     if (nworks && works_cls)
         k_works_set_class<<<(unsigned)((nworks + 255) / 256), 256, 0, s>>>(works, nworks, contribs, d.sh_class, works_cls);
     return cudaGetLastError() != cudaSuccess;

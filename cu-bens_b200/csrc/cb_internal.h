@@ -134,34 +134,41 @@ static_assert(sizeof(CbTile2) == 40, "tile records are prefetched as five 8-byte
 // (steps) that covers WHOLE joint-pair blocks, one after the other: it accumulates a block's 6x6 in
 // registers over the block's contributions (reference order) and stores it into the tile image when
 // the block's last contribution has been added - a segmented reduction over the sorted
-// element-to-nonzero map with the segments aligned to lanes, so no partial sums ever meet in shared
-// memory: every shell record is read once per contribution, every image entry is written once.
-#define CB_S_MAXSTEPS 8          // contributions per lane and tile (the plate: 6 = three off-diagonal blocks of
-                                 // two contributions, or one diagonal block of six)
-#define CB_S_IMG 2560            // max doubles of Ax per tile (10 plate joints x 252)
-#define CB_S_SLOTS 44            // max distinct shells per tile (a run of 10 plate joints touches 42); lane l stages
-                                 // the records of slots l and l + 32
-#define CB_S_PAIRS 96            // max joint-pair blocks per tile
-#ifndef CB_S_WARPS
-#define CB_S_WARPS 6             // warps (= concurrent tiles) per CTA, one CTA per SM: 6 x 35.1 KB of shared memory
-#endif
+// element-to-nonzero map with the segments aligned to lanes: every shell record is read once per
+// contribution, every image entry is written once.  A block with more contributions than a lane has
+// steps is cut in two: its second part ("follower") is the last block of another lane, which adds its
+// sum to the stored first part once, at the end of the tile.
+// Two compiled shapes (the planner is told which): steps per lane S, image / shell-slot / pair capacity.
+//   wide   S = 6: 10 plate joints per tile (3 lanes each: 2+2+2 | 6 | 2+2+2), 6 warps per SM
+//   narrow S = 4:  6 plate joints per tile (5 lanes each: 2+2 | 2+2 | 2+2 | 3 | 3 follower), 8 warps per SM
+// Everything a tile needs sits at a fixed stride of its number, so nothing but the tile number is needed
+// to prefetch it: steps[(tile * S + step) * 32 + lane], pairs[tile * PAIRS + k], elems[tile * SLOTS + slot]
+// (padded with a valid shell), kebc[((tile * S + step) * 9 + i) * 32 + lane].
+struct CbStreamShape {
+    int img;          // max doubles of Ax per tile
+    int slots;        // max distinct shells per tile
+    int steps;        // contributions per lane and tile
+    int pairs;        // max joint-pair blocks per tile (multiple of 4)
+    int warps;        // warps (= concurrent tiles) per CTA, one CTA per SM
+};
+#define CB_S_MAXSTEPS_ANY 6       // the larger S of the two shapes
+#define CB_S_SHAPE_WIDE   {2560, 44, 6, 80, 6}
+#define CB_S_SHAPE_NARROW {1536, 28, 4, 48, 8}
 struct CbTileS {
     int64_t out0;     // first Ax index of the tile's contiguous output range
     int32_t nout;
-    int32_t r0;       // first row of the step records: steps[(r0 + s) * 32 + lane]
-    int32_t p0;       // first pair record (multiple of 4: copied as 16-byte units)
-    int32_t e0;       // first entry of tile_elems
     uint8_t nsteps, np, ne, pad;
-    int32_t pad2;
 };
-static_assert(sizeof(CbTileS) == 32, "tile records are read as two 16-byte words");
+static_assert(sizeof(CbTileS) == 16, "tile records are read as one 16-byte word");
 // step record (uint32): bits 0-5 shell slot (CB_S_IDLE = no work), 6-7 local row joint a, 8-9 local column
-// joint b, 10 = last contribution of its block (store + reset), 11-17 pair record index, 18-31 geometry
-// class of the shell (0 when the classes are off)
+// joint b, 10 = last contribution of its block (or block part), 11 = this part is a follower (held in
+// registers and added to the image at the end of the tile), 12-18 pair record index, 19 = first contribution
+// of its block part (the running sum restarts), 20-31 geometry class of the shell (0 when the classes are
+// off).  An idle record is all zero but for the slot field.
 #define CB_S_IDLE 63u
-#define CB_S_REC(slot, a, b, last, dst, cls) \
+#define CB_S_REC(slot, a, b, first, last, follow, dst, cls) \
     ((uint32_t)(slot) | ((uint32_t)(a) << 6) | ((uint32_t)(b) << 8) | ((uint32_t)(last) << 10) | \
-     ((uint32_t)(dst) << 11) | ((uint32_t)(cls) << 18))
+     ((uint32_t)(follow) << 11) | ((uint32_t)(dst) << 12) | ((uint32_t)(first) << 19) | ((uint32_t)(cls) << 20))
 // pair record (uint32): bits 0-11 offset of (first free row of A, first free column of B) in the tile
 // image, 12-19 column height of joint B, 20-25 free-DOF mask of A, 26-31 of B
 #define CB_S_PAIR(rel, colh, ma, mb) \
@@ -213,6 +220,7 @@ struct CbDev {
     // model has too many classes (or after mass_* rewrote the reference geometry, App. B.5).
     const int32_t *sh_class; // [NE] class of each shell
     const double *keb_tab;   // [ncls][81] component order of sh_keb (CB_KEB)
+    const double *keb_tab10; // [ncls][9][10] the same 3x3 blocks padded to ten doubles (16-byte loads)
     const double *der_tab;   // [ncls][CB_SH_DER]
     // frames
     const int32_t *fr_nodes; // [NE][2]
@@ -283,7 +291,7 @@ struct CbStiffArgs {
     const CbTile2 *tiles2; long ntiles2; const CbWork *works; const CbTPair *tpairs2;
     const int32_t *tile_elems;
     const CbTileS *tilesS; long ntilesS; const uint32_t *stepsS; const uint32_t *pairsS;   // stream plan
-    const int32_t *elemsS;
+    const int32_t *elemsS; int shapeS;                                                     // 0 wide, 1 narrow
     int tile_smem_out;       // doubles of output staging per tile
     int max_dof;             // 3, 6 or 7: largest DOF count per joint among the model's elements
     int mixed;               // element types with different DOF counts per joint are present
@@ -333,10 +341,10 @@ int cbk_shell_init_kebc2(const CbDev &d, const CbTile2 *tiles, long ntiles, cons
                          const CbContrib *contribs, double *kebc, cudaStream_t s);
 int cbk_shell_init_kebc(const CbDev &d, const CbContrib *contribs, long ncontrib, double *kebc,
                         cudaStream_t s);
-int cbk_shell_init_kebcS(const CbDev &d, const CbTileS *tiles, long ntiles, const uint32_t *steps,
-                         const int32_t *elems, double *kebc, cudaStream_t s);
+int cbk_shell_init_kebcS(const CbDev &d, const CbTileS *tiles, long ntiles, int steps_per_tile, int slots_per_tile,
+                         const uint32_t *steps, const int32_t *elems, double *kebc, cudaStream_t s);
 int cbk_shell_prep(const CbDev &d, const double *x, const double *sh_frame, cudaStream_t s);
-int cbk_shell_class_tables(const CbDev &d, const int32_t *rep, int ncls, double *keb_tab, double *der_tab,
+int cbk_shell_class_tables(const CbDev &d, const int32_t *rep, int ncls, double *keb_tab, double *keb_tab10, double *der_tab,
                            const CbWork *works, long nworks, const CbContrib *contribs, CbWork *works_cls,
                            cudaStream_t s);
 int cbk_shell_plastic_prep(const CbDev &d, const double *sh_frame, const double *sh_dsl,

@@ -1052,90 +1052,125 @@ static int launch_shell_tiles(const CbStiffArgs &a, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------------------------------
-// CSC, shell-only models: "stream" tile kernel (plan: cb_internal.h, CbTileS).  One persistent WARP walks
-// tiles (runs of consecutive joints whose CSC columns are one contiguous slice of Ax); the warps of a CTA
-// share nothing, so there is no CTA barrier anywhere.  Per tile:
-//   * the records of the tile's distinct shells (krec, 144 B each, lane l brings slot l), its step and
-//     pair records arrive by cp.async, double-buffered one tile ahead; tile records and element ids are
-//     register-prefetched two / three tiles ahead;
+// CSC, shell-only models: "stream" tile kernel (plan: cb_internal.h, CbStreamShape / CbTileS).  One
+// persistent WARP walks tiles (runs of consecutive joints whose CSC columns are one contiguous slice of
+// Ax); the warps of a CTA share nothing, so there is no CTA barrier anywhere.  Per tile:
+//   * the records of the tile's distinct shells (krec, 144 B each), its step and pair records arrive by
+//     cp.async, double-buffered one tile ahead; element ids and the tile record are register-prefetched
+//     (their addresses depend on the tile number only);
 //   * every lane walks its steps: one contribution per step, the shell record read ONCE from shared
-//     memory (9 x 16 bytes), the full 6x6 accumulated in registers (FMA chains onto the running sum of
-//     the joint-pair block, reference order), the block written into the tile image ONCE (18 x 16-byte
-//     stores) when its last contribution has been added.  The planner hands whole blocks to lanes, so no
-//     partial sums are ever combined through shared memory (the duo kernel's read-modify-write rounds,
-//     its second read of every record and its CTA barriers are gone);
+//     memory (9 x 16 bytes), the DKT sub-block of the NEXT step already on its way, the full 6x6
+//     accumulated in registers (FMA chains onto the running sum of the joint-pair block), the block
+//     written into the tile image ONCE (18 x 16-byte stores) when its last contribution has been added.
+//     The planner hands whole blocks to lanes, so no partial sums meet in shared memory - except the
+//     second part of a block too long for one lane, which is added once at the end of the tile;
 //   * the finished image leaves as one bulk asynchronous copy shared -> global (TMA engine).
 // shared memory per warp: image | shell records x2 | step records x2 | pair records x2
 // ------------------------------------------------------------------------------------------
-#define CB_S_IMG_BYTES ((CB_S_IMG + 2) * 8)
-#define CB_S_KREC_BYTES (2 * CB_S_SLOTS * CB_SH_KREC * 8)
-#define CB_S_REC_BYTES (2 * CB_S_MAXSTEPS * 32 * 4)
-#define CB_S_PAIR_BYTES (2 * CB_S_PAIRS * 4)
-#define CB_S_WARP_BYTES (CB_S_IMG_BYTES + CB_S_KREC_BYTES + CB_S_REC_BYTES + CB_S_PAIR_BYTES)
-static_assert(CB_S_WARP_BYTES % 16 == 0 && CB_S_IMG_BYTES % 16 == 0, "per-warp regions stay 16-byte aligned");
+#ifndef CB_S_PREK
+#define CB_S_PREK 1               // the next step's shell record is read into registers while this step is evaluated
+#endif
+#ifndef CB_S_NARROW_WARPS
+#define CB_S_NARROW_WARPS 8
+#endif
+template <int IMG, int SLOTS, int S, int PAIRS>
+struct SLayout {
+    static constexpr int IMG_BYTES = (IMG + 2) * 8;
+    static constexpr int KREC_BYTES = 2 * SLOTS * CB_SH_KREC * 8;
+    static constexpr int REC_BYTES = 2 * S * 32 * 4;
+    static constexpr int PAIR_BYTES = 2 * PAIRS * 4;
+    static constexpr int WARP_BYTES = IMG_BYTES + KREC_BYTES + REC_BYTES + PAIR_BYTES;
+    static_assert(WARP_BYTES % 16 == 0 && IMG_BYTES % 16 == 0 && PAIRS % 4 == 0, "16-byte aligned regions");
+};
 
-__device__ __forceinline__ CbTileS s_load_tile(const CbTileS *p)
+// loads that must be ISSUED where they are written (their results are used an iteration later; a plain
+// load would be sunk to its first use and expose the full DRAM latency there)
+__device__ __forceinline__ int4 s_ldg16(const void *p)
 {
-    const int4 a = __ldg(reinterpret_cast<const int4 *>(p)), b = __ldg(reinterpret_cast<const int4 *>(p) + 1);
-    CbTileS t;
-    t.out0 = ((int64_t)(unsigned)a.x) | ((int64_t)a.y << 32);
-    t.nout = a.z; t.r0 = a.w; t.p0 = b.x; t.e0 = b.y;
-    t.nsteps = (uint8_t)(b.z & 0xff); t.np = (uint8_t)((b.z >> 8) & 0xff); t.ne = (uint8_t)((b.z >> 16) & 0xff);
-    t.pad = 0; t.pad2 = 0;
-    return t;
+    int4 v;
+    asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int s_ldg4(const void *p)
+{
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
 }
 
-// stage one tile: lane l copies the record of shell slot l (9 x 16 B), two 16-byte chunks of the step
-// records and one of the pair records
-struct SEids { int v[2]; };          // element ids of slots lane and lane + 32
-__device__ __forceinline__ SEids s_load_eids(const CbStiffArgs &A, const CbTileS &tl, int lane)
+template <int SLOTS>
+struct SEids { int v[(SLOTS + 31) / 32]; };
+template <int SLOTS>
+__device__ __forceinline__ SEids<SLOTS> s_load_eids(const CbStiffArgs &A, long tile, int lane)
 {
-    SEids e;
-    e.v[0] = (lane < tl.ne) ? __ldg(A.elemsS + tl.e0 + lane) : 0;
-    e.v[1] = (lane + 32 < tl.ne) ? __ldg(A.elemsS + tl.e0 + lane + 32) : 0;
+    SEids<SLOTS> e;
+#pragma unroll
+    for (int h = 0; h < (SLOTS + 31) / 32; ++h)
+        e.v[h] = (lane + 32 * h < SLOTS) ? s_ldg4(A.elemsS + tile * SLOTS + lane + 32 * h) : 0;
     return e;
 }
-__device__ __forceinline__ void s_issue_stage(const CbStiffArgs &A, const CbTileS &tl, const SEids &eid, int lane,
+
+// stage one tile: lane l copies the records of shell slots l, l + 32 (9 x 16 B each; slots past the
+// tile's last shell repeat a valid one), 16-byte chunks of the step records and of the pair records
+template <int SLOTS, int S, int PAIRS>
+__device__ __forceinline__ void s_issue_stage(const CbStiffArgs &A, long tile, const SEids<SLOTS> &eid, int lane,
                                               double *krec_dst, uint32_t *rec_dst, uint32_t *pair_dst)
 {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < (SLOTS + 31) / 32; ++h) {
         const int slot = lane + 32 * h;
-        if (slot < tl.ne) {
+        if (slot < SLOTS) {
             const double *src = A.d.sh_Nm + (long)eid.v[h] * CB_SH_KREC;
 #pragma unroll
             for (int ch = 0; ch < 9; ++ch) CB_CPA(16, "cg", krec_dst + slot * CB_SH_KREC + ch * 2, src + ch * 2);
         }
     }
-    const uint32_t *rs = A.stepsS + (long)tl.r0 * 32;
+    const uint32_t *rs = A.stepsS + tile * (S * 32);
 #pragma unroll
-    for (int k = 0; k < (CB_S_MAXSTEPS * 8 + 31) / 32; ++k) {
+    for (int k = 0; k < (S * 8 + 31) / 32; ++k) {
         const int c = lane + 32 * k;
-        if (c < tl.nsteps * 8) CB_CPA(16, "cg", rec_dst + c * 4, rs + c * 4);
+        if (c < S * 8) CB_CPA(16, "cg", rec_dst + c * 4, rs + c * 4);
     }
-    if (lane * 4 < tl.np) CB_CPA(16, "cg", pair_dst + lane * 4, A.pairsS + tl.p0 + lane * 4);
+    if (lane < PAIRS / 4) CB_CPA(16, "cg", pair_dst + lane * 4, A.pairsS + tile * PAIRS + lane * 4);
+}
+
+// n == 0 ? v0 : (n == 1 ? v1 : v2) as two selp (the lanes of a warp hold different local joints: the
+// compiler's own lowering of the ternaries is a divergent branch)
+__device__ __forceinline__ double sel3(int n, double v0, double v1, double v2)
+{
+    double r;
+    asm("{\n"
+        ".reg .pred p0, p1;\n"
+        ".reg .f64 t;\n"
+        "setp.eq.s32 p0, %1, 0;\n"
+        "setp.eq.s32 p1, %1, 1;\n"
+        "selp.f64 t, %3, %4, p1;\n"
+        "selp.f64 %0, %2, t, p0;\n"
+        "}\n" : "=d"(r) : "r"(n), "d"(v0), "d"(v1), "d"(v2));
+    return r;
 }
 
 // acc (column-major 6x6: acc[q * 6 + r] = K[r][q]) += R^T-rotated local block (a, b) of one shell
-__device__ __forceinline__ void s_contrib(const double *kr /*shared*/, const double *kb, int a, int b, double *acc)
+__device__ __forceinline__ void s_load_krec(const double *kr /*shared*/, double *k)
 {
-    double k[CB_SH_KREC];
-    {
-        const double2 *k2 = reinterpret_cast<const double2 *>(kr);
+    const double2 *k2 = reinterpret_cast<const double2 *>(kr);
 #pragma unroll
-        for (int i = 0; i < CB_SH_KREC / 2; ++i) { const double2 v = k2[i]; k[2 * i] = v.x; k[2 * i + 1] = v.y; }
-    }
+    for (int i = 0; i < CB_SH_KREC / 2; ++i) { const double2 v = k2[i]; k[2 * i] = v.x; k[2 * i + 1] = v.y; }
+}
+__device__ __forceinline__ void s_contrib(const double *k /*registers*/, const double *kb, int a, int b, double *acc)
+{
     const double *R = k;
-    double bxa, bya, bxb, byb;
-    cst_grad(a, k[9], k[10], k[11], bxa, bya);
-    cst_grad(b, k[9], k[10], k[11], bxb, byb);
+    // CST shape-function gradients (x 2A) of local joints a, b: (-Y3, X3 - X2), (Y3, -X3), (0, X2)
+    const double nY3 = -k[11], dX = k[10] - k[9], nX3 = -k[10];
+    const double bxa = sel3(a, nY3, k[11], 0.0), bya = sel3(a, dX, nX3, k[9]);
+    const double bxb = sel3(b, nY3, k[11], 0.0), byb = sel3(b, dX, nX3, k[9]);
     const double g = bxa * (k[15] * bxb + k[17] * byb) + bya * (k[17] * bxb + k[16] * byb);
     const double s00 = k[12] * bxa * bxb + k[14] * bya * byb + g;
     const double s01 = k[13] * bxa * byb + k[14] * bya * bxb;
     const double s10 = k[13] * bya * bxb + k[14] * bxa * byb;
     const double s11 = k[12] * bya * byb + k[14] * bxa * bxb + g;
     const double s22 = kb[0] + g;
-    const double drill = (a == b) ? kb[4] / 10000 : 0.0;
+    const double drill = sel3(a == b ? 0 : 1, kb[4] * 1e-4, 0.0, 0.0);       // shell.c:482-484 (k / 1e4)
     double W0[3], W1[3], W2[3], U0[3], U1[3], U2[3], w[3], v[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
@@ -1161,127 +1196,210 @@ __device__ __forceinline__ void s_contrib(const double *kr /*shared*/, const dou
         }
 }
 
-template <bool CLS>
-__global__ void __launch_bounds__(32 * CB_S_WARPS, 1)
+// the block held in acc goes to (ADD: is added to) its place in the tile image
+template <bool ADD>
+__device__ __forceinline__ void s_store_block(double *obuf, int shift, uint32_t pr, const double *acc)
+{
+    const int rel = pr & 0xfff, colh = (pr >> 12) & 0xff;
+    const unsigned maskA = (pr >> 20) & 0x3f, maskB = pr >> 26;
+    double *img = obuf + shift + rel;
+    if (maskA == 0x3f && maskB == 0x3f && ((((shift + rel) | colh) & 1) == 0)) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            double2 *col = reinterpret_cast<double2 *>(img + q * colh);
+            double2 v0 = make_double2(acc[q * 6], acc[q * 6 + 1]);
+            double2 v1 = make_double2(acc[q * 6 + 2], acc[q * 6 + 3]);
+            double2 v2 = make_double2(acc[q * 6 + 4], acc[q * 6 + 5]);
+            if (ADD) {
+                const double2 o0 = col[0], o1 = col[1], o2 = col[2];
+                v0.x += o0.x; v0.y += o0.y; v1.x += o1.x; v1.y += o1.y; v2.x += o2.x; v2.y += o2.y;
+            }
+            col[0] = v0; col[1] = v1; col[2] = v2;
+        }
+    } else {
+        int cc = 0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            if (!((maskB >> q) & 1)) continue;
+            double *col = img + cc * colh;
+            int rr = 0;
+#pragma unroll
+            for (int p = 0; p < 6; ++p)
+                if ((maskA >> p) & 1) { if (ADD) col[rr] += acc[q * 6 + p]; else col[rr] = acc[q * 6 + p]; ++rr; }
+            ++cc;
+        }
+    }
+}
+
+// registers: one CTA per SM of at most 8 warps, so every thread may use the full 255 (the register file is
+// handed out to warps in groups of four: 10 warps would be budgeted like 12, 168 registers, and spill)
+template <int IMG, int SLOTS, int S, int PAIRS, int WARPS, bool CLS>
+__global__ void __launch_bounds__(32 * WARPS, 1)
 k_assemble_shell_stream(CbStiffArgs A)
 {
+    using L = SLayout<IMG, SLOTS, S, PAIRS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *wbase = smem_raw + (size_t)warp * CB_S_WARP_BYTES;
-    double *obuf = reinterpret_cast<double *>(wbase);                                           // [CB_S_IMG + 2]
-    double *skrec = reinterpret_cast<double *>(wbase + CB_S_IMG_BYTES);                         // [2][SLOTS][18]
-    uint32_t *srec = reinterpret_cast<uint32_t *>(wbase + CB_S_IMG_BYTES + CB_S_KREC_BYTES);     // [2][MAXSTEPS][32]
-    uint32_t *spair = srec + 2 * CB_S_MAXSTEPS * 32;                                             // [2][PAIRS]
-    const long G = (long)gridDim.x * CB_S_WARPS, N = A.ntilesS;
-    long tile = (long)blockIdx.x * CB_S_WARPS + warp;
+    unsigned char *wbase = smem_raw + (size_t)warp * L::WARP_BYTES;
+    double *obuf = reinterpret_cast<double *>(wbase);                                           // [IMG + 2]
+    double *skrec = reinterpret_cast<double *>(wbase + L::IMG_BYTES);                           // [2][SLOTS][18]
+    uint32_t *srec = reinterpret_cast<uint32_t *>(wbase + L::IMG_BYTES + L::KREC_BYTES);         // [2][S][32]
+    uint32_t *spair = srec + 2 * S * 32;                                                         // [2][PAIRS]
+    const long G = (long)gridDim.x * WARPS, N = A.ntilesS;
+    long tile = (long)blockIdx.x * WARPS + warp;
     if (tile >= N) return;
     constexpr unsigned FULL = 0xffffffffu;
 
-    // prologue: this tile staged directly, the next one's record and element ids in registers
-    CbTileS tl = s_load_tile(A.tilesS + tile), tln = tl, tlnn = tl;
-    SEids eid_n{};
+    // prologue: this tile staged directly; the next tile's record and element ids into registers
+    int4 tlr = s_ldg16(A.tilesS + tile), tlr_n = tlr;
+    SEids<SLOTS> eid_n{};
     {
-        const SEids eid = s_load_eids(A, tl, lane);
-        s_issue_stage(A, tl, eid, lane, skrec, srec, spair);
+        const SEids<SLOTS> eid = s_load_eids<SLOTS>(A, tile, lane);
+        s_issue_stage<SLOTS, S, PAIRS>(A, tile, eid, lane, skrec, srec, spair);
         CB_CPA_COMMIT();
-        if (tile + G < N) {
-            tln = s_load_tile(A.tilesS + tile + G);
-            eid_n = s_load_eids(A, tln, lane);
-        }
-        if (tile + 2 * G < N) tlnn = s_load_tile(A.tilesS + tile + 2 * G);
+        if (tile + G < N) { tlr_n = s_ldg16(A.tilesS + tile + G); eid_n = s_load_eids<SLOTS>(A, tile + G, lane); }
     }
     int buf = 0;
     bool img_busy = false;            // a bulk read-out of the image may still be in flight
+    // first tile: wait for its records here and fetch step 0's record and DKT block the slow way
+    uint32_t r0n;
+    double kbC[10], kbN[10];
+    {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        r0n = srec[lane];
+        if (CLS) {
+            const double *k0 = A.d.keb_tab10 + ((r0n >> 20) * 9 + 3 * ((r0n >> 6) & 3) + ((r0n >> 8) & 3)) * 10;
+#pragma unroll
+            for (int i = 0; i < 10; ++i) kbC[i] = __ldg(k0 + i);
+        } else {
+            const double *k0 = A.kebc + (tile * (S * 9L)) * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) kbC[i] = __ldg(k0 + (long)i * 32);
+            kbC[9] = 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 10; ++i) kbN[i] = kbC[i];
+    }
 
     double acc[36];
 #pragma unroll
     for (int i = 0; i < 36; ++i) acc[i] = 0.0;
 
     for (;;) {
-        const bool has_next = tile + G < N, has_next2 = tile + 2 * G < N, has_next3 = tile + 3 * G < N;
+        const bool has_next = tile + G < N, has_next2 = tile + 2 * G < N;
         // the other buffer was last read by the previous tile (the warp re-converged at its end)
         if (has_next)
-            s_issue_stage(A, tln, eid_n, lane, skrec + (buf ^ 1) * CB_S_SLOTS * CB_SH_KREC,
-                          srec + (buf ^ 1) * CB_S_MAXSTEPS * 32, spair + (buf ^ 1) * CB_S_PAIRS);
+            s_issue_stage<SLOTS, S, PAIRS>(A, tile + G, eid_n, lane, skrec + (buf ^ 1) * SLOTS * CB_SH_KREC,
+                                           srec + (buf ^ 1) * S * 32, spair + (buf ^ 1) * PAIRS);
         CB_CPA_COMMIT();
-        SEids eid_nn{};
-        CbTileS tl3 = tlnn;
-        if (has_next2) eid_nn = s_load_eids(A, tlnn, lane);
-        if (has_next3) tl3 = s_load_tile(A.tilesS + tile + 3 * G);
+        SEids<SLOTS> eid_nn{};
+        int4 tlr_nn = tlr_n;
+        if (has_next2) { eid_nn = s_load_eids<SLOTS>(A, tile + 2 * G, lane); tlr_nn = s_ldg16(A.tilesS + tile + 2 * G); }
         asm volatile("cp.async.wait_group 1;" ::: "memory");       // this tile's records have landed
         __syncwarp();
 
-        const double *kr0 = skrec + buf * CB_S_SLOTS * CB_SH_KREC;
-        const uint32_t *rec = srec + buf * CB_S_MAXSTEPS * 32 + lane;
-        const uint32_t *pairs = spair + buf * CB_S_PAIRS;
-        const int shift = (int)((tl.out0 + A.out_par) & 1);
-        const int nsteps = tl.nsteps;
-        const double *kbs = CLS ? nullptr : A.kebc + ((long)tl.r0 * 9) * 32 + lane;
+        const long out0 = ((long)(unsigned)tlr.x) | ((long)tlr.y << 32);
+        const int nout = tlr.z, nsteps = tlr.w & 0xff;
+        const double *kr0 = skrec + buf * SLOTS * CB_SH_KREC;
+        const uint32_t *rec = srec + buf * S * 32 + lane;
+        const uint32_t *pairs = spair + buf * PAIRS;
+        const int shift = (int)((out0 + A.out_par) & 1);
+        const double *kbs = CLS ? nullptr : A.kebc + (tile * (S * 9L)) * 32 + lane;
+        if (!CLS && has_next) {                // step 0 of the next tile: its address depends on the tile number only
+            const double *kn0 = A.kebc + ((tile + G) * (S * 9L)) * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < 9; ++i)
+                asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(kbN[i]) : "l"(kn0 + (long)i * 32));
+        }
 
-        uint32_t r = rec[0];
-#pragma unroll 1
-        for (int st = 0; st < nsteps; ++st) {
-            const uint32_t rn = (st + 1 < nsteps) ? rec[(st + 1) * 32] : CB_S_IDLE;
-            const unsigned slot = r & 63u;
-            if (slot != CB_S_IDLE) {
-                const int a = (r >> 6) & 3, b = (r >> 8) & 3;
-                double kb[9];
-                if (CLS) {
-                    const double *k0 = A.d.keb_tab + (r >> 18) * 81 + (3 * a + b) * 9;
+        // DKT sub-block of a step, requested one step ahead of its use: class table (padded to ten
+        // doubles per 3x3 block: five 16-byte loads) or the step-ordered copy in HBM (nine coalesced
+        // 8-byte loads).  Idle lanes (slot 63: a = b = class 0) read valid memory and compute a block
+        // that is never stored - the step has no divergent branch around its arithmetic.
+        auto load_kb = [&](uint32_t r, int st, double *kb) {
+            if (CLS) {
+                const double *k0 = A.d.keb_tab10 + ((r >> 20) * 9 + 3 * ((r >> 6) & 3) + ((r >> 8) & 3)) * 10;
 #pragma unroll
-                    for (int i = 0; i < 9; ++i) kb[i] = __ldg(k0 + i);
-                } else {
+                for (int i = 0; i < 5; ++i)
+                    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(kb[2 * i]), "=d"(kb[2 * i + 1]) : "l"(k0 + 2 * i));
+            } else {
 #pragma unroll
-                    for (int i = 0; i < 9; ++i) kb[i] = __ldg(kbs + ((long)st * 9 + i) * 32);
-                }
-                s_contrib(kr0 + slot * CB_SH_KREC, kb, a, b, acc);
+                for (int i = 0; i < 9; ++i)
+                    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(kb[i]) : "l"(kbs + ((long)st * 9 + i) * 32));
             }
-            const bool last = (slot != CB_S_IDLE) && ((r >> 10) & 1u);
-            if (__any_sync(FULL, last)) {
-                if (img_busy) {        // the copy engine must have read the previous image out
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    __syncwarp();
-                    img_busy = false;
-                }
-                if (last) {
-                    const uint32_t pr = pairs[(r >> 11) & 127u];
-                    const int rel = pr & 0xfff, colh = (pr >> 12) & 0xff;
-                    const unsigned maskA = (pr >> 20) & 0x3f, maskB = pr >> 26;
-                    double *img = obuf + shift + rel;
-                    if (maskA == 0x3f && maskB == 0x3f && ((((shift + rel) | colh) & 1) == 0)) {
+        };
+        // step 0's record and DKT block were requested at the end of the previous tile (r0n / kbC); the
+        // other step records of the tile go to registers now (rows past nsteps are idle)
+        uint32_t rs[S];
+        rs[0] = r0n;
 #pragma unroll
-                        for (int q = 0; q < 6; ++q) {
-                            double2 *col = reinterpret_cast<double2 *>(img + q * colh);
-                            col[0] = make_double2(acc[q * 6], acc[q * 6 + 1]);
-                            col[1] = make_double2(acc[q * 6 + 2], acc[q * 6 + 3]);
-                            col[2] = make_double2(acc[q * 6 + 4], acc[q * 6 + 5]);
-                        }
-                    } else {
-                        int cc = 0;
+        for (int st = 1; st < S; ++st) rs[st] = rec[st * 32];
+        double kbA[10], kbB[10], krA[CB_SH_KREC], krB[CB_SH_KREC];
 #pragma unroll
-                        for (int q = 0; q < 6; ++q) {
-                            if (!((maskB >> q) & 1)) continue;
-                            double *col = img + cc * colh;
-                            int rr = 0;
+        for (int i = 0; i < 10; ++i) kbA[i] = kbC[i];
+        if ((rs[0] & 63u) != CB_S_IDLE) s_load_krec(kr0 + (rs[0] & 63u) * CB_SH_KREC, krA);
+        bool pend = false; uint32_t pend_pr = 0;
 #pragma unroll
-                            for (int p = 0; p < 6; ++p)
-                                if ((maskA >> p) & 1) col[rr++] = acc[q * 6 + p];
-                            ++cc;
-                        }
+        for (int st = 0; st < S; ++st) {
+            if (st < nsteps) {                              // warp-uniform
+                const uint32_t r = rs[st];
+                double *kb = (st & 1) ? kbB : kbA, *kbn = (st & 1) ? kbA : kbB;
+                double *kr = (st & 1) ? krB : krA, *krn = (st & 1) ? krA : krB;
+                const unsigned slot = r & 63u;
+                const bool idle = slot == CB_S_IDLE;
+                const bool first = (r >> 19) & 1u;
+                const bool last = !idle && ((r >> 10) & 1u);
+                const bool follow = last && ((r >> 11) & 1u);
+                uint32_t pr = 0;
+                if (last) pr = pairs[(r >> 12) & 127u];     // needed at the end of the step
+                if (st + 1 < S) {                           // the next step's inputs are on their way while
+                    const uint32_t rn = rs[st + 1];         // this one is evaluated
+                    if ((rn & 63u) != CB_S_IDLE) {
+                        load_kb(rn, st + 1, kbn);
+                        if (CB_S_PREK) s_load_krec(kr0 + (rn & 63u) * CB_SH_KREC, krn);
                     }
+                }
+                if (st + 1 == nsteps && has_next) {
+                    // last step: the next tile's records have landed long ago - request its first DKT block
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                    r0n = srec[(buf ^ 1) * S * 32 + lane];
+                    if (CLS && (r0n & 63u) != CB_S_IDLE) load_kb(r0n, 0, kbC);
+                }
+                // a lane that starts a block forgets the previous one (its store has long read the registers)
+                if (__any_sync(FULL, first)) {
+                    if (first) {
 #pragma unroll
-                    for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+                        for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+                    }
+                }
+                if (!idle) {
+                    if (!CB_S_PREK) s_load_krec(kr0 + slot * CB_SH_KREC, kr);
+                    s_contrib(kr, kb, (r >> 6) & 3, (r >> 8) & 3, acc);
+                }
+                if (follow) { pend = true; pend_pr = pr; }                  // held until the tile's end
+                if (__any_sync(FULL, last && !follow)) {
+                    if (img_busy) {        // the copy engine must have read the previous image out
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                        img_busy = false;
+                    }
+                    if (last && !follow) s_store_block<false>(obuf, shift, pr, acc);
                 }
             }
-            r = rn;
+        }
+        if (__any_sync(FULL, pend)) {          // second parts of the blocks that were cut in two
+            __syncwarp();                      // their first parts are in the image
+            if (pend) s_store_block<true>(obuf, shift, pend_pr, acc);
         }
         // writes of the image (generic proxy) ordered before the copy engine's reads (async proxy)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-            double *dst = A.out + tl.out0;
+            double *dst = A.out + out0;
             const double *im = obuf + shift;
-            const int nv = (tl.nout - shift) >> 1;
+            const int nv = (nout - shift) >> 1;
             if (nv > 0)
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + shift),
                              "r"(t2_saddr(im + shift)), "r"(nv * 16)
@@ -1289,36 +1407,50 @@ k_assemble_shell_stream(CbStiffArgs A)
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             if (shift) dst[0] = im[0];
             const int tail = shift + 2 * nv;
-            if (tail < tl.nout) dst[tail] = im[tail];
+            if (tail < nout) dst[tail] = im[tail];
         }
         img_busy = true;
         if (!has_next) break;
-        tile += G; tl = tln; tln = tlnn; tlnn = tl3; eid_n = eid_nn; buf ^= 1;
+        if (!CLS) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) kbC[i] = kbN[i];
+        }
+        tile += G; tlr = tlr_n; tlr_n = tlr_nn; eid_n = eid_nn; buf ^= 1;
         __syncwarp();
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <bool CLS>
-static int launch_shell_stream(const CbStiffArgs &a, cudaStream_t s)
+template <int IMG, int SLOTS, int S, int PAIRS, int WARPS, bool CLS>
+static int launch_shell_stream_t(const CbStiffArgs &a, cudaStream_t s)
 {
-    const size_t smem = (size_t)CB_S_WARPS * CB_S_WARP_BYTES;
+    const size_t smem = (size_t)WARPS * SLayout<IMG, SLOTS, S, PAIRS>::WARP_BYTES;
     static CbPerDevice cache{};                      // SM count per device (0: not configured)
     int &nsm = cache.v[cb_device_slot()];
     if (!nsm) {
-        if (cudaFuncSetAttribute(k_assemble_shell_stream<CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem) != cudaSuccess)
-            return 1;
+        const cudaError_t e = cudaFuncSetAttribute(k_assemble_shell_stream<IMG, SLOTS, S, PAIRS, WARPS, CLS>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
         int dev = 0, n = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         nsm = n;
     }
-    long grid = nsm;                                 // persistent: one CTA of CB_S_WARPS independent warps per SM
-    const long need = (a.ntilesS + CB_S_WARPS - 1) / CB_S_WARPS;
+    long grid = nsm;                                 // persistent: one CTA of WARPS independent warps per SM
+    const long need = (a.ntilesS + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
-    k_assemble_shell_stream<CLS><<<(unsigned)grid, 32 * CB_S_WARPS, smem, s>>>(a);
-    return cudaGetLastError() != cudaSuccess;
+    k_assemble_shell_stream<IMG, SLOTS, S, PAIRS, WARPS, CLS><<<(unsigned)grid, 32 * WARPS, smem, s>>>(a);
+    return (int)cudaGetLastError();
+}
+
+// the two compiled shapes of cb_internal.h (CB_S_SHAPE_WIDE / CB_S_SHAPE_NARROW)
+static int launch_shell_stream(const CbStiffArgs &a, cudaStream_t s)
+{
+    const bool cls = a.d.keb_tab != nullptr;
+    if (a.shapeS == 0)
+        return cls ? launch_shell_stream_t<2560, 44, 6, 80, 6, true>(a, s) : launch_shell_stream_t<2560, 44, 6, 80, 6, false>(a, s);
+    return cls ? launch_shell_stream_t<1536, 28, 4, 48, CB_S_NARROW_WARPS, true>(a, s)
+               : launch_shell_stream_t<1536, 28, 4, 48, CB_S_NARROW_WARPS, false>(a, s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1430,7 +1562,7 @@ int cbk_stiff(const CbStiffArgs &a, cudaStream_t s, long *launches)
     }
     if (!a.skyline && a.ntilesS > 0 && a.tilesS) {
         ++*launches;
-        return a.d.keb_tab ? launch_shell_stream<true>(a, s) : launch_shell_stream<false>(a, s);
+        return launch_shell_stream(a, s);
     }
     if (!a.skyline && a.ntiles2 > 0 && a.tiles2) {
         ++*launches;

@@ -23,9 +23,11 @@ BRICK_DEF = (2.1e11, 0.3, 8050.0, 3.45e8)           # E, nu, rho, fy
 
 
 def plate_model(nx, ny, lx=1.0, ly=1.0, props=SHELL_5C, load=-1000.0, ANAFLAG=2, ALGFLAG=1,
-                SLVFLAG=0, pinned=True, z_bump=0.0, jitter=0.0, jitter_seed=7):
+                SLVFLAG=0, pinned=True, z_bump=0.0, jitter=0.0, jitter_seed=7, unionjack=False):
     """``jitter``: interior joints moved in-plane by up to that fraction of a cell (seeded) - an
-    unstructured variant of the same plate in which no two shells share their geometry"""
+    unstructured variant of the same plate in which no two shells share their geometry.
+    ``unionjack``: the cell diagonals alternate, so joints have 4 or 8 shells around them instead of 6
+    (joint-pair blocks of 4 and 8 contributions)"""
     i, j = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="ij")
     xs = (i * (lx / nx)).astype(F64)
     ys = (j * (ly / ny)).astype(F64)
@@ -42,6 +44,10 @@ def plate_model(nx, ny, lx=1.0, ly=1.0, props=SHELL_5C, load=-1000.0, ANAFLAG=2,
     a = nid[:-1, :-1]; b = nid[1:, :-1]; c = nid[1:, 1:]; d = nid[:-1, 1:]
     t1 = np.stack([a, b, c], axis=-1)
     t2 = np.stack([a, c, d], axis=-1)
+    if unionjack:
+        odd = ((i[:-1, :-1] + j[:-1, :-1]) % 2 == 1)[..., None]
+        t1 = np.where(odd, np.stack([a, b, d], axis=-1), t1)
+        t2 = np.where(odd, np.stack([b, c, d], axis=-1), t2)
     shells = np.stack([t1, t2], axis=2).reshape(-1, 3)
     fixed = []
     if pinned:

@@ -1,0 +1,9 @@
+#!/bin/bash
+out=gpurun_out; mkdir -p $out
+timeout 900 python -m pytest tests/test_midsize_gpu.py tests/test_shell_gpu.py -m gpu -x -q > $out/r02c_tests.log 2>&1; echo "tests rc=$?" >> $out/r02c_tests.log
+tail -5 $out/r02c_tests.log
+timeout 600 python scripts/kt_compare.py 1000 wide,narrow,narrow8 > $out/r02c_kt.log 2>&1; cat $out/r02c_kt.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_assemble_shell_stream -s 3 -c 1 \
+    -o $out/r02c_prof_narrow python scripts/kt_compare.py 1000 narrow > $out/r02c_ncu.log 2>&1; tail -2 $out/r02c_ncu.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_assemble_shell_stream -s 3 -c 1 \
+    -o $out/r02c_prof_narrow8 python scripts/kt_compare.py 1000 narrow8 > $out/r02c_ncu8.log 2>&1; tail -2 $out/r02c_ncu8.log

@@ -6,7 +6,7 @@ import numpy as np
 import cubens_b200 as cb
 from cubens_b200 import meshgen
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
-kinds = sys.argv[2].split(",") if len(sys.argv) > 2 else ["duo", "stream"]
+kinds = sys.argv[2].split(",") if len(sys.argv) > 2 else ["duo", "wide", "narrow"]
 jit = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
 m = meshgen.plate_model(n, n, SLVFLAG=2, jitter=jit)
 dd = meshgen.perturbation(m)

@@ -330,17 +330,19 @@ def test_fp64_probe_needs_a_device():
 @pytest.mark.parametrize("nx,ny,jitter,own", [(1, 1, 0.0, None), (2, 2, 0.0, None), (9, 7, 0.0, None),
                                                (40, 25, 0.0, None), (40, 25, 0.2, None), (60, 40, 0.0, (300, 1500)),
                                                (120, 3, 0.0, None), (3, 120, 0.0, (100, 101))])
-def test_stream_plan_interpreter(nx, ny, jitter, own):
+@pytest.mark.parametrize("shape", ["narrow", "wide"])
+def test_stream_plan_interpreter(nx, ny, jitter, own, shape, monkeypatch):
     """the sorted element-to-nonzero map of the shell stream kernel (k_assemble_shell_stream), built on
     the host without a device and walked the way the kernel walks it: every joint-pair block is summed
     from exactly its contribution list in reference order and stored once, the blocks tile each tile's
     output without overlap or gap, the tiles cover the owned CSC slice contiguously"""
     import cubens_b200 as cb
     from cubens_b200 import meshgen
+    monkeypatch.setenv("CB_KT", shape)
     m = meshgen.plate_model(nx, ny, SLVFLAG=2, jitter=jitter, pinned=nx > 1)
     j0, j1 = own if own else (0, 0)
     st = cb.plan_selfcheck(m, j0, j1)
-    assert st["kind"] == 3 and st["tiles"] >= 1 and st["steps"] <= 8
+    assert st["kind"] == 3 and st["tiles"] >= 1 and st["steps"] == (4 if shape == "narrow" else 6)
     if own is None:
         # nnz of the structural joint-block pattern: sum over joints of nfree(B) * sum of nfree(neighbours)
         jc = (np.asarray(m.jcode).reshape(-1, 7) != 0).sum(axis=1)
@@ -349,6 +351,17 @@ def test_stream_plan_interpreter(nx, ny, jitter, own):
             for a in tri:
                 nb[a].update(int(b) for b in tri)
         assert st["nnz"] == sum(int(jc[b]) * sum(int(jc[a]) for a in nb[b]) for b in range(m.NJ))
+
+
+@pytest.mark.parametrize("shape", ["narrow", "wide"])
+def test_stream_plan_split_blocks(shape, monkeypatch):
+    """union-jack plate: joints with 8 shells around them - their diagonal blocks (8 contributions) are cut
+    in two parts, the second a follower that is added at the end of the tile"""
+    import cubens_b200 as cb
+    from cubens_b200 import meshgen
+    monkeypatch.setenv("CB_KT", shape)
+    st = cb.plan_selfcheck(meshgen.plate_model(24, 17, SLVFLAG=2, unionjack=True, z_bump=0.02))
+    assert st["kind"] == 3
 
 
 def test_plan_selfcheck_other_element_types():

@@ -60,7 +60,9 @@ def _walk_csc(m, ref, asm, n_iter=3, scale=1e-4, seed=5):
     return s
 
 
-def test_plate_200x60_classes_on(gpu, ref):
+@pytest.mark.parametrize("shape", ["narrow", "wide"])
+def test_plate_200x60_classes_on(gpu, ref, shape, monkeypatch):
+    monkeypatch.setenv("CB_KT", shape)            # both compiled shapes of the stream kernel
     m = meshgen.plate_model(200, 60, SLVFLAG=0)
     asm = cb.Assembler(m, layout=cb.CB_MAT_CSC)
     asm.begin_increment(); asm.stiff()
@@ -70,12 +72,25 @@ def test_plate_200x60_classes_on(gpu, ref):
     asm.close()
 
 
-def test_plate_200x60_jittered_classes_off(gpu, ref):
+@pytest.mark.parametrize("shape", ["narrow", "wide"])
+def test_plate_200x60_jittered_classes_off(gpu, ref, shape, monkeypatch):
+    monkeypatch.setenv("CB_KT", shape)
     m = meshgen.plate_model(200, 60, SLVFLAG=0, jitter=0.2, z_bump=0.01)
     asm = cb.Assembler(m, layout=cb.CB_MAT_CSC)
     asm.begin_increment(); asm.stiff()
     assert asm.geometry_classes == 0, "jittered plate: every shell streams / recomputes its own DKT data (<0>)"
     _walk_csc(m, ref, asm)
+    asm.close()
+
+
+@pytest.mark.parametrize("shape", ["narrow", "wide"])
+def test_plate_unionjack_split_blocks(gpu, ref, shape, monkeypatch):
+    """joints with 8 shells around them: diagonal blocks of 8 contributions are cut in two lane parts
+    (first part stored, follower part added at the end of the tile)"""
+    monkeypatch.setenv("CB_KT", shape)
+    m = meshgen.plate_model(90, 40, SLVFLAG=0, unionjack=True, z_bump=0.02)
+    asm = cb.Assembler(m, layout=cb.CB_MAT_CSC)
+    _walk_csc(m, ref, asm, n_iter=2)
     asm.close()
 
 

@@ -134,6 +134,8 @@ struct cb_handle {
     long jl0 = 0, jl1 = 0, ql0 = 0, ql1 = 0;   // joints touched by local elements, their equations
     // shells
     DevBuf<int32_t> sh_nodes;
+    DevBuf<uint8_t> sh_own;       // first-element-at-joint bits (fused nodal update, CbDev::sh_own)
+    bool fuse_node = false;       // shell-only, ANAFLAG 2, every touched joint has a shell: see CbForceArgs
     DevBuf<double> sh_const, sh_keb, sh_kebc, sh_der, sh_Nm, sh_fg, sh_dens;
     long ncontrib = 0;
     DevBuf<double> sh_frame[3], sh_dsl[3], sh_ef[3];   // 0 = committed, 1/2 = iterate ping-pong
@@ -199,7 +201,7 @@ static CbDev make_dev(cb_handle *h)
     d.NE_TR = h->sz.NE_TR; d.NE_FR = h->sz.NE_FR; d.NE_SH = h->sz.NE_SH; d.NE_BR = h->NE_BR;
     d.ANAFLAG = h->fl.ANAFLAG;
     d.jc = h->jc.p;
-    d.sh_nodes = h->sh_nodes.p; d.sh_const = h->sh_const.p; d.sh_keb = h->sh_keb.p;
+    d.sh_nodes = h->sh_nodes.p; d.sh_const = h->sh_const.p; d.sh_keb = h->sh_keb.p; d.sh_own = h->sh_own.p;
     d.sh_Nm = h->sh_Nm.p; d.sh_fg = h->sh_fg.p; d.sh_der = h->sh_der.p;
     d.fr_nodes = h->fr_nodes.p; d.fr_const = h->fr_const.p; d.fr_offset = h->fr_offset.p;
     d.fr_osflag = h->fr_osflag.p; d.fr_mendrel = h->fr_mendrel.p; d.fr_simple = h->fr_simple;
@@ -566,6 +568,7 @@ extern "C" void cb_destroy(cb_handle *h)
         h->fr_frame[g].release(); h->fr_xfr[g].release(); h->fr_efFE[g].release();
         h->fr_ef[g].release();
     }
+    h->sh_own.release();
     for (DevBuf<int32_t> *b : {&h->fr_gid, &h->sh_gid, &h->jc, &h->sh_nodes, &h->tr_nodes, &h->fr_nodes, &h->fr_osflag,
                                &h->fr_mendrel, &h->br_nodes, &h->node_cstart})
         b->release();
@@ -625,6 +628,22 @@ static int build_plan(cb_handle *h)
                     CbCorner c{}; c.e = (int32_t)e; c.type = (uint8_t)t; c.b = (uint8_t)a;
                     corners[fill[j]++] = c;
                 }
+    }
+    {   // fused nodal update (CbForceArgs::fuse_node): which shell writes a joint's new coordinates
+        std::vector<uint8_t> own(ne[2], 0);
+        bool all_touched = true;
+        long lo = NJ, hi = 0;
+        for (long j = 0; j < NJ; ++j)
+            if (cstart[j + 1] > cstart[j]) {
+                const CbCorner &c = corners[cstart[j]];
+                if (c.type == CB_T_SHELL) own[c.e] |= (uint8_t)(1u << c.b);
+                lo = std::min(lo, j); hi = j + 1;
+            }
+        const bool whole = h->j0 == 0 && h->j1 == NJ;
+        for (long j = whole ? 0 : lo; j < (whole ? NJ : hi); ++j) if (cstart[j + 1] == cstart[j]) all_touched = false;
+        h->fuse_node = ne[2] && !ne[0] && !ne[1] && !ne[3] && h->fl.ANAFLAG == 2 && all_touched &&
+                       !getenv("CB_NO_FUSED_NODE_UPDATE");
+        if (h->fuse_node && h->sh_own.upload(own)) return CB_ERR_CUDA;
     }
     // joints touched by this rank's elements and their equation range
     h->jl0 = NJ; h->jl1 = 0; h->ql0 = h->sz.NEQ; h->ql1 = 0;
@@ -821,6 +840,7 @@ static int build_plan(cb_handle *h)
                 if ((h->h_mask[j] >> r) & 1) top = r + 1;
         h->max_dof = top <= 3 ? 3 : (top <= 6 ? 6 : 7);
         h->mixed = (has3 && h->max_dof != 3) || (has6 && h->max_dof != 6) || (has7 && h->max_dof != 7);
+        if (h->max_dof != 6) h->fuse_node = false;      // the fused gather walks six equations per joint
     }
     {   // Blocks whose columns start on an odd Ax index fall off the tile kernels' 16-byte store path.
         // Which parity the bulk of the blocks has depends on the free DOFs of the joints ahead of them
@@ -1647,8 +1667,11 @@ extern "C" int cb_update_forces_begin(cb_handle *h, const double *dd_dev, double
         const long q0 = whole ? 0 : h->ql0, nq = whole ? h->sz.NEQ : h->ql1 - h->ql0;
         a.axpy_n = nq > 0 ? nq : 0; a.axpy_x = h->dd.p + q0; a.axpy_y = h->d_temp.p + q0;
     }
-    if (cbk_node_update(a, s)) return fail(CB_ERR_CUDA, "node update launch");
-    ++h->launches;
+    a.fuse_node = h->fuse_node ? 1 : 0; a.d_temp = h->d_temp.p;
+    if (!h->fuse_node) {
+        if (cbk_node_update(a, s)) return fail(CB_ERR_CUDA, "node update launch");
+        ++h->launches;
+    }
     if (cbk_forces(a, s, &h->launches)) return fail(CB_ERR_CUDA, "forces launch");
     h->forces_open = true;
     if (h->fl.ANAFLAG == 3 && (first_fr || first_sh)) {
@@ -1686,8 +1709,10 @@ extern "C" int cb_update_forces_end(cb_handle *h, int first_fr, int first_sh, do
         }
     }
     if (cbk_frame_trip(a.d, s, &h->launches)) return fail(CB_ERR_CUDA, "frame trip launch");
+    a.fuse_node = h->fuse_node ? 1 : 0; a.d_temp = h->d_temp.p;
     if (cbk_gather_f(a, s)) return fail(CB_ERR_CUDA, "gather launch");
     ++h->launches;
+    if (h->fuse_node) std::swap(h->x_temp.p, h->x_ip.p);     // the force kernel left x_temp + dd in x_ip's buffer
     CUDA_TRY(cudaEventRecord(h->ev5, s));
     std::swap(h->eP, h->eN);                      // ef_ip <- ef_i (main.c:1982-1984) by renaming
     h->forces_timed = true; h->krec_fresh = true;

@@ -508,12 +508,14 @@ __device__ __forceinline__ void shell_triad(const double *xj, const double *xk, 
 #ifndef CB_FORCES_CTAS
 #define CB_FORCES_CTAS 4          // class tables: latency-bound, 4 resident CTAs per SM (128 registers)
 #endif                            // per-element matrices: HBM-bound, 2 CTAs with 254 registers measure faster
-template <bool CLS>
+// FUSE: x_temp holds the coordinates BEFORE this iteration's update; the kernel forms x + dd itself and
+// the first shell at a joint writes the result to x_new (CbForceArgs::fuse_node)
+template <bool CLS, bool FUSE>
 __global__ void __launch_bounds__(CB_TPB, CLS ? CB_FORCES_CTAS : 2)
 k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restrict__ dd,
                const double *__restrict__ frame_ip, double *__restrict__ frame_i,
                double *__restrict__ dsl_i, const double *__restrict__ ef_ip,
-               double *__restrict__ ef_i)
+               double *__restrict__ ef_i, double *__restrict__ x_new)
 {
     // [99][CB_TPB]: the element's DKT matrix (81) and previous end forces (18), copied straight
     // from HBM by cp.async at kernel entry so their latency overlaps the geometry update; the
@@ -569,6 +571,24 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
     for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int m = 0; m < 3; ++m) X[a][m] = __ldg(&x_temp[(long)nn[a] * 3 + m]);
+    double DD[3][6];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) gather_node6(d.jc, dd, nn[a], DD[a]);
+    if (FUSE) {
+        // updatc, nodal part (misc.c:83-93): x_temp += dd on the free translations.  gather_node6 reads a
+        // fixed DOF as 0 and x + 0.0 == x bit for bit, so every shell at a joint forms the same value;
+        // the first one stores it
+        const unsigned own = d.sh_own[e];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int m = 0; m < 3; ++m) X[a][m] = X[a][m] + DD[a][m];
+            if ((own >> a) & 1u) {
+#pragma unroll
+                for (int m = 0; m < 3; ++m) x_new[(long)nn[a] * 3 + m] = X[a][m];
+            }
+        }
+    }
 
     shell_triad(X[0], X[1], X[2], Ri, dsl);
 
@@ -596,9 +616,6 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
     }
 
     // bending: incremental force ke_b * ddb, ddb = T_ip * DD on the bending DOFs (1746-1785)
-    double DD[3][6];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) gather_node6(d.jc, dd, nn[a], DD[a]);
     double ddb[9];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -1470,8 +1487,46 @@ k_gather_f(CbDev d, long j0, long j1, const int32_t *__restrict__ cstart,
     }
 }
 
+// shell-only models with the nodal update fused into the force kernel: the same segmented reduction over
+// the joints [jl0, jl1) this rank touches - f_temp for the ones it owns - plus d_temp += dd (main.c:1949) on
+// every touched joint's equations
+__global__ void __launch_bounds__(256)
+k_gather_f_axpy(CbDev d, long jl0, long jl1, long jo0, long jo1, const int32_t *__restrict__ cstart,
+                const CbCorner *__restrict__ corners, double *__restrict__ f, const double *__restrict__ dd,
+                double *__restrict__ d_temp)
+{
+    const long n = jl0 + blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (n >= jl1) return;
+    const int4 qa = reinterpret_cast<const int4 *>(d.jc)[n * 2], qb = reinterpret_cast<const int4 *>(d.jc)[n * 2 + 1];
+    const int q[6] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y};
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    const bool own = n >= jo0 && n < jo1;
+    if (own) {
+        const int c0 = cstart[n], c1 = cstart[n + 1];
+        for (int c = c0; c < c1; ++c) {
+            const CbCorner cr = corners[c];
+            const double2 *p = reinterpret_cast<const double2 *>(CB_FG(d.sh_fg, cr.b, cr.e, d.NE_SH));
+            const double2 v0 = p[0], v1 = p[1], v2 = p[2];
+            acc[0] += v0.x; acc[1] += v0.y; acc[2] += v1.x; acc[3] += v1.y; acc[4] += v2.x; acc[5] += v2.y;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+        if (q[r] != 0) {
+            if (own) f[q[r] - 1] = acc[r];
+            d_temp[q[r] - 1] += dd[q[r] - 1];
+        }
+}
+
 int cbk_gather_f(const CbForceArgs &a, cudaStream_t s)
 {
+    if (a.fuse_node) {
+        const long nj = a.jl1 - a.jl0;
+        if (nj <= 0) return 0;
+        k_gather_f_axpy<<<(unsigned)((nj + 255) / 256), 256, 0, s>>>(a.d, a.jl0, a.jl1, a.jo0, a.jo1, a.node_cstart,
+                                                                     a.corners, a.f_temp, a.dd, a.d_temp);
+        return cudaGetLastError() != cudaSuccess;
+    }
     const long nj = a.jo1 - a.jo0;
     if (nj <= 0) return 0;
     unsigned g = (unsigned)((nj + 255) / 256);
@@ -1536,10 +1591,10 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
         static CbPerDevice cfg{};
         int &configured = cfg.v[cb_device_slot()];
         if (!configured) {
-            if (cudaFuncSetAttribute(k_shell_forces<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem) != cudaSuccess ||
-                cudaFuncSetAttribute(k_shell_forces<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem) != cudaSuccess)
+            if (cudaFuncSetAttribute(k_shell_forces<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                cudaFuncSetAttribute(k_shell_forces<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                cudaFuncSetAttribute(k_shell_forces<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                cudaFuncSetAttribute(k_shell_forces<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                 return 1;
             configured = 1;
         }
@@ -1549,12 +1604,19 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
             k_shell_forces_pl<<<(unsigned)((d.NE_SH + 63) / 64), 64, 0, s>>>(
                 d, a.x_temp, a.x_ip, a.dd, a.sh_frame_ip, a.sh_frame_i, a.sh_dsl_ip, a.sh_dsl_i,
                 a.sh_ef_ip, a.sh_ef_i);
+        } else if (a.fuse_node) {       // x_temp: coordinates before the update, x_ip's buffer receives the new ones
+            if (d.sh_class)
+                k_shell_forces<true, true><<<g, CB_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
+                                                                   a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i, a.x_ip);
+            else
+                k_shell_forces<false, true><<<g, CB_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
+                                                                    a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i, a.x_ip);
         } else if (d.sh_class)
-            k_shell_forces<true><<<g, CB_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
-                                                         a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i);
+            k_shell_forces<true, false><<<g, CB_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
+                                                                a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i, nullptr);
         else
-            k_shell_forces<false><<<g, CB_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
-                                                          a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i);
+            k_shell_forces<false, false><<<g, CB_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
+                                                                 a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i, nullptr);
         ++*launches;
     }
     return cudaGetLastError() != cudaSuccess;

@@ -207,6 +207,8 @@ struct CbDev {
     const int32_t *jc;       // [NJ][8]
     // shells
     const int32_t *sh_nodes; // [NE][4] 0-based
+    const uint8_t *sh_own;   // [NE] bit a: this shell is the first element at its local joint a (it writes the
+                             // joint's updated coordinates when the nodal update is fused into the force kernel)
     const double *sh_const;  // [CB_SH_CONST][NE]
     const double *sh_keb;    // [81][NE], component = CB_KEB(i,j)
     double *sh_der;          // [CB_SH_DER][NE] geometry-constant derived data (k_shell_init_keb):
@@ -313,6 +315,12 @@ struct CbForceArgs {
     CbDev d;
     double *x_temp, *x_ip;
     const double *dd;        // [NEQ] device
+    // shell-only geometric-nonlinear models: updatc's nodal part (misc.c:83-93) is evaluated inside the force
+    // kernel (every shell forms x_temp + dd of its joints anyway; the first shell at a joint writes it) into
+    // the buffer that held x_ip, which then becomes x_temp by renaming - and d_temp += dd (main.c:1949)
+    // rides in the gather: two launches per force pass instead of three
+    int fuse_node;
+    double *d_temp;
     // shells
     const double *sh_frame_ip; double *sh_frame_i; double *sh_dsl_i; const double *sh_dsl_ip;
     const double *sh_ef_ip; double *sh_ef_i;

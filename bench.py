@@ -401,36 +401,85 @@ def run_gpu(a):
     ms_step = dev_ms / a.steps
     value = total_el / (ms_step * 1e-3)
 
-    # ---- e2e through the C-ABI with host buffers (N=1: dd H2D, f_temp + CSC values D2H) -------
-    e2e = None
-    if world == 1:
-        hdd = asm.pinned(m.NEQ); hdd[:] = step_dd
-        hf = asm.pinned(m.NEQ)
-        hAx = asm.pinned(nnz)
-        import ctypes as C
-        lib = asm.lib
+    # ---- e2e through the C-ABI with HOST buffers, every rank over its own PCIe link: dd host -> device,
+    # f_temp and the CSC values of the owned column slice device -> pinned host, every step.  The matrix
+    # crosses as its packed upper triangle (K_t is symmetric) on a second stream and `threads` host threads
+    # rebuild the full columns umfpack_di_* takes while later chunks are still on the wire
+    # (cb_csc_values_begin / _end around cb_update_forces); `plain` is the same step with the full 2 GB copy
+    # of cb_get_csc_values.
+    import ctypes as C
+    lib = asm.lib
+    threads = max(1, min(32, (os.cpu_count() or 1) // max(1, world)))
+    # how much of the matrix crosses as full columns (no host work) and how much as packed upper triangles
+    # (half the bytes, rebuilt by host threads): with >= 12 threads per rank every third chunk goes in full,
+    # with fewer the host cannot keep up with the copy engine and everything does (measured, profiles/README)
+    os.environ.setdefault("CB_SYM_FULL_EVERY", "3" if threads >= 12 else "1")
+    nnz_u = lib.cb_csc_upper_nnz(asm.h)
+    neq_loc = lib.cb_local_equations(asm.h)
+    hdd = asm.pinned(m.NEQ); hdd[:] = step_dd
+    hf = asm.pinned(m.NEQ)
+    hAx = asm.pinned(nnz)
+    hAxu = asm.pinned(nnz_u)
 
-        def e2e_step():
-            asm.stiff()
-            rc = lib.cb_get_csc_values(asm.h, C.c_void_p(hAx.ctypes.data)); assert rc == 0
-            cdl = C.c_double(1.0); fr = C.c_int(0); sh = C.c_int(0)
-            rc = lib.cb_update_forces(asm.h, C.c_void_p(hdd.ctypes.data), C.byref(cdl), C.c_int(0),
-                                      C.c_void_p(hf.ctypes.data), C.byref(fr), C.byref(sh))
-            assert rc == 0
-            asm.end_iteration()
+    def forces_host():
+        cdl = C.c_double(1.0); fr = C.c_int(0); sh = C.c_int(0)
+        rc = lib.cb_update_forces(asm.h, C.c_void_p(hdd.ctypes.data), C.byref(cdl), C.c_int(0),
+                                  C.c_void_p(hf.ctypes.data), C.byref(fr), C.byref(sh))
+        assert rc == 0
 
-        e2e_step()
-        asm.sync()
-        ke = max(3, min(a.steps, 10))
+    def e2e_step_mirror():
+        asm.stiff()
+        rc = lib.cb_csc_values_begin(asm.h, C.c_void_p(hAx.ctypes.data), C.c_void_p(hAxu.ctypes.data), C.c_int(threads))
+        assert rc == 0, lib.cb_last_error()
+        forces_host()
+        rc = lib.cb_csc_values_end(asm.h); assert rc == 0
+        asm.end_iteration()
+
+    def e2e_step_plain():
+        asm.stiff()
+        rc = lib.cb_get_csc_values(asm.h, C.c_void_p(hAx.ctypes.data)); assert rc == 0
+        forces_host()
+        asm.end_iteration()
+
+    def time_e2e(fn, k):
+        fn(); barrier()
         t0 = time.perf_counter()
-        for _ in range(ke):
-            e2e_step()
-        asm.sync()
-        e_ms = 1e3 * (time.perf_counter() - t0) / ke
-        e2e = {"value": total_el / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
-               "h2d_bytes_per_step": int(m.NEQ * 8), "d2h_bytes_per_step": int(m.NEQ * 8 + nnz * 8),
-               "note": "dd pinned host->device; f_temp and all CSC values device->pinned host each "
-                       "step (what the host-side solve() consumes); steps=%d" % ke}
+        for _ in range(k):
+            fn()
+        barrier()
+        ms = 1e3 * (time.perf_counter() - t0) / k
+        if dist is not None:
+            import torch
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+
+    def e2e_step_upper():
+        asm.stiff()
+        rc = lib.cb_get_csc_upper_values(asm.h, C.c_void_p(hAxu.ctypes.data)); assert rc == 0
+        forces_host()
+        asm.end_iteration()
+
+    ke = max(3, min(a.steps, 10))
+    e_ms = time_e2e(e2e_step_mirror, ke)
+    p_ms = time_e2e(e2e_step_plain, max(3, ke // 2))
+    u_ms = time_e2e(e2e_step_upper, max(3, ke // 2))
+    e2e = {"value": total_el / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
+           "h2d_bytes_per_step": int(neq_loc * 8) * world, "d2h_bytes_per_step": int(lib.cb_csc_values_d2h_bytes(asm.h) + neq_loc * 8) * world,
+           "host_threads_per_rank": threads, "steps": ke,
+           "full_every": int(os.environ["CB_SYM_FULL_EVERY"]),
+           "plain": {"ms_per_step": p_ms, "value": total_el / (p_ms * 1e-3),
+                     "d2h_bytes_per_step": int(neq_loc * 8 + nnz * 8) * world},
+           "upper_only": {"ms_per_step": u_ms, "value": total_el / (u_ms * 1e-3),
+                          "d2h_bytes_per_step": int(neq_loc * 8 + nnz_u * 8) * world,
+                          "note": "the packed upper-triangular CSC alone (cb_get_csc_upper_values): what a symmetric "
+                                  "host solver needs; not the full matrix umfpack_di_* takes"},
+           "note": "per rank and step: dd pinned host->device; f_temp and the owned CSC slice device->pinned host in "
+                   "chunks on a second stream while cb_update_forces runs - every full_every-th chunk as full columns, "
+                   "the others as packed upper triangles whose full columns host threads rebuild (the FULL matrix "
+                   "umfpack_di_* consumes ends up on the host); wall clock between barriers, max over ranks; `plain` "
+                   "ships all nnz values with cb_get_csc_values"}
 
     ncls = asm.geometry_classes
     map_bytes = asm.map_bytes

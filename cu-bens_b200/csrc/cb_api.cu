@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <chrono>
 #include <unordered_map>
 #include <cstring>
 #include <cstdlib>
@@ -78,6 +79,8 @@ template <typename T> struct DevBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
+
+#include "cb_sym.cuh"
 
 struct Plan {
     DevBuf<CbPair> pairs;
@@ -178,6 +181,7 @@ struct cb_handle {
     DevBuf<CbContrib> contribs;
     int max_dof = 3, mixed = 0;
     Plan plan_csc, plan_sky;
+    SymPlan sym;                  // symmetric hand-off to the host solver (cb_sym.cuh)
     DevBuf<int> Ap, Ai;
     DevBuf<long> maxa;
     DevBuf<double> Ax, ss, Mx;    // Mx: full-order mass on the CSC pattern (models with bricks)
@@ -551,7 +555,13 @@ extern "C" void cb_destroy(cb_handle *h)
 {
     if (!h) return;
     if (!g_host_only) cudaSetDevice(h->fl.device);
+    if (h->sym.busy) { h->sym.worker.join(); h->sym.busy = false; }
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->sym.copy_stream) { cudaStreamSynchronize(h->sym.copy_stream); cudaStreamDestroy(h->sym.copy_stream); }
+    if (h->sym.ev_pack) cudaEventDestroy(h->sym.ev_pack);
+    for (cudaEvent_t e : h->sym.ev_chunk) if (e) cudaEventDestroy(e);
+    h->sym.d_ulen0.release(); h->sym.d_slen.release(); h->sym.d_nfree.release(); h->sym.d_colh.release();
+    h->sym.d_ubase.release(); h->sym.d_base.release(); h->sym.packed.release();
     for (DevBuf<double> *b : {&h->x, &h->x_temp, &h->x_ip, &h->dd, &h->f_temp, &h->f, &h->d,
                               &h->d_temp, &h->sm, &h->qvec, &h->sums, &h->sums_part, &h->sh_const, &h->sh_keb, &h->sh_kebc, &h->sh_der, &h->sh_Nm, &h->sh_fg,
                               &h->sh_dens, &h->tr_const, &h->tr_fg, &h->tr_dens, &h->fr_const,
@@ -1764,12 +1774,18 @@ extern "C" int cb_update_forces(cb_handle *h, const double *dd, double *dlpf_ino
 {
     if (!h || !dd) return fail(CB_ERR_ARG, "null argument");
     cudaSetDevice(h->fl.device);
-    CUDA_TRY(cudaMemcpyAsync(h->dd.p, dd, h->sz.NEQ * sizeof(double), cudaMemcpyHostToDevice,
-                             h->stream));
-    int rc = cb_update_forces_dev(h, h->dd.p, dlpf_inout, itecnt, frcchk_fr, frcchk_sh);
+    int rc = build_plan(h); if (rc) return rc;
+    // an element-partitioned rank only reads / produces the equations of the joints its elements touch: the
+    // host vectors keep their global length, the copies cover that range (per-rank PCIe traffic does not
+    // grow with the number of ranks)
+    const bool whole = h->j0 == 0 && h->j1 == h->sz.NJ;
+    const long q0 = whole ? 0 : h->ql0, nq = whole ? h->sz.NEQ : h->ql1 - h->ql0;
+    if (nq > 0)
+        CUDA_TRY(cudaMemcpyAsync(h->dd.p + q0, dd + q0, nq * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    rc = cb_update_forces_dev(h, h->dd.p, dlpf_inout, itecnt, frcchk_fr, frcchk_sh);
     if (rc) return rc;
-    if (f_temp_out)
-        CUDA_TRY(cudaMemcpyAsync(f_temp_out, h->f_temp.p, h->sz.NEQ * sizeof(double),
+    if (f_temp_out && nq > 0)
+        CUDA_TRY(cudaMemcpyAsync(f_temp_out + q0, h->f_temp.p + q0, nq * sizeof(double),
                                  cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return CB_OK;
@@ -2315,6 +2331,11 @@ extern "C" void *cb_host_alloc(unsigned long bytes)
 }
 extern "C" void cb_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" long cb_map_bytes(cb_handle *h) { return h ? h->map_bytes : 0; }
+extern "C" long cb_local_equations(cb_handle *h)
+{
+    if (!h || build_plan(h)) return -1;
+    return (h->j0 == 0 && h->j1 == h->sz.NJ) ? h->sz.NEQ : h->ql1 - h->ql0;
+}
 extern "C" int cb_geometry_classes(cb_handle *h) { return (h && h->cls_on) ? h->ncls : 0; }
 extern "C" int cb_sync(cb_handle *h)
 {
@@ -2324,3 +2345,5 @@ extern "C" int cb_sync(cb_handle *h)
     return CB_OK;
 }
 extern "C" void *cb_stream(cb_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+#include "cb_sym_impl.cuh"

@@ -38,7 +38,9 @@ EXPORTS = [
     "cb_dev_sums", "cb_get_sums", "cb_get_yldflag", "cb_set_yldflag", "cb_get_mass_csc_values", "cb_dev_Mx",
     "cb_geometry_classes", "cb_keep_ip", "cb_checkpoint_save", "cb_checkpoint_load",
     "cb_set_element_ids", "cb_update_forces_begin", "cb_update_forces_end", "cb_measure_fp64_tflops",
-    "cb_plan_selfcheck",
+    "cb_plan_selfcheck", "cb_csc_upper_nnz", "cb_csc_upper_pattern", "cb_get_csc_upper_values",
+    "cb_csc_values_begin", "cb_csc_values_end", "cb_get_csc_values_mirrored", "cb_sym_selftest",
+    "cb_local_equations", "cb_csc_values_d2h_bytes",
 ]
 
 
@@ -80,6 +82,9 @@ def load_library(path=None):
     lib.cb_last_error.restype = C.c_char_p
     lib.cb_csc_nnz.restype = C.c_long
     lib.cb_csc_compact.restype = C.c_long
+    lib.cb_csc_upper_nnz.restype = C.c_long
+    lib.cb_local_equations.restype = C.c_long
+    lib.cb_csc_values_d2h_bytes.restype = C.c_long
     lib.cb_launch_count.restype = C.c_long
     lib.cb_map_bytes.restype = C.c_long
     lib.cb_last_stiff_ms.restype = C.c_double
@@ -130,6 +135,19 @@ def plan_selfcheck(m, j0=0, j1=0, layout=CB_MAT_CSC):
     if rc != 0:
         raise CubensError(f"cb_plan_selfcheck error {rc}: {lib.cb_last_error().decode()}")
     return dict(zip(("nnz", "tiles", "rows", "pairs", "steps", "kind"), list(st)))
+
+
+def sym_selftest(m, j0=0, j1=0, nthreads=4, layout=CB_MAT_CSC):
+    """cb_sym_selftest: packed upper-triangle layout + threaded rebuild of the full matrix, on the host.
+    Returns the wall time of the rebuild in seconds."""
+    lib = load_library()
+    sz, fl, cm, keep = _c_model(m, layout, 0)
+    sec = C.c_double(0.0)
+    rc = lib.cb_sym_selftest(C.byref(sz), C.byref(fl), C.byref(cm), C.c_long(j0), C.c_long(j1), C.c_int(nthreads),
+                             C.byref(sec))
+    if rc != 0:
+        raise CubensError(f"cb_sym_selftest error {rc}: {lib.cb_last_error().decode()}")
+    return sec.value
 
 
 class Assembler:
@@ -279,6 +297,24 @@ class Assembler:
     def csc_values(self):
         Ax = np.zeros(self.lib.cb_csc_nnz(self.h))
         self._check(self.lib.cb_get_csc_values(self.h, _p(Ax)))
+        return Ax
+
+    def csc_upper(self):
+        """upper-triangular CSC of the owned slice (Apu, Aiu, Axu)"""
+        nu = self.lib.cb_csc_upper_nnz(self.h)
+        if nu < 0:
+            raise CubensError(self.lib.cb_last_error().decode())
+        Apu = np.zeros(self.m.NEQ + 1, dtype=np.int32); Aiu = np.zeros(nu, dtype=np.int32); Axu = np.zeros(nu)
+        self._check(self.lib.cb_csc_upper_pattern(self.h, _p(Apu), _p(Aiu)))
+        self._check(self.lib.cb_get_csc_upper_values(self.h, _p(Axu)))
+        return Apu, Aiu, Axu
+
+    def csc_values_mirrored(self, nthreads=8, Ax=None, staging=None):
+        """full Ax rebuilt on the host from the packed upper triangle (half the PCIe traffic)"""
+        nnz = self.lib.cb_csc_nnz(self.h); nu = self.lib.cb_csc_upper_nnz(self.h)
+        Ax = np.zeros(nnz) if Ax is None else Ax
+        staging = self.pinned(nu) if staging is None else staging
+        self._check(self.lib.cb_get_csc_values_mirrored(self.h, _p(Ax), C.c_void_p(staging.ctypes.data), C.c_int(nthreads)))
         return Ax
 
     def csc_compact(self, drop_tol=1e-10):

@@ -180,6 +180,29 @@ int  cb_get_csc_values(cb_handle *h, double *Ax);
 /* value-thresholded copy with the reference's rule fabs(a) > drop_tol (solve.c:112);      */
 /* returns the compacted nnz (Ap/Ai/Ax sized for cb_csc_nnz), or -1                        */
 long cb_csc_compact(cb_handle *h, double drop_tol, int *Ap, int *Ai, double *Ax);
+/* Symmetric hand-off (K_t is symmetric; the device -> host copy of Ax is what an iteration with a
+ * host-side solver waits for): the upper triangle of the owned column slice - a prefix of
+ * every column, rows being ascending - is packed on the device and shipped in chunks on a second stream.
+ *   cb_csc_upper_nnz / _pattern / cb_get_csc_upper_values   standard upper-triangular CSC (Apu[NEQ+1],
+ *       Aiu, Axu) for symmetric solvers; on an element-partitioned handle the rows of neighbour joints
+ *       past the owned range are appended to each column (their mirror images live on another rank)
+ *   cb_csc_values_begin / _end      the FULL Ax[cb_csc_nnz] that umfpack_di_* takes (solve.c:122-134) from
+ *       half the PCIe traffic: nthreads host threads rebuild the columns (copy of the upper part,
+ *       transposes of the upper blocks of higher-numbered joints) while later chunks are on the wire.
+ *       Axu_staging [cb_csc_upper_nnz] must be page-locked (cb_host_alloc).  _begin only queues the work,
+ *       so the caller can run cb_update_forces meanwhile; _end waits for the matrix
+ *   cb_get_csc_values_mirrored      = _begin + _end                                                    */
+long cb_csc_upper_nnz(cb_handle *h);
+int  cb_csc_upper_pattern(cb_handle *h, int *Apu, int *Aiu);
+int  cb_get_csc_upper_values(cb_handle *h, double *Axu);
+int  cb_csc_values_begin(cb_handle *h, double *Ax, double *Axu_staging, int nthreads);
+int  cb_csc_values_end(cb_handle *h);
+int  cb_get_csc_values_mirrored(cb_handle *h, double *Ax, double *Axu_staging, int nthreads);
+/* The copy engine and the host's memory bandwidth are balanced by sending every k-th chunk of joints as
+ * full columns straight into Ax (no host work) - environment CB_SYM_FULL_EVERY = k when the first of these
+ * calls is made (default 5; 1 = everything in full, 0 = everything packed); Ax should be page-locked too.
+ * cb_csc_values_d2h_bytes: bytes one cb_csc_values_begin moves device -> host                       */
+long cb_csc_values_d2h_bytes(cb_handle *h);
 int  cb_get_mass(cb_handle *h, double *sm_diag);       /* diagonal [NEQ], SLVFLAG 0 layout */
 /* models with bricks: cb_mass also assembles the reference's full-order mass matrix (consistent
  * mass_br brick.c:399-537, lumped mass_sh on the diagonal shell.c:1576-1588; dense [NEQ][NEQ] in
@@ -247,6 +270,9 @@ double cb_last_stiff_ms(cb_handle *h);
 double cb_last_forces_ms(cb_handle *h);
 /* bytes of implementation-only maps read per cb_stiff (reported next to the roofline)      */
 long cb_map_bytes(cb_handle *h);
+/* equations of the joints this handle's elements touch (= NEQ unless element-partitioned): the part of
+ * dd / f_temp that cb_update_forces moves between host and device                            */
+long cb_local_equations(cb_handle *h);
 /* number of geometry classes in use (shells whose geometry-constant inputs are bit-identical share
  * one cache-resident copy of the DKT matrix), 0 when every shell keeps its own copy: more than
  * 1024 classes, or after cb_mass rewrote the reference geometry.  Setting the
@@ -273,6 +299,11 @@ double cb_measure_fp64_tflops(int device);
  * mean steps per tile, plan kind (3 stream, 2 duo, 1 general tiles, 0 block-owner).                 */
 int  cb_plan_selfcheck(const cb_sizes *sz, const cb_flags *fl, const cb_model *m, long j0, long j1,
                        long *stats);
+/* Host-only self test of the packed upper-triangle layout and of the threaded rebuild of the full
+ * matrix (no device): synthetic symmetric values on the model's pattern; seconds (may be NULL) receives the
+ * wall time of the rebuild with nthreads threads                                                       */
+int  cb_sym_selftest(const cb_sizes *sz, const cb_flags *fl, const cb_model *m, long j0, long j1,
+                     int nthreads, double *seconds);
 /* the CUDA stream (cudaStream_t cast to void*) all of this handle's kernels run on         */
 void *cb_stream(cb_handle *h);
 

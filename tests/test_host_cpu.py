@@ -371,3 +371,22 @@ def test_plan_selfcheck_other_element_types():
     assert cb.plan_selfcheck(meshgen.lattice_model(5, SLVFLAG=2))["kind"] == 1
     assert cb.plan_selfcheck(meshgen.truss_model(4, SLVFLAG=2))["kind"] == 1
     assert cb.plan_selfcheck(meshgen.brick_model(3, 3, 3, skin=True))["kind"] == 1
+
+
+@pytest.mark.parametrize("kind", ["plate", "jitter", "partition_lo", "partition_mid", "partition_hi", "unionjack",
+                                  "lattice", "brick_skin"])
+def test_symmetric_handoff_host_side(kind):
+    """packed upper-triangle layout (what k_pack_upper produces), its CSC pattern and the threaded rebuild of
+    the full matrix, on the host with synthetic symmetric values (cb_sym_selftest; no device)"""
+    import cubens_b200 as cb
+    from cubens_b200 import meshgen
+    own = (0, 0)
+    if kind == "lattice":
+        m = meshgen.lattice_model(6, SLVFLAG=2)
+    elif kind == "brick_skin":
+        m = meshgen.brick_model(3, 4, 3, skin=True)
+    else:
+        m = meshgen.plate_model(60, 40, SLVFLAG=2, jitter=0.2 if kind == "jitter" else 0.0,
+                                unionjack=kind == "unionjack")
+        own = {"partition_lo": (0, 900), "partition_mid": (300, 1500), "partition_hi": (1500, m.NJ)}.get(kind, (0, 0))
+    assert cb.sym_selftest(m, own[0], own[1], nthreads=3) >= 0.0

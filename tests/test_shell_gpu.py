@@ -119,3 +119,27 @@ def test_upload_geometry_rebuilds_derived_data(gpu):
     b.begin_increment(); b.stiff()
     assert np.array_equal(b.skyline(), K1) and np.array_equal(b.csc_values(), A1)
     b.close()
+
+
+def test_symmetric_handoff_rebuilds_full_matrix(gpu):
+    """cb_csc_values_begin / _end: the packed upper triangle crosses PCIe, host threads rebuild the full
+    columns.  The upper part is bit-identical to cb_get_csc_values, the lower part is its exact mirror
+    (the device's own lower entries agree with it to rounding: K_t is symmetric)."""
+    m = meshgen.plate_model(40, 27, z_bump=0.02, SLVFLAG=2)
+    a = cb.Assembler(m, layout=cb.CB_MAT_CSC)
+    a.begin_increment(); a.update_forces(meshgen.perturbation(m, scale=1e-3)); a.end_iteration(); a.stiff()
+    Ap, Ai, Ax = a.csc()
+    full = a.csc_values_mirrored(nthreads=3)
+    cols = np.repeat(np.arange(m.NEQ), np.diff(Ap))
+    up = Ai <= cols
+    assert np.array_equal(full[up], Ax[up])
+    assert np.abs(full - Ax).max() <= 1e-13 * np.abs(Ax).max()
+    # exact symmetry of the rebuilt matrix
+    import scipy.sparse as sp
+    K = sp.csc_matrix((full, Ai, Ap), shape=(m.NEQ, m.NEQ))
+    assert abs(K - K.T).max() == 0.0
+    # the packed stream is an upper-triangular CSC of its own
+    Apu, Aiu, Axu = a.csc_upper()
+    U = sp.csc_matrix((Axu, Aiu, Apu), shape=(m.NEQ, m.NEQ))
+    assert abs(sp.triu(K) - U).max() == 0.0 and U.nnz == sp.triu(K).nnz
+    a.close()

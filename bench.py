@@ -317,34 +317,44 @@ def run_gpu(a):
     from cubens_b200.partition import plate_partition
 
     n = a.n
-    if world == 1:
-        m = meshgen.plate_model(n, n, SLVFLAG=2)
-        owned = None
-        n_local = m.NE_SH
-    else:
-        m, owned, n_local = plate_partition(n, n, world, rank, weak=not a.strong)
-    asm = cb.Assembler(m, layout=cb.CB_MAT_CSC, device=local)
-    if owned is not None:
-        asm.set_owned_joints(*owned)
-    # seeded perturbation so the plate is no longer flat and every local entry is non-zero
-    full_dd = meshgen.perturbation(m)
-    asm.begin_increment()
-    asm.update_forces(full_dd, want_f=False)
-    asm.end_iteration()
-    step_dd = full_dd * 1e-3
-    asm.set_dd(step_dd)
-    nnz = asm.lib.cb_csc_nnz(asm.h)
+    from cubens_b200.partition import InterfaceExchange
 
-    exchange = None
-    if world > 1:
-        from cubens_b200.partition import InterfaceExchange
+    def build(weak):
+        """the model of this rank (whole plate at N=1), resident on the GPU, perturbed; setup times in seconds"""
+        t0 = time.perf_counter()
+        if world == 1:
+            m = meshgen.plate_model(n, n, SLVFLAG=2)
+            owned = None
+            n_local = m.NE_SH
+        else:
+            m, owned, n_local = plate_partition(n, n, world, rank, weak=weak)
+        t1 = time.perf_counter()
+        asm = cb.Assembler(m, layout=cb.CB_MAT_CSC, device=local)
+        if owned is not None:
+            asm.set_owned_joints(*owned)
+        asm.sync()
+        t2 = time.perf_counter()
+        asm.begin_increment(); asm.stiff(); asm.sync()        # first cb_stiff builds the element-to-nonzero maps
+        t3 = time.perf_counter()
+        # seeded perturbation so the plate is no longer flat and every local entry is non-zero
+        full_dd = meshgen.perturbation(m)
+        asm.update_forces(full_dd, want_f=False)
+        asm.end_iteration()
+        step_dd = full_dd * 1e-3
+        asm.set_dd(step_dd)
+        # the collective lives in the library (cb_comm_init / cb_residual_allreduce); N=1 forms the same sums
         exchange = InterfaceExchange(asm, m, world, rank, dist, owned)
+        return m, owned, n_local, asm, step_dd, exchange, {"mesh_and_reference_maps": t1 - t0, "cb_create": t2 - t1,
+                                                           "plan_and_first_stiff": t3 - t2}
+
+    m, owned, n_local, asm, step_dd, exchange, setup_s = build(weak=not a.strong)
+    nnz = asm.lib.cb_csc_nnz(asm.h)
 
     def step():
         asm.stiff()                      # K_t  -> device CSC
         asm.update_forces_dev()          # updatc + f_int -> device f_temp
-        if exchange is not None and not os.environ.get("BENCH_NO_EXCHANGE"):
-            exchange.reduce()            # interface residual sums over NVLink (NCCL)
+        if not os.environ.get("BENCH_NO_EXCHANGE"):
+            exchange.reduce()            # convergence / reaction sums (+ NCCL all-reduce over NVLink at N > 1)
         asm.end_iteration()
 
     def barrier():
@@ -485,11 +495,39 @@ def run_gpu(a):
     map_bytes = asm.map_bytes
     asm_lib = asm.lib
 
+    # ---- strong scaling (north_star "Target"): per-iteration assembly time of THE fixed n x n plate split
+    # over the N ranks, same step, same timing (CUDA events, max over ranks).  At N=1 it is the run above.
+    strong = None
+    if world > 1 and not a.strong and not a.no_strong:
+        asm.close()
+        m_s, owned_s, n_loc_s, asm_s, _dd_s, ex_s, _ = build(weak=False)
+
+        def sstep():
+            asm_s.stiff(); asm_s.update_forces_dev(); ex_s.reduce(); asm_s.end_iteration()
+        for _ in range(5):
+            sstep()
+        asm_s.sync(); dist.barrier()
+        ks = max(a.steps, 50)
+        asm_s.timer_start()
+        for _ in range(ks):
+            sstep()
+        s_ms = asm_s.timer_stop_ms() / ks
+        import torch
+        t = torch.tensor([s_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        s_ms = float(t[0])
+        tot = 2 * n * n
+        strong = {"ms_per_step": s_ms, "value": tot / (s_ms * 1e-3), "unit": UNIT, "elements": tot, "steps": ks,
+                  "workload": f"ONE {n}x{n}-cell plate ({tot} elements) split over {world} ranks",
+                  "note": "divide the N=1 line's ms_per_step by N x this ms_per_step for the strong-scaling efficiency"}
+        asm_s.close()
+        asm = None
+
     # ---- the same plate with every interior joint moved (seeded): no two shells share their
     # geometry, so every shell streams its own DKT matrix from HBM (N=1, shorter run) -----------
     unstructured = None
     if world == 1 and not a.no_unstructured:
-        asm.close()
+        asm.close(); asm = None
         mu = meshgen.plate_model(n, n, SLVFLAG=2, jitter=0.2)
         au = cb.Assembler(mu, layout=cb.CB_MAT_CSC, device=local)
         ddu = meshgen.perturbation(mu)
@@ -522,7 +560,7 @@ def run_gpu(a):
     peak, peak_src = measured_peak()
     others = None
     if world == 1 and not a.no_others:
-        if unstructured is None:
+        if asm is not None:
             asm.close()
         others = other_configs(cb, meshgen, local, peak)
         if cpu_frames is not None:
@@ -577,6 +615,12 @@ def run_gpu(a):
                      "map_bytes_per_launch": map_bytes},
     }
     line["fp64"] = fp64
+    line["setup_s"] = setup_s
+    if strong is not None:
+        line["strong"] = strong
+    elif world == 1:
+        line["strong"] = {"ms_per_step": ms_step, "value": value, "unit": UNIT, "elements": total_el,
+                          "note": "N=1: the weak and the strong workload coincide"}
     if unstructured is not None:
         line["unstructured"] = unstructured
     if others is not None:
@@ -604,6 +648,7 @@ def main():
                     help="skip the second (jittered-plate) measurement")
     ap.add_argument("--no-others", action="store_true",
                     help="skip the frame-lattice / brick measurements (BASELINE configs[3], [4] shapes)")
+    ap.add_argument("--no-strong", action="store_true", help="N>1: skip the strong-scaling measurement")
     ap.add_argument("--strong", action="store_true",
                     help="N>1: split ONE n x n plate across the ranks (default: weak scaling, every "
                          "rank owns an n x n-cell strip of an (n*N) x n plate)")

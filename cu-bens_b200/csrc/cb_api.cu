@@ -28,6 +28,7 @@
 #include <cstdlib>
 
 static thread_local char g_err[512] = "";
+extern "C" int cb_comm_destroy(struct cb_handle *h);
 
 static int fail(int code, const char *fmt, ...)
 {
@@ -132,7 +133,7 @@ struct cb_handle {
     // device: nodes and vectors
     DevBuf<int32_t> jc;
     DevBuf<double> x, x_temp, x_ip;
-    DevBuf<double> dd, f_temp, f, d, d_temp, sm, qvec, sums, sums_part;
+    DevBuf<double> dd, f_temp, f_ip, f, d, d_temp, sm, qvec, sums, sums_part;
     long eq0 = 0, eq1 = 0;        // equation range of the owned joints
     long jl0 = 0, jl1 = 0, ql0 = 0, ql1 = 0;   // joints touched by local elements, their equations
     // shells
@@ -182,6 +183,9 @@ struct cb_handle {
     int max_dof = 3, mixed = 0;
     Plan plan_csc, plan_sky;
     SymPlan sym;                  // symmetric hand-off to the host solver (cb_sym.cuh)
+    void *comm = nullptr;         // ncclComm_t of an element-partitioned run (cb_comm_init)
+    int comm_rank = 0, comm_world = 1;
+    DevBuf<int32_t> trip_buf, sums_ticket;
     DevBuf<int> Ap, Ai;
     DevBuf<long> maxa;
     DevBuf<double> Ax, ss, Mx;    // Mx: full-order mass on the CSC pattern (models with bricks)
@@ -320,7 +324,7 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
     std::vector<double> hx(m->x, m->x + (size_t)NJ * 3);
     if (h->jc.upload(h->h_jc) || h->x.upload(hx) || h->x_temp.upload(hx) || h->x_ip.upload(hx))
         BAIL(CB_ERR_CUDA);
-    for (DevBuf<double> *b : {&h->dd, &h->f_temp, &h->f, &h->d, &h->d_temp, &h->sm}) {
+    for (DevBuf<double> *b : {&h->dd, &h->f_temp, &h->f_ip, &h->f, &h->d, &h->d_temp, &h->sm}) {
         if (b->alloc(sz->NEQ)) BAIL(CB_ERR_CUDA);
         dev_zero(b->p, sz->NEQ * sizeof(double));
     }
@@ -556,13 +560,15 @@ extern "C" void cb_destroy(cb_handle *h)
     if (!h) return;
     if (!g_host_only) cudaSetDevice(h->fl.device);
     if (h->sym.busy) { h->sym.worker.join(); h->sym.busy = false; }
+    if (h->comm) cb_comm_destroy(h);
+    h->trip_buf.release(); h->sums_ticket.release();
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->sym.copy_stream) { cudaStreamSynchronize(h->sym.copy_stream); cudaStreamDestroy(h->sym.copy_stream); }
     if (h->sym.ev_pack) cudaEventDestroy(h->sym.ev_pack);
     for (cudaEvent_t e : h->sym.ev_chunk) if (e) cudaEventDestroy(e);
     h->sym.d_ulen0.release(); h->sym.d_slen.release(); h->sym.d_nfree.release(); h->sym.d_colh.release();
     h->sym.d_ubase.release(); h->sym.d_base.release(); h->sym.packed.release();
-    for (DevBuf<double> *b : {&h->x, &h->x_temp, &h->x_ip, &h->dd, &h->f_temp, &h->f, &h->d,
+    for (DevBuf<double> *b : {&h->x, &h->x_temp, &h->x_ip, &h->dd, &h->f_temp, &h->f_ip, &h->f, &h->d,
                               &h->d_temp, &h->sm, &h->qvec, &h->sums, &h->sums_part, &h->sh_const, &h->sh_keb, &h->sh_kebc, &h->sh_der, &h->sh_Nm, &h->sh_fg,
                               &h->sh_dens, &h->tr_const, &h->tr_fg, &h->tr_dens, &h->fr_const,
                               &h->fr_offset, &h->fr_efFE_ref, &h->fr_fg, &h->fr_dens, &h->br_const, &h->br_prep,
@@ -1417,6 +1423,7 @@ extern "C" int cb_begin_increment(cb_handle *h)
     int bad = 0;
     bad |= d2d(h->d_temp.p, h->d.p, h->sz.NEQ, s);
     bad |= d2d(h->f_temp.p, h->f.p, h->sz.NEQ, s);
+    bad |= d2d(h->f_ip.p, h->f.p, h->sz.NEQ, s);
     bad |= d2d(h->x_temp.p, h->x.p, (size_t)h->sz.NJ * 3, s);
     for (int g = 1; g <= 2; ++g) {
         bad |= d2d(h->sh_frame[g].p, h->sh_frame[0].p, (size_t)SH * CB_SH_FRAME, s);
@@ -1553,42 +1560,89 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
     return CB_OK;
 }
 
-// two-stage fixed-order reduction of the three convergence sums (misc.c:187-250)
-__global__ void __launch_bounds__(256)
-k_resid_sums1(long e0, long e1, double lpf, const double *__restrict__ q, const double *__restrict__ f,
-              const double *__restrict__ dd, double *__restrict__ part)
+// Convergence sums of test() (misc.c:187-250) over the owned equations - unbfi = |qtot - f_temp|^2, deltad =
+// |dd|^2, inteneri = dd.(qtot - f_ip), totald = |d_temp|^2, unbfp = |qtot - fp|^2 with qtot = lpf*q - and the
+// reaction resultants: the element forces that arrive at FIXED degrees of freedom
+// of the owned joints, which the reference drops at mcode == 0 (shell.c:2393-2396, frame.c:1273-1309,
+// truss.c:366-376), summed per direction (Fx Fy Fz Mx My Mz).  One launch: every block reduces its share
+// in a fixed order, the last block to finish (a ticket counter, the only atomic and it carries no data)
+// reduces the per-block partials in a fixed order - bit-reproducible run to run.
+__device__ __forceinline__ void joint_force_sum(const CbDev &d, long n, const int32_t *cstart, const CbCorner *corners,
+                                                double *acc /*[7]*/)
 {
-    __shared__ double sh[3][256];
-    double a0 = 0, a1 = 0, a2 = 0;
-    for (long i = e0 + blockIdx.x * 256L + threadIdx.x; i < e1; i += 256L * gridDim.x) {
-        const double r = lpf * q[i] - f[i], di = dd[i];
-        a0 += r * r; a1 += di * di; a2 += di * r;
+    const int c0 = cstart[n], c1 = cstart[n + 1];
+    const int fr_end = (d.ANAFLAG == 3 && d.fr_trip) ? d.fr_trip[0] : 0x7fffffff;
+    const int sh_end = (d.ANAFLAG == 3 && d.sh_trip) ? d.sh_trip[0] : 0x7fffffff;
+    for (int c = c0; c < c1; ++c) {
+        const CbCorner cr = corners[c];
+        if (cr.type == CB_T_SHELL) {
+            if ((d.sh_gid && sh_end != 0x7fffffff ? d.sh_gid[cr.e] : cr.e) >= sh_end) continue;
+            const double *p = CB_FG(d.sh_fg, cr.b, cr.e, d.NE_SH);
+            for (int r = 0; r < 6; ++r) acc[r] += p[r];
+        } else if (cr.type == CB_T_FRAME) {
+            if ((d.fr_gid && fr_end != 0x7fffffff ? d.fr_gid[cr.e] : cr.e) >= fr_end) continue;
+            const double *p = d.fr_fg + (long)cr.e * 14 + cr.b * 7;
+            for (int r = 0; r < 7; ++r) acc[r] += p[r];
+        } else if (cr.type == CB_T_TRUSS) {
+            const double *p = d.tr_fg + (long)cr.e * 6 + cr.b * 3;
+            for (int r = 0; r < 3; ++r) acc[r] += p[r];
+        }
     }
-    sh[0][threadIdx.x] = a0; sh[1][threadIdx.x] = a1; sh[2][threadIdx.x] = a2;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s)
-            for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
-        __syncthreads();
-    }
-    if (threadIdx.x < 3) part[blockIdx.x * 3 + threadIdx.x] = sh[threadIdx.x][0];
 }
-// second stage: 256 threads, fixed strided order + fixed tree (bit-reproducible run to run); the
-// serial version (3 threads x 592 dependent L2 round trips) cost more than the first stage
+
+#define CB_NSUMS 11
 __global__ void __launch_bounds__(256)
-k_resid_sums2(int nblk, const double *__restrict__ part, double *__restrict__ out)
+k_resid_sums(CbDev d, long e0, long e1, double lpf, const double *__restrict__ q, const double *__restrict__ f,
+             const double *__restrict__ f_ip, const double *__restrict__ fp, const double *__restrict__ d_temp,
+             const double *__restrict__ dd, long jo0, long jo1, const int32_t *__restrict__ cstart,
+             const CbCorner *__restrict__ corners, double *__restrict__ part, double *__restrict__ out,
+             int32_t *__restrict__ ticket)
 {
-    __shared__ double sh[3][256];
-    double a0 = 0, a1 = 0, a2 = 0;
-    for (int b = threadIdx.x; b < nblk; b += 256) { a0 += part[b * 3]; a1 += part[b * 3 + 1]; a2 += part[b * 3 + 2]; }
-    sh[0][threadIdx.x] = a0; sh[1][threadIdx.x] = a1; sh[2][threadIdx.x] = a2;
+    __shared__ double sh[CB_NSUMS][256];
+    __shared__ bool last;
+    double a[CB_NSUMS];
+    for (int k = 0; k < CB_NSUMS; ++k) a[k] = 0;
+    for (long i = e0 + blockIdx.x * 256L + threadIdx.x; i < e1; i += 256L * gridDim.x) {
+        // misc.c:201-237 with qtot = lpf * q: unbfi, deltad, inteneri (f_ip: the residual BEFORE this update),
+        // totald, unbfp (fp: the committed internal force)
+        const double qt = lpf * q[i], r = qt - f[i], di = dd[i], dt = d_temp[i], rp = qt - fp[i];
+        a[0] += r * r; a[1] += di * di; a[2] += di * (qt - f_ip[i]); a[3] += dt * dt; a[4] += rp * rp;
+    }
+    for (long n = jo0 + blockIdx.x * 256L + threadIdx.x; n < jo1; n += 256L * gridDim.x) {
+        const int4 qa = reinterpret_cast<const int4 *>(d.jc)[n * 2], qb = reinterpret_cast<const int4 *>(d.jc)[n * 2 + 1];
+        if (qa.x && qa.y && qa.z && qa.w && qb.x && qb.y) continue;        // nothing fixed at this joint
+        if (cstart[n + 1] == cstart[n]) continue;
+        double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+        joint_force_sum(d, n, cstart, corners, acc);
+        const int qq[6] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y};
+        for (int r = 0; r < 6; ++r) if (!qq[r]) a[5 + r] += acc[r];
+    }
+    for (int k = 0; k < CB_NSUMS; ++k) sh[k][threadIdx.x] = a[k];
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
         if (threadIdx.x < s)
-            for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+            for (int k = 0; k < CB_NSUMS; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x < 3) out[threadIdx.x] = sh[threadIdx.x][0];
+    if (threadIdx.x < CB_NSUMS) part[blockIdx.x * CB_NSUMS + threadIdx.x] = sh[threadIdx.x][0];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int k = 0; k < CB_NSUMS; ++k) a[k] = 0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += 256)
+        for (int k = 0; k < CB_NSUMS; ++k) a[k] += __ldcg(part + b * CB_NSUMS + k);
+    for (int k = 0; k < CB_NSUMS; ++k) sh[k][threadIdx.x] = a[k];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+            for (int k = 0; k < CB_NSUMS; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x < CB_NSUMS) out[threadIdx.x] = sh[threadIdx.x][0];
+    if (threadIdx.x == 0) *ticket = 0;
 }
 
 
@@ -1668,6 +1722,9 @@ extern "C" int cb_update_forces_begin(cb_handle *h, const double *dd_dev, double
     cudaStream_t s = h->stream;
     // after end_iteration/begin_increment *_i aliases *_ip: the next iterate goes to the other buffer
     if (h->i_is_ip) h->i_is_ip = false;
+    // f_ip <- f_temp (main.c:1941-1943, read by test()'s energy norm): the gather rewrites every owned entry
+    // of f_temp, so the two buffers simply trade places
+    std::swap(h->f_temp.p, h->f_ip.p);
     CbForceArgs a = force_args(h);
     if (dd_dev && dd_dev != h->dd.p) { if (d2d(h->dd.p, dd_dev, h->sz.NEQ, s)) return fail(CB_ERR_CUDA, "dd copy"); }
     a.dlpf = dlpf; a.itecnt = itecnt;
@@ -2040,8 +2097,12 @@ extern "C" int cb_set_q(cb_handle *h, const double *q)
 {
     if (!h || !q) return fail(CB_ERR_ARG, "null argument");
     cudaSetDevice(h->fl.device);
-    if (!h->qvec.p && (h->qvec.alloc(h->sz.NEQ) || h->sums.alloc(4) || h->sums_part.alloc(CB_SUM_BLOCKS * 3)))
-        return CB_ERR_CUDA;
+    if (!h->qvec.p) {
+        if (h->qvec.alloc(h->sz.NEQ) || h->sums.alloc(CB_NSUMS + 1) || h->sums_part.alloc(CB_SUM_BLOCKS * CB_NSUMS) ||
+            h->sums_ticket.alloc(1))
+            return CB_ERR_CUDA;
+        dev_zero(h->sums_ticket.p, sizeof(int32_t));
+    }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaMemcpy(h->qvec.p, q, h->sz.NEQ * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaDeviceSynchronize());
@@ -2059,20 +2120,58 @@ extern "C" int cb_residual_sums(cb_handle *h, double lpf)
 {
     if (!h || !h->qvec.p) return fail(CB_ERR_ARG, "cb_set_q has not been called");
     cudaSetDevice(h->fl.device);
-    k_resid_sums1<<<CB_SUM_BLOCKS, 256, 0, h->stream>>>(h->eq0, h->eq1, lpf, h->qvec.p, h->f_temp.p,
-                                                         h->dd.p, h->sums_part.p);
-    k_resid_sums2<<<1, 256, 0, h->stream>>>(CB_SUM_BLOCKS, h->sums_part.p, h->sums.p);
-    h->launches += 2;
+    int rc = build_plan(h); if (rc) return rc;
+    const CbForceArgs a = force_args(h);
+    k_resid_sums<<<CB_SUM_BLOCKS, 256, 0, h->stream>>>(a.d, h->eq0, h->eq1, lpf, h->qvec.p, h->f_temp.p, h->f_ip.p, h->f.p,
+                                                        h->d_temp.p, h->dd.p, a.jo0, a.jo1,
+                                                        h->node_cstart.p, h->corners.p, h->sums_part.p, h->sums.p,
+                                                        h->sums_ticket.p);
+    h->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return CB_OK;
 }
 extern "C" double *cb_dev_sums(cb_handle *h) { return h ? h->sums.p : nullptr; }
+extern "C" int cb_residual_allreduce(cb_handle *h);
+// test() of the reference (misc.c:187-250) from the device-resident vectors: forms the sums, adds them over
+// the ranks, applies the three tolerance checks.  Returns 0 with *convchk = 0 / +10 / +100 / +1000 exactly
+// as test() does, or 1 where test() prints its "... are zero" errors.
+extern "C" int cb_convergence_test(cb_handle *h, double lpf, double intener1, double toldisp, double tolforc,
+                                   double tolener, int *convchk, double *sums5_out)
+{
+    if (!h || !convchk) return fail(CB_ERR_ARG, "null argument");
+    *convchk = 0;
+    if (cb_residual_sums(h, lpf) || cb_residual_allreduce(h)) return 1;
+    double s[5];
+    if (cb_get_sums(h, s)) return 1;
+    if (sums5_out) memcpy(sums5_out, s, sizeof s);
+    if (toldisp < 1) {
+        if (s[3] == 0) return fail(1, "Displacements are zero");
+        if (sqrt(s[1]) / sqrt(s[3]) > toldisp) *convchk += 10;
+    }
+    if (tolforc < 1) {
+        if (s[4] == 0) return fail(1, "Force increment is zero");
+        if (sqrt(s[0]) / sqrt(s[4]) > tolforc) *convchk += 100;
+    }
+    if (tolener < 1) {
+        if (intener1 == 0) return fail(1, "Energy increment is zero");
+        if (fabs(s[2] / intener1) > tolener) *convchk += 1000;
+    }
+    return 0;
+}
+extern "C" int cb_get_reaction_sums(cb_handle *h, double *r6)
+{
+    if (!h || !r6 || !h->sums.p) return fail(CB_ERR_ARG, "null argument");
+    cudaSetDevice(h->fl.device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(r6, h->sums.p + 5, 6 * sizeof(double), cudaMemcpyDeviceToHost));
+    return CB_OK;
+}
 extern "C" int cb_get_sums(cb_handle *h, double *s3)
 {
     if (!h || !s3 || !h->sums.p) return fail(CB_ERR_ARG, "null argument");
     cudaSetDevice(h->fl.device);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    CUDA_TRY(cudaMemcpy(s3, h->sums.p, 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(s3, h->sums.p, 5 * sizeof(double), cudaMemcpyDeviceToHost));
     return CB_OK;
 }
 
@@ -2347,3 +2446,4 @@ extern "C" int cb_sync(cb_handle *h)
 extern "C" void *cb_stream(cb_handle *h) { return h ? (void *)h->stream : nullptr; }
 
 #include "cb_sym_impl.cuh"
+#include "cb_comm_impl.cuh"

@@ -40,7 +40,8 @@ EXPORTS = [
     "cb_set_element_ids", "cb_update_forces_begin", "cb_update_forces_end", "cb_measure_fp64_tflops",
     "cb_plan_selfcheck", "cb_csc_upper_nnz", "cb_csc_upper_pattern", "cb_get_csc_upper_values",
     "cb_csc_values_begin", "cb_csc_values_end", "cb_get_csc_values_mirrored", "cb_sym_selftest",
-    "cb_local_equations", "cb_csc_values_d2h_bytes",
+    "cb_local_equations", "cb_csc_values_d2h_bytes", "cb_get_reaction_sums", "cb_comm_unique_id", "cb_comm_init",
+    "cb_comm_destroy", "cb_residual_allreduce", "cb_trip_allreduce", "cb_convergence_test",
 ]
 
 
@@ -389,9 +390,39 @@ class Assembler:
     def residual_sums(self, lpf=1.0, fetch=False):
         self._check(self.lib.cb_residual_sums(self.h, C.c_double(lpf)))
         if fetch:
-            s = np.zeros(3)
+            s = np.zeros(5)
             self._check(self.lib.cb_get_sums(self.h, _p(s)))
             return s
+
+    def convergence_test(self, lpf, intener1, toldisp, tolforc, tolener):
+        """test() of the reference (misc.c:187-250) on the device-resident vectors; returns (err, convchk, sums5)"""
+        conv = C.c_int(0); s = np.zeros(5)
+        err = self.lib.cb_convergence_test(self.h, C.c_double(lpf), C.c_double(intener1), C.c_double(toldisp),
+                                           C.c_double(tolforc), C.c_double(tolener), C.byref(conv), _p(s))
+        return err, conv.value, s
+
+    def reaction_sums(self):
+        r = np.zeros(6)
+        self._check(self.lib.cb_get_reaction_sums(self.h, _p(r)))
+        return r
+
+    # ---- the collective inside the library (NCCL bound at run time) ---------------------------
+    def comm_unique_id(self):
+        buf = (C.c_char * 128)()
+        self._check(self.lib.cb_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, uid, rank, world):
+        assert len(uid) == 128
+        self._check(self.lib.cb_comm_init(self.h, C.c_char_p(uid), C.c_int(rank), C.c_int(world)))
+
+    def residual_allreduce(self):
+        self._check(self.lib.cb_residual_allreduce(self.h))
+
+    def trip_allreduce(self, first_fr, first_sh):
+        a = C.c_int(first_fr); b = C.c_int(first_sh)
+        self._check(self.lib.cb_trip_allreduce(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def set_dd(self, dd):
         dd = np.ascontiguousarray(dd, dtype=np.float64)

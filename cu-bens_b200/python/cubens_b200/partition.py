@@ -155,19 +155,45 @@ class _DevVec:
 
 
 class InterfaceExchange:
-    """Per-iteration NCCL step: the three convergence sums of test() (misc.c:187-250) are formed
-    over the owned equations by the library (cb_residual_sums, one fused pass, fixed order) and
-    all-reduced over the ranks; 24 bytes cross NVLink per iteration."""
+    """Per-iteration NCCL step: the three convergence sums of test() (misc.c:187-250) and the six reaction
+    resultants are formed over the owned equations / joints by the library (cb_residual_sums, one fused
+    pass, fixed order) and all-reduced over the ranks BY THE LIBRARY (cb_residual_allreduce: ncclAllReduce
+    on the handle's stream, include/cubens_b200.h); 72 bytes cross NVLink per iteration.  torch.distributed
+    only carries the 128-byte ncclUniqueId to the ranks once."""
 
     def __init__(self, asm, m, world, rank, dist, owned=None):
         import torch
-        self.torch, self.dist, self.asm = torch, dist, asm
+        self.asm = asm
         asm.set_q(m.q)
-        self.sums = torch.as_tensor(_DevVec(asm.lib.cb_dev_sums(asm.h), 3), device="cuda")
-        self.stream = torch.cuda.ExternalStream(asm.lib.cb_stream(asm.h))
+        if world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(asm.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, src=0)
+            asm.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
 
     def reduce(self, lpf=1.0):
         self.asm.residual_sums(lpf)
-        with self.torch.cuda.stream(self.stream):
-            self.dist.all_reduce(self.sums)
-        return self.sums
+        self.asm.residual_allreduce()
+
+
+def write_submodel(path, m, owned, q, dd, lpf, layout=1, device=0):
+    """binary image of a (sub-)model for the C host cu-bens_b200/host/cb_multi_gpu_demo.c: cb_sizes, cb_flags,
+    owned joint range, every cb_model array as (count, data) in the struct's order, q, dd, lpf"""
+    import struct
+    from . import _MODEL_FIELDS
+    with open(path, "wb") as f:
+        f.write(struct.pack("7l", m.NJ, m.NE_TR, m.NE_FR, m.NE_SH, m.NE_SBR, m.NE_FBR, m.NEQ))
+        f.write(struct.pack("5i", m.ANAFLAG, m.ALGFLAG, m.SLVFLAG, layout, device))
+        f.write(struct.pack("2l", *(owned if owned is not None else (0, m.NJ))))
+        for n in _MODEL_FIELDS:
+            a = getattr(m, "yld" if n == "yield" else n, None)
+            if a is None or np.size(a) == 0:
+                f.write(struct.pack("l", 0)); continue
+            dt = np.int32 if n in ("osflag", "mendrel") else (np.int64 if n in ("minc", "jcode", "mcode", "maxa") else np.float64)
+            a = np.ascontiguousarray(a, dtype=dt)
+            f.write(struct.pack("l", a.size)); f.write(a.tobytes())
+        for v in (q, dd):
+            v = np.ascontiguousarray(v, dtype=np.float64)
+            f.write(struct.pack("l", v.size)); f.write(v.tobytes())
+        f.write(struct.pack("d", float(lpf)))

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 2
+#define CB_ABI_VERSION 3
 
 /* status codes (the reference uses 0 = ok / 1 = error, solve.c:558-562, frame.c:1201) */
 enum {
@@ -220,15 +220,44 @@ const int *cb_dev_Ap(cb_handle *h);
 const int *cb_dev_Ai(cb_handle *h);       /* built lazily on first use                     */
 
 /* ---- convergence sums on the device ("next" row 2: the NEQ-vector work between the kernels) --
- * cb_set_q stages the reference load vector q [NEQ]; cb_residual_sums leaves, in the device
- * buffer cb_dev_sums() (3 doubles), the sums test() needs (misc.c:201, 217-220, 235-237) over
- * the equations of the owned joints:  |lpf*q - f_temp|^2,  |dd|^2,  dd.(lpf*q - f_temp).
- * Fixed-order two-stage reduction (bit-reproducible).  With several GPUs the launcher all-reduces
- * the 3 doubles (NCCL) - the only per-iteration collective.                */
+ * cb_set_q stages the reference load vector q [NEQ]; cb_residual_sums leaves, in the device buffer
+ * cb_dev_sums() (11 doubles), what test() needs (misc.c:187-250) over the equations of the owned joints, with
+ * qtot = lpf*q:  [0] unbfi = |qtot - f_temp|^2   [1] deltad = |dd|^2   [2] inteneri = dd.(qtot - f_ip)
+ *                [3] totald = |d_temp|^2         [4] unbfp = |qtot - fp|^2   (f_ip: f_temp before the last
+ * cb_update_forces, main.c:1941-1943; fp: the committed f), and [5..10] the reaction resultants below.
+ * Fixed-order reduction in one launch (bit-reproducible).  With several GPUs cb_residual_allreduce sums
+ * them over the ranks (NCCL, below) - the only per-iteration collective.
+ * cb_get_sums copies the first five to the host.  cb_convergence_test is test() itself on those sums
+ * (same return value and *convchk codes; all-reduce included): dd and f_temp need not cross PCIe for it. */
 int     cb_set_q(cb_handle *h, const double *q);
 int     cb_residual_sums(cb_handle *h, double lpf);
 double *cb_dev_sums(cb_handle *h);
-int     cb_get_sums(cb_handle *h, double *sums3);
+int     cb_get_sums(cb_handle *h, double *sums5);
+int     cb_convergence_test(cb_handle *h, double lpf, double intener1, double toldisp, double tolforc,
+                            double tolener, int *convchk, double *sums5_out /* may be NULL */);
+/* cb_residual_sums also leaves, in cb_dev_sums()[5..10], the REACTION resultants of the owned joints: the
+ * element forces arriving at fixed degrees of freedom, which the reference drops at mcode == 0
+ * (shell.c:2393-2396, frame.c:1273-1309, truss.c:366-376), summed per direction Fx Fy Fz Mx My Mz          */
+int     cb_get_reaction_sums(cb_handle *h, double *r6);
+
+/* ---- the collective of an element-partitioned run, inside the library ----------------
+ * One process (or host thread) per GPU creates its handle from its sub-model and joins an NCCL communicator:
+ *   cb_comm_unique_id   rank 0 obtains the 128-byte ncclUniqueId and hands it to the others by whatever means
+ *                       the host has (file, pipe, MPI_Bcast, ...)
+ *   cb_comm_init        collective: every rank calls it with the same id; NCCL is bound at run time
+ *                       (libnccl.so.2; a process that already holds one reuses it) - CB_ERR_UNSUPPORTED if absent
+ *   cb_residual_allreduce   ncclAllReduce(sum) of the eleven doubles of cb_dev_sums() in place, on the handle's
+ *                       stream, no host synchronisation: call it after cb_residual_sums, read with cb_get_sums /
+ *                       cb_get_reaction_sums.  The matrix columns and f_int of the owned joints need no exchange
+ *                       (halo elements); these sums are the per-iteration traffic over NVLink
+ *   cb_trip_allreduce   ANAFLAG 3: minimum over the ranks of the tripping element indices, between
+ *                       cb_update_forces_begin and cb_update_forces_end
+ * Without a communicator (one rank) the two all-reduce calls return at once.                              */
+int  cb_comm_unique_id(void *id128);
+int  cb_comm_init(cb_handle *h, const void *id128, int rank, int world);
+int  cb_comm_destroy(cb_handle *h);
+int  cb_residual_allreduce(cb_handle *h);
+int  cb_trip_allreduce(cb_handle *h, int *first_fr, int *first_sh);
 
 /* ---- state transfer for output()/checkPoint()/restartStep() (misc.c:345,494,605) ------ */
 enum {

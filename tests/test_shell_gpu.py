@@ -82,20 +82,48 @@ def test_repeatable(gpu):
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
 
 
-def test_residual_sums(gpu):
-    """fused convergence sums (misc.c:187-250) on the device vs numpy"""
+def test_convergence_test_matches_reference_test(gpu, ref):
+    """test() of the reference (misc.c:187-250) evaluated from the device-resident vectors: the five sums, the
+    convergence code, and the reaction resultants (forces the reference drops at fixed DOFs)"""
+    import ctypes as C
     m = meshgen.plate_model(20, 15, z_bump=0.02)
     asm = cb.Assembler(m, layout=cb.CB_MAT_CSC)
-    asm.begin_increment()
-    dd = meshgen.perturbation(m)
-    f, *_ = asm.update_forces(dd)
+    s = ref.RefState(m)
+    l = ref.set_model(m)
     asm.set_q(m.q)
-    s = asm.residual_sums(0.7, fetch=True)
-    r = 0.7 * m.q - f
-    want = np.array([r @ r, dd @ dd, dd @ r])
-    assert np.allclose(s, want, rtol=1e-12, atol=0)
-    s2 = asm.residual_sums(0.7, fetch=True)
-    assert np.array_equal(s, s2)
+    rng = np.random.default_rng(11)
+    lpf = 0.7
+    qtot = lpf * m.q
+    s.begin_increment(); asm.begin_increment()
+    intener1 = None
+    for it in range(3):
+        dd = rng.uniform(-1e-4, 1e-4, size=m.NEQ) * (0.1 ** it)
+        f_ip = s.f_temp.copy(); fp = s.f.copy()
+        ref.update_forces(m, s, dd, itecnt=it)
+        f, *_ = asm.update_forces(dd, itecnt=it)
+        want = np.array([(qtot - s.f_temp) @ (qtot - s.f_temp), dd @ dd, dd @ (qtot - f_ip), s.d_temp @ s.d_temp,
+                         (qtot - fp) @ (qtot - fp)])
+        if it == 0:
+            intener1 = float(dd @ (qtot - fp))
+        for tols in ((1e-3, 1e-3, 1e-3), (1e-1, 1e-9, 0.5), (2.0, 1e-12, 1e-12)):
+            ref.set_model(m)
+            conv = C.c_int(0); ie = C.c_double(intener1)
+            err = l.test(ref.P(s.d_temp), ref.P(dd), ref.P(s.f_temp), ref.P(fp), ref.P(qtot), ref.P(f_ip), C.byref(ie),
+                         C.byref(conv), C.byref(C.c_double(tols[0])), C.byref(C.c_double(tols[1])),
+                         C.byref(C.c_double(tols[2])))
+            gerr, gconv, sums = asm.convergence_test(lpf, intener1, *tols)
+            assert (gerr, gconv) == (err, conv.value)
+            assert np.allclose(sums, want, rtol=1e-12, atol=0)
+        # deterministic
+        assert np.array_equal(asm.residual_sums(lpf, fetch=True), asm.residual_sums(lpf, fetch=True))
+        # reactions: every element's joint forces are self-equilibrated, so the translational resultants at
+        # the fixed DOFs balance the internal forces at the free ones
+        R = asm.reaction_sums()
+        jc = np.asarray(m.jcode).reshape(-1, 7)
+        for k in range(3):
+            free = jc[:, k][jc[:, k] > 0] - 1
+            assert abs(R[k] + f[free].sum()) <= 1e-9 * np.abs(f).max()
+        s.end_iteration(); asm.end_iteration()
     asm.close()
 
 

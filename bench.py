@@ -291,6 +291,10 @@ def run_gpu(a):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries ONE JSON line: anything a library prints on the way (NCCL's version banner ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     dist = None
     if world > 1:
         import torch
@@ -423,7 +427,8 @@ def run_gpu(a):
     # how much of the matrix crosses as full columns (no host work) and how much as packed upper triangles
     # (half the bytes, rebuilt by host threads): with >= 12 threads per rank every third chunk goes in full,
     # with fewer the host cannot keep up with the copy engine and everything does (measured, profiles/README)
-    os.environ.setdefault("CB_SYM_FULL_EVERY", "3" if threads >= 12 else "1")
+    # and with several ranks sharing the host its memory bandwidth is the bottleneck either way)
+    os.environ.setdefault("CB_SYM_FULL_EVERY", "3" if (threads >= 12 and world == 1) else "1")
     nnz_u = lib.cb_csc_upper_nnz(asm.h)
     neq_loc = lib.cb_local_equations(asm.h)
     hdd = asm.pinned(m.NEQ); hdd[:] = step_dd
@@ -629,7 +634,10 @@ def run_gpu(a):
         line["e2e"] = e2e
     if cpu is not None:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -149,10 +149,13 @@ def test_upload_geometry_rebuilds_derived_data(gpu):
     b.close()
 
 
-def test_symmetric_handoff_rebuilds_full_matrix(gpu):
+@pytest.mark.parametrize("full_every", ["0", "1", "3", "5"])
+def test_symmetric_handoff_rebuilds_full_matrix(gpu, full_every, monkeypatch):
     """cb_csc_values_begin / _end: the packed upper triangle crosses PCIe, host threads rebuild the full
     columns.  The upper part is bit-identical to cb_get_csc_values, the lower part is its exact mirror
-    (the device's own lower entries agree with it to rounding: K_t is symmetric)."""
+    (the device's own lower entries agree with it to rounding: K_t is symmetric); chunks sent in full
+    (CB_SYM_FULL_EVERY) keep the device's own lower entries."""
+    monkeypatch.setenv("CB_SYM_FULL_EVERY", full_every)
     m = meshgen.plate_model(40, 27, z_bump=0.02, SLVFLAG=2)
     a = cb.Assembler(m, layout=cb.CB_MAT_CSC)
     a.begin_increment(); a.update_forces(meshgen.perturbation(m, scale=1e-3)); a.end_iteration(); a.stiff()
@@ -165,7 +168,11 @@ def test_symmetric_handoff_rebuilds_full_matrix(gpu):
     # exact symmetry of the rebuilt matrix
     import scipy.sparse as sp
     K = sp.csc_matrix((full, Ai, Ap), shape=(m.NEQ, m.NEQ))
-    assert abs(K - K.T).max() == 0.0
+    if full_every == "0":
+        assert abs(K - K.T).max() == 0.0
+    elif full_every == "1":
+        assert np.array_equal(full, Ax)
+    assert abs(K - K.T).max() <= 1e-13 * np.abs(Ax).max()
     # the packed stream is an upper-triangular CSC of its own
     Apu, Aiu, Axu = a.csc_upper()
     U = sp.csc_matrix((Axu, Aiu, Apu), shape=(m.NEQ, m.NEQ))

@@ -167,10 +167,14 @@ def cpu_sample_frames(steps, warmup, cores=None):
                       f"skyline), {steps} iterations per core, unmodified stiff_fr+updatc+forces_fr at gcc -O2"}
 
 
-def cpu_sample(steps, warmup, cell, cores=None):
+def cpu_sample(steps, warmup, cell, cores=None, o0=False):
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context("fork")
+    if o0:
+        os.environ["CUBENS_REF_O0"] = "1"        # read by oracle.refbind in the forked workers
+    else:
+        os.environ.pop("CUBENS_REF_O0", None)
     with ctx.Pool(cores) as pool:
         t0 = time.perf_counter()
         res = pool.map(_cpu_worker, [(w, steps, warmup, cell) for w in range(cores)])
@@ -185,6 +189,25 @@ def cpu_sample(steps, warmup, cell, cores=None):
                       f"assemblies per core, unmodified stiff_sh+updatc+forces_sh at gcc -O2",
             "ms_per_step": 1e3 * total / steps, "wall_s": wall,
             "per_core_elements_per_s": ne * steps / total}
+
+
+def cpu_details(cell):
+    """SURVEY 8(d) detail next to the headline CPU figure: the serial reference on ONE core (what the program
+    as shipped does), and all cores at the optimisation level it ships with (Makefile:6,21: no -O)"""
+    out = {}
+    try:
+        r1 = cpu_sample(6, 1, cell, cores=1)
+        out["one_core_O2"] = {"value": r1["value"], "unit": UNIT, "cores": 1}
+        if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libcubens_ref_O0.so")):
+            r0 = cpu_sample(3, 1, cell, o0=True)
+            out["all_cores_O0_as_shipped"] = {"value": r0["value"], "unit": UNIT, "cores": r0["cores"]}
+            r01 = cpu_sample(2, 1, cell, cores=1, o0=True)
+            out["one_core_O0_as_shipped"] = {"value": r01["value"], "unit": UNIT, "cores": 1}
+    except Exception as e:                          # extras, never fatal
+        out["unavailable"] = repr(e)
+    finally:
+        os.environ.pop("CUBENS_REF_O0", None)
+    return out
 
 
 def run_reference(a):
@@ -240,6 +263,12 @@ def other_configs(cb, meshgen, device, peak):
     for _ in range(K):
         a.stiff(); a.update_forces_dev(); a.end_iteration()
     step_ms = a.timer_stop_ms() / K
+    # the Newmark loop of configs[3] (main.c:3590-3619) refreshes the lumped mass with the stiffness in every
+    # iteration: the transient step is K_t + mass + f_int
+    a.sync(); a.timer_start()
+    for _ in range(K):
+        a.stiff(); a._check(a.lib.cb_mass(a.h)); a.update_forces_dev(); a.end_iteration()
+    tstep_ms = a.timer_stop_ms() / K
     for _ in range(5):
         a.stiff(); ks.append(a.last_stiff_ms); a.update_forces_dev(); fs.append(a.last_forces_ms)
         a.end_iteration()
@@ -252,6 +281,8 @@ def other_configs(cb, meshgen, device, peak):
         "workload": f"119^3-joint cubic frame lattice, {m.NE_FR} frames, NEQ {m.NEQ}, nnz "
                     f"{a.lib.cb_csc_nnz(a.h)}, ANAFLAG 2 (BASELINE.json configs[3] shape)",
         "value": m.NE_FR / (step_ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms, "steps": K,
+        "transient_step": {"ms_per_step": tstep_ms, "value": m.NE_FR / (tstep_ms * 1e-3),
+                           "note": "K_t + lumped-mass refresh + f_int, what one Newmark iteration assembles"},
         "split_ms": {"stiff_total": k_ms, "update_forces": f_ms, "mass_refresh": mass_ms},
         "roofline_frac": {"K_t": ALG_BYTES_FR_KT * m.NE_FR / (k_ms * 1e-3) / 1e9 / peak,
                           "f_int": ALG_BYTES_FR_FINT * m.NE_FR / (f_ms * 1e-3) / 1e9 / peak,
@@ -310,6 +341,7 @@ def run_gpu(a):
         from oracle import refbind as R
         if R.available():
             cpu = cpu_sample(a.cpu_steps, 1, 1.0 / a.n)
+            cpu["detail"] = cpu_details(1.0 / a.n)
             if not a.no_others:
                 try:
                     cpu_frames = cpu_sample_frames(max(4, a.cpu_steps // 4), 1)
@@ -633,7 +665,7 @@ def run_gpu(a):
     if e2e is not None:
         line["e2e"] = e2e
     if cpu is not None:
-        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "detail")}
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)

@@ -17,7 +17,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF_SO = os.path.join(HERE, "_ref", "libcubens_ref.so")
+# CUBENS_REF_O0=1 (set before the first call): the build at the reference's shipped optimisation level (no -O)
+REF_SO = os.path.join(HERE, "_ref", "libcubens_ref_O0.so" if os.environ.get("CUBENS_REF_O0") else "libcubens_ref.so")
 
 _lib = None
 

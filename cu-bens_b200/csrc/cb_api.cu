@@ -14,6 +14,7 @@
 //                         model.c:944-960, which is what makes the block pattern valid)
 #include "../../include/cubens_b200.h"
 #include "cb_internal.h"
+#include "cb_plan_pack.h"
 
 #include <algorithm>
 #include <cmath>
@@ -183,6 +184,10 @@ struct cb_handle {
     int max_dof = 3, mixed = 0;
     Plan plan_csc, plan_sky;
     SymPlan sym;                  // symmetric hand-off to the host solver (cb_sym.cuh)
+    // device-built plan (cb_plan_device.cuh): what stays resident for cb_dev_Ai, and how long the build took
+    DevBuf<int32_t> d_adj, d_jpair, d_nfree, d_first, d_colh; DevBuf<int64_t> d_base;
+    bool plan_on_device = false;
+    double plan_seconds = 0;
     void *comm = nullptr;         // ncclComm_t of an element-partitioned run (cb_comm_init)
     int comm_rank = 0, comm_world = 1;
     DevBuf<int32_t> trip_buf, sums_ticket;
@@ -562,6 +567,7 @@ extern "C" void cb_destroy(cb_handle *h)
     if (h->sym.busy) { h->sym.worker.join(); h->sym.busy = false; }
     if (h->comm) cb_comm_destroy(h);
     h->trip_buf.release(); h->sums_ticket.release();
+    h->d_adj.release(); h->d_jpair.release(); h->d_nfree.release(); h->d_first.release(); h->d_colh.release(); h->d_base.release();
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->sym.copy_stream) { cudaStreamSynchronize(h->sym.copy_stream); cudaStreamDestroy(h->sym.copy_stream); }
     if (h->sym.ev_pack) cudaEventDestroy(h->sym.ev_pack);
@@ -619,10 +625,24 @@ extern "C" int cb_set_owned_joints(cb_handle *h, long j0, long j1)
 // the sorted element-to-nonzero maps
 // ------------------------------------------------------------------------------------------
 static void host_pattern(cb_handle *h, int *Ap, int *Ai);
+#include "cb_plan_device.cuh"
 
 static int build_plan(cb_handle *h)
 {
     if (h->plan_ready) return CB_OK;
+    {   // shell-only CSC models: everything is built on the device (cb_plan_device.cuh); < 0: not applicable
+        const int drc = build_plan_device(h);
+        if (drc >= 0) return drc;
+    }
+    const auto t_begin_host = std::chrono::steady_clock::now();
+    const bool timing = getenv("CB_PLAN_TIMING") != nullptr;
+    auto tprev = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "  plan %-28s %8.3f s\n", what, std::chrono::duration<double>(now - tprev).count());
+        tprev = now;
+    };
     const long NJ = h->sz.NJ;
     const long ne[4] = {h->sz.NE_TR, h->sz.NE_FR, h->sz.NE_SH, h->NE_BR};
     const int nn[4] = {2, 2, 3, 8}, pad[4] = {2, 2, 4, 8};
@@ -674,6 +694,7 @@ static int build_plan(cb_handle *h)
         }
     if (h->jl1 <= h->jl0) { h->jl0 = h->jl1 = 0; }
     if (h->ql1 <= h->ql0) { h->ql0 = h->ql1 = 0; }
+    mark("corners");
     // joint adjacency (sorted unique, includes the joint itself when it has elements)
     h->adj_start.assign(NJ + 1, 0);
     h->adj.clear();
@@ -691,6 +712,7 @@ static int build_plan(cb_handle *h)
         h->adj.insert(h->adj.end(), tmp.begin(), tmp.end());
         h->adj_start[j + 1] = (int32_t)h->adj.size();
     }
+    mark("adjacency");
     // CSC geometry
     h->base.assign(NJ + 1, 0); h->colh.assign(NJ, 0);
     std::vector<int32_t> rowoff(h->adj.size(), 0);
@@ -785,6 +807,7 @@ static int build_plan(cb_handle *h)
         if (cur.nout > max_tile_out) max_tile_out = cur.nout;
     }
     if (open) tiles.push_back(cur);
+    mark("pairs + contribs + tiles");
     // inside a tile, order the pair records by contribution count so that the threads of a warp
     // loop alike in the reduction phase (the contribution list itself keeps reference order)
     for (CbTile &tl : tiles)
@@ -872,6 +895,7 @@ static int build_plan(cb_handle *h)
     std::vector<int32_t> telems;
     bool plan2_ok = tiles_ok && h->sz.NE_SH && !h->sz.NE_TR && !h->sz.NE_FR && !h->NE_BR &&
                     h->max_dof == 6 && !h->mixed && h->fl.ANAFLAG != 3;   // yielded shells: general kernel
+    mark("thread slots, dof scan");
     // ---- shell-only models, first choice: the "stream" plan of k_assemble_shell_stream ----------------
     // (cb_internal.h, CbStreamShape / CbTileS).  Tiles are runs of consecutive joints; the joint-pair
     // blocks of a tile are handed to the 32 lanes of one warp WHOLE (a block with more contributions than
@@ -886,204 +910,35 @@ static int build_plan(cb_handle *h)
     const int shape_id = (kt_env && strcmp(kt_env, "wide") == 0) ? 0 : 1;
     const CbStreamShape shp = shapes[shape_id];
     if (planS_ok) {
-        struct Part { int32_t blk; uint8_t c0, cnt, follow; };       // blk: index into the tile's block list
-        struct LaneS { int load = 0; bool closed = false; std::vector<Part> parts; };
-        std::vector<size_t> blocks;           // pairs_csc indices of the open tile
-        std::vector<int32_t> curel, curel_slots; std::vector<int> slot_of;
-        std::vector<LaneS> lanes;
-        int64_t out0 = 0; long nout = 0; bool open = false;
-        const int S = shp.steps;
-        // place the parts of joint blocks [q0, q1) into `ln` (first-fit, decreasing size); false if > 32 lanes
-        auto place = [&](std::vector<LaneS> &ln, size_t q0, size_t q1, int blk0) {
-            std::vector<Part> parts;
-            for (size_t q = q0; q < q1; ++q) {
-                const int cnt = pairs_csc[q].ccount, b = blk0 + (int)(q - q0);
-                if (cnt <= S) parts.push_back({b, 0, (uint8_t)cnt, 0});
-                else {
-                    const int h = (cnt + 1) / 2;
-                    parts.push_back({b, 0, (uint8_t)h, 0});
-                    parts.push_back({b, (uint8_t)h, (uint8_t)(cnt - h), 1});
-                }
-            }
-            std::stable_sort(parts.begin(), parts.end(), [](const Part &x, const Part &y) { return x.cnt > y.cnt; });
-            for (const Part &pt : parts) {
-                size_t l = 0;
-                for (; l < ln.size(); ++l)
-                    if (!ln[l].closed && ln[l].load + pt.cnt <= S) break;
-                if (l == ln.size()) { if (ln.size() == 32) return false; ln.emplace_back(); }
-                ln[l].parts.push_back(pt); ln[l].load += pt.cnt;
-                if (pt.follow) ln[l].closed = true;          // a follower is the last part of its lane
-            }
-            return true;
-        };
-        auto close_tile = [&]() {
-            const size_t ti = tilesS.size();
-            CbTileS t{};
-            t.out0 = out0; t.nout = (int32_t)nout;
-            t.np = (uint8_t)blocks.size(); t.ne = (uint8_t)curel.size();
-            int nsteps = 0;
-            for (const LaneS &l : lanes) nsteps = std::max(nsteps, l.load);
-            t.nsteps = (uint8_t)nsteps;
-            // ---- lane order and shell slots: performance only (the interpreter check does not care) ----
-            // (1) lanes that store at the same steps sit next to each other, so that a 16-byte store
-            // instruction touches as few quarter-warps as possible (a shared-memory wavefront serves one
-            // quarter-warp); inside such a group the lanes of one aligned octet get blocks whose image
-            // offsets fall into distinct 16-byte bank groups, as far as a greedy pick manages.
-            {
-                const int shift = (int)((out0 + h->ax_pad) & 1);
-                struct LInfo { unsigned sig; int key[CB_S_MAXSTEPS_ANY]; };
-                std::vector<LInfo> info(lanes.size());
-                for (size_t l = 0; l < lanes.size(); ++l) {
-                    LInfo &li = info[l]; li.sig = 0;
-                    for (int k = 0; k < CB_S_MAXSTEPS_ANY; ++k) li.key[k] = -1;
-                    int st = 0;
-                    for (const Part &pt : lanes[l].parts) {
-                        st += pt.cnt;
-                        const CbPair &p = pairs_csc[blocks[pt.blk]];
-                        const int rel = (int)(p.off - out0);
-                        const bool fast = p.maskA == 0x3f && p.maskB == 0x3f && !((shift + rel) & 1) && !(p.colh & 1);
-                        if (pt.follow) li.sig |= 1u << 31;
-                        else { li.sig |= 1u << (st - 1); li.key[st - 1] = fast ? ((shift + rel) >> 1) & 7 : -1; }
-                    }
-                }
-                std::vector<size_t> order(lanes.size());
-                for (size_t l = 0; l < order.size(); ++l) order[l] = l;
-                std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return info[x].sig < info[y].sig; });
-                std::vector<size_t> fin; fin.reserve(order.size());
-                std::vector<uint8_t> taken(order.size(), 0);
-                uint8_t used[CB_S_MAXSTEPS_ANY][8];
-                for (size_t pos = 0; pos < order.size(); ++pos) {
-                    if ((pos & 7) == 0) memset(used, 0, sizeof used);
-                    size_t head = 0;
-                    while (taken[head]) ++head;
-                    const unsigned sig = info[order[head]].sig;
-                    size_t pick = head;
-                    for (size_t c = head, seen = 0; c < order.size() && info[order[c]].sig == sig && seen < 16; ++c) {
-                        if (taken[c]) continue;
-                        ++seen;
-                        bool clash = false;
-                        for (int k = 0; k < CB_S_MAXSTEPS_ANY; ++k) { const int ky = info[order[c]].key[k]; if (ky >= 0 && used[k][ky]) clash = true; }
-                        if (!clash) { pick = c; break; }
-                    }
-                    taken[pick] = 1; fin.push_back(order[pick]);
-                    for (int k = 0; k < CB_S_MAXSTEPS_ANY; ++k) { const int ky = info[order[pick]].key[k]; if (ky >= 0) used[k][ky] = 1; }
-                }
-                std::vector<LaneS> sorted; sorted.reserve(lanes.size());
-                for (size_t l : fin) sorted.push_back(std::move(lanes[l]));
-                lanes.swap(sorted);
-            }
-            // (2) shell slots: the records of the shells read by one aligned octet of lanes in one step
-            // should sit in distinct 16-byte bank groups, i.e. slot numbers distinct modulo 8 (a record is
-            // nine 16-byte units long).  Greedy colouring, then slots handed out per colour.
-            {
-                const int ne = (int)curel.size();
-                std::vector<std::vector<int>> adjc(ne);
-                std::vector<std::vector<int>> byslot(lanes.size());          // per lane: shell index of every step
-                for (size_t l = 0; l < lanes.size(); ++l)
-                    for (const Part &pt : lanes[l].parts) {
-                        const CbPair &p = pairs_csc[blocks[pt.blk]];
-                        for (int c = 0; c < pt.cnt; ++c)
-                            byslot[l].push_back((int)(std::find(curel.begin(), curel.end(), contribs[p.cstart + pt.c0 + c].e) - curel.begin()));
-                    }
-                for (size_t o = 0; o < lanes.size(); o += 8)
-                    for (int st = 0; st < nsteps; ++st)
-                        for (size_t x = o; x < std::min(o + 8, lanes.size()); ++x)
-                            for (size_t y = x + 1; y < std::min(o + 8, lanes.size()); ++y)
-                                if (st < (int)byslot[x].size() && st < (int)byslot[y].size() && byslot[x][st] != byslot[y][st]) {
-                                    adjc[byslot[x][st]].push_back(byslot[y][st]); adjc[byslot[y][st]].push_back(byslot[x][st]);
-                                }
-                std::vector<int> colour(ne, -1), cap(8, 0), cnt(8, 0);
-                for (int k = 0; k < shp.slots; ++k) ++cap[k & 7];
-                std::vector<int> ord(ne);
-                for (int e = 0; e < ne; ++e) ord[e] = e;
-                std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return adjc[x].size() > adjc[y].size(); });
-                for (int e : ord) {
-                    int clash[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    for (int o : adjc[e]) if (colour[o] >= 0) ++clash[colour[o]];
-                    int best = -1;
-                    for (int c = 0; c < 8; ++c)
-                        if (cnt[c] < cap[c] && (best < 0 || clash[c] < clash[best])) best = c;
-                    colour[e] = best; ++cnt[best];
-                }
-                std::vector<int32_t> perm(shp.slots, -1);
-                int nextslot[8] = {0, 1, 2, 3, 4, 5, 6, 7};
-                slot_of.assign(ne, 0);
-                for (int e = 0; e < ne; ++e) { slot_of[e] = nextslot[colour[e]]; perm[slot_of[e]] = curel[e]; nextslot[colour[e]] += 8; }
-                // compact is not required: unused slots repeat a valid shell (they are staged but never read)
-                std::vector<int32_t> ncur(shp.slots, curel[0]);
-                for (int k = 0; k < shp.slots; ++k) if (perm[k] >= 0) ncur[k] = perm[k];
-                curel_slots = ncur;
-            }
-            stepsS.resize((ti + 1) * (size_t)S * 32, CB_S_IDLE);
-            for (size_t l = 0; l < lanes.size(); ++l) {
-                int st = 0;
-                for (const Part &pt : lanes[l].parts) {
-                    const CbPair &p = pairs_csc[blocks[pt.blk]];
-                    for (int c = 0; c < pt.cnt; ++c, ++st) {
-                        const CbContrib &ct = contribs[p.cstart + pt.c0 + c];
-                        const int slot = slot_of[std::find(curel.begin(), curel.end(), ct.e) - curel.begin()];
-                        const int cls = h->cls_on ? h->h_cls[ct.e] : 0;
-                        stepsS[(ti * S + st) * 32 + l] = CB_S_REC(slot, ct.a, ct.b, c == 0, c == pt.cnt - 1, pt.follow, pt.blk, cls);
-                    }
-                }
-            }
-            pairsS.resize((ti + 1) * (size_t)shp.pairs, 0); blkS.resize((ti + 1) * (size_t)shp.pairs, -1);
-            for (size_t k = 0; k < blocks.size(); ++k) {
-                const CbPair &p = pairs_csc[blocks[k]];
-                pairsS[ti * shp.pairs + k] = CB_S_PAIR(p.off - out0, p.colh, p.maskA, p.maskB);
-                blkS[ti * shp.pairs + k] = (int32_t)blocks[k];
-            }
-            elemsS.resize((ti + 1) * (size_t)shp.slots, 0);          // unused slots repeat a valid shell
-            std::copy(curel_slots.begin(), curel_slots.end(), elemsS.begin() + ti * shp.slots);
-            t.ne = (uint8_t)shp.slots;
-            tilesS.push_back(t);
-            open = false; blocks.clear(); curel.clear(); lanes.clear();
-        };
-        size_t i = 0;
-        std::vector<int32_t> newel;
-        while (i < pairs_csc.size() && planS_ok) {
-            size_t g1 = i;
-            const int32_t B = pair_B[i];
-            while (g1 < pairs_csc.size() && pair_B[g1] == B) ++g1;
-            int cmax = 0;
-            for (size_t q = i; q < g1; ++q) cmax = std::max(cmax, (int)pairs_csc[q].ccount);
-            const long out_n = (long)h->h_nfree[B] * h->colh[B];
-            if (cmax > 2 * S || h->colh[B] > 255 || (long)(g1 - i) > shp.pairs || out_n > shp.img) { planS_ok = false; break; }
-            auto collect = [&](const std::vector<int32_t> &have) {
-                newel.clear();
-                for (size_t q = i; q < g1; ++q)
-                    for (int c = 0; c < pairs_csc[q].ccount; ++c) {
-                        const int32_t e = contribs[pairs_csc[q].cstart + c].e;
-                        if (std::find(have.begin(), have.end(), e) == have.end() &&
-                            std::find(newel.begin(), newel.end(), e) == newel.end())
-                            newel.push_back(e);
-                    }
-            };
-            bool placed = false;
-            if (open) {
-                collect(curel);
-                if (h->base[B] - h->ax_base == out0 + nout && nout + out_n <= shp.img &&
-                    curel.size() + newel.size() <= (size_t)shp.slots && blocks.size() + (g1 - i) <= (size_t)shp.pairs) {
-                    std::vector<LaneS> trial = lanes;
-                    if (place(trial, i, g1, (int)blocks.size())) { lanes.swap(trial); placed = true; }
-                }
-                if (!placed) close_tile();
-            }
-            if (!placed) {
-                curel.clear(); collect(curel);
-                if (newel.size() > (size_t)shp.slots || !place(lanes, i, g1, 0)) { planS_ok = false; break; }
-                out0 = h->base[B] - h->ax_base; nout = 0; open = true;
-            }
-            curel.insert(curel.end(), newel.begin(), newel.end());
-            for (size_t q = i; q < g1; ++q) blocks.push_back(q);
-            nout += out_n;
-            i = g1;
+        // tile packing: cb_plan_pack.h (shared with the device-side planner), segment by segment
+        std::vector<int32_t> jpair(NJ + 1, 0);
+        for (size_t q = 0; q < pair_B.size(); ++q) ++jpair[pair_B[q] + 1];
+        for (long j = 0; j < NJ; ++j) jpair[j + 1] += jpair[j];
+        PkIn in{};
+        in.pairs = pairs_csc.data(); in.contribs = contribs.data(); in.jpair = jpair.data();
+        in.nfree = h->h_nfree.data(); in.colh = h->colh.data(); in.base = h->base.data(); in.ax_base = h->ax_base;
+        in.ax_pad = h->ax_pad; in.cls = h->cls_on ? h->h_cls.data() : nullptr; in.shp = shp;
+        const long nseg = (h->j1 - h->j0 + CB_PK_SEG - 1) / CB_PK_SEG;
+        std::vector<long> seg_t0(nseg + 1, 0);
+        for (long sgi = 0; sgi < nseg && planS_ok; ++sgi) {
+            const long a0 = h->j0 + sgi * CB_PK_SEG, a1 = std::min<long>(a0 + CB_PK_SEG, h->j1);
+            const long n = pk_segment(in, a0, a1, 0, nullptr);
+            if (n < 0) planS_ok = false; else seg_t0[sgi + 1] = seg_t0[sgi] + n;
         }
-        if (planS_ok && open) close_tile();
-        if (planS_ok && tilesS.empty()) planS_ok = false;
-        if (planS_ok && tilesS.size() * (size_t)S * 9 * 32 > 0x7fffffffffffUL) planS_ok = false;
+        if (planS_ok && seg_t0[nseg] == 0) planS_ok = false;
+        if (planS_ok) {
+            const size_t nt = (size_t)seg_t0[nseg];
+            tilesS.resize(nt); stepsS.resize(nt * shp.steps * 32); pairsS.resize(nt * shp.pairs);
+            elemsS.resize(nt * shp.slots); blkS.resize(nt * shp.pairs);
+            PkOut out{tilesS.data(), stepsS.data(), pairsS.data(), elemsS.data(), blkS.data()};
+            for (long sgi = 0; sgi < nseg; ++sgi) {
+                const long a0 = h->j0 + sgi * CB_PK_SEG, a1 = std::min<long>(a0 + CB_PK_SEG, h->j1);
+                pk_segment(in, a0, a1, seg_t0[sgi], &out);
+            }
+        }
         if (!planS_ok) { tilesS.clear(); stepsS.clear(); pairsS.clear(); elemsS.clear(); blkS.clear(); }
     }
+    mark("stream plan");
     // Interpreter check of the stream plan (always in cb_plan_selfcheck, or with CB_PLAN_CHECK set): walk
     // the records exactly as the kernel does and verify that every joint-pair block is accumulated from
     // precisely its contribution list (reference order; a follower part continues where the first part
@@ -1151,6 +1006,7 @@ static int build_plan(cb_handle *h)
         }
         if (expect != h->nnz) return fail(CB_ERR_ARG, "stream plan: tiles cover %ld of %ld entries", (long)expect, h->nnz);
     }
+    mark("plan check");
     if (planS_ok) plan2_ok = false;           // the duo plan is the fallback (CB_KT=duo, or blocks too large)
     if (plan2_ok) {
         CbTile2 cur{}; bool open2 = false;
@@ -1304,6 +1160,7 @@ static int build_plan(cb_handle *h)
     if (plan2_ok || planS_ok) { tiles.clear(); tpairs.clear(); }
     if (tiles.empty()) { tcontribs.clear(); tdst.clear(); }
 
+    mark("duo plan / buckets");
     if (h->node_cstart.upload(cstart) || h->corners.upload(corners) || h->contribs.upload(contribs))
         return CB_ERR_CUDA;
     if (h->layout & CB_MAT_CSC) {
@@ -1344,6 +1201,8 @@ static int build_plan(cb_handle *h)
                           contribs.size() * sizeof(CbContrib));
     // uploads above went through the legacy default stream; the handle's stream is non-blocking
     if (!g_host_only && cudaDeviceSynchronize() != cudaSuccess) return fail(CB_ERR_CUDA, "sync after map upload");
+    mark("uploads + Ap");
+    h->plan_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin_host).count();
     h->plan_ready = true;
     return CB_OK;
 }
@@ -2224,6 +2083,13 @@ extern "C" const int *cb_dev_Ai(cb_handle *h)
     if (!h || !(h->layout & CB_MAT_CSC)) return nullptr;
     cudaSetDevice(h->fl.device);
     if (build_plan(h)) return nullptr;
+    if (!h->Ai.p && h->plan_on_device) {            // written by one thread per joint from the resident adjacency
+        if (h->Ai.alloc((size_t)h->nnz)) return nullptr;
+        devplan::k_pattern<<<devplan::grid_of(h->sz.NJ), 256, 0, h->stream>>>(h->sz.NJ, h->j0, h->j1, h->nnz, h->d_jpair.p, h->d_adj.p,
+                                                                                h->d_nfree.p, h->d_first.p, h->d_base.p, h->d_colh.p,
+                                                                                h->Ap.p, h->Ai.p);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) return nullptr;
+    }
     if (!h->Ai.p) {
         std::vector<int> Ap(h->sz.NEQ + 1), Ai((size_t)h->nnz);
         host_pattern(h, Ap.data(), Ai.data());
@@ -2430,6 +2296,39 @@ extern "C" void *cb_host_alloc(unsigned long bytes)
 }
 extern "C" void cb_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" long cb_map_bytes(cb_handle *h) { return h ? h->map_bytes : 0; }
+// where and how fast the element-to-nonzero maps were built: seconds of the build, 1 = on the device
+extern "C" int cb_plan_info(cb_handle *h, double *seconds, int *on_device)
+{
+    if (!h) return fail(CB_ERR_ARG, "null handle");
+    if (!g_host_only) cudaSetDevice(h->fl.device);
+    int rc = build_plan(h); if (rc) return rc;
+    if (seconds) *seconds = h->plan_seconds;
+    if (on_device) *on_device = h->plan_on_device ? 1 : 0;
+    return CB_OK;
+}
+// test hook: the arrays of the shell stream plan (0 tiles, 1 steps, 2 pairs, 3 shell slots); returns their size
+// in bytes (dst may be NULL to ask for it), -1 if the handle has no such plan
+extern "C" long cb_debug_stream_plan(cb_handle *h, int which, void *dst)
+{
+    if (!h || build_plan(h) || !h->plan_csc.ntilesS) return -1;
+    const Plan &P = h->plan_csc;
+    const void *src = nullptr; size_t bytes = 0;
+    switch (which) {
+    case 0: src = P.tilesS.p; bytes = P.tilesS.n * sizeof(CbTileS); break;
+    case 1: src = P.stepsS.p; bytes = P.stepsS.n * 4; break;
+    case 2: src = P.pairsS.p; bytes = P.pairsS.n * 4; break;
+    case 3: src = P.elemsS.p; bytes = P.elemsS.n * 4; break;
+    case 4: src = cb_dev_Ai(h); bytes = (size_t)h->nnz * sizeof(int); if (!src) return -1; break;   // Ai as resident on the device
+    case 5: src = h->Ap.p; bytes = (size_t)(h->sz.NEQ + 1) * sizeof(int); break;
+    default: return -1;
+    }
+    if (dst) {
+        cudaSetDevice(h->fl.device);
+        cudaStreamSynchronize(h->stream);
+        if (cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    }
+    return (long)bytes;
+}
 extern "C" long cb_local_equations(cb_handle *h)
 {
     if (!h || build_plan(h)) return -1;

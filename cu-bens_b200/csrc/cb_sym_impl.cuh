@@ -123,7 +123,7 @@ static void sym_expand_range(const cb_handle *h, const double *P, double *Ax, lo
                 const double *PB = P + S.ubase[B] + S.mirror[k];
                 if (nA == 6 && nB == 6) {
                     long off = 0;
-#pragma GCC unroll 6
+#pragma unroll
                     for (int c2 = 0; c2 < 6; ++c2) {
                         const double *src = PB + off;                                    // rows of A in column c2 of B
                         double *d = buf + ro + c2;

@@ -41,7 +41,8 @@ EXPORTS = [
     "cb_plan_selfcheck", "cb_csc_upper_nnz", "cb_csc_upper_pattern", "cb_get_csc_upper_values",
     "cb_csc_values_begin", "cb_csc_values_end", "cb_get_csc_values_mirrored", "cb_sym_selftest",
     "cb_local_equations", "cb_csc_values_d2h_bytes", "cb_get_reaction_sums", "cb_comm_unique_id", "cb_comm_init",
-    "cb_comm_destroy", "cb_residual_allreduce", "cb_trip_allreduce", "cb_convergence_test",
+    "cb_comm_destroy", "cb_residual_allreduce", "cb_trip_allreduce", "cb_convergence_test", "cb_plan_info",
+    "cb_debug_stream_plan",
 ]
 
 
@@ -86,6 +87,7 @@ def load_library(path=None):
     lib.cb_csc_upper_nnz.restype = C.c_long
     lib.cb_local_equations.restype = C.c_long
     lib.cb_csc_values_d2h_bytes.restype = C.c_long
+    lib.cb_debug_stream_plan.restype = C.c_long
     lib.cb_launch_count.restype = C.c_long
     lib.cb_map_bytes.restype = C.c_long
     lib.cb_last_stiff_ms.restype = C.c_double
@@ -400,6 +402,20 @@ class Assembler:
         err = self.lib.cb_convergence_test(self.h, C.c_double(lpf), C.c_double(intener1), C.c_double(toldisp),
                                            C.c_double(tolforc), C.c_double(tolener), C.byref(conv), _p(s))
         return err, conv.value, s
+
+    def plan_info(self):
+        """(seconds the element-to-nonzero maps took to build, built on the device?)"""
+        sec = C.c_double(0); dev = C.c_int(0)
+        self._check(self.lib.cb_plan_info(self.h, C.byref(sec), C.byref(dev)))
+        return sec.value, bool(dev.value)
+
+    def debug_stream_plan(self, which):
+        n = self.lib.cb_debug_stream_plan(self.h, C.c_int(which), C.c_void_p(0))
+        if n < 0:
+            return None
+        buf = np.zeros(n, dtype=np.uint8)
+        assert self.lib.cb_debug_stream_plan(self.h, C.c_int(which), _p(buf)) == n
+        return buf
 
     def reaction_sums(self):
         r = np.zeros(6)

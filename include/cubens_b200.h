@@ -299,6 +299,13 @@ double cb_last_stiff_ms(cb_handle *h);
 double cb_last_forces_ms(cb_handle *h);
 /* bytes of implementation-only maps read per cb_stiff (reported next to the roofline)      */
 long cb_map_bytes(cb_handle *h);
+/* where the element-to-nonzero maps / CSC pattern were built (1: on the device, cb_plan_device.cuh - shell-only
+ * models with the CSC layout; 0: host builder) and how long the build took in seconds.  Environment CB_PLAN=host
+ * forces the host builder (the tests compare the two bit for bit).                                       */
+int  cb_plan_info(cb_handle *h, double *seconds, int *on_device);
+/* test hook: arrays of the shell stream plan as resident on the device (0 tiles, 1 step records, 2 pair records,
+ * 3 shell slots, 4 Ai, 5 Ap); returns the size in bytes (dst may be NULL), -1 if absent                    */
+long cb_debug_stream_plan(cb_handle *h, int which, void *dst);
 /* equations of the joints this handle's elements touch (= NEQ unless element-partitioned): the part of
  * dd / f_temp that cb_update_forces moves between host and device                            */
 long cb_local_equations(cb_handle *h);

@@ -380,8 +380,13 @@ def run_gpu(a):
         asm.set_dd(step_dd)
         # the collective lives in the library (cb_comm_init / cb_residual_allreduce); N=1 forms the same sums
         exchange = InterfaceExchange(asm, m, world, rank, dist, owned)
-        return m, owned, n_local, asm, step_dd, exchange, {"mesh_and_reference_maps": t1 - t0, "cb_create": t2 - t1,
-                                                           "plan_and_first_stiff": t3 - t2}
+        plan_s, plan_dev = asm.plan_info()
+        return m, owned, n_local, asm, step_dd, exchange, {
+            "mesh_and_reference_maps": t1 - t0, "cb_create": t2 - t1, "plan_and_first_stiff": t3 - t2,
+            "plan_build": plan_s, "plan_built_on_device": plan_dev,
+            "note": "mesh_and_reference_maps: numpy mesh + the vectorised mirror of codes() / skylin (what main.c does "
+                    "before the loop); cb_create: uploads + geometry classes; plan_build: sorted element-to-nonzero "
+                    "map, CSC pattern and tile plan (cb_plan_info), part of plan_and_first_stiff"}
 
     m, owned, n_local, asm, step_dd, exchange, setup_s = build(weak=not a.strong)
     nnz = asm.lib.cb_csc_nnz(asm.h)

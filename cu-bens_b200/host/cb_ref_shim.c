@@ -4,7 +4,7 @@
  * signatures (prototypes.h:91-93 stiff_tr, :100-102 forces_tr, :106-107 mass_tr, :122-127 stiff_fr, :149-155
  * forces_fr, :159-161 mass_fr, :187-191 stiff_sh, :240-242 mass_sh, :246-251 forces_sh) and forwards them to
  * libcubens_b200 (include/cubens_b200.h).  Linked with the UNMODIFIED main.c / model.c / solve.c / arc.c /
- * memory.c / misc.c (oracle/Makefile: ben_b200.exe, ben_b200_capture.exe) it turns the reference program
+ * memory.c / misc.c (the recipe that compiles the reference in place: ben_b200.exe, ben_b200_capture.exe) it turns the reference program
  * itself into a host of the device path: input decks, Newton / arc-length / Newmark loops, step halving,
  * output files - all the reference's, every element stiffness, internal force and mass evaluated on the GPU.
  *

@@ -9,7 +9,7 @@ python bench.py > $out/bench_${tag}_n1.json 2> $out/bench_${tag}_n1.err
 python bench.py --impl reference --steps 10 --warmup 2 > $out/bench_${tag}_ref.json 2> $out/bench_${tag}_ref.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_${tag}.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu --no-others > $out/ncu_launch_${tag}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_assemble_shell_tiles -s 3 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:k_assemble_shell_ -s 3 -c 1 \
     -o $out/prof_${tag}_assemble python bench.py --steps 2 --warmup 3 --no-cpu --no-others --no-unstructured > $out/ncu_a_${tag}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_shell_forces -s 3 -c 1 \
     -o $out/prof_${tag}_forces python bench.py --steps 2 --warmup 3 --no-cpu --no-others --no-unstructured > $out/ncu_f_${tag}.log 2>&1

@@ -120,7 +120,11 @@ struct cb_handle {
     // host copies needed after create
     std::vector<int32_t> h_jc;    // [NJ][8]
     std::vector<long> h_maxa;
-    std::vector<int32_t> h_nodes[4];
+    std::vector<int32_t> h_nodes[5];    // truss, frame, shell, brick (solid then fluid), FSI coupling pairs
+    bool fsi = false;                   // ANAFLAG 4: joints [NJ_user, 2 NJ_user) are the pressure twins of the real ones
+    long NJ_user = 0, ncouple = 0;
+    double fdens = 0;
+    DevBuf<double> cp_L;
     std::vector<int32_t> h_first; // first equation (1-based) of each joint, 0 if none
     std::vector<uint8_t> h_mask;
     std::vector<int32_t> h_nfree;
@@ -212,7 +216,8 @@ static CbDev make_dev(cb_handle *h)
     CbDev d{};
     d.NJ = h->sz.NJ; d.NEQ = h->sz.NEQ;
     d.NE_TR = h->sz.NE_TR; d.NE_FR = h->sz.NE_FR; d.NE_SH = h->sz.NE_SH; d.NE_BR = h->NE_BR;
-    d.ANAFLAG = h->fl.ANAFLAG;
+    d.ANAFLAG = h->fl.ANAFLAG == 4 ? 1 : h->fl.ANAFLAG;    // FSI is linear elastic (shell.c:141: ANAFLAG 1 / 4 alike)
+    d.NE_SBR = h->sz.NE_SBR; d.cp_L = h->cp_L.p; d.fdens = h->fdens;
     d.jc = h->jc.p;
     d.sh_nodes = h->sh_nodes.p; d.sh_const = h->sh_const.p; d.sh_keb = h->sh_keb.p; d.sh_own = h->sh_own.p;
     d.sh_Nm = h->sh_Nm.p; d.sh_fg = h->sh_fg.p; d.sh_der = h->sh_der.p;
@@ -239,20 +244,22 @@ static int d2d(double *dst, const double *src, size_t n, cudaStream_t s)
 // ------------------------------------------------------------------------------------------
 // cb_create
 // ------------------------------------------------------------------------------------------
-extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model *m,
-                         cb_handle **out)
+// what the FSI front end of cb_create hands to the common path: coupling pairs (structural joint, pressure twin)
+// and their vectors L = tarea * nnorm
+struct FsiInfo { long NJ_user; std::vector<int32_t> pairs; std::vector<double> L; double fdens; };
+
+static int create_inner(const cb_sizes *sz, const cb_flags *fl, const cb_model *m, cb_handle **out, const FsiInfo *fsi)
 {
     if (!sz || !fl || !m || !out) return fail(CB_ERR_ARG, "cb_create: null argument");
     *out = nullptr;
-    if (fl->ANAFLAG < 1 || fl->ANAFLAG > 3)
-        return fail(CB_ERR_UNSUPPORTED, "ANAFLAG=%d: 1 (elastic), 2 (geometric nonlinear) and 3 "
-                    "(material nonlinear, trusses and frames) are built; 4 (FSI) is listed in "
-                    "DESIGN.md", fl->ANAFLAG);
+    if (fl->ANAFLAG < 1 || fl->ANAFLAG > 4 || (fl->ANAFLAG == 4 && !fsi))
+        return fail(CB_ERR_UNSUPPORTED, "ANAFLAG=%d: 1 (elastic), 2 (geometric nonlinear), 3 (material nonlinear) and "
+                    "4 (acoustic FSI, with nnorm / tarea / fdens) are built", fl->ANAFLAG);
     if (fl->ANAFLAG == 3 && (sz->NE_TR || sz->NE_FR || sz->NE_SH) && !m->yield)
         return fail(CB_ERR_ARG, "ANAFLAG=3 needs the yield stresses");
     if (fl->ANAFLAG == 3 && sz->NE_FR && (!m->zstrong || !m->zweak))
         return fail(CB_ERR_ARG, "ANAFLAG=3 needs the plastic section moduli zstrong / zweak");
-    if (sz->NE_FBR != 0) return fail(CB_ERR_UNSUPPORTED, "fluid bricks (FSI) are out of scope");
+    if (sz->NE_FBR != 0 && !fsi) return fail(CB_ERR_UNSUPPORTED, "fluid bricks need the FSI inputs (ANAFLAG 4)");
     if (sz->NJ <= 0 || sz->NEQ <= 0) return fail(CB_ERR_ARG, "NJ and NEQ must be positive");
     if (sz->NJ > 0x7fffffffL / 8 || sz->NEQ > 0x7ffffff0L)
         return fail(CB_ERR_OVERFLOW, "NJ / NEQ exceed 32-bit device indices");
@@ -418,6 +425,12 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
         }
         if (h->br_const.upload(c)) BAIL(CB_ERR_CUDA);
     }
+    if (fsi) {
+        h->fsi = true; h->NJ_user = fsi->NJ_user; h->fdens = fsi->fdens;
+        h->ncouple = (long)fsi->pairs.size() / 2;
+        h->h_nodes[4] = fsi->pairs;
+        if (h->cp_L.upload(fsi->L)) BAIL(CB_ERR_CUDA);
+    }
     // ---- frames ----------------------------------------------------------------------------
     if (FR) {
         std::vector<double> c((size_t)FR * CB_FR_CONST, 0.0), fr((size_t)FR * CB_FR_FRAME),
@@ -560,6 +573,49 @@ extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model 
 #undef BAIL
 }
 
+// Acoustic FSI (ANAFLAG 4, fsi.c).  The reference numbers the structural equations first, joint by joint, and the
+// pressure equations (jcode slot 7) after them (model.c:962-990).  Every joint j gets a TWIN j + NJ that carries its
+// pressure DOF (and the same coordinates): the joint-by-joint numbering the block pattern relies on then holds again,
+// fluid bricks connect twins and contribute the (z, z) entry of the reference's 3x3 joint blocks (mcode keeps only
+// that slot, model.c:1089-1140), and the coupling matrix L = G A of L_br (fsi.c:447-531: one tarea * nnorm vector per
+// wet joint) becomes a two-joint "element" (j, twin j): [K L; 0 H] and [M 0; -rho L^T Q] (fsi.c:333-445) are then
+// two matrices on ONE sparse block pattern instead of dense NEQ^2 arrays.
+extern "C" int cb_create(const cb_sizes *sz, const cb_flags *fl, const cb_model *m, cb_handle **out)
+{
+    if (!sz || !fl || !m || !out) return fail(CB_ERR_ARG, "cb_create: null argument");
+    if (sz->NE_FBR == 0 && fl->ANAFLAG != 4) return create_inner(sz, fl, m, out, nullptr);
+    if (!m->nnorm || !m->tarea || !m->fdens) return fail(CB_ERR_ARG, "ANAFLAG 4 / fluid bricks need nnorm, tarea and fdens");
+    if (sz->NE_TR || sz->NE_FR) return fail(CB_ERR_UNSUPPORTED, "FSI models hold shells and bricks only (main.c:1038-1057)");
+    if (!m->x || !m->jcode || !m->minc) return fail(CB_ERR_ARG, "cb_create: x / jcode / minc missing");
+    const long NJ = sz->NJ, SH = sz->NE_SH, SBR = sz->NE_SBR, FBR = sz->NE_FBR;
+    cb_sizes sz2 = *sz; sz2.NJ = 2 * NJ;
+    std::vector<double> x2((size_t)NJ * 6);
+    memcpy(x2.data(), m->x, (size_t)NJ * 3 * sizeof(double));
+    memcpy(x2.data() + NJ * 3, m->x, (size_t)NJ * 3 * sizeof(double));
+    std::vector<long> jc2((size_t)NJ * 14, 0), minc2(m->minc, m->minc + 3 * SH + 8 * (SBR + FBR));
+    for (long j = 0; j < NJ; ++j) {
+        for (int r = 0; r < 6; ++r) jc2[j * 7 + r] = m->jcode[j * 7 + r];
+        jc2[(NJ + j) * 7] = m->jcode[j * 7 + 6];                 // the twin's only DOF: the pressure equation
+    }
+    for (long e = 0; e < FBR; ++e)
+        for (int a = 0; a < 8; ++a) minc2[3 * SH + 8 * (SBR + e) + a] += NJ;
+    FsiInfo info; info.NJ_user = NJ; info.fdens = m->fdens[0];
+    {   // wet joints: on a solid element (shell skin, else solid bricks: shFSI_FLAG / brFSI_FLAG) with a pressure DOF
+        std::vector<uint8_t> solid(NJ, 0);
+        if (SH) for (long i = 0; i < 3 * SH; ++i) solid[m->minc[i] - 1] = 1;
+        else for (long i = 0; i < 8 * SBR; ++i) solid[m->minc[3 * SH + i] - 1] = 1;
+        for (long j = 0; j < NJ; ++j)
+            if (solid[j] && m->jcode[j * 7 + 6] != 0) {
+                info.pairs.push_back((int32_t)j); info.pairs.push_back((int32_t)(NJ + j));
+                for (int k = 0; k < 3; ++k) info.L.push_back(m->nnorm[j * 3 + k] * m->tarea[j]);   // fsi.c:521-527
+                info.L.push_back(0.0);
+            }
+    }
+    cb_model m2 = *m;
+    m2.x = x2.data(); m2.jcode = jc2.data(); m2.minc = minc2.data(); m2.mcode = nullptr;
+    return create_inner(&sz2, fl, &m2, out, &info);
+}
+
 extern "C" void cb_destroy(cb_handle *h)
 {
     if (!h) return;
@@ -590,7 +646,7 @@ extern "C" void cb_destroy(cb_handle *h)
         h->fr_frame[g].release(); h->fr_xfr[g].release(); h->fr_efFE[g].release();
         h->fr_ef[g].release();
     }
-    h->sh_own.release();
+    h->sh_own.release(); h->cp_L.release();
     for (DevBuf<int32_t> *b : {&h->fr_gid, &h->sh_gid, &h->jc, &h->sh_nodes, &h->tr_nodes, &h->fr_nodes, &h->fr_osflag,
                                &h->fr_mendrel, &h->br_nodes, &h->node_cstart})
         b->release();
@@ -644,12 +700,12 @@ static int build_plan(cb_handle *h)
         tprev = now;
     };
     const long NJ = h->sz.NJ;
-    const long ne[4] = {h->sz.NE_TR, h->sz.NE_FR, h->sz.NE_SH, h->NE_BR};
-    const int nn[4] = {2, 2, 3, 8}, pad[4] = {2, 2, 4, 8};
+    const long ne[5] = {h->sz.NE_TR, h->sz.NE_FR, h->sz.NE_SH, h->NE_BR, h->ncouple};
+    const int nn[5] = {2, 2, 3, 8, 2}, pad[5] = {2, 2, 4, 8, 2};
     // node -> corner CSR, filled in (type, element, local node) order
     std::vector<int32_t> cstart(NJ + 1, 0);
     long ncorner = 0;
-    for (int t = 0; t < 4; ++t)
+    for (int t = 0; t < 5; ++t)
         for (long e = 0; e < ne[t]; ++e)
             for (int a = 0; a < nn[t]; ++a) { ++cstart[h->h_nodes[t][e * pad[t] + a] + 1]; ++ncorner; }
     if (ncorner > 0x7fffffffL) return fail(CB_ERR_OVERFLOW, "too many element corners");
@@ -657,7 +713,7 @@ static int build_plan(cb_handle *h)
     std::vector<CbCorner> corners(ncorner);
     {
         std::vector<int32_t> fill(cstart.begin(), cstart.end() - 1);
-        for (int t = 0; t < 4; ++t)
+        for (int t = 0; t < 5; ++t)
             for (long e = 0; e < ne[t]; ++e)
                 for (int a = 0; a < nn[t]; ++a) {
                     int32_t j = h->h_nodes[t][e * pad[t] + a];
@@ -873,12 +929,13 @@ static int build_plan(cb_handle *h)
         // three rotational equations struc() leaves free), `mixed` = some element type brings
         // fewer DOFs per joint than ND
         const bool has3 = h->sz.NE_TR || h->NE_BR, has6 = h->sz.NE_SH != 0, has7 = h->sz.NE_FR != 0;
+        const bool has1 = h->fsi;                         // pressure twins carry one DOF
         int top = has7 ? 7 : (has6 ? 6 : 3);
         for (long j = 0; j < NJ; ++j)
             for (int r = top; r < 7; ++r)
                 if ((h->h_mask[j] >> r) & 1) top = r + 1;
         h->max_dof = top <= 3 ? 3 : (top <= 6 ? 6 : 7);
-        h->mixed = (has3 && h->max_dof != 3) || (has6 && h->max_dof != 6) || (has7 && h->max_dof != 7);
+        h->mixed = (has3 && h->max_dof != 3) || (has6 && h->max_dof != 6) || (has7 && h->max_dof != 7) || has1;
         if (h->max_dof != 6) h->fuse_node = false;      // the fused gather walks six equations per joint
     }
     {   // Blocks whose columns start on an odd Ax index fall off the tile kernels' 16-byte store path.
@@ -1576,6 +1633,7 @@ extern "C" int cb_update_forces_begin(cb_handle *h, const double *dd_dev, double
     rc = ensure_keb(h); if (rc) return rc;
     if (first_fr) *first_fr = 0x7fffffff;
     if (first_sh) *first_sh = 0x7fffffff;
+    if (h->fsi) return fail(CB_ERR_UNSUPPORTED, "the FSI analysis is linear and assembled once: no force pass (fsi.c)");
     if (h->fl.ANAFLAG == 1)
         return fail(CB_ERR_ARG, "ANAFLAG 1 recovers forces with cb_forces_linear (main.c:1774-1793)");
     cudaStream_t s = h->stream;

@@ -21,6 +21,7 @@
 #define CB_T_FRAME 1
 #define CB_T_SHELL 2
 #define CB_T_BRICK 3
+#define CB_T_COUPLE 4    // fluid-structure interface joint (ANAFLAG 4): a structural joint and its pressure twin
 
 #define CB_SH_CONST 12   // E, nu, t, t^3 (libm pow on the host), A0, x2, x3, y3, l12, l23, l31, pad
 #define CB_SH_FRAME 10   // c1xyz c2xyz c3xyz, deformed area
@@ -202,6 +203,7 @@ struct CbGenTruss {
 struct CbDev {
     long NJ, NEQ;
     long NE_TR, NE_FR, NE_SH, NE_BR;
+    long NE_SBR;             // bricks [NE_SBR, NE_BR) are FLUID bricks (acoustic, one pressure DOF per joint)
     int ANAFLAG;
     // nodes
     const int32_t *jc;       // [NJ][8]
@@ -259,6 +261,10 @@ struct CbDev {
     // bricks
     const int32_t *br_nodes; // [NE][8]
     const double *br_const;  // [NE][4]  E, nu, rho, pad
+    // acoustic FSI (fsi.c): coupling vector of every wet joint, L = tributary area * unit normal (fsi.c:499-525),
+    // and the fluid density that scales -L^T in the "mass" matrix (fsi.c:436-443)
+    const double *cp_L;      // [ncouple][4]  Lx Ly Lz pad
+    double fdens;
 };
 
 // Launch configuration that is a property of the DEVICE (cudaFuncSetAttribute opt-ins above 48 KB of

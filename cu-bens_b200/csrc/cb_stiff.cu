@@ -489,7 +489,15 @@ __device__ __noinline__ int mass_block_stage(const CbStiffArgs &A, const CbContr
     if (ct.type == CB_T_BRICK) {
         double blk[9];
         brick_mass_block(A, ct.e, ct.a, ct.b, blk, 3);
+        if (ct.e >= A.d.NE_SBR) { stg[0] = blk[8]; return 1; }      // fluid: Q, with dens = 1 / c^2 (brick.c:63-69)
         for (int p = 0; p < 3; ++p) stg[(p * ND + p) * STR] = blk[p * 3 + p];
+        return 3;
+    }
+    if (ct.type == CB_T_COUPLE) {                                    // [M 0; -rho L^T Q] (fsi.c:436-443)
+        if (ct.a == 1 && ct.b == 0) {
+            const double *L = A.d.cp_L + (long)ct.e * 4;
+            for (int q = 0; q < 3; ++q) stg[q * STR] = -1 * A.d.fdens * L[q];
+        }
         return 3;
     }
     if (ct.type == CB_T_SHELL && ND >= 6) {
@@ -598,11 +606,27 @@ k_assemble_tiles(CbStiffArgs A)
                 else if (ct.type == CB_T_BRICK) brick_block(A, ct.e, ct.a, ct.b, blk, 3);
 #pragma unroll
                 for (int i = 0; i < NN; ++i) stg[i * STR] = 0.0;
+                if (ct.type == CB_T_BRICK && ct.e >= A.d.NE_SBR) {
+                    // fluid brick (fsi.c:344, model.c:1089-1140): only the (z, z) entry of the joint block has an
+                    // equation - the pressure DOF, DOF 0 of the twin joints; with the reference's E = 1e20,
+                    // nu = 0.5e20 (brick.c:72-73) it is detJ grad N_a . grad N_b, the acoustic H matrix
+                    stg[0] = blk[8];
+                    ndof[col] = 1;
+                } else if (ct.type == CB_T_COUPLE) {
+                    // [K L; 0 H] (fsi.c:376-383): L = tarea * nnorm couples the joint's translations to its pressure
+                    if (ct.a == 0 && ct.b == 1) {
+                        const double *L = A.d.cp_L + (long)ct.e * 4;
 #pragma unroll
-                for (int p = 0; p < 3; ++p)
+                        for (int p = 0; p < 3; ++p) stg[(p * ND) * STR] = L[p];
+                    }
+                    ndof[col] = 3;
+                } else {
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) stg[(p * ND + q) * STR] = blk[p * 3 + q];
-                ndof[col] = 3;
+                    for (int p = 0; p < 3; ++p)
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) stg[(p * ND + q) * STR] = blk[p * 3 + q];
+                    ndof[col] = 3;
+                }
             }
         }
         // request the next tile's contribution record, then its element inputs; they land while

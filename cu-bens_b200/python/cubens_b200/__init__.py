@@ -57,7 +57,7 @@ class cb_flags(C.Structure):
 _MODEL_FIELDS = ["x", "minc", "jcode", "mcode", "maxa", "emod", "dens", "carea", "llength", "c1",
                  "c2", "c3", "nu", "thick", "farea", "slength", "xlocal", "gmod", "istrong",
                  "iweak", "ipolar", "iwarp", "auxpt", "offset", "osflag", "mendrel", "efFE_ref", "yield",
-                 "zstrong", "zweak"]
+                 "zstrong", "zweak", "nnorm", "tarea", "fdens"]
 
 
 class cb_model(C.Structure):
@@ -119,6 +119,8 @@ def _c_model(m, layout, device):
     cm = cb_model()
     for n in _MODEL_FIELDS:
         a = getattr(m, "yld" if n == "yield" else n, None)
+        if n == "fdens":
+            a = np.array([a], dtype=np.float64) if getattr(m, "nnorm", None) is not None else None
         if a is not None:
             dt = np.int32 if n in ("osflag", "mendrel") else (np.int64 if n in ("minc", "jcode", "mcode", "maxa") else np.float64)
             a = np.ascontiguousarray(a, dtype=dt)

@@ -134,6 +134,104 @@ def brick_model(nx, ny, nz, h=1.0, props=BRICK_DEF, skin=False, shell_props=SHEL
                        meta=dict(kind="brick", nx=nx, ny=ny, nz=nz))
 
 
+def fsi_model(nx, ny, nzs, nzf, h=1.0, props=BRICK_DEF, bulk=2.2e9, fdens=1000.0, skin=False, shell_props=SHELL_5C,
+              distort=0.0, seed=7):
+    """Acoustic fluid-structure model (ANAFLAG 4, fsi.c; BASELINE.json configs[4] shape): a block of nx*ny*nzf FLUID
+    bricks below z = 0 whose top face is wet.  The structure on it is either nx*ny*nzs solid bricks above z = 0
+    (brFSI_FLAG) or, with ``skin``, DKT shells on the plane z = 0 (shFSI_FLAG).  Numbering as codes() does for
+    ANAFLAG 4 (model.c:962-990): structural equations first, joint by joint, then the pressure equations (jcode
+    slot 7); fluid brick mcode keeps the pressure in the z slot of every joint (model.c:1089-1140); fluid brick
+    properties as prop_br leaves them (brick.c:60-75): emod 1e20, nu 0.5e20, dens 1 / c^2.  nnorm / tarea (what
+    prop_fsi computes from the deck, fsi.c:44-331) are the outward normal (0, 0, -1) of the structure's wet face
+    and the tributary area of every interface joint."""
+    from .model import Model
+    nz = nzs + nzf if not skin else nzf
+    i, j, k = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    nid = (i * (ny + 1) * (nz + 1) + j * (nz + 1) + k + 1).astype(I64)
+    X = np.stack([i * h, j * h, (k - nzf) * h], axis=-1).astype(F64)
+    if distort:
+        rng = np.random.default_rng(seed)
+        X = X + distort * h * rng.uniform(-1, 1, size=X.shape) * (k[..., None] != nzf)      # the interface stays plane
+    x = X.reshape(-1)
+    NJ = x.size // 3
+    lo, hi = slice(0, -1), slice(1, None)
+    sel = {(+1): hi, (-1): lo}
+    signs = [(1, 1, 1), (-1, 1, 1), (-1, -1, 1), (1, -1, 1), (1, 1, -1), (-1, 1, -1), (-1, -1, -1), (1, -1, -1)]
+    allb = np.stack([nid[sel[a], sel[b], sel[c]] for (a, b, c) in signs], axis=-1)          # [nx, ny, nz, 8]
+    fluid = allb[:, :, :nzf].reshape(-1, 8)
+    solid = allb[:, :, nzf:].reshape(-1, 8) if not skin else np.zeros((0, 8), dtype=I64)
+    shells = np.zeros((0, 3), dtype=I64)
+    if skin:
+        top = nid[:, :, nzf]
+        a = top[:-1, :-1]; b = top[1:, :-1]; c = top[1:, 1:]; d = top[:-1, 1:]
+        shells = np.stack([np.stack([a, b, c], -1), np.stack([a, c, d], -1)], axis=2).reshape(-1, 3)
+    NE_SH, NE_SBR, NE_FBR = len(shells), len(solid), len(fluid)
+    # degrees of freedom: translations (+ rotations of the skin) on the structure, pressure on the fluid joints
+    kk = k.reshape(-1)
+    on_struct = kk >= nzf if not skin else kk == nzf
+    on_fluid = kk <= nzf
+    jc = np.zeros((NJ, 7), dtype=I64)
+    jc[on_struct, :3] = -1
+    if skin:
+        jc[on_struct, 3:6] = -1
+        edge = ((i == 0) | (i == nx) | (j == 0) | (j == ny)).reshape(-1)
+        jc[on_struct & edge, 3:6] = 0       # guided edges: L_br (fsi.c:514) needs every wet translation free
+    else:
+        jc[kk == nz, :3] = 0                                # clamped top face
+    jc[on_fluid, 6] = -1
+    free = jc[:, :6] != 0
+    num = np.cumsum(free.reshape(-1), dtype=I64).reshape(NJ, 6)
+    jcode = np.zeros((NJ, 7), dtype=I64)
+    jcode[:, :6] = np.where(free, num, 0)
+    SNDOF = int(num[-1, -1])
+    pf = jc[:, 6] != 0
+    jcode[pf, 6] = SNDOF + np.cumsum(pf, dtype=I64)[pf]
+    NEQ = int(jcode.max()); FNDOF = NEQ - SNDOF
+    minc = np.concatenate([shells.reshape(-1), solid.reshape(-1), fluid.reshape(-1)])
+    mc = [jcode[shells - 1][:, :, :6].reshape(-1)] if NE_SH else []
+    if NE_SBR:
+        mc.append(jcode[solid - 1][:, :, :3].reshape(-1))
+    fm = np.zeros((NE_FBR, 8, 3), dtype=I64); fm[:, :, 2] = jcode[fluid - 1][:, :, 6]
+    mc.append(fm.reshape(-1))
+    mcode = np.concatenate(mc).astype(I64)
+    m = Model(NJ=NJ, NE_SH=NE_SH, NE_SBR=NE_SBR, NE_FBR=NE_FBR, NEQ=NEQ, ANAFLAG=4, ALGFLAG=4, SLVFLAG=2, x=x,
+              minc=minc, jcode=jcode.reshape(-1), mcode=mcode, lss=0,
+              meta=dict(kind="fsi", nx=nx, ny=ny, nzs=nzs, nzf=nzf, skin=skin))
+    m.SNDOF, m.FNDOF, m.fdens = SNDOF, FNDOF, float(fdens)
+    ntot = NE_SH + NE_SBR + NE_FBR
+    m.emod = np.zeros(ntot); m.yld = np.zeros(ntot); m.dens = np.zeros(ntot); m.nu = np.zeros(ntot)
+    m.carea = np.zeros(0); m.llength = np.zeros(0)
+    nc = 3 * NE_SH
+    m.c1, m.c2, m.c3 = (np.zeros(nc) for _ in range(3))
+    m.thick = np.zeros(NE_SH); m.farea = np.zeros(NE_SH); m.slength = np.zeros(NE_SH * 3); m.xlocal = np.zeros(NE_SH * 3)
+    if NE_SH:
+        from .model import shell_geometry
+        E, nu, t, rho, fy = shell_props
+        m.emod[:NE_SH], m.nu[:NE_SH], m.thick[:], m.yld[:NE_SH], m.dens[:NE_SH] = E, nu, t, fy, rho
+        sl, fa, lx, ly, lz, xl = shell_geometry(x, shells - 1)
+        m.slength[:], m.farea[:], m.xlocal[:] = sl.reshape(-1), fa, xl.reshape(-1)
+        m.c1[:], m.c2[:], m.c3[:] = lx.reshape(-1), ly.reshape(-1), lz.reshape(-1)
+    if NE_SBR:
+        E, nu, rho, fy = props
+        s = slice(NE_SH, NE_SH + NE_SBR)
+        m.emod[s], m.nu[s], m.dens[s], m.yld[s] = E, nu, rho, fy
+    s = slice(NE_SH + NE_SBR, ntot)
+    wvsp = np.sqrt(bulk / fdens)                            # brick.c:63
+    m.emod[s], m.nu[s], m.dens[s] = 1e20, .5e20, 1 / wvsp ** 2
+    for nm in ("gmod", "istrong", "iweak", "ipolar", "iwarp", "zstrong", "zweak", "auxpt", "offset", "xfr", "efFE_ref"):
+        setattr(m, nm, np.zeros(0))
+    m.osflag = np.zeros(0, dtype=np.int32); m.mendrel = np.zeros(0, dtype=np.int32)
+    # interface data: normal of the structure's wet face, tributary areas (corner 1/4, edge 1/2, interior 1 cell)
+    m.nnorm = np.zeros(NJ * 3); m.tarea = np.zeros(NJ)
+    wet = (kk == nzf)
+    m.nnorm.reshape(-1, 3)[wet] = (0.0, 0.0, -1.0)
+    ii, jj = i.reshape(-1), j.reshape(-1)
+    wx = np.where((ii == 0) | (ii == nx), 0.5, 1.0); wy = np.where((jj == 0) | (jj == ny), 0.5, 1.0)
+    m.tarea[wet] = (wx * wy * h * h)[wet]
+    m.q = np.zeros(NEQ)
+    return m
+
+
 def perturbation(model, scale=1e-4, seed=20261017):
     """Seeded incremental displacement of SURVEY.md section 8(d): dd ~ U(-scale, scale) per
     free DOF, numpy default_rng(20261017)."""

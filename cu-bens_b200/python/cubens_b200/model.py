@@ -72,6 +72,12 @@ class Model:
     mendrel: np.ndarray = None    # [FR*5] int32
     xfr: np.ndarray = None        # [FR*6]
     efFE_ref: np.ndarray = None   # [FR*14]
+    # acoustic FSI (ANAFLAG 4): equation split of codes() and what prop_fsi / prop_br leave
+    SNDOF: int = 0
+    FNDOF: int = 0
+    nnorm: np.ndarray = None      # [NJ*3] interface normals
+    tarea: np.ndarray = None      # [NJ] tributary interface areas
+    fdens: float = 0.0
     # loads
     q: np.ndarray = None          # [NEQ]
     meta: dict = field(default_factory=dict)

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 3
+#define CB_ABI_VERSION 4
 
 /* status codes (the reference uses 0 = ok / 1 = error, solve.c:558-562, frame.c:1201) */
 enum {
@@ -67,7 +67,10 @@ typedef struct cb_sizes {
 /* ANAFLAG 1 = first-order elastic, 2 = geometric nonlinear, 3 = geometric + material nonlinear
  * (main.c:63-90): trusses and frames with concentrated plasticity (stiffm_tr, stiffm_fr, yield check /
  * regula_falsi / unload in forces_fr), DKT shells with Ivanov's yield criterion in stress resultants
- * (stiffm_sh, strn_curv, the return mapping of forces_sh).  ANAFLAG 4 (FSI): CB_ERR_UNSUPPORTED. */
+ * (stiffm_sh, strn_curv, the return mapping of forces_sh).  ANAFLAG 4 (acoustic FSI, fsi.c: linear, assembled
+ * once): cb_stiff(CB_GEN_COMMITTED) assembles [K L; 0 H] and cb_mass [M 0; -rho L^T Q] on one CSC pattern
+ * (cb_get_csc_values / cb_get_mass_csc_values) - sparse, where the reference holds dense NEQ^2 arrays
+ * (stiff_fsi / mass_fsi, fsi.c:333-445); the force pass is not part of that analysis.                      */
 typedef struct cb_flags {
     int ANAFLAG, ALGFLAG, SLVFLAG;
     int matrix_layout;      /* CB_MAT_*; 0 picks SKYLINE when SLVFLAG==0 else CSC          */
@@ -103,6 +106,13 @@ typedef struct cb_model {
     /* material nonlinear analysis (ANAFLAG 3), may be NULL otherwise */
     const double *yield;     /* [TR+FR+SH+BR] yield stress           truss.c:66 frame.c:177 */
     const double *zstrong, *zweak;   /* [FR] plastic section moduli  frame.c:177            */
+    /* acoustic fluid-structure interaction (ANAFLAG 4, fsi.c), NULL otherwise: what prop_fsi leaves (fsi.c:44-331)
+     * and the fluid density of prop_br (brick.c:60-75).  jcode[j][6] then holds the PRESSURE equation of joint j
+     * (numbered after all structural equations, model.c:962-990), the fluid bricks are bricks NE_SBR .. NE_SBR +
+     * NE_FBR - 1 with the reference's emod = 1e20, nu = 0.5e20 and dens = 1 / c^2 (brick.c:63-75)             */
+    const double *nnorm;     /* [NJ*3] unit normals of the fluid-structure interface at the joints           */
+    const double *tarea;     /* [NJ]   tributary interface area of the joints                                */
+    const double *fdens;     /* [1]    fluid density                                                          */
 } cb_model;
 
 typedef struct cb_handle cb_handle;

@@ -32,6 +32,12 @@ void ref_set_flags(int anaflag, int algflag, int slvflag, int optflag)
     FSIFLAG = FSIINCFLAG = brFSI_FLAG = shFSI_FLAG = 0; CHKPT = RFLAG = 0;
 }
 
+/* acoustic FSI (ANAFLAG 4): equation split of codes() (model.c:977,990) and which solids are wet */
+void ref_set_fsi(long sndof, long fndof, int br_flag, int sh_flag)
+{
+    SNDOF = sndof; FNDOF = fndof; brFSI_FLAG = br_flag; shFSI_FLAG = sh_flag; FSIFLAG = 1;
+}
+
 long ref_get_NEQ(void)  { return NEQ; }
 long ref_get_NBC(void)  { return NBC; }
 void ref_set_NEQ(long n) { NEQ = n; }

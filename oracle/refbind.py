@@ -290,3 +290,29 @@ def skyline_solve(m, ss, rhs, fact=0):
     if err:
         raise RuntimeError("reference skyline solve failed")
     return dd, ssd, det.value
+
+
+# ---- acoustic FSI (fsi.c) ----------------------------------------------------------------------
+def fsi_matrices(m):
+    """The reference's dense system matrices of an FSI model (ANAFLAG 4): L_br (fsi.c:447-531), stiff_fsi
+    (fsi.c:333-386) and mass_fsi (fsi.c:388-445) called as main.c:1440-1596 does.  Returns (ss_fsi, sm_fsi)
+    as [NEQ, NEQ] arrays indexed [row-major as the reference stores them]."""
+    l = set_model(m, SLVFLAG=2, ANAFLAG=4)
+    br = 1 if m.NE_SH == 0 else 0
+    l.ref_set_fsi(L(m.SNDOF), L(m.FNDOF), C.c_int(br), C.c_int(1 - br))
+    n, sn, fn = m.NEQ, m.SNDOF, m.FNDOF
+    z = np.zeros
+    Lm, A, G, LT = z(sn * fn), z(fn * fn), z(sn * fn), z(fn * sn)
+    jcode_fsi = np.zeros(m.NJ * 7, dtype=np.int64)
+    l.L_br(P(m.minc), P(m.mcode), P(m.jcode), P(jcode_fsi), P(m.nnorm), P(m.tarea), P(Lm), P(A), P(G))
+    s = RefState(m)
+    ss, ss_fsi, sm, sm_fsi = z(n * n), z(n * n), z(n * n), z(n * n)
+    fdens = np.array([m.fdens], dtype=np.float64)
+    l.stiff_fsi(P(m.minc), P(m.mcode), P(m.jcode), P(m.nnorm), P(m.tarea), P(s.farea), P(m.thick), P(s.deffarea),
+                P(s.slength), P(s.defslen), P(Lm), P(A), P(ss), P(ss_fsi), P(s.x), P(m.xlocal), P(m.emod), P(m.nu),
+                P(s.Jinv), P(s.jac), P(m.yld), P(s.c1), P(s.c2), P(s.c3), P(s.ef), P(s.d), P(s.chi), P(s.efN),
+                P(s.efM), P(m.maxa if m.maxa is not None else np.zeros(n + 1, dtype=np.int64)))
+    l.mass_fsi(P(m.minc), P(m.mcode), P(m.jcode), P(m.nnorm), P(m.tarea), P(m.carea), P(s.farea), P(m.thick),
+               P(s.slength), P(Lm), P(LT), P(sm), P(sm_fsi), P(s.x), P(m.dens), P(fdens), P(s.Jinv), P(s.jac))
+    l.ref_set_flags(C.c_int(m.ANAFLAG), C.c_int(m.ALGFLAG), C.c_int(m.SLVFLAG), C.c_int(1))
+    return ss_fsi.reshape(n, n), sm_fsi.reshape(n, n)

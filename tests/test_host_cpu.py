@@ -20,7 +20,7 @@ def test_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert set(cb.EXPORTS) <= set(declared)
-    assert lib.cb_abi_version() == int(re.search(r"#define CB_ABI_VERSION (\d+)", hdr).group(1)) == 3
+    assert lib.cb_abi_version() == int(re.search(r"#define CB_ABI_VERSION (\d+)", hdr).group(1)) == 4
 
 
 def test_no_cpu_fallback():
@@ -390,3 +390,15 @@ def test_symmetric_handoff_host_side(kind):
                                 unionjack=kind == "unionjack")
         own = {"partition_lo": (0, 900), "partition_mid": (300, 1500), "partition_hi": (1500, m.NJ)}.get(kind, (0, 0))
     assert cb.sym_selftest(m, own[0], own[1], nthreads=3) >= 0.0
+
+
+@pytest.mark.parametrize("skin", [False, True])
+def test_fsi_plan_selfcheck(skin):
+    """ANAFLAG 4: pressure twins + the coupling element go through the same plan builder / interpreter"""
+    import cubens_b200 as cb
+    from cubens_b200 import meshgen
+    m = meshgen.fsi_model(5, 4, 2, 3, skin=skin, distort=0.1)
+    st = cb.plan_selfcheck(m)
+    assert st["nnz"] > 0 and st["tiles"] > 0
+    # block pattern: structure block columns hold the wet joint's pressure row and vice versa
+    assert st["nnz"] < 90 * m.NEQ

@@ -22,6 +22,9 @@
 #ifndef CB_TPB
 #define CB_TPB 128
 #endif
+#ifndef CB_FORCES_RECOMPUTE_KEB
+#define CB_FORCES_RECOMPUTE_KEB 1 // shells without a geometry class: ke_b * ddb as alpha W (alpha^T ddb) from 11 constants
+#endif                            // per shell instead of streaming the cached 81-entry matrix (648 B / shell / iteration)
 #ifndef CB_FORCES_STAGE_KEB
 #define CB_FORCES_STAGE_KEB 0     // 1: per-element DKT matrix staged by cp.async (see k_shell_forces)
 #endif
@@ -61,7 +64,8 @@ __device__ __forceinline__ double cube_rn(double x)
 // ------------------------------------------------------------------------------------------
 // DKT plate-bending stiffness, Batoz explicit form (shell.c:533-658).  ke_b[9][9] row-major.
 // ------------------------------------------------------------------------------------------
-__device__ void dkt_alpha_T(const double *sc, double aT[9][9])
+template <class Store>
+__device__ __forceinline__ void dkt_alpha_T_gen(const double *sc, Store st)
 {
     const double X2 = sc[5], X3 = sc[6], Y3 = sc[7];
     const double x23 = X2 - X3;
@@ -76,48 +80,86 @@ __device__ void dkt_alpha_T(const double *sc, double aT[9][9])
     const double r4 = 3 * (Y3 * Y3) / l23;
     const double r5 = 3 * (Y3 * Y3) / l31;
     // transpose of Batoz' alpha (rows = w, theta_x, theta_y of vertices 1, 2, 3)
-    aT[0][0] = Y3 * p6;        aT[0][1] = -(Y3 * p6);      aT[0][2] = Y3 * p5;
-    aT[0][3] = -(X2 * t5);     aT[0][4] = 0;               aT[0][5] = x23 * t5;
-    aT[0][6] = -(X3 * p6) - X2 * p5;  aT[0][7] = -x23 * p6;  aT[0][8] = x23 * p5 + Y3 * t5;
+    st(0, 0, Y3 * p6);        st(0, 1, -(Y3 * p6));      st(0, 2, Y3 * p5);
+    st(0, 3, -(X2 * t5));     st(0, 4, 0);               st(0, 5, x23 * t5);
+    st(0, 6, -(X3 * p6) - X2 * p5);  st(0, 7, -x23 * p6);  st(0, 8, x23 * p5 + Y3 * t5);
 
-    aT[1][0] = 0;              aT[1][1] = 0;               aT[1][2] = -(Y3 * q5);
-    aT[1][3] = x23 + X2 * r5;  aT[1][4] = x23;             aT[1][5] = x23 * (1 - r5);
-    aT[1][6] = X2 * q5 + Y3;   aT[1][7] = Y3;              aT[1][8] = -x23 * q5 + Y3 * (1 - r5);
+    st(1, 0, 0);              st(1, 1, 0);               st(1, 2, -(Y3 * q5));
+    st(1, 3, x23 + X2 * r5);  st(1, 4, x23);             st(1, 5, x23 * (1 - r5));
+    st(1, 6, X2 * q5 + Y3);   st(1, 7, Y3);              st(1, 8, -x23 * q5 + Y3 * (1 - r5));
 
-    aT[2][0] = -4 * Y3;        aT[2][1] = 2 * Y3;          aT[2][2] = Y3 * (2 - r5);
-    aT[2][3] = -(X2 * q5);     aT[2][4] = 0;               aT[2][5] = x23 * q5;
-    aT[2][6] = -4 * x23 + X2 * r5;  aT[2][7] = 2 * x23;    aT[2][8] = x23 * (2 - r5) + Y3 * q5;
+    st(2, 0, -4 * Y3);        st(2, 1, 2 * Y3);          st(2, 2, Y3 * (2 - r5));
+    st(2, 3, -(X2 * q5));     st(2, 4, 0);               st(2, 5, x23 * q5);
+    st(2, 6, -4 * x23 + X2 * r5);  st(2, 7, 2 * x23);    st(2, 8, x23 * (2 - r5) + Y3 * q5);
 
-    aT[3][0] = -(Y3 * p6);     aT[3][1] = Y3 * p6;         aT[3][2] = Y3 * p4;
-    aT[3][3] = 0;              aT[3][4] = X2 * t4;         aT[3][5] = -(X3 * t4);
-    aT[3][6] = X3 * p6;        aT[3][7] = x23 * p6 + X2 * p4;  aT[3][8] = -(X3 * p4) + Y3 * t4;
+    st(3, 0, -(Y3 * p6));     st(3, 1, Y3 * p6);         st(3, 2, Y3 * p4);
+    st(3, 3, 0);              st(3, 4, X2 * t4);         st(3, 5, -(X3 * t4));
+    st(3, 6, X3 * p6);        st(3, 7, x23 * p6 + X2 * p4);  st(3, 8, -(X3 * p4) + Y3 * t4);
 
-    aT[4][0] = 0;              aT[4][1] = 0;               aT[4][2] = Y3 * q4;
-    aT[4][3] = X3;             aT[4][4] = X3 + X2 * r4;    aT[4][5] = X3 * (1 - r4);
-    aT[4][6] = -Y3;            aT[4][7] = -Y3 + X2 * q4;   aT[4][8] = Y3 * (r4 - 1) - X3 * q4;
+    st(4, 0, 0);              st(4, 1, 0);               st(4, 2, Y3 * q4);
+    st(4, 3, X3);             st(4, 4, X3 + X2 * r4);    st(4, 5, X3 * (1 - r4));
+    st(4, 6, -Y3);            st(4, 7, -Y3 + X2 * q4);   st(4, 8, Y3 * (r4 - 1) - X3 * q4);
 
-    aT[5][0] = -2 * Y3;        aT[5][1] = 4 * Y3;          aT[5][2] = Y3 * (r4 - 2);
-    aT[5][3] = 0;              aT[5][4] = -(X2 * q4);      aT[5][5] = X3 * q4;
-    aT[5][6] = 2 * X3;         aT[5][7] = -4 * X3 + X2 * r4;  aT[5][8] = X3 * (2 - r4) - Y3 * q4;
+    st(5, 0, -2 * Y3);        st(5, 1, 4 * Y3);          st(5, 2, Y3 * (r4 - 2));
+    st(5, 3, 0);              st(5, 4, -(X2 * q4));      st(5, 5, X3 * q4);
+    st(5, 6, 2 * X3);         st(5, 7, -4 * X3 + X2 * r4);  st(5, 8, X3 * (2 - r4) - Y3 * q4);
 
-    aT[6][0] = 0;              aT[6][1] = 0;               aT[6][2] = -(Y3 * (p4 + p5));
-    aT[6][3] = X2 * t5;        aT[6][4] = -(X2 * t4);      aT[6][5] = -x23 * t5 + X3 * t4;
-    aT[6][6] = X2 * p5;        aT[6][7] = -(X2 * p4);
-    aT[6][8] = -x23 * p5 + X3 * p4 - Y3 * (t4 + t5);
+    st(6, 0, 0);              st(6, 1, 0);               st(6, 2, -(Y3 * (p4 + p5)));
+    st(6, 3, X2 * t5);        st(6, 4, -(X2 * t4));      st(6, 5, -x23 * t5 + X3 * t4);
+    st(6, 6, X2 * p5);        st(6, 7, -(X2 * p4));
+    st(6, 8, -x23 * p5 + X3 * p4 - Y3 * (t4 + t5));
 
-    aT[7][0] = 0;              aT[7][1] = 0;               aT[7][2] = Y3 * (q4 - q5);
-    aT[7][3] = X2 * (r5 - 1);  aT[7][4] = X2 * (r4 - 1);   aT[7][5] = -x23 * r5 - X3 * r4 - X2;
-    aT[7][6] = X2 * q5;        aT[7][7] = X2 * q4;
-    aT[7][8] = -x23 * q5 - X3 * q4 + Y3 * (r4 - r5);
+    st(7, 0, 0);              st(7, 1, 0);               st(7, 2, Y3 * (q4 - q5));
+    st(7, 3, X2 * (r5 - 1));  st(7, 4, X2 * (r4 - 1));   st(7, 5, -x23 * r5 - X3 * r4 - X2);
+    st(7, 6, X2 * q5);        st(7, 7, X2 * q4);
+    st(7, 8, -x23 * q5 - X3 * q4 + Y3 * (r4 - r5));
 
-    aT[8][0] = 0;              aT[8][1] = 0;               aT[8][2] = Y3 * (r4 - r5);
-    aT[8][3] = -(X2 * q5);     aT[8][4] = -(X2 * q4);      aT[8][5] = X3 * q4 + x23 * q5;
-    aT[8][6] = X2 * (r5 - 2);  aT[8][7] = X2 * (r4 - 2);
-    aT[8][8] = -x23 * r5 - X3 * r4 + 4 * X2 + Y3 * (q5 - q4);
+    st(8, 0, 0);              st(8, 1, 0);               st(8, 2, Y3 * (r4 - r5));
+    st(8, 3, -(X2 * q5));     st(8, 4, -(X2 * q4));      st(8, 5, X3 * q4 + x23 * q5);
+    st(8, 6, X2 * (r5 - 2));  st(8, 7, X2 * (r4 - 2));
+    st(8, 8, -x23 * r5 - X3 * r4 + 4 * X2 + Y3 * (q5 - q4));
 }
 
+__device__ void dkt_alpha_T(const double *sc, double aT[9][9])
+{
+    dkt_alpha_T_gen(sc, [&](int i, int j, double v) { aT[i][j] = v; });
+}
 __device__ __forceinline__ void plane_stress(double E, double nu, double &C00, double &C01, double &C22);
 __device__ __forceinline__ void membrane_B(const double *sc, double A, double Bm[3][6]);
+
+// membrane data of a shell that never changes: the three columns of ke_m (shell.c:487-531) that the membrane
+// displacement vector dm = (0,0,dm2,0,dm4,dm5) multiplies [0..17], the plane-stress coefficients [18..20] and
+// t*A0*C/(2 A0)^2 [21..23]
+__device__ __forceinline__ void shell_der(const double *sc, double *der)
+{
+    double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    plane_stress(sc[0], sc[1], C[0][0], C[0][1], C[2][2]);
+    C[1][1] = C[0][0]; C[1][0] = C[0][1];
+    double Bm[3][6];
+    membrane_B(sc, sc[4], Bm);
+    const int col[3] = {2, 4, 5};
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double BC[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {           // Bm_C[i][j] (shell.c:513-521)
+            double sum = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) sum += Bm[k][i] * C[k][j];
+            BC[j] = sum;
+        }
+#pragma unroll
+        for (int jc = 0; jc < 3; ++jc) {
+            double sum = 0;                      // ke_m[i][j] (shell.c:522-530)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) sum += BC[k] * Bm[k][col[jc]];
+            der[i * 3 + jc] = sc[2] * sc[4] * sum;
+        }
+    }
+    der[18] = C[0][0]; der[19] = C[0][1]; der[20] = C[2][2];
+    const double smc = sc[2] / (4 * sc[4]);
+    der[21] = smc * C[0][0]; der[22] = smc * C[0][1]; der[23] = smc * C[2][2];
+}
 
 __global__ void __launch_bounds__(CB_TPB)
 k_shell_init_keb(CbDev d, double *__restrict__ keb)
@@ -153,32 +195,9 @@ k_shell_init_keb(CbDev d, double *__restrict__ keb)
             for (int k = 0; k < 9; ++k) sum += Q[i][k] * aT[j][k];
             SOA(keb, CB_KEB(i, j), e, d.NE_SH) = sum / (2 * A0);
         }
-    // membrane: the three columns of ke_m (shell.c:487-531) that the membrane displacement vector
-    // dm = (0,0,dm2,0,dm4,dm5) multiplies, the plane-stress coefficients and t*A0*C/(2 A0)^2
-    double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    plane_stress(sc[0], sc[1], C[0][0], C[0][1], C[2][2]);
-    C[1][1] = C[0][0]; C[1][0] = C[0][1];
-    double Bm[3][6];
-    membrane_B(sc, sc[4], Bm);
-    const int col[3] = {2, 4, 5};
-    for (int i = 0; i < 6; ++i) {
-        double BC[3];
-        for (int j = 0; j < 3; ++j) {           // Bm_C[i][j] (shell.c:513-521)
-            double sum = 0;
-            for (int k = 0; k < 3; ++k) sum += Bm[k][i] * C[k][j];
-            BC[j] = sum;
-        }
-        for (int jc = 0; jc < 3; ++jc) {
-            double sum = 0;                      // ke_m[i][j] (shell.c:522-530)
-            for (int k = 0; k < 3; ++k) sum += BC[k] * Bm[k][col[jc]];
-            SOA(d.sh_der, i * 3 + jc, e, d.NE_SH) = sc[2] * sc[4] * sum;
-        }
-    }
-    SOA(d.sh_der, 18, e, d.NE_SH) = C[0][0]; SOA(d.sh_der, 19, e, d.NE_SH) = C[0][1];
-    SOA(d.sh_der, 20, e, d.NE_SH) = C[2][2];
-    const double smc = sc[2] / (4 * sc[4]);
-    SOA(d.sh_der, 21, e, d.NE_SH) = smc * C[0][0]; SOA(d.sh_der, 22, e, d.NE_SH) = smc * C[0][1];
-    SOA(d.sh_der, 23, e, d.NE_SH) = smc * C[2][2];
+    double der[CB_SH_DER];
+    shell_der(sc, der);
+    for (int i = 0; i < CB_SH_DER; ++i) SOA(d.sh_der, i, e, d.NE_SH) = der[i];
 }
 
 int cbk_shell_init_keb(const CbDev &d, double *keb_out, cudaStream_t s)
@@ -510,8 +529,11 @@ __device__ __forceinline__ void shell_triad(const double *xj, const double *xk, 
 #endif                            // per-element matrices: HBM-bound, 2 CTAs with 254 registers measure faster
 // FUSE: x_temp holds the coordinates BEFORE this iteration's update; the kernel forms x + dd itself and
 // the first shell at a joint writes the result to x_new (CbForceArgs::fuse_node)
+#ifndef CB_FORCES_CTAS_NOCLS
+#define CB_FORCES_CTAS_NOCLS 3
+#endif
 template <bool CLS, bool FUSE>
-__global__ void __launch_bounds__(CB_TPB, CLS ? CB_FORCES_CTAS : 2)
+__global__ void __launch_bounds__(CB_TPB, CLS ? CB_FORCES_CTAS : CB_FORCES_CTAS_NOCLS)
 k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restrict__ dd,
                const double *__restrict__ frame_ip, double *__restrict__ frame_i,
                double *__restrict__ dsl_i, const double *__restrict__ ef_ip,
@@ -526,7 +548,9 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
     const bool live = e < d.NE_SH;
     double kr[CB_SH_KREC];
     double *mycol = sbuf + threadIdx.x;
-    constexpr int KOFF = (CLS || !CB_FORCES_STAGE_KEB) ? 0 : 81;   // first column of the staged ef_ip
+    constexpr bool RECOMP = !CLS && CB_FORCES_RECOMPUTE_KEB;
+    constexpr bool STAGE = !CLS && CB_FORCES_STAGE_KEB && !RECOMP;
+    constexpr int KOFF = STAGE ? 81 : 0;                           // first column of the staged ef_ip
     // geometry-constant data: per element, or one L1-resident copy per geometry class
     const double *kebsrc = nullptr, *der = nullptr;
     long kstr = 0, dstr = 0;
@@ -545,7 +569,7 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
         // per-element matrix: staged in this thread's column.  Class table: read in place later -
         // the lanes of a warp mostly share a class, so those loads are L1 broadcasts, whereas
         // 81 private copies per thread would saturate the L1 data pipe with identical bytes.
-        if (!CLS && CB_FORCES_STAGE_KEB) {
+        if (STAGE) {
 #pragma unroll
         for (int c = 0; c < 81; ++c)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + c * CB_TPB * 8),
@@ -553,8 +577,9 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
         }
 #pragma unroll
         for (int c = 0; c < 18; ++c)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + (KOFF + c) * CB_TPB * 8),
-                         "l"(ef_ip + (long)c * d.NE_SH + e));
+            if (c % 6 >= 2)                     // the membrane slots of ef_ip are dropped (shell.c:1773)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + (KOFF + c) * CB_TPB * 8),
+                             "l"(ef_ip + (long)c * d.NE_SH + e));
         asm volatile("cp.async.commit_group;");
     }
     if (live) {
@@ -562,6 +587,11 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
     sc[2] = __ldg(&SOA(d.sh_const, 2, e, d.NE_SH));               // thickness
 #pragma unroll
     for (int i = 5; i < 8; ++i) sc[i] = __ldg(&SOA(d.sh_const, i, e, d.NE_SH));   // x2, x3, y3
+    if (RECOMP) {
+#pragma unroll
+        for (int i = 0; i < 11; ++i)
+            if (i != 2 && (i < 5 || i > 7)) sc[i] = __ldg(&SOA(d.sh_const, i, e, d.NE_SH));
+    }
 #pragma unroll
     for (int i = 0; i < CB_SH_FRAME; ++i) Rp[i] = __ldg(&SOA(frame_ip, i, e, d.NE_SH));
     const int4 nd = reinterpret_cast<const int4 *>(d.sh_nodes)[e];
@@ -597,10 +627,12 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
     membrane_dm(X[0], X[1], X[2], Ri, sc, dm2, dm4, dm5);
     // record for the next stiffness pass: after `_ip <- _i` this triad / area / dm are exactly
     // what stiff_sh evaluates (shell.c:159-171)
+    double derl[RECOMP ? CB_SH_DER : 1];
+    if (RECOMP) shell_der(sc, derl);          // same operations as k_shell_init_keb: the cached values bit for bit
     {
         double cst[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) cst[i] = __ldg(der + (18 + i) * dstr);
+        for (int i = 0; i < 6; ++i) cst[i] = RECOMP ? derl[RECOMP ? 18 + i : 0] : __ldg(der + (18 + i) * dstr);
         shell_krec(sc[5], sc[6], sc[7], sc[2], Ri, cst, dm2, dm4, dm5, d.ANAFLAG, kr);
     }
     // ke_m * dm with the geometry-constant membrane columns (shell.c:1767-1775): the structural
@@ -609,9 +641,9 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         double acc = 0;
-        acc += __ldg(der + (i * 3 + 0) * dstr) * dm2;
-        acc += __ldg(der + (i * 3 + 1) * dstr) * dm4;
-        acc += __ldg(der + (i * 3 + 2) * dstr) * dm5;
+        acc += (RECOMP ? derl[RECOMP ? i * 3 + 0 : 0] : __ldg(der + (i * 3 + 0) * dstr)) * dm2;
+        acc += (RECOMP ? derl[RECOMP ? i * 3 + 1 : 0] : __ldg(der + (i * 3 + 1) * dstr)) * dm4;
+        acc += (RECOMP ? derl[RECOMP ? i * 3 + 2 : 0] : __ldg(der + (i * 3 + 2) * dstr)) * dm5;
         ef_temp[i] = acc;
     }
 
@@ -624,15 +656,39 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
         ddb[3 * a + 2] = dot3(Rp + 3, DD[a] + 3);    // theta_y : c2_ip . rotations
     }
     double defb[9];
+    if (RECOMP) {
+        // ke_b = alpha W alpha^T / (2 A0) (shell.c:610-658: Q = alpha W, ke_b = Q alpha^T / (2 A0)), so
+        // ke_b ddb = alpha (W (alpha^T ddb)) / (2 A0): the entries of alpha are closed forms of six lengths and
+        // are evaluated in registers for both products; W is the closed form of the three row blocks of
+        // shell.c:610-648
+        double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, u[9];
+        dkt_alpha_T_gen(sc, [&](int i, int j, double a) { v[j] += a * ddb[i]; });      // v = alpha^T ddb
+        const double D0 = sc[0] * sc[3] / (12 * (1 - sc[1] * sc[1]));
+        const double E1 = D0, E2 = D0 * sc[1], E4 = D0 * (1 - sc[1]) / 2;
+        const double s0 = v[0] + v[1] + v[2], s1 = v[3] + v[4] + v[5], s2 = v[6] + v[7] + v[8];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            u[j] = (E1 * (v[j] + s0) + E2 * (v[j + 3] + s1)) / 24;
+            u[j + 3] = (E2 * (v[j] + s0) + E1 * (v[j + 3] + s1)) / 24;
+            u[j + 6] = (E4 * (v[j + 6] + s2)) / 24;
+        }
+        const double inv2A = 1.0 / (2 * sc[4]);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) defb[i] = 0;
+        dkt_alpha_T_gen(sc, [&](int i, int j, double a) { defb[i] += a * u[j]; });     // alpha u
+#pragma unroll
+        for (int i = 0; i < 9; ++i) defb[i] *= inv2A;
+    }
     asm volatile("cp.async.wait_group 0;" ::: "memory");      // own copies only: no barrier needed
+    if (!RECOMP) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
         double sum = 0;
 #pragma unroll
         for (int j = 0; j < 9; ++j)
-            sum += ((CLS || !CB_FORCES_STAGE_KEB) ? __ldg(kebsrc + CB_KEB(i, j) * kstr)
-                                                  : mycol[CB_KEB(i, j) * CB_TPB]) * ddb[j];
+            sum += (!STAGE ? __ldg(kebsrc + CB_KEB(i, j) * kstr) : mycol[CB_KEB(i, j) * CB_TPB]) * ddb[j];
         defb[i] = sum;
+    }
     }
     double efp[18];
 #pragma unroll
@@ -1586,7 +1642,7 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
         unsigned g = (unsigned)((d.NE_SH + CB_TPB - 1) / CB_TPB);
         // staged columns per thread (ef_ip, + the DKT matrix when CB_FORCES_STAGE_KEB) or the krec
         // transposition tile, whichever is larger
-        const size_t cols = CB_FORCES_STAGE_KEB ? 99 : 18;
+        const size_t cols = (CB_FORCES_STAGE_KEB && !CB_FORCES_RECOMPUTE_KEB) ? 99 : 18;
         const size_t smem = std::max(cols * CB_TPB, (size_t)(CB_TPB / 32) * 32 * (CB_SH_KREC + 1)) * sizeof(double);
         static CbPerDevice cfg{};
         int &configured = cfg.v[cb_device_slot()];

@@ -44,6 +44,7 @@ int main(int argc, char **argv)
     m.gmod = rd(f, &n, 8); m.istrong = rd(f, &n, 8); m.iweak = rd(f, &n, 8); m.ipolar = rd(f, &n, 8); m.iwarp = rd(f, &n, 8);
     m.auxpt = rd(f, &n, 8); m.offset = rd(f, &n, 8); m.osflag = rd(f, &n, 4); m.mendrel = rd(f, &n, 4); m.efFE_ref = rd(f, &n, 8);
     m.yield = rd(f, &n, 8); m.zstrong = rd(f, &n, 8); m.zweak = rd(f, &n, 8);
+    m.nnorm = rd(f, &n, 8); m.tarea = rd(f, &n, 8); m.fdens = rd(f, &n, 8);
     double *q = rd(f, &n, 8), *dd = rd(f, &n, 8), lpf = 0;
     if (fread(&lpf, sizeof lpf, 1, f) != 1) return 2;
     fclose(f);

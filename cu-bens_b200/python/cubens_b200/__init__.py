@@ -111,6 +111,17 @@ def _p(a):
     return C.c_void_p(a.ctypes.data) if a is not None and a.size else C.c_void_p(0)
 
 
+def _model_array(m, n):
+    """the array behind cb_model field ``n`` of a Model in the C dtype, or None"""
+    a = getattr(m, "yld" if n == "yield" else n, None)
+    if n == "fdens":
+        a = np.array([a], dtype=np.float64) if getattr(m, "nnorm", None) is not None else None
+    if a is None:
+        return None
+    dt = np.int32 if n in ("osflag", "mendrel") else (np.int64 if n in ("minc", "jcode", "mcode", "maxa") else np.float64)
+    return np.ascontiguousarray(a, dtype=dt)
+
+
 def _c_model(m, layout, device):
     """the C structs of include/cubens_b200.h for a Model (plus the arrays that must stay alive)"""
     sz = cb_sizes(m.NJ, m.NE_TR, m.NE_FR, m.NE_SH, m.NE_SBR, m.NE_FBR, m.NEQ)
@@ -118,12 +129,8 @@ def _c_model(m, layout, device):
     keep = {}
     cm = cb_model()
     for n in _MODEL_FIELDS:
-        a = getattr(m, "yld" if n == "yield" else n, None)
-        if n == "fdens":
-            a = np.array([a], dtype=np.float64) if getattr(m, "nnorm", None) is not None else None
+        a = _model_array(m, n)
         if a is not None:
-            dt = np.int32 if n in ("osflag", "mendrel") else (np.int64 if n in ("minc", "jcode", "mcode", "maxa") else np.float64)
-            a = np.ascontiguousarray(a, dtype=dt)
             keep[n] = a
         setattr(cm, n, _p(a) if a is not None else C.c_void_p(0))
     return sz, fl, cm, keep

@@ -181,17 +181,15 @@ def write_submodel(path, m, owned, q, dd, lpf, layout=1, device=0):
     """binary image of a (sub-)model for the C host cu-bens_b200/host/cb_multi_gpu_demo.c: cb_sizes, cb_flags,
     owned joint range, every cb_model array as (count, data) in the struct's order, q, dd, lpf"""
     import struct
-    from . import _MODEL_FIELDS
+    from . import _MODEL_FIELDS, _model_array
     with open(path, "wb") as f:
         f.write(struct.pack("7l", m.NJ, m.NE_TR, m.NE_FR, m.NE_SH, m.NE_SBR, m.NE_FBR, m.NEQ))
         f.write(struct.pack("5i", m.ANAFLAG, m.ALGFLAG, m.SLVFLAG, layout, device))
         f.write(struct.pack("2l", *(owned if owned is not None else (0, m.NJ))))
         for n in _MODEL_FIELDS:
-            a = getattr(m, "yld" if n == "yield" else n, None)
-            if a is None or np.size(a) == 0:
+            a = _model_array(m, n)
+            if a is None or a.size == 0:
                 f.write(struct.pack("l", 0)); continue
-            dt = np.int32 if n in ("osflag", "mendrel") else (np.int64 if n in ("minc", "jcode", "mcode", "maxa") else np.float64)
-            a = np.ascontiguousarray(a, dtype=dt)
             f.write(struct.pack("l", a.size)); f.write(a.tobytes())
         for v in (q, dd):
             v = np.ascontiguousarray(v, dtype=np.float64)

@@ -79,10 +79,14 @@ def test_fullsize_properties(gpu):
         r = K @ t
         rows = jc[inner][:, :6].reshape(-1) - 1
         assert np.abs(r[rows]).max() <= 1e-9 * scale, c
-    # geometry classes off: bit-identical
+    # geometry classes off: K_t bit-identical (same cached DKT blocks); the force pass of class-less shells
+    # evaluates ke_b ddb as alpha W (alpha^T ddb) instead of reading the matrix: same value to rounding
     b, Axb, fb = _state(m, no_classes=True)
     assert b.geometry_classes == 0
-    assert np.array_equal(Axb, Ax) and np.array_equal(fb, f) and np.array_equal(b.download("EF_I"), ef)
+    assert np.array_equal(Axb, Ax)
+    assert np.abs(fb - f).max() <= 1e-12 * np.abs(f).max()
+    efb = b.download("EF_I")
+    assert np.abs(efb - ef).max() <= 1e-12 * np.abs(ef).max()
     b.close()
     del Axb, K
     # partition invariance (strong split in two, rank 1's owned slice)

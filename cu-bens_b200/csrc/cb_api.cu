@@ -963,8 +963,9 @@ static int build_plan(cb_handle *h)
     std::vector<int32_t> blkS;                // pairs_csc index of every pair record (plan check)
     const char *kt_env = getenv("CB_KT");
     bool planS_ok = plan2_ok && !(kt_env && strcmp(kt_env, "duo") == 0);
-    const CbStreamShape shapes[2] = {CB_S_SHAPE_WIDE, CB_S_SHAPE_NARROW};
-    const int shape_id = (kt_env && strcmp(kt_env, "wide") == 0) ? 0 : 1;
+    const CbStreamShape shapes[5] = {CB_S_SHAPE_WIDE, CB_S_SHAPE_NARROW, CB_S_SHAPE_MINI, CB_S_SHAPE_NARROW12, CB_S_SHAPE_MINI};
+    // default: the narrow plan on 12 warps (CB_KT = wide | narrow | mini | mini16 select the other compiled kernels)
+    const int shape_id = !kt_env ? 3 : (strcmp(kt_env, "wide") == 0 ? 0 : (strcmp(kt_env, "narrow") == 0 ? 1 : (strcmp(kt_env, "mini") == 0 ? 2 : (strcmp(kt_env, "mini16") == 0 ? 4 : 3))));
     const CbStreamShape shp = shapes[shape_id];
     if (planS_ok) {
         // tile packing: cb_plan_pack.h (shared with the device-side planner), segment by segment

@@ -155,6 +155,8 @@ struct CbStreamShape {
 #define CB_S_MAXSTEPS_ANY 6       // the larger S of the two shapes
 #define CB_S_SHAPE_WIDE   {2560, 44, 6, 80, 6}
 #define CB_S_SHAPE_NARROW {1536, 28, 4, 48, 8}
+#define CB_S_SHAPE_MINI   {1024, 20, 3, 32, 12}      // 12 warps / SM at 168 registers (no register prefetches)
+#define CB_S_SHAPE_NARROW12 {1536, 28, 4, 48, 12}    // the narrow plan, 12 warps with single record buffers
 struct CbTileS {
     int64_t out0;     // first Ax index of the tile's contiguous output range
     int32_t nout;

@@ -150,8 +150,9 @@ static int build_plan_device(cb_handle *h)
     if (SH * 9 > 0x7fffffffL || NJ >= (1L << 31)) return -1;
     const auto t_begin = std::chrono::steady_clock::now();
     cudaStream_t s = h->stream;
-    const CbStreamShape shapes[2] = {CB_S_SHAPE_WIDE, CB_S_SHAPE_NARROW};
-    const int shape_id = (kt_env && strcmp(kt_env, "wide") == 0) ? 0 : 1;
+    const CbStreamShape shapes[5] = {CB_S_SHAPE_WIDE, CB_S_SHAPE_NARROW, CB_S_SHAPE_MINI, CB_S_SHAPE_NARROW12, CB_S_SHAPE_MINI};
+    // default: the narrow plan on 12 warps (CB_KT = wide | narrow | mini | mini16 select the other compiled kernels)
+    const int shape_id = !kt_env ? 3 : (strcmp(kt_env, "wide") == 0 ? 0 : (strcmp(kt_env, "narrow") == 0 ? 1 : (strcmp(kt_env, "mini") == 0 ? 2 : (strcmp(kt_env, "mini16") == 0 ? 4 : 3))));
     const CbStreamShape shp = shapes[shape_id];
 #define DP_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(CB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } while (0)
 

@@ -1097,12 +1097,12 @@ static int launch_shell_tiles(const CbStiffArgs &a, cudaStream_t s)
 #ifndef CB_S_NARROW_WARPS
 #define CB_S_NARROW_WARPS 8
 #endif
-template <int IMG, int SLOTS, int S, int PAIRS>
+template <int IMG, int SLOTS, int S, int PAIRS, int NBUF = 2>
 struct SLayout {
     static constexpr int IMG_BYTES = (IMG + 2) * 8;
-    static constexpr int KREC_BYTES = 2 * SLOTS * CB_SH_KREC * 8;
-    static constexpr int REC_BYTES = 2 * S * 32 * 4;
-    static constexpr int PAIR_BYTES = 2 * PAIRS * 4;
+    static constexpr int KREC_BYTES = NBUF * SLOTS * CB_SH_KREC * 8;
+    static constexpr int REC_BYTES = NBUF * S * 32 * 4;
+    static constexpr int PAIR_BYTES = NBUF * PAIRS * 4;
     static constexpr int WARP_BYTES = IMG_BYTES + KREC_BYTES + REC_BYTES + PAIR_BYTES;
     static_assert(WARP_BYTES % 16 == 0 && IMG_BYTES % 16 == 0 && PAIRS % 4 == 0, "16-byte aligned regions");
 };
@@ -1257,22 +1257,29 @@ __device__ __forceinline__ void s_store_block(double *obuf, int shift, uint32_t 
 
 // registers: one CTA per SM of at most 8 warps, so every thread may use the full 255 (the register file is
 // handed out to warps in groups of four: 10 warps would be budgeted like 12, 168 registers, and spill)
-template <int IMG, int SLOTS, int S, int PAIRS, int WARPS, bool CLS>
+// NBUF 1: one set of record buffers per warp - the next tile's records are requested when this tile's last
+// step has read them (their latency is hidden by the other warps, not by the tile's own arithmetic)
+template <int IMG, int SLOTS, int S, int PAIRS, int WARPS, bool CLS, int NBUF = 2>
 __global__ void __launch_bounds__(32 * WARPS, 1)
 k_assemble_shell_stream(CbStiffArgs A)
 {
-    using L = SLayout<IMG, SLOTS, S, PAIRS>;
+    using L = SLayout<IMG, SLOTS, S, PAIRS, NBUF>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *wbase = smem_raw + (size_t)warp * L::WARP_BYTES;
     double *obuf = reinterpret_cast<double *>(wbase);                                           // [IMG + 2]
     double *skrec = reinterpret_cast<double *>(wbase + L::IMG_BYTES);                           // [2][SLOTS][18]
     uint32_t *srec = reinterpret_cast<uint32_t *>(wbase + L::IMG_BYTES + L::KREC_BYTES);         // [2][S][32]
-    uint32_t *spair = srec + 2 * S * 32;                                                         // [2][PAIRS]
+    uint32_t *spair = srec + NBUF * S * 32;                                                      // [2][PAIRS]
     const long G = (long)gridDim.x * WARPS, N = A.ntilesS;
     long tile = (long)blockIdx.x * WARPS + warp;
     if (tile >= N) return;
     constexpr unsigned FULL = 0xffffffffu;
+    // more than 8 warps per SM leave 168 registers per thread: the register prefetches (next step's shell record,
+    // next tile's first DKT block) go, the extra warps hide those latencies instead
+    constexpr bool LEAN = WARPS > 8;
+    constexpr bool PREK = CB_S_PREK && !LEAN;
+    static_assert(NBUF == 2 || LEAN, "single record buffers go with the lean variant");
 
     // prologue: this tile staged directly; the next tile's record and element ids into registers
     int4 tlr = s_ldg16(A.tilesS + tile), tlr_n = tlr;
@@ -1292,6 +1299,8 @@ k_assemble_shell_stream(CbStiffArgs A)
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         r0n = srec[lane];
+    }
+    if constexpr (!LEAN) {
         if (CLS) {
             const double *k0 = A.d.keb_tab10 + ((r0n >> 20) * 9 + 3 * ((r0n >> 6) & 3) + ((r0n >> 8) & 3)) * 10;
 #pragma unroll
@@ -1313,14 +1322,17 @@ k_assemble_shell_stream(CbStiffArgs A)
     for (;;) {
         const bool has_next = tile + G < N, has_next2 = tile + 2 * G < N;
         // the other buffer was last read by the previous tile (the warp re-converged at its end)
-        if (has_next)
-            s_issue_stage<SLOTS, S, PAIRS>(A, tile + G, eid_n, lane, skrec + (buf ^ 1) * SLOTS * CB_SH_KREC,
-                                           srec + (buf ^ 1) * S * 32, spair + (buf ^ 1) * PAIRS);
-        CB_CPA_COMMIT();
+        if (NBUF == 2) {
+            if (has_next)
+                s_issue_stage<SLOTS, S, PAIRS>(A, tile + G, eid_n, lane, skrec + (buf ^ 1) * SLOTS * CB_SH_KREC,
+                                               srec + (buf ^ 1) * S * 32, spair + (buf ^ 1) * PAIRS);
+            CB_CPA_COMMIT();
+        }
         SEids<SLOTS> eid_nn{};
         int4 tlr_nn = tlr_n;
         if (has_next2) { eid_nn = s_load_eids<SLOTS>(A, tile + 2 * G, lane); tlr_nn = s_ldg16(A.tilesS + tile + 2 * G); }
-        asm volatile("cp.async.wait_group 1;" ::: "memory");       // this tile's records have landed
+        if (NBUF == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");       // this tile's records have landed
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
 
         const long out0 = ((long)(unsigned)tlr.x) | ((long)tlr.y << 32);
@@ -1330,7 +1342,7 @@ k_assemble_shell_stream(CbStiffArgs A)
         const uint32_t *pairs = spair + buf * PAIRS;
         const int shift = (int)((out0 + A.out_par) & 1);
         const double *kbs = CLS ? nullptr : A.kebc + (tile * (S * 9L)) * 32 + lane;
-        if (!CLS && has_next) {                // step 0 of the next tile: its address depends on the tile number only
+        if (!LEAN && !CLS && has_next) {       // step 0 of the next tile: its address depends on the tile number only
             const double *kn0 = A.kebc + ((tile + G) * (S * 9L)) * 32 + lane;
 #pragma unroll
             for (int i = 0; i < 9; ++i)
@@ -1356,13 +1368,17 @@ k_assemble_shell_stream(CbStiffArgs A)
         // step 0's record and DKT block were requested at the end of the previous tile (r0n / kbC); the
         // other step records of the tile go to registers now (rows past nsteps are idle)
         uint32_t rs[S];
-        rs[0] = r0n;
+        rs[0] = LEAN ? rec[0] : r0n;
 #pragma unroll
         for (int st = 1; st < S; ++st) rs[st] = rec[st * 32];
         double kbA[10], kbB[10], krA[CB_SH_KREC], krB[CB_SH_KREC];
+        if constexpr (LEAN) {
+            load_kb(rs[0], 0, kbA);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 10; ++i) kbA[i] = kbC[i];
-        if ((rs[0] & 63u) != CB_S_IDLE) s_load_krec(kr0 + (rs[0] & 63u) * CB_SH_KREC, krA);
+            for (int i = 0; i < 10; ++i) kbA[i] = kbC[i];
+        }
+        if (PREK && (rs[0] & 63u) != CB_S_IDLE) s_load_krec(kr0 + (rs[0] & 63u) * CB_SH_KREC, krA);
         bool pend = false; uint32_t pend_pr = 0;
 #pragma unroll
         for (int st = 0; st < S; ++st) {
@@ -1381,10 +1397,10 @@ k_assemble_shell_stream(CbStiffArgs A)
                     const uint32_t rn = rs[st + 1];         // this one is evaluated
                     if ((rn & 63u) != CB_S_IDLE) {
                         load_kb(rn, st + 1, kbn);
-                        if (CB_S_PREK) s_load_krec(kr0 + (rn & 63u) * CB_SH_KREC, krn);
+                        if (PREK) s_load_krec(kr0 + (rn & 63u) * CB_SH_KREC, krn);
                     }
                 }
-                if (st + 1 == nsteps && has_next) {
+                if (!LEAN && st + 1 == nsteps && has_next) {
                     // last step: the next tile's records have landed long ago - request its first DKT block
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
                     __syncwarp();
@@ -1399,7 +1415,7 @@ k_assemble_shell_stream(CbStiffArgs A)
                     }
                 }
                 if (!idle) {
-                    if (!CB_S_PREK) s_load_krec(kr0 + slot * CB_SH_KREC, kr);
+                    if (!PREK) s_load_krec(kr0 + slot * CB_SH_KREC, kr);
                     s_contrib(kr, kb, (r >> 6) & 3, (r >> 8) & 3, acc);
                 }
                 if (follow) { pend = true; pend_pr = pr; }                  // held until the tile's end
@@ -1416,6 +1432,11 @@ k_assemble_shell_stream(CbStiffArgs A)
         if (__any_sync(FULL, pend)) {          // second parts of the blocks that were cut in two
             __syncwarp();                      // their first parts are in the image
             if (pend) s_store_block<true>(obuf, shift, pend_pr, acc);
+        }
+        if (NBUF == 1) {                       // every lane has read its last record: request the next tile's
+            __syncwarp();
+            if (has_next) s_issue_stage<SLOTS, S, PAIRS>(A, tile + G, eid_n, lane, skrec, srec, spair);
+            CB_CPA_COMMIT();
         }
         // writes of the image (generic proxy) ordered before the copy engine's reads (async proxy)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1435,24 +1456,24 @@ k_assemble_shell_stream(CbStiffArgs A)
         }
         img_busy = true;
         if (!has_next) break;
-        if (!CLS) {
+        if (!LEAN && !CLS) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) kbC[i] = kbN[i];
         }
-        tile += G; tlr = tlr_n; tlr_n = tlr_nn; eid_n = eid_nn; buf ^= 1;
+        tile += G; tlr = tlr_n; tlr_n = tlr_nn; eid_n = eid_nn; if (NBUF == 2) buf ^= 1;
         __syncwarp();
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <int IMG, int SLOTS, int S, int PAIRS, int WARPS, bool CLS>
+template <int IMG, int SLOTS, int S, int PAIRS, int WARPS, bool CLS, int NBUF = 2>
 static int launch_shell_stream_t(const CbStiffArgs &a, cudaStream_t s)
 {
-    const size_t smem = (size_t)WARPS * SLayout<IMG, SLOTS, S, PAIRS>::WARP_BYTES;
+    const size_t smem = (size_t)WARPS * SLayout<IMG, SLOTS, S, PAIRS, NBUF>::WARP_BYTES;
     static CbPerDevice cache{};                      // SM count per device (0: not configured)
     int &nsm = cache.v[cb_device_slot()];
     if (!nsm) {
-        const cudaError_t e = cudaFuncSetAttribute(k_assemble_shell_stream<IMG, SLOTS, S, PAIRS, WARPS, CLS>,
+        const cudaError_t e = cudaFuncSetAttribute(k_assemble_shell_stream<IMG, SLOTS, S, PAIRS, WARPS, CLS, NBUF>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         int dev = 0, n = 148;
@@ -1463,7 +1484,7 @@ static int launch_shell_stream_t(const CbStiffArgs &a, cudaStream_t s)
     long grid = nsm;                                 // persistent: one CTA of WARPS independent warps per SM
     const long need = (a.ntilesS + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
-    k_assemble_shell_stream<IMG, SLOTS, S, PAIRS, WARPS, CLS><<<(unsigned)grid, 32 * WARPS, smem, s>>>(a);
+    k_assemble_shell_stream<IMG, SLOTS, S, PAIRS, WARPS, CLS, NBUF><<<(unsigned)grid, 32 * WARPS, smem, s>>>(a);
     return (int)cudaGetLastError();
 }
 
@@ -1473,6 +1494,12 @@ static int launch_shell_stream(const CbStiffArgs &a, cudaStream_t s)
     const bool cls = a.d.keb_tab != nullptr;
     if (a.shapeS == 0)
         return cls ? launch_shell_stream_t<2560, 44, 6, 80, 6, true>(a, s) : launch_shell_stream_t<2560, 44, 6, 80, 6, false>(a, s);
+    if (a.shapeS == 4)                      // experiment: 16 warps at 128 registers
+        return cls ? launch_shell_stream_t<1024, 20, 3, 32, 16, true, 1>(a, s) : launch_shell_stream_t<1024, 20, 3, 32, 16, false, 1>(a, s);
+    if (a.shapeS == 3)                      // the narrow plan on 12 warps with single record buffers
+        return cls ? launch_shell_stream_t<1536, 28, 4, 48, 12, true, 1>(a, s) : launch_shell_stream_t<1536, 28, 4, 48, 12, false, 1>(a, s);
+    if (a.shapeS == 2)
+        return cls ? launch_shell_stream_t<1024, 20, 3, 32, 12, true>(a, s) : launch_shell_stream_t<1024, 20, 3, 32, 12, false>(a, s);
     return cls ? launch_shell_stream_t<1536, 28, 4, 48, CB_S_NARROW_WARPS, true>(a, s)
                : launch_shell_stream_t<1536, 28, 4, 48, CB_S_NARROW_WARPS, false>(a, s);
 }

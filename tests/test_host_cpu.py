@@ -330,7 +330,7 @@ def test_fp64_probe_needs_a_device():
 @pytest.mark.parametrize("nx,ny,jitter,own", [(1, 1, 0.0, None), (2, 2, 0.0, None), (9, 7, 0.0, None),
                                                (40, 25, 0.0, None), (40, 25, 0.2, None), (60, 40, 0.0, (300, 1500)),
                                                (120, 3, 0.0, None), (3, 120, 0.0, (100, 101))])
-@pytest.mark.parametrize("shape", ["narrow", "wide"])
+@pytest.mark.parametrize("shape", ["narrow", "wide", "mini"])
 def test_stream_plan_interpreter(nx, ny, jitter, own, shape, monkeypatch):
     """the sorted element-to-nonzero map of the shell stream kernel (k_assemble_shell_stream), built on
     the host without a device and walked the way the kernel walks it: every joint-pair block is summed
@@ -342,7 +342,7 @@ def test_stream_plan_interpreter(nx, ny, jitter, own, shape, monkeypatch):
     m = meshgen.plate_model(nx, ny, SLVFLAG=2, jitter=jitter, pinned=nx > 1)
     j0, j1 = own if own else (0, 0)
     st = cb.plan_selfcheck(m, j0, j1)
-    assert st["kind"] == 3 and st["tiles"] >= 1 and st["steps"] == (4 if shape == "narrow" else 6)
+    assert st["kind"] == 3 and st["tiles"] >= 1 and st["steps"] == {"narrow": 4, "wide": 6, "mini": 3}[shape]
     if own is None:
         # nnz of the structural joint-block pattern: sum over joints of nfree(B) * sum of nfree(neighbours)
         jc = (np.asarray(m.jcode).reshape(-1, 7) != 0).sum(axis=1)

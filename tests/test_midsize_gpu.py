@@ -60,7 +60,7 @@ def _walk_csc(m, ref, asm, n_iter=3, scale=1e-4, seed=5):
     return s
 
 
-@pytest.mark.parametrize("shape", ["narrow", "wide"])
+@pytest.mark.parametrize("shape", ["narrow", "wide", "mini", "narrow12"])
 def test_plate_200x60_classes_on(gpu, ref, shape, monkeypatch):
     monkeypatch.setenv("CB_KT", shape)            # both compiled shapes of the stream kernel
     m = meshgen.plate_model(200, 60, SLVFLAG=0)
@@ -72,7 +72,7 @@ def test_plate_200x60_classes_on(gpu, ref, shape, monkeypatch):
     asm.close()
 
 
-@pytest.mark.parametrize("shape", ["narrow", "wide"])
+@pytest.mark.parametrize("shape", ["narrow", "wide", "mini", "narrow12"])
 def test_plate_200x60_jittered_classes_off(gpu, ref, shape, monkeypatch):
     monkeypatch.setenv("CB_KT", shape)
     m = meshgen.plate_model(200, 60, SLVFLAG=0, jitter=0.2, z_bump=0.01)
@@ -83,7 +83,7 @@ def test_plate_200x60_jittered_classes_off(gpu, ref, shape, monkeypatch):
     asm.close()
 
 
-@pytest.mark.parametrize("shape", ["narrow", "wide"])
+@pytest.mark.parametrize("shape", ["narrow", "wide", "mini", "narrow12"])
 def test_plate_unionjack_split_blocks(gpu, ref, shape, monkeypatch):
     """joints with 8 shells around them: diagonal blocks of 8 contributions are cut in two lane parts
     (first part stored, follower part added at the end of the tile)"""

@@ -1134,20 +1134,27 @@ __device__ __forceinline__ SEids<SLOTS> s_load_eids(const CbStiffArgs &A, long t
     return e;
 }
 
-// stage one tile: lane l copies the records of shell slots l, l + 32 (9 x 16 B each; slots past the
-// tile's last shell repeat a valid one), 16-byte chunks of the step records and of the pair records
+// stage one tile: the shell records of the tile's slots are SLOTS x 9 chunks of 16 bytes, chunk q copied by lane
+// q % 32 - consecutive lanes read the consecutive bytes of one 144-byte record and write consecutive shared
+// memory (one lane per SLOT made every request 28 separate sectors and the shared-memory write of each
+// returning sector its own wavefront: 44 % of the kernel's shared-memory wavefronts); the element index of
+// a slot is held by lane slot % 32 (s_load_eids) and fetched by shuffle.  Slots past the tile's last shell
+// repeat a valid one.  Then 16-byte chunks of the step records and of the pair records.
 template <int SLOTS, int S, int PAIRS>
 __device__ __forceinline__ void s_issue_stage(const CbStiffArgs &A, long tile, const SEids<SLOTS> &eid, int lane,
                                               double *krec_dst, uint32_t *rec_dst, uint32_t *pair_dst)
 {
+    constexpr int NCH = SLOTS * 9;
 #pragma unroll
-    for (int h = 0; h < (SLOTS + 31) / 32; ++h) {
-        const int slot = lane + 32 * h;
-        if (slot < SLOTS) {
-            const double *src = A.d.sh_Nm + (long)eid.v[h] * CB_SH_KREC;
-#pragma unroll
-            for (int ch = 0; ch < 9; ++ch) CB_CPA(16, "cg", krec_dst + slot * CB_SH_KREC + ch * 2, src + ch * 2);
+    for (int k = 0; k < (NCH + 31) / 32; ++k) {
+        const int q = lane + 32 * k;
+        const int slot = min(q / 9, SLOTS - 1), ch = q - slot * 9;
+        int e = __shfl_sync(0xffffffffu, eid.v[0], slot & 31);
+        if constexpr (SLOTS > 32) {
+            const int e1 = __shfl_sync(0xffffffffu, eid.v[1], slot & 31);
+            if (slot >= 32) e = e1;
         }
+        if (q < NCH) CB_CPA(16, "cg", krec_dst + q * 2, A.d.sh_Nm + (long)e * CB_SH_KREC + ch * 2);
     }
     const uint32_t *rs = A.stepsS + tile * (S * 32);
 #pragma unroll

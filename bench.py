@@ -301,11 +301,33 @@ def other_configs(cb, meshgen, device, peak):
     k_ms = float(np.median(ks))
     out["brick_skin"] = {
         "workload": f"80^3 8-node bricks + {m.NE_SH} DKT skin shells, NEQ {m.NEQ}, nnz "
-                    f"{a.lib.cb_csc_nnz(a.h)} (BASELINE.json configs[4] shape without the dense FSI "
-                    "coupling of fsi.c, which is out of scope)",
+                    f"{a.lib.cb_csc_nnz(a.h)} (BASELINE.json configs[4] structure without the fluid; "
+                    "linear, assembled once per analysis)",
         "value": m.NE_SBR / (k_ms * 1e-3), "unit": "bricks/s", "ms_stiff": k_ms,
         "ms_consistent_mass": mass_ms,
         "roofline_frac": ALG_BYTES_BR_K * m.NE_SBR / (k_ms * 1e-3) / 1e9 / peak}
+    a.close()
+    # acoustic FSI (fsi.c, ANAFLAG 4): [K L; 0 H] and [M 0; -rho L^T Q] sparse, on one block pattern
+    m = meshgen.fsi_model(64, 64, 32, 32)
+    t0 = time.perf_counter()
+    a = cb.Assembler(m, layout=cb.CB_MAT_CSC, device=device)
+    a.stiff(cb.CB_GEN_COMMITTED); a.sync()
+    setup = time.perf_counter() - t0
+    ks = []
+    for _ in range(3):
+        a.stiff(cb.CB_GEN_COMMITTED); ks.append(a.last_stiff_ms)
+    a._check(a.lib.cb_mass(a.h)); a.sync(); a.timer_start()
+    for _ in range(3):
+        a._check(a.lib.cb_mass(a.h))
+    mass_ms = a.timer_stop_ms() / 3
+    nnz = int(a.lib.cb_csc_nnz(a.h))
+    out["fsi"] = {
+        "workload": f"64x64x(32 solid + 32 fluid) bricks, acoustic FSI (ANAFLAG 4): {m.NE_SBR} solid + {m.NE_FBR} "
+                    f"fluid bricks, {m.SNDOF} structural + {m.FNDOF} pressure equations (BASELINE.json configs[4])",
+        "nnz": nnz, "dense_entries_of_the_reference": int(m.NEQ) ** 2,
+        "ms_stiff_fsi": float(np.median(ks)), "ms_mass_fsi": mass_ms, "create_plan_first_assembly_s": setup,
+        "note": "stiff_fsi / mass_fsi (fsi.c:333-445) build dense NEQ^2 arrays; here both are value arrays on one "
+                "sparse block pattern (pressure DOFs on twin joints, L as a two-joint coupling element)"}
     a.close()
     return out
 
@@ -611,13 +633,15 @@ def run_gpu(a):
     ach = ALG_BYTES_KT * n_local / (k_ms * 1e-3) / 1e9
     traffic = None
     fl_a = fl_f = None
+    fl_src = "profiles/traffic.json"
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            traffic = tj.get("k_assemble_shell_tiles_dram_bytes_per_launch")
-            fl_a = tj.get("k_assemble_shell_tiles_fp64_flops_per_launch")
+            traffic = tj.get("k_assemble_shell_stream_dram_bytes_per_launch")
+            fl_a = tj.get("k_assemble_shell_stream_fp64_flops_per_launch")
             fl_f = tj.get("k_shell_forces_fp64_flops_per_launch")
+            fl_src = tj.get("source", "profiles/traffic.json")
         except Exception:
             traffic = None
     # FP64 side of the roofline (north_star: achieved FP64 FLOP/s against the B200 peak): peak from the
@@ -626,10 +650,10 @@ def run_gpu(a):
     try:
         pk = float(asm_lib.cb_measure_fp64_tflops(local))
         fp64 = {"peak_tflops": pk, "peak_source": "DFMA micro-kernel, this run (cb_measure_fp64_tflops)",
-                "k_assemble_shell_tiles": None if not fl_a else
+                "k_assemble_shell_stream": None if not fl_a else
                 {"executed_flops_per_launch": fl_a, "achieved_tflops": fl_a / (k_ms * 1e-3) / 1e12,
                  "frac": fl_a / (k_ms * 1e-3) / 1e12 / pk},
-                "flops_source": "ncu r01f (dadd + dmul + 2 x dfma thread instructions), profiles/traffic.json"}
+                "flops_source": "dadd + dmul + 2 x dfma thread instructions of the committed ncu capture: " + fl_src}
     except Exception as e:
         fp64 = {"unavailable": repr(e)}
     line = {
@@ -649,7 +673,7 @@ def run_gpu(a):
         "clocks": clk, "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / a.steps,
         "split_ms": {"stiff_total": float(np.median(st_ms)), "assemble_kernel": k_ms,
                      "update_forces": float(np.median(fo_ms))},
-        "roofline": {"kernel": "k_assemble_shell_tiles", "bound": "hbm", "achieved": ach, "peak": peak,
+        "roofline": {"kernel": "k_assemble_shell_stream", "bound": "hbm", "achieved": ach, "peak": peak,
                      "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALG_BYTES_KT * n_local,

@@ -1103,7 +1103,8 @@ struct SLayout {
     static constexpr int KREC_BYTES = NBUF * SLOTS * CB_SH_KREC * 8;
     static constexpr int REC_BYTES = NBUF * S * 32 * 4;
     static constexpr int PAIR_BYTES = NBUF * PAIRS * 4;
-    static constexpr int WARP_BYTES = IMG_BYTES + KREC_BYTES + REC_BYTES + PAIR_BYTES;
+    static constexpr int AUX_BYTES = NBUF == 1 ? 144 : 0;        // next tile's element ids (32 x 4) + tile record (16)
+    static constexpr int WARP_BYTES = IMG_BYTES + KREC_BYTES + REC_BYTES + PAIR_BYTES + AUX_BYTES;
     static_assert(WARP_BYTES % 16 == 0 && IMG_BYTES % 16 == 0 && PAIRS % 4 == 0, "16-byte aligned regions");
 };
 
@@ -1278,6 +1279,8 @@ k_assemble_shell_stream(CbStiffArgs A)
     double *skrec = reinterpret_cast<double *>(wbase + L::IMG_BYTES);                           // [2][SLOTS][18]
     uint32_t *srec = reinterpret_cast<uint32_t *>(wbase + L::IMG_BYTES + L::KREC_BYTES);         // [2][S][32]
     uint32_t *spair = srec + NBUF * S * 32;                                                      // [2][PAIRS]
+    int *seid = reinterpret_cast<int *>(spair + NBUF * PAIRS);                                   // [32]   (NBUF 1)
+    int4 *stlr = reinterpret_cast<int4 *>(seid + 32);                                            // [1]    (NBUF 1)
     const long G = (long)gridDim.x * WARPS, N = A.ntilesS;
     long tile = (long)blockIdx.x * WARPS + warp;
     if (tile >= N) return;
@@ -1287,11 +1290,21 @@ k_assemble_shell_stream(CbStiffArgs A)
     constexpr bool LEAN = WARPS > 8;
     constexpr bool PREK = CB_S_PREK && !LEAN;
     static_assert(NBUF == 2 || LEAN, "single record buffers go with the lean variant");
+    static_assert(NBUF == 2 || SLOTS <= 32, "one element id per lane");
 
-    // prologue: this tile staged directly; the next tile's record and element ids into registers
-    int4 tlr = s_ldg16(A.tilesS + tile), tlr_n = tlr;
+    // prologue: this tile staged directly; the next tile's record and element ids into registers - or, with
+    // single buffers (168 registers: prefetched registers would be spilled, and the spill store WAITS for the
+    // load), into shared memory by cp.async: tile record with the tile's stage, element ids one tile ahead
+    int4 tlr, tlr_n;
     SEids<SLOTS> eid_n{};
-    {
+    if constexpr (NBUF == 1) {
+        const SEids<SLOTS> eid = s_load_eids<SLOTS>(A, tile, lane);
+        s_issue_stage<SLOTS, S, PAIRS>(A, tile, eid, lane, skrec, srec, spair);
+        if (lane == 0) CB_CPA(16, "cg", stlr, A.tilesS + tile);
+        CB_CPA_COMMIT();
+        tlr = tlr_n = make_int4(0, 0, 0, 0);
+    } else {
+        tlr = s_ldg16(A.tilesS + tile); tlr_n = tlr;
         const SEids<SLOTS> eid = s_load_eids<SLOTS>(A, tile, lane);
         s_issue_stage<SLOTS, S, PAIRS>(A, tile, eid, lane, skrec, srec, spair);
         CB_CPA_COMMIT();
@@ -1337,10 +1350,15 @@ k_assemble_shell_stream(CbStiffArgs A)
         }
         SEids<SLOTS> eid_nn{};
         int4 tlr_nn = tlr_n;
-        if (has_next2) { eid_nn = s_load_eids<SLOTS>(A, tile + 2 * G, lane); tlr_nn = s_ldg16(A.tilesS + tile + 2 * G); }
-        if (NBUF == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");       // this tile's records have landed
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if constexpr (NBUF == 2) {
+            if (has_next2) { eid_nn = s_load_eids<SLOTS>(A, tile + 2 * G, lane); tlr_nn = s_ldg16(A.tilesS + tile + 2 * G); }
+        } else {
+            if (has_next && lane < SLOTS) CB_CPA(4, "ca", seid + lane, A.elemsS + (tile + G) * SLOTS + lane);
+            CB_CPA_COMMIT();
+        }
+        asm volatile("cp.async.wait_group 1;" ::: "memory");       // this tile's records have landed
         __syncwarp();
+        if constexpr (NBUF == 1) tlr = *stlr;
 
         const long out0 = ((long)(unsigned)tlr.x) | ((long)tlr.y << 32);
         const int nout = tlr.z, nsteps = tlr.w & 0xff;
@@ -1440,9 +1458,15 @@ k_assemble_shell_stream(CbStiffArgs A)
             __syncwarp();                      // their first parts are in the image
             if (pend) s_store_block<true>(obuf, shift, pend_pr, acc);
         }
-        if (NBUF == 1) {                       // every lane has read its last record: request the next tile's
+        if constexpr (NBUF == 1) {             // every lane has read its last record: request the next tile's
+            asm volatile("cp.async.wait_group 0;" ::: "memory");       // its element ids arrived a tile ago
             __syncwarp();
-            if (has_next) s_issue_stage<SLOTS, S, PAIRS>(A, tile + G, eid_n, lane, skrec, srec, spair);
+            if (has_next) {
+                SEids<SLOTS> e;
+                e.v[0] = lane < SLOTS ? seid[lane] : 0;
+                s_issue_stage<SLOTS, S, PAIRS>(A, tile + G, e, lane, skrec, srec, spair);
+                if (lane == 0) CB_CPA(16, "cg", stlr, A.tilesS + tile + G);
+            }
             CB_CPA_COMMIT();
         }
         // writes of the image (generic proxy) ordered before the copy engine's reads (async proxy)
@@ -1467,7 +1491,8 @@ k_assemble_shell_stream(CbStiffArgs A)
 #pragma unroll
             for (int i = 0; i < 9; ++i) kbC[i] = kbN[i];
         }
-        tile += G; tlr = tlr_n; tlr_n = tlr_nn; eid_n = eid_nn; if (NBUF == 2) buf ^= 1;
+        tile += G;
+        if constexpr (NBUF == 2) { tlr = tlr_n; tlr_n = tlr_nn; eid_n = eid_nn; buf ^= 1; }
         __syncwarp();
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

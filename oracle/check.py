@@ -35,3 +35,27 @@ def compare_iteration(m, dd, ss_after, f_after):
     s.end_iteration()
     ss = B.stiff(m, s, SLVFLAG=0)
     return max(_rel(ss_after, ss), _rel(f_after, s.f_temp))
+
+
+def compare_iteration_csc(m, dd, Ap, Ai, Ax_after, f_after):
+    """the same sequence for the device CSC layout: entry (i <= j) of the oracle's skyline lives at
+    ss[maxa[j-1] + (j-i) - 1] (1-based, model.c:1269-1278); both triangles of the CSC are held against it,
+    structural CSC entries outside the skyline profile must be exactly zero"""
+    B = _backend()
+    from .refbind import RefState
+    s = RefState(m)
+    s.begin_increment()
+    B.stiff(m, s, SLVFLAG=0)
+    B.update_forces(m, s, dd)
+    s.end_iteration()
+    ss = B.stiff(m, s, SLVFLAG=0)
+    n = m.NEQ
+    maxa = np.asarray(m.maxa, dtype=np.int64)
+    cols = np.repeat(np.arange(n, dtype=np.int64), np.diff(Ap))
+    rows = np.asarray(Ai, dtype=np.int64)
+    lo, hi = np.minimum(rows, cols), np.maximum(rows, cols)
+    addr = maxa[hi] - 1 + (hi - lo)
+    inside = addr < maxa[hi + 1] - 1
+    if np.any(Ax_after[~inside] != 0.0):
+        return float("inf")
+    return max(float(np.abs(Ax_after[inside] - ss[addr[inside]]).max() / np.abs(ss).max()), _rel(f_after, s.f_temp))

@@ -312,8 +312,10 @@ __device__ __noinline__ void brick_block(const CbStiffArgs &A, int e, int a, int
 {
     const double E = A.d.br_const[(long)e * 4], v = A.d.br_const[(long)e * 4 + 1];
     const double lam = E * v / ((1 + v) * (1 - 2 * v)), mu = .5 * (E / (1 + v));
-    const int sga = c_br_sg[a], sra = c_br_sr[a], ssa = c_br_ss[a], sta = c_br_st[a];
-    const int sgb = c_br_sg[b], srb = c_br_sr[b], ssb = c_br_ss[b], stb = c_br_st[b];
+    // natural-coordinate signs of local joints a, b (the c_br_* tables as arithmetic: a table indexed by a
+    // lane-varying joint serialises in the constant cache)
+    const int sra = 1 - 2 * (((a + 1) >> 1) & 1), ssa = 1 - (a & 2), sta = 1 - ((a & 4) >> 1), sga = sra * ssa * sta;
+    const int srb = 1 - 2 * (((b + 1) >> 1) & 1), ssb = 1 - (b & 2), stb = 1 - ((b & 4) >> 1), sgb = srb * ssb * stb;
     double K[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     const double gp = 0.57735026918962576451;      // 1/sqrt(3)
     const double2 *pr = reinterpret_cast<const double2 *>(A.br_prep + (long)e * 8 * CB_BR_PREP);
@@ -485,7 +487,12 @@ template <int ND>
 __device__ __noinline__ int mass_block_stage(const CbStiffArgs &A, const CbContrib &ct, double *stg)
 {
     constexpr int STR = CB_TILE_T + 1;
-    for (int i = 0; i < ND * ND; ++i) stg[i * STR] = 0.0;
+    if (A.mixed && ND > 3 && ct.type != CB_T_SHELL && ct.type != CB_T_FRAME) {     // see the stiffness mode
+        for (int p = 0; p < 3; ++p)
+            for (int q = 0; q < 3; ++q) stg[(p * ND + q) * STR] = 0.0;
+    } else {
+        for (int i = 0; i < ND * ND; ++i) stg[i * STR] = 0.0;
+    }
     if (ct.type == CB_T_BRICK) {
         double blk[9];
         brick_mass_block(A, ct.e, ct.a, ct.b, blk, 3);
@@ -604,8 +611,18 @@ k_assemble_tiles(CbStiffArgs A)
                 for (int i = 0; i < 9; ++i) blk[i] = 0.0;
                 if (ct.type == CB_T_TRUSS) truss_block(A, ct.e, ct.a, ct.b, blk, 3);
                 else if (ct.type == CB_T_BRICK) brick_block(A, ct.e, ct.a, ct.b, blk, 3);
+                // a 3-DOF contribution in a wider stage column: the mixed reduction reads its leading 3x3 only
+                // (r, c < ndof), so the other 27 of 36 slots need no zeros (they were 80 % of this kernel's
+                // shared-memory stores on the brick + skin model)
+                if (A.mixed && ND > 3) {
 #pragma unroll
-                for (int i = 0; i < NN; ++i) stg[i * STR] = 0.0;
+                    for (int p = 0; p < 3; ++p)
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) stg[(p * ND + q) * STR] = 0.0;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NN; ++i) stg[i * STR] = 0.0;
+                }
                 if (ct.type == CB_T_BRICK && ct.e >= A.d.NE_SBR) {
                     // fluid brick (fsi.c:344, model.c:1089-1140): only the (z, z) entry of the joint block has an
                     // equation - the pressure DOF, DOF 0 of the twin joints; with the reference's E = 1e20,

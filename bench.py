@@ -581,9 +581,28 @@ def run_gpu(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         s_ms = float(t[0])
         tot = 2 * n * n
+        # what the fixed per-step cost is made of: the same loop without the sums + collective, and the
+        # CUDA-event times of the two passes alone (rank 0's; read in a separate loop, the reads synchronise)
+        asm_s.sync(); dist.barrier()
+        asm_s.timer_start()
+        for _ in range(ks):
+            asm_s.stiff(); asm_s.update_forces_dev(); asm_s.end_iteration()
+        nc_ms = asm_s.timer_stop_ms() / ks
+        t = torch.tensor([nc_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nc_ms = float(t[0])
+        kk, ff = [], []
+        for _ in range(5):
+            asm_s.stiff(); kk.append(asm_s.last_stiff_ms); asm_s.update_forces_dev(); ff.append(asm_s.last_forces_ms)
+            asm_s.end_iteration()
         strong = {"ms_per_step": s_ms, "value": tot / (s_ms * 1e-3), "unit": UNIT, "elements": tot, "steps": ks,
                   "workload": f"ONE {n}x{n}-cell plate ({tot} elements) split over {world} ranks",
-                  "note": "divide the N=1 line's ms_per_step by N x this ms_per_step for the strong-scaling efficiency"}
+                  "ms_per_step_without_sums_and_collective": nc_ms,
+                  "split_ms_rank0": {"stiff_total": float(np.median(kk)), "update_forces": float(np.median(ff))},
+                  "note": "divide the N=1 line's ms_per_step by N x this ms_per_step for the strong-scaling efficiency; "
+                          "ms_per_step - ms_per_step_without_sums_and_collective = the residual-sums launch + the "
+                          "88-byte ncclAllReduce; without - (stiff_total + update_forces) = launch gaps of the four "
+                          "kernels"}
         asm_s.close()
         asm = None
 

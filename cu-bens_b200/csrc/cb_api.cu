@@ -194,6 +194,10 @@ struct cb_handle {
     double plan_seconds = 0;
     void *comm = nullptr;         // ncclComm_t of an element-partitioned run (cb_comm_init)
     int comm_rank = 0, comm_world = 1;
+    // peer-memory mailboxes of the fused sums + all-reduce kernel (cb_comm_impl.cuh); p2p: all ranks opened them
+    bool p2p = false; uint32_t xseq = 0;
+    DevBuf<uint2> mbox; DevBuf<unsigned long long> peer_tab; DevBuf<int32_t> xerr;
+    std::vector<void *> peer_open;
     DevBuf<int32_t> trip_buf, sums_ticket;
     DevBuf<int> Ap, Ai;
     DevBuf<long> maxa;
@@ -1508,15 +1512,67 @@ __device__ __forceinline__ void joint_force_sum(const CbDev &d, long n, const in
 }
 
 #define CB_NSUMS 11
+// ---- all-reduce of the CB_NSUMS partial sums over NVLink peer memory, fused into the kernel that forms them --
+// Every rank owns a mailbox mbox[2][world][2 * CB_NSUMS] of 8-byte words {32 bits of data, sequence number}
+// that its peers have mapped (CUDA IPC, cb_comm_init).  The last block of k_resid_sums writes the two halves of
+// each of its sums into slot [parity][rank] of EVERY rank's mailbox (8-byte stores are single transactions: a
+// word whose sequence number matches carries its data - the LL protocol), polls its own mailbox until all
+// ranks' words of this call have landed and adds them in rank order (the same bits on every rank).  Calls are
+// collective and in lockstep, so two parities keep a fast rank's next call from overwriting words a slow one
+// still reads.  One launch, no NCCL kernel, ~2 NVLink latencies.  A poll that sees nothing for ~1 s sets
+// *err (a peer died) instead of hanging the GPU.
+struct CbXchg {
+    uint2 *const *peers;      // [world] every rank's mailbox as mapped here (own entry: local pointer); null: off
+    uint2 *mine;
+    int world, rank;
+    uint32_t seq;
+    int32_t *err;
+};
+#define CB_X_WORDS (2 * CB_NSUMS)
+__device__ __forceinline__ void cb_xchg_allreduce(const CbXchg &X, const double *loc /* shared, [CB_NSUMS] */,
+                                                  uint32_t (*got)[CB_X_WORDS] /* shared, [world] */, double *out)
+{
+    const int t = threadIdx.x, par = (int)(X.seq & 1u);
+    if (t < CB_X_WORDS) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(loc[t >> 1]);
+        const uint32_t half = (t & 1) ? (uint32_t)(bits >> 32) : (uint32_t)bits;
+        for (int r = 0; r < X.world; ++r) {
+            uint2 *dst = X.peers[r] + ((size_t)par * X.world + X.rank) * CB_X_WORDS + t;
+            asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(half), "r"(X.seq) : "memory");
+        }
+    }
+    if (t < CB_X_WORDS * X.world) {
+        const int r = t / CB_X_WORDS, i = t - r * CB_X_WORDS;
+        const uint2 *src = X.mine + ((size_t)par * X.world + r) * CB_X_WORDS + i;
+        uint32_t v = 0, f = 0;
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(src) : "memory");
+            if (f == X.seq) break;
+            if (clock64() - t0 > (1LL << 31)) { atomicExch(X.err, 1); break; }
+        }
+        got[r][i] = v;
+    }
+    __syncthreads();
+    if (t < CB_NSUMS) {
+        double sum = 0.0;
+        for (int r = 0; r < X.world; ++r)
+            sum += __longlong_as_double((long long)(((unsigned long long)got[r][2 * t + 1] << 32) | got[r][2 * t]));
+        out[t] = sum;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_resid_sums(CbDev d, long e0, long e1, double lpf, const double *__restrict__ q, const double *__restrict__ f,
              const double *__restrict__ f_ip, const double *__restrict__ fp, const double *__restrict__ d_temp,
              const double *__restrict__ dd, long jo0, long jo1, const int32_t *__restrict__ cstart,
              const CbCorner *__restrict__ corners, double *__restrict__ part, double *__restrict__ out,
-             int32_t *__restrict__ ticket)
+             int32_t *__restrict__ ticket, CbXchg X)
 {
     __shared__ double sh[CB_NSUMS][256];
     __shared__ bool last;
+    __shared__ double loc[CB_NSUMS];
+    __shared__ uint32_t got[8][CB_X_WORDS];
     double a[CB_NSUMS];
     for (int k = 0; k < CB_NSUMS; ++k) a[k] = 0;
     for (long i = e0 + blockIdx.x * 256L + threadIdx.x; i < e1; i += 256L * gridDim.x) {
@@ -1558,8 +1614,22 @@ k_resid_sums(CbDev d, long e0, long e1, double lpf, const double *__restrict__ q
             for (int k = 0; k < CB_NSUMS; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x < CB_NSUMS) out[threadIdx.x] = sh[threadIdx.x][0];
+    if (X.peers) {                       // fused all-reduce over peer memory
+        if (threadIdx.x < CB_NSUMS) loc[threadIdx.x] = sh[threadIdx.x][0];
+        __syncthreads();
+        cb_xchg_allreduce(X, loc, got, out);
+    } else if (threadIdx.x < CB_NSUMS) out[threadIdx.x] = sh[threadIdx.x][0];
     if (threadIdx.x == 0) *ticket = 0;
+}
+
+// the exchange alone, for sums that are already in place (cb_residual_allreduce after cb_residual_sums)
+__global__ void __launch_bounds__(256) k_xchg_sums(double *__restrict__ sums, CbXchg X)
+{
+    __shared__ double loc[CB_NSUMS];
+    __shared__ uint32_t got[8][CB_X_WORDS];
+    if (threadIdx.x < CB_NSUMS) loc[threadIdx.x] = sums[threadIdx.x];
+    __syncthreads();
+    cb_xchg_allreduce(X, loc, got, sums);
 }
 
 
@@ -2034,7 +2104,16 @@ extern "C" int cb_set_q(cb_handle *h, const double *q)
     if (h->eq1 < h->eq0) h->eq0 = h->eq1 = 0;
     return CB_OK;
 }
-extern "C" int cb_residual_sums(cb_handle *h, double lpf)
+static CbXchg xchg_args(cb_handle *h, bool on)
+{
+    CbXchg X{};
+    if (on && h->p2p) {
+        X.peers = reinterpret_cast<uint2 *const *>(h->peer_tab.p); X.mine = h->mbox.p;
+        X.world = h->comm_world; X.rank = h->comm_rank; X.seq = ++h->xseq; X.err = h->xerr.p;
+    }
+    return X;
+}
+static int residual_sums_impl(cb_handle *h, double lpf, bool fuse_allreduce)
 {
     if (!h || !h->qvec.p) return fail(CB_ERR_ARG, "cb_set_q has not been called");
     cudaSetDevice(h->fl.device);
@@ -2043,10 +2122,19 @@ extern "C" int cb_residual_sums(cb_handle *h, double lpf)
     k_resid_sums<<<CB_SUM_BLOCKS, 256, 0, h->stream>>>(a.d, h->eq0, h->eq1, lpf, h->qvec.p, h->f_temp.p, h->f_ip.p, h->f.p,
                                                         h->d_temp.p, h->dd.p, a.jo0, a.jo1,
                                                         h->node_cstart.p, h->corners.p, h->sums_part.p, h->sums.p,
-                                                        h->sums_ticket.p);
+                                                        h->sums_ticket.p, xchg_args(h, fuse_allreduce));
     h->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return CB_OK;
+}
+extern "C" int cb_residual_sums(cb_handle *h, double lpf) { return residual_sums_impl(h, lpf, false); }
+extern "C" int cb_residual_allreduce(cb_handle *h);
+// sums + all-reduce in ONE launch when the ranks share peer memory (cb_comm_init), else the two calls
+extern "C" int cb_residual_sums_allreduce(cb_handle *h, double lpf)
+{
+    if (h && h->p2p) return residual_sums_impl(h, lpf, true);
+    const int rc = residual_sums_impl(h, lpf, false);
+    return rc ? rc : cb_residual_allreduce(h);
 }
 extern "C" double *cb_dev_sums(cb_handle *h) { return h ? h->sums.p : nullptr; }
 extern "C" int cb_residual_allreduce(cb_handle *h);
@@ -2058,7 +2146,7 @@ extern "C" int cb_convergence_test(cb_handle *h, double lpf, double intener1, do
 {
     if (!h || !convchk) return fail(CB_ERR_ARG, "null argument");
     *convchk = 0;
-    if (cb_residual_sums(h, lpf) || cb_residual_allreduce(h)) return 1;
+    if (cb_residual_sums_allreduce(h, lpf)) return 1;
     double s[5];
     if (cb_get_sums(h, s)) return 1;
     if (sums5_out) memcpy(sums5_out, s, sizeof s);
@@ -2090,6 +2178,11 @@ extern "C" int cb_get_sums(cb_handle *h, double *s3)
     cudaSetDevice(h->fl.device);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaMemcpy(s3, h->sums.p, 5 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h->p2p) {
+        int32_t e = 0;
+        CUDA_TRY(cudaMemcpy(&e, h->xerr.p, sizeof e, cudaMemcpyDeviceToHost));
+        if (e) return fail(CB_ERR_CUDA, "peer-memory all-reduce: a rank did not answer within ~1 s");
+    }
     return CB_OK;
 }
 

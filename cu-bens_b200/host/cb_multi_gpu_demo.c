@@ -9,7 +9,7 @@
  * owned joint range, the load vector q, one displacement increment dd and the load factor.  The program does
  * what one Newton iteration of main.c:1891-2030 does on the device path - cb_begin_increment, cb_stiff,
  * cb_update_forces, cb_residual_sums + cb_residual_allreduce (NCCL over NVLink) - and writes the eleven
- * all-reduced sums, so that a test can hold them against a one-GPU run of the whole model.                 */
+ * all-reduced sums (and 1 / 0: exchanged over mapped peer memory / NCCL), so that a test can hold them against a one-GPU run of the whole model.                 */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -75,13 +75,21 @@ int main(int argc, char **argv)
     CK(cb_set_q(h, q));
     CK(cb_residual_sums(h, lpf));
     CK(cb_residual_allreduce(h));                 /* ncclAllReduce on the handle's stream, from C */
-    double out[11];
+    double out[11], fused[11];
     CK(cb_get_sums(h, out));
     CK(cb_get_reaction_sums(h, out + 5));
+    /* the same in one launch (sums + exchange over NVLink peer memory where the ranks could map each other) */
+    CK(cb_residual_sums_allreduce(h, lpf));
+    CK(cb_get_sums(h, fused));
+    CK(cb_get_reaction_sums(h, fused + 5));
+    if (memcmp(out, fused, sizeof out)) { fprintf(stderr, "rank %d: fused sums + all-reduce differ from the two calls\n", rank); return 1; }
     FILE *o = fopen(argv[5], "wb"); if (!o) { perror(argv[5]); return 2; }
-    fwrite(out, sizeof(double), 11, o); fclose(o);
+    const double mode = cb_comm_peer_memory(h);
+    fwrite(out, sizeof(double), 11, o); fwrite(&mode, sizeof mode, 1, o); fclose(o);
+    const int peer = cb_comm_peer_memory(h);
     CK(cb_comm_destroy(h));
     cb_destroy(h);
-    printf("rank %d of %d: sums %.17g %.17g %.17g\n", rank, world, out[0], out[1], out[2]);
+    printf("rank %d of %d: sums %.17g %.17g %.17g (all-reduce over %s)\n", rank, world, out[0], out[1], out[2],
+           peer ? "mapped peer memory" : "NCCL");
     return 0;
 }

@@ -41,7 +41,7 @@ EXPORTS = [
     "cb_plan_selfcheck", "cb_csc_upper_nnz", "cb_csc_upper_pattern", "cb_get_csc_upper_values",
     "cb_csc_values_begin", "cb_csc_values_end", "cb_get_csc_values_mirrored", "cb_sym_selftest",
     "cb_local_equations", "cb_csc_values_d2h_bytes", "cb_get_reaction_sums", "cb_comm_unique_id", "cb_comm_init",
-    "cb_comm_destroy", "cb_residual_allreduce", "cb_trip_allreduce", "cb_convergence_test", "cb_plan_info",
+    "cb_comm_destroy", "cb_residual_allreduce", "cb_residual_sums_allreduce", "cb_comm_peer_memory", "cb_trip_allreduce", "cb_convergence_test", "cb_plan_info",
     "cb_debug_stream_plan",
 ]
 
@@ -440,6 +440,14 @@ class Assembler:
     def comm_init(self, uid, rank, world):
         assert len(uid) == 128
         self._check(self.lib.cb_comm_init(self.h, C.c_char_p(uid), C.c_int(rank), C.c_int(world)))
+
+    @property
+    def comm_peer_memory(self):
+        return bool(self.lib.cb_comm_peer_memory(self.h))
+
+    def residual_sums_allreduce(self, lpf=1.0):
+        """cb_residual_sums + the all-reduce over the ranks in one launch where the ranks share peer memory"""
+        self._check(self.lib.cb_residual_sums_allreduce(self.h, C.c_double(lpf)))
 
     def residual_allreduce(self):
         self._check(self.lib.cb_residual_allreduce(self.h))

@@ -173,8 +173,7 @@ class InterfaceExchange:
             asm.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
 
     def reduce(self, lpf=1.0):
-        self.asm.residual_sums(lpf)
-        self.asm.residual_allreduce()
+        self.asm.residual_sums_allreduce(lpf)      # one launch: sums + exchange over NVLink peer memory (else NCCL)
 
 
 def write_submodel(path, m, owned, q, dd, lpf, layout=1, device=0):

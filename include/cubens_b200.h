@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 4
+#define CB_ABI_VERSION 5
 
 /* status codes (the reference uses 0 = ok / 1 = error, solve.c:558-562, frame.c:1201) */
 enum {
@@ -243,6 +243,8 @@ int     cb_set_q(cb_handle *h, const double *q);
 int     cb_residual_sums(cb_handle *h, double lpf);
 double *cb_dev_sums(cb_handle *h);
 int     cb_get_sums(cb_handle *h, double *sums5);
+int     cb_residual_sums_allreduce(cb_handle *h, double lpf);   /* sums + all-reduce; ONE launch over NVLink peer
+                                                                 * memory when cb_comm_init could map the peers   */
 int     cb_convergence_test(cb_handle *h, double lpf, double intener1, double toldisp, double tolforc,
                             double tolener, int *convchk, double *sums5_out /* may be NULL */);
 /* cb_residual_sums also leaves, in cb_dev_sums()[5..10], the REACTION resultants of the owned joints: the
@@ -256,15 +258,21 @@ int     cb_get_reaction_sums(cb_handle *h, double *r6);
  *                       the host has (file, pipe, MPI_Bcast, ...)
  *   cb_comm_init        collective: every rank calls it with the same id; NCCL is bound at run time
  *                       (libnccl.so.2; a process that already holds one reuses it) - CB_ERR_UNSUPPORTED if absent
- *   cb_residual_allreduce   ncclAllReduce(sum) of the eleven doubles of cb_dev_sums() in place, on the handle's
- *                       stream, no host synchronisation: call it after cb_residual_sums, read with cb_get_sums /
- *                       cb_get_reaction_sums.  The matrix columns and f_int of the owned joints need no exchange
- *                       (halo elements); these sums are the per-iteration traffic over NVLink
+ *                       cb_comm_init also tries to map every rank's 2.8 KB mailbox into every other rank (CUDA IPC
+ *                       handles through one ncclAllGather, one process per GPU on one NVLink / NVSwitch node,
+ *                       CB_COMM_P2P=0 disables): with it the all-reduce below is the library's own exchange
+ *                       over peer memory - fused into the sums kernel by cb_residual_sums_allreduce
+ *   cb_residual_allreduce   sum over the ranks of the eleven doubles of cb_dev_sums() in place, on the handle's
+ *                       stream, no host synchronisation (peer-memory exchange kernel, else ncclAllReduce): call it
+ *                       after cb_residual_sums, read with cb_get_sums / cb_get_reaction_sums.  The matrix columns
+ *                       and f_int of the owned joints need no exchange (halo elements); these sums are the
+ *                       per-iteration traffic over NVLink
  *   cb_trip_allreduce   ANAFLAG 3: minimum over the ranks of the tripping element indices, between
  *                       cb_update_forces_begin and cb_update_forces_end
  * Without a communicator (one rank) the two all-reduce calls return at once.                              */
 int  cb_comm_unique_id(void *id128);
 int  cb_comm_init(cb_handle *h, const void *id128, int rank, int world);
+int  cb_comm_peer_memory(cb_handle *h);      /* 1: the all-reduce runs over mapped peer memory, 0: through NCCL */
 int  cb_comm_destroy(cb_handle *h);
 int  cb_residual_allreduce(cb_handle *h);
 int  cb_trip_allreduce(cb_handle *h, int *first_fr, int *first_sh);

@@ -25,8 +25,12 @@ def _whole(m, dd, lpf):
     return np.concatenate([s, r])
 
 
+@pytest.mark.parametrize("collective", ["auto", "nccl"])
 @pytest.mark.parametrize("world", [1, 2])
-def test_c_host_ranks_allreduce_in_library(gpu, tmp_path, world):
+def test_c_host_ranks_allreduce_in_library(gpu, tmp_path, world, collective):
+    """collective "auto": the library's own exchange over mapped peer memory where cb_comm_init could map the
+    ranks' mailboxes (fused into the sums kernel by cb_residual_sums_allreduce; the demo checks that the fused
+    launch and the two separate calls give the same bits); "nccl": CB_COMM_P2P=0 forces ncclAllReduce"""
     if gpu.cb_device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     assert os.path.exists(DEMO), "make -C cu-bens_b200 builds cb_multi_gpu_demo"
@@ -41,15 +45,22 @@ def test_c_host_ranks_allreduce_in_library(gpu, tmp_path, world):
         mp = tmp_path / f"model_{r}.bin"; op = tmp_path / f"out_{r}.bin"
         write_submodel(mp, sub, own, m.q, dd, lpf)
         outs.append(op)
-        procs.append(subprocess.Popen([DEMO, str(mp), str(r), str(world), str(uid), str(op)],
+        env = dict(os.environ, CB_COMM_P2P="0") if collective == "nccl" else dict(os.environ)
+        procs.append(subprocess.Popen([DEMO, str(mp), str(r), str(world), str(uid), str(op)], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     for p in procs:
         out, _ = p.communicate(timeout=300)
         assert p.returncode == 0, out
+        print(out.strip().splitlines()[-1])
     for op in outs:
         got = np.fromfile(op, dtype=np.float64)
-        assert got.shape == (11,)
+        assert got.shape == (12,)
+        if collective == "nccl" or world == 1:
+            assert got[11] == 0.0
+        got = got[:11]
         # the ranks add their partial sums in a different association than the one-GPU reduction
         assert np.allclose(got[:5], want[:5], rtol=1e-12, atol=0)
         assert np.allclose(got[5:], want[5:], rtol=1e-9, atol=1e-9 * np.abs(want[5:]).max())
     assert np.array_equal(np.fromfile(outs[0], dtype=np.float64), np.fromfile(outs[-1], dtype=np.float64))
+    if collective == "auto" and world > 1 and os.environ.get("CB_EXPECT_PEER_MEMORY"):
+        assert np.fromfile(outs[0], dtype=np.float64)[11] == 1.0, "the ranks did not map each other's mailboxes"

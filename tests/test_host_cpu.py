@@ -20,7 +20,7 @@ def test_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert set(cb.EXPORTS) <= set(declared)
-    assert lib.cb_abi_version() == int(re.search(r"#define CB_ABI_VERSION (\d+)", hdr).group(1)) == 4
+    assert lib.cb_abi_version() == int(re.search(r"#define CB_ABI_VERSION (\d+)", hdr).group(1)) == 5
 
 
 def test_no_cpu_fallback():

@@ -151,7 +151,7 @@ struct cb_handle {
     // geometry classes (cb_internal.h): class of each shell, representatives, tables, work records
     DevBuf<int32_t> sh_class, cls_rep;
     std::vector<int32_t> h_cls;   // host copy of sh_class (the stream plan packs it into its step records)
-    DevBuf<double> keb_tab, keb_tab10, der_tab;
+    DevBuf<double> keb_tab, keb_tab10, keb_row, der_tab;
     DevBuf<CbWork> works_cls;
     int ncls = 0;
     bool cls_on = false;
@@ -229,7 +229,7 @@ static CbDev make_dev(cb_handle *h)
     d.fr_osflag = h->fr_osflag.p; d.fr_mendrel = h->fr_mendrel.p; d.fr_simple = h->fr_simple;
     d.fr_efFE_ref = h->fr_efFE_ref.p; d.fr_fg = h->fr_fg.p;
     d.fr_plast = h->fr_plast.p; d.fr_yldflag = h->fr_yldflag.p; d.fr_ynew = h->fr_ynew.p;
-    if (h->cls_on) { d.sh_class = h->sh_class.p; d.keb_tab = h->keb_tab.p; d.keb_tab10 = h->keb_tab10.p; d.der_tab = h->der_tab.p; }
+    if (h->cls_on) { d.sh_class = h->sh_class.p; d.keb_tab = h->keb_tab.p; d.keb_tab10 = h->keb_tab10.p; d.keb_row = h->keb_row.p; d.der_tab = h->der_tab.p; }
     d.sh_yield = h->sh_yield.p; d.sh_pl = h->sh_pl[1].p; d.sh_yv = h->sh_yv.p; d.sh_kpl = h->sh_kpl.p;
     d.sh_trip = h->sh_trip.p;
     d.fr_code = h->fr_code.p; d.fr_tau = h->fr_tau.p; d.fr_trip = h->fr_trip.p; d.tr_py = h->tr_py.p;
@@ -545,7 +545,7 @@ static int create_inner(const cb_sizes *sz, const cb_flags *fl, const cb_model *
             if (ok && getenv("CB_NO_GEOMETRY_CLASSES") == nullptr) {
                 h->ncls = (int)rep.size();
                 h->h_cls = cls;
-                if (h->sh_class.upload(cls) || h->cls_rep.upload(rep) || h->keb_tab.alloc((size_t)h->ncls * 81) || h->keb_tab10.alloc((size_t)h->ncls * 90) ||
+                if (h->sh_class.upload(cls) || h->cls_rep.upload(rep) || h->keb_tab.alloc((size_t)h->ncls * 81) || h->keb_tab10.alloc((size_t)h->ncls * 90) || h->keb_row.alloc((size_t)h->ncls * 9 * CB_KROW) ||
                     h->der_tab.alloc((size_t)h->ncls * CB_SH_DER))
                     BAIL(CB_ERR_CUDA);
                 h->cls_on = true;
@@ -640,7 +640,7 @@ extern "C" void cb_destroy(cb_handle *h)
                               &h->fr_offset, &h->fr_efFE_ref, &h->fr_fg, &h->fr_dens, &h->br_const, &h->br_prep,
                               &h->Ax, &h->ss, &h->Mx, &h->fr_plast, &h->fr_tau, &h->tr_py})
         b->release();
-    h->sh_class.release(); h->cls_rep.release(); h->keb_tab.release(); h->keb_tab10.release(); h->der_tab.release(); h->works_cls.release();
+    h->sh_class.release(); h->cls_rep.release(); h->keb_tab.release(); h->keb_tab10.release(); h->keb_row.release(); h->der_tab.release(); h->works_cls.release();
     for (DevBuf<int32_t> *b : {&h->fr_yldflag, &h->fr_ynew, &h->fr_code, &h->fr_trip, &h->sh_yv, &h->sh_trip})
         b->release();
     h->sh_yield.release(); h->sh_pl[0].release(); h->sh_pl[1].release(); h->sh_kpl.release();
@@ -1301,7 +1301,7 @@ static int ensure_keb(cb_handle *h)
     if (h->sz.NE_SH && h->cls_on) {
         const bool duo = h->plan_ready && h->plan_csc.ntiles2;
         if (duo && !h->works_cls.p && h->works_cls.alloc((size_t)h->plan_csc.nworks)) return CB_ERR_CUDA;
-        if (cbk_shell_class_tables(d, h->cls_rep.p, h->ncls, h->keb_tab.p, h->keb_tab10.p, h->der_tab.p,
+        if (cbk_shell_class_tables(d, h->cls_rep.p, h->ncls, h->keb_tab.p, h->keb_tab10.p, h->keb_row.p, h->der_tab.p,
                                    duo ? h->plan_csc.works.p : nullptr, duo ? h->plan_csc.nworks : 0,
                                    h->contribs.p, h->works_cls.p, h->stream))
             return fail(CB_ERR_CUDA, "class table launch");

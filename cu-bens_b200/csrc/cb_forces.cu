@@ -297,11 +297,32 @@ int cbk_shell_init_kebcS(const CbDev &d, const CbTileS *tiles, long ntiles, int 
 // records of the duo plan with the classes of their two contributions packed into c0
 __global__ void __launch_bounds__(128)
 k_class_tables(CbDev d, const int32_t *__restrict__ rep, int ncls, double *__restrict__ keb_tab,
-               double *__restrict__ keb_tab10, double *__restrict__ der_tab)
+               double *__restrict__ keb_tab10, double *__restrict__ keb_row, double *__restrict__ der_tab)
 {
     const int k = blockIdx.x, c = threadIdx.x;
     if (k >= ncls) return;
     const long e = rep[k];
+    // keb_row: what the local block (a, b) of a shell of this class holds besides its state (cb_stiff.cu,
+    // s_contrib_cls).  CST gradients (x 2A) of the local joints: (-Y3, X3 - X2), (Y3, -X3), (0, X2); membrane
+    // coefficients t A0 C / (2 A0)^2 from sh_der[21..23]; stiff_sh's drilling term k_thetay,thetay / 1e4 (shell.c:482)
+    for (int i = c; i < 9 * CB_KROW; i += blockDim.x) {
+        const int ab = i / CB_KROW, f = i - ab * CB_KROW, a = ab / 3, b = ab - 3 * a;
+        const double X2 = SOA(d.sh_const, 5, e, d.NE_SH), X3 = SOA(d.sh_const, 6, e, d.NE_SH), Y3 = SOA(d.sh_const, 7, e, d.NE_SH);
+        const double bx[3] = {-Y3, Y3, 0.0}, by[3] = {X3 - X2, -X3, X2};
+        const double c00 = SOA(d.sh_der, 21, e, d.NE_SH), c01 = SOA(d.sh_der, 22, e, d.NE_SH), c22 = SOA(d.sh_der, 23, e, d.NE_SH);
+        const double bxa = bx[a], bya = by[a], bxb = bx[b], byb = by[b];
+        double v = 0.0;
+        if (f < 9) v = SOA(d.sh_keb, ab * 9 + f, e, d.NE_SH);
+        else if (f == 9) v = (a == b) ? SOA(d.sh_keb, ab * 9 + 4, e, d.NE_SH) * 1e-4 : 0.0;
+        else if (f == 10) v = c00 * bxa * bxb + c22 * bya * byb;
+        else if (f == 11) v = c01 * bxa * byb + c22 * bya * bxb;
+        else if (f == 12) v = c01 * bya * bxb + c22 * bxa * byb;
+        else if (f == 13) v = c00 * bya * byb + c22 * bxa * bxb;
+        else if (f == 14) v = bxa * bxb;
+        else if (f == 15) v = bya * byb;
+        else if (f == 16) v = bxa * byb + bya * bxb;
+        keb_row[(long)k * 9 * CB_KROW + i] = v;
+    }
     if (c < 81) keb_tab[k * 81 + c] = SOA(d.sh_keb, c, e, d.NE_SH);
     if (c < 90) keb_tab10[k * 90 + c] = (c % 10 < 9) ? SOA(d.sh_keb, (c / 10) * 9 + c % 10, e, d.NE_SH) : 0.0;
     if (c < CB_SH_DER) der_tab[k * CB_SH_DER + c] = SOA(d.sh_der, c, e, d.NE_SH);
@@ -319,11 +340,11 @@ k_works_set_class(const CbWork *__restrict__ works, long nworks, const CbContrib
     w.c0 = c0 | (c1 << 16);
     out[i] = w;
 }
-int cbk_shell_class_tables(const CbDev &d, const int32_t *rep, int ncls, double *keb_tab, double *keb_tab10, double *der_tab,
+int cbk_shell_class_tables(const CbDev &d, const int32_t *rep, int ncls, double *keb_tab, double *keb_tab10, double *keb_row, double *der_tab,
                            const CbWork *works, long nworks, const CbContrib *contribs, CbWork *works_cls,
                            cudaStream_t s)
 {
-    k_class_tables<<<ncls, 128, 0, s>>>(d, rep, ncls, keb_tab, keb_tab10, der_tab);
+    k_class_tables<<<ncls, 128, 0, s>>>(d, rep, ncls, keb_tab, keb_tab10, keb_row, der_tab);
     if (nworks && works_cls)
         k_works_set_class<<<(unsigned)((nworks + 255) / 256), 256, 0, s>>>(works, nworks, contribs, d.sh_class, works_cls);
     return cudaGetLastError() != cudaSuccess;

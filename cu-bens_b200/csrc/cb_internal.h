@@ -178,6 +178,7 @@ static_assert(sizeof(CbTileS) == 16, "tile records are read as one 16-byte word"
     ((uint32_t)(rel) | ((uint32_t)(colh) << 12) | ((uint32_t)(ma) << 20) | ((uint32_t)(mb) << 26))
 
 #define CB_SH_DER 24
+#define CB_KROW 18                // doubles per (class, a, b) row of keb_row
 #define CB_SH_KREC 18   // per-shell record for the stiffness pass: R[9], X2,X3,Y3, cm00,cm01,cm22, n0,n1,n2
 
 // one element corner touching a node (node -> corner CSR), used by the f_int / mass gathers
@@ -227,6 +228,8 @@ struct CbDev {
     const int32_t *sh_class; // [NE] class of each shell
     const double *keb_tab;   // [ncls][81] component order of sh_keb (CB_KEB)
     const double *keb_tab10; // [ncls][9][10] the same 3x3 blocks padded to ten doubles (16-byte loads)
+    const double *keb_row;   // [ncls][9][CB_KROW] per local joint pair (a, b): DKT block, drilling term, material
+                             // membrane block, gradient products of the geometric stiffness (k_class_tables)
     const double *der_tab;   // [ncls][CB_SH_DER]
     // frames
     const int32_t *fr_nodes; // [NE][2]
@@ -360,7 +363,7 @@ int cbk_shell_init_kebc(const CbDev &d, const CbContrib *contribs, long ncontrib
 int cbk_shell_init_kebcS(const CbDev &d, const CbTileS *tiles, long ntiles, int steps_per_tile, int slots_per_tile,
                          const uint32_t *steps, const int32_t *elems, double *kebc, cudaStream_t s);
 int cbk_shell_prep(const CbDev &d, const double *x, const double *sh_frame, cudaStream_t s);
-int cbk_shell_class_tables(const CbDev &d, const int32_t *rep, int ncls, double *keb_tab, double *keb_tab10, double *der_tab,
+int cbk_shell_class_tables(const CbDev &d, const int32_t *rep, int ncls, double *keb_tab, double *keb_tab10, double *keb_row, double *der_tab,
                            const CbWork *works, long nworks, const CbContrib *contribs, CbWork *works_cls,
                            cudaStream_t s);
 int cbk_shell_plastic_prep(const CbDev &d, const double *sh_frame, const double *sh_dsl,

@@ -1206,20 +1206,9 @@ __device__ __forceinline__ void s_load_krec(const double *kr /*shared*/, double 
 #pragma unroll
     for (int i = 0; i < CB_SH_KREC / 2; ++i) { const double2 v = k2[i]; k[2 * i] = v.x; k[2 * i + 1] = v.y; }
 }
-__device__ __forceinline__ void s_contrib(const double *k /*registers*/, const double *kb, int a, int b, double *acc)
+__device__ __forceinline__ void s_contrib_core(const double *R, const double *kb, double s00, double s01, double s10,
+                                               double s11, double s22, double drill, double *acc)
 {
-    const double *R = k;
-    // CST shape-function gradients (x 2A) of local joints a, b: (-Y3, X3 - X2), (Y3, -X3), (0, X2)
-    const double nY3 = -k[11], dX = k[10] - k[9], nX3 = -k[10];
-    const double bxa = sel3(a, nY3, k[11], 0.0), bya = sel3(a, dX, nX3, k[9]);
-    const double bxb = sel3(b, nY3, k[11], 0.0), byb = sel3(b, dX, nX3, k[9]);
-    const double g = bxa * (k[15] * bxb + k[17] * byb) + bya * (k[17] * bxb + k[16] * byb);
-    const double s00 = k[12] * bxa * bxb + k[14] * bya * byb + g;
-    const double s01 = k[13] * bxa * byb + k[14] * bya * bxb;
-    const double s10 = k[13] * bya * bxb + k[14] * bxa * byb;
-    const double s11 = k[12] * bya * byb + k[14] * bxa * bxb + g;
-    const double s22 = kb[0] + g;
-    const double drill = sel3(a == b ? 0 : 1, kb[4] * 1e-4, 0.0, 0.0);       // shell.c:482-484 (k / 1e4)
     double W0[3], W1[3], W2[3], U0[3], U1[3], U2[3], w[3], v[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
@@ -1243,6 +1232,38 @@ __device__ __forceinline__ void s_contrib(const double *k /*registers*/, const d
             acc[(3 + q) * 6 + 3 + p] =
                 fma(R[6 + p], U2[q], fma(R[3 + p], U1[q], fma(R[p], U0[q], acc[(3 + q) * 6 + 3 + p])));
         }
+}
+__device__ __forceinline__ void s_contrib(const double *k /*registers*/, const double *kb, int a, int b, double *acc)
+{
+    // CST shape-function gradients (x 2A) of local joints a, b: (-Y3, X3 - X2), (Y3, -X3), (0, X2)
+    const double nY3 = -k[11], dX = k[10] - k[9], nX3 = -k[10];
+    const double bxa = sel3(a, nY3, k[11], 0.0), bya = sel3(a, dX, nX3, k[9]);
+    const double bxb = sel3(b, nY3, k[11], 0.0), byb = sel3(b, dX, nX3, k[9]);
+    const double g = bxa * (k[15] * bxb + k[17] * byb) + bya * (k[17] * bxb + k[16] * byb);
+    const double s00 = k[12] * bxa * bxb + k[14] * bya * byb + g;
+    const double s01 = k[13] * bxa * byb + k[14] * bya * bxb;
+    const double s10 = k[13] * bya * bxb + k[14] * bxa * byb;
+    const double s11 = k[12] * bya * byb + k[14] * bxa * bxb + g;
+    const double s22 = kb[0] + g;
+    const double drill = sel3(a == b ? 0 : 1, kb[4] * 1e-4, 0.0, 0.0);       // shell.c:482-484 (k / 1e4)
+    s_contrib_core(k, kb, s00, s01, s10, s11, s22, drill, acc);
+}
+// geometry classes: everything of the local block (a, b) that does not depend on the shell's state comes from the
+// class row (CB_KROW doubles, k_class_tables): [0..8] the DKT 3x3 block, [9] the drilling term, [10..13] the
+// material membrane block, [14..16] the gradient products that the membrane forces n0, n1, n2 (the only state
+// besides the triad) multiply in the geometric stiffness - no selects on (a, b), no gradients, 14 record doubles
+__device__ __forceinline__ void s_contrib_cls(const double *k /*registers: R[9] at 0, n at 15..17*/, const double *kb, double *acc)
+{
+    const double g = k[15] * kb[14] + k[16] * kb[15] + k[17] * kb[16];
+    s_contrib_core(k, kb, kb[10] + g, kb[11], kb[12], kb[13] + g, kb[0] + g, kb[9], acc);
+}
+// the 14 doubles s_contrib_cls reads of a shell record: 16-byte units 0-4 (triad; k[9] rides along) and 7, 8
+__device__ __forceinline__ void s_load_krec_cls(const double *kr /*shared*/, double *k)
+{
+    const double2 *k2 = reinterpret_cast<const double2 *>(kr);
+#pragma unroll
+    for (int i = 0; i < CB_SH_KREC / 2; ++i)
+        if (i < 5 || i > 6) { const double2 v = k2[i]; k[2 * i] = v.x; k[2 * i + 1] = v.y; }
 }
 
 // the block held in acc goes to (ADD: is added to) its place in the tile image
@@ -1306,6 +1327,14 @@ k_assemble_shell_stream(CbStiffArgs A)
     // next tile's first DKT block) go, the extra warps hide those latencies instead
     constexpr bool LEAN = WARPS > 8;
     constexpr bool PREK = CB_S_PREK && !LEAN;
+#ifndef CB_S_LEAN_KBPRE
+#define CB_S_LEAN_KBPRE 0         // lean variants: 1 = request the next step's DKT block a step ahead (20 registers; measured 1 % slower)
+#endif
+    constexpr bool KBPRE = !LEAN || CB_S_LEAN_KBPRE;
+#ifndef CB_S_CLSROW
+#define CB_S_CLSROW 1             // lean class variants: the state-independent part of a block comes from the class row
+#endif
+    constexpr bool CLSROW = LEAN && CLS && CB_S_CLSROW && !KBPRE;
     static_assert(NBUF == 2 || LEAN, "single record buffers go with the lean variant");
     static_assert(NBUF == 2 || SLOTS <= 32, "one element id per lane");
 
@@ -1396,7 +1425,12 @@ k_assemble_shell_stream(CbStiffArgs A)
         // 8-byte loads).  Idle lanes (slot 63: a = b = class 0) read valid memory and compute a block
         // that is never stored - the step has no divergent branch around its arithmetic.
         auto load_kb = [&](uint32_t r, int st, double *kb) {
-            if (CLS) {
+            if (CLSROW) {
+                const double *k0 = A.d.keb_row + ((r >> 20) * 9 + 3 * ((r >> 6) & 3) + ((r >> 8) & 3)) * CB_KROW;
+#pragma unroll
+                for (int i = 0; i < CB_KROW / 2; ++i)
+                    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(kb[2 * i]), "=d"(kb[2 * i + 1]) : "l"(k0 + 2 * i));
+            } else if (CLS) {
                 const double *k0 = A.d.keb_tab10 + ((r >> 20) * 9 + 3 * ((r >> 6) & 3) + ((r >> 8) & 3)) * 10;
 #pragma unroll
                 for (int i = 0; i < 5; ++i)
@@ -1413,7 +1447,7 @@ k_assemble_shell_stream(CbStiffArgs A)
         rs[0] = LEAN ? rec[0] : r0n;
 #pragma unroll
         for (int st = 1; st < S; ++st) rs[st] = rec[st * 32];
-        double kbA[10], kbB[10], krA[CB_SH_KREC], krB[CB_SH_KREC];
+        double kbA[CB_KROW], kbB[CB_KROW], krA[CB_SH_KREC], krB[CB_SH_KREC];
         if constexpr (LEAN) {
             load_kb(rs[0], 0, kbA);
         } else {
@@ -1438,7 +1472,7 @@ k_assemble_shell_stream(CbStiffArgs A)
                 if (st + 1 < S) {                           // the next step's inputs are on their way while
                     const uint32_t rn = rs[st + 1];         // this one is evaluated
                     if ((rn & 63u) != CB_S_IDLE) {
-                        load_kb(rn, st + 1, kbn);
+                        if (KBPRE) load_kb(rn, st + 1, kbn);
                         if (PREK) s_load_krec(kr0 + (rn & 63u) * CB_SH_KREC, krn);
                     }
                 }
@@ -1456,7 +1490,13 @@ k_assemble_shell_stream(CbStiffArgs A)
                         for (int i = 0; i < 36; ++i) acc[i] = 0.0;
                     }
                 }
-                if (!idle) {
+                if (!idle && CLSROW) {
+                    if (st > 0) load_kb(r, st, kb);
+                    s_load_krec_cls(kr0 + slot * CB_SH_KREC, kr);
+                    s_contrib_cls(kr, kb, acc);
+                }
+                if (!idle && !CLSROW) {
+                    if (!KBPRE && st > 0) load_kb(r, st, kb);
                     if (!PREK) s_load_krec(kr0 + slot * CB_SH_KREC, kr);
                     s_contrib(kr, kb, (r >> 6) & 3, (r >> 8) & 3, acc);
                 }

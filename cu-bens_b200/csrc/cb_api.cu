@@ -145,6 +145,9 @@ struct cb_handle {
     DevBuf<int32_t> sh_nodes;
     DevBuf<uint8_t> sh_own;       // first-element-at-joint bits (fused nodal update, CbDev::sh_own)
     bool fuse_node = false;       // shell-only, ANAFLAG 2, every touched joint has a shell: see CbForceArgs
+    // warp-level partial sums of the force pass (cb_wsum.cuh)
+    bool ws_tried = false, ws_ready = false; long ws_nslot = 0, ws_nwarp = 0;
+    DevBuf<int32_t> ws_start, js_start, js_slots; DevBuf<unsigned long long> ws_corners; DevBuf<double> ws_fg;
     DevBuf<double> sh_const, sh_keb, sh_kebc, sh_der, sh_Nm, sh_fg, sh_dens;
     long ncontrib = 0;
     DevBuf<double> sh_frame[3], sh_dsl[3], sh_ef[3];   // 0 = committed, 1/2 = iterate ping-pong
@@ -225,6 +228,10 @@ static CbDev make_dev(cb_handle *h)
     d.jc = h->jc.p;
     d.sh_nodes = h->sh_nodes.p; d.sh_const = h->sh_const.p; d.sh_keb = h->sh_keb.p; d.sh_own = h->sh_own.p;
     d.sh_Nm = h->sh_Nm.p; d.sh_fg = h->sh_fg.p; d.sh_der = h->sh_der.p;
+    if (h->ws_ready) {
+        d.ws_start = h->ws_start.p; d.ws_corners = h->ws_corners.p; d.ws_fg = h->ws_fg.p;
+        d.js_start = h->js_start.p; d.js_slots = h->js_slots.p; d.ws_nwarp = h->ws_nwarp;
+    }
     d.fr_nodes = h->fr_nodes.p; d.fr_const = h->fr_const.p; d.fr_offset = h->fr_offset.p;
     d.fr_osflag = h->fr_osflag.p; d.fr_mendrel = h->fr_mendrel.p; d.fr_simple = h->fr_simple;
     d.fr_efFE_ref = h->fr_efFE_ref.p; d.fr_fg = h->fr_fg.p;
@@ -651,6 +658,7 @@ extern "C" void cb_destroy(cb_handle *h)
         h->fr_ef[g].release();
     }
     h->sh_own.release(); h->cp_L.release();
+    h->ws_start.release(); h->js_start.release(); h->js_slots.release(); h->ws_corners.release(); h->ws_fg.release();
     for (DevBuf<int32_t> *b : {&h->fr_gid, &h->sh_gid, &h->jc, &h->sh_nodes, &h->tr_nodes, &h->fr_nodes, &h->fr_osflag,
                                &h->fr_mendrel, &h->br_nodes, &h->node_cstart})
         b->release();
@@ -686,6 +694,7 @@ extern "C" int cb_set_owned_joints(cb_handle *h, long j0, long j1)
 // ------------------------------------------------------------------------------------------
 static void host_pattern(cb_handle *h, int *Ap, int *Ai);
 #include "cb_plan_device.cuh"
+#include "cb_wsum.cuh"
 
 static int build_plan(cb_handle *h)
 {
@@ -1491,6 +1500,13 @@ extern "C" int cb_stiff(cb_handle *h, int gen)
 __device__ __forceinline__ void joint_force_sum(const CbDev &d, long n, const int32_t *cstart, const CbCorner *corners,
                                                 double *acc /*[7]*/)
 {
+    if (d.ws_fg) {                        // shell-only model with warp-level partial sums: the joint's slots
+        for (int c = d.js_start[n]; c < d.js_start[n + 1]; ++c) {
+            const double *p = d.ws_fg + (long)d.js_slots[c] * 6;
+            for (int r = 0; r < 6; ++r) acc[r] += p[r];
+        }
+        return;
+    }
     const int c0 = cstart[n], c1 = cstart[n + 1];
     const int fr_end = (d.ANAFLAG == 3 && d.fr_trip) ? d.fr_trip[0] : 0x7fffffff;
     const int sh_end = (d.ANAFLAG == 3 && d.sh_trip) ? d.sh_trip[0] : 0x7fffffff;
@@ -1705,6 +1721,7 @@ extern "C" int cb_update_forces_begin(cb_handle *h, const double *dd_dev, double
     if (first_fr) *first_fr = 0x7fffffff;
     if (first_sh) *first_sh = 0x7fffffff;
     if (h->fsi) return fail(CB_ERR_UNSUPPORTED, "the FSI analysis is linear and assembled once: no force pass (fsi.c)");
+    if (!h->ws_tried) { rc = build_wsum(h); if (rc) return rc; }
     if (h->fl.ANAFLAG == 1)
         return fail(CB_ERR_ARG, "ANAFLAG 1 recovers forces with cb_forces_linear (main.c:1774-1793)");
     cudaStream_t s = h->stream;

@@ -603,6 +603,7 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
                              "l"(ef_ip + (long)c * d.NE_SH + e));
         asm volatile("cp.async.commit_group;");
     }
+    double fg[18];            // element force in global axes: staged per corner, or summed per joint by the warp
     if (live) {
     double sc[CB_SH_CONST], Rp[CB_SH_FRAME], Ri[CB_SH_FRAME], dsl[3];
     sc[2] = __ldg(&SOA(d.sh_const, 2, e, d.NE_SH));               // thickness
@@ -723,7 +724,7 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
         for (int s2 = 0; s2 < 3; ++s2) M[r][s2] = dot3(Ri + 3 * r, Rp + 3 * s2);
 
     // ef_i = ef_temp + Ti_Tip (def + ef_ip) with the membrane slots of ef_ip zeroed (1773, 2342-2348)
-    double efi[18], fg[18];
+    double efi[18];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         double vt[3], vr[3];
@@ -752,18 +753,48 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
             sum += Ri[6 + c] * efi[3 * g + 2];
             fg[3 * g + c] = sum;
         }
+    if (!d.ws_fg) {
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
-        double2 *o = reinterpret_cast<double2 *>(CB_FG(d.sh_fg, b, e, d.NE_SH));
+        for (int b = 0; b < 3; ++b) {
+            double2 *o = reinterpret_cast<double2 *>(CB_FG(d.sh_fg, b, e, d.NE_SH));
 #pragma unroll
-        for (int i = 0; i < 3; ++i) o[i] = make_double2(fg[6 * b + 2 * i], fg[6 * b + 2 * i + 1]);
+            for (int i = 0; i < 3; ++i) o[i] = make_double2(fg[6 * b + 2 * i], fg[6 * b + 2 * i + 1]);
+        }
     }
 #pragma unroll
     for (int i = 0; i < CB_SH_FRAME; ++i) SOA(frame_i, i, e, d.NE_SH) = Ri[i];
 #pragma unroll
     for (int i = 0; i < 3; ++i) SOA(dsl_i, i, e, d.NE_SH) = dsl[i];
     }
-    __syncthreads();          // everyone is done with sbuf before it becomes the krec tile
+    __syncthreads();          // everyone is done with sbuf before it becomes the warps' tiles
+    if (d.ws_fg) {
+        // warp-level partial sums (cb_wsum.cuh): the 32 x 18 force components of the warp's shells meet in its
+        // tile, one lane per slot adds the (at most six) corners of its joint in element order and stages 48 bytes
+        double (*t)[CB_SH_KREC + 1] = tile[threadIdx.x >> 5];
+        const int lane = threadIdx.x & 31;
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < 18; ++i) t[lane][i] = fg[i];
+        }
+        __syncwarp();
+        const long w = (e - lane) >> 5;
+        if (w < d.ws_nwarp) {
+            const int s1 = d.ws_start[w + 1];
+            for (int sl = d.ws_start[w] + lane; sl < s1; sl += 32) {
+                const unsigned long long pk = d.ws_corners[sl];
+                const int cnt = (int)(pk & 7ull);
+                double a6[6] = {0, 0, 0, 0, 0, 0};
+                for (int k = 0; k < cnt; ++k) {
+                    const int idx = (int)((pk >> (3 + 7 * k)) & 127ull), l = idx / 3, a = idx - 3 * l;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) a6[j] += t[l][6 * a + j];
+                }
+                double2 *o = reinterpret_cast<double2 *>(d.ws_fg + (long)sl * 6);
+                o[0] = make_double2(a6[0], a6[1]); o[1] = make_double2(a6[2], a6[3]); o[2] = make_double2(a6[4], a6[5]);
+            }
+        }
+        __syncwarp();         // the tile becomes the krec tile
+    }
     warp_store_krec(d.sh_Nm, e - (threadIdx.x & 31), d.NE_SH, kr, tile[threadIdx.x >> 5]);
 }
 
@@ -1578,7 +1609,14 @@ k_gather_f_axpy(CbDev d, long jl0, long jl1, long jo0, long jo1, const int32_t *
     const int q[6] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y};
     double acc[6] = {0, 0, 0, 0, 0, 0};
     const bool own = n >= jo0 && n < jo1;
-    if (own) {
+    if (own && d.ws_fg) {                 // the joint's slots of warp-level partial sums, in warp order
+        const int c0 = d.js_start[n], c1 = d.js_start[n + 1];
+        for (int c = c0; c < c1; ++c) {
+            const double2 *p = reinterpret_cast<const double2 *>(d.ws_fg + (long)d.js_slots[c] * 6);
+            const double2 v0 = p[0], v1 = p[1], v2 = p[2];
+            acc[0] += v0.x; acc[1] += v0.y; acc[2] += v1.x; acc[3] += v1.y; acc[4] += v2.x; acc[5] += v2.y;
+        }
+    } else if (own) {
         const int c0 = cstart[n], c1 = cstart[n + 1];
         for (int c = c0; c < c1; ++c) {
             const CbCorner cr = corners[c];

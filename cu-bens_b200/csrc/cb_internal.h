@@ -221,6 +221,12 @@ struct CbDev {
                              // plane-stress C00,C01,C22, 21-23 t/(4 A0) * C
     double *sh_Nm;           // [NE][CB_SH_KREC] stiffness-pass record written by k_shell_prep
     double *sh_fg;           // [3][NE][6] element force in global axes (staging for the gather)
+    // warp-level partial sums of the shell force pass (cb_wsum.cuh; null: every corner is staged in sh_fg)
+    const int32_t *ws_start;              // [nwarp + 1] first slot of every warp of 32 consecutive shells
+    const unsigned long long *ws_corners; // [nslot] corners summed into the slot: count (3 bits), 7 bits each
+    double *ws_fg;                        // [nslot][6] the staged sums
+    const int32_t *js_start, *js_slots;   // [NJ + 1], [nslot] the slots of every joint, in warp order
+    long ws_nwarp;
     // geometry classes: shells whose geometry-constant inputs (E, nu, t, A0, local coordinates, side
     // lengths) are bit-identical share one copy of the DKT matrix and of sh_der - structured meshes
     // have a handful of classes, so the per-element 105 doubles never leave L1.  nullptr when the

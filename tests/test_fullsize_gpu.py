@@ -97,7 +97,9 @@ def test_fullsize_properties(gpu):
     p, Axp, fp = _state(m1, owned=owned)
     first_eq = int(jc[owned[0]][jc[owned[0]] > 0].min()) - 1
     assert np.array_equal(Axp, Ax[Ap[first_eq]:])
-    assert np.array_equal(fp[first_eq:], f[first_eq:])
+    # f_temp: the warps of the force pass pre-sum their corners per joint (cb_wsum.cuh) and a partition numbers its
+    # shells - hence groups them into warps - differently: the same sums in another association
+    assert np.abs(fp[first_eq:] - f[first_eq:]).max() <= 1e-13 * np.abs(f).max()
     p.close()
 
 

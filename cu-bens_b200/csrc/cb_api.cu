@@ -1535,8 +1535,9 @@ __device__ __forceinline__ void joint_force_sum(const CbDev &d, long n, const in
 // word whose sequence number matches carries its data - the LL protocol), polls its own mailbox until all
 // ranks' words of this call have landed and adds them in rank order (the same bits on every rank).  Calls are
 // collective and in lockstep, so two parities keep a fast rank's next call from overwriting words a slow one
-// still reads.  One launch, no NCCL kernel, ~2 NVLink latencies.  A poll that sees nothing for ~1 s sets
-// *err (a peer died) instead of hanging the GPU.
+// still reads.  One launch, no NCCL kernel, ~2 NVLink latencies.  Ranks may reach a call seconds apart (plan
+// building, host work): the poll waits; one that sees nothing for ~35 s sets *err (a peer died) instead of
+// hanging the GPU for good.
 struct CbXchg {
     uint2 *const *peers;      // [world] every rank's mailbox as mapped here (own entry: local pointer); null: off
     uint2 *mine;
@@ -1565,7 +1566,7 @@ __device__ __forceinline__ void cb_xchg_allreduce(const CbXchg &X, const double 
         for (;;) {
             asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(src) : "memory");
             if (f == X.seq) break;
-            if (clock64() - t0 > (1LL << 31)) { atomicExch(X.err, 1); break; }
+            if (clock64() - t0 > (1LL << 36)) { atomicExch(X.err, 1); break; }     // ~35 s: a rank is gone
         }
         got[r][i] = v;
     }
@@ -2198,7 +2199,7 @@ extern "C" int cb_get_sums(cb_handle *h, double *s3)
     if (h->p2p) {
         int32_t e = 0;
         CUDA_TRY(cudaMemcpy(&e, h->xerr.p, sizeof e, cudaMemcpyDeviceToHost));
-        if (e) return fail(CB_ERR_CUDA, "peer-memory all-reduce: a rank did not answer within ~1 s");
+        if (e) return fail(CB_ERR_CUDA, "peer-memory all-reduce: a rank did not answer within ~35 s");
     }
     return CB_OK;
 }

@@ -178,3 +178,35 @@ def test_symmetric_handoff_rebuilds_full_matrix(gpu, full_every, monkeypatch):
     U = sp.csc_matrix((Axu, Aiu, Apu), shape=(m.NEQ, m.NEQ))
     assert abs(sp.triu(K) - U).max() == 0.0 and U.nnz == sp.triu(K).nnz
     a.close()
+
+
+def test_warp_partial_sums_equal_the_corner_gather(gpu, ref, monkeypatch):
+    """cb_wsum.cuh: the warps of the force pass pre-sum their corners per joint before staging.  The same f_temp
+    and reaction resultants as the corner-by-corner gather (CB_NO_WARP_SUMS=1) up to the association of the
+    additions, both within 1e-12 of forces_sh; a union-jack plate puts eight corners of one joint into one warp
+    (more than a slot holds: the joint gets a second slot)"""
+    for kw in (dict(z_bump=0.02), dict(unionjack=True, z_bump=0.02), dict(jitter=0.2, z_bump=0.01)):
+        m = meshgen.plate_model(37, 23, **kw)
+        dd = meshgen.perturbation(m, scale=1e-3)
+        s = ref.RefState(m); s.begin_increment()
+        ref.update_forces(m, s, dd, itecnt=0)
+        out = []
+        for off in (False, True):
+            if off:
+                monkeypatch.setenv("CB_NO_WARP_SUMS", "1")
+            else:
+                monkeypatch.delenv("CB_NO_WARP_SUMS", raising=False)
+            a = cb.Assembler(m, layout=cb.CB_MAT_CSC)
+            a.begin_increment(); a.stiff()
+            f, *_ = a.update_forces(dd, itecnt=0)
+            a.set_q(m.q)
+            sums = a.residual_sums(0.8, fetch=True); reac = a.reaction_sums()
+            assert relerr(f, s.f_temp) < 1e-12
+            out.append((f, sums, reac, a.map_bytes))
+            a.close()
+        (f0, s0, r0, mb0), (f1, s1, r1, mb1) = out
+        assert mb0 > mb1, "the slot lists of the warp-level sums were not built"
+        assert np.abs(f0 - f1).max() <= 1e-14 * np.abs(f1).max()
+        assert np.allclose(s0, s1, rtol=1e-12, atol=0)
+        assert np.allclose(r0, r1, rtol=1e-11, atol=1e-12 * np.abs(f1).max())
+    monkeypatch.delenv("CB_NO_WARP_SUMS", raising=False)

@@ -553,14 +553,20 @@ __device__ __forceinline__ void shell_triad(const double *xj, const double *xk, 
 #ifndef CB_FORCES_CTAS_NOCLS
 #define CB_FORCES_CTAS_NOCLS 3
 #endif
+// threads per CTA of k_shell_forces: one warp.  The kernel's only block-wide barrier (before the warps' tiles
+// reuse the staging columns) then waits for nobody else: 128-thread CTAs measured 3.6 % slower (0.443 vs 0.427 ms)
+#ifndef CB_SHF_TPB
+#define CB_SHF_TPB 32
+#endif
+#define CB_SHF_SCALE (128 / CB_SHF_TPB)
 template <bool CLS, bool FUSE>
-__global__ void __launch_bounds__(CB_TPB, CLS ? CB_FORCES_CTAS : CB_FORCES_CTAS_NOCLS)
+__global__ void __launch_bounds__(CB_SHF_TPB, (CLS ? CB_FORCES_CTAS : CB_FORCES_CTAS_NOCLS) * CB_SHF_SCALE)
 k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restrict__ dd,
                const double *__restrict__ frame_ip, double *__restrict__ frame_i,
                double *__restrict__ dsl_i, const double *__restrict__ ef_ip,
                double *__restrict__ ef_i, double *__restrict__ x_new)
 {
-    // [99][CB_TPB]: the element's DKT matrix (81) and previous end forces (18), copied straight
+    // [99][CB_SHF_TPB]: the element's DKT matrix (81) and previous end forces (18), copied straight
     // from HBM by cp.async at kernel entry so their latency overlaps the geometry update; the
     // region is reused for the krec transposition at the end.
     extern __shared__ double sbuf[];
@@ -593,13 +599,13 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
         if (STAGE) {
 #pragma unroll
         for (int c = 0; c < 81; ++c)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + c * CB_TPB * 8),
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + c * CB_SHF_TPB * 8),
                          "l"(kebsrc + (long)c * kstr));
         }
 #pragma unroll
         for (int c = 0; c < 18; ++c)
             if (c % 6 >= 2)                     // the membrane slots of ef_ip are dropped (shell.c:1773)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + (KOFF + c) * CB_TPB * 8),
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + (KOFF + c) * CB_SHF_TPB * 8),
                              "l"(ef_ip + (long)c * d.NE_SH + e));
         asm volatile("cp.async.commit_group;");
     }
@@ -708,13 +714,13 @@ k_shell_forces(CbDev d, const double *__restrict__ x_temp, const double *__restr
         double sum = 0;
 #pragma unroll
         for (int j = 0; j < 9; ++j)
-            sum += (!STAGE ? __ldg(kebsrc + CB_KEB(i, j) * kstr) : mycol[CB_KEB(i, j) * CB_TPB]) * ddb[j];
+            sum += (!STAGE ? __ldg(kebsrc + CB_KEB(i, j) * kstr) : mycol[CB_KEB(i, j) * CB_SHF_TPB]) * ddb[j];
         defb[i] = sum;
     }
     }
     double efp[18];
 #pragma unroll
-    for (int i = 0; i < 18; ++i) efp[i] = (i % 6 >= 2) ? mycol[(KOFF + i) * CB_TPB] : 0.0;
+    for (int i = 0; i < 18; ++i) efp[i] = (i % 6 >= 2) ? mycol[(KOFF + i) * CB_SHF_TPB] : 0.0;
 
     // T_i * T_ip^T is block diagonal with M = R_i R_ip^T (shell.c:2326-2338)
     double M[3][3];
@@ -1698,11 +1704,11 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
         ++*launches;
     }
     if (d.NE_SH) {
-        unsigned g = (unsigned)((d.NE_SH + CB_TPB - 1) / CB_TPB);
+        unsigned g = (unsigned)((d.NE_SH + CB_SHF_TPB - 1) / CB_SHF_TPB);
         // staged columns per thread (ef_ip, + the DKT matrix when CB_FORCES_STAGE_KEB) or the krec
         // transposition tile, whichever is larger
         const size_t cols = (CB_FORCES_STAGE_KEB && !CB_FORCES_RECOMPUTE_KEB) ? 99 : 18;
-        const size_t smem = std::max(cols * CB_TPB, (size_t)(CB_TPB / 32) * 32 * (CB_SH_KREC + 1)) * sizeof(double);
+        const size_t smem = std::max(cols * CB_SHF_TPB, (size_t)(CB_SHF_TPB / 32) * 32 * (CB_SH_KREC + 1)) * sizeof(double);
         static CbPerDevice cfg{};
         int &configured = cfg.v[cb_device_slot()];
         if (!configured) {
@@ -1721,16 +1727,16 @@ int cbk_forces(const CbForceArgs &a, cudaStream_t s, long *launches)
                 a.sh_ef_ip, a.sh_ef_i);
         } else if (a.fuse_node) {       // x_temp: coordinates before the update, x_ip's buffer receives the new ones
             if (d.sh_class)
-                k_shell_forces<true, true><<<g, CB_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
+                k_shell_forces<true, true><<<g, CB_SHF_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
                                                                    a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i, a.x_ip);
             else
-                k_shell_forces<false, true><<<g, CB_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
+                k_shell_forces<false, true><<<g, CB_SHF_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
                                                                     a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i, a.x_ip);
         } else if (d.sh_class)
-            k_shell_forces<true, false><<<g, CB_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
+            k_shell_forces<true, false><<<g, CB_SHF_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
                                                                 a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i, nullptr);
         else
-            k_shell_forces<false, false><<<g, CB_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
+            k_shell_forces<false, false><<<g, CB_SHF_TPB, smem, s>>>(d, a.x_temp, a.dd, a.sh_frame_ip, a.sh_frame_i,
                                                                  a.sh_dsl_i, a.sh_ef_ip, a.sh_ef_i, nullptr);
         ++*launches;
     }

@@ -910,6 +910,33 @@ static int build_plan(cb_handle *h)
                 int j = i; while (j < tl.nc && kind(idx[j]) == kind(idx[i])) ++j;
                 groups.push_back({i, j - i}); i = j;
             }
+            // Blocks that are their pair's only contribution are written straight into the tile image at
+            // image[rel + i + j * colh] (CbTDst::direct): the sixteen lanes of a half-warp store the same (i, j) of
+            // their blocks at once, conflict-free iff their rel differ modulo 16 doubles.  In reference order the
+            // blocks of one kind step through rel = 7 (k + 49 column) with k in a set of three - residues repeat up
+            // to three times per half-warp (a 3-way bank conflict on every store).  Within a kind, deal the direct
+            // blocks out round-robin over the sixteen residues instead; staged blocks (conflict-free anyway) follow.
+            {
+                std::vector<int> bucket[17], order;
+                for (auto &g : groups) {
+                    for (auto &b : bucket) b.clear();
+                    for (int i = 0; i < g.second; ++i) {
+                        const int ci = idx[g.first + i];
+                        const CbTPair &tp = tpairs[tl.p0 + pmap[ci]];
+                        const bool direct = tp.cnt == 1 && tp.maskA == 0x7f && tp.maskB == 0x7f && tp.colh < 65536;
+                        bucket[direct ? (tp.rel & 15) : 16].push_back(ci);
+                    }
+                    order.clear();
+                    size_t pos[16] = {0};
+                    for (bool any = true; any;) {
+                        any = false;
+                        for (int r = 0; r < 16; ++r)
+                            if (pos[r] < bucket[r].size()) { order.push_back(bucket[r][pos[r]++]); any = true; }
+                    }
+                    for (int ci : bucket[16]) order.push_back(ci);
+                    for (int i = 0; i < g.second; ++i) idx[g.first + i] = order[i];
+                }
+            }
             // lanes lost if every group that straddles a boundary is moved to the next warp
             int need = 0;
             for (auto &g : groups) {

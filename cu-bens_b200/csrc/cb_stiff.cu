@@ -651,7 +651,8 @@ k_assemble_tiles(CbStiffArgs A)
         CbContrib ctn{}; ctn.type = 0xff;
         CbTDst tdn{};
         if (has_next && t < tln.ns) { ctn = A.tcontribs[tln.t0 + t]; if (FRAME_SIMPLE) tdn = A.tdst[tln.t0 + t]; }
-        __syncthreads();
+        // pairs with more than one contribution come first (the planner sorts a tile's pairs by count)
+        const int npd = __syncthreads_count(t < tl.np && spair[t].cnt > 1);
         if (!FRAME_SIMPLE && ND >= 6 && ctn.type == CB_T_SHELL && !A.mass_mode) shell_load(A, ctn, (long)tln.c0 + ctn.pad, in);
 
         // ---- phase 2: segmented reduction over the sorted contribution list, one thread per
@@ -659,9 +660,16 @@ k_assemble_tiles(CbStiffArgs A)
         // reference order, written as one contiguous column run of the tile's output image.  The
         // image is shifted by the parity of out0 so phase 3 can use aligned 16-byte accesses.
         const int shift = (int)((tl.out0 + A.out_par) & 1);
-        const int nitems = tl.np * ND;
+        // FRAME_SIMPLE: the pairs that are reduced (npd of them, the joints' own blocks in a lattice) are walked
+        // column-major - consecutive lanes take consecutive PAIRS of one column c, whose staged contributions sit
+        // three thread columns apart: sixteen distinct banks.  Pair-major (seven lanes per pair) put the lanes of
+        // neighbouring pairs on overlapping banks (a 2.5-way conflict on every load of the reduction).
+        const int nred = FRAME_SIMPLE ? npd : 0;
+        const int nitems = (tl.np - nred) * ND + nred * ND;
         for (int it = t; it < nitems; it += CB_TILE_T) {
-            const int p = it / ND, c = it - p * ND;
+            int p, c;
+            if (FRAME_SIMPLE && it < nred * ND) { c = it / nred; p = it - c * nred; }
+            else { p = it / ND; c = it - p * ND; }
             const CbTPair pr = spair[p];
             constexpr unsigned FULL = (1u << ND) - 1u;
             if (FRAME_SIMPLE && pr.cnt == 1 && pr.maskA == FULL && pr.maskB == FULL) continue;   // written in phase 1
